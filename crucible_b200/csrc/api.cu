@@ -1,0 +1,862 @@
+// api.cu — the C ABI of include/crucible_gpu.h: scene staging, the host BVH build that reproduces
+// BVHWrapper::new_wrapper (src/objects/bvhwrapper.rs:15-94) and flattens it to preorder records,
+// device upload, and the trace / render entry points.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "integrator.h"
+
+using namespace crb;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define API_CUDA(call)                                                                                     \
+    do {                                                                                                   \
+        cudaError_t e__ = (call);                                                                          \
+        if (e__ != cudaSuccess) return fail(CR_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
+    } while (0)
+
+const double INF = std::numeric_limits<double>::infinity();
+
+// ---- host geometry in reference arithmetic (this file is compiled with -ffp-contract=off) ---------
+struct Box {  // Aabb, src/objects/bvh.rs:19-34; default = EMPTY intervals
+    double lo[3] = {INF, INF, INF};
+    double hi[3] = {-INF, -INF, -INF};
+};
+// Aabb::new_from_boxes / Interval::tight_enclose, bvh.rs:69-75, utils.rs:631-635
+inline Box box_union(const Box& a, const Box& b) {
+    Box r;
+    for (int k = 0; k < 3; ++k) {
+        r.lo[k] = (a.lo[k] <= b.lo[k]) ? a.lo[k] : b.lo[k];
+        r.hi[k] = (a.hi[k] >= b.hi[k]) ? a.hi[k] : b.hi[k];
+    }
+    return r;
+}
+// Aabb::new_from_points, bvh.rs:46-66
+inline Box box_from_points(const double a[3], const double b[3]) {
+    Box r;
+    for (int k = 0; k < 3; ++k) {
+        if (a[k] <= b[k]) {
+            r.lo[k] = a[k];
+            r.hi[k] = b[k];
+        } else {
+            r.lo[k] = b[k];
+            r.hi[k] = a[k];
+        }
+    }
+    return r;
+}
+// Aabb::longest_axis, bvh.rs:82-94
+inline int longest_axis(const Box& b) {
+    const double sx = b.hi[0] - b.lo[0], sy = b.hi[1] - b.lo[1], sz = b.hi[2] - b.lo[2];
+    if (sx > sy) return (sx > sz) ? 0 : 2;
+    if (sy > sz) return 1;
+    return 2;
+}
+
+struct Element {  // one entry of Scene.elements (scene/mod.rs:77), insertion order
+    uint32_t kind, idx;
+    bool hide;
+    Box box;
+};
+
+struct HostImage {
+    int w, h;
+    std::vector<uint8_t> rgb;
+    cudaArray_t arr = nullptr;
+    cudaTextureObject_t tex = 0;
+};
+
+struct FlatNode {
+    Box box;
+    uint32_t left, right, axis;
+};
+
+}  // namespace
+
+struct CrScene {
+    int device = -1;  // -1 = host-only (no CUDA device): build/introspection work, compute fails
+    int num_sms = 148;
+    cudaStream_t stream = nullptr;
+    // staging
+    std::vector<Element> elements;
+    std::vector<double> spheres;  // [n][4]
+    std::vector<double> tris;     // [n][9] a,b,c
+    std::vector<double> quads;    // [n][9] Q,u,v
+    std::vector<int32_t> mat_of[3], obj_of[3], prim_of[3];
+    std::vector<CrMaterial> mats;
+    std::vector<CrTexture> texs;
+    std::vector<HostImage> images;
+    int sky_kind = CR_SKY_DEFAULT, sky_image = -1;
+    // built
+    bool committed = false;
+    std::vector<FlatNode> nodes;
+    uint32_t root = REF_MISS;
+    uint32_t max_depth = 0;
+    uint64_t n_visible = 0;
+    // device
+    SceneDeviceData dev;
+    std::vector<void*> dev_allocs;
+    Workspace ws;
+    void* d_out_rgb = nullptr;
+    void* d_out_rgb8 = nullptr;
+    size_t out_cap = 0;
+    void* d_io = nullptr;  // trace_batch staging
+    size_t io_cap = 0;
+
+    void free_device_scene() {
+        for (void* p : dev_allocs) cudaFree(p);
+        dev_allocs.clear();
+        for (auto& im : images) {
+            if (im.tex) cudaDestroyTextureObject(im.tex);
+            if (im.arr) cudaFreeArray(im.arr);
+            im.tex = 0;
+            im.arr = nullptr;
+        }
+        dev = SceneDeviceData();
+    }
+};
+
+namespace {
+
+// number of nodes BVHWrapper::help_generate creates for a span (bvhwrapper.rs:46-80)
+uint64_t node_count(uint64_t span) {
+    if (span <= 2) return 1;
+    return 1 + node_count(span / 2) + node_count(span - span / 2);
+}
+
+struct Builder {
+    CrScene& sc;
+    std::vector<uint32_t>& objs;  // indices into sc.elements (the cloned, re-sorted list)
+    std::vector<FlatNode>& nodes;
+    uint32_t max_depth = 0;
+
+    uint32_t leaf_ref(uint32_t e) const { return make_leaf(sc.elements[e].kind, sc.elements[e].idx); }
+
+    // Writes the subtree of objs[start,end) at nodes[at...] in preorder and returns its depth.
+    uint32_t build(size_t start, size_t end, uint32_t at, int par_depth) {
+        Box bbox;  // Aabb::default()
+        for (size_t i = start; i < end; ++i) bbox = box_union(bbox, sc.elements[objs[i]].box);
+        const int axis = longest_axis(bbox);
+        const size_t span = end - start;
+        FlatNode n;
+        n.box = bbox;
+        n.axis = (uint32_t)axis;
+        uint32_t depth = 1;
+        if (span == 1) {
+            n.left = leaf_ref(objs[start]);
+            n.right = REF_NONE;  // reference stores the same object twice; second test provably None
+        } else if (span == 2) {
+            n.left = leaf_ref(objs[start]);
+            n.right = leaf_ref(objs[start + 1]);
+        } else {
+            // stable sort by bbox.min on the axis (box_compare, bvhwrapper.rs:82-94; NaN -> Equal)
+            struct Key {
+                double k;
+                uint32_t e;
+            };
+            std::vector<Key> keys(span);
+            for (size_t i = 0; i < span; ++i) keys[i] = {sc.elements[objs[start + i]].box.lo[axis], objs[start + i]};
+            std::stable_sort(keys.begin(), keys.end(), [](const Key& a, const Key& b) { return a.k < b.k; });
+            for (size_t i = 0; i < span; ++i) objs[start + i] = keys[i].e;
+            keys.clear();
+            keys.shrink_to_fit();
+            const size_t mid = start + span / 2;
+            const uint32_t l_at = at + 1;
+            const uint32_t r_at = at + 1 + (uint32_t)node_count(mid - start);
+            n.left = l_at;
+            n.right = r_at;
+            uint32_t dl = 0, dr = 0;
+            if (par_depth > 0 && span > 65536) {
+                std::thread th([&] { dl = build(start, mid, l_at, par_depth - 1); });
+                dr = build(mid, end, r_at, par_depth - 1);
+                th.join();
+            } else {
+                dl = build(start, mid, l_at, 0);
+                dr = build(mid, end, r_at, 0);
+            }
+            depth = 1 + std::max(dl, dr);
+        }
+        nodes[at] = n;
+        return depth;
+    }
+};
+
+inline float f32_down(double x) {
+    float f = (float)x;
+    if ((double)f > x) f = std::nextafterf(f, -std::numeric_limits<float>::infinity());
+    return f;
+}
+inline float f32_up(double x) {
+    float f = (float)x;
+    if ((double)f < x) f = std::nextafterf(f, std::numeric_limits<float>::infinity());
+    return f;
+}
+
+template <typename T>
+int upload(CrScene* s, const std::vector<T>& host, void** out) {
+    *out = nullptr;
+    if (host.empty()) return CR_OK;
+    void* d = nullptr;
+    API_CUDA(cudaMalloc(&d, host.size() * sizeof(T)));
+    s->dev_allocs.push_back(d);
+    API_CUDA(cudaMemcpy(d, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *out = d;
+    return CR_OK;
+}
+
+int upload_scene(CrScene* s) {
+    API_CUDA(cudaSetDevice(s->device));
+    s->free_device_scene();
+    SceneDeviceData& d = s->dev;
+    d.num_sms = s->num_sms;
+    d.root = s->root;
+    d.sky_kind = s->sky_kind;
+    d.sky_image = s->sky_image;
+    d.clamp_colors = 1;
+    for (auto& m : s->mats)
+        if (m.kind == CR_MAT_EMISSIVE) d.clamp_colors = 0;
+    // nodes
+    {
+        std::vector<NodeRec<double>> n64(s->nodes.size());
+        std::vector<NodeRec<float>> n32(s->nodes.size());
+        for (size_t i = 0; i < s->nodes.size(); ++i) {
+            const FlatNode& n = s->nodes[i];
+            NodeRec<double>& a = n64[i];
+            a.xmin = n.box.lo[0]; a.xmax = n.box.hi[0];
+            a.ymin = n.box.lo[1]; a.ymax = n.box.hi[1];
+            a.zmin = n.box.lo[2]; a.zmax = n.box.hi[2];
+            a.left = n.left | (n.axis << AXIS_SHIFT);
+            a.right = n.right;
+            a.pad0 = a.pad1 = 0;
+            NodeRec<float>& b = n32[i];
+            b.xmin = f32_down(n.box.lo[0]); b.xmax = f32_up(n.box.hi[0]);
+            b.ymin = f32_down(n.box.lo[1]); b.ymax = f32_up(n.box.hi[1]);
+            b.zmin = f32_down(n.box.lo[2]); b.zmax = f32_up(n.box.hi[2]);
+            b.left = a.left;
+            b.right = a.right;
+        }
+        int rc;
+        if ((rc = upload(s, n64, &d.nodes[0])) != CR_OK) return rc;
+        if ((rc = upload(s, n32, &d.nodes[1])) != CR_OK) return rc;
+    }
+    // spheres
+    {
+        const size_t n = s->spheres.size() / 4;
+        std::vector<SphereRec<double>> a(n);
+        std::vector<SphereRec<float>> b(n);
+        for (size_t i = 0; i < n; ++i) {
+            const double* p = &s->spheres[4 * i];
+            a[i] = {p[0], p[1], p[2], p[3]};
+            b[i] = {(float)p[0], (float)p[1], (float)p[2], (float)p[3]};
+        }
+        int rc;
+        if ((rc = upload(s, a, &d.spheres[0])) != CR_OK) return rc;
+        if ((rc = upload(s, b, &d.spheres[1])) != CR_OK) return rc;
+    }
+    // triangles: a, e1 = b - a, e2 = c - a (triangle.rs:99-100; x - y == x + (-y) bit for bit)
+    {
+        const size_t n = s->tris.size() / 9;
+        std::vector<TriRec<double>> a(n);
+        std::vector<TriRec<float>> b(n);
+        for (size_t i = 0; i < n; ++i) {
+            const double* p = &s->tris[9 * i];
+            TriRec<double>& t = a[i];
+            t.ax = p[0]; t.ay = p[1]; t.az = p[2];
+            t.e1x = p[3] - p[0]; t.e1y = p[4] - p[1]; t.e1z = p[5] - p[2];
+            t.e2x = p[6] - p[0]; t.e2y = p[7] - p[1]; t.e2z = p[8] - p[2];
+            t.pad = 0.0;
+            TriRec<float>& u = b[i];
+            u.ax = (float)t.ax; u.ay = (float)t.ay; u.az = (float)t.az;
+            u.e1x = (float)t.e1x; u.e1y = (float)t.e1y; u.e1z = (float)t.e1z;
+            u.e2x = (float)t.e2x; u.e2y = (float)t.e2y; u.e2z = (float)t.e2z;
+            u.pad0 = u.pad1 = u.pad2 = 0.f;
+        }
+        int rc;
+        if ((rc = upload(s, a, &d.tris[0])) != CR_OK) return rc;
+        if ((rc = upload(s, b, &d.tris[1])) != CR_OK) return rc;
+    }
+    // quads (EXTENSION): normal = unit(u x v), D = normal . Q, w = n / (n . n)
+    {
+        const size_t n = s->quads.size() / 9;
+        std::vector<QuadRec<double>> a(n);
+        std::vector<QuadRec<float>> b(n);
+        for (size_t i = 0; i < n; ++i) {
+            const double* p = &s->quads[9 * i];
+            const double ux = p[3], uy = p[4], uz = p[5], vx = p[6], vy = p[7], vz = p[8];
+            const double nx = uy * vz - uz * vy, ny = uz * vx - ux * vz, nz = ux * vy - uy * vx;
+            const double l2 = nx * nx + ny * ny + nz * nz;
+            const double il = 1.0 / std::sqrt(l2);
+            const double ux_ = il * nx, uy_ = il * ny, uz_ = il * nz;  // unit_vector: (1/len) * n
+            const double dd = ux_ * p[0] + uy_ * p[1] + uz_ * p[2];
+            const double nn = nx * nx + ny * ny + nz * nz;  // dot(n, n)
+            const double inn = 1.0 / nn;
+            QuadRec<double>& q = a[i];
+            q.qx = p[0]; q.qy = p[1]; q.qz = p[2];
+            q.ux = ux; q.uy = uy; q.uz = uz;
+            q.vx = vx; q.vy = vy; q.vz = vz;
+            q.nx = ux_; q.ny = uy_; q.nz = uz_;
+            q.wx = inn * nx; q.wy = inn * ny; q.wz = inn * nz;
+            q.d = dd;
+            QuadRec<float>& f = b[i];
+            f.qx = (float)q.qx; f.qy = (float)q.qy; f.qz = (float)q.qz;
+            f.ux = (float)q.ux; f.uy = (float)q.uy; f.uz = (float)q.uz;
+            f.vx = (float)q.vx; f.vy = (float)q.vy; f.vz = (float)q.vz;
+            f.nx = (float)q.nx; f.ny = (float)q.ny; f.nz = (float)q.nz;
+            f.wx = (float)q.wx; f.wy = (float)q.wy; f.wz = (float)q.wz;
+            f.d = (float)q.d;
+        }
+        int rc;
+        if ((rc = upload(s, a, &d.quads[0])) != CR_OK) return rc;
+        if ((rc = upload(s, b, &d.quads[1])) != CR_OK) return rc;
+    }
+    // per-primitive metadata
+    for (int k = 0; k < 3; ++k) {
+        std::vector<PrimMeta> m(s->mat_of[k].size());
+        for (size_t i = 0; i < m.size(); ++i) {
+            m[i].material = s->mat_of[k][i];
+            m[i].prim_index = s->prim_of[k][i];
+            m[i].obj_id = s->obj_of[k][i];
+            m[i].mat_kind = s->mats[(size_t)m[i].material].kind;
+        }
+        void* p = nullptr;
+        int rc = upload(s, m, &p);
+        if (rc != CR_OK) return rc;
+        d.meta[k] = static_cast<PrimMeta*>(p);
+    }
+    // materials, textures
+    {
+        std::vector<DevMaterial> m(s->mats.size());
+        for (size_t i = 0; i < m.size(); ++i) {
+            const CrMaterial& c = s->mats[i];
+            m[i].kind = c.kind;
+            m[i].tex = c.tex;
+            m[i].scatter_prob = c.scatter_prob;
+            m[i].fuzz = c.fuzz;
+            m[i].ior = c.ior;
+            for (int k = 0; k < 3; ++k) {
+                m[i].albedo[k] = c.albedo[k];
+                m[i].emit[k] = c.emit[k];
+            }
+        }
+        void* p = nullptr;
+        int rc = upload(s, m, &p);
+        if (rc != CR_OK) return rc;
+        d.mats = static_cast<DevMaterial*>(p);
+        std::vector<DevTexture> t(s->texs.size());
+        for (size_t i = 0; i < t.size(); ++i) {
+            const CrTexture& c = s->texs[i];
+            t[i].kind = c.kind;
+            t[i].even = c.even;
+            t[i].odd = c.odd;
+            t[i].image = c.image;
+            t[i].inv_scale = c.inv_scale;
+            for (int k = 0; k < 3; ++k) t[i].color[k] = c.color[k];
+        }
+        rc = upload(s, t, &p);
+        if (rc != CR_OK) return rc;
+        d.texs = static_cast<DevTexture*>(p);
+    }
+    // images -> uchar4 CUDA arrays + point-sampled texture objects
+    {
+        std::vector<DevImage> di(s->images.size());
+        for (size_t i = 0; i < di.size(); ++i) {
+            HostImage& im = s->images[i];
+            std::vector<uchar4> px((size_t)im.w * im.h);
+            for (size_t k = 0; k < px.size(); ++k) px[k] = make_uchar4(im.rgb[3 * k], im.rgb[3 * k + 1], im.rgb[3 * k + 2], 255);
+            cudaChannelFormatDesc fmt = cudaCreateChannelDesc<uchar4>();
+            API_CUDA(cudaMallocArray(&im.arr, &fmt, (size_t)im.w, (size_t)im.h));
+            API_CUDA(cudaMemcpy2DToArray(im.arr, 0, 0, px.data(), (size_t)im.w * sizeof(uchar4), (size_t)im.w * sizeof(uchar4),
+                                         (size_t)im.h, cudaMemcpyHostToDevice));
+            cudaResourceDesc res;
+            memset(&res, 0, sizeof(res));
+            res.resType = cudaResourceTypeArray;
+            res.res.array.array = im.arr;
+            cudaTextureDesc td;
+            memset(&td, 0, sizeof(td));
+            td.addressMode[0] = cudaAddressModeClamp;
+            td.addressMode[1] = cudaAddressModeClamp;
+            td.filterMode = cudaFilterModePoint;
+            td.readMode = cudaReadModeElementType;
+            td.normalizedCoords = 0;
+            API_CUDA(cudaCreateTextureObject(&im.tex, &res, &td, nullptr));
+            di[i].tex = im.tex;
+            di[i].w = im.w;
+            di[i].h = im.h;
+        }
+        void* p = nullptr;
+        int rc = upload(s, di, &p);
+        if (rc != CR_OK) return rc;
+        d.images = static_cast<DevImage*>(p);
+    }
+    return CR_OK;
+}
+
+int validate(CrScene* s) {
+    const int nm = (int)s->mats.size(), nt = (int)s->texs.size(), ni = (int)s->images.size();
+    for (int k = 0; k < 3; ++k)
+        for (int32_t m : s->mat_of[k])
+            if (m < 0 || m >= nm) return fail(CR_ERR_INVALID, "primitive references material " + std::to_string(m) + " of " + std::to_string(nm));
+    for (auto& m : s->mats) {
+        if (m.kind < CR_MAT_LAMBERTIAN || m.kind > CR_MAT_EMISSIVE) return fail(CR_ERR_INVALID, "bad material kind");
+        if (m.kind == CR_MAT_LAMBERTIAN) {
+            if (m.tex < 0 || m.tex >= nt) return fail(CR_ERR_INVALID, "lambertian references a missing texture");
+            if (!(m.scatter_prob > 0.0)) return fail(CR_ERR_INVALID, "lambertian scatter_prob must be > 0");
+        }
+        // Metal::new asserts fuzz in [0,1] (metal.rs:21-25); Color::new asserts [0,1] (utils.rs:345-351)
+        if (m.kind == CR_MAT_METAL) {
+            if (!(m.fuzz >= 0.0 && m.fuzz <= 1.0)) return fail(CR_ERR_INVALID, "A metal cannot have a fuzz factor outside [0,1]");
+            for (int k = 0; k < 3; ++k)
+                if (!(m.albedo[k] >= 0.0 && m.albedo[k] <= 1.0)) return fail(CR_ERR_INVALID, "metal albedo must be in [0,1]");
+        }
+    }
+    for (auto& t : s->texs) {
+        if (t.kind == CR_TEX_SOLID) {
+            for (int k = 0; k < 3; ++k)
+                if (!(t.color[k] >= 0.0 && t.color[k] <= 1.0)) return fail(CR_ERR_INVALID, "solid colour must be in [0,1]");
+        } else if (t.kind == CR_TEX_CHECKER) {
+            if (t.even < 0 || t.even >= nt || t.odd < 0 || t.odd >= nt) return fail(CR_ERR_INVALID, "checker references a missing texture");
+        } else if (t.kind == CR_TEX_IMAGE) {
+            if (t.image < 0 || t.image >= ni) return fail(CR_ERR_INVALID, "image texture references a missing image");
+        } else {
+            return fail(CR_ERR_INVALID, "bad texture kind");
+        }
+    }
+    // checker nesting must terminate within MAX_TEX_NEST
+    for (int i = 0; i < nt; ++i) {
+        std::vector<int> frontier = {i};
+        for (int depth = 0; depth <= MAX_TEX_NEST && !frontier.empty(); ++depth) {
+            std::vector<int> next;
+            for (int t : frontier)
+                if (s->texs[(size_t)t].kind == CR_TEX_CHECKER) {
+                    next.push_back(s->texs[(size_t)t].even);
+                    next.push_back(s->texs[(size_t)t].odd);
+                }
+            if (depth == MAX_TEX_NEST - 1 && !next.empty()) return fail(CR_ERR_LIMIT, "checker textures nested deeper than 8");
+            frontier.swap(next);
+        }
+    }
+    if (s->sky_kind == CR_SKY_SPHERICAL && (s->sky_image < 0 || s->sky_image >= ni))
+        return fail(CR_ERR_INVALID, "spherical sky references a missing image");
+    return CR_OK;
+}
+
+int need_device(CrScene* s) {
+    if (!s) return fail(CR_ERR_INVALID, "null scene");
+    if (s->device < 0) return fail(CR_ERR_NO_DEVICE, "no CUDA sm_100 device: crucible_b200 has no CPU fallback");
+    if (!s->committed) return fail(CR_ERR_STATE, "scene not committed (call cr_scene_commit)");
+    return CR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* cr_last_error(void) { return g_err.c_str(); }
+const char* cr_version(void) { return "crucible_b200 0.1 (sm_100a)"; }
+
+int cr_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    int ok = 0;
+    for (int i = 0; i < n; ++i) {
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major == 10) ++ok;
+    }
+    return ok;
+}
+
+CrScene* cr_scene_create(int device) {
+    CrScene* s = new CrScene();
+    if (device >= 0) {
+        int n = 0;
+        if (cudaGetDeviceCount(&n) != cudaSuccess || device >= n) {
+            cudaGetLastError();
+            g_err = "cr_scene_create: CUDA device " + std::to_string(device) + " not available";
+            delete s;
+            return nullptr;
+        }
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, device) != cudaSuccess || p.major != 10) {
+            g_err = "cr_scene_create: device is not sm_100 (this library ships sm_100a code only)";
+            delete s;
+            return nullptr;
+        }
+        s->device = device;
+        s->num_sms = p.multiProcessorCount;
+        cudaSetDevice(device);
+        if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) {
+            g_err = "cr_scene_create: cudaStreamCreate failed";
+            delete s;
+            return nullptr;
+        }
+    }
+    return s;
+}
+
+void cr_scene_destroy(CrScene* s) {
+    if (!s) return;
+    if (s->device >= 0) {
+        cudaSetDevice(s->device);
+        s->free_device_scene();
+        s->ws.release();
+        if (s->d_out_rgb) cudaFree(s->d_out_rgb);
+        if (s->d_out_rgb8) cudaFree(s->d_out_rgb8);
+        if (s->d_io) cudaFree(s->d_io);
+        if (s->stream) cudaStreamDestroy(s->stream);
+    }
+    delete s;
+}
+
+static int64_t add_prims(CrScene* s, uint32_t kind, const double* data, size_t stride, const int32_t* material,
+                         const int32_t* obj_id, size_t n) {
+    if (!s || (!data && n)) return fail(CR_ERR_INVALID, "null argument");
+    const int64_t first = (int64_t)s->elements.size();
+    if (s->elements.size() + n > REF_MAX_INDEX) return fail(CR_ERR_LIMIT, "too many primitives");
+    std::vector<double>& store = kind == CR_PRIM_SPHERE ? s->spheres : (kind == CR_PRIM_TRIANGLE ? s->tris : s->quads);
+    for (size_t i = 0; i < n; ++i) {
+        const double* p = data + stride * i;
+        Element e;
+        e.kind = kind;
+        e.idx = (uint32_t)(store.size() / stride);
+        e.hide = false;
+        if (kind == CR_PRIM_SPHERE) {
+            if (!(p[3] >= 0.0)) return fail(CR_ERR_INVALID, "Cannot make a sphere with negative radius");  // sphere.rs:26
+            // sphere.rs:29-30: new_from_points(center - rvec, center + rvec); a - b == a + (-b)
+            const double lo[3] = {p[0] - p[3], p[1] - p[3], p[2] - p[3]};
+            const double hi[3] = {p[0] + p[3], p[1] + p[3], p[2] + p[3]};
+            e.box = box_from_points(lo, hi);
+        } else if (kind == CR_PRIM_TRIANGLE) {
+            // triangle.rs:48-62: a.min(b.min(c)) / a.max(b.max(c)) per axis (f64::min/max ignore NaN)
+            for (int k = 0; k < 3; ++k) {
+                e.box.lo[k] = std::fmin(p[k], std::fmin(p[3 + k], p[6 + k]));
+                e.box.hi[k] = std::fmax(p[k], std::fmax(p[3 + k], p[6 + k]));
+            }
+        } else {
+            // EXTENSION quad: box of both diagonals, sides thinner than 1e-4 padded (Interval::pad, utils.rs:624-627)
+            double quv[3], qu[3], qv[3];
+            for (int k = 0; k < 3; ++k) {
+                qu[k] = p[k] + p[3 + k];
+                qv[k] = p[k] + p[6 + k];
+                quv[k] = qu[k] + p[6 + k];
+            }
+            Box b = box_union(box_from_points(p, quv), box_from_points(qu, qv));
+            const double delta = 0.0001;
+            for (int k = 0; k < 3; ++k)
+                if (b.hi[k] - b.lo[k] < delta) {
+                    const double pad = delta / 2.0;
+                    b.lo[k] = b.lo[k] - pad;
+                    b.hi[k] = b.hi[k] + pad;
+                }
+            e.box = b;
+        }
+        store.insert(store.end(), p, p + stride);
+        s->mat_of[kind].push_back(material ? material[i] : 0);
+        s->obj_of[kind].push_back(obj_id ? obj_id[i] : (int32_t)s->elements.size());
+        s->prim_of[kind].push_back((int32_t)s->elements.size());
+        s->elements.push_back(e);
+    }
+    s->committed = false;
+    return first;
+}
+
+int64_t cr_scene_add_spheres(CrScene* s, const double* d, const int32_t* m, const int32_t* o, size_t n) {
+    return add_prims(s, CR_PRIM_SPHERE, d, 4, m, o, n);
+}
+int64_t cr_scene_add_triangles(CrScene* s, const double* d, const int32_t* m, const int32_t* o, size_t n) {
+    return add_prims(s, CR_PRIM_TRIANGLE, d, 9, m, o, n);
+}
+int64_t cr_scene_add_quads(CrScene* s, const double* d, const int32_t* m, const int32_t* o, size_t n) {
+    return add_prims(s, CR_PRIM_QUAD, d, 9, m, o, n);
+}
+
+int cr_scene_set_hidden(CrScene* s, size_t prim_index, int hide) {
+    if (!s || prim_index >= s->elements.size()) return fail(CR_ERR_INVALID, "prim_index out of range");
+    s->elements[prim_index].hide = hide != 0;
+    s->committed = false;
+    return CR_OK;
+}
+int cr_scene_set_materials(CrScene* s, const CrMaterial* m, size_t n) {
+    if (!s || (!m && n)) return fail(CR_ERR_INVALID, "null argument");
+    s->mats.assign(m, m + n);
+    s->committed = false;
+    return CR_OK;
+}
+int cr_scene_set_textures(CrScene* s, const CrTexture* t, size_t n) {
+    if (!s || (!t && n)) return fail(CR_ERR_INVALID, "null argument");
+    s->texs.assign(t, t + n);
+    s->committed = false;
+    return CR_OK;
+}
+int cr_scene_add_image(CrScene* s, const uint8_t* rgb8, int w, int h) {
+    if (!s || !rgb8 || w <= 0 || h <= 0) return fail(CR_ERR_INVALID, "bad image");
+    HostImage im;
+    im.w = w;
+    im.h = h;
+    im.rgb.assign(rgb8, rgb8 + (size_t)w * h * 3);
+    s->images.push_back(std::move(im));
+    s->committed = false;
+    return (int)s->images.size() - 1;
+}
+int cr_scene_set_sky(CrScene* s, int kind, int image) {
+    if (!s || kind < CR_SKY_DEFAULT || kind > CR_SKY_BLACK) return fail(CR_ERR_INVALID, "bad sky kind");
+    s->sky_kind = kind;
+    s->sky_image = image;
+    s->committed = false;
+    return CR_OK;
+}
+
+int cr_scene_commit(CrScene* s) {
+    if (!s) return fail(CR_ERR_INVALID, "null scene");
+    int rc = validate(s);
+    if (rc != CR_OK) return rc;
+    // BVHWrapper::new_wrapper: drop hidden primitives, empty -> empty HitList (bvhwrapper.rs:16-31)
+    std::vector<uint32_t> visible;
+    visible.reserve(s->elements.size());
+    for (uint32_t i = 0; i < (uint32_t)s->elements.size(); ++i)
+        if (!s->elements[i].hide) visible.push_back(i);
+    s->n_visible = visible.size();
+    s->nodes.clear();
+    s->root = REF_MISS;
+    s->max_depth = 0;
+    if (!visible.empty()) {
+        const uint64_t nn = node_count(visible.size());
+        if (nn > REF_MAX_INDEX) return fail(CR_ERR_LIMIT, "BVH too large");
+        s->nodes.resize((size_t)nn);
+        Builder b{*s, visible, s->nodes};
+        s->max_depth = b.build(0, visible.size(), 0, 4);
+        if ((int)s->max_depth + 2 > MAX_STACK) return fail(CR_ERR_LIMIT, "BVH deeper than the traversal stack");
+        // new_from_vec (bvhwrapper.rs:34-44): the root box is re-derived from its two children
+        FlatNode& r = s->nodes[0];
+        auto child_box = [&](uint32_t ref) -> Box {
+            if (ref_is_leaf(ref)) return s->elements[(size_t)s->prim_of[ref_kind(ref)][ref_index(ref)]].box;
+            return s->nodes[ref].box;
+        };
+        const Box lb = child_box(r.left);
+        const Box rb = (r.right == REF_NONE) ? lb : child_box(r.right);
+        r.box = box_union(lb, rb);
+        s->root = 0;
+    }
+    s->committed = true;
+    if (s->device >= 0) {
+        rc = upload_scene(s);
+        if (rc != CR_OK) {
+            s->committed = false;
+            return rc;
+        }
+    }
+    return CR_OK;
+}
+
+int cr_scene_bvh_info(const CrScene* s, uint64_t* n_nodes, uint32_t* max_depth, uint64_t* n_visible) {
+    if (!s || !s->committed) return fail(CR_ERR_STATE, "scene not committed");
+    if (n_nodes) *n_nodes = s->nodes.size();
+    if (max_depth) *max_depth = s->max_depth;
+    if (n_visible) *n_visible = s->n_visible;
+    return CR_OK;
+}
+
+int64_t cr_scene_bvh_leaf_order(const CrScene* s, int32_t* out, size_t cap) {
+    if (!s || !s->committed) return fail(CR_ERR_STATE, "scene not committed");
+    // preorder array + "left before right" == DFS leaf order; span-1 nodes list their primitive twice
+    // in the reference (left == right), which this enumeration reproduces for comparison with the oracle
+    std::vector<int32_t> order;
+    std::vector<uint32_t> stack;
+    if (s->root != REF_MISS) stack.push_back(s->root);
+    auto prim_index_of = [&](uint32_t ref) { return s->prim_of[ref_kind(ref)][ref_index(ref)]; };
+    while (!stack.empty()) {
+        const uint32_t ref = stack.back();
+        stack.pop_back();
+        if (ref_is_leaf(ref)) {
+            order.push_back(prim_index_of(ref));
+            continue;
+        }
+        const FlatNode& n = s->nodes[ref];
+        if (n.right == REF_NONE) {
+            order.push_back(prim_index_of(n.left));
+            order.push_back(prim_index_of(n.left));
+        } else {
+            stack.push_back(n.right);
+            stack.push_back(n.left);
+        }
+    }
+    const size_t n = std::min(cap, order.size());
+    if (out && n) memcpy(out, order.data(), n * sizeof(int32_t));
+    return (int64_t)order.size();
+}
+
+int cr_trace_batch(CrScene* s, const double* rays, size_t n, double tmin, double tmax, int precision, CrHit* out) {
+    int rc = need_device(s);
+    if (rc != CR_OK) return rc;
+    if ((!rays || !out) && n) return fail(CR_ERR_INVALID, "null argument");
+    if (precision != CR_PRECISION_F64 && precision != CR_PRECISION_F32) return fail(CR_ERR_INVALID, "bad precision");
+    if (n == 0) return CR_OK;
+    API_CUDA(cudaSetDevice(s->device));
+    const size_t bytes_in = n * 7 * sizeof(double), bytes_out = n * sizeof(CrHit);
+    const size_t need = ((bytes_in + 255) & ~(size_t)255) + bytes_out;
+    if (need > s->io_cap) {
+        if (s->d_io) cudaFree(s->d_io);
+        s->d_io = nullptr;
+        s->io_cap = 0;
+        API_CUDA(cudaMalloc(&s->d_io, need));
+        s->io_cap = need;
+    }
+    double* d_rays = static_cast<double*>(s->d_io);
+    CrHit* d_out = reinterpret_cast<CrHit*>(static_cast<char*>(s->d_io) + ((bytes_in + 255) & ~(size_t)255));
+    API_CUDA(cudaMemcpyAsync(d_rays, rays, bytes_in, cudaMemcpyHostToDevice, s->stream));
+    std::string err;
+    rc = (precision == CR_PRECISION_F64) ? trace_batch_impl<double>(s->dev, d_rays, n, tmin, tmax, d_out, s->stream, err)
+                                         : trace_batch_impl<float>(s->dev, d_rays, n, tmin, tmax, d_out, s->stream, err);
+    if (rc != CR_OK) return fail(rc, err);
+    API_CUDA(cudaMemcpyAsync(out, d_out, bytes_out, cudaMemcpyDeviceToHost, s->stream));
+    API_CUDA(cudaStreamSynchronize(s->stream));
+    return CR_OK;
+}
+
+static int check_camera(const CrCamera* c) {
+    if (!c) return fail(CR_ERR_INVALID, "null camera");
+    if (c->image_width == 0 || c->image_height == 0) return fail(CR_ERR_INVALID, "empty image");
+    // Camera::set_samples asserts s > 0 (camera/mod.rs:233-240)
+    if (c->samples == 0) return fail(CR_ERR_INVALID, "The camera must have a positive number of samples. 0 is invalid.");
+    if (c->n_from_keys > CR_MAX_CAM_KEYS || c->n_at_keys > CR_MAX_CAM_KEYS) return fail(CR_ERR_LIMIT, "too many camera keyframes");
+    if (!(c->frame_rate > 0.0)) return fail(CR_ERR_INVALID, "frame_rate must be positive");
+    if ((uint64_t)c->image_width * c->image_height > 0xFFFFFFFFull) return fail(CR_ERR_LIMIT, "image too large");
+    return CR_OK;
+}
+
+int cr_render_device(CrScene* s, const CrCamera* cam, const CrRenderOpts* opts, void* d_out_rgb, void* d_out_rgb8,
+                     void* cuda_stream, CrStats* stats) {
+    int rc = need_device(s);
+    if (rc != CR_OK) return rc;
+    if ((rc = check_camera(cam)) != CR_OK) return rc;
+    if (!opts) return fail(CR_ERR_INVALID, "null opts");
+    if (opts->row_world > 1 && opts->row_rank >= opts->row_world) return fail(CR_ERR_INVALID, "row_rank >= row_world");
+    API_CUDA(cudaSetDevice(s->device));
+    if (stats) memset(stats, 0, sizeof(*stats));
+    cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : s->stream;
+    std::string err;
+    // device variant: rows of this rank are written PACKED ([rows_local][W][3]) so the result is the
+    // NCCL gather send buffer as is
+    rc = (opts->precision == CR_PRECISION_F32)
+             ? render_impl<float>(s->dev, s->ws, *cam, *opts, d_out_rgb, d_out_rgb8, 1, st, stats, err)
+             : render_impl<double>(s->dev, s->ws, *cam, *opts, d_out_rgb, d_out_rgb8, 1, st, stats, err);
+    if (rc != CR_OK) return fail(rc, err);
+    return CR_OK;
+}
+
+int cr_render(CrScene* s, const CrCamera* cam, const CrRenderOpts* opts, double* out_rgb, uint8_t* out_rgb8, CrStats* stats) {
+    int rc = need_device(s);
+    if (rc != CR_OK) return rc;
+    if ((rc = check_camera(cam)) != CR_OK) return rc;
+    if (!opts) return fail(CR_ERR_INVALID, "null opts");
+    if (opts->row_world > 1 && opts->row_rank >= opts->row_world) return fail(CR_ERR_INVALID, "row_rank >= row_world");
+    API_CUDA(cudaSetDevice(s->device));
+    if (stats) memset(stats, 0, sizeof(*stats));
+    const size_t npix = (size_t)cam->image_width * cam->image_height;
+    if (npix > s->out_cap) {
+        if (s->d_out_rgb) cudaFree(s->d_out_rgb);
+        if (s->d_out_rgb8) cudaFree(s->d_out_rgb8);
+        s->d_out_rgb = s->d_out_rgb8 = nullptr;
+        s->out_cap = 0;
+        API_CUDA(cudaMalloc(&s->d_out_rgb, npix * 3 * sizeof(double)));
+        API_CUDA(cudaMalloc(&s->d_out_rgb8, npix * 3));
+        s->out_cap = npix;
+    }
+    const bool sharded = opts->row_world > 1;
+    if (sharded) {
+        // untouched rows must stay untouched on the host: start from the caller's buffers
+        if (out_rgb) API_CUDA(cudaMemcpyAsync(s->d_out_rgb, out_rgb, npix * 3 * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+        if (out_rgb8) API_CUDA(cudaMemcpyAsync(s->d_out_rgb8, out_rgb8, npix * 3, cudaMemcpyHostToDevice, s->stream));
+    }
+    std::string err;
+    rc = (opts->precision == CR_PRECISION_F32)
+             ? render_impl<float>(s->dev, s->ws, *cam, *opts, out_rgb ? s->d_out_rgb : nullptr, out_rgb8 ? s->d_out_rgb8 : nullptr, 0,
+                                  s->stream, stats, err)
+             : render_impl<double>(s->dev, s->ws, *cam, *opts, out_rgb ? s->d_out_rgb : nullptr, out_rgb8 ? s->d_out_rgb8 : nullptr,
+                                   0, s->stream, stats, err);
+    if (rc != CR_OK) return fail(rc, err);
+    cudaEvent_t a, b;
+    API_CUDA(cudaEventCreate(&a));
+    API_CUDA(cudaEventCreate(&b));
+    API_CUDA(cudaEventRecord(a, s->stream));
+    if (out_rgb) API_CUDA(cudaMemcpyAsync(out_rgb, s->d_out_rgb, npix * 3 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    if (out_rgb8) API_CUDA(cudaMemcpyAsync(out_rgb8, s->d_out_rgb8, npix * 3, cudaMemcpyDeviceToHost, s->stream));
+    API_CUDA(cudaEventRecord(b, s->stream));
+    API_CUDA(cudaEventSynchronize(b));
+    if (stats) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, a, b);
+        stats->ms_d2h = ms;
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    return CR_OK;
+}
+
+// TransformTimeline::combine_and_compute for a camera point, timeline/mod.rs:233-263 (host copy of
+// the device routine; used by the frame-sharding driver and by tests)
+int cr_camera_point_at(const double init[3], const CrKeyframe* keys, size_t n, double t, double out[3]) {
+    if (!init || !out || (!keys && n)) return fail(CR_ERR_INVALID, "null argument");
+    double p[3] = {init[0], init[1], init[2]};
+    for (size_t k = 0; k < n; ++k) {
+        const double t0 = keys[k].t0, t1 = keys[k].t1;
+        if (keys[k].axis < 0 || keys[k].axis > 2) return fail(CR_ERR_INVALID, "keyframe axis out of range");
+        if (!((t > t1) || (t0 <= t && t <= t1))) continue;
+        double s = (t - t0) / (t1 - t0);
+        s = s < 0.0 ? 0.0 : (s > 1.0 ? 1.0 : s);
+        const double off = (keys[k].interp == CR_LERP) ? keys[k].delta * s : keys[k].delta;
+        p[keys[k].axis] = off + p[keys[k].axis];
+    }
+    out[0] = p[0];
+    out[1] = p[1];
+    out[2] = p[2];
+    return CR_OK;
+}
+
+int cr_measure_fma_peak(int device, double* fp64_tflops, double* fp32_tflops) {
+    if (!fp64_tflops || !fp32_tflops) return fail(CR_ERR_INVALID, "null argument");
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) {
+        cudaGetLastError();
+        return fail(CR_ERR_NO_DEVICE, "no CUDA device");
+    }
+    API_CUDA(cudaSetDevice(device));
+    cudaDeviceProp p;
+    API_CUDA(cudaGetDeviceProperties(&p, device));
+    std::string err;
+    int rc = measure_fma_peak(p.multiProcessorCount, fp64_tflops, fp32_tflops, err);
+    if (rc != CR_OK) return fail(rc, err);
+    return CR_OK;
+}
+
+void cr_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];
+    for (int i = 0; i < 10; ++i) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1;
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+}  // extern "C"

@@ -1,0 +1,184 @@
+// common.cuh — device-side data layout shared by every kernel of the wavefront integrator.
+//
+// Layout in HBM (one CrScene per device, sized for 180 GB):
+//   nodes   : 64 B (f64) / 32 B (f32) per BVH node, four / two 128-bit words, preorder;
+//   spheres : (cx,cy,cz,r)                 32 B / 16 B
+//   tris    : (a, e1=b-a, e2=c-a)          80 B / 48 B (padded to whole 128-bit words)
+//   quads   : (Q,u,v,normal,w,D)           128 B / 64 B
+//   paths   : one 128 B (f64) / 64 B (f32) record per in-flight path, double buffered; the shade
+//             kernels read a record through the material queue and write the survivor compactly
+//             into the other buffer (stream compaction between bounces).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/crucible_gpu.h"
+
+namespace crb {
+
+// ---- child / primitive references -------------------------------------------------------------
+// bit31 = leaf; bits 29..30 = CrPrimKind; bits 0..26 = index into that kind's array (134 M).
+// Inner nodes are plain indices.  Bits 27..28 of a node's `left` field carry that NODE's split
+// axis (used by the near-first f32 traversal only); node_left() strips them.  REF_NONE marks "no right child to visit" (span-1 nodes hold the
+// same primitive twice in the reference, bvhwrapper.rs:59-61; the second test provably returns None).
+static constexpr uint32_t REF_LEAF = 0x80000000u;
+static constexpr uint32_t REF_NONE = 0x7FFFFFFFu;
+static constexpr uint32_t REF_MISS = 0xFFFFFFFFu;
+__host__ __device__ inline uint32_t make_leaf(uint32_t kind, uint32_t idx) { return REF_LEAF | (kind << 29) | idx; }
+__host__ __device__ inline bool ref_is_leaf(uint32_t r) { return (r & REF_LEAF) != 0; }
+__host__ __device__ inline uint32_t ref_kind(uint32_t r) { return (r >> 29) & 3u; }
+__host__ __device__ inline uint32_t ref_index(uint32_t r) { return r & 0x07FFFFFFu; }
+static constexpr uint32_t REF_MAX_INDEX = 0x07FFFFFEu;
+static constexpr uint32_t AXIS_SHIFT = 27;
+static constexpr uint32_t AXIS_MASK = 3u << AXIS_SHIFT;
+
+static constexpr int MAX_STACK = 48;  // the host refuses trees deeper than MAX_STACK-2
+static constexpr int MAX_TEX_NEST = 8;
+
+// ---- shading queues ------------------------------------------------------------------------------
+enum Queue : int { Q_MISS = 0, Q_LAMBERTIAN = 1, Q_METAL = 2, Q_DIELECTRIC = 3, Q_EMISSIVE = 4, Q_COUNT = 5 };
+
+// ---- node / primitive records (templated on the arithmetic type) ---------------------------------
+template <typename R>
+struct NodeRec;
+template <>
+struct __align__(16) NodeRec<double> {
+    double xmin, xmax, ymin, ymax, zmin, zmax;
+    uint32_t left, right, pad0, pad1;
+};
+template <>
+struct __align__(16) NodeRec<float> {
+    float xmin, xmax, ymin, ymax, zmin, zmax;
+    uint32_t left, right;
+};
+static_assert(sizeof(NodeRec<double>) == 64, "f64 node = 4 x 128 bit");
+static_assert(sizeof(NodeRec<float>) == 32, "f32 node = 2 x 128 bit");
+
+template <typename R>
+struct __align__(16) SphereRec {
+    R cx, cy, cz, r;
+};
+template <typename R>
+struct TriRec;
+template <>
+struct __align__(16) TriRec<double> {
+    double ax, ay, az, e1x, e1y, e1z, e2x, e2y, e2z, pad;
+};
+template <>
+struct __align__(16) TriRec<float> {
+    float ax, ay, az, e1x, e1y, e1z, e2x, e2y, e2z, pad0, pad1, pad2;
+};
+template <typename R>
+struct __align__(16) QuadRec {
+    R qx, qy, qz, ux, uy, uz, vx, vy, vz, nx, ny, nz, wx, wy, wz, d;
+};
+
+struct PrimMeta {  // per primitive, per kind
+    int32_t material;
+    int32_t prim_index;
+    int32_t obj_id;
+    int32_t mat_kind;
+};
+
+struct DevMaterial {
+    int32_t kind, tex;
+    double scatter_prob, fuzz, ior;
+    double albedo[3];
+    double emit[3];
+};
+struct DevTexture {
+    int32_t kind, even, odd, image;
+    double color[3];
+    double inv_scale;
+};
+struct DevImage {
+    cudaTextureObject_t tex;  // uchar4, point sampled, unnormalised coordinates
+    int32_t w, h;
+};
+
+template <typename R>
+struct DevScene {
+    const NodeRec<R>* nodes;
+    const SphereRec<R>* spheres;
+    const TriRec<R>* tris;
+    const QuadRec<R>* quads;
+    const PrimMeta* meta[3];
+    const DevMaterial* mats;
+    const DevTexture* texs;
+    const DevImage* images;
+    uint32_t root;  // REF_MISS when the world is the empty HitList
+    int32_t sky_kind, sky_image;
+    int32_t clamp_colors;  // 1 = reference Color semantics; 0 when the scene holds an Emissive (extension)
+};
+
+// ---- in-flight path record --------------------------------------------------------------------
+template <typename R>
+struct PathRec;
+template <>
+struct __align__(16) PathRec<double> {
+    double ox, oy, oz, dx, dy, dz;  // ray (direction NOT normalised, ray_casting.rs:102)
+    double tm, t;                   // ray time; closest-hit t written by trace
+    double tr, tg, tb;              // product of attenuations so far
+    uint32_t ref, bounce;           // closest-hit reference written by trace; hits so far
+    uint32_t pixel, sample;         // GLOBAL pixel index (RNG key), sample index
+    uint32_t fb, pad0;              // local framebuffer index
+    double pad1, pad2;
+};
+template <>
+struct __align__(16) PathRec<float> {
+    float ox, oy, oz, dx, dy, dz;
+    float tm, t;
+    float tr, tg, tb;
+    uint32_t ref;
+    uint32_t pixel, sample, bounce, fb;
+};
+static_assert(sizeof(PathRec<double>) == 128, "f64 path record = one 128 B line");
+static_assert(sizeof(PathRec<float>) == 64, "f32 path record = half a line");
+
+// ---- wavefront control block (device resident, one per render) -----------------------------------
+struct Control {
+    // per ping-pong side
+    uint32_t n_in[2];        // paths to trace in buffer side s
+    uint32_t out_count[2];   // survivors appended to side s by the shade kernels
+    uint32_t trace_next;     // warp-level work fetch cursor of the trace kernel
+    uint32_t gen_base;       // raygen: first free record of the target side
+    uint32_t gen_count;      // raygen: records to generate
+    uint32_t pad0;
+    uint64_t gen_first;      // raygen: first global sample id
+    uint64_t next_sample;    // samples handed out so far
+    uint64_t total_samples;  // npix_local * spp
+    uint64_t rays_traced;    // sum of n_in over iterations
+    uint32_t queue_count[Q_COUNT];
+    uint32_t queue_next[Q_COUNT];
+    uint32_t pool;
+    uint32_t iteration;
+};
+
+// ---- camera as the kernels see it ----------------------------------------------------------------
+struct DevCamera {
+    CrCamera c;
+    uint32_t row_block, row_rank, row_world, rows_local;
+    uint64_t seed;
+    uint32_t fb_scale_bits;
+    uint32_t pad;
+};
+
+// ---- small vector helpers --------------------------------------------------------------------------
+template <typename R>
+struct V3 {
+    R x, y, z;
+};
+
+// 128-bit read-only loads (LDG.E.128.CONSTANT) of a record made of N 16-byte words
+template <int NWORDS, typename T>
+__device__ __forceinline__ T ldg_rec(const T* p) {
+    static_assert(sizeof(T) == NWORDS * 16, "record size");
+    T out;
+    const int4* s = reinterpret_cast<const int4*>(p);
+    int4* d = reinterpret_cast<int4*>(&out);
+#pragma unroll
+    for (int i = 0; i < NWORDS; ++i) d[i] = __ldg(s + i);
+    return out;
+}
+
+}  // namespace crb

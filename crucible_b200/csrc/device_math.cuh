@@ -1,0 +1,367 @@
+// device_math.cuh — Vec3 / Color / Interval arithmetic in the reference's operation order
+// (src/utils.rs), Philox4x32-10, and the per-primitive hit tests.  Templated on R = double
+// (bit-faithful path; its translation unit is compiled with -fmad=false so no DFMA is formed)
+// or float (fast path).
+#pragma once
+#include "common.cuh"
+
+namespace crb {
+
+template <typename R> struct Num;
+template <> struct Num<double> {
+    static __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }  // IEEE rn
+    static __device__ __forceinline__ double abs_(double x) { return fabs(x); }
+    static __device__ __forceinline__ double floor_(double x) { return floor(x); }
+    static __device__ __forceinline__ double min_(double a, double b) { return fmin(a, b); }
+    static __device__ __forceinline__ double acos_(double x) { return acos(x); }
+    static __device__ __forceinline__ double asin_(double x) { return asin(x); }
+    static __device__ __forceinline__ double atan2_(double y, double x) { return atan2(y, x); }
+    static __device__ __forceinline__ double inf() { return __longlong_as_double(0x7ff0000000000000LL); }
+    static __device__ __forceinline__ double eps() { return 2.220446049250313e-16; }  // f64::EPSILON
+    static __device__ __forceinline__ double pi() { return 3.14159265358979323846; }
+};
+template <> struct Num<float> {
+    static __device__ __forceinline__ float sqrt_(float x) { return sqrtf(x); }
+    static __device__ __forceinline__ float abs_(float x) { return fabsf(x); }
+    static __device__ __forceinline__ float floor_(float x) { return floorf(x); }
+    static __device__ __forceinline__ float min_(float a, float b) { return fminf(a, b); }
+    static __device__ __forceinline__ float acos_(float x) { return acosf(x); }
+    static __device__ __forceinline__ float asin_(float x) { return asinf(x); }
+    static __device__ __forceinline__ float atan2_(float y, float x) { return atan2f(y, x); }
+    static __device__ __forceinline__ float inf() { return __int_as_float(0x7f800000); }
+    static __device__ __forceinline__ float eps() { return 1.1920929e-7f; }
+    static __device__ __forceinline__ float pi() { return 3.14159265358979323846f; }
+};
+
+// ---- utils.rs Point3/Vec3 (operation order is the contract) --------------------------------------
+template <typename R> __device__ __forceinline__ V3<R> vneg(V3<R> a) { return {-a.x, -a.y, -a.z}; }                 // :248-257
+template <typename R> __device__ __forceinline__ V3<R> vadd(V3<R> a, V3<R> b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }  // :283-293
+template <typename R> __device__ __forceinline__ V3<R> vsub(V3<R> a, V3<R> b) { return vadd(a, vneg(b)); }          // :295-301
+template <typename R> __device__ __forceinline__ V3<R> vmul(R s, V3<R> v) { return {s * v.x, s * v.y, s * v.z}; }   // :303-311
+template <typename R> __device__ __forceinline__ V3<R> vdiv(V3<R> v, R s) { return vmul(R(1) / s, v); }             // :325-331
+template <typename R> __device__ __forceinline__ R vlen2(V3<R> v) { return v.x * v.x + v.y * v.y + v.z * v.z; }     // :183-186
+template <typename R> __device__ __forceinline__ R vdot(V3<R> a, V3<R> b) { return a.x * b.x + a.y * b.y + a.z * b.z; }  // :194-199
+template <typename R> __device__ __forceinline__ V3<R> vcross(V3<R> v, V3<R> o) {                                    // :201-212
+    return {v.y * o.z - v.z * o.y, v.z * o.x - v.x * o.z, v.x * o.y - v.y * o.x};
+}
+template <typename R> __device__ __forceinline__ V3<R> vunit(V3<R> v) { return vdiv(v, Num<R>::sqrt_(vlen2(v))); }  // :215-218
+template <typename R> __device__ __forceinline__ bool vnear_zero(V3<R> v) {                                         // :189-192
+    const R tol = R(1e-8);
+    return Num<R>::abs_(v.x) < tol && Num<R>::abs_(v.y) < tol && Num<R>::abs_(v.z) < tol;
+}
+template <typename R> __device__ __forceinline__ V3<R> vreflect(V3<R> v, V3<R> n) {                                  // :151-153
+    return vsub(v, vmul(R(2) * vdot(v, n), n));
+}
+template <typename R> __device__ __forceinline__ V3<R> vrefract(V3<R> v, V3<R> n, R eta) {                           // :159-165
+    R cos_theta = Num<R>::min_(vdot(vneg(v), n), R(1));
+    V3<R> perp = vmul(eta, vadd(v, vmul(cos_theta, n)));
+    V3<R> par = vmul(-(Num<R>::sqrt_(Num<R>::abs_(R(1) - vlen2(perp)))), n);
+    return vadd(perp, par);
+}
+template <typename R> __device__ __forceinline__ R rclamp(R x, R lo, R hi) {  // Rust f64::clamp
+    if (x < lo) return lo;
+    if (x > hi) return hi;
+    return x;
+}
+
+// ---- utils.rs Color: every operator clamps to [0,1] (utils.rs:487-603) ---------------------------
+template <typename R> __device__ __forceinline__ R c01(R x, bool cl) { return cl ? rclamp(x, R(0), R(1)) : x; }
+template <typename R> __device__ __forceinline__ V3<R> col_neg(V3<R> c) {  // :445-459 (hilo complement)
+    R mn = (c.x < c.y ? c.x : c.y);
+    mn = (mn < c.z ? mn : c.z);
+    R mx = (c.x > c.y ? c.x : c.y);
+    mx = (mx > c.z ? mx : c.z);
+    R k = mn + mx;
+    return {Num<R>::abs_(k - c.x), Num<R>::abs_(k - c.y), Num<R>::abs_(k - c.z)};
+}
+template <typename R> __device__ __forceinline__ V3<R> col_add(V3<R> a, V3<R> b, bool cl) {  // :516-529
+    return {c01(a.x + b.x, cl), c01(a.y + b.y, cl), c01(a.z + b.z, cl)};
+}
+template <typename R> __device__ __forceinline__ V3<R> col_scale(R s, V3<R> c, bool cl) {  // :558-574
+    V3<R> m = (s < R(0)) ? col_neg(c) : c;
+    R p = Num<R>::abs_(s);
+    return {c01(p * m.x, cl), c01(p * m.y, cl), c01(p * m.z, cl)};
+}
+template <typename R> __device__ __forceinline__ V3<R> col_mul(V3<R> a, V3<R> b, bool cl) {  // :576-590
+    return {c01(a.x * b.x, cl), c01(a.y * b.y, cl), c01(a.z * b.z, cl)};
+}
+template <typename R> __device__ __forceinline__ V3<R> col_div(V3<R> c, R rhs, bool cl) {  // :592-601
+    V3<R> inv = (rhs < R(0)) ? col_neg(c) : c;
+    return col_scale(R(1) / Num<R>::abs_(rhs), inv, cl);
+}
+
+// ---- Philox4x32-10, keyed (seed; pixel, sample, bounce, block) -----------------------------------
+__host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                                        uint32_t k1, uint32_t out[4]) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        uint32_t n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+template <typename R> struct Rng;
+// f64: two 53-bit uniforms per block, identical to the oracle's stream (path-by-path comparable)
+template <> struct Rng<double> {
+    uint32_t k0, k1, c0, c1, c2, c3;
+    uint32_t b2, b3;
+    int have;
+    __device__ __forceinline__ Rng(uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t bounce)
+        : k0((uint32_t)seed), k1((uint32_t)(seed >> 32)), c0(pixel), c1(sample), c2(bounce), c3(0), b2(0), b3(0), have(0) {}
+    __device__ __forceinline__ double next() {
+        uint64_t x;
+        if (have == 0) {
+            uint32_t o[4];
+            philox4x32_10(c0, c1, c2, c3, k0, k1, o);
+            c3++;
+            b2 = o[2];
+            b3 = o[3];
+            have = 1;
+            x = ((uint64_t)o[1] << 32) | o[0];
+        } else {
+            have = 0;
+            x = ((uint64_t)b3 << 32) | b2;
+        }
+        return (double)(x >> 11) * (1.0 / 9007199254740992.0);
+    }
+    __device__ __forceinline__ double range(double lo, double hi) { return lo + (hi - lo) * next(); }
+};
+// f32: four 24-bit uniforms per block (a different, equally valid stream)
+template <> struct Rng<float> {
+    uint32_t k0, k1, c0, c1, c2, c3;
+    uint32_t b[4];
+    int have;
+    __device__ __forceinline__ Rng(uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t bounce)
+        : k0((uint32_t)seed), k1((uint32_t)(seed >> 32)), c0(pixel), c1(sample), c2(bounce), c3(0), have(0) {}
+    __device__ __forceinline__ float next() {
+        if (have == 0) {
+            philox4x32_10(c0, c1, c2, c3, k0, k1, b);
+            c3++;
+            have = 4;
+        }
+        uint32_t w = (have == 4) ? b[0] : (have == 3) ? b[1] : (have == 2) ? b[2] : b[3];
+        have--;
+        return (float)(w >> 8) * (1.0f / 16777216.0f);
+    }
+    __device__ __forceinline__ float range(float lo, float hi) { return lo + (hi - lo) * next(); }
+};
+
+template <typename R> __device__ __forceinline__ V3<R> random_unit_vector(Rng<R>& g) {  // utils.rs:128-138
+    for (;;) {
+        R x = g.range(R(-1), R(1));
+        R y = g.range(R(-1), R(1));
+        R z = g.range(R(-1), R(1));
+        V3<R> p = {x, y, z};
+        R l2 = vlen2(p);
+        if (R(1e-160) < l2 && l2 <= R(1)) return vdiv(p, Num<R>::sqrt_(l2));
+    }
+}
+template <> __device__ __forceinline__ V3<float> random_unit_vector<float>(Rng<float>& g) {
+    for (;;) {
+        float x = g.range(-1.f, 1.f), y = g.range(-1.f, 1.f), z = g.range(-1.f, 1.f);
+        V3<float> p = {x, y, z};
+        float l2 = vlen2(p);
+        if (1e-30f < l2 && l2 <= 1.f) return vdiv(p, sqrtf(l2));
+    }
+}
+template <typename R> __device__ __forceinline__ V3<R> random_in_unit_disk(Rng<R>& g) {  // utils.rs:112-126
+    for (;;) {
+        R x = g.range(R(-1), R(1));
+        R y = g.range(R(-1), R(1));
+        V3<R> p = {x, y, R(0)};
+        if (vlen2(p) < R(1)) return p;
+    }
+}
+
+// ---- Aabb::hit, src/objects/bvh.rs:96-132, comparison form (defines NaN behaviour) ---------------
+// inv = 1.0 / d per axis is a pure function of the ray, so it is hoisted out of the node loop.
+template <typename R>
+__device__ __forceinline__ bool slab_axis(R bmin, R bmax, R o, R inv, R& tmin, R& tmax) {
+    R t0 = (bmin - o) * inv;
+    R t1 = (bmax - o) * inv;
+    R nmin, nmax;
+    if (t0 < t1) {
+        nmin = (t0 > tmin) ? t0 : tmin;
+        nmax = (t1 < tmax) ? t1 : tmax;
+    } else {
+        nmin = (t1 > tmin) ? t1 : tmin;
+        nmax = (t0 < tmax) ? t0 : tmax;
+    }
+    tmin = nmin;
+    tmax = nmax;
+    return !(tmax <= tmin);
+}
+template <typename R>
+__device__ __forceinline__ bool aabb_hit(const NodeRec<R>& n, V3<R> o, V3<R> inv, R tmin, R tmax) {
+    if (!slab_axis(n.xmin, n.xmax, o.x, inv.x, tmin, tmax)) return false;
+    if (!slab_axis(n.ymin, n.ymax, o.y, inv.y, tmin, tmax)) return false;
+    return slab_axis(n.zmin, n.zmax, o.z, inv.z, tmin, tmax);
+}
+
+// ---- Sphere::hit, src/objects/sphere.rs:61-105: returns the accepted root ------------------------
+template <typename R>
+__device__ __forceinline__ bool sphere_hit_t(const SphereRec<R>& s, V3<R> o, V3<R> d, R a, R tmin, R tmax, R& t) {
+    V3<R> oc = vsub(V3<R>{s.cx, s.cy, s.cz}, o);
+    R h = vdot(d, oc);
+    R c = vlen2(oc) - s.r * s.r;
+    R disc = h * h - a * c;
+    if (disc < R(0)) return false;
+    R sq = Num<R>::sqrt_(disc);
+    R root = (h - sq) / a;
+    if (!(tmin < root && root < tmax)) {
+        root = (h + sq) / a;
+        if (!(tmin < root && root < tmax)) return false;
+    }
+    t = root;
+    return true;
+}
+// ---- Triangle::hit, src/objects/triangle.rs:86-140 (e1, e2 precomputed with the same ops) --------
+template <typename R>
+__device__ __forceinline__ bool tri_hit_t(const TriRec<R>& tr, V3<R> o, V3<R> d, R tmin, R tmax, R& t) {
+    V3<R> e1 = {tr.e1x, tr.e1y, tr.e1z}, e2 = {tr.e2x, tr.e2y, tr.e2z};
+    V3<R> pv = vcross(d, e2);
+    R det = vdot(e1, pv);
+    if (det > -Num<R>::eps() && det < Num<R>::eps()) return false;
+    R inv = R(1) / det;
+    V3<R> s = vsub(o, V3<R>{tr.ax, tr.ay, tr.az});
+    R u = inv * vdot(s, pv);
+    if (!(R(0) <= u && u <= R(1))) return false;
+    V3<R> q = vcross(s, e1);
+    R v = inv * vdot(d, q);
+    if (v < R(0) || u + v > R(1)) return false;
+    R tt = inv * vdot(e2, q);
+    if (!(tmin < tt && tt < tmax)) return false;
+    t = tt;
+    return true;
+}
+// ---- EXTENSION quad (same definition as oracle/oracle.cpp quad_hit) -------------------------------
+template <typename R>
+__device__ __forceinline__ bool quad_hit_t(const QuadRec<R>& q, V3<R> o, V3<R> d, R tmin, R tmax, R& t, R& alpha, R& beta) {
+    V3<R> n = {q.nx, q.ny, q.nz};
+    R denom = vdot(n, d);
+    if (Num<R>::abs_(denom) < R(1e-8)) return false;
+    R tt = (q.d - vdot(n, o)) / denom;
+    if (!(tmin < tt && tt < tmax)) return false;
+    V3<R> p = vadd(o, vmul(tt, d));
+    V3<R> ph = vsub(p, V3<R>{q.qx, q.qy, q.qz});
+    V3<R> w = {q.wx, q.wy, q.wz};
+    alpha = vdot(w, vcross(ph, V3<R>{q.vx, q.vy, q.vz}));
+    beta = vdot(w, vcross(V3<R>{q.ux, q.uy, q.uz}, ph));
+    if (!(R(0) <= alpha && alpha <= R(1)) || !(R(0) <= beta && beta <= R(1))) return false;
+    t = tt;
+    return true;
+}
+
+// ---- HitRecord (src/objects/mod.rs:21-87) rebuilt from (ref, t) -----------------------------------
+template <typename R> struct HitInfo {
+    V3<R> p, n;
+    R u, v;
+    bool front;
+    int32_t material, mat_kind, prim_index, obj_id;
+};
+template <typename R>
+__device__ __forceinline__ HitInfo<R> finalize_hit(const DevScene<R>& sc, uint32_t ref, R t, V3<R> o, V3<R> d) {
+    HitInfo<R> h;
+    const uint32_t kind = ref_kind(ref), idx = ref_index(ref);
+    const PrimMeta m = sc.meta[kind][idx];
+    h.material = m.material;
+    h.mat_kind = m.mat_kind;
+    h.prim_index = m.prim_index;
+    h.obj_id = m.obj_id;
+    h.p = vadd(o, vmul(t, d));  // Ray::at, ray_casting.rs:53-59
+    V3<R> n;
+    if (kind == CR_PRIM_SPHERE) {
+        SphereRec<R> s = ldg_rec<sizeof(SphereRec<R>) / 16>(sc.spheres + idx);
+        n = vdiv(vsub(h.p, V3<R>{s.cx, s.cy, s.cz}), s.r);  // sphere.rs:96
+        R theta = Num<R>::acos_(-n.y);                      // sphere.rs:41-46
+        R phi = Num<R>::atan2_(-n.z, n.x) + Num<R>::pi();
+        h.u = phi / (R(2) * Num<R>::pi());
+        h.v = theta / Num<R>::pi();
+    } else if (kind == CR_PRIM_TRIANGLE) {
+        TriRec<R> tr = ldg_rec<sizeof(TriRec<R>) / 16>(sc.tris + idx);
+        n = vunit(vcross(V3<R>{tr.e1x, tr.e1y, tr.e1z}, V3<R>{tr.e2x, tr.e2y, tr.e2z}));  // triangle.rs:124 + safe_new
+        h.u = R(0);  // triangle.rs:133-134
+        h.v = R(0);
+    } else {
+        QuadRec<R> q = ldg_rec<sizeof(QuadRec<R>) / 16>(sc.quads + idx);
+        n = {q.nx, q.ny, q.nz};
+        V3<R> ph = vsub(h.p, V3<R>{q.qx, q.qy, q.qz});
+        V3<R> w = {q.wx, q.wy, q.wz};
+        h.u = vdot(w, vcross(ph, V3<R>{q.vx, q.vy, q.vz}));
+        h.v = vdot(w, vcross(V3<R>{q.ux, q.uy, q.uz}, ph));
+    }
+    h.front = vdot(d, n) < R(0);  // objects/mod.rs:47-48
+    h.n = h.front ? n : vneg(n);
+    return h;
+}
+
+// ---- closest hit: BVHWrapper::hit, src/objects/bvhwrapper.rs:97-126 as an explicit-stack DFS ------
+// The recursion "left with (tmin,tmax), right with (tmin, left.t or tmax), prefer right" is a DFS with
+// ONE running closest-t: a later primitive only wins when strictly closer, inner boxes are tested with
+// the running interval at the time they are entered, leaves are tested with no box of their own.
+// EXACT = reference order (always left first).  !EXACT = near child first along the split axis.
+template <typename R, bool EXACT>
+__device__ __forceinline__ void closest_hit(const DevScene<R>& sc, V3<R> o, V3<R> d, R tmin, R tmax, uint32_t* stack,
+                                            int stride, uint32_t& best_ref, R& best_t) {
+    best_ref = REF_MISS;
+    best_t = tmax;
+    if (sc.root == REF_MISS) return;
+    const V3<R> inv = {R(1) / d.x, R(1) / d.y, R(1) / d.z};  // adinv, bvh.rs:111
+    const R a = vlen2(d);                                     // sphere.rs:74
+    int sp = 0;
+    uint32_t cur = sc.root;
+    for (;;) {
+        if (!ref_is_leaf(cur)) {
+            const NodeRec<R> n = ldg_rec<sizeof(NodeRec<R>) / 16>(sc.nodes + cur);
+            if (aabb_hit(n, o, inv, tmin, best_t)) {
+                uint32_t first = n.left & ~AXIS_MASK, second = n.right;
+                if (!EXACT) {
+                    const uint32_t ax = (n.left & AXIS_MASK) >> AXIS_SHIFT;
+                    const R dd = ax == 0 ? d.x : (ax == 1 ? d.y : d.z);
+                    if (dd < R(0) && second != REF_NONE) {
+                        second = first;
+                        first = n.right;
+                    }
+                }
+                if (second != REF_NONE) {
+                    stack[sp * stride] = second;
+                    ++sp;
+                }
+                cur = first;
+                continue;
+            }
+        } else {
+            const uint32_t kind = ref_kind(cur), idx = ref_index(cur);
+            R t;
+            bool got;
+            if (kind == CR_PRIM_SPHERE) {
+                const SphereRec<R> s = ldg_rec<sizeof(SphereRec<R>) / 16>(sc.spheres + idx);
+                got = sphere_hit_t(s, o, d, a, tmin, best_t, t);
+            } else if (kind == CR_PRIM_TRIANGLE) {
+                const TriRec<R> tr = ldg_rec<sizeof(TriRec<R>) / 16>(sc.tris + idx);
+                got = tri_hit_t(tr, o, d, tmin, best_t, t);
+            } else {
+                const QuadRec<R> q = ldg_rec<sizeof(QuadRec<R>) / 16>(sc.quads + idx);
+                R al, be;
+                got = quad_hit_t(q, o, d, tmin, best_t, t, al, be);
+            }
+            if (got) {
+                best_t = t;
+                best_ref = cur;
+            }
+        }
+        if (sp == 0) break;
+        --sp;
+        cur = stack[sp * stride];
+    }
+}
+
+}  // namespace crb

@@ -1,0 +1,698 @@
+// integrator.cuh — the wavefront path tracer: raygen -> persistent-thread trace -> material-sorted
+// shade kernels with stream compaction -> resolve.  Everything is templated on R (double = faithful,
+// float = fast) and instantiated by integrator_f64.cu (-fmad=false) and integrator_f32.cu.
+//
+// Replaces Camera::cast_ray / ray_color / average_samples (src/camera/ray_casting.rs:64-173) and the
+// worker pool of src/camera/cpu_threading.rs:25-115.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "device_math.cuh"
+#include "integrator.h"
+
+namespace crb {
+
+static constexpr int TRACE_BLOCK = 128;
+static constexpr int SHADE_BLOCK = 128;
+
+// ---- warp-aggregated append (one atomic per warp per destination) --------------------------------
+static __device__ __forceinline__ uint32_t warp_append(uint32_t* counter, bool pred) {
+    const uint32_t mask = __ballot_sync(0xffffffffu, pred);
+    if (mask == 0) return 0;
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(mask) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    return base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
+}
+
+// ---- textures (src/textures/*.rs) -------------------------------------------------------------------
+// image_texture.rs:23-32 and SkyboxImage::get_color (scene/mod.rs:37-45): clamp, flip v, truncate,
+// clamp to the last texel (img_loader.rs:69-77), byte / 255.0 (img_loader.rs:40-42).  The fetch goes
+// through a point-sampled CUDA texture object (uchar4), so the texel is exact and cached by the TEX unit.
+template <typename R>
+__device__ __forceinline__ V3<R> image_lookup(const DevImage& im, R u, R v) {
+    u = rclamp(u, R(0), R(1));
+    v = R(1) - rclamp(v, R(0), R(1));
+    R fi = u * (R)im.w, fj = v * (R)im.h;
+    // `as usize`: truncation toward zero, saturating, NaN -> 0
+    long long i = (fi == fi) ? (long long)fi : 0;
+    long long j = (fj == fj) ? (long long)fj : 0;
+    if (i < 0) i = 0;
+    if (j < 0) j = 0;
+    if (i > im.w - 1) i = im.w - 1;
+    if (j > im.h - 1) j = im.h - 1;
+    const uchar4 t = tex2D<uchar4>(im.tex, (float)i + 0.5f, (float)j + 0.5f);
+    return {(R)t.x / R(255), (R)t.y / R(255), (R)t.z / R(255)};
+}
+template <typename R>
+__device__ __forceinline__ int32_t floor_i32(R x) {  // `.floor() as i32` (saturating, NaN -> 0)
+    R f = Num<R>::floor_(x);
+    if (!(f == f)) return 0;
+    if (f <= R(-2147483648.0)) return INT32_MIN;
+    if (f >= R(2147483647.0)) return INT32_MAX;
+    return (int32_t)f;
+}
+template <typename R>
+__device__ __forceinline__ V3<R> tex_value(const DevScene<R>& sc, int tex, R u, R v, V3<R> p) {
+    for (int nest = 0; nest < MAX_TEX_NEST; ++nest) {
+        const DevTexture& t = sc.texs[tex];
+        if (t.kind == CR_TEX_SOLID) return {(R)t.color[0], (R)t.color[1], (R)t.color[2]};  // solid_color.rs:25-27
+        if (t.kind == CR_TEX_IMAGE) return image_lookup<R>(sc.images[t.image], u, v);
+        // checker_texture.rs:39-51
+        const R s = (R)t.inv_scale;
+        const int32_t xi = floor_i32(s * p.x), yi = floor_i32(s * p.y), zi = floor_i32(s * p.z);
+        const int32_t sum = (int32_t)((uint32_t)xi + (uint32_t)yi + (uint32_t)zi);
+        tex = (sum % 2 == 0) ? t.even : t.odd;
+    }
+    return {R(0), R(0), R(0)};
+}
+
+// ---- sky, src/camera/ray_casting.rs:133-151 ---------------------------------------------------------
+template <typename R>
+__device__ __forceinline__ V3<R> sky_color(const DevScene<R>& sc, V3<R> d) {
+    const bool cl = sc.clamp_colors != 0;
+    if (sc.sky_kind == CR_SKY_SPHERICAL) {
+        V3<R> ud = vunit(d);
+        R theta = Num<R>::atan2_(ud.x, ud.z);
+        R phi = Num<R>::asin_(ud.y);
+        R u = (theta / (R(2) * Num<R>::pi())) + R(0.5);
+        R v = (phi / Num<R>::pi()) + R(0.5);
+        return image_lookup<R>(sc.images[sc.sky_image], u, v);
+    }
+    if (sc.sky_kind == CR_SKY_BLACK) return {R(0), R(0), R(0)};
+    V3<R> ud = vunit(d);
+    R a = R(0.5) * (ud.y + R(1));
+    return col_add(col_scale(R(1) - a, V3<R>{R(1), R(1), R(1)}, cl), col_scale(a, V3<R>{R(0.5), R(0.7), R(1)}, cl), cl);
+}
+
+// ---- camera, src/camera/rendering_compute.rs + ray_casting.rs:77-104 -----------------------------
+// TransformTimeline::combine_and_compute for a camera point (timeline/mod.rs:233-263)
+template <typename R>
+__device__ __forceinline__ V3<R> point_at(const double init[3], const CrKeyframe* keys, uint32_t n, R t) {
+    R p[3] = {(R)init[0], (R)init[1], (R)init[2]};
+    for (uint32_t k = 0; k < n; ++k) {
+        const R t0 = (R)keys[k].t0, t1 = (R)keys[k].t1;
+        if (!((t > t1) || (t0 <= t && t <= t1))) continue;
+        R s = rclamp((t - t0) / (t1 - t0), R(0), R(1));
+        R off = (keys[k].interp == CR_LERP) ? (R)keys[k].delta * s : (R)keys[k].delta;
+        const int ax = keys[k].axis;
+        p[ax] = off + p[ax];
+    }
+    return {p[0], p[1], p[2]};
+}
+// One iteration of the sample loop.  Every basis function of the reference is a pure function of t,
+// so evaluating each once gives the same bits as the reference's ~20 re-evaluations.
+template <typename R>
+__device__ __forceinline__ void camera_sample(const DevCamera& cam, uint32_t i, uint32_t j, Rng<R>& g, V3<R>& ro, V3<R>& rd,
+                                              R& tm) {
+    const CrCamera& c = cam.c;
+    const R current_time = (R)c.frame * (R(1) / (R)c.frame_rate);
+    const R shutter_length = ((R)c.shutter_angle / R(360)) * (R(1) / (R)c.frame_rate);
+    const R t = current_time + g.range(R(0), shutter_length);
+    const V3<R> from = point_at<R>(c.look_from, c.from_keys, c.n_from_keys, t);
+    const V3<R> at = point_at<R>(c.look_at, c.at_keys, c.n_at_keys, t);
+    const R ox = g.next() - R(0.5);  // sample_square, camera/mod.rs:369-376
+    const R oy = g.next() - R(0.5);
+    const V3<R> vup = {(R)c.vup[0], (R)c.vup[1], (R)c.vup[2]};
+    const V3<R> w = vunit(vsub(from, at));                          // w_basis :88-93
+    const V3<R> u = vunit(vcross(vup, w));                          // u_basis :77-80
+    const V3<R> v = vcross(w, u);                                   // v_basis :82-85
+    const V3<R> vu = vmul((R)c.viewport_width, u);                  // viewport_u :16-19
+    const V3<R> vv = vmul((R)c.viewport_height, vneg(v));           // viewport_v :24-27
+    const V3<R> pdu = vdiv(vu, (R)c.image_width);                   // pixel_delta_u :32-35
+    const V3<R> pdv = vdiv(vv, (R)c.image_height);                  // pixel_delta_v :40-43
+    const V3<R> ul = vsub(vsub(vsub(from, vmul((R)c.focus_dist, w)), vdiv(vu, R(2))), vdiv(vv, R(2)));  // :49-55
+    const V3<R> psl = vadd(ul, vmul(R(0.5), vadd(pdu, pdv)));       // pixel_start_location :57-60
+    const V3<R> ps = vadd(vadd(psl, vmul((R)i + ox, pdu)), vmul((R)j + oy, pdv));  // get_pixel_pos :64-68
+    V3<R> orig = from;
+    if (!(c.defocus_angle <= 0.0)) {                                // ray_casting.rs:96-100
+        const V3<R> p = random_in_unit_disk(g);                     // defocus_disk_sample :105-110
+        const V3<R> du = vmul((R)c.defocus_radius, u);
+        const V3<R> dv = vmul((R)c.defocus_radius, v);
+        orig = vadd(vadd(from, vmul(p.x, du)), vmul(p.y, dv));
+    }
+    ro = orig;
+    rd = vsub(ps, orig);
+    tm = t;
+}
+
+// local (per-rank) row -> global row: rows j with (j / row_block) % row_world == row_rank, in order
+__host__ __device__ inline uint32_t local_to_global_row(uint32_t lr, uint32_t block, uint32_t rank, uint32_t world) {
+    if (world <= 1) return lr;
+    const uint32_t tile = lr / block, within = lr % block;
+    return (tile * world + rank) * block + within;
+}
+
+// ---- kernels --------------------------------------------------------------------------------------
+// plan: single thread.  Closes iteration `side`->`nxt`: survivors are already in side nxt; decide how
+// many camera samples top the pool up, publish the trace size of the next iteration, reset cursors.
+static __global__ void k_plan(Control* ctl, int nxt, uint32_t* host_n_in) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const uint32_t survivors = ctl->out_count[nxt];
+    const uint64_t remaining = ctl->total_samples - ctl->next_sample;
+    uint64_t room = (uint64_t)ctl->pool - survivors;
+    const uint32_t n_new = (uint32_t)(remaining < room ? remaining : room);
+    ctl->gen_base = survivors;
+    ctl->gen_count = n_new;
+    ctl->gen_first = ctl->next_sample;
+    ctl->next_sample += n_new;
+    const uint32_t n_in = survivors + n_new;
+    ctl->n_in[nxt] = n_in;
+    ctl->rays_traced += n_in;
+    ctl->out_count[nxt ^ 1] = 0;
+    ctl->trace_next = 0;
+    for (int q = 0; q < Q_COUNT; ++q) ctl->queue_count[q] = 0;
+    ctl->iteration++;
+    if (host_n_in) *host_n_in = n_in;
+}
+
+// raygen: persistent grid-stride over the samples the plan handed out.  Sample-major order
+// (g = sample * npix + pixel) keeps neighbouring lanes on neighbouring pixels.
+template <typename R>
+__global__ void __launch_bounds__(SHADE_BLOCK) k_raygen(const Control* __restrict__ ctl, const DevCamera* __restrict__ camp,
+                                                         PathRec<R>* __restrict__ out) {
+    const uint32_t n = ctl->gen_count;
+    if (n == 0) return;
+    const uint32_t base = ctl->gen_base;
+    const uint64_t first = ctl->gen_first;
+    const DevCamera& cam = *camp;
+    const uint32_t W = cam.c.image_width;
+    const uint64_t npix = (uint64_t)W * cam.rows_local;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const uint64_t g = first + k;
+        const uint32_t sample = (uint32_t)(g / npix);
+        const uint32_t lp = (uint32_t)(g % npix);
+        const uint32_t lrow = lp / W, i = lp % W;
+        const uint32_t j = local_to_global_row(lrow, cam.row_block, cam.row_rank, cam.row_world);
+        const uint32_t pixel = j * W + i;
+        Rng<R> rng(cam.seed, pixel, sample, 0);
+        V3<R> o, d;
+        R tm;
+        camera_sample<R>(cam, i, j, rng, o, d, tm);
+        PathRec<R> p;
+        p.ox = o.x; p.oy = o.y; p.oz = o.z;
+        p.dx = d.x; p.dy = d.y; p.dz = d.z;
+        p.tm = tm;
+        p.t = R(0);
+        p.tr = R(1); p.tg = R(1); p.tb = R(1);
+        p.ref = REF_MISS;
+        p.bounce = 0;
+        p.pixel = pixel;
+        p.sample = sample;
+        p.fb = lp;
+        out[base + k] = p;
+    }
+}
+
+// trace: persistent threads, warp-level work fetch (lane 0 grabs 32 rays), traversal stack in shared
+// memory ([depth][thread], conflict free), 128-bit node / primitive loads, then classification of the
+// ray into its material queue with one atomic per warp per queue.
+template <typename R, bool EXACT>
+__global__ void __launch_bounds__(TRACE_BLOCK) k_trace(DevScene<R> sc, PathRec<R>* __restrict__ paths, Control* __restrict__ ctl,
+                                                        int side, uint32_t* __restrict__ queues, uint32_t pool) {
+    __shared__ uint32_t s_stack[MAX_STACK * TRACE_BLOCK];
+    const uint32_t n = ctl->n_in[side];
+    const int lane = threadIdx.x & 31;
+    uint32_t* stack = s_stack + threadIdx.x;
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&ctl->trace_next, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        const uint32_t i = base + lane;
+        const bool valid = i < n;
+        int q = -1;
+        if (valid) {
+            // the first 48 (24) bytes of the record: origin + direction
+            PathRec<R>* p = paths + i;
+            V3<R> o, d;
+            if constexpr (sizeof(R) == 8) {
+                const double2 a = *reinterpret_cast<const double2*>(&p->ox);
+                const double2 b = *reinterpret_cast<const double2*>(&p->oz);
+                const double2 c = *reinterpret_cast<const double2*>(&p->dy);
+                o = {a.x, a.y, b.x};
+                d = {b.y, c.x, c.y};
+            } else {
+                const float4 a = *reinterpret_cast<const float4*>(&p->ox);
+                const float2 b = *reinterpret_cast<const float2*>(&p->dy);
+                o = {a.x, a.y, a.z};
+                d = {a.w, b.x, b.y};
+            }
+            uint32_t ref;
+            R t;
+            closest_hit<R, EXACT>(sc, o, d, R(0.001), Num<R>::inf(), stack, TRACE_BLOCK, ref, t);  // ray_casting.rs:119
+            p->t = t;
+            p->ref = ref;
+            q = (ref == REF_MISS) ? (int)Q_MISS : (int)Q_LAMBERTIAN + sc.meta[ref_kind(ref)][ref_index(ref)].mat_kind;
+        }
+#pragma unroll
+        for (int k = 0; k < Q_COUNT; ++k) {
+            const bool mine = (q == k);
+            const uint32_t pos = warp_append(&ctl->queue_count[k], mine);
+            if (mine) queues[(size_t)k * pool + pos] = i;
+        }
+    }
+}
+
+// fixed-point accumulation: order independent => bit-reproducible for any schedule and GPU count
+static __device__ __forceinline__ void fb_add(unsigned long long* fb, uint32_t idx, double r, double g, double b, double scale) {
+    atomicAdd(fb + 3ull * idx + 0, __double2ull_rn(r * scale));
+    atomicAdd(fb + 3ull * idx + 1, __double2ull_rn(g * scale));
+    atomicAdd(fb + 3ull * idx + 2, __double2ull_rn(b * scale));
+}
+
+template <typename R>
+__device__ __forceinline__ void load_path(const PathRec<R>* p, PathRec<R>& out) {
+    const int4* s = reinterpret_cast<const int4*>(p);
+    int4* d = reinterpret_cast<int4*>(&out);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(PathRec<R>) / 16); ++i) d[i] = s[i];
+}
+template <typename R>
+__device__ __forceinline__ void store_path(PathRec<R>* p, const PathRec<R>& in) {
+    int4* d = reinterpret_cast<int4*>(p);
+    const int4* s = reinterpret_cast<const int4*>(&in);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(PathRec<R>) / 16); ++i) d[i] = s[i];
+}
+
+// miss: ray_color's skybox arm; the path ends and thr * sky is accumulated
+template <typename R>
+__global__ void __launch_bounds__(SHADE_BLOCK) k_shade_miss(DevScene<R> sc, const PathRec<R>* __restrict__ in,
+                                                             const Control* __restrict__ ctl, const uint32_t* __restrict__ queue,
+                                                             unsigned long long* __restrict__ fb, double fb_scale) {
+    const uint32_t n = ctl->queue_count[Q_MISS];
+    const bool cl = sc.clamp_colors != 0;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        PathRec<R> p;
+        load_path(in + queue[k], p);
+        const V3<R> sky = sky_color<R>(sc, V3<R>{p.dx, p.dy, p.dz});
+        const V3<R> c = col_mul(V3<R>{p.tr, p.tg, p.tb}, sky, cl);
+        fb_add(fb, p.fb, (double)c.x, (double)c.y, (double)c.z, fb_scale);
+    }
+}
+
+// EXTENSION emissive: the path ends with thr * emit
+template <typename R>
+__global__ void __launch_bounds__(SHADE_BLOCK) k_shade_emissive(DevScene<R> sc, const PathRec<R>* __restrict__ in,
+                                                                 const Control* __restrict__ ctl,
+                                                                 const uint32_t* __restrict__ queue,
+                                                                 unsigned long long* __restrict__ fb, double fb_scale) {
+    const uint32_t n = ctl->queue_count[Q_EMISSIVE];
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        PathRec<R> p;
+        load_path(in + queue[k], p);
+        const PrimMeta m = sc.meta[ref_kind(p.ref)][ref_index(p.ref)];
+        const DevMaterial& mat = sc.mats[m.material];
+        fb_add(fb, p.fb, (double)(p.tr * (R)mat.emit[0]), (double)(p.tg * (R)mat.emit[1]), (double)(p.tb * (R)mat.emit[2]),
+               fb_scale);
+    }
+}
+
+// scatter kernels: one per material so a warp runs one BSDF.  MAT selects the arm at compile time.
+template <typename R, int MAT>
+__global__ void __launch_bounds__(SHADE_BLOCK) k_shade_scatter(DevScene<R> sc, const PathRec<R>* __restrict__ in,
+                                                                PathRec<R>* __restrict__ out, Control* __restrict__ ctl, int nxt,
+                                                                const uint32_t* __restrict__ queue, const DevCamera* __restrict__ camp) {
+    const uint32_t n = ctl->queue_count[Q_LAMBERTIAN + MAT];
+    if (n == 0) return;
+    const uint64_t seed = camp->seed;
+    const uint32_t max_depth = camp->c.max_depth;
+    const bool cl = sc.clamp_colors != 0;
+    const uint32_t n_round = (n + 31u) & ~31u;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n_round; k += gridDim.x * blockDim.x) {
+        bool alive = false;
+        PathRec<R> p;
+        if (k < n) {
+            load_path(in + queue[k], p);
+            const V3<R> o = {p.ox, p.oy, p.oz}, d = {p.dx, p.dy, p.dz};
+            const HitInfo<R> h = finalize_hit<R>(sc, p.ref, p.t, o, d);
+            const DevMaterial& mat = sc.mats[h.material];
+            const uint32_t bounce = p.bounce + 1;  // this is the bounce-th hit of the path
+            Rng<R> g(seed, p.pixel, p.sample, bounce);
+            V3<R> att, nd;
+            if (MAT == CR_MAT_LAMBERTIAN) {  // lambertian.rs:40-61
+                V3<R> dir = vadd(h.n, random_unit_vector(g));
+                if (vnear_zero(dir)) dir = h.n;
+                nd = dir;
+                att = col_div(tex_value<R>(sc, mat.tex, h.u, h.v, h.p), (R)mat.scatter_prob, true);
+                alive = g.next() <= (R)mat.scatter_prob;
+            } else if (MAT == CR_MAT_METAL) {  // metal.rs:29-42
+                const V3<R> refl = vreflect(d, h.n);
+                nd = vadd(vunit(refl), vmul((R)mat.fuzz, random_unit_vector(g)));
+                att = {(R)mat.albedo[0], (R)mat.albedo[1], (R)mat.albedo[2]};
+                alive = vdot(nd, h.n) > R(0);
+            } else {  // dielectric.rs:30-55
+                att = {R(1), R(1), R(1)};
+                const R ri = h.front ? R(1) / (R)mat.ior : (R)mat.ior;
+                const V3<R> ud = vunit(d);
+                const R cos_theta = -(Num<R>::min_(vdot(ud, h.n), R(1)));
+                const R sin_theta = Num<R>::sqrt_(R(1) - cos_theta * cos_theta);
+                bool refl = ri * sin_theta > R(1);
+                if (!refl) {
+                    R r0 = (R(1) - ri) / (R(1) + ri);
+                    r0 = r0 * r0;
+                    const R x = R(1) - cos_theta;
+                    const R x2 = x * x;
+                    const R x5 = x * (x2 * x2);
+                    refl = (r0 + (R(1) - r0) * x5) > g.next();
+                }
+                nd = refl ? vreflect(ud, h.n) : vrefract(ud, h.n, ri);
+                alive = true;
+            }
+            // ray_color(depth == 0) returns black: a path that has used max_depth hits contributes nothing
+            if (bounce >= max_depth) alive = false;
+            if (alive) {
+                const V3<R> thr = col_mul(V3<R>{p.tr, p.tg, p.tb}, att, cl);
+                p.ox = h.p.x; p.oy = h.p.y; p.oz = h.p.z;
+                p.dx = nd.x; p.dy = nd.y; p.dz = nd.z;
+                p.tr = thr.x; p.tg = thr.y; p.tb = thr.z;
+                p.bounce = bounce;
+                p.ref = REF_MISS;
+            }
+        }
+        const uint32_t pos = warp_append(&ctl->out_count[nxt], alive);
+        if (alive) store_path(out + pos, p);
+    }
+}
+
+// resolve: average_samples (ray_casting.rs:154-173) + Display for Color (utils.rs:422-438)
+static __global__ void k_resolve(const unsigned long long* __restrict__ fb, uint32_t npix_local, uint32_t W, uint32_t row_block,
+                          uint32_t row_rank, uint32_t row_world, int packed, double inv_scale, double spp, int clamp_out,
+                          double* __restrict__ out_rgb, uint8_t* __restrict__ out_rgb8) {
+    for (uint32_t lp = blockIdx.x * blockDim.x + threadIdx.x; lp < npix_local; lp += gridDim.x * blockDim.x) {
+        const uint32_t lrow = lp / W, i = lp % W;
+        const uint32_t j = packed ? lrow : local_to_global_row(lrow, row_block, row_rank, row_world);
+        const size_t o = ((size_t)j * W + i) * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            double v = (double)fb[3ull * lp + c] * inv_scale;
+            v = v / spp;
+            if (clamp_out) v = v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v);
+            if (out_rgb) out_rgb[o + c] = v;
+            if (out_rgb8) {
+                const double b = 255.0 * sqrt(v);
+                out_rgb8[o + c] = (uint8_t)(b >= 255.0 ? 255u : (uint32_t)b);
+            }
+        }
+    }
+}
+
+// trace_batch: Hittables::hit on caller-supplied rays, full HitRecord out
+template <typename R, bool EXACT>
+__global__ void __launch_bounds__(TRACE_BLOCK) k_trace_batch(DevScene<R> sc, const double* __restrict__ rays, size_t n, double tmin,
+                                                              double tmax, CrHit* __restrict__ out) {
+    __shared__ uint32_t s_stack[MAX_STACK * TRACE_BLOCK];
+    uint32_t* stack = s_stack + threadIdx.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const double* r = rays + 7 * i;
+        const V3<R> o = {(R)r[0], (R)r[1], (R)r[2]}, d = {(R)r[3], (R)r[4], (R)r[5]};
+        uint32_t ref;
+        R t;
+        closest_hit<R, EXACT>(sc, o, d, (R)tmin, (R)tmax, stack, TRACE_BLOCK, ref, t);
+        CrHit h;
+        if (ref == REF_MISS) {
+            h.prim_index = -1; h.obj_id = -1; h.front_face = 0; h.material = -1;
+            h.t = 0.0; h.p[0] = h.p[1] = h.p[2] = 0.0; h.n[0] = h.n[1] = h.n[2] = 0.0; h.u = h.v = 0.0;
+        } else {
+            const HitInfo<R> hi = finalize_hit<R>(sc, ref, t, o, d);
+            h.prim_index = hi.prim_index; h.obj_id = hi.obj_id; h.front_face = hi.front ? 1 : 0; h.material = hi.material;
+            h.t = (double)t;
+            h.p[0] = (double)hi.p.x; h.p[1] = (double)hi.p.y; h.p[2] = (double)hi.p.z;
+            h.n[0] = (double)hi.n.x; h.n[1] = (double)hi.n.y; h.n[2] = (double)hi.n.z;
+            h.u = (double)hi.u; h.v = (double)hi.v;
+        }
+        out[i] = h;
+    }
+}
+
+// ---- host side: typed view of the scene + wavefront driver -----------------------------------------
+template <typename R>
+static DevScene<R> make_dev_scene(const SceneDeviceData& s) {
+    DevScene<R> d;
+    const int k = (sizeof(R) == 8) ? 0 : 1;
+    d.nodes = reinterpret_cast<const NodeRec<R>*>(s.nodes[k]);
+    d.spheres = reinterpret_cast<const SphereRec<R>*>(s.spheres[k]);
+    d.tris = reinterpret_cast<const TriRec<R>*>(s.tris[k]);
+    d.quads = reinterpret_cast<const QuadRec<R>*>(s.quads[k]);
+    for (int i = 0; i < 3; ++i) d.meta[i] = s.meta[i];
+    d.mats = s.mats;
+    d.texs = s.texs;
+    d.images = s.images;
+    d.root = s.root;
+    d.sky_kind = s.sky_kind;
+    d.sky_image = s.sky_image;
+    d.clamp_colors = s.clamp_colors;
+    return d;
+}
+
+#define CRB_CUDA(call)                                                                        \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess) {                                                             \
+            err = std::string(#call) + ": " + cudaGetErrorString(e__);                        \
+            return CR_ERR_CUDA;                                                               \
+        }                                                                                     \
+    } while (0)
+
+template <typename F>
+static int persistent_grid(F kernel, int block, int num_sms) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    return per_sm * num_sms;  // a whole number of resident CTAs per SM (148 SMs on B200)
+}
+
+template <typename R>
+int trace_batch_impl(const SceneDeviceData& s, const double* d_rays, size_t n, double tmin, double tmax, CrHit* d_out,
+                     cudaStream_t stream, std::string& err) {
+    if (n == 0) return CR_OK;
+    constexpr bool EXACT = sizeof(R) == 8;
+    const DevScene<R> sc = make_dev_scene<R>(s);
+    int grid = persistent_grid(k_trace_batch<R, EXACT>, TRACE_BLOCK, s.num_sms);
+    const size_t need = (n + TRACE_BLOCK - 1) / TRACE_BLOCK;
+    if ((size_t)grid > need) grid = (int)need;
+    k_trace_batch<R, EXACT><<<grid, TRACE_BLOCK, 0, stream>>>(sc, d_rays, n, tmin, tmax, d_out);
+    CRB_CUDA(cudaGetLastError());
+    return CR_OK;
+}
+
+struct EventTimer {
+    bool on;
+    cudaStream_t st;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> spans[4];
+    void begin(int cls, cudaEvent_t& a) {
+        if (!on) return;
+        cudaEventCreate(&a);
+        cudaEventRecord(a, st);
+        (void)cls;
+    }
+    void end(int cls, cudaEvent_t a) {
+        if (!on) return;
+        cudaEvent_t b;
+        cudaEventCreate(&b);
+        cudaEventRecord(b, st);
+        spans[cls].push_back({a, b});
+    }
+    double total(int cls) {
+        double ms = 0;
+        for (auto& p : spans[cls]) {
+            float f = 0;
+            cudaEventElapsedTime(&f, p.first, p.second);
+            ms += f;
+            cudaEventDestroy(p.first);
+            cudaEventDestroy(p.second);
+        }
+        spans[cls].clear();
+        return ms;
+    }
+};
+
+template <typename R>
+int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in, const CrRenderOpts& opts, void* d_out_rgb,
+                void* d_out_rgb8, int packed, cudaStream_t stream, CrStats* stats, std::string& err) {
+    constexpr bool EXACT = sizeof(R) == 8;
+    const uint32_t W = cam_in.image_width, H = cam_in.image_height;
+    const uint32_t world = opts.row_world <= 1 ? 1 : opts.row_world;
+    const uint32_t block = opts.row_block == 0 ? 8 : opts.row_block;
+    const uint32_t rank = world == 1 ? 0 : opts.row_rank;
+    uint32_t rows_local = 0;
+    if (world == 1) {
+        rows_local = H;
+    } else {
+        for (uint32_t j = 0; j < H; ++j)
+            if ((j / block) % world == rank) ++rows_local;
+    }
+    const uint64_t npix = (uint64_t)W * rows_local;
+    const uint64_t total = npix * cam_in.samples;
+    uint32_t pool = opts.pool_paths ? opts.pool_paths : (1u << 20);
+    if (pool < 1024) pool = 1024;
+    if ((uint64_t)pool > total && total > 0) pool = (uint32_t)((total + 31) & ~31ull);
+    const uint32_t scale_bits = s.clamp_colors ? 44u : 32u;
+    const double fb_scale = (double)(1ull << scale_bits);
+
+    // workspace carve-up
+    size_t off = 0;
+    auto carve = [&](size_t bytes) {
+        size_t o = off;
+        off += (bytes + 255) & ~(size_t)255;
+        return o;
+    };
+    const size_t o_ctl = carve(sizeof(Control));
+    const size_t o_cam = carve(sizeof(DevCamera));
+    const size_t o_paths0 = carve((size_t)pool * sizeof(PathRec<R>));
+    const size_t o_paths1 = carve((size_t)pool * sizeof(PathRec<R>));
+    const size_t o_queues = carve((size_t)pool * Q_COUNT * sizeof(uint32_t));
+    const size_t o_fb = carve((size_t)npix * 3 * sizeof(unsigned long long));
+    int rc = ws.ensure(off, err);
+    if (rc != CR_OK) return rc;
+    char* base = static_cast<char*>(ws.ptr);
+    Control* ctl = reinterpret_cast<Control*>(base + o_ctl);
+    DevCamera* d_cam = reinterpret_cast<DevCamera*>(base + o_cam);
+    PathRec<R>* paths[2] = {reinterpret_cast<PathRec<R>*>(base + o_paths0), reinterpret_cast<PathRec<R>*>(base + o_paths1)};
+    uint32_t* queues = reinterpret_cast<uint32_t*>(base + o_queues);
+    unsigned long long* fb = reinterpret_cast<unsigned long long*>(base + o_fb);
+
+    if (!ws.pinned) {
+        CRB_CUDA(cudaHostAlloc(&ws.pinned, 4096, cudaHostAllocDefault));
+    }
+    DevCamera hcam;
+    memset(&hcam, 0, sizeof(hcam));
+    hcam.c = cam_in;
+    hcam.row_block = block;
+    hcam.row_rank = rank;
+    hcam.row_world = world;
+    hcam.rows_local = rows_local;
+    hcam.seed = opts.seed;
+    hcam.fb_scale_bits = scale_bits;
+    Control hctl;
+    memset(&hctl, 0, sizeof(hctl));
+    hctl.total_samples = total;
+    hctl.pool = pool;
+
+    cudaEvent_t ev_begin, ev_end;
+    CRB_CUDA(cudaEventCreate(&ev_begin));
+    CRB_CUDA(cudaEventCreate(&ev_end));
+    CRB_CUDA(cudaEventRecord(ev_begin, stream));
+    // staging copies come from pinned memory so they are truly asynchronous
+    char* pin = static_cast<char*>(ws.pinned);
+    memcpy(pin, &hctl, sizeof(hctl));
+    memcpy(pin + 512, &hcam, sizeof(hcam));
+    static_assert(sizeof(Control) <= 512 && sizeof(DevCamera) <= 3072, "pinned staging layout");
+    CRB_CUDA(cudaMemcpyAsync(ctl, pin, sizeof(hctl), cudaMemcpyHostToDevice, stream));
+    CRB_CUDA(cudaMemcpyAsync(d_cam, pin + 512, sizeof(hcam), cudaMemcpyHostToDevice, stream));
+    CRB_CUDA(cudaMemsetAsync(fb, 0, (size_t)npix * 3 * sizeof(unsigned long long), stream));
+
+    const DevScene<R> sc = make_dev_scene<R>(s);
+    const int g_trace = persistent_grid(k_trace<R, EXACT>, TRACE_BLOCK, s.num_sms);
+    const int g_gen = persistent_grid(k_raygen<R>, SHADE_BLOCK, s.num_sms);
+    const int g_miss = persistent_grid(k_shade_miss<R>, SHADE_BLOCK, s.num_sms);
+    const int g_emit = persistent_grid(k_shade_emissive<R>, SHADE_BLOCK, s.num_sms);
+    const int g_lam = persistent_grid(k_shade_scatter<R, CR_MAT_LAMBERTIAN>, SHADE_BLOCK, s.num_sms);
+    const int g_met = persistent_grid(k_shade_scatter<R, CR_MAT_METAL>, SHADE_BLOCK, s.num_sms);
+    const int g_die = persistent_grid(k_shade_scatter<R, CR_MAT_DIELECTRIC>, SHADE_BLOCK, s.num_sms);
+
+    EventTimer tm;
+    tm.on = opts.time_kernels != 0;
+    tm.st = stream;
+    uint64_t launches = 0;
+    // n_in of iteration k lands in pinned slot k % RING; the host looks LAG iterations behind so the
+    // GPU always has work queued while the host decides whether the render is finished
+    constexpr int RING = 8, LAG = 3;
+    volatile uint32_t* h_n_in = reinterpret_cast<volatile uint32_t*>(pin + 3584);
+    uint32_t* d_n_in_ring = reinterpret_cast<uint32_t*>(pin + 3584);  // plan writes through zero-copy? no: device copy below
+    (void)d_n_in_ring;
+    cudaEvent_t ring_ev[RING];
+    for (int i = 0; i < RING; ++i) CRB_CUDA(cudaEventCreateWithFlags(&ring_ev[i], cudaEventDisableTiming));
+
+    cudaEvent_t a;
+    // prologue: plan + raygen fill side 0
+    tm.begin(2, a);
+    k_plan<<<1, 32, 0, stream>>>(ctl, 0, nullptr);
+    k_raygen<R><<<g_gen, SHADE_BLOCK, 0, stream>>>(ctl, d_cam, paths[0]);
+    tm.end(2, a);
+    launches += 2;
+    uint64_t it = 0;
+    bool done = (total == 0);
+    while (!done) {
+        const int cur = (int)(it & 1), nxt = cur ^ 1;
+        tm.begin(0, a);
+        k_trace<R, EXACT><<<g_trace, TRACE_BLOCK, 0, stream>>>(sc, paths[cur], ctl, cur, queues, pool);
+        tm.end(0, a);
+        tm.begin(1, a);
+        k_shade_miss<R><<<g_miss, SHADE_BLOCK, 0, stream>>>(sc, paths[cur], ctl, queues + (size_t)Q_MISS * pool, fb, fb_scale);
+        k_shade_scatter<R, CR_MAT_LAMBERTIAN><<<g_lam, SHADE_BLOCK, 0, stream>>>(sc, paths[cur], paths[nxt], ctl, nxt,
+                                                                                  queues + (size_t)Q_LAMBERTIAN * pool, d_cam);
+        k_shade_scatter<R, CR_MAT_METAL><<<g_met, SHADE_BLOCK, 0, stream>>>(sc, paths[cur], paths[nxt], ctl, nxt,
+                                                                             queues + (size_t)Q_METAL * pool, d_cam);
+        k_shade_scatter<R, CR_MAT_DIELECTRIC><<<g_die, SHADE_BLOCK, 0, stream>>>(sc, paths[cur], paths[nxt], ctl, nxt,
+                                                                                  queues + (size_t)Q_DIELECTRIC * pool, d_cam);
+        launches += 5;
+        if (!s.clamp_colors) {
+            k_shade_emissive<R><<<g_emit, SHADE_BLOCK, 0, stream>>>(sc, paths[cur], ctl, queues + (size_t)Q_EMISSIVE * pool, fb,
+                                                                    fb_scale);
+            ++launches;
+        }
+        tm.end(1, a);
+        tm.begin(2, a);
+        k_plan<<<1, 32, 0, stream>>>(ctl, nxt, nullptr);
+        k_raygen<R><<<g_gen, SHADE_BLOCK, 0, stream>>>(ctl, d_cam, paths[nxt]);
+        tm.end(2, a);
+        launches += 2;
+        const int slot = (int)(it % RING);
+        CRB_CUDA(cudaMemcpyAsync((void*)(h_n_in + slot), &ctl->n_in[nxt], sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+        CRB_CUDA(cudaEventRecord(ring_ev[slot], stream));
+        ++it;
+        if (it >= (uint64_t)LAG) {
+            const int old = (int)((it - LAG) % RING);
+            CRB_CUDA(cudaEventSynchronize(ring_ev[old]));
+            if (h_n_in[old] == 0) done = true;  // nothing left to trace after iteration it-LAG: later ones were no-ops
+        }
+        if (it > 100000000ull) {
+            err = "render: iteration limit";
+            return CR_ERR_LIMIT;
+        }
+    }
+    CRB_CUDA(cudaGetLastError());
+    // resolve
+    cudaEvent_t r0;
+    tm.begin(3, r0);
+    if (npix > 0) {
+        int g_res = (int)((npix + 255) / 256);
+        if (g_res > s.num_sms * 8) g_res = s.num_sms * 8;
+        k_resolve<<<g_res, 256, 0, stream>>>(fb, (uint32_t)npix, W, block, rank, world, packed, 1.0 / fb_scale,
+                                             (double)cam_in.samples, s.clamp_colors ? 0 : 1, static_cast<double*>(d_out_rgb),
+                                             static_cast<uint8_t*>(d_out_rgb8));
+        ++launches;
+    }
+    tm.end(3, r0);
+    CRB_CUDA(cudaMemcpyAsync(pin, ctl, sizeof(Control), cudaMemcpyDeviceToHost, stream));
+    CRB_CUDA(cudaEventRecord(ev_end, stream));
+    CRB_CUDA(cudaEventSynchronize(ev_end));
+    CRB_CUDA(cudaGetLastError());
+    for (int i = 0; i < RING; ++i) cudaEventDestroy(ring_ev[i]);
+    if (stats) {
+        Control fin;
+        memcpy(&fin, pin, sizeof(fin));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ev_begin, ev_end);
+        stats->samples = total;
+        stats->rays = fin.rays_traced;
+        stats->iterations = it;
+        stats->launches = launches;
+        stats->ms_total = ms;
+        stats->ms_trace = tm.total(0);
+        stats->ms_shade = tm.total(1);
+        stats->ms_raygen = tm.total(2);
+        stats->ms_resolve = tm.total(3);
+    } else {
+        for (int c = 0; c < 4; ++c) tm.total(c);
+    }
+    cudaEventDestroy(ev_begin);
+    cudaEventDestroy(ev_end);
+    return CR_OK;
+}
+
+}  // namespace crb

@@ -1,0 +1,65 @@
+// integrator.h — interface between the C-ABI layer (api.cu) and the two precision-specific
+// translation units (integrator_f64.cu compiled with -fmad=false, integrator_f32.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+
+#include "common.cuh"
+
+namespace crb {
+
+// Type-erased device pointers of a committed scene; index 0 = f64 records, 1 = f32 records.
+struct SceneDeviceData {
+    void* nodes[2] = {nullptr, nullptr};
+    void* spheres[2] = {nullptr, nullptr};
+    void* tris[2] = {nullptr, nullptr};
+    void* quads[2] = {nullptr, nullptr};
+    PrimMeta* meta[3] = {nullptr, nullptr, nullptr};
+    DevMaterial* mats = nullptr;
+    DevTexture* texs = nullptr;
+    DevImage* images = nullptr;
+    uint32_t root = REF_MISS;
+    int32_t sky_kind = CR_SKY_DEFAULT, sky_image = -1;
+    int32_t clamp_colors = 1;
+    int num_sms = 148;
+};
+
+// Grow-only device scratch owned by the CrScene (path pool, queues, fixed-point framebuffer).
+struct Workspace {
+    void* ptr = nullptr;
+    size_t bytes = 0;
+    void* pinned = nullptr;  // 4 KiB of pinned host memory for control-block staging
+    int ensure(size_t need, std::string& err) {
+        if (need <= bytes) return CR_OK;
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        bytes = 0;
+        cudaError_t e = cudaMalloc(&ptr, need);
+        if (e != cudaSuccess) {
+            err = std::string("cudaMalloc(workspace): ") + cudaGetErrorString(e);
+            return CR_ERR_CUDA;
+        }
+        bytes = need;
+        return CR_OK;
+    }
+    void release() {
+        if (ptr) cudaFree(ptr);
+        if (pinned) cudaFreeHost(pinned);
+        ptr = nullptr;
+        pinned = nullptr;
+        bytes = 0;
+    }
+};
+
+template <typename R>
+int render_impl(const SceneDeviceData&, Workspace&, const CrCamera&, const CrRenderOpts&, void* d_out_rgb, void* d_out_rgb8,
+                int packed, cudaStream_t, CrStats*, std::string& err);
+template <typename R>
+int trace_batch_impl(const SceneDeviceData&, const double* d_rays, size_t n, double tmin, double tmax, CrHit* d_out, cudaStream_t,
+                     std::string& err);
+
+// FMA micro-benchmarks (roofline denominators); defined in integrator_f32.cu
+int measure_fma_peak(int num_sms, double* fp64_tflops, double* fp32_tflops, std::string& err);
+
+}  // namespace crb

@@ -1,0 +1,86 @@
+"""Multi-GPU sharding of the render: one process per GPU, scene replicated, image rows
+sharded in interleaved blocks (stills) or whole frames (timeline animations).  The path has no data-path
+collective: every rank traces its own pixels; the only exchange is the framebuffer gather to rank 0
+(torch.distributed: NCCL over NVLink on GPUs, gloo in the CPU tests).  The RNG is keyed by the GLOBAL
+pixel index, so the assembled image is bit-identical for any world size.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import abi
+from .gpu import GpuScene, rows_of_rank
+
+
+def frames_of_rank(n_frames: int, rank: int, world: int):
+    """Whole-frame sharding for `render_movie` (scene/mod.rs:295-322): frame f -> rank f % world."""
+    return list(range(rank, n_frames, max(world, 1)))
+
+
+def gather_rows(local: torch.Tensor, height: int, row_block: int, rank: int, world: int, group=None, dst: int = 0):
+    """Assemble the full [H][W][C] image on `dst` from each rank's packed rows.
+
+    `local` is [rows_local][W][C] holding rows (j // row_block) % world == rank in ascending order.
+    Returns the full tensor on dst, None elsewhere.  world == 1 returns `local` unchanged."""
+    if world <= 1:
+        return local
+    counts = [len(rows_of_rank(height, row_block, r, world)) for r in range(world)]
+    assert local.shape[0] == counts[rank], (local.shape, counts, rank)
+    max_rows = max(counts)
+    send = local
+    if local.shape[0] != max_rows:  # NCCL gather wants equal shapes: pad the short ranks
+        send = torch.zeros((max_rows,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        send[: local.shape[0]] = local
+    send = send.contiguous()
+    if rank == dst:
+        bufs = [torch.empty_like(send) for _ in range(world)]
+        dist.gather(send, gather_list=bufs, dst=dst, group=group)
+        full = torch.empty((height,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        for r in range(world):
+            rows = torch.as_tensor(rows_of_rank(height, row_block, r, world), device=local.device, dtype=torch.long)
+            full[rows] = bufs[r][: counts[r]]
+        return full
+    dist.gather(send, gather_list=None, dst=dst, group=group)
+    return None
+
+
+def render_sharded(gs: GpuScene, cam: abi.CrCamera, rank: int, world: int, seed=1, precision=abi.CR_PRECISION_F64,
+                   row_block=8, pool_paths=0, time_kernels=False, group=None, want_rgb8=True):
+    """Render this rank's rows on its GPU and gather the framebuffer to rank 0 over NCCL.
+
+    Returns (rgb [H][W][3] f64 device tensor on rank 0 else None, rgb8 likewise, stats dict)."""
+    H, W = cam.image_height, cam.image_width
+    dev = torch.device("cuda", gs.device)
+    rows = rows_of_rank(H, row_block, rank, world)
+    local = torch.empty((len(rows), W, 3), dtype=torch.float64, device=dev)
+    local8 = torch.empty((len(rows), W, 3), dtype=torch.uint8, device=dev) if want_rgb8 else None
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    st = gs.render_device(cam, local.data_ptr(), local8.data_ptr() if want_rgb8 else 0, stream=stream, seed=seed,
+                          precision=precision, pool_paths=pool_paths, row_block=row_block, row_rank=rank,
+                          row_world=world, time_kernels=time_kernels)
+    full = gather_rows(local, H, row_block, rank, world, group)
+    full8 = gather_rows(local8, H, row_block, rank, world, group) if want_rgb8 else None
+    return full, full8, st
+
+
+def render_frames_sharded(gs: GpuScene, scene, rank: int, world: int, seed=1, precision=abi.CR_PRECISION_F64,
+                          pool_paths=0, on_frame=None):
+    """Timeline animation: each rank renders frames rank, rank+world, ...; no inter-GPU traffic.
+    `on_frame(frame, rgb8)` receives each finished frame (host array) of this rank."""
+    n = scene.compute_frame_count()
+    stats = []
+    cam = scene.scene_cam.to_abi()
+    for f in frames_of_rank(n, rank, world):
+        cam.frame = f  # Camera::next_frame advances by one per rendered image (camera/mod.rs:160-162)
+        _, rgb8, st = gs.render(cam, seed=seed, precision=precision, pool_paths=pool_paths, want_rgb=False)
+        if on_frame is not None:
+            on_frame(f, rgb8)
+        stats.append(st)
+    return stats
+
+
+def np_rows(full: np.ndarray, row_block: int, rank: int, world: int):
+    """Packed rows of `rank` taken from a full image (host helper for tests)."""
+    return full[rows_of_rank(full.shape[0], row_block, rank, world)]

@@ -1,0 +1,245 @@
+/*
+ * crucible_gpu.h — C ABI of the B200-native path-tracing backend for Crucible.
+ *
+ * This is the drop-in boundary: the entry points below are exactly what a
+ * `mod gpu` inside the Crucible crate would bind over `extern "C"` to replace the
+ * CPU sample loop of `Camera::render` (reference src/camera/mod.rs:270-317, the
+ * part between the PPM header and the write loop, :284-303).  Every function cites
+ * the reference item it replaces.  All citations are paths under the reference
+ * repository (kylittle/Crucible).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++ / torch types in any signature;
+ *   - every function returns 0 on success or a negative CrStatus; it never aborts
+ *     (the reference panics instead, e.g. src/camera/mod.rs:294,302,308);
+ *     `cr_last_error()` returns a thread-local message for the last failure;
+ *   - inputs are borrowed for the duration of the call (the library copies what it
+ *     needs to the device), outputs are caller-allocated;
+ *   - one host thread drives one CrScene; a CrScene lives on one CUDA device
+ *     (one process per GPU; multi-GPU jobs shard image rows or frames, see
+ *     CrRenderOpts.row_*);
+ *   - there is NO CPU fallback: with no CUDA device every compute entry point
+ *     fails with CR_ERR_NO_DEVICE.
+ *
+ * Numeric contract
+ *   - CR_PRECISION_F64 reproduces the reference's f64 arithmetic operation by
+ *     operation (no FMA contraction, reference traversal order): closest-hit
+ *     `prim_index` and `front_face` are bit-exact, t / normal / uv differ only
+ *     through libm (acos/atan2/asin) by a few ulp.
+ *   - CR_PRECISION_F32 is the fast path (f32 boxes and primitives, near-first
+ *     traversal); it is statistically equivalent, not bit-exact.
+ */
+#ifndef CRUCIBLE_GPU_H
+#define CRUCIBLE_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CrScene CrScene; /* opaque; owns host staging + device copies */
+
+typedef enum CrStatus {
+    CR_OK = 0,
+    CR_ERR_INVALID = -1,    /* bad argument (null pointer, index out of range, NaN where forbidden) */
+    CR_ERR_NO_DEVICE = -2,  /* no CUDA device / wrong architecture: there is no CPU fallback */
+    CR_ERR_CUDA = -3,       /* a CUDA runtime call failed; see cr_last_error() */
+    CR_ERR_STATE = -4,      /* call order violated (e.g. render before cr_scene_commit) */
+    CR_ERR_LIMIT = -5       /* a built-in limit was exceeded (BVH depth, texture nesting) */
+} CrStatus;
+
+/* ---- materials: reference src/materials/mod.rs:16-20 (+ Emissive extension) ---- */
+typedef enum CrMaterialKind {
+    CR_MAT_LAMBERTIAN = 0, /* src/materials/lambertian.rs:40-61 */
+    CR_MAT_METAL = 1,      /* src/materials/metal.rs:29-42 */
+    CR_MAT_DIELECTRIC = 2, /* src/materials/dielectric.rs:21-55 */
+    CR_MAT_EMISSIVE = 3    /* EXTENSION (absent in reference): emits `emit`, never scatters */
+} CrMaterialKind;
+
+typedef struct CrMaterial {
+    int32_t kind;        /* CrMaterialKind */
+    int32_t tex;         /* Lambertian: texture index (Lambertian.tex, lambertian.rs:17) */
+    double scatter_prob; /* Lambertian.scatter_prob (lambertian.rs:18); must be > 0 */
+    double albedo[3];    /* Metal.albedo (metal.rs:12) */
+    double fuzz;         /* Metal.fuzz (metal.rs:13), in [0,1] */
+    double ior;          /* Dielectric.refraction_index (dielectric.rs:10) */
+    double emit[3];      /* Emissive radiance (extension; unclamped) */
+} CrMaterial;
+
+/* ---- textures: reference src/textures/mod.rs:13-17 ---- */
+typedef enum CrTextureKind {
+    CR_TEX_SOLID = 0,   /* src/textures/solid_color.rs:25-27 */
+    CR_TEX_CHECKER = 1, /* src/textures/checker_texture.rs:39-51 (even/odd are texture indices) */
+    CR_TEX_IMAGE = 2    /* src/textures/image_texture.rs:23-32 (nearest texel of an RGB8 image) */
+} CrTextureKind;
+
+typedef struct CrTexture {
+    int32_t kind;     /* CrTextureKind */
+    int32_t even;     /* checker: texture index used when floor-sum is even */
+    int32_t odd;      /* checker: texture index used when floor-sum is odd */
+    int32_t image;    /* image: index returned by cr_scene_add_image */
+    double color[3];  /* solid: albedo, each in [0,1] */
+    double inv_scale; /* checker: 1.0/scale, computed by the caller as checker_texture.rs:24 does */
+} CrTexture;
+
+/* ---- sky: reference src/scene/mod.rs:19-26, src/camera/ray_casting.rs:133-151 ---- */
+typedef enum CrSkyKind {
+    CR_SKY_DEFAULT = 0,   /* white -> (0.5,0.7,1.0) lerp, ray_casting.rs:145-150 */
+    CR_SKY_SPHERICAL = 1, /* equirect image, nearest texel, ray_casting.rs:134-144 + scene/mod.rs:37-45 */
+    CR_SKY_BLACK = 2      /* EXTENSION for closed emissive scenes (Cornell box) */
+} CrSkyKind;
+
+/* ---- primitives ---- */
+typedef enum CrPrimKind {
+    CR_PRIM_SPHERE = 0,   /* src/objects/sphere.rs */
+    CR_PRIM_TRIANGLE = 1, /* src/objects/triangle.rs */
+    CR_PRIM_QUAD = 2      /* EXTENSION: parallelogram Q,u,v with a padded bbox */
+} CrPrimKind;
+
+/* ---- camera: reference src/camera/mod.rs:66-100 flattened ---- */
+typedef enum CrInterp { CR_NERP = 0, CR_LERP = 1 } CrInterp; /* src/timeline/mod.rs:100-104 */
+
+/* One translate keyframe of a camera timeline, already in the relative form the
+ * reference stores (src/timeline/transform_builder.rs:348-469): at time t it
+ * contributes  delta * s  on `axis`, with s = clamp((t-t0)/(t1-t0),0,1) for LERP and
+ * 1 for NERP, and only when t >= t0 (Interval::is_less || contains,
+ * src/timeline/mod.rs:239-243).  Keyframes are listed in the timeline's sorted order. */
+typedef struct CrKeyframe {
+    double t0, t1, delta;
+    int32_t axis;   /* 0,1,2 */
+    int32_t interp; /* CrInterp */
+} CrKeyframe;
+
+#define CR_MAX_CAM_KEYS 32
+
+typedef struct CrCamera {
+    uint32_t image_width, image_height; /* Viewport, camera/mod.rs:26-47 */
+    double viewport_width, viewport_height; /* fix_viewport, rendering_compute.rs:5-11 (host computes tan) */
+    double focus_dist;                      /* camera/mod.rs:81 */
+    double defocus_angle;                   /* radians; <= 0 disables the thin lens (ray_casting.rs:96) */
+    double defocus_radius;                  /* focus_dist * tan(defocus_angle/2), rendering_compute.rs:72-74 */
+    double vup[3];
+    double look_from[3], look_at[3];        /* InitTranslate of the two timelines */
+    double frame_rate;                      /* camera/mod.rs:95 */
+    uint32_t frame;                         /* camera/mod.rs:96 */
+    uint32_t samples;                       /* camera/mod.rs:84 */
+    uint32_t max_depth;                     /* camera/mod.rs:86 */
+    uint32_t n_from_keys, n_at_keys;
+    double shutter_angle;                   /* degrees, camera/mod.rs:99 */
+    CrKeyframe from_keys[CR_MAX_CAM_KEYS];  /* cam_translate_*("from"), scene_animator.rs:460-552 */
+    CrKeyframe at_keys[CR_MAX_CAM_KEYS];
+} CrCamera;
+
+typedef enum CrPrecision { CR_PRECISION_F64 = 0, CR_PRECISION_F32 = 1 } CrPrecision;
+
+typedef struct CrRenderOpts {
+    uint64_t seed;        /* Philox key; same seed => same image, for any GPU count */
+    int32_t precision;    /* CrPrecision */
+    uint32_t pool_paths;  /* wavefront pool size; 0 = default */
+    /* Row sharding for multi-GPU: this call renders only rows j with
+     * (j / row_block) % row_world == row_rank.  row_world = 0 or 1 renders everything.
+     * The RNG is keyed by the GLOBAL pixel index, so the union over ranks is
+     * bit-identical to a single-GPU render. */
+    uint32_t row_block, row_rank, row_world;
+    uint32_t time_kernels; /* 1 = bracket every kernel class with CUDA events (CrStats.ms_*) */
+} CrRenderOpts;
+
+typedef struct CrStats {
+    uint64_t samples;      /* camera samples generated (W*H*spp over the rows rendered) */
+    uint64_t rays;         /* ray segments traced = world.hit calls (primary + bounces) */
+    uint64_t iterations;   /* wavefront iterations */
+    uint64_t launches;     /* CUDA kernels launched by this call */
+    double ms_total;       /* device time of the whole call (CUDA events on the render stream) */
+    double ms_trace;       /* time_kernels=1: sum over trace launches */
+    double ms_shade;       /* time_kernels=1: shade + miss kernels */
+    double ms_raygen;      /* time_kernels=1: plan + raygen */
+    double ms_resolve;
+    double ms_h2d, ms_d2h; /* host-buffer entry points only */
+} CrStats;
+
+/* Result of a closest-hit query: the fields of HitRecord (src/objects/mod.rs:21-29)
+ * plus the ids defined in SURVEY 8b. prim_index = insertion index in the scene's flat
+ * element list (hidden primitives keep their slot); -1 = miss. */
+typedef struct CrHit {
+    int32_t prim_index;
+    int32_t obj_id;
+    int32_t front_face;
+    int32_t material;
+    double t;
+    double p[3];
+    double n[3];
+    double u, v;
+} CrHit;
+
+/* ---- lifetime ---- */
+/* Number of usable sm_100 devices (0 when CUDA is unavailable). */
+int cr_device_count(void);
+CrScene* cr_scene_create(int device);
+void cr_scene_destroy(CrScene*);
+const char* cr_last_error(void);
+const char* cr_version(void);
+
+/* ---- scene description (replaces crate-private access to Scene.elements,
+ *      src/scene/mod.rs:75-82, 159-230).  Each call APPENDS to the flat element list in
+ *      call order, exactly like Scene::add_element / load_asset, and returns the index of
+ *      the first appended primitive (>= 0) or a negative CrStatus. ---- */
+/* Sphere::new, sphere.rs:25-39: cxyz_r = [n][4] (centre, radius >= 0). */
+int64_t cr_scene_add_spheres(CrScene*, const double* cxyz_r, const int32_t* material,
+                             const int32_t* obj_id, size_t n);
+/* Triangle::new, triangle.rs:23-46: abc = [n][9]. */
+int64_t cr_scene_add_triangles(CrScene*, const double* abc, const int32_t* material,
+                               const int32_t* obj_id, size_t n);
+/* EXTENSION: quads Q,u,v = [n][9]. */
+int64_t cr_scene_add_quads(CrScene*, const double* quv, const int32_t* material,
+                           const int32_t* obj_id, size_t n);
+/* Scene::hide_element / show_element, scene/mod.rs:232-281 (per primitive). */
+int cr_scene_set_hidden(CrScene*, size_t prim_index, int hide);
+int cr_scene_set_materials(CrScene*, const CrMaterial*, size_t n);
+int cr_scene_set_textures(CrScene*, const CrTexture*, size_t n);
+/* RTWImage (asset_loader/img_loader.rs:9-13): rgb8 = [h][w][3]; returns the image index. */
+int cr_scene_add_image(CrScene*, const uint8_t* rgb8, int w, int h);
+/* Scene::load_default_skybox / load_spherical_skybox, scene/mod.rs:146-156. */
+int cr_scene_set_sky(CrScene*, int kind, int image);
+/* BVHWrapper::new_wrapper (bvhwrapper.rs:15-94) reproduced on the host, then flattened
+ * and uploaded.  Must be called after the last edit and before trace/render. */
+int cr_scene_commit(CrScene*);
+/* Introspection of the committed BVH (tests): node count, max depth, leaf order. */
+int cr_scene_bvh_info(const CrScene*, uint64_t* n_nodes, uint32_t* max_depth, uint64_t* n_visible);
+/* DFS leaf order of the committed BVH as prim_index values (cap entries at most). */
+int64_t cr_scene_bvh_leaf_order(const CrScene*, int32_t* out, size_t cap);
+
+/* ---- the hot path ---- */
+/* Replaces Hittables::hit (src/objects/mod.rs:118-125) on fixed ray batches.
+ * rays = [n][7] (origin, direction, time); interval (tmin,tmax) open as Interval::surrounds. */
+int cr_trace_batch(CrScene*, const double* rays, size_t n, double tmin, double tmax,
+                   int precision, CrHit* out);
+
+/* Replaces thread_setup .. join of Camera::render (camera/mod.rs:284-303): one averaged
+ * linear colour per pixel, row-major j then i (camera/mod.rs:306-311).
+ *   out_rgb  : [H][W][3] f64 linear mean (average_samples, ray_casting.rs:154-173), or NULL
+ *   out_rgb8 : [H][W][3] bytes floor(255*sqrt(c)) (Display for Color, utils.rs:422-438), or NULL
+ * With row sharding only the rows of this rank are written; the others are left untouched. */
+int cr_render(CrScene*, const CrCamera*, const CrRenderOpts*, double* out_rgb, uint8_t* out_rgb8,
+              CrStats* stats);
+/* Same, but the outputs are DEVICE pointers on the scene's device and the work is enqueued
+ * on `cuda_stream` (a cudaStream_t; NULL = the library's own stream).  The call returns
+ * after the stream has drained.  Used by the multi-GPU driver, which gathers rows over NCCL. */
+int cr_render_device(CrScene*, const CrCamera*, const CrRenderOpts*, void* d_out_rgb,
+                     void* d_out_rgb8, void* cuda_stream, CrStats* stats);
+
+/* ---- host helpers on the path ---- */
+/* TransformTimeline::combine_and_compute for a camera point (timeline/mod.rs:233-263):
+ * out = init + sum of keyframe contributions at time t. */
+int cr_camera_point_at(const double init[3], const CrKeyframe* keys, size_t n, double t, double out[3]);
+/* FP64 / FP32 FMA peak of the device measured with a register-resident micro-kernel
+ * (roofline denominators that MEASURED_PEAKS.json does not hold). TFLOP/s. */
+int cr_measure_fma_peak(int device, double* fp64_tflops, double* fp32_tflops);
+/* Philox4x32-10 block (tests pin it against the Random123 known answers). */
+void cr_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CRUCIBLE_GPU_H */
