@@ -16,6 +16,18 @@ pytestmark = pytest.mark.gpu
 TOL_F64 = 1e-11
 
 
+def assert_bytes_match(rgb, rgb8, ref, ref8):
+    """The byte conversion itself is exact (floor(255*sqrt(mean)), utils.rs:422-438).  Because the means
+    agree to 1e-11 rather than bit for bit, a byte may differ from the oracle's only where 255*sqrt(c)
+    sits within 1e-8 of an integer (e.g. the sky's blue channel, which is 1.0 -+ 1 ulp)."""
+    assert np.array_equal(rgb8, np.floor(255.0 * np.sqrt(rgb)).astype(np.uint8))
+    diff = rgb8 != ref8
+    if diff.any():
+        x = 255.0 * np.sqrt(ref[diff])
+        assert np.all(np.abs(x - np.round(x)) < 1e-8)
+        assert np.all(np.abs(rgb8[diff].astype(int) - ref8[diff].astype(int)) == 1)
+
+
 def _both(sc, gpu_device, oracle, **kw):
     desc, cam = sc.describe(), sc.scene_cam.to_abi()
     gs, orc = GpuScene(desc, gpu_device), oracle.OracleScene(desc)
@@ -37,7 +49,7 @@ def test_f64_render_matches_oracle_path_by_path(gpu_device, oracle, name, kw):
         assert bad.mean() < 1e-3
     else:
         assert np.abs(rgb - ref).max() <= TOL_F64
-        assert np.array_equal(rgb8, ref8)
+        assert_bytes_match(rgb, rgb8, ref, ref8)
 
 
 def test_f64_render_is_reproducible_and_pool_independent(gpu_device, oracle):
@@ -68,7 +80,7 @@ def test_moving_camera_and_motion_blur(gpu_device, oracle):
         rgb, rgb8, _ = gs.render(cam, seed=2)
         ref, ref8, _ = orc.render(cam, seed=2)
         assert np.abs(rgb - ref).max() <= TOL_F64
-        assert np.array_equal(rgb8, ref8)
+        assert_bytes_match(rgb, rgb8, ref, ref8)
 
 
 def test_depth_limit_and_single_sample(gpu_device, oracle):
