@@ -227,8 +227,13 @@ int upload_scene(CrScene* s) {
     d.sky_kind = s->sky_kind;
     d.sky_image = s->sky_image;
     d.clamp_colors = 1;
+    d.max_radiance = 1.0;
     for (auto& m : s->mats)
-        if (m.kind == CR_MAT_EMISSIVE) d.clamp_colors = 0;
+        if (m.kind == CR_MAT_EMISSIVE) {
+            d.clamp_colors = 0;
+            for (int k = 0; k < 3; ++k)
+                if (m.emit[k] > d.max_radiance) d.max_radiance = m.emit[k];
+        }
     // nodes
     {
         std::vector<NodeRec<double>> n64(s->nodes.size());

@@ -530,7 +530,9 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
     uint32_t pool = opts.pool_paths ? opts.pool_paths : (1u << 20);
     if (pool < 1024) pool = 1024;
     if ((uint64_t)pool > total && total > 0) pool = (uint32_t)((total + 31) & ~31ull);
-    const uint32_t scale_bits = s.clamp_colors ? 44u : 32u;
+    // u64 fixed point: 2^-44 resolution unless max_radiance * spp would overflow 62 bits
+    uint32_t scale_bits = 44u;
+    while (scale_bits > 8u && s.max_radiance * (double)cam_in.samples * (double)(1ull << scale_bits) >= 4.0e18) --scale_bits;
     const double fb_scale = (double)(1ull << scale_bits);
 
     // workspace carve-up

@@ -22,6 +22,7 @@ struct SceneDeviceData {
     uint32_t root = REF_MISS;
     int32_t sky_kind = CR_SKY_DEFAULT, sky_image = -1;
     int32_t clamp_colors = 1;
+    double max_radiance = 1.0;  // largest per-sample colour component (1 unless the scene holds an Emissive)
     int num_sms = 148;
 };
 
