@@ -714,7 +714,7 @@ int cr_trace_batch(CrScene* s, const double* rays, size_t n, double tmin, double
     if (n == 0) return CR_OK;
     API_CUDA(cudaSetDevice(s->device));
     const size_t bytes_in = n * 7 * sizeof(double), bytes_out = n * sizeof(CrHit);
-    const size_t need = ((bytes_in + 255) & ~(size_t)255) + bytes_out;
+    const size_t need = ((bytes_in + 255) & ~(size_t)255) + ((bytes_out + 255) & ~(size_t)255) + 256;
     if (need > s->io_cap) {
         if (s->d_io) cudaFree(s->d_io);
         s->d_io = nullptr;
@@ -724,10 +724,11 @@ int cr_trace_batch(CrScene* s, const double* rays, size_t n, double tmin, double
     }
     double* d_rays = static_cast<double*>(s->d_io);
     CrHit* d_out = reinterpret_cast<CrHit*>(static_cast<char*>(s->d_io) + ((bytes_in + 255) & ~(size_t)255));
+    uint32_t* d_cursor = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(d_out) + ((bytes_out + 255) & ~(size_t)255));
     API_CUDA(cudaMemcpyAsync(d_rays, rays, bytes_in, cudaMemcpyHostToDevice, s->stream));
     std::string err;
-    rc = (precision == CR_PRECISION_F64) ? trace_batch_impl<double>(s->dev, d_rays, n, tmin, tmax, d_out, s->stream, err)
-                                         : trace_batch_impl<float>(s->dev, d_rays, n, tmin, tmax, d_out, s->stream, err);
+    rc = (precision == CR_PRECISION_F64) ? trace_batch_impl<double>(s->dev, d_rays, n, tmin, tmax, d_out, d_cursor, s->stream, err)
+                                         : trace_batch_impl<float>(s->dev, d_rays, n, tmin, tmax, d_out, d_cursor, s->stream, err);
     if (rc != CR_OK) return fail(rc, err);
     API_CUDA(cudaMemcpyAsync(out, d_out, bytes_out, cudaMemcpyDeviceToHost, s->stream));
     API_CUDA(cudaStreamSynchronize(s->stream));

@@ -271,7 +271,8 @@ template <typename R>
 __device__ __forceinline__ HitInfo<R> finalize_hit(const DevScene<R>& sc, uint32_t ref, R t, V3<R> o, V3<R> d) {
     HitInfo<R> h;
     const uint32_t kind = ref_kind(ref), idx = ref_index(ref);
-    const PrimMeta m = sc.meta[kind][idx];
+    const PrimMeta* mp = kind == CR_PRIM_SPHERE ? sc.meta[0] : (kind == CR_PRIM_TRIANGLE ? sc.meta[1] : sc.meta[2]);
+    const PrimMeta m = mp[idx];
     h.material = m.material;
     h.mat_kind = m.mat_kind;
     h.prim_index = m.prim_index;
@@ -308,59 +309,171 @@ __device__ __forceinline__ HitInfo<R> finalize_hit(const DevScene<R>& sc, uint32
 // ONE running closest-t: a later primitive only wins when strictly closer, inner boxes are tested with
 // the running interval at the time they are entered, leaves are tested with no box of their own.
 // EXACT = reference order (always left first).  !EXACT = near child first along the split axis.
-template <typename R, bool EXACT>
-__device__ __forceinline__ void closest_hit(const DevScene<R>& sc, V3<R> o, V3<R> d, R tmin, R tmax, uint32_t* stack,
-                                            int stride, uint32_t& best_ref, R& best_t) {
-    best_ref = REF_MISS;
-    best_t = tmax;
-    if (sc.root == REF_MISS) return;
-    const V3<R> inv = {R(1) / d.x, R(1) / d.y, R(1) / d.z};  // adinv, bvh.rs:111
-    const R a = vlen2(d);                                     // sphere.rs:74
-    int sp = 0;
-    uint32_t cur = sc.root;
-    for (;;) {
-        if (!ref_is_leaf(cur)) {
-            const NodeRec<R> n = ldg_rec<sizeof(NodeRec<R>) / 16>(sc.nodes + cur);
-            if (aabb_hit(n, o, inv, tmin, best_t)) {
-                uint32_t first = n.left & ~AXIS_MASK, second = n.right;
-                if (!EXACT) {
-                    const uint32_t ax = (n.left & AXIS_MASK) >> AXIS_SHIFT;
-                    const R dd = ax == 0 ? d.x : (ax == 1 ? d.y : d.z);
-                    if (dd < R(0) && second != REF_NONE) {
-                        second = first;
-                        first = n.right;
-                    }
-                }
-                if (second != REF_NONE) {
-                    stack[sp * stride] = second;
-                    ++sp;
-                }
-                cur = first;
-                continue;
-            }
-        } else {
-            const uint32_t kind = ref_kind(cur), idx = ref_index(cur);
-            R t;
-            bool got;
-            if (kind == CR_PRIM_SPHERE) {
-                const SphereRec<R> s = ldg_rec<sizeof(SphereRec<R>) / 16>(sc.spheres + idx);
-                got = sphere_hit_t(s, o, d, a, tmin, best_t, t);
-            } else if (kind == CR_PRIM_TRIANGLE) {
-                const TriRec<R> tr = ldg_rec<sizeof(TriRec<R>) / 16>(sc.tris + idx);
-                got = tri_hit_t(tr, o, d, tmin, best_t, t);
-            } else {
-                const QuadRec<R> q = ldg_rec<sizeof(QuadRec<R>) / 16>(sc.quads + idx);
-                R al, be;
-                got = quad_hit_t(q, o, d, tmin, best_t, t, al, be);
-            }
-            if (got) {
-                best_t = t;
-                best_ref = cur;
-            }
-        }
-        if (sp == 0) break;
+//
+// Branch-free box test for REGULAR rays (every origin/direction component finite, every 1/d finite and
+// non-zero).  For such rays t0, t1 are never NaN, so the reference's comparison form reduces to
+//   lo = max(tmin, min(t0,t1) per axis), hi = min(tmax, max(t0,t1) per axis), hit <=> hi > lo
+// and `t0 < t1` is decided by the sign of 1/d (equal values make both arms identical).  The per-axis
+// early exits of bvh.rs:127-129 are implied: lo only grows and hi only shrinks, so an intermediate
+// `hi <= lo` stays true to the end.  Decisions are therefore IDENTICAL to aabb_hit(); irregular rays
+// (axis parallel, NaN, inf) take aabb_hit() itself.
+template <typename R>
+__device__ __forceinline__ bool aabb_hit_regular(const NodeRec<R>& n, V3<R> o, V3<R> inv, bool px, bool py, bool pz, R tmin,
+                                                 R tmax) {
+    const R x0 = (n.xmin - o.x) * inv.x, x1 = (n.xmax - o.x) * inv.x;
+    const R y0 = (n.ymin - o.y) * inv.y, y1 = (n.ymax - o.y) * inv.y;
+    const R z0 = (n.zmin - o.z) * inv.z, z1 = (n.zmax - o.z) * inv.z;
+    const R lx = px ? x0 : x1, hx = px ? x1 : x0;
+    const R ly = py ? y0 : y1, hy = py ? y1 : y0;
+    const R lz = pz ? z0 : z1, hz = pz ? z1 : z0;
+    R lo = (lx > tmin) ? lx : tmin;
+    R hi = (hx < tmax) ? hx : tmax;
+    lo = (ly > lo) ? ly : lo;
+    hi = (hy < hi) ? hy : hi;
+    lo = (lz > lo) ? lz : lo;
+    hi = (hz < hi) ? hz : hi;
+    return hi > lo;
+}
+template <typename R>
+__device__ __forceinline__ bool is_finite(R x) {
+    return Num<R>::abs_(x) < Num<R>::inf();
+}
+
+// Per-lane traversal state.  One step functions are shared by the render trace kernel and by
+// cr_trace_batch, so the parity-tested code IS the code that renders.
+template <typename R>
+struct Trav {
+    V3<R> o, d, inv;
+    R a, tmin, best_t;
+    uint32_t best_ref, cur;
+    int sp;
+    bool px, py, pz, regular;
+    __device__ __forceinline__ void init(V3<R> o_, V3<R> d_, R tmin_, R tmax_, uint32_t root) {
+        o = o_;
+        d = d_;
+        inv = {R(1) / d.x, R(1) / d.y, R(1) / d.z};  // adinv, bvh.rs:111 (a pure function of the ray)
+        a = vlen2(d);                                // sphere.rs:74
+        tmin = tmin_;
+        best_t = tmax_;
+        best_ref = REF_MISS;
+        cur = root;
+        sp = 0;
+        px = inv.x > R(0);
+        py = inv.y > R(0);
+        pz = inv.z > R(0);
+        regular = is_finite(o.x) && is_finite(o.y) && is_finite(o.z) && is_finite(inv.x) && is_finite(inv.y) && is_finite(inv.z) &&
+                  inv.x != R(0) && inv.y != R(0) && inv.z != R(0) && !(tmin != tmin) && !(best_t != best_t);
+    }
+    // pops the next reference; false when the walk is complete
+    __device__ __forceinline__ bool pop(const uint32_t* stack, int stride) {
+        if (sp == 0) return false;
         --sp;
         cur = stack[sp * stride];
+        return true;
+    }
+    // cur is an inner node: box test, descend left (or near) and push the other child.  Returns false
+    // when the walk is complete.
+    template <bool EXACT>
+    __device__ __forceinline__ bool step_node(const DevScene<R>& sc, uint32_t* stack, int stride) {
+        const NodeRec<R> n = ldg_rec<sizeof(NodeRec<R>) / 16>(sc.nodes + cur);
+        const bool hit = regular ? aabb_hit_regular(n, o, inv, px, py, pz, tmin, best_t) : aabb_hit(n, o, inv, tmin, best_t);
+        if (hit) {
+            uint32_t first = n.left & ~AXIS_MASK, second = n.right;
+            if (!EXACT) {
+                const uint32_t ax = (n.left & AXIS_MASK) >> AXIS_SHIFT;
+                const bool pos = ax == 0 ? px : (ax == 1 ? py : pz);
+                if (!pos && second != REF_NONE) {
+                    second = first;
+                    first = n.right;
+                }
+            }
+            if (second != REF_NONE) {
+                stack[sp * stride] = second;
+                ++sp;
+            }
+            cur = first;
+            return true;
+        }
+        return pop(stack, stride);
+    }
+    // cur is a leaf: primitive test with the running interval (no box of its own), then pop
+    __device__ __forceinline__ bool step_leaf(const DevScene<R>& sc, const uint32_t* stack, int stride) {
+        const uint32_t kind = ref_kind(cur), idx = ref_index(cur);
+        R t;
+        bool got;
+        if (kind == CR_PRIM_SPHERE) {
+            const SphereRec<R> s = ldg_rec<sizeof(SphereRec<R>) / 16>(sc.spheres + idx);
+            got = sphere_hit_t(s, o, d, a, tmin, best_t, t);
+        } else if (kind == CR_PRIM_TRIANGLE) {
+            const TriRec<R> tr = ldg_rec<sizeof(TriRec<R>) / 16>(sc.tris + idx);
+            got = tri_hit_t(tr, o, d, tmin, best_t, t);
+        } else {
+            const QuadRec<R> q = ldg_rec<sizeof(QuadRec<R>) / 16>(sc.quads + idx);
+            R al, be;
+            got = quad_hit_t(q, o, d, tmin, best_t, t, al, be);
+        }
+        if (got) {
+            best_t = t;
+            best_ref = cur;
+        }
+        return pop(stack, stride);
+    }
+};
+
+// Warp-persistent closest-hit engine: "while-while" traversal (all lanes walk inner nodes, then all
+// lanes test their leaf) with lane refill: as soon as REFILL lanes are idle the warp commits their
+// results and fetches that many new rays with ONE atomic (warp-level work fetch), so the SIMD lanes
+// stay occupied although rays differ wildly in trip count.
+//   IO::count()                      number of rays
+//   IO::cursor()                     global work cursor (uint32_t*)
+//   IO::load(i, o, d)                ray i
+//   IO::commit(has, i, ref, t, o, d) called warp-synchronously by all 32 lanes; `has` marks lanes holding a result
+template <typename R, bool EXACT, int REFILL, typename IO>
+__device__ __forceinline__ void trace_persistent(const DevScene<R>& sc, uint32_t* stack, int stride, R tmin, R tmax, IO& io) {
+    const uint32_t n = io.count();
+    const int lane = threadIdx.x & 31;
+    Trav<R> tv;
+    tv.regular = true;
+    tv.cur = REF_MISS;
+    tv.sp = 0;
+    tv.best_ref = REF_MISS;
+    tv.best_t = tmax;
+    uint32_t my = 0;
+    int st = 0;  // 0 = idle, 1 = walking, 2 = result pending
+    bool exhausted = false;
+    for (;;) {
+        const uint32_t walking = __ballot_sync(0xffffffffu, st == 1);
+        const int n_free = 32 - __popc(walking);
+        if ((!exhausted && n_free >= REFILL) || walking == 0u) {  // warp-uniform
+            io.commit(st == 2, my, tv.best_ref, tv.best_t, tv.o, tv.d);
+            if (st == 2) st = 0;
+            if (!exhausted) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(io.cursor(), (uint32_t)n_free);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (st == 0) {
+                    const uint32_t i = base + (uint32_t)__popc(~walking & ((1u << lane) - 1u));
+                    if (i < n) {
+                        V3<R> o, d;
+                        io.load(i, o, d);
+                        my = i;
+                        tv.init(o, d, tmin, tmax, sc.root);
+                        st = (sc.root == REF_MISS) ? 2 : 1;
+                    }
+                }
+                if (base + (uint32_t)n_free >= n) exhausted = true;
+            }
+            if (__ballot_sync(0xffffffffu, st != 0) == 0u) break;  // nothing walking, nothing pending
+            if (__ballot_sync(0xffffffffu, st == 1) == 0u) continue;  // only pending results (empty world)
+        }
+        // phase 1: every walking lane advances through inner nodes until it holds a leaf (or finishes)
+        while (st == 1 && !ref_is_leaf(tv.cur)) {
+            if (!tv.template step_node<EXACT>(sc, stack, stride)) st = 2;
+        }
+        // phase 2: every walking lane tests its leaf primitive
+        if (st == 1) {
+            if (!tv.step_leaf(sc, stack, stride)) st = 2;
+        }
     }
 }
 

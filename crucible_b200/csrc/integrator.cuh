@@ -5,6 +5,7 @@
 // Replaces Camera::cast_ray / ray_color / average_samples (src/camera/ray_casting.rs:64-173) and the
 // worker pool of src/camera/cpu_threading.rs:25-115.
 #pragma once
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -26,6 +27,23 @@ static __device__ __forceinline__ uint32_t warp_append(uint32_t* counter, bool p
     if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(mask));
     base = __shfl_sync(0xffffffffu, base, leader);
     return base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
+}
+
+// Enqueue every lane with q >= 0 into queue q: Q_COUNT ballots, then lanes 0..Q_COUNT-1 each issue the ONE
+// atomic of "their" queue (distinct addresses, one instruction), bases come back by shuffle.
+static __device__ __forceinline__ uint32_t warp_enqueue(uint32_t* counts, int q) {
+    const int lane = threadIdx.x & 31;
+    uint32_t my_mask = 0, lane_cnt = 0;
+#pragma unroll
+    for (int k = 0; k < Q_COUNT; ++k) {
+        const uint32_t m = __ballot_sync(0xffffffffu, q == k);
+        if (q == k) my_mask = m;
+        if (lane == k) lane_cnt = (uint32_t)__popc(m);
+    }
+    uint32_t base = 0;
+    if (lane_cnt) base = atomicAdd(counts + lane, lane_cnt);
+    base = __shfl_sync(0xffffffffu, base, q < 0 ? 0 : q);
+    return base + (uint32_t)__popc(my_mask & ((1u << lane) - 1u));
 }
 
 // ---- textures (src/textures/*.rs) -------------------------------------------------------------------
@@ -207,54 +225,60 @@ __global__ void __launch_bounds__(SHADE_BLOCK) k_raygen(const Control* __restric
     }
 }
 
-// trace: persistent threads, warp-level work fetch (lane 0 grabs 32 rays), traversal stack in shared
-// memory ([depth][thread], conflict free), 128-bit node / primitive loads, then classification of the
-// ray into its material queue with one atomic per warp per queue.
-template <typename R, bool EXACT>
+// trace: persistent threads with warp-level work fetch and lane refill (trace_persistent), traversal
+// stack in shared memory ([depth][thread], conflict free), 128-bit node / primitive loads, then
+// classification of the finished rays into their material queues with one atomic per warp per queue.
+#ifndef CRB_REFILL
+#define CRB_REFILL 12
+#endif
+template <typename R>
+struct RenderTraceIO {
+    const DevScene<R>& sc;
+    PathRec<R>* paths;
+    Control* ctl;
+    uint32_t* queues;
+    uint32_t n, pool;
+    __device__ __forceinline__ uint32_t count() const { return n; }
+    __device__ __forceinline__ uint32_t* cursor() const { return &ctl->trace_next; }
+    __device__ __forceinline__ void load(uint32_t i, V3<R>& o, V3<R>& d) const {
+        const PathRec<R>* p = paths + i;  // the first 48 (24) bytes of the record: origin + direction
+        if constexpr (sizeof(R) == 8) {
+            const double2 a = *reinterpret_cast<const double2*>(&p->ox);
+            const double2 b = *reinterpret_cast<const double2*>(&p->oz);
+            const double2 c = *reinterpret_cast<const double2*>(&p->dy);
+            o = {a.x, a.y, b.x};
+            d = {b.y, c.x, c.y};
+        } else {
+            const float4 a = *reinterpret_cast<const float4*>(&p->ox);
+            const float2 b = *reinterpret_cast<const float2*>(&p->dy);
+            o = {a.x, a.y, a.z};
+            d = {a.w, b.x, b.y};
+        }
+    }
+    __device__ __forceinline__ void commit(bool has, uint32_t i, uint32_t ref, R t, V3<R>, V3<R>) const {
+        int q = -1;
+        if (has) {
+            paths[i].t = t;
+            paths[i].ref = ref;
+            if (ref == REF_MISS) {
+                q = Q_MISS;
+            } else {
+                const uint32_t kind = ref_kind(ref);
+                const PrimMeta* m = kind == CR_PRIM_SPHERE ? sc.meta[0] : (kind == CR_PRIM_TRIANGLE ? sc.meta[1] : sc.meta[2]);
+                q = (int)Q_LAMBERTIAN + m[ref_index(ref)].mat_kind;
+            }
+        }
+        const uint32_t pos = warp_enqueue(ctl->queue_count, q);
+        if (q >= 0) queues[(size_t)q * pool + pos] = i;
+    }
+};
+
+template <typename R, bool EXACT, int REFILL>
 __global__ void __launch_bounds__(TRACE_BLOCK) k_trace(DevScene<R> sc, PathRec<R>* __restrict__ paths, Control* __restrict__ ctl,
                                                         int side, uint32_t* __restrict__ queues, uint32_t pool) {
     __shared__ uint32_t s_stack[MAX_STACK * TRACE_BLOCK];
-    const uint32_t n = ctl->n_in[side];
-    const int lane = threadIdx.x & 31;
-    uint32_t* stack = s_stack + threadIdx.x;
-    for (;;) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(&ctl->trace_next, 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n) break;
-        const uint32_t i = base + lane;
-        const bool valid = i < n;
-        int q = -1;
-        if (valid) {
-            // the first 48 (24) bytes of the record: origin + direction
-            PathRec<R>* p = paths + i;
-            V3<R> o, d;
-            if constexpr (sizeof(R) == 8) {
-                const double2 a = *reinterpret_cast<const double2*>(&p->ox);
-                const double2 b = *reinterpret_cast<const double2*>(&p->oz);
-                const double2 c = *reinterpret_cast<const double2*>(&p->dy);
-                o = {a.x, a.y, b.x};
-                d = {b.y, c.x, c.y};
-            } else {
-                const float4 a = *reinterpret_cast<const float4*>(&p->ox);
-                const float2 b = *reinterpret_cast<const float2*>(&p->dy);
-                o = {a.x, a.y, a.z};
-                d = {a.w, b.x, b.y};
-            }
-            uint32_t ref;
-            R t;
-            closest_hit<R, EXACT>(sc, o, d, R(0.001), Num<R>::inf(), stack, TRACE_BLOCK, ref, t);  // ray_casting.rs:119
-            p->t = t;
-            p->ref = ref;
-            q = (ref == REF_MISS) ? (int)Q_MISS : (int)Q_LAMBERTIAN + sc.meta[ref_kind(ref)][ref_index(ref)].mat_kind;
-        }
-#pragma unroll
-        for (int k = 0; k < Q_COUNT; ++k) {
-            const bool mine = (q == k);
-            const uint32_t pos = warp_append(&ctl->queue_count[k], mine);
-            if (mine) queues[(size_t)k * pool + pos] = i;
-        }
-    }
+    RenderTraceIO<R> io{sc, paths, ctl, queues, ctl->n_in[side], pool};
+    trace_persistent<R, EXACT, REFILL>(sc, s_stack + threadIdx.x, TRACE_BLOCK, R(0.001), Num<R>::inf(), io);  // ray_casting.rs:119
 }
 
 // fixed-point accumulation: order independent => bit-reproducible for any schedule and GPU count
@@ -305,7 +329,8 @@ __global__ void __launch_bounds__(SHADE_BLOCK) k_shade_emissive(DevScene<R> sc, 
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         PathRec<R> p;
         load_path(in + queue[k], p);
-        const PrimMeta m = sc.meta[ref_kind(p.ref)][ref_index(p.ref)];
+        const uint32_t kind = ref_kind(p.ref);
+        const PrimMeta m = (kind == CR_PRIM_SPHERE ? sc.meta[0] : (kind == CR_PRIM_TRIANGLE ? sc.meta[1] : sc.meta[2]))[ref_index(p.ref)];
         const DevMaterial& mat = sc.mats[m.material];
         fb_add(fb, p.fb, (double)(p.tr * (R)mat.emit[0]), (double)(p.tg * (R)mat.emit[1]), (double)(p.tb * (R)mat.emit[2]),
                fb_scale);
@@ -401,18 +426,24 @@ static __global__ void k_resolve(const unsigned long long* __restrict__ fb, uint
     }
 }
 
-// trace_batch: Hittables::hit on caller-supplied rays, full HitRecord out
-template <typename R, bool EXACT>
-__global__ void __launch_bounds__(TRACE_BLOCK) k_trace_batch(DevScene<R> sc, const double* __restrict__ rays, size_t n, double tmin,
-                                                              double tmax, CrHit* __restrict__ out) {
-    __shared__ uint32_t s_stack[MAX_STACK * TRACE_BLOCK];
-    uint32_t* stack = s_stack + threadIdx.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const double* r = rays + 7 * i;
-        const V3<R> o = {(R)r[0], (R)r[1], (R)r[2]}, d = {(R)r[3], (R)r[4], (R)r[5]};
-        uint32_t ref;
-        R t;
-        closest_hit<R, EXACT>(sc, o, d, (R)tmin, (R)tmax, stack, TRACE_BLOCK, ref, t);
+// trace_batch: Hittables::hit on caller-supplied rays, full HitRecord out.  Same traversal engine as
+// the render path.
+template <typename R>
+struct BatchTraceIO {
+    const DevScene<R>& sc;
+    const double* rays;
+    CrHit* out;
+    uint32_t* cur;
+    uint32_t n;
+    __device__ __forceinline__ uint32_t count() const { return n; }
+    __device__ __forceinline__ uint32_t* cursor() const { return cur; }
+    __device__ __forceinline__ void load(uint32_t i, V3<R>& o, V3<R>& d) const {
+        const double* r = rays + 7ull * i;
+        o = {(R)r[0], (R)r[1], (R)r[2]};
+        d = {(R)r[3], (R)r[4], (R)r[5]};
+    }
+    __device__ __forceinline__ void commit(bool has, uint32_t i, uint32_t ref, R t, V3<R> o, V3<R> d) const {
+        if (!has) return;
         CrHit h;
         if (ref == REF_MISS) {
             h.prim_index = -1; h.obj_id = -1; h.front_face = 0; h.material = -1;
@@ -427,6 +458,13 @@ __global__ void __launch_bounds__(TRACE_BLOCK) k_trace_batch(DevScene<R> sc, con
         }
         out[i] = h;
     }
+};
+template <typename R, bool EXACT>
+__global__ void __launch_bounds__(TRACE_BLOCK) k_trace_batch(DevScene<R> sc, const double* __restrict__ rays, uint32_t n, double tmin,
+                                                              double tmax, CrHit* __restrict__ out, uint32_t* __restrict__ cursor) {
+    __shared__ uint32_t s_stack[MAX_STACK * TRACE_BLOCK];
+    BatchTraceIO<R> io{sc, rays, out, cursor, n};
+    trace_persistent<R, EXACT, CRB_REFILL>(sc, s_stack + threadIdx.x, TRACE_BLOCK, (R)tmin, (R)tmax, io);
 }
 
 // ---- host side: typed view of the scene + wavefront driver -----------------------------------------
@@ -467,14 +505,19 @@ static int persistent_grid(F kernel, int block, int num_sms) {
 
 template <typename R>
 int trace_batch_impl(const SceneDeviceData& s, const double* d_rays, size_t n, double tmin, double tmax, CrHit* d_out,
-                     cudaStream_t stream, std::string& err) {
+                     uint32_t* d_cursor, cudaStream_t stream, std::string& err) {
     if (n == 0) return CR_OK;
+    if (n > 0xFFFFFF00ull) {
+        err = "trace_batch: more than 2^32 rays in one call";
+        return CR_ERR_LIMIT;
+    }
     constexpr bool EXACT = sizeof(R) == 8;
     const DevScene<R> sc = make_dev_scene<R>(s);
     int grid = persistent_grid(k_trace_batch<R, EXACT>, TRACE_BLOCK, s.num_sms);
     const size_t need = (n + TRACE_BLOCK - 1) / TRACE_BLOCK;
     if ((size_t)grid > need) grid = (int)need;
-    k_trace_batch<R, EXACT><<<grid, TRACE_BLOCK, 0, stream>>>(sc, d_rays, n, tmin, tmax, d_out);
+    CRB_CUDA(cudaMemsetAsync(d_cursor, 0, sizeof(uint32_t), stream));
+    k_trace_batch<R, EXACT><<<grid, TRACE_BLOCK, 0, stream>>>(sc, d_rays, (uint32_t)n, tmin, tmax, d_out, d_cursor);
     CRB_CUDA(cudaGetLastError());
     return CR_OK;
 }
@@ -588,7 +631,13 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
     CRB_CUDA(cudaMemsetAsync(fb, 0, (size_t)npix * 3 * sizeof(unsigned long long), stream));
 
     const DevScene<R> sc = make_dev_scene<R>(s);
-    const int g_trace = persistent_grid(k_trace<R, EXACT>, TRACE_BLOCK, s.num_sms);
+    // lane-refill threshold of the trace kernel (tuning knob; CRB_REFILL in the environment overrides)
+    typedef void (*TraceFn)(DevScene<R>, PathRec<R>*, Control*, int, uint32_t*, uint32_t);
+    int refill = CRB_REFILL;
+    if (const char* e = getenv("CRB_REFILL")) refill = atoi(e);
+    TraceFn trace_fn = refill <= 4 ? k_trace<R, EXACT, 4> : refill <= 8 ? k_trace<R, EXACT, 8> : refill <= 12 ? k_trace<R, EXACT, 12>
+                     : refill <= 16 ? k_trace<R, EXACT, 16> : refill <= 24 ? k_trace<R, EXACT, 24> : k_trace<R, EXACT, 32>;
+    const int g_trace = persistent_grid(trace_fn, TRACE_BLOCK, s.num_sms);
     const int g_gen = persistent_grid(k_raygen<R>, SHADE_BLOCK, s.num_sms);
     const int g_miss = persistent_grid(k_shade_miss<R>, SHADE_BLOCK, s.num_sms);
     const int g_emit = persistent_grid(k_shade_emissive<R>, SHADE_BLOCK, s.num_sms);
@@ -621,7 +670,7 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
     while (!done) {
         const int cur = (int)(it & 1), nxt = cur ^ 1;
         tm.begin(0, a);
-        k_trace<R, EXACT><<<g_trace, TRACE_BLOCK, 0, stream>>>(sc, paths[cur], ctl, cur, queues, pool);
+        trace_fn<<<g_trace, TRACE_BLOCK, 0, stream>>>(sc, paths[cur], ctl, cur, queues, pool);
         tm.end(0, a);
         tm.begin(1, a);
         k_shade_miss<R><<<g_miss, SHADE_BLOCK, 0, stream>>>(sc, paths[cur], ctl, queues + (size_t)Q_MISS * pool, fb, fb_scale);

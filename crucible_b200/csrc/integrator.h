@@ -57,8 +57,8 @@ template <typename R>
 int render_impl(const SceneDeviceData&, Workspace&, const CrCamera&, const CrRenderOpts&, void* d_out_rgb, void* d_out_rgb8,
                 int packed, cudaStream_t, CrStats*, std::string& err);
 template <typename R>
-int trace_batch_impl(const SceneDeviceData&, const double* d_rays, size_t n, double tmin, double tmax, CrHit* d_out, cudaStream_t,
-                     std::string& err);
+int trace_batch_impl(const SceneDeviceData&, const double* d_rays, size_t n, double tmin, double tmax, CrHit* d_out,
+                     uint32_t* d_cursor, cudaStream_t, std::string& err);
 
 // FMA micro-benchmarks (roofline denominators); defined in integrator_f32.cu
 int measure_fma_peak(int num_sms, double* fp64_tflops, double* fp32_tflops, std::string& err);
