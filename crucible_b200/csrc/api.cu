@@ -254,6 +254,10 @@ int upload_scene(CrScene* s) {
             b.left = a.left;
             b.right = a.right;
         }
+        double bm = 0.0;
+        if (!s->nodes.empty())
+            for (int k = 0; k < 3; ++k) bm = std::max(bm, std::max(std::fabs(s->nodes[0].box.lo[k]), std::fabs(s->nodes[0].box.hi[k])));
+        d.bmax = f32_up(bm);
         int rc;
         if ((rc = upload(s, n64, &d.nodes[0])) != CR_OK) return rc;
         if ((rc = upload(s, n32, &d.nodes[1])) != CR_OK) return rc;
@@ -541,6 +545,8 @@ static int64_t add_prims(CrScene* s, uint32_t kind, const double* data, size_t s
         e.kind = kind;
         e.idx = (uint32_t)(store.size() / stride);
         e.hide = false;
+        for (size_t k = 0; k < stride; ++k)
+            if (!std::isfinite(p[k])) return fail(CR_ERR_INVALID, "non-finite primitive coordinate");
         if (kind == CR_PRIM_SPHERE) {
             if (!(p[3] >= 0.0)) return fail(CR_ERR_INVALID, "Cannot make a sphere with negative radius");  // sphere.rs:26
             // sphere.rs:29-30: new_from_points(center - rvec, center + rvec); a - b == a + (-b)

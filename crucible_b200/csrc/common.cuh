@@ -99,6 +99,8 @@ struct DevImage {
 template <typename R>
 struct DevScene {
     const NodeRec<R>* nodes;
+    const NodeRec<float>* nodes32;  // outward-rounded f32 copy of the boxes (conservative filter of the f64 path)
+    float bmax;                     // largest |coordinate| of the root box, rounded up
     const SphereRec<R>* spheres;
     const TriRec<R>* tris;
     const QuadRec<R>* quads;

@@ -339,13 +339,65 @@ __device__ __forceinline__ bool is_finite(R x) {
     return Num<R>::abs_(x) < Num<R>::inf();
 }
 
-// Per-lane traversal state.  One step functions are shared by the render trace kernel and by
+// ---- conservative f32 box filter (f64 path only) --------------------------------------------------
+// The reference's decision at a node is  min(best_t, hi_x, hi_y, hi_z) > max(tmin, lo_x, lo_y, lo_z)
+// evaluated in f64.  The same expression evaluated in f32 on the outward-rounded f32 copy of the box
+// differs from the f64 values by at most
+//     |t32 - t64| <= |inv| (|b| 2^-23 + |o| 2^-24)(1 + 2^-22) + 3 * 2^-24 |t64|
+// (rounding of b, o and inv to f32, one subtraction, one multiplication).  With B = the largest
+// |coordinate| of the scene's root box, e = max over axes of |inv|(B 2^-23 + |o| 2^-24) is a per-ray
+// constant, and  E = 2.5 e + 2^-21 (|lo32| + |hi32|)  bounds the error of (hi - lo).  So
+//     hi32 - lo32 >  E  =>  the f64 test passes,     hi32 - lo32 < -E  =>  the f64 test fails,
+// and only the sliver in between (a few % of the tests) is re-decided by the exact f64 test.  The
+// decision taken is therefore ALWAYS the reference's decision; the filter only saves work.
+struct FilterRay {
+    float ox, oy, oz, ix, iy, iz, e, tmin;
+    bool ok;
+};
+__device__ __forceinline__ FilterRay make_filter_ray(V3<double> o, V3<double> inv, double tmin, float bmax, bool regular) {
+    FilterRay f;
+    f.ox = (float)o.x; f.oy = (float)o.y; f.oz = (float)o.z;
+    f.ix = (float)inv.x; f.iy = (float)inv.y; f.iz = (float)inv.z;
+    f.tmin = (float)tmin;
+    const float kb = bmax * 1.1920929e-7f;  // B * 2^-23
+    const float ex = fabsf(f.ix) * (kb + fabsf(f.ox) * 5.9604645e-8f);
+    const float ey = fabsf(f.iy) * (kb + fabsf(f.oy) * 5.9604645e-8f);
+    const float ez = fabsf(f.iz) * (kb + fabsf(f.oz) * 5.9604645e-8f);
+    f.e = 2.5f * fmaxf(ex, fmaxf(ey, ez));
+    // the filter is skipped for irregular rays and when f32 cannot represent the ray (overflow / underflow)
+    f.ok = regular && f.e < 3.0e37f && fabsf(f.ix) > 1.0e-30f && fabsf(f.iy) > 1.0e-30f && fabsf(f.iz) > 1.0e-30f;
+    return f;
+}
+// +1 = passes, -1 = fails, 0 = undecided (exact f64 test required)
+__device__ __forceinline__ int filter_box(const NodeRec<float>& n, const FilterRay& f, float best) {
+    const float x0 = (n.xmin - f.ox) * f.ix, x1 = (n.xmax - f.ox) * f.ix;
+    const float y0 = (n.ymin - f.oy) * f.iy, y1 = (n.ymax - f.oy) * f.iy;
+    const float z0 = (n.zmin - f.oz) * f.iz, z1 = (n.zmax - f.oz) * f.iz;
+    const float lo = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), f.tmin));
+    const float hi = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), best));
+    const float diff = hi - lo;
+    const float E = f.e + 4.7683716e-7f * (fabsf(lo) + fabsf(hi));
+    if (diff > E) return 1;
+    if (diff < -E) return -1;
+    return 0;  // also NaN / inf
+}
+
+// ---- warp-persistent closest-hit engine -------------------------------------------------------------
+// Lane states of the step scheduler
+enum : int { ST_IDLE = 0, ST_NODE = 1, ST_EXACT = 2, ST_LEAF = 3, ST_DONE = 4 };
+
+// Per-lane traversal state.  The step functions are shared by the render trace kernel and by
 // cr_trace_batch, so the parity-tested code IS the code that renders.
+//
+// Tree shape (bvhwrapper.rs:46-80): a node built from a span >= 3 has two NODE children; a node built
+// from a span of 1 or 2 holds its 1 or 2 primitives directly ("leaf node").  The stack therefore only
+// ever holds node indices, and a leaf node's primitives are tested (left, then right with the updated
+// interval, strict comparisons) right after its box test passes — exactly the reference's order.
 template <typename R>
 struct Trav {
     V3<R> o, d, inv;
     R a, tmin, best_t;
-    uint32_t best_ref, cur;
+    uint32_t best_ref, cur, aux;  // cur = node index (ST_NODE/ST_EXACT) or left primitive (ST_LEAF); aux = right primitive
     int sp;
     bool px, py, pz, regular;
     __device__ __forceinline__ void init(V3<R> o_, V3<R> d_, R tmin_, R tmax_, uint32_t root) {
@@ -357,6 +409,7 @@ struct Trav {
         best_t = tmax_;
         best_ref = REF_MISS;
         cur = root;
+        aux = REF_NONE;
         sp = 0;
         px = inv.x > R(0);
         py = inv.y > R(0);
@@ -364,41 +417,45 @@ struct Trav {
         regular = is_finite(o.x) && is_finite(o.y) && is_finite(o.z) && is_finite(inv.x) && is_finite(inv.y) && is_finite(inv.z) &&
                   inv.x != R(0) && inv.y != R(0) && inv.z != R(0) && !(tmin != tmin) && !(best_t != best_t);
     }
-    // pops the next reference; false when the walk is complete
-    __device__ __forceinline__ bool pop(const uint32_t* stack, int stride) {
-        if (sp == 0) return false;
+    // next node from the stack; ST_DONE when the walk is complete
+    __device__ __forceinline__ int pop(const uint32_t* stack, int stride) {
+        if (sp == 0) return ST_DONE;
         --sp;
         cur = stack[sp * stride];
-        return true;
+        return ST_NODE;
     }
-    // cur is an inner node: box test, descend left (or near) and push the other child.  Returns false
-    // when the walk is complete.
+    // the box test of node `cur` has been decided: descend / park at the leaf node / pop
     template <bool EXACT>
-    __device__ __forceinline__ bool step_node(const DevScene<R>& sc, uint32_t* stack, int stride) {
+    __device__ __forceinline__ int after_box(bool hit, uint32_t left_raw, uint32_t right, uint32_t* stack, int stride) {
+        if (!hit) return pop(stack, stride);
+        uint32_t first = left_raw & ~AXIS_MASK, second = right;
+        if (ref_is_leaf(first)) {  // leaf node: its primitives are tested next, left then right
+            cur = first;
+            aux = second;
+            return ST_LEAF;
+        }
+        if (!EXACT) {
+            const uint32_t ax = (left_raw & AXIS_MASK) >> AXIS_SHIFT;
+            const bool pos = ax == 0 ? px : (ax == 1 ? py : pz);
+            if (!pos) {
+                second = first;
+                first = right;
+            }
+        }
+        stack[sp * stride] = second;
+        ++sp;
+        cur = first;
+        return ST_NODE;
+    }
+    // exact box test of node `cur` in R arithmetic
+    template <bool EXACT>
+    __device__ __forceinline__ int step_exact(const DevScene<R>& sc, uint32_t* stack, int stride) {
         const NodeRec<R> n = ldg_rec<sizeof(NodeRec<R>) / 16>(sc.nodes + cur);
         const bool hit = regular ? aabb_hit_regular(n, o, inv, px, py, pz, tmin, best_t) : aabb_hit(n, o, inv, tmin, best_t);
-        if (hit) {
-            uint32_t first = n.left & ~AXIS_MASK, second = n.right;
-            if (!EXACT) {
-                const uint32_t ax = (n.left & AXIS_MASK) >> AXIS_SHIFT;
-                const bool pos = ax == 0 ? px : (ax == 1 ? py : pz);
-                if (!pos && second != REF_NONE) {
-                    second = first;
-                    first = n.right;
-                }
-            }
-            if (second != REF_NONE) {
-                stack[sp * stride] = second;
-                ++sp;
-            }
-            cur = first;
-            return true;
-        }
-        return pop(stack, stride);
+        return after_box<EXACT>(hit, n.left, n.right, stack, stride);
     }
-    // cur is a leaf: primitive test with the running interval (no box of its own), then pop
-    __device__ __forceinline__ bool step_leaf(const DevScene<R>& sc, const uint32_t* stack, int stride) {
-        const uint32_t kind = ref_kind(cur), idx = ref_index(cur);
+    __device__ __forceinline__ void test_prim(const DevScene<R>& sc, uint32_t ref) {
+        const uint32_t kind = ref_kind(ref), idx = ref_index(ref);
         R t;
         bool got;
         if (kind == CR_PRIM_SPHERE) {
@@ -414,65 +471,91 @@ struct Trav {
         }
         if (got) {
             best_t = t;
-            best_ref = cur;
+            best_ref = ref;
         }
+    }
+    // leaf node: left primitive with (tmin, best_t), right primitive with the updated interval; no boxes
+    __device__ __forceinline__ int step_leaf(const DevScene<R>& sc, const uint32_t* stack, int stride) {
+        test_prim(sc, cur);
+        if (aux != REF_NONE) test_prim(sc, aux);
         return pop(stack, stride);
     }
 };
 
-// Warp-persistent closest-hit engine: "while-while" traversal (all lanes walk inner nodes, then all
-// lanes test their leaf) with lane refill: as soon as REFILL lanes are idle the warp commits their
-// results and fetches that many new rays with ONE atomic (warp-level work fetch), so the SIMD lanes
-// stay occupied although rays differ wildly in trip count.
-//   IO::count()                      number of rays
-//   IO::cursor()                     global work cursor (uint32_t*)
-//   IO::load(i, o, d)                ray i
-//   IO::commit(has, i, ref, t, o, d) called warp-synchronously by all 32 lanes; `has` marks lanes holding a result
+// Warp-persistent engine.  Every iteration the warp votes on what its lanes need and runs ONE kind of
+// step for the lanes that need it:
+//   ST_NODE  cheap box test (f64 path: conservative f32 filter; f32 path: the f32 test itself)
+//   ST_EXACT exact f64 box test for the few nodes the filter could not decide
+//   ST_LEAF  primitive tests of a leaf node
+// Rare, expensive steps (EXACT, LEAF) are parked until PARK lanes wait for them or nothing cheap is
+// left, so they run with many lanes instead of dragging the whole warp along for one lane.  Each lane's
+// own sequence of tests is unchanged, so the result is the reference's.
+//   IO::count() / cursor() / load(i,o,d) / commit(has,i,ref,t,o,d)  (commit is warp-synchronous)
 template <typename R, bool EXACT, int REFILL, typename IO>
 __device__ __forceinline__ void trace_persistent(const DevScene<R>& sc, uint32_t* stack, int stride, R tmin, R tmax, IO& io) {
+    constexpr int PARK = 10;
     const uint32_t n = io.count();
     const int lane = threadIdx.x & 31;
     Trav<R> tv;
     tv.regular = true;
     tv.cur = REF_MISS;
+    tv.aux = REF_NONE;
     tv.sp = 0;
     tv.best_ref = REF_MISS;
     tv.best_t = tmax;
+    FilterRay fr;
+    fr.ok = false;
     uint32_t my = 0;
-    int st = 0;  // 0 = idle, 1 = walking, 2 = result pending
+    int st = ST_IDLE;
     bool exhausted = false;
     for (;;) {
-        const uint32_t walking = __ballot_sync(0xffffffffu, st == 1);
+        const uint32_t mN = __ballot_sync(0xffffffffu, st == ST_NODE);
+        const uint32_t mE = __ballot_sync(0xffffffffu, st == ST_EXACT);
+        const uint32_t mL = __ballot_sync(0xffffffffu, st == ST_LEAF);
+        const uint32_t walking = mN | mE | mL;
         const int n_free = 32 - __popc(walking);
         if ((!exhausted && n_free >= REFILL) || walking == 0u) {  // warp-uniform
-            io.commit(st == 2, my, tv.best_ref, tv.best_t, tv.o, tv.d);
-            if (st == 2) st = 0;
+            io.commit(st == ST_DONE, my, tv.best_ref, tv.best_t, tv.o, tv.d);
+            if (st == ST_DONE) st = ST_IDLE;
             if (!exhausted) {
                 uint32_t base = 0;
                 if (lane == 0) base = atomicAdd(io.cursor(), (uint32_t)n_free);
                 base = __shfl_sync(0xffffffffu, base, 0);
-                if (st == 0) {
+                if (st == ST_IDLE) {
                     const uint32_t i = base + (uint32_t)__popc(~walking & ((1u << lane) - 1u));
                     if (i < n) {
                         V3<R> o, d;
                         io.load(i, o, d);
                         my = i;
                         tv.init(o, d, tmin, tmax, sc.root);
-                        st = (sc.root == REF_MISS) ? 2 : 1;
+                        if constexpr (sizeof(R) == 8) fr = make_filter_ray(tv.o, tv.inv, tv.tmin, sc.bmax, tv.regular);
+                        st = (sc.root == REF_MISS) ? ST_DONE : ST_NODE;
                     }
                 }
                 if (base + (uint32_t)n_free >= n) exhausted = true;
             }
-            if (__ballot_sync(0xffffffffu, st != 0) == 0u) break;  // nothing walking, nothing pending
-            if (__ballot_sync(0xffffffffu, st == 1) == 0u) continue;  // only pending results (empty world)
+            if (__ballot_sync(0xffffffffu, st != ST_IDLE) == 0u) break;  // nothing walking, nothing pending
+            continue;
         }
-        // phase 1: every walking lane advances through inner nodes until it holds a leaf (or finishes)
-        while (st == 1 && !ref_is_leaf(tv.cur)) {
-            if (!tv.template step_node<EXACT>(sc, stack, stride)) st = 2;
-        }
-        // phase 2: every walking lane tests its leaf primitive
-        if (st == 1) {
-            if (!tv.step_leaf(sc, stack, stride)) st = 2;
+        const int nN = __popc(mN), nE = __popc(mE), nL = __popc(mL);
+        if (nN > 0 && nE < PARK && nL < PARK) {
+            if (st == ST_NODE) {
+                if constexpr (sizeof(R) == 8) {
+                    if (fr.ok) {
+                        const NodeRec<float> nf = ldg_rec<2>(sc.nodes32 + tv.cur);
+                        const int dec = filter_box(nf, fr, (float)tv.best_t);
+                        st = (dec == 0) ? (int)ST_EXACT : tv.template after_box<EXACT>(dec > 0, nf.left, nf.right, stack, stride);
+                    } else {
+                        st = ST_EXACT;
+                    }
+                } else {
+                    st = tv.template step_exact<EXACT>(sc, stack, stride);
+                }
+            }
+        } else if (nL >= nE) {
+            if (st == ST_LEAF) st = tv.step_leaf(sc, stack, stride);
+        } else {
+            if (st == ST_EXACT) st = tv.template step_exact<EXACT>(sc, stack, stride);
         }
     }
 }

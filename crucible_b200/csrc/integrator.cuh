@@ -473,6 +473,8 @@ static DevScene<R> make_dev_scene(const SceneDeviceData& s) {
     DevScene<R> d;
     const int k = (sizeof(R) == 8) ? 0 : 1;
     d.nodes = reinterpret_cast<const NodeRec<R>*>(s.nodes[k]);
+    d.nodes32 = reinterpret_cast<const NodeRec<float>*>(s.nodes[1]);
+    d.bmax = s.bmax;
     d.spheres = reinterpret_cast<const SphereRec<R>*>(s.spheres[k]);
     d.tris = reinterpret_cast<const TriRec<R>*>(s.tris[k]);
     d.quads = reinterpret_cast<const QuadRec<R>*>(s.quads[k]);
