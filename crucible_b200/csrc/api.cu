@@ -82,7 +82,9 @@ struct HostImage {
 
 struct FlatNode {
     Box box;
-    uint32_t left, right, axis;
+    uint32_t left, right, axis;  // children: node indices, or primitive refs for a leaf node
+    uint32_t lchild, rchild;     // node children (REF_NONE for a leaf node)
+    uint32_t skip;               // preorder index of the first node after this subtree
 };
 
 }  // namespace
@@ -156,6 +158,8 @@ struct Builder {
         n.box = bbox;
         n.axis = (uint32_t)axis;
         uint32_t depth = 1;
+        n.skip = at + (uint32_t)node_count(span);
+        n.lchild = n.rchild = REF_NONE;
         if (span == 1) {
             n.left = leaf_ref(objs[start]);
             n.right = REF_NONE;  // reference stores the same object twice; second test provably None
@@ -177,8 +181,8 @@ struct Builder {
             const size_t mid = start + span / 2;
             const uint32_t l_at = at + 1;
             const uint32_t r_at = at + 1 + (uint32_t)node_count(mid - start);
-            n.left = l_at;
-            n.right = r_at;
+            n.left = n.lchild = l_at;
+            n.right = n.rchild = r_at;
             uint32_t dl = 0, dr = 0;
             if (par_depth > 0 && span > 65536) {
                 std::thread th([&] { dl = build(start, mid, l_at, par_depth - 1); });
@@ -223,7 +227,7 @@ int upload_scene(CrScene* s) {
     s->free_device_scene();
     SceneDeviceData& d = s->dev;
     d.num_sms = s->num_sms;
-    d.root = s->root;
+    d.n_nodes = (uint32_t)s->nodes.size();
     d.sky_kind = s->sky_kind;
     d.sky_image = s->sky_image;
     d.clamp_colors = 1;
@@ -244,8 +248,10 @@ int upload_scene(CrScene* s) {
             a.xmin = n.box.lo[0]; a.xmax = n.box.hi[0];
             a.ymin = n.box.lo[1]; a.ymax = n.box.hi[1];
             a.zmin = n.box.lo[2]; a.zmax = n.box.hi[2];
-            a.left = n.left | (n.axis << AXIS_SHIFT);
-            a.right = n.right;
+            // device words: inner = (skip link, axis), leaf node = (left primitive, right primitive)
+            const bool leafnode = ref_is_leaf(n.left);
+            a.left = leafnode ? n.left : n.skip;
+            a.right = leafnode ? n.right : n.axis;
             a.pad0 = a.pad1 = 0;
             NodeRec<float>& b = n32[i];
             b.xmin = f32_down(n.box.lo[0]); b.xmax = f32_up(n.box.hi[0]);
@@ -652,7 +658,6 @@ int cr_scene_commit(CrScene* s) {
         s->nodes.resize((size_t)nn);
         Builder b{*s, visible, s->nodes};
         s->max_depth = b.build(0, visible.size(), 0, 4);
-        if ((int)s->max_depth + 2 > MAX_STACK) return fail(CR_ERR_LIMIT, "BVH deeper than the traversal stack");
         // new_from_vec (bvhwrapper.rs:34-44): the root box is re-derived from its two children
         FlatNode& r = s->nodes[0];
         auto child_box = [&](uint32_t ref) -> Box {

@@ -17,10 +17,11 @@
 namespace crb {
 
 // ---- child / primitive references -------------------------------------------------------------
-// bit31 = leaf; bits 29..30 = CrPrimKind; bits 0..26 = index into that kind's array (134 M).
-// Inner nodes are plain indices.  Bits 27..28 of a node's `left` field carry that NODE's split
-// axis (used by the near-first f32 traversal only); node_left() strips them.  REF_NONE marks "no right child to visit" (span-1 nodes hold the
-// same primitive twice in the reference, bvhwrapper.rs:59-61; the second test provably returns None).
+// bit31 = primitive; bits 29..30 = CrPrimKind; bits 0..26 = index into that kind's array (134 M).
+// Node indices are plain integers.  REF_NONE marks "no right primitive" (span-1 nodes hold the same
+// primitive twice in the reference, bvhwrapper.rs:59-61; the second test provably returns None).
+// Node words (`left`, `right` fields of NodeRec): inner node = (skip link, split axis); leaf node =
+// (left primitive ref, right primitive ref or REF_NONE).
 static constexpr uint32_t REF_LEAF = 0x80000000u;
 static constexpr uint32_t REF_NONE = 0x7FFFFFFFu;
 static constexpr uint32_t REF_MISS = 0xFFFFFFFFu;
@@ -32,7 +33,6 @@ static constexpr uint32_t REF_MAX_INDEX = 0x07FFFFFEu;
 static constexpr uint32_t AXIS_SHIFT = 27;
 static constexpr uint32_t AXIS_MASK = 3u << AXIS_SHIFT;
 
-static constexpr int MAX_STACK = 48;  // the host refuses trees deeper than MAX_STACK-2
 static constexpr int MAX_TEX_NEST = 8;
 
 // ---- shading queues ------------------------------------------------------------------------------
@@ -108,7 +108,7 @@ struct DevScene {
     const DevMaterial* mats;
     const DevTexture* texs;
     const DevImage* images;
-    uint32_t root;  // REF_MISS when the world is the empty HitList
+    uint32_t n_nodes;  // 0 when the world is the empty HitList (bvhwrapper.rs:29-31)
     int32_t sky_kind, sky_image;
     int32_t clamp_colors;  // 1 = reference Color semantics; 0 when the scene holds an Emissive (extension)
 };

@@ -383,24 +383,26 @@ __device__ __forceinline__ int filter_box(const NodeRec<float>& n, const FilterR
 }
 
 // ---- warp-persistent closest-hit engine -------------------------------------------------------------
-// Lane states of the step scheduler
+// Lane states
 enum : int { ST_IDLE = 0, ST_NODE = 1, ST_EXACT = 2, ST_LEAF = 3, ST_DONE = 4 };
 
-// Per-lane traversal state.  The step functions are shared by the render trace kernel and by
-// cr_trace_batch, so the parity-tested code IS the code that renders.
-//
-// Tree shape (bvhwrapper.rs:46-80): a node built from a span >= 3 has two NODE children; a node built
-// from a span of 1 or 2 holds its 1 or 2 primitives directly ("leaf node").  The stack therefore only
-// ever holds node indices, and a leaf node's primitives are tested (left, then right with the updated
-// interval, strict comparisons) right after its box test passes — exactly the reference's order.
+// Stackless, threaded traversal.  The host flattens the reference tree in PREORDER, so the reference's
+// recursion (bvhwrapper.rs:97-126: box test, then left subtree, then right subtree, one running
+// closest t) visits nodes in increasing index order and a failed box test jumps to the node's SKIP
+// link (first node after its subtree).  No stack, no depth limit:
+//     i = 0; while (i < n_nodes) { if (box(i) passes) { test leaf primitives; i = i + 1 } else i = skip(i) }
+// Node words: inner node  a = skip link,            b = split axis (unused here)
+//             leaf node   a = left primitive ref,   b = right primitive ref or REF_NONE   (skip = i + 1)
+// (a node built from a span of 1 or 2 holds its primitives directly, a node built from a span >= 3
+// has two node children: bvhwrapper.rs:57-74.)  Leaves are tested with no box of their own, left
+// first, right with the updated interval, strict comparisons — the reference's order.
 template <typename R>
 struct Trav {
     V3<R> o, d, inv;
     R a, tmin, best_t;
-    uint32_t best_ref, cur, aux;  // cur = node index (ST_NODE/ST_EXACT) or left primitive (ST_LEAF); aux = right primitive
-    int sp;
+    uint32_t best_ref, i, pl, pr;  // i = next node index; pl/pr = parked leaf primitives
     bool px, py, pz, regular;
-    __device__ __forceinline__ void init(V3<R> o_, V3<R> d_, R tmin_, R tmax_, uint32_t root) {
+    __device__ __forceinline__ void init(V3<R> o_, V3<R> d_, R tmin_, R tmax_) {
         o = o_;
         d = d_;
         inv = {R(1) / d.x, R(1) / d.y, R(1) / d.z};  // adinv, bvh.rs:111 (a pure function of the ray)
@@ -408,51 +410,31 @@ struct Trav {
         tmin = tmin_;
         best_t = tmax_;
         best_ref = REF_MISS;
-        cur = root;
-        aux = REF_NONE;
-        sp = 0;
+        i = 0;
+        pl = pr = REF_NONE;
         px = inv.x > R(0);
         py = inv.y > R(0);
         pz = inv.z > R(0);
         regular = is_finite(o.x) && is_finite(o.y) && is_finite(o.z) && is_finite(inv.x) && is_finite(inv.y) && is_finite(inv.z) &&
                   inv.x != R(0) && inv.y != R(0) && inv.z != R(0) && !(tmin != tmin) && !(best_t != best_t);
     }
-    // next node from the stack; ST_DONE when the walk is complete
-    __device__ __forceinline__ int pop(const uint32_t* stack, int stride) {
-        if (sp == 0) return ST_DONE;
-        --sp;
-        cur = stack[sp * stride];
-        return ST_NODE;
-    }
-    // the box test of node `cur` has been decided: descend / park at the leaf node / pop
-    template <bool EXACT>
-    __device__ __forceinline__ int after_box(bool hit, uint32_t left_raw, uint32_t right, uint32_t* stack, int stride) {
-        if (!hit) return pop(stack, stride);
-        uint32_t first = left_raw & ~AXIS_MASK, second = right;
-        if (ref_is_leaf(first)) {  // leaf node: its primitives are tested next, left then right
-            cur = first;
-            aux = second;
+    // the box test of node i has been decided
+    __device__ __forceinline__ int after_box(bool hit, uint32_t wa, uint32_t wb, uint32_t n_nodes) {
+        const bool leafnode = ref_is_leaf(wa);
+        const uint32_t here = i;
+        i = (hit || leafnode) ? here + 1u : wa;
+        if (hit && leafnode) {
+            pl = wa;
+            pr = wb;
             return ST_LEAF;
         }
-        if (!EXACT) {
-            const uint32_t ax = (left_raw & AXIS_MASK) >> AXIS_SHIFT;
-            const bool pos = ax == 0 ? px : (ax == 1 ? py : pz);
-            if (!pos) {
-                second = first;
-                first = right;
-            }
-        }
-        stack[sp * stride] = second;
-        ++sp;
-        cur = first;
-        return ST_NODE;
+        return i >= n_nodes ? ST_DONE : ST_NODE;
     }
-    // exact box test of node `cur` in R arithmetic
-    template <bool EXACT>
-    __device__ __forceinline__ int step_exact(const DevScene<R>& sc, uint32_t* stack, int stride) {
-        const NodeRec<R> n = ldg_rec<sizeof(NodeRec<R>) / 16>(sc.nodes + cur);
+    // exact box test of node i in R arithmetic
+    __device__ __forceinline__ int step_exact(const DevScene<R>& sc) {
+        const NodeRec<R> n = ldg_rec<sizeof(NodeRec<R>) / 16>(sc.nodes + i);
         const bool hit = regular ? aabb_hit_regular(n, o, inv, px, py, pz, tmin, best_t) : aabb_hit(n, o, inv, tmin, best_t);
-        return after_box<EXACT>(hit, n.left, n.right, stack, stride);
+        return after_box(hit, n.left, n.right, sc.n_nodes);
     }
     __device__ __forceinline__ void test_prim(const DevScene<R>& sc, uint32_t ref) {
         const uint32_t kind = ref_kind(ref), idx = ref_index(ref);
@@ -474,33 +456,32 @@ struct Trav {
             best_ref = ref;
         }
     }
-    // leaf node: left primitive with (tmin, best_t), right primitive with the updated interval; no boxes
-    __device__ __forceinline__ int step_leaf(const DevScene<R>& sc, const uint32_t* stack, int stride) {
-        test_prim(sc, cur);
-        if (aux != REF_NONE) test_prim(sc, aux);
-        return pop(stack, stride);
+    __device__ __forceinline__ int step_leaf(const DevScene<R>& sc) {
+        test_prim(sc, pl);
+        if (pr != REF_NONE) test_prim(sc, pr);
+        return i >= sc.n_nodes ? ST_DONE : ST_NODE;
     }
 };
 
-// Warp-persistent engine.  Every iteration the warp votes on what its lanes need and runs ONE kind of
-// step for the lanes that need it:
-//   ST_NODE  cheap box test (f64 path: conservative f32 filter; f32 path: the f32 test itself)
-//   ST_EXACT exact f64 box test for the few nodes the filter could not decide
-//   ST_LEAF  primitive tests of a leaf node
-// Rare, expensive steps (EXACT, LEAF) are parked until PARK lanes wait for them or nothing cheap is
-// left, so they run with many lanes instead of dragging the whole warp along for one lane.  Each lane's
-// own sequence of tests is unchanged, so the result is the reference's.
+// Warp-persistent engine.  The warp alternates between
+//   - a NODE phase: up to NODE_SLICE cheap box tests per lane (f64 path: the conservative f32 filter;
+//     f32 path: the f32 test itself).  A lane whose node the filter cannot decide parks in ST_EXACT, a
+//     lane that entered a leaf node parks in ST_LEAF;
+//   - an EXACT phase: the f64 box test for the parked undecided nodes (a few % of the tests);
+//   - a LEAF phase: the primitive tests of the parked leaf nodes.
+// Parking the rare, expensive steps lets them run with many lanes at once instead of dragging the
+// whole warp along for one lane.  Finished lanes are refilled (one atomic per warp) as soon as REFILL
+// of them are idle.  Each lane's own sequence of tests is the reference's, so is the result.
 //   IO::count() / cursor() / load(i,o,d) / commit(has,i,ref,t,o,d)  (commit is warp-synchronous)
 template <typename R, bool EXACT, int REFILL, typename IO>
-__device__ __forceinline__ void trace_persistent(const DevScene<R>& sc, uint32_t* stack, int stride, R tmin, R tmax, IO& io) {
-    constexpr int PARK = 10;
+__device__ __forceinline__ void trace_persistent(const DevScene<R>& sc, R tmin, R tmax, IO& io) {
+    constexpr int NODE_SLICE = 8;
     const uint32_t n = io.count();
     const int lane = threadIdx.x & 31;
     Trav<R> tv;
     tv.regular = true;
-    tv.cur = REF_MISS;
-    tv.aux = REF_NONE;
-    tv.sp = 0;
+    tv.i = 0;
+    tv.pl = tv.pr = REF_NONE;
     tv.best_ref = REF_MISS;
     tv.best_t = tmax;
     FilterRay fr;
@@ -509,10 +490,7 @@ __device__ __forceinline__ void trace_persistent(const DevScene<R>& sc, uint32_t
     int st = ST_IDLE;
     bool exhausted = false;
     for (;;) {
-        const uint32_t mN = __ballot_sync(0xffffffffu, st == ST_NODE);
-        const uint32_t mE = __ballot_sync(0xffffffffu, st == ST_EXACT);
-        const uint32_t mL = __ballot_sync(0xffffffffu, st == ST_LEAF);
-        const uint32_t walking = mN | mE | mL;
+        const uint32_t walking = __ballot_sync(0xffffffffu, st == ST_NODE || st == ST_EXACT || st == ST_LEAF);
         const int n_free = 32 - __popc(walking);
         if ((!exhausted && n_free >= REFILL) || walking == 0u) {  // warp-uniform
             io.commit(st == ST_DONE, my, tv.best_ref, tv.best_t, tv.o, tv.d);
@@ -522,40 +500,46 @@ __device__ __forceinline__ void trace_persistent(const DevScene<R>& sc, uint32_t
                 if (lane == 0) base = atomicAdd(io.cursor(), (uint32_t)n_free);
                 base = __shfl_sync(0xffffffffu, base, 0);
                 if (st == ST_IDLE) {
-                    const uint32_t i = base + (uint32_t)__popc(~walking & ((1u << lane) - 1u));
-                    if (i < n) {
+                    const uint32_t k = base + (uint32_t)__popc(~walking & ((1u << lane) - 1u));
+                    if (k < n) {
                         V3<R> o, d;
-                        io.load(i, o, d);
-                        my = i;
-                        tv.init(o, d, tmin, tmax, sc.root);
+                        io.load(k, o, d);
+                        my = k;
+                        tv.init(o, d, tmin, tmax);
                         if constexpr (sizeof(R) == 8) fr = make_filter_ray(tv.o, tv.inv, tv.tmin, sc.bmax, tv.regular);
-                        st = (sc.root == REF_MISS) ? ST_DONE : ST_NODE;
+                        st = (sc.n_nodes == 0u) ? ST_DONE : ST_NODE;
                     }
                 }
                 if (base + (uint32_t)n_free >= n) exhausted = true;
             }
             if (__ballot_sync(0xffffffffu, st != ST_IDLE) == 0u) break;  // nothing walking, nothing pending
-            continue;
         }
-        const int nN = __popc(mN), nE = __popc(mE), nL = __popc(mL);
-        if (nN > 0 && nE < PARK && nL < PARK) {
+        // ---- NODE phase
+#pragma unroll 1
+        for (int k = 0; k < NODE_SLICE; ++k) {
             if (st == ST_NODE) {
                 if constexpr (sizeof(R) == 8) {
                     if (fr.ok) {
-                        const NodeRec<float> nf = ldg_rec<2>(sc.nodes32 + tv.cur);
+                        const NodeRec<float> nf = ldg_rec<2>(sc.nodes32 + tv.i);
                         const int dec = filter_box(nf, fr, (float)tv.best_t);
-                        st = (dec == 0) ? (int)ST_EXACT : tv.template after_box<EXACT>(dec > 0, nf.left, nf.right, stack, stride);
+                        st = (dec == 0) ? (int)ST_EXACT : tv.after_box(dec > 0, nf.left, nf.right, sc.n_nodes);
                     } else {
                         st = ST_EXACT;
                     }
                 } else {
-                    st = tv.template step_exact<EXACT>(sc, stack, stride);
+                    st = tv.step_exact(sc);
                 }
             }
-        } else if (nL >= nE) {
-            if (st == ST_LEAF) st = tv.step_leaf(sc, stack, stride);
-        } else {
-            if (st == ST_EXACT) st = tv.template step_exact<EXACT>(sc, stack, stride);
+        }
+        // ---- EXACT phase (f64 path only)
+        if constexpr (sizeof(R) == 8) {
+            if (__any_sync(0xffffffffu, st == ST_EXACT)) {
+                if (st == ST_EXACT) st = tv.step_exact(sc);
+            }
+        }
+        // ---- LEAF phase
+        if (__any_sync(0xffffffffu, st == ST_LEAF)) {
+            if (st == ST_LEAF) st = tv.step_leaf(sc);
         }
     }
 }

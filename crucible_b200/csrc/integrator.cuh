@@ -225,9 +225,8 @@ __global__ void __launch_bounds__(SHADE_BLOCK) k_raygen(const Control* __restric
     }
 }
 
-// trace: persistent threads with warp-level work fetch and lane refill (trace_persistent), traversal
-// stack in shared memory ([depth][thread], conflict free), 128-bit node / primitive loads, then
-// classification of the finished rays into their material queues with one atomic per warp per queue.
+// trace: persistent threads with warp-level work fetch and lane refill (trace_persistent), stackless
+// threaded traversal, 128-bit node / primitive loads, then classification of the finished rays into their material queues with one atomic per warp per queue.
 #ifndef CRB_REFILL
 #define CRB_REFILL 12
 #endif
@@ -276,9 +275,8 @@ struct RenderTraceIO {
 template <typename R, bool EXACT, int REFILL>
 __global__ void __launch_bounds__(TRACE_BLOCK) k_trace(DevScene<R> sc, PathRec<R>* __restrict__ paths, Control* __restrict__ ctl,
                                                         int side, uint32_t* __restrict__ queues, uint32_t pool) {
-    __shared__ uint32_t s_stack[MAX_STACK * TRACE_BLOCK];
     RenderTraceIO<R> io{sc, paths, ctl, queues, ctl->n_in[side], pool};
-    trace_persistent<R, EXACT, REFILL>(sc, s_stack + threadIdx.x, TRACE_BLOCK, R(0.001), Num<R>::inf(), io);  // ray_casting.rs:119
+    trace_persistent<R, EXACT, REFILL>(sc, R(0.001), Num<R>::inf(), io);  // ray_casting.rs:119
 }
 
 // fixed-point accumulation: order independent => bit-reproducible for any schedule and GPU count
@@ -462,9 +460,8 @@ struct BatchTraceIO {
 template <typename R, bool EXACT>
 __global__ void __launch_bounds__(TRACE_BLOCK) k_trace_batch(DevScene<R> sc, const double* __restrict__ rays, uint32_t n, double tmin,
                                                               double tmax, CrHit* __restrict__ out, uint32_t* __restrict__ cursor) {
-    __shared__ uint32_t s_stack[MAX_STACK * TRACE_BLOCK];
     BatchTraceIO<R> io{sc, rays, out, cursor, n};
-    trace_persistent<R, EXACT, CRB_REFILL>(sc, s_stack + threadIdx.x, TRACE_BLOCK, (R)tmin, (R)tmax, io);
+    trace_persistent<R, EXACT, CRB_REFILL>(sc, (R)tmin, (R)tmax, io);
 }
 
 // ---- host side: typed view of the scene + wavefront driver -----------------------------------------
@@ -482,7 +479,7 @@ static DevScene<R> make_dev_scene(const SceneDeviceData& s) {
     d.mats = s.mats;
     d.texs = s.texs;
     d.images = s.images;
-    d.root = s.root;
+    d.n_nodes = s.n_nodes;
     d.sky_kind = s.sky_kind;
     d.sky_image = s.sky_image;
     d.clamp_colors = s.clamp_colors;

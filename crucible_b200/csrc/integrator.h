@@ -19,7 +19,7 @@ struct SceneDeviceData {
     DevMaterial* mats = nullptr;
     DevTexture* texs = nullptr;
     DevImage* images = nullptr;
-    uint32_t root = REF_MISS;
+    uint32_t n_nodes = 0;
     int32_t sky_kind = CR_SKY_DEFAULT, sky_image = -1;
     int32_t clamp_colors = 1;
     float bmax = 0.f;            // largest |coordinate| of the root box (f32, rounded up)
