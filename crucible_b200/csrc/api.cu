@@ -222,6 +222,15 @@ int upload(CrScene* s, const std::vector<T>& host, void** out) {
     return CR_OK;
 }
 
+// does the texture tree under `tex` reach an image texture (the only consumer of u, v)?
+bool tex_needs_uv(const CrScene* s, int tex, int depth = 0) {
+    if (tex < 0 || tex >= (int)s->texs.size() || depth > MAX_TEX_NEST) return true;
+    const CrTexture& t = s->texs[(size_t)tex];
+    if (t.kind == CR_TEX_IMAGE) return true;
+    if (t.kind == CR_TEX_CHECKER) return tex_needs_uv(s, t.even, depth + 1) || tex_needs_uv(s, t.odd, depth + 1);
+    return false;
+}
+
 int upload_scene(CrScene* s) {
     API_CUDA(cudaSetDevice(s->device));
     s->free_device_scene();
@@ -345,7 +354,8 @@ int upload_scene(CrScene* s) {
             m[i].material = s->mat_of[k][i];
             m[i].prim_index = s->prim_of[k][i];
             m[i].obj_id = s->obj_of[k][i];
-            m[i].mat_kind = s->mats[(size_t)m[i].material].kind;
+            const CrMaterial& cm = s->mats[(size_t)m[i].material];
+            m[i].mat_kind = cm.kind | ((cm.kind == CR_MAT_LAMBERTIAN && tex_needs_uv(s, cm.tex)) ? MATKIND_NEEDS_UV : 0);
         }
         void* p = nullptr;
         int rc = upload(s, m, &p);

@@ -77,8 +77,10 @@ struct PrimMeta {  // per primitive, per kind
     int32_t material;
     int32_t prim_index;
     int32_t obj_id;
-    int32_t mat_kind;
+    int32_t mat_kind;  // bits 0..7 = CrMaterialKind, bit 8 = the material's texture tree reaches an image (needs u, v)
 };
+static constexpr int32_t MATKIND_MASK = 0xff;
+static constexpr int32_t MATKIND_NEEDS_UV = 0x100;
 
 struct DevMaterial {
     int32_t kind, tex;
@@ -111,6 +113,7 @@ struct DevScene {
     uint32_t n_nodes;  // 0 when the world is the empty HitList (bvhwrapper.rs:29-31)
     int32_t sky_kind, sky_image;
     int32_t clamp_colors;  // 1 = reference Color semantics; 0 when the scene holds an Emissive (extension)
+    int32_t node_slice;    // box tests per lane between two exact/leaf phases of the trace engine
 };
 
 // ---- in-flight path record --------------------------------------------------------------------

@@ -267,14 +267,17 @@ template <typename R> struct HitInfo {
     bool front;
     int32_t material, mat_kind, prim_index, obj_id;
 };
+// want_uv = false skips get_sphere_uv (acos + atan2): the texture coordinates only reach image textures
+// (solid_color.rs:25-27 and checker_texture.rs:39-51 ignore u, v), so skipping them cannot change a result.
 template <typename R>
-__device__ __forceinline__ HitInfo<R> finalize_hit(const DevScene<R>& sc, uint32_t ref, R t, V3<R> o, V3<R> d) {
+__device__ __forceinline__ HitInfo<R> finalize_hit(const DevScene<R>& sc, uint32_t ref, R t, V3<R> o, V3<R> d, bool always_uv = true) {
     HitInfo<R> h;
     const uint32_t kind = ref_kind(ref), idx = ref_index(ref);
     const PrimMeta* mp = kind == CR_PRIM_SPHERE ? sc.meta[0] : (kind == CR_PRIM_TRIANGLE ? sc.meta[1] : sc.meta[2]);
     const PrimMeta m = mp[idx];
     h.material = m.material;
-    h.mat_kind = m.mat_kind;
+    h.mat_kind = m.mat_kind & MATKIND_MASK;
+    const bool want_uv = always_uv || (m.mat_kind & MATKIND_NEEDS_UV) != 0;
     h.prim_index = m.prim_index;
     h.obj_id = m.obj_id;
     h.p = vadd(o, vmul(t, d));  // Ray::at, ray_casting.rs:53-59
@@ -282,10 +285,13 @@ __device__ __forceinline__ HitInfo<R> finalize_hit(const DevScene<R>& sc, uint32
     if (kind == CR_PRIM_SPHERE) {
         SphereRec<R> s = ldg_rec<sizeof(SphereRec<R>) / 16>(sc.spheres + idx);
         n = vdiv(vsub(h.p, V3<R>{s.cx, s.cy, s.cz}), s.r);  // sphere.rs:96
-        R theta = Num<R>::acos_(-n.y);                      // sphere.rs:41-46
-        R phi = Num<R>::atan2_(-n.z, n.x) + Num<R>::pi();
-        h.u = phi / (R(2) * Num<R>::pi());
-        h.v = theta / Num<R>::pi();
+        h.u = h.v = R(0);
+        if (want_uv) {
+            R theta = Num<R>::acos_(-n.y);  // sphere.rs:41-46
+            R phi = Num<R>::atan2_(-n.z, n.x) + Num<R>::pi();
+            h.u = phi / (R(2) * Num<R>::pi());
+            h.v = theta / Num<R>::pi();
+        }
     } else if (kind == CR_PRIM_TRIANGLE) {
         TriRec<R> tr = ldg_rec<sizeof(TriRec<R>) / 16>(sc.tris + idx);
         n = vunit(vcross(V3<R>{tr.e1x, tr.e1y, tr.e1z}, V3<R>{tr.e2x, tr.e2y, tr.e2z}));  // triangle.rs:124 + safe_new
@@ -475,7 +481,7 @@ struct Trav {
 //   IO::count() / cursor() / load(i,o,d) / commit(has,i,ref,t,o,d)  (commit is warp-synchronous)
 template <typename R, bool EXACT, int REFILL, typename IO>
 __device__ __forceinline__ void trace_persistent(const DevScene<R>& sc, R tmin, R tmax, IO& io) {
-    constexpr int NODE_SLICE = 8;
+    const int NODE_SLICE = sc.node_slice;
     const uint32_t n = io.count();
     const int lane = threadIdx.x & 31;
     Trav<R> tv;

@@ -264,7 +264,7 @@ struct RenderTraceIO {
             } else {
                 const uint32_t kind = ref_kind(ref);
                 const PrimMeta* m = kind == CR_PRIM_SPHERE ? sc.meta[0] : (kind == CR_PRIM_TRIANGLE ? sc.meta[1] : sc.meta[2]);
-                q = (int)Q_LAMBERTIAN + m[ref_index(ref)].mat_kind;
+                q = (int)Q_LAMBERTIAN + (m[ref_index(ref)].mat_kind & MATKIND_MASK);
             }
         }
         const uint32_t pos = warp_enqueue(ctl->queue_count, q);
@@ -272,8 +272,8 @@ struct RenderTraceIO {
     }
 };
 
-template <typename R, bool EXACT, int REFILL>
-__global__ void __launch_bounds__(TRACE_BLOCK) k_trace(DevScene<R> sc, PathRec<R>* __restrict__ paths, Control* __restrict__ ctl,
+template <typename R, bool EXACT, int REFILL, int MINB>
+__global__ void __launch_bounds__(TRACE_BLOCK, MINB) k_trace(DevScene<R> sc, PathRec<R>* __restrict__ paths, Control* __restrict__ ctl,
                                                         int side, uint32_t* __restrict__ queues, uint32_t pool) {
     RenderTraceIO<R> io{sc, paths, ctl, queues, ctl->n_in[side], pool};
     trace_persistent<R, EXACT, REFILL>(sc, R(0.001), Num<R>::inf(), io);  // ray_casting.rs:119
@@ -352,7 +352,8 @@ __global__ void __launch_bounds__(SHADE_BLOCK) k_shade_scatter(DevScene<R> sc, c
         if (k < n) {
             load_path(in + queue[k], p);
             const V3<R> o = {p.ox, p.oy, p.oz}, d = {p.dx, p.dy, p.dz};
-            const HitInfo<R> h = finalize_hit<R>(sc, p.ref, p.t, o, d);
+            // u, v are needed only when a Lambertian's texture tree reaches an image
+            const HitInfo<R> h = finalize_hit<R>(sc, p.ref, p.t, o, d, false);
             const DevMaterial& mat = sc.mats[h.material];
             const uint32_t bounce = p.bounce + 1;  // this is the bounce-th hit of the path
             Rng<R> g(seed, p.pixel, p.sample, bounce);
@@ -483,6 +484,8 @@ static DevScene<R> make_dev_scene(const SceneDeviceData& s) {
     d.sky_kind = s.sky_kind;
     d.sky_image = s.sky_image;
     d.clamp_colors = s.clamp_colors;
+    d.node_slice = s.node_slice;
+    if (const char* e = getenv("CRB_NODE_SLICE")) d.node_slice = atoi(e) > 0 ? atoi(e) : 8;
     return d;
 }
 
@@ -634,8 +637,13 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
     typedef void (*TraceFn)(DevScene<R>, PathRec<R>*, Control*, int, uint32_t*, uint32_t);
     int refill = CRB_REFILL;
     if (const char* e = getenv("CRB_REFILL")) refill = atoi(e);
-    TraceFn trace_fn = refill <= 4 ? k_trace<R, EXACT, 4> : refill <= 8 ? k_trace<R, EXACT, 8> : refill <= 12 ? k_trace<R, EXACT, 12>
-                     : refill <= 16 ? k_trace<R, EXACT, 16> : refill <= 24 ? k_trace<R, EXACT, 24> : k_trace<R, EXACT, 32>;
+    int minb = 4;
+    if (const char* e = getenv("CRB_MINB")) minb = atoi(e);
+#define CRB_PICK(MB)                                                                                                        \
+    (refill <= 8 ? k_trace<R, EXACT, 8, MB> : refill <= 16 ? k_trace<R, EXACT, 16, MB> : refill <= 24 ? k_trace<R, EXACT, 24, MB> \
+                                                                                                  : k_trace<R, EXACT, 32, MB>)
+    TraceFn trace_fn = minb <= 4 ? CRB_PICK(4) : minb <= 6 ? CRB_PICK(6) : CRB_PICK(8);
+#undef CRB_PICK
     const int g_trace = persistent_grid(trace_fn, TRACE_BLOCK, s.num_sms);
     const int g_gen = persistent_grid(k_raygen<R>, SHADE_BLOCK, s.num_sms);
     const int g_miss = persistent_grid(k_shade_miss<R>, SHADE_BLOCK, s.num_sms);
