@@ -112,7 +112,6 @@ struct CrScene {
     // device
     SceneDeviceData dev;
     std::vector<void*> dev_allocs;
-    Workspace ws;
     void* d_out_rgb = nullptr;
     void* d_out_rgb8 = nullptr;
     size_t out_cap = 0;
@@ -133,6 +132,14 @@ struct CrScene {
 };
 
 namespace {
+
+// One grow-only scratch arena per device, shared by every scene of the process (path pool, queues,
+// fixed-point framebuffer): a second render, or a second scene, reuses the memory instead of paying
+// cudaMalloc for gigabytes again.  Guarded by the "one host thread drives one device" contract.
+Workspace& device_workspace(int device) {
+    static Workspace ws[64];
+    return ws[device < 0 || device >= 64 ? 0 : device];
+}
 
 // number of nodes BVHWrapper::help_generate creates for a span (bvhwrapper.rs:46-80)
 uint64_t node_count(uint64_t span) {
@@ -540,7 +547,6 @@ void cr_scene_destroy(CrScene* s) {
     if (s->device >= 0) {
         cudaSetDevice(s->device);
         s->free_device_scene();
-        s->ws.release();
         if (s->d_out_rgb) cudaFree(s->d_out_rgb);
         if (s->d_out_rgb8) cudaFree(s->d_out_rgb8);
         if (s->d_io) cudaFree(s->d_io);
@@ -781,8 +787,8 @@ int cr_render_device(CrScene* s, const CrCamera* cam, const CrRenderOpts* opts, 
     // device variant: rows of this rank are written PACKED ([rows_local][W][3]) so the result is the
     // NCCL gather send buffer as is
     rc = (opts->precision == CR_PRECISION_F32)
-             ? render_impl<float>(s->dev, s->ws, *cam, *opts, d_out_rgb, d_out_rgb8, 1, st, stats, err)
-             : render_impl<double>(s->dev, s->ws, *cam, *opts, d_out_rgb, d_out_rgb8, 1, st, stats, err);
+             ? render_impl<float>(s->dev, device_workspace(s->device), *cam, *opts, d_out_rgb, d_out_rgb8, 1, st, stats, err)
+             : render_impl<double>(s->dev, device_workspace(s->device), *cam, *opts, d_out_rgb, d_out_rgb8, 1, st, stats, err);
     if (rc != CR_OK) return fail(rc, err);
     return CR_OK;
 }
@@ -813,9 +819,9 @@ int cr_render(CrScene* s, const CrCamera* cam, const CrRenderOpts* opts, double*
     }
     std::string err;
     rc = (opts->precision == CR_PRECISION_F32)
-             ? render_impl<float>(s->dev, s->ws, *cam, *opts, out_rgb ? s->d_out_rgb : nullptr, out_rgb8 ? s->d_out_rgb8 : nullptr, 0,
+             ? render_impl<float>(s->dev, device_workspace(s->device), *cam, *opts, out_rgb ? s->d_out_rgb : nullptr, out_rgb8 ? s->d_out_rgb8 : nullptr, 0,
                                   s->stream, stats, err)
-             : render_impl<double>(s->dev, s->ws, *cam, *opts, out_rgb ? s->d_out_rgb : nullptr, out_rgb8 ? s->d_out_rgb8 : nullptr,
+             : render_impl<double>(s->dev, device_workspace(s->device), *cam, *opts, out_rgb ? s->d_out_rgb : nullptr, out_rgb8 ? s->d_out_rgb8 : nullptr,
                                    0, s->stream, stats, err);
     if (rc != CR_OK) return fail(rc, err);
     cudaEvent_t a, b;

@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK) k_raygen(const Control* __restric
 // trace: persistent threads with warp-level work fetch and lane refill (trace_persistent), stackless
 // threaded traversal, 128-bit node / primitive loads, then classification of the finished rays into their material queues with one atomic per warp per queue.
 #ifndef CRB_REFILL
-#define CRB_REFILL 12
+#define CRB_REFILL 24
 #endif
 template <typename R>
 struct RenderTraceIO {
@@ -572,7 +572,8 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
     }
     const uint64_t npix = (uint64_t)W * rows_local;
     const uint64_t total = npix * cam_in.samples;
-    uint32_t pool = opts.pool_paths ? opts.pool_paths : (1u << 20);
+    // few, large wavefronts: per-iteration launch gaps and kernel tails dominate below ~4 M paths (profiles/)
+    uint32_t pool = opts.pool_paths ? opts.pool_paths : (16u << 20);
     if (pool < 1024) pool = 1024;
     if ((uint64_t)pool > total && total > 0) pool = (uint32_t)((total + 31) & ~31ull);
     // u64 fixed point: 2^-44 resolution unless max_radiance * spp would overflow 62 bits
@@ -637,7 +638,7 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
     typedef void (*TraceFn)(DevScene<R>, PathRec<R>*, Control*, int, uint32_t*, uint32_t);
     int refill = CRB_REFILL;
     if (const char* e = getenv("CRB_REFILL")) refill = atoi(e);
-    int minb = 4;
+    int minb = 6;
     if (const char* e = getenv("CRB_MINB")) minb = atoi(e);
 #define CRB_PICK(MB)                                                                                                        \
     (refill <= 8 ? k_trace<R, EXACT, 8, MB> : refill <= 16 ? k_trace<R, EXACT, 16, MB> : refill <= 24 ? k_trace<R, EXACT, 24, MB> \

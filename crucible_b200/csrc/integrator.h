@@ -25,7 +25,7 @@ struct SceneDeviceData {
     float bmax = 0.f;            // largest |coordinate| of the root box (f32, rounded up)
     double max_radiance = 1.0;  // largest per-sample colour component (1 unless the scene holds an Emissive)
     int num_sms = 148;
-    int node_slice = 8;
+    int node_slice = 4;
 };
 
 // Grow-only device scratch owned by the CrScene (path pool, queues, fixed-point framebuffer).
