@@ -276,10 +276,25 @@ int upload_scene(CrScene* s) {
             b.left = a.left;
             b.right = a.right;
         }
-        double bm = 0.0;
-        if (!s->nodes.empty())
-            for (int k = 0; k < 3; ++k) bm = std::max(bm, std::max(std::fabs(s->nodes[0].box.lo[k]), std::fabs(s->nodes[0].box.hi[k])));
-        d.bmax = f32_up(bm);
+        // per-node |coordinate| bound; the ~90 % smallest share the tight filter bound, the rest get BIGBOX_BIT
+        std::vector<float> nb(s->nodes.size());
+        for (size_t i = 0; i < s->nodes.size(); ++i) {
+            double bm = 0.0;
+            for (int k = 0; k < 3; ++k) bm = std::max(bm, std::max(std::fabs(s->nodes[i].box.lo[k]), std::fabs(s->nodes[i].box.hi[k])));
+            nb[i] = f32_up(bm);
+        }
+        d.bmax = nb.empty() ? 0.f : *std::max_element(nb.begin(), nb.end());
+        d.bsmall = d.bmax;
+        if (!nb.empty()) {
+            std::vector<float> sorted = nb;
+            std::sort(sorted.begin(), sorted.end());
+            d.bsmall = sorted[(size_t)((sorted.size() - 1) * 0.9)];
+        }
+        for (size_t i = 0; i < s->nodes.size(); ++i) {
+            const uint32_t big = nb[i] > d.bsmall ? (1u << 27) : 0u;
+            n64[i].left |= big;
+            n32[i].left |= big;
+        }
         int rc;
         if ((rc = upload(s, n64, &d.nodes[0])) != CR_OK) return rc;
         if ((rc = upload(s, n32, &d.nodes[1])) != CR_OK) return rc;

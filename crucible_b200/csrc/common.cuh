@@ -29,9 +29,7 @@ __host__ __device__ inline uint32_t make_leaf(uint32_t kind, uint32_t idx) { ret
 __host__ __device__ inline bool ref_is_leaf(uint32_t r) { return (r & REF_LEAF) != 0; }
 __host__ __device__ inline uint32_t ref_kind(uint32_t r) { return (r >> 29) & 3u; }
 __host__ __device__ inline uint32_t ref_index(uint32_t r) { return r & 0x07FFFFFFu; }
-static constexpr uint32_t REF_MAX_INDEX = 0x07FFFFFEu;
-static constexpr uint32_t AXIS_SHIFT = 27;
-static constexpr uint32_t AXIS_MASK = 3u << AXIS_SHIFT;
+static constexpr uint32_t REF_MAX_INDEX = 0x07FFFFFEu;  // bit 27 of a node's first word = BIGBOX_BIT (device_math.cuh)
 
 static constexpr int MAX_TEX_NEST = 8;
 
@@ -102,7 +100,9 @@ template <typename R>
 struct DevScene {
     const NodeRec<R>* nodes;
     const NodeRec<float>* nodes32;  // outward-rounded f32 copy of the boxes (conservative filter of the f64 path)
+    const SphereRec<float>* spheres32;
     float bmax;                     // largest |coordinate| of the root box, rounded up
+    float bsmall;                   // |coordinate| bound of the nodes whose first word has BIGBOX_BIT clear
     const SphereRec<R>* spheres;
     const TriRec<R>* tris;
     const QuadRec<R>* quads;
@@ -165,7 +165,11 @@ struct DevCamera {
     uint32_t row_block, row_rank, row_world, rows_local;
     uint64_t seed;
     uint32_t fb_scale_bits;
-    uint32_t pad;
+    uint32_t is_static;  // no camera keyframes: the basis below is valid for every sample time
+    // camera basis at a fixed time, filled on the DEVICE by k_camera_setup with the same routine the
+    // per-sample path uses (bit-identical): from, pixel_start_location, pixel_delta_u/v, defocus_disk_u/v
+    double s_from[3], s_psl[3], s_pdu[3], s_pdv[3], s_du[3], s_dv[3];
+    float f_from[3], f_psl[3], f_pdu[3], f_pdv[3], f_du[3], f_dv[3];
 };
 
 // ---- small vector helpers --------------------------------------------------------------------------

@@ -345,47 +345,80 @@ __device__ __forceinline__ bool is_finite(R x) {
     return Num<R>::abs_(x) < Num<R>::inf();
 }
 
-// ---- conservative f32 box filter (f64 path only) --------------------------------------------------
-// The reference's decision at a node is  min(best_t, hi_x, hi_y, hi_z) > max(tmin, lo_x, lo_y, lo_z)
+// ---- conservative f32 filters (f64 path) ----------------------------------------------------------
+// BOX.  The reference's decision at a node is  min(best_t, hi_x, hi_y, hi_z) > max(tmin, lo_x, lo_y, lo_z)
 // evaluated in f64.  The same expression evaluated in f32 on the outward-rounded f32 copy of the box
 // differs from the f64 values by at most
 //     |t32 - t64| <= |inv| (|b| 2^-23 + |o| 2^-24)(1 + 2^-22) + 3 * 2^-24 |t64|
-// (rounding of b, o and inv to f32, one subtraction, one multiplication).  With B = the largest
-// |coordinate| of the scene's root box, e = max over axes of |inv|(B 2^-23 + |o| 2^-24) is a per-ray
-// constant, and  E = 2.5 e + 2^-21 (|lo32| + |hi32|)  bounds the error of (hi - lo).  So
-//     hi32 - lo32 >  E  =>  the f64 test passes,     hi32 - lo32 < -E  =>  the f64 test fails,
-// and only the sliver in between (a few % of the tests) is re-decided by the exact f64 test.  The
-// decision taken is therefore ALWAYS the reference's decision; the filter only saves work.
+// (rounding of b, o and inv to f32, one subtraction, one multiplication).  With B an upper bound of the
+// box's |coordinates|, e = max over axes of |inv|(B 2^-23 + |o| 2^-24) is a per-ray constant and
+//     E = 2.5 e + 2^-21 (|lo32| + |hi32|)
+// bounds the error of (hi - lo).  So  hi32 - lo32 > E  =>  the f64 test passes,  hi32 - lo32 < -E  =>  it
+// fails, and only the sliver in between is re-decided by the exact f64 test.  Two bounds are kept per ray:
+// e_big for B = the root box (book1: 2000, because of the r=1000 ground sphere) and e_small for the
+// B_small that covers ~90 % of the nodes; bit 27 of a node's first word says which one applies.
+//
+// SPHERE.  disc = h^2 - a (|oc|^2 - r^2) evaluated in f32 from f32 copies of c, r, o, d differs from the
+// f64 value by at most  2^-17.5 a (|c|^2 + |o|^2 + r^2)  (derivation in DESIGN.md section 5.1), so
+// disc32 < -1.0e-5 a32 (|c|^2+|o|^2+r^2)  =>  the f64 discriminant is negative  =>  Sphere::hit returns None
+// (sphere.rs:79-81).  A leaf node whose primitives are all definite misses is not visited at all.
+//
+// In both cases the decision taken is ALWAYS the reference's decision; the filters only save work.
 struct FilterRay {
-    float ox, oy, oz, ix, iy, iz, e, tmin;
-    bool ok;
+    float ox, oy, oz, ix, iy, iz, dx, dy, dz;
+    float e_small, e_big, o2;
+    bool ok;  // the ray is regular and representable in f32: filters may be used
 };
-__device__ __forceinline__ FilterRay make_filter_ray(V3<double> o, V3<double> inv, double tmin, float bmax, bool regular) {
+static constexpr uint32_t BIGBOX_BIT = 1u << 27;
+static constexpr uint32_t INDEX_MASK = 0x07FFFFFFu;
+
+template <typename R>
+__device__ __forceinline__ FilterRay make_filter_ray(V3<R> o, V3<R> d, V3<R> inv, R tmin, R tmax, float bsmall, float bmax) {
     FilterRay f;
     f.ox = (float)o.x; f.oy = (float)o.y; f.oz = (float)o.z;
     f.ix = (float)inv.x; f.iy = (float)inv.y; f.iz = (float)inv.z;
-    f.tmin = (float)tmin;
-    const float kb = bmax * 1.1920929e-7f;  // B * 2^-23
-    const float ex = fabsf(f.ix) * (kb + fabsf(f.ox) * 5.9604645e-8f);
-    const float ey = fabsf(f.iy) * (kb + fabsf(f.oy) * 5.9604645e-8f);
-    const float ez = fabsf(f.iz) * (kb + fabsf(f.oz) * 5.9604645e-8f);
-    f.e = 2.5f * fmaxf(ex, fmaxf(ey, ez));
-    // the filter is skipped for irregular rays and when f32 cannot represent the ray (overflow / underflow)
-    f.ok = regular && f.e < 3.0e37f && fabsf(f.ix) > 1.0e-30f && fabsf(f.iy) > 1.0e-30f && fabsf(f.iz) > 1.0e-30f;
+    f.dx = (float)d.x; f.dy = (float)d.y; f.dz = (float)d.z;
+    const float ax = fabsf(f.ix), ay = fabsf(f.iy), az = fabsf(f.iz);
+    const float oo_x = fabsf(f.ox) * 5.9604645e-8f, oo_y = fabsf(f.oy) * 5.9604645e-8f, oo_z = fabsf(f.oz) * 5.9604645e-8f;
+    const float ks = bsmall * 1.1920929e-7f, kb = bmax * 1.1920929e-7f;  // B * 2^-23
+    f.e_small = 2.5f * fmaxf(ax * (ks + oo_x), fmaxf(ay * (ks + oo_y), az * (ks + oo_z)));
+    f.e_big = 2.5f * fmaxf(ax * (kb + oo_x), fmaxf(ay * (kb + oo_y), az * (kb + oo_z)));
+    f.o2 = f.ox * f.ox + f.oy * f.oy + f.oz * f.oz;
+    const bool regular = is_finite(o.x) && is_finite(o.y) && is_finite(o.z) && is_finite(inv.x) && is_finite(inv.y) &&
+                         is_finite(inv.z) && inv.x != R(0) && inv.y != R(0) && inv.z != R(0) && !(tmin != tmin) && !(tmax != tmax);
+    // skipped for irregular rays and when f32 cannot represent the ray (overflow / underflow)
+    f.ok = regular && f.e_big < 3.0e37f && ax > 1.0e-30f && ay > 1.0e-30f && az > 1.0e-30f && f.o2 < 1.0e30f;
     return f;
 }
-// +1 = passes, -1 = fails, 0 = undecided (exact f64 test required)
-__device__ __forceinline__ int filter_box(const NodeRec<float>& n, const FilterRay& f, float best) {
+// f32 evaluation of the slab intervals (shared by the filter and by the f32 path's own box test)
+__device__ __forceinline__ void slab32(const NodeRec<float>& n, const FilterRay& f, float tmin, float best, float& lo, float& hi) {
     const float x0 = (n.xmin - f.ox) * f.ix, x1 = (n.xmax - f.ox) * f.ix;
     const float y0 = (n.ymin - f.oy) * f.iy, y1 = (n.ymax - f.oy) * f.iy;
     const float z0 = (n.zmin - f.oz) * f.iz, z1 = (n.zmax - f.oz) * f.iz;
-    const float lo = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), f.tmin));
-    const float hi = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), best));
+    lo = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), tmin));
+    hi = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), best));
+}
+// +1 = passes, -1 = fails, 0 = undecided (exact f64 test required)
+__device__ __forceinline__ int filter_box(const NodeRec<float>& n, const FilterRay& f, float tmin, float best) {
+    float lo, hi;
+    slab32(n, f, tmin, best, lo, hi);
     const float diff = hi - lo;
-    const float E = f.e + 4.7683716e-7f * (fabsf(lo) + fabsf(hi));
+    const float E = ((n.left & BIGBOX_BIT) ? f.e_big : f.e_small) + 4.7683716e-7f * (fabsf(lo) + fabsf(hi));
     if (diff > E) return 1;
     if (diff < -E) return -1;
     return 0;  // also NaN / inf
+}
+// true = Sphere::hit certainly returns None for this ray (f64 discriminant certainly negative)
+__device__ __forceinline__ bool sphere_definite_miss(const SphereRec<float>& s, const FilterRay& f) {
+    const float ocx = s.cx - f.ox, ocy = s.cy - f.oy, ocz = s.cz - f.oz;
+    const float a = f.dx * f.dx + f.dy * f.dy + f.dz * f.dz;
+    const float h = f.dx * ocx + f.dy * ocy + f.dz * ocz;
+    const float c2 = s.cx * s.cx + s.cy * s.cy + s.cz * s.cz;
+    const float r2 = s.r * s.r;
+    const float cq = (ocx * ocx + ocy * ocy + ocz * ocz) - r2;
+    const float disc = h * h - a * cq;
+    const float err = 1.0e-5f * a * (c2 + f.o2 + r2);
+    return disc < -err;  // false for NaN / inf
 }
 
 // ---- warp-persistent closest-hit engine -------------------------------------------------------------
@@ -397,52 +430,82 @@ enum : int { ST_IDLE = 0, ST_NODE = 1, ST_EXACT = 2, ST_LEAF = 3, ST_DONE = 4 };
 // closest t) visits nodes in increasing index order and a failed box test jumps to the node's SKIP
 // link (first node after its subtree).  No stack, no depth limit:
 //     i = 0; while (i < n_nodes) { if (box(i) passes) { test leaf primitives; i = i + 1 } else i = skip(i) }
-// Node words: inner node  a = skip link,            b = split axis (unused here)
-//             leaf node   a = left primitive ref,   b = right primitive ref or REF_NONE   (skip = i + 1)
+// Node words: inner node  a = skip link (+ BIGBOX_BIT),          b = split axis (unused here)
+//             leaf node   a = left primitive ref (+ BIGBOX_BIT), b = right primitive ref or REF_NONE (skip = i + 1)
 // (a node built from a span of 1 or 2 holds its primitives directly, a node built from a span >= 3
 // has two node children: bvhwrapper.rs:57-74.)  Leaves are tested with no box of their own, left
 // first, right with the updated interval, strict comparisons — the reference's order.
+//
+// The per-lane state kept in registers across steps is deliberately small (f32 ray for the cheap steps,
+// closest hit, cursor); the f64 ray is re-read from the ray's record for the rare exact / leaf steps.
 template <typename R>
 struct Trav {
-    V3<R> o, d, inv;
-    R a, tmin, best_t;
+    FilterRay fr;
+    R best_t;
     uint32_t best_ref, i, pl, pr;  // i = next node index; pl/pr = parked leaf primitives
-    bool px, py, pz, regular;
-    __device__ __forceinline__ void init(V3<R> o_, V3<R> d_, R tmin_, R tmax_) {
-        o = o_;
-        d = d_;
-        inv = {R(1) / d.x, R(1) / d.y, R(1) / d.z};  // adinv, bvh.rs:111 (a pure function of the ray)
-        a = vlen2(d);                                // sphere.rs:74
-        tmin = tmin_;
-        best_t = tmax_;
+
+    __device__ __forceinline__ void init(V3<R> o, V3<R> d, R tmin, R tmax, float bsmall, float bmax) {
+        const V3<R> inv = {R(1) / d.x, R(1) / d.y, R(1) / d.z};  // adinv, bvh.rs:111
+        fr = make_filter_ray<R>(o, d, inv, tmin, tmax, bsmall, bmax);
+        best_t = tmax;
         best_ref = REF_MISS;
         i = 0;
         pl = pr = REF_NONE;
-        px = inv.x > R(0);
-        py = inv.y > R(0);
-        pz = inv.z > R(0);
-        regular = is_finite(o.x) && is_finite(o.y) && is_finite(o.z) && is_finite(inv.x) && is_finite(inv.y) && is_finite(inv.z) &&
-                  inv.x != R(0) && inv.y != R(0) && inv.z != R(0) && !(tmin != tmin) && !(best_t != best_t);
     }
     // the box test of node i has been decided
     __device__ __forceinline__ int after_box(bool hit, uint32_t wa, uint32_t wb, uint32_t n_nodes) {
         const bool leafnode = ref_is_leaf(wa);
         const uint32_t here = i;
-        i = (hit || leafnode) ? here + 1u : wa;
+        i = (hit || leafnode) ? here + 1u : (wa & INDEX_MASK);
         if (hit && leafnode) {
-            pl = wa;
+            pl = wa & ~BIGBOX_BIT;
             pr = wb;
             return ST_LEAF;
         }
         return i >= n_nodes ? ST_DONE : ST_NODE;
     }
-    // exact box test of node i in R arithmetic
-    __device__ __forceinline__ int step_exact(const DevScene<R>& sc) {
+    // NODE step.  f64 path: conservative filter (may answer ST_EXACT); f32 path: the f32 box test itself
+    // (regular rays: min/max form == comparison form; irregular rays go to the comparison form in step_exact).
+    // When a leaf node is entered its primitives are pre-filtered: all definite misses => nothing to test.
+    __device__ __forceinline__ int step_node(const DevScene<R>& sc, R tmin) {
+        if (!fr.ok) return ST_EXACT;
+        const NodeRec<float> nf = ldg_rec<2>(sc.nodes32 + i);
+        bool hit;
+        if constexpr (sizeof(R) == 8) {
+            const int dec = filter_box(nf, fr, (float)tmin, (float)best_t);
+            if (dec == 0) return ST_EXACT;
+            hit = dec > 0;
+        } else {
+            float lo, hi;
+            slab32(nf, fr, tmin, best_t, lo, hi);
+            hit = hi > lo;
+        }
+        int st = after_box(hit, nf.left, nf.right, sc.n_nodes);
+        if constexpr (sizeof(R) == 8) {
+            if (st == ST_LEAF) {
+                bool all_miss = true;
+                if (ref_kind(pl) == CR_PRIM_SPHERE) {
+                    all_miss = sphere_definite_miss(ldg_rec<1>(sc.spheres32 + ref_index(pl)), fr);
+                } else {
+                    all_miss = false;
+                }
+                if (all_miss && pr != REF_NONE) {
+                    all_miss = (ref_kind(pr) == CR_PRIM_SPHERE) && sphere_definite_miss(ldg_rec<1>(sc.spheres32 + ref_index(pr)), fr);
+                }
+                if (all_miss) st = i >= sc.n_nodes ? ST_DONE : ST_NODE;
+            }
+        }
+        return st;
+    }
+    // exact box test of node i in R arithmetic on the ray re-read from its record
+    __device__ __forceinline__ int step_exact(const DevScene<R>& sc, V3<R> o, V3<R> d, R tmin) {
+        const V3<R> inv = {R(1) / d.x, R(1) / d.y, R(1) / d.z};
         const NodeRec<R> n = ldg_rec<sizeof(NodeRec<R>) / 16>(sc.nodes + i);
-        const bool hit = regular ? aabb_hit_regular(n, o, inv, px, py, pz, tmin, best_t) : aabb_hit(n, o, inv, tmin, best_t);
+        const bool hit = fr.ok ? aabb_hit_regular(n, o, inv, inv.x > R(0), inv.y > R(0), inv.z > R(0), tmin, best_t)
+                               : aabb_hit(n, o, inv, tmin, best_t);
         return after_box(hit, n.left, n.right, sc.n_nodes);
     }
-    __device__ __forceinline__ void test_prim(const DevScene<R>& sc, uint32_t ref) {
+    __device__ __forceinline__ void test_prim(const DevScene<R>& sc, uint32_t ref, V3<R> o, V3<R> d, R a, R tmin) {
         const uint32_t kind = ref_kind(ref), idx = ref_index(ref);
         R t;
         bool got;
@@ -462,20 +525,20 @@ struct Trav {
             best_ref = ref;
         }
     }
-    __device__ __forceinline__ int step_leaf(const DevScene<R>& sc) {
-        test_prim(sc, pl);
-        if (pr != REF_NONE) test_prim(sc, pr);
+    __device__ __forceinline__ int step_leaf(const DevScene<R>& sc, V3<R> o, V3<R> d, R tmin) {
+        const R a = vlen2(d);  // sphere.rs:74
+        test_prim(sc, pl, o, d, a, tmin);
+        if (pr != REF_NONE) test_prim(sc, pr, o, d, a, tmin);
         return i >= sc.n_nodes ? ST_DONE : ST_NODE;
     }
 };
 
 // Warp-persistent engine.  The warp alternates between
-//   - a NODE phase: up to NODE_SLICE cheap box tests per lane (f64 path: the conservative f32 filter;
-//     f32 path: the f32 test itself).  A lane whose node the filter cannot decide parks in ST_EXACT, a
-//     lane that entered a leaf node parks in ST_LEAF;
-//   - an EXACT phase: the f64 box test for the parked undecided nodes (a few % of the tests);
+//   - a NODE phase: up to node_slice cheap box tests per lane.  A lane whose node the filter cannot
+//     decide parks in ST_EXACT, a lane that entered a leaf node with a possible hit parks in ST_LEAF;
+//   - an EXACT phase: the exact box test for the parked undecided nodes (a few % of the tests);
 //   - a LEAF phase: the primitive tests of the parked leaf nodes.
-// Parking the rare, expensive steps lets them run with many lanes at once instead of dragging the
+// Parking the rare, expensive steps lets them run with several lanes at once instead of dragging the
 // whole warp along for one lane.  Finished lanes are refilled (one atomic per warp) as soon as REFILL
 // of them are idle.  Each lane's own sequence of tests is the reference's, so is the result.
 //   IO::count() / cursor() / load(i,o,d) / commit(has,i,ref,t,o,d)  (commit is warp-synchronous)
@@ -485,13 +548,11 @@ __device__ __forceinline__ void trace_persistent(const DevScene<R>& sc, R tmin, 
     const uint32_t n = io.count();
     const int lane = threadIdx.x & 31;
     Trav<R> tv;
-    tv.regular = true;
+    tv.fr.ok = false;
     tv.i = 0;
     tv.pl = tv.pr = REF_NONE;
     tv.best_ref = REF_MISS;
     tv.best_t = tmax;
-    FilterRay fr;
-    fr.ok = false;
     uint32_t my = 0;
     int st = ST_IDLE;
     bool exhausted = false;
@@ -499,7 +560,11 @@ __device__ __forceinline__ void trace_persistent(const DevScene<R>& sc, R tmin, 
         const uint32_t walking = __ballot_sync(0xffffffffu, st == ST_NODE || st == ST_EXACT || st == ST_LEAF);
         const int n_free = 32 - __popc(walking);
         if ((!exhausted && n_free >= REFILL) || walking == 0u) {  // warp-uniform
-            io.commit(st == ST_DONE, my, tv.best_ref, tv.best_t, tv.o, tv.d);
+            {
+                V3<R> o = {R(0), R(0), R(0)}, d = {R(0), R(0), R(0)};
+                if (st == ST_DONE && io.commit_needs_ray()) io.load(my, o, d);
+                io.commit(st == ST_DONE, my, tv.best_ref, tv.best_t, o, d);
+            }
             if (st == ST_DONE) st = ST_IDLE;
             if (!exhausted) {
                 uint32_t base = 0;
@@ -511,8 +576,7 @@ __device__ __forceinline__ void trace_persistent(const DevScene<R>& sc, R tmin, 
                         V3<R> o, d;
                         io.load(k, o, d);
                         my = k;
-                        tv.init(o, d, tmin, tmax);
-                        if constexpr (sizeof(R) == 8) fr = make_filter_ray(tv.o, tv.inv, tv.tmin, sc.bmax, tv.regular);
+                        tv.init(o, d, tmin, tmax, sc.bsmall, sc.bmax);
                         st = (sc.n_nodes == 0u) ? ST_DONE : ST_NODE;
                     }
                 }
@@ -523,29 +587,16 @@ __device__ __forceinline__ void trace_persistent(const DevScene<R>& sc, R tmin, 
         // ---- NODE phase
 #pragma unroll 1
         for (int k = 0; k < NODE_SLICE; ++k) {
-            if (st == ST_NODE) {
-                if constexpr (sizeof(R) == 8) {
-                    if (fr.ok) {
-                        const NodeRec<float> nf = ldg_rec<2>(sc.nodes32 + tv.i);
-                        const int dec = filter_box(nf, fr, (float)tv.best_t);
-                        st = (dec == 0) ? (int)ST_EXACT : tv.after_box(dec > 0, nf.left, nf.right, sc.n_nodes);
-                    } else {
-                        st = ST_EXACT;
-                    }
-                } else {
-                    st = tv.step_exact(sc);
-                }
-            }
+            if (st == ST_NODE) st = tv.step_node(sc, tmin);
         }
-        // ---- EXACT phase (f64 path only)
-        if constexpr (sizeof(R) == 8) {
-            if (__any_sync(0xffffffffu, st == ST_EXACT)) {
-                if (st == ST_EXACT) st = tv.step_exact(sc);
+        // ---- EXACT + LEAF phases share one re-read of the f64 ray
+        if (__any_sync(0xffffffffu, st == ST_EXACT || st == ST_LEAF)) {
+            if (st == ST_EXACT || st == ST_LEAF) {
+                V3<R> o, d;
+                io.load(my, o, d);
+                if (st == ST_EXACT) st = tv.step_exact(sc, o, d, tmin);
+                if (st == ST_LEAF) st = tv.step_leaf(sc, o, d, tmin);
             }
-        }
-        // ---- LEAF phase
-        if (__any_sync(0xffffffffu, st == ST_LEAF)) {
-            if (st == ST_LEAF) st = tv.step_leaf(sc);
         }
     }
 }

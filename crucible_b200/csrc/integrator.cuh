@@ -121,8 +121,34 @@ __device__ __forceinline__ V3<R> point_at(const double init[3], const CrKeyframe
     }
     return {p[0], p[1], p[2]};
 }
-// One iteration of the sample loop.  Every basis function of the reference is a pure function of t,
-// so evaluating each once gives the same bits as the reference's ~20 re-evaluations.
+// Camera basis at time t.  Every basis function of the reference (rendering_compute.rs:5-111) is a pure
+// function of t, so evaluating each once gives the same bits as the reference's ~20 re-evaluations.
+template <typename R>
+struct CamBasis {
+    V3<R> from, psl, pdu, pdv, du, dv;
+};
+template <typename R>
+__device__ __forceinline__ CamBasis<R> camera_basis(const CrCamera& c, R t) {
+    CamBasis<R> b;
+    const V3<R> from = point_at<R>(c.look_from, c.from_keys, c.n_from_keys, t);
+    const V3<R> at = point_at<R>(c.look_at, c.at_keys, c.n_at_keys, t);
+    const V3<R> vup = {(R)c.vup[0], (R)c.vup[1], (R)c.vup[2]};
+    const V3<R> w = vunit(vsub(from, at));                          // w_basis :88-93
+    const V3<R> u = vunit(vcross(vup, w));                          // u_basis :77-80
+    const V3<R> v = vcross(w, u);                                   // v_basis :82-85
+    const V3<R> vu = vmul((R)c.viewport_width, u);                  // viewport_u :16-19
+    const V3<R> vv = vmul((R)c.viewport_height, vneg(v));           // viewport_v :24-27
+    b.pdu = vdiv(vu, (R)c.image_width);                             // pixel_delta_u :32-35
+    b.pdv = vdiv(vv, (R)c.image_height);                            // pixel_delta_v :40-43
+    const V3<R> ul = vsub(vsub(vsub(from, vmul((R)c.focus_dist, w)), vdiv(vu, R(2))), vdiv(vv, R(2)));  // :49-55
+    b.psl = vadd(ul, vmul(R(0.5), vadd(b.pdu, b.pdv)));             // pixel_start_location :57-60
+    b.du = vmul((R)c.defocus_radius, u);                            // defocus_disk_u/v :95-103
+    b.dv = vmul((R)c.defocus_radius, v);
+    b.from = from;
+    return b;
+}
+template <typename R> __device__ __forceinline__ V3<R> ld3(const double* p) { return {(R)p[0], (R)p[1], (R)p[2]}; }
+// One iteration of the sample loop, ray_casting.rs:82-104
 template <typename R>
 __device__ __forceinline__ void camera_sample(const DevCamera& cam, uint32_t i, uint32_t j, Rng<R>& g, V3<R>& ro, V3<R>& rd,
                                               R& tm) {
@@ -130,31 +156,44 @@ __device__ __forceinline__ void camera_sample(const DevCamera& cam, uint32_t i, 
     const R current_time = (R)c.frame * (R(1) / (R)c.frame_rate);
     const R shutter_length = ((R)c.shutter_angle / R(360)) * (R(1) / (R)c.frame_rate);
     const R t = current_time + g.range(R(0), shutter_length);
-    const V3<R> from = point_at<R>(c.look_from, c.from_keys, c.n_from_keys, t);
-    const V3<R> at = point_at<R>(c.look_at, c.at_keys, c.n_at_keys, t);
+    CamBasis<R> b;
+    if (cam.is_static) {  // no keyframes: the basis does not depend on t (k_camera_setup computed it once)
+        if constexpr (sizeof(R) == 8) {
+            b.from = ld3<R>(cam.s_from); b.psl = ld3<R>(cam.s_psl); b.pdu = ld3<R>(cam.s_pdu);
+            b.pdv = ld3<R>(cam.s_pdv); b.du = ld3<R>(cam.s_du); b.dv = ld3<R>(cam.s_dv);
+        } else {
+            b.from = {cam.f_from[0], cam.f_from[1], cam.f_from[2]}; b.psl = {cam.f_psl[0], cam.f_psl[1], cam.f_psl[2]};
+            b.pdu = {cam.f_pdu[0], cam.f_pdu[1], cam.f_pdu[2]}; b.pdv = {cam.f_pdv[0], cam.f_pdv[1], cam.f_pdv[2]};
+            b.du = {cam.f_du[0], cam.f_du[1], cam.f_du[2]}; b.dv = {cam.f_dv[0], cam.f_dv[1], cam.f_dv[2]};
+        }
+    } else {
+        b = camera_basis<R>(c, t);
+    }
     const R ox = g.next() - R(0.5);  // sample_square, camera/mod.rs:369-376
     const R oy = g.next() - R(0.5);
-    const V3<R> vup = {(R)c.vup[0], (R)c.vup[1], (R)c.vup[2]};
-    const V3<R> w = vunit(vsub(from, at));                          // w_basis :88-93
-    const V3<R> u = vunit(vcross(vup, w));                          // u_basis :77-80
-    const V3<R> v = vcross(w, u);                                   // v_basis :82-85
-    const V3<R> vu = vmul((R)c.viewport_width, u);                  // viewport_u :16-19
-    const V3<R> vv = vmul((R)c.viewport_height, vneg(v));           // viewport_v :24-27
-    const V3<R> pdu = vdiv(vu, (R)c.image_width);                   // pixel_delta_u :32-35
-    const V3<R> pdv = vdiv(vv, (R)c.image_height);                  // pixel_delta_v :40-43
-    const V3<R> ul = vsub(vsub(vsub(from, vmul((R)c.focus_dist, w)), vdiv(vu, R(2))), vdiv(vv, R(2)));  // :49-55
-    const V3<R> psl = vadd(ul, vmul(R(0.5), vadd(pdu, pdv)));       // pixel_start_location :57-60
-    const V3<R> ps = vadd(vadd(psl, vmul((R)i + ox, pdu)), vmul((R)j + oy, pdv));  // get_pixel_pos :64-68
-    V3<R> orig = from;
+    const V3<R> ps = vadd(vadd(b.psl, vmul((R)i + ox, b.pdu)), vmul((R)j + oy, b.pdv));  // get_pixel_pos :64-68
+    V3<R> orig = b.from;
     if (!(c.defocus_angle <= 0.0)) {                                // ray_casting.rs:96-100
         const V3<R> p = random_in_unit_disk(g);                     // defocus_disk_sample :105-110
-        const V3<R> du = vmul((R)c.defocus_radius, u);
-        const V3<R> dv = vmul((R)c.defocus_radius, v);
-        orig = vadd(vadd(from, vmul(p.x, du)), vmul(p.y, dv));
+        orig = vadd(vadd(b.from, vmul(p.x, b.du)), vmul(p.y, b.dv));
     }
     ro = orig;
     rd = vsub(ps, orig);
     tm = t;
+}
+// fills the static basis of a keyframe-free camera (one thread)
+template <typename R>
+__global__ void k_camera_setup(DevCamera* cam) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const CamBasis<R> b = camera_basis<R>(cam->c, R(0));
+    const V3<R> v[6] = {b.from, b.psl, b.pdu, b.pdv, b.du, b.dv};
+    if constexpr (sizeof(R) == 8) {
+        double* dst[6] = {cam->s_from, cam->s_psl, cam->s_pdu, cam->s_pdv, cam->s_du, cam->s_dv};
+        for (int k = 0; k < 6; ++k) { dst[k][0] = v[k].x; dst[k][1] = v[k].y; dst[k][2] = v[k].z; }
+    } else {
+        float* dst[6] = {cam->f_from, cam->f_psl, cam->f_pdu, cam->f_pdv, cam->f_du, cam->f_dv};
+        for (int k = 0; k < 6; ++k) { dst[k][0] = v[k].x; dst[k][1] = v[k].y; dst[k][2] = v[k].z; }
+    }
 }
 
 // local (per-rank) row -> global row: rows j with (j / row_block) % row_world == row_rank, in order
@@ -254,6 +293,7 @@ struct RenderTraceIO {
             d = {a.w, b.x, b.y};
         }
     }
+    __device__ __forceinline__ bool commit_needs_ray() const { return false; }
     __device__ __forceinline__ void commit(bool has, uint32_t i, uint32_t ref, R t, V3<R>, V3<R>) const {
         int q = -1;
         if (has) {
@@ -441,6 +481,7 @@ struct BatchTraceIO {
         o = {(R)r[0], (R)r[1], (R)r[2]};
         d = {(R)r[3], (R)r[4], (R)r[5]};
     }
+    __device__ __forceinline__ bool commit_needs_ray() const { return true; }
     __device__ __forceinline__ void commit(bool has, uint32_t i, uint32_t ref, R t, V3<R> o, V3<R> d) const {
         if (!has) return;
         CrHit h;
@@ -472,7 +513,9 @@ static DevScene<R> make_dev_scene(const SceneDeviceData& s) {
     const int k = (sizeof(R) == 8) ? 0 : 1;
     d.nodes = reinterpret_cast<const NodeRec<R>*>(s.nodes[k]);
     d.nodes32 = reinterpret_cast<const NodeRec<float>*>(s.nodes[1]);
+    d.spheres32 = reinterpret_cast<const SphereRec<float>*>(s.spheres[1]);
     d.bmax = s.bmax;
+    d.bsmall = s.bsmall;
     d.spheres = reinterpret_cast<const SphereRec<R>*>(s.spheres[k]);
     d.tris = reinterpret_cast<const TriRec<R>*>(s.tris[k]);
     d.quads = reinterpret_cast<const QuadRec<R>*>(s.quads[k]);
@@ -615,6 +658,7 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
     hcam.rows_local = rows_local;
     hcam.seed = opts.seed;
     hcam.fb_scale_bits = scale_bits;
+    hcam.is_static = (cam_in.n_from_keys == 0 && cam_in.n_at_keys == 0) ? 1u : 0u;
     Control hctl;
     memset(&hctl, 0, sizeof(hctl));
     hctl.total_samples = total;
@@ -667,8 +711,12 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
     for (int i = 0; i < RING; ++i) CRB_CUDA(cudaEventCreateWithFlags(&ring_ev[i], cudaEventDisableTiming));
 
     cudaEvent_t a;
-    // prologue: plan + raygen fill side 0
+    // prologue: camera basis (static cameras), plan + raygen fill side 0
     tm.begin(2, a);
+    if (hcam.is_static) {
+        k_camera_setup<R><<<1, 32, 0, stream>>>(d_cam);
+        ++launches;
+    }
     k_plan<<<1, 32, 0, stream>>>(ctl, 0, nullptr);
     k_raygen<R><<<g_gen, SHADE_BLOCK, 0, stream>>>(ctl, d_cam, paths[0]);
     tm.end(2, a);

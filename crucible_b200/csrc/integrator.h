@@ -23,6 +23,7 @@ struct SceneDeviceData {
     int32_t sky_kind = CR_SKY_DEFAULT, sky_image = -1;
     int32_t clamp_colors = 1;
     float bmax = 0.f;            // largest |coordinate| of the root box (f32, rounded up)
+    float bsmall = 0.f;          // bound of the nodes without BIGBOX_BIT
     double max_radiance = 1.0;  // largest per-sample colour component (1 unless the scene holds an Emissive)
     int num_sms = 148;
     int node_slice = 4;
