@@ -345,8 +345,8 @@ __device__ __forceinline__ bool is_finite(R x) {
     return Num<R>::abs_(x) < Num<R>::inf();
 }
 
-// ---- conservative f32 box filter (f64 path) -------------------------------------------------------
-// The reference's decision at a node is  min(best_t, hi_x, hi_y, hi_z) > max(tmin, lo_x, lo_y, lo_z)
+// ---- conservative f32 filters (f64 path) ----------------------------------------------------------
+// BOX.  The reference's decision at a node is  min(best_t, hi_x, hi_y, hi_z) > max(tmin, lo_x, lo_y, lo_z)
 // evaluated in f64.  The same expression evaluated in f32 on the outward-rounded f32 copy of the box
 // differs from the f64 values by at most
 //     |t32 - t64| <= |inv| (|b| 2^-23 + |o| 2^-24)(1 + 2^-22) + 3 * 2^-24 |t64|
@@ -358,7 +358,12 @@ __device__ __forceinline__ bool is_finite(R x) {
 // e_big for B = the root box (book1: 2000, because of the r=1000 ground sphere) and e_small for the
 // B_small that covers ~90 % of the nodes; bit 27 of a node's first word says which one applies.
 //
-// The decision taken is ALWAYS the reference's decision; the filter only saves work.
+// SPHERE.  disc = h^2 - a (|oc|^2 - r^2) evaluated in f32 from f32 copies of c, r, o, d differs from the
+// f64 value by at most  2^-17.5 a (|c|^2 + |o|^2 + r^2)  (derivation in DESIGN.md section 5.1), so
+// disc32 < -1.0e-5 a32 (|c|^2+|o|^2+r^2)  =>  the f64 discriminant is negative  =>  Sphere::hit returns None
+// (sphere.rs:79-81).  A leaf node whose primitives are all definite misses is not visited at all.
+//
+// In both cases the decision taken is ALWAYS the reference's decision; the filters only save work.
 struct FilterRay {
     float ox, oy, oz, ix, iy, iz, dx, dy, dz;
     float e_small, e_big, o2;
@@ -403,7 +408,20 @@ __device__ __forceinline__ int filter_box(const NodeRec<float>& n, const FilterR
     if (diff < -E) return -1;
     return 0;  // also NaN / inf
 }
-// ---- block-pooled closest-hit engine ------------------------------------------------------------------
+// true = Sphere::hit certainly returns None for this ray (f64 discriminant certainly negative)
+__device__ __forceinline__ bool sphere_definite_miss(const SphereRec<float>& s, const FilterRay& f) {
+    const float ocx = s.cx - f.ox, ocy = s.cy - f.oy, ocz = s.cz - f.oz;
+    const float a = f.dx * f.dx + f.dy * f.dy + f.dz * f.dz;
+    const float h = f.dx * ocx + f.dy * ocy + f.dz * ocz;
+    const float c2 = s.cx * s.cx + s.cy * s.cy + s.cz * s.cz;
+    const float r2 = s.r * s.r;
+    const float cq = (ocx * ocx + ocy * ocy + ocz * ocz) - r2;
+    const float disc = h * h - a * cq;
+    const float err = 1.0e-5f * a * (c2 + f.o2 + r2);
+    return disc < -err;  // false for NaN / inf
+}
+
+// ---- warp-persistent closest-hit engine -------------------------------------------------------------
 // Lane states
 enum : int { ST_IDLE = 0, ST_NODE = 1, ST_EXACT = 2, ST_LEAF = 3, ST_DONE = 4 };
 
@@ -418,35 +436,22 @@ enum : int { ST_IDLE = 0, ST_NODE = 1, ST_EXACT = 2, ST_LEAF = 3, ST_DONE = 4 };
 // has two node children: bvhwrapper.rs:57-74.)  Leaves are tested with no box of their own, left
 // first, right with the updated interval, strict comparisons — the reference's order.
 //
-// SIMT organisation.  Each lane owns one ray and runs ONLY the cheap step in its own control flow: the
-// f32 box filter (f64 path) or the f32 box test (f32 path), NODE_SLICE of them per round.  Everything
-// rare and expensive is posted as a TASK into shared memory and executed by densely packed threads of
-// the block between two barriers:
-//     EXACT  exact R-arithmetic box test of a node the filter could not decide (+ its leaves if it is a
-//            leaf node that passes)
-//     LEAF   the primitive tests of a leaf node whose box passed
-//     REFILL commit a finished ray (result + material queue) and fetch / initialise the next one
-// So a task kind runs with full warps no matter how few lanes of any one warp needed it.  Each ray's
-// own sequence of tests is untouched, therefore so is the result.
-struct PoolTask {
-    uint32_t ray, a, b, owner;
-    double best;
-    uint32_t i, ok;
-};
-struct PoolResult {
-    float f[12];
-    double best;
-    uint32_t best_ref, i, ray, st;
-    uint32_t ok, pad0;
-};
-static_assert(sizeof(PoolTask) == 32 && sizeof(PoolResult) == 80, "pool records");
-
+// The per-lane state kept in registers across steps is deliberately small (f32 ray for the cheap steps,
+// closest hit, cursor); the f64 ray is re-read from the ray's record for the rare exact / leaf steps.
 template <typename R>
 struct Trav {
     FilterRay fr;
     R best_t;
-    uint32_t best_ref, i, pl, pr;  // i = next node index; pl/pr = primitives of the entered leaf node
+    uint32_t best_ref, i, pl, pr;  // i = next node index; pl/pr = parked leaf primitives
 
+    __device__ __forceinline__ void init(V3<R> o, V3<R> d, R tmin, R tmax, float bsmall, float bmax) {
+        const V3<R> inv = {R(1) / d.x, R(1) / d.y, R(1) / d.z};  // adinv, bvh.rs:111
+        fr = make_filter_ray<R>(o, d, inv, tmin, tmax, bsmall, bmax);
+        best_t = tmax;
+        best_ref = REF_MISS;
+        i = 0;
+        pl = pr = REF_NONE;
+    }
     // the box test of node i has been decided
     __device__ __forceinline__ int after_box(bool hit, uint32_t wa, uint32_t wb, uint32_t n_nodes) {
         const bool leafnode = ref_is_leaf(wa);
@@ -460,7 +465,8 @@ struct Trav {
         return i >= n_nodes ? ST_DONE : ST_NODE;
     }
     // NODE step.  f64 path: conservative filter (may answer ST_EXACT); f32 path: the f32 box test itself
-    // (regular rays: min/max form == comparison form; irregular rays take the comparison form as a task).
+    // (regular rays: min/max form == comparison form; irregular rays go to the comparison form in step_exact).
+    // When a leaf node is entered its primitives are pre-filtered: all definite misses => nothing to test.
     __device__ __forceinline__ int step_node(const DevScene<R>& sc, R tmin) {
         if (!fr.ok) return ST_EXACT;
         const NodeRec<float> nf = ldg_rec<2>(sc.nodes32 + i);
@@ -474,162 +480,122 @@ struct Trav {
             slab32(nf, fr, tmin, best_t, lo, hi);
             hit = hi > lo;
         }
-        return after_box(hit, nf.left, nf.right, sc.n_nodes);
+        int st = after_box(hit, nf.left, nf.right, sc.n_nodes);
+        if constexpr (sizeof(R) == 8) {
+            if (st == ST_LEAF) {
+                bool all_miss = true;
+                if (ref_kind(pl) == CR_PRIM_SPHERE) {
+                    all_miss = sphere_definite_miss(ldg_rec<1>(sc.spheres32 + ref_index(pl)), fr);
+                } else {
+                    all_miss = false;
+                }
+                if (all_miss && pr != REF_NONE) {
+                    all_miss = (ref_kind(pr) == CR_PRIM_SPHERE) && sphere_definite_miss(ldg_rec<1>(sc.spheres32 + ref_index(pr)), fr);
+                }
+                if (all_miss) st = i >= sc.n_nodes ? ST_DONE : ST_NODE;
+            }
+        }
+        return st;
+    }
+    // exact box test of node i in R arithmetic on the ray re-read from its record
+    __device__ __forceinline__ int step_exact(const DevScene<R>& sc, V3<R> o, V3<R> d, R tmin) {
+        const V3<R> inv = {R(1) / d.x, R(1) / d.y, R(1) / d.z};
+        const NodeRec<R> n = ldg_rec<sizeof(NodeRec<R>) / 16>(sc.nodes + i);
+        const bool hit = fr.ok ? aabb_hit_regular(n, o, inv, inv.x > R(0), inv.y > R(0), inv.z > R(0), tmin, best_t)
+                               : aabb_hit(n, o, inv, tmin, best_t);
+        return after_box(hit, n.left, n.right, sc.n_nodes);
+    }
+    __device__ __forceinline__ void test_prim(const DevScene<R>& sc, uint32_t ref, V3<R> o, V3<R> d, R a, R tmin) {
+        const uint32_t kind = ref_kind(ref), idx = ref_index(ref);
+        R t;
+        bool got;
+        if (kind == CR_PRIM_SPHERE) {
+            const SphereRec<R> s = ldg_rec<sizeof(SphereRec<R>) / 16>(sc.spheres + idx);
+            got = sphere_hit_t(s, o, d, a, tmin, best_t, t);
+        } else if (kind == CR_PRIM_TRIANGLE) {
+            const TriRec<R> tr = ldg_rec<sizeof(TriRec<R>) / 16>(sc.tris + idx);
+            got = tri_hit_t(tr, o, d, tmin, best_t, t);
+        } else {
+            const QuadRec<R> q = ldg_rec<sizeof(QuadRec<R>) / 16>(sc.quads + idx);
+            R al, be;
+            got = quad_hit_t(q, o, d, tmin, best_t, t, al, be);
+        }
+        if (got) {
+            best_t = t;
+            best_ref = ref;
+        }
+    }
+    __device__ __forceinline__ int step_leaf(const DevScene<R>& sc, V3<R> o, V3<R> d, R tmin) {
+        const R a = vlen2(d);  // sphere.rs:74
+        test_prim(sc, pl, o, d, a, tmin);
+        if (pr != REF_NONE) test_prim(sc, pr, o, d, a, tmin);
+        return i >= sc.n_nodes ? ST_DONE : ST_NODE;
     }
 };
 
-template <typename R>
-__device__ __forceinline__ void pool_test_prim(const DevScene<R>& sc, uint32_t ref, V3<R> o, V3<R> d, R a, R tmin, R& best_t,
-                                               uint32_t& best_ref) {
-    const uint32_t kind = ref_kind(ref), idx = ref_index(ref);
-    R t;
-    bool got;
-    if (kind == CR_PRIM_SPHERE) {
-        const SphereRec<R> s = ldg_rec<sizeof(SphereRec<R>) / 16>(sc.spheres + idx);
-        got = sphere_hit_t(s, o, d, a, tmin, best_t, t);
-    } else if (kind == CR_PRIM_TRIANGLE) {
-        const TriRec<R> tr = ldg_rec<sizeof(TriRec<R>) / 16>(sc.tris + idx);
-        got = tri_hit_t(tr, o, d, tmin, best_t, t);
-    } else {
-        const QuadRec<R> q = ldg_rec<sizeof(QuadRec<R>) / 16>(sc.quads + idx);
-        R al, be;
-        got = quad_hit_t(q, o, d, tmin, best_t, t, al, be);
-    }
-    if (got) {
-        best_t = t;
-        best_ref = ref;
-    }
-}
-
-//   IO::count() / cursor() / load(i,o,d) / commit_needs_ray() / commit(has,i,ref,t,o,d)  (commit is warp-synchronous)
-template <typename R, int BLOCK, typename IO>
-__device__ __forceinline__ void trace_pooled(const DevScene<R>& sc, R tmin, R tmax, IO& io) {
-    __shared__ PoolTask s_task[BLOCK];    // EXACT tasks from the front, LEAF tasks from the back
-    __shared__ PoolTask s_refill[BLOCK];  // REFILL tasks from the front
-    __shared__ PoolResult s_res[BLOCK];   // indexed by owner thread
-    __shared__ uint32_t s_cnt[2][4];
+// Warp-persistent engine.  The warp alternates between
+//   - a NODE phase: up to node_slice cheap box tests per lane.  A lane whose node the filter cannot
+//     decide parks in ST_EXACT, a lane that entered a leaf node with a possible hit parks in ST_LEAF;
+//   - an EXACT phase: the exact box test for the parked undecided nodes (a few % of the tests);
+//   - a LEAF phase: the primitive tests of the parked leaf nodes.
+// Parking the rare, expensive steps lets them run with several lanes at once instead of dragging the
+// whole warp along for one lane.  Finished lanes are refilled (one atomic per warp) as soon as REFILL
+// of them are idle.  Each lane's own sequence of tests is the reference's, so is the result.
+//   IO::count() / cursor() / load(i,o,d) / commit(has,i,ref,t,o,d)  (commit is warp-synchronous)
+template <typename R, bool EXACT, int REFILL, typename IO>
+__device__ __forceinline__ void trace_persistent(const DevScene<R>& sc, R tmin, R tmax, IO& io) {
     const int NODE_SLICE = sc.node_slice;
     const uint32_t n = io.count();
-    const uint32_t tid = threadIdx.x;
-    const int lane = tid & 31;
+    const int lane = threadIdx.x & 31;
     Trav<R> tv;
     tv.fr.ok = false;
     tv.i = 0;
     tv.pl = tv.pr = REF_NONE;
     tv.best_ref = REF_MISS;
     tv.best_t = tmax;
-    uint32_t my = REF_MISS;  // no ray yet
-    int st = ST_DONE;        // "finished, nothing to commit": the first round fetches a ray
-    if (tid < 8) s_cnt[tid >> 2][tid & 3] = 0;
-    __syncthreads();
-    for (uint32_t round = 0;; ++round) {
-        uint32_t* cnt = s_cnt[round & 1];
-        // ---- NODE phase: the only per-lane control flow
+    uint32_t my = 0;
+    int st = ST_IDLE;
+    bool exhausted = false;
+    for (;;) {
+        const uint32_t walking = __ballot_sync(0xffffffffu, st == ST_NODE || st == ST_EXACT || st == ST_LEAF);
+        const int n_free = 32 - __popc(walking);
+        if ((!exhausted && n_free >= REFILL) || walking == 0u) {  // warp-uniform
+            {
+                V3<R> o = {R(0), R(0), R(0)}, d = {R(0), R(0), R(0)};
+                if (st == ST_DONE && io.commit_needs_ray()) io.load(my, o, d);
+                io.commit(st == ST_DONE, my, tv.best_ref, tv.best_t, o, d);
+            }
+            if (st == ST_DONE) st = ST_IDLE;
+            if (!exhausted) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(io.cursor(), (uint32_t)n_free);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (st == ST_IDLE) {
+                    const uint32_t k = base + (uint32_t)__popc(~walking & ((1u << lane) - 1u));
+                    if (k < n) {
+                        V3<R> o, d;
+                        io.load(k, o, d);
+                        my = k;
+                        tv.init(o, d, tmin, tmax, sc.bsmall, sc.bmax);
+                        st = (sc.n_nodes == 0u) ? ST_DONE : ST_NODE;
+                    }
+                }
+                if (base + (uint32_t)n_free >= n) exhausted = true;
+            }
+            if (__ballot_sync(0xffffffffu, st != ST_IDLE) == 0u) break;  // nothing walking, nothing pending
+        }
+        // ---- NODE phase
 #pragma unroll 1
         for (int k = 0; k < NODE_SLICE; ++k) {
             if (st == ST_NODE) st = tv.step_node(sc, tmin);
         }
-        // ---- post tasks
-        if (st == ST_EXACT) {
-            const uint32_t slot = atomicAdd(&cnt[0], 1u);
-            s_task[slot] = PoolTask{my, 0u, 0u, tid, (double)tv.best_t, tv.i, tv.fr.ok ? 1u : 0u};
-            s_res[tid].best_ref = tv.best_ref;
-        } else if (st == ST_LEAF) {
-            const uint32_t slot = (uint32_t)BLOCK - 1u - atomicAdd(&cnt[1], 1u);
-            s_task[slot] = PoolTask{my, tv.pl, tv.pr, tid, (double)tv.best_t, tv.i, 1u};
-            s_res[tid].best_ref = tv.best_ref;
-        } else if (st == ST_DONE) {
-            const uint32_t slot = atomicAdd(&cnt[2], 1u);
-            s_refill[slot] = PoolTask{my, tv.best_ref, 0u, tid, (double)tv.best_t, 0u, 0u};
-        }
-        if (!__syncthreads_or(st != ST_IDLE)) break;
-        const uint32_t nE = cnt[0], nL = cnt[1], nR = cnt[2];
-        if (tid == 0) {
-            uint32_t* nxt = s_cnt[(round + 1) & 1];
-            nxt[0] = nxt[1] = nxt[2] = 0;
-        }
-        // ---- EXACT tasks (threads 0..nE) and LEAF tasks (threads BLOCK-nL..BLOCK): packed warps
-        if (tid < nE || tid >= (uint32_t)BLOCK - nL) {
-            const PoolTask t = s_task[tid];
-            V3<R> o, d;
-            io.load(t.ray, o, d);
-            R best_t = (R)t.best;
-            uint32_t best_ref = s_res[t.owner].best_ref;
-            uint32_t ni = t.i, pl = t.a, pr = t.b;
-            bool leaf = true;
-            if (tid < nE) {  // exact box test in R arithmetic
-                const V3<R> inv = {R(1) / d.x, R(1) / d.y, R(1) / d.z};  // adinv, bvh.rs:111
-                const NodeRec<R> nd = ldg_rec<sizeof(NodeRec<R>) / 16>(sc.nodes + t.i);
-                const bool hit = t.ok ? aabb_hit_regular(nd, o, inv, inv.x > R(0), inv.y > R(0), inv.z > R(0), tmin, best_t)
-                                      : aabb_hit(nd, o, inv, tmin, best_t);
-                const bool leafnode = ref_is_leaf(nd.left);
-                ni = (hit || leafnode) ? t.i + 1u : (nd.left & INDEX_MASK);
-                leaf = hit && leafnode;
-                pl = nd.left & ~BIGBOX_BIT;
-                pr = nd.right;
-            }
-            if (leaf) {  // left primitive, then right with the updated interval; no boxes (bvhwrapper.rs:108-119)
-                const R a = vlen2(d);  // sphere.rs:74
-                pool_test_prim(sc, pl, o, d, a, tmin, best_t, best_ref);
-                if (pr != REF_NONE) pool_test_prim(sc, pr, o, d, a, tmin, best_t, best_ref);
-            }
-            PoolResult& r = s_res[t.owner];
-            r.best = (double)best_t;
-            r.best_ref = best_ref;
-            r.i = ni;
-        }
-        // ---- REFILL tasks: commit the finished ray, fetch and initialise the next one
-        if ((tid & ~31u) < nR) {  // warp-uniform
-            const bool has = tid < nR;
-            PoolTask t = PoolTask{REF_MISS, REF_MISS, 0u, 0u, 0.0, 0u, 0u};
-            if (has) t = s_refill[tid];
-            const bool fin = has && t.ray != REF_MISS;
-            {
-                V3<R> o = {R(0), R(0), R(0)}, d = {R(0), R(0), R(0)};
-                if (fin && io.commit_needs_ray()) io.load(t.ray, o, d);
-                io.commit(fin, t.ray, t.a, (R)t.best, o, d);
-            }
-            const uint32_t m = __ballot_sync(0xffffffffu, has);
-            uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(io.cursor(), (uint32_t)__popc(m));  // warp-level work fetch
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (has) {
-                const uint32_t k = base + (uint32_t)__popc(m & ((1u << lane) - 1u));
-                PoolResult& r = s_res[t.owner];
-                if (k < n) {
-                    V3<R> o, d;
-                    io.load(k, o, d);
-                    const V3<R> inv = {R(1) / d.x, R(1) / d.y, R(1) / d.z};
-                    const FilterRay f = make_filter_ray<R>(o, d, inv, tmin, tmax, sc.bsmall, sc.bmax);
-                    r.f[0] = f.ox; r.f[1] = f.oy; r.f[2] = f.oz; r.f[3] = f.ix; r.f[4] = f.iy; r.f[5] = f.iz;
-                    r.f[6] = f.dx; r.f[7] = f.dy; r.f[8] = f.dz; r.f[9] = f.e_small; r.f[10] = f.e_big; r.f[11] = f.o2;
-                    r.ok = f.ok ? 1u : 0u;
-                    r.ray = k;
-                    r.st = (sc.n_nodes == 0u) ? (uint32_t)ST_DONE : (uint32_t)ST_NODE;
-                } else {
-                    r.st = ST_IDLE;
-                }
-            }
-        }
-        __syncthreads();
-        // ---- owners pick their results up
-        if (st == ST_EXACT || st == ST_LEAF) {
-            const PoolResult& r = s_res[tid];
-            tv.best_t = (R)r.best;
-            tv.best_ref = r.best_ref;
-            tv.i = r.i;
-            st = tv.i >= sc.n_nodes ? ST_DONE : ST_NODE;
-        } else if (st == ST_DONE) {
-            const PoolResult& r = s_res[tid];
-            st = (int)r.st;
-            if (st != ST_IDLE) {
-                tv.fr.ox = r.f[0]; tv.fr.oy = r.f[1]; tv.fr.oz = r.f[2]; tv.fr.ix = r.f[3]; tv.fr.iy = r.f[4]; tv.fr.iz = r.f[5];
-                tv.fr.dx = r.f[6]; tv.fr.dy = r.f[7]; tv.fr.dz = r.f[8]; tv.fr.e_small = r.f[9]; tv.fr.e_big = r.f[10]; tv.fr.o2 = r.f[11];
-                tv.fr.ok = r.ok != 0u;
-                my = r.ray;
-                tv.i = 0;
-                tv.best_t = tmax;
-                tv.best_ref = REF_MISS;
+        // ---- EXACT + LEAF phases share one re-read of the f64 ray
+        if (__any_sync(0xffffffffu, st == ST_EXACT || st == ST_LEAF)) {
+            if (st == ST_EXACT || st == ST_LEAF) {
+                V3<R> o, d;
+                io.load(my, o, d);
+                if (st == ST_EXACT) st = tv.step_exact(sc, o, d, tmin);
+                if (st == ST_LEAF) st = tv.step_leaf(sc, o, d, tmin);
             }
         }
     }

@@ -14,7 +14,7 @@
 
 namespace crb {
 
-static constexpr int TRACE_BLOCK = 256;
+static constexpr int TRACE_BLOCK = 128;
 static constexpr int SHADE_BLOCK = 128;
 
 // ---- warp-aggregated append (one atomic per warp per destination) --------------------------------
@@ -266,6 +266,9 @@ __global__ void __launch_bounds__(SHADE_BLOCK) k_raygen(const Control* __restric
 
 // trace: persistent threads with warp-level work fetch and lane refill (trace_persistent), stackless
 // threaded traversal, 128-bit node / primitive loads, then classification of the finished rays into their material queues with one atomic per warp per queue.
+#ifndef CRB_REFILL
+#define CRB_REFILL 24
+#endif
 template <typename R>
 struct RenderTraceIO {
     const DevScene<R>& sc;
@@ -309,11 +312,11 @@ struct RenderTraceIO {
     }
 };
 
-template <typename R, int MINB>
+template <typename R, bool EXACT, int REFILL, int MINB>
 __global__ void __launch_bounds__(TRACE_BLOCK, MINB) k_trace(DevScene<R> sc, PathRec<R>* __restrict__ paths, Control* __restrict__ ctl,
-                                                              int side, uint32_t* __restrict__ queues, uint32_t pool) {
+                                                        int side, uint32_t* __restrict__ queues, uint32_t pool) {
     RenderTraceIO<R> io{sc, paths, ctl, queues, ctl->n_in[side], pool};
-    trace_pooled<R, TRACE_BLOCK>(sc, R(0.001), Num<R>::inf(), io);  // ray_casting.rs:119
+    trace_persistent<R, EXACT, REFILL>(sc, R(0.001), Num<R>::inf(), io);  // ray_casting.rs:119
 }
 
 // fixed-point accumulation: order independent => bit-reproducible for any schedule and GPU count
@@ -496,11 +499,11 @@ struct BatchTraceIO {
         out[i] = h;
     }
 };
-template <typename R>
-__global__ void __launch_bounds__(TRACE_BLOCK, 2) k_trace_batch(DevScene<R> sc, const double* __restrict__ rays, uint32_t n, double tmin,
-                                                                 double tmax, CrHit* __restrict__ out, uint32_t* __restrict__ cursor) {
+template <typename R, bool EXACT>
+__global__ void __launch_bounds__(TRACE_BLOCK) k_trace_batch(DevScene<R> sc, const double* __restrict__ rays, uint32_t n, double tmin,
+                                                              double tmax, CrHit* __restrict__ out, uint32_t* __restrict__ cursor) {
     BatchTraceIO<R> io{sc, rays, out, cursor, n};
-    trace_pooled<R, TRACE_BLOCK>(sc, (R)tmin, (R)tmax, io);
+    trace_persistent<R, EXACT, CRB_REFILL>(sc, (R)tmin, (R)tmax, io);
 }
 
 // ---- host side: typed view of the scene + wavefront driver -----------------------------------------
@@ -553,12 +556,13 @@ int trace_batch_impl(const SceneDeviceData& s, const double* d_rays, size_t n, d
         err = "trace_batch: more than 2^32 rays in one call";
         return CR_ERR_LIMIT;
     }
+    constexpr bool EXACT = sizeof(R) == 8;
     const DevScene<R> sc = make_dev_scene<R>(s);
-    int grid = persistent_grid(k_trace_batch<R>, TRACE_BLOCK, s.num_sms);
+    int grid = persistent_grid(k_trace_batch<R, EXACT>, TRACE_BLOCK, s.num_sms);
     const size_t need = (n + TRACE_BLOCK - 1) / TRACE_BLOCK;
     if ((size_t)grid > need) grid = (int)need;
     CRB_CUDA(cudaMemsetAsync(d_cursor, 0, sizeof(uint32_t), stream));
-    k_trace_batch<R><<<grid, TRACE_BLOCK, 0, stream>>>(sc, d_rays, (uint32_t)n, tmin, tmax, d_out, d_cursor);
+    k_trace_batch<R, EXACT><<<grid, TRACE_BLOCK, 0, stream>>>(sc, d_rays, (uint32_t)n, tmin, tmax, d_out, d_cursor);
     CRB_CUDA(cudaGetLastError());
     return CR_OK;
 }
@@ -597,6 +601,7 @@ struct EventTimer {
 template <typename R>
 int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in, const CrRenderOpts& opts, void* d_out_rgb,
                 void* d_out_rgb8, int packed, cudaStream_t stream, CrStats* stats, std::string& err) {
+    constexpr bool EXACT = sizeof(R) == 8;
     const uint32_t W = cam_in.image_width, H = cam_in.image_height;
     const uint32_t world = opts.row_world <= 1 ? 1 : opts.row_world;
     const uint32_t block = opts.row_block == 0 ? 8 : opts.row_block;
@@ -673,11 +678,17 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
     CRB_CUDA(cudaMemsetAsync(fb, 0, (size_t)npix * 3 * sizeof(unsigned long long), stream));
 
     const DevScene<R> sc = make_dev_scene<R>(s);
-    // occupancy of the trace kernel (tuning knob; CRB_MINB in the environment overrides): blocks of 256 per SM
+    // lane-refill threshold of the trace kernel (tuning knob; CRB_REFILL in the environment overrides)
     typedef void (*TraceFn)(DevScene<R>, PathRec<R>*, Control*, int, uint32_t*, uint32_t);
-    int minb = 3;
+    int refill = CRB_REFILL;
+    if (const char* e = getenv("CRB_REFILL")) refill = atoi(e);
+    int minb = 8;
     if (const char* e = getenv("CRB_MINB")) minb = atoi(e);
-    TraceFn trace_fn = minb <= 2 ? k_trace<R, 2> : minb == 3 ? k_trace<R, 3> : k_trace<R, 4>;
+#define CRB_PICK(MB)                                                                                                        \
+    (refill <= 8 ? k_trace<R, EXACT, 8, MB> : refill <= 16 ? k_trace<R, EXACT, 16, MB> : refill <= 24 ? k_trace<R, EXACT, 24, MB> \
+                                                                                                  : k_trace<R, EXACT, 32, MB>)
+    TraceFn trace_fn = minb <= 4 ? CRB_PICK(4) : minb <= 6 ? CRB_PICK(6) : CRB_PICK(8);
+#undef CRB_PICK
     const int g_trace = persistent_grid(trace_fn, TRACE_BLOCK, s.num_sms);
     const int g_gen = persistent_grid(k_raygen<R>, SHADE_BLOCK, s.num_sms);
     const int g_miss = persistent_grid(k_shade_miss<R>, SHADE_BLOCK, s.num_sms);

@@ -8,6 +8,6 @@ for l in sys.stdin:
         d=json.loads(l); r=d['roofline']; print('  Msamples/s %.1f  ms/step %.2f trace %.2f shade %.2f gen %.2f frac %.3f'%(d['value'],d['ms_per_step'],r['ms_trace'],r['ms_shade'],r['ms_raygen'],r['frac']))
 "
 }
-for mb in 2 3 4; do for sl in 2 4 8; do
-  echo "MINB=$mb SLICE=$sl"; CRB_MINB=$mb CRB_NODE_SLICE=$sl run
-done; done
+for mb in 4 6 8; do for r in 16 24; do for sl in 4 8; do
+  echo "MINB=$mb REFILL=$r SLICE=$sl"; CRB_MINB=$mb CRB_REFILL=$r CRB_NODE_SLICE=$sl run
+done; done; done
