@@ -114,6 +114,7 @@ struct DevScene {
     int32_t sky_kind, sky_image;
     int32_t clamp_colors;  // 1 = reference Color semantics; 0 when the scene holds an Emissive (extension)
     int32_t node_slice;    // box tests per lane between two exact/leaf phases of the trace engine
+    int32_t min_node_lanes;  // a node slice ends early when fewer lanes than this still have a cheap step
 };
 
 // ---- in-flight path record --------------------------------------------------------------------
@@ -165,11 +166,7 @@ struct DevCamera {
     uint32_t row_block, row_rank, row_world, rows_local;
     uint64_t seed;
     uint32_t fb_scale_bits;
-    uint32_t is_static;  // no camera keyframes: the basis below is valid for every sample time
-    // camera basis at a fixed time, filled on the DEVICE by k_camera_setup with the same routine the
-    // per-sample path uses (bit-identical): from, pixel_start_location, pixel_delta_u/v, defocus_disk_u/v
-    double s_from[3], s_psl[3], s_pdu[3], s_pdv[3], s_du[3], s_dv[3];
-    float f_from[3], f_psl[3], f_pdu[3], f_pdv[3], f_du[3], f_dv[3];
+    uint32_t is_static;  // no camera keyframes: raygen uses the host-evaluated basis (RaygenParams)
 };
 
 // ---- small vector helpers --------------------------------------------------------------------------

@@ -480,22 +480,7 @@ struct Trav {
             slab32(nf, fr, tmin, best_t, lo, hi);
             hit = hi > lo;
         }
-        int st = after_box(hit, nf.left, nf.right, sc.n_nodes);
-        if constexpr (sizeof(R) == 8) {
-            if (st == ST_LEAF) {
-                bool all_miss = true;
-                if (ref_kind(pl) == CR_PRIM_SPHERE) {
-                    all_miss = sphere_definite_miss(ldg_rec<1>(sc.spheres32 + ref_index(pl)), fr);
-                } else {
-                    all_miss = false;
-                }
-                if (all_miss && pr != REF_NONE) {
-                    all_miss = (ref_kind(pr) == CR_PRIM_SPHERE) && sphere_definite_miss(ldg_rec<1>(sc.spheres32 + ref_index(pr)), fr);
-                }
-                if (all_miss) st = i >= sc.n_nodes ? ST_DONE : ST_NODE;
-            }
-        }
-        return st;
+        return after_box(hit, nf.left, nf.right, sc.n_nodes);
     }
     // exact box test of node i in R arithmetic on the ray re-read from its record
     __device__ __forceinline__ int step_exact(const DevScene<R>& sc, V3<R> o, V3<R> d, R tmin) {
@@ -523,6 +508,17 @@ struct Trav {
         if (got) {
             best_t = t;
             best_ref = ref;
+        }
+    }
+    // f64 path: are all primitives of the parked leaf node certain misses (nothing to test)?
+    __device__ __forceinline__ bool leaf_certain_miss(const DevScene<R>& sc) const {
+        if constexpr (sizeof(R) == 8) {
+            if (!fr.ok || ref_kind(pl) != CR_PRIM_SPHERE) return false;
+            if (!sphere_definite_miss(ldg_rec<1>(sc.spheres32 + ref_index(pl)), fr)) return false;
+            if (pr == REF_NONE) return true;
+            return ref_kind(pr) == CR_PRIM_SPHERE && sphere_definite_miss(ldg_rec<1>(sc.spheres32 + ref_index(pr)), fr);
+        } else {
+            return false;
         }
     }
     __device__ __forceinline__ int step_leaf(const DevScene<R>& sc, V3<R> o, V3<R> d, R tmin) {
@@ -585,10 +581,14 @@ __device__ __forceinline__ void trace_persistent(const DevScene<R>& sc, R tmin, 
             if (__ballot_sync(0xffffffffu, st != ST_IDLE) == 0u) break;  // nothing walking, nothing pending
         }
         // ---- NODE phase
+        // (the slice ends early once fewer than MIN_NODE_LANES lanes still have a cheap step to do)
 #pragma unroll 1
         for (int k = 0; k < NODE_SLICE; ++k) {
             if (st == ST_NODE) st = tv.step_node(sc, tmin);
+            if (__popc(__ballot_sync(0xffffffffu, st == ST_NODE)) < sc.min_node_lanes) break;
         }
+        // ---- LEAF pre-filter: leaf nodes whose primitives are all certain misses need no f64 work
+        if (st == ST_LEAF && tv.leaf_certain_miss(sc)) st = tv.i >= sc.n_nodes ? ST_DONE : ST_NODE;
         // ---- EXACT + LEAF phases share one re-read of the f64 ray
         if (__any_sync(0xffffffffu, st == ST_EXACT || st == ST_LEAF)) {
             if (st == ST_EXACT || st == ST_LEAF) {

@@ -5,6 +5,7 @@
 // Replaces Camera::cast_ray / ray_color / average_samples (src/camera/ray_casting.rs:64-173) and the
 // worker pool of src/camera/cpu_threading.rs:25-115.
 #pragma once
+#include <cmath>
 #include <cstdlib>
 #include <string>
 #include <vector>
@@ -156,19 +157,7 @@ __device__ __forceinline__ void camera_sample(const DevCamera& cam, uint32_t i, 
     const R current_time = (R)c.frame * (R(1) / (R)c.frame_rate);
     const R shutter_length = ((R)c.shutter_angle / R(360)) * (R(1) / (R)c.frame_rate);
     const R t = current_time + g.range(R(0), shutter_length);
-    CamBasis<R> b;
-    if (cam.is_static) {  // no keyframes: the basis does not depend on t (k_camera_setup computed it once)
-        if constexpr (sizeof(R) == 8) {
-            b.from = ld3<R>(cam.s_from); b.psl = ld3<R>(cam.s_psl); b.pdu = ld3<R>(cam.s_pdu);
-            b.pdv = ld3<R>(cam.s_pdv); b.du = ld3<R>(cam.s_du); b.dv = ld3<R>(cam.s_dv);
-        } else {
-            b.from = {cam.f_from[0], cam.f_from[1], cam.f_from[2]}; b.psl = {cam.f_psl[0], cam.f_psl[1], cam.f_psl[2]};
-            b.pdu = {cam.f_pdu[0], cam.f_pdu[1], cam.f_pdu[2]}; b.pdv = {cam.f_pdv[0], cam.f_pdv[1], cam.f_pdv[2]};
-            b.du = {cam.f_du[0], cam.f_du[1], cam.f_du[2]}; b.dv = {cam.f_dv[0], cam.f_dv[1], cam.f_dv[2]};
-        }
-    } else {
-        b = camera_basis<R>(c, t);
-    }
+    const CamBasis<R> b = camera_basis<R>(c, t);
     const R ox = g.next() - R(0.5);  // sample_square, camera/mod.rs:369-376
     const R oy = g.next() - R(0.5);
     const V3<R> ps = vadd(vadd(b.psl, vmul((R)i + ox, b.pdu)), vmul((R)j + oy, b.pdv));  // get_pixel_pos :64-68
@@ -181,21 +170,6 @@ __device__ __forceinline__ void camera_sample(const DevCamera& cam, uint32_t i, 
     rd = vsub(ps, orig);
     tm = t;
 }
-// fills the static basis of a keyframe-free camera (one thread)
-template <typename R>
-__global__ void k_camera_setup(DevCamera* cam) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    const CamBasis<R> b = camera_basis<R>(cam->c, R(0));
-    const V3<R> v[6] = {b.from, b.psl, b.pdu, b.pdv, b.du, b.dv};
-    if constexpr (sizeof(R) == 8) {
-        double* dst[6] = {cam->s_from, cam->s_psl, cam->s_pdu, cam->s_pdv, cam->s_du, cam->s_dv};
-        for (int k = 0; k < 6; ++k) { dst[k][0] = v[k].x; dst[k][1] = v[k].y; dst[k][2] = v[k].z; }
-    } else {
-        float* dst[6] = {cam->f_from, cam->f_psl, cam->f_pdu, cam->f_pdv, cam->f_du, cam->f_dv};
-        for (int k = 0; k < 6; ++k) { dst[k][0] = v[k].x; dst[k][1] = v[k].y; dst[k][2] = v[k].z; }
-    }
-}
-
 // local (per-rank) row -> global row: rows j with (j / row_block) % row_world == row_rank, in order
 __host__ __device__ inline uint32_t local_to_global_row(uint32_t lr, uint32_t block, uint32_t rank, uint32_t world) {
     if (world <= 1) return lr;
@@ -226,29 +200,63 @@ static __global__ void k_plan(Control* ctl, int nxt, uint32_t* host_n_in) {
     if (host_n_in) *host_n_in = n_in;
 }
 
-// raygen: persistent grid-stride over the samples the plan handed out.  Sample-major order
-// (g = sample * npix + pixel) keeps neighbouring lanes on neighbouring pixels.
 template <typename R>
-__global__ void __launch_bounds__(SHADE_BLOCK) k_raygen(const Control* __restrict__ ctl, const DevCamera* __restrict__ camp,
-                                                         PathRec<R>* __restrict__ out) {
+__device__ __forceinline__ void store_path(PathRec<R>* p, const PathRec<R>& in);
+
+// raygen: persistent grid-stride over the samples the plan handed out.  Sample-major order
+// (g = sample * npix + pixel) keeps neighbouring lanes on neighbouring pixels.  Everything that is
+// constant for the launch arrives BY VALUE (constant bank, no load latency): for a keyframe-free camera
+// that includes the whole basis, evaluated once on the host with the same IEEE operations
+// (host_camera_basis), so the per-sample work is the jitter, the lens and one 128 B record.
+template <typename R>
+struct RaygenParams {
+    uint32_t W, rows_local, row_block, row_rank, row_world, is_static, lens, small;  // small: total samples < 2^32
+    uint64_t seed;
+    R current_time, shutter_length;
+    R from[3], psl[3], pdu[3], pdv[3], du[3], dv[3];
+};
+template <typename R, int MINB>
+__global__ void __launch_bounds__(SHADE_BLOCK, MINB) k_raygen(const Control* __restrict__ ctl, const DevCamera* __restrict__ camp,
+                                                               const __grid_constant__ RaygenParams<R> rp, PathRec<R>* __restrict__ out) {
     const uint32_t n = ctl->gen_count;
     if (n == 0) return;
     const uint32_t base = ctl->gen_base;
     const uint64_t first = ctl->gen_first;
-    const DevCamera& cam = *camp;
-    const uint32_t W = cam.c.image_width;
-    const uint64_t npix = (uint64_t)W * cam.rows_local;
+    const uint32_t W = rp.W;
+    const uint64_t npix = (uint64_t)W * rp.rows_local;
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         const uint64_t g = first + k;
-        const uint32_t sample = (uint32_t)(g / npix);
-        const uint32_t lp = (uint32_t)(g % npix);
-        const uint32_t lrow = lp / W, i = lp % W;
-        const uint32_t j = local_to_global_row(lrow, cam.row_block, cam.row_rank, cam.row_world);
+        uint32_t sample, lp;
+        if (rp.small) {  // 32-bit division is ~5x cheaper than the 64-bit one
+            sample = (uint32_t)g / (uint32_t)npix;
+            lp = (uint32_t)g - sample * (uint32_t)npix;
+        } else {
+            sample = (uint32_t)(g / npix);
+            lp = (uint32_t)(g - (uint64_t)sample * npix);
+        }
+        const uint32_t lrow = lp / W, i = lp - lrow * W;
+        const uint32_t j = local_to_global_row(lrow, rp.row_block, rp.row_rank, rp.row_world);
         const uint32_t pixel = j * W + i;
-        Rng<R> rng(cam.seed, pixel, sample, 0);
+        Rng<R> rng(rp.seed, pixel, sample, 0);
         V3<R> o, d;
         R tm;
-        camera_sample<R>(cam, i, j, rng, o, d, tm);
+        if (rp.is_static) {
+            // ray_casting.rs:82-104 with the basis hoisted (it does not depend on the sample time)
+            tm = rp.current_time + rng.range(R(0), rp.shutter_length);
+            const R ox = rng.next() - R(0.5);  // sample_square, camera/mod.rs:369-376
+            const R oy = rng.next() - R(0.5);
+            const V3<R> psl = {rp.psl[0], rp.psl[1], rp.psl[2]}, pdu = {rp.pdu[0], rp.pdu[1], rp.pdu[2]},
+                        pdv = {rp.pdv[0], rp.pdv[1], rp.pdv[2]}, from = {rp.from[0], rp.from[1], rp.from[2]};
+            const V3<R> ps = vadd(vadd(psl, vmul((R)i + ox, pdu)), vmul((R)j + oy, pdv));  // get_pixel_pos :64-68
+            o = from;
+            if (rp.lens) {  // defocus_disk_sample :105-110
+                const V3<R> p = random_in_unit_disk(rng);
+                o = vadd(vadd(from, vmul(p.x, V3<R>{rp.du[0], rp.du[1], rp.du[2]})), vmul(p.y, V3<R>{rp.dv[0], rp.dv[1], rp.dv[2]}));
+            }
+            d = vsub(ps, o);
+        } else {
+            camera_sample<R>(*camp, i, j, rng, o, d, tm);
+        }
         PathRec<R> p;
         p.ox = o.x; p.oy = o.y; p.oz = o.z;
         p.dx = d.x; p.dy = d.y; p.dz = d.z;
@@ -260,7 +268,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK) k_raygen(const Control* __restric
         p.pixel = pixel;
         p.sample = sample;
         p.fb = lp;
-        out[base + k] = p;
+        store_path(out + base + k, p);
     }
 }
 
@@ -343,7 +351,7 @@ __device__ __forceinline__ void store_path(PathRec<R>* p, const PathRec<R>& in) 
 
 // miss: ray_color's skybox arm; the path ends and thr * sky is accumulated
 template <typename R>
-__global__ void __launch_bounds__(SHADE_BLOCK) k_shade_miss(DevScene<R> sc, const PathRec<R>* __restrict__ in,
+__global__ void __launch_bounds__(SHADE_BLOCK, 8) k_shade_miss(DevScene<R> sc, const PathRec<R>* __restrict__ in,
                                                              const Control* __restrict__ ctl, const uint32_t* __restrict__ queue,
                                                              unsigned long long* __restrict__ fb, double fb_scale) {
     const uint32_t n = ctl->queue_count[Q_MISS];
@@ -376,14 +384,13 @@ __global__ void __launch_bounds__(SHADE_BLOCK) k_shade_emissive(DevScene<R> sc, 
 }
 
 // scatter kernels: one per material so a warp runs one BSDF.  MAT selects the arm at compile time.
-template <typename R, int MAT>
-__global__ void __launch_bounds__(SHADE_BLOCK) k_shade_scatter(DevScene<R> sc, const PathRec<R>* __restrict__ in,
-                                                                PathRec<R>* __restrict__ out, Control* __restrict__ ctl, int nxt,
-                                                                const uint32_t* __restrict__ queue, const DevCamera* __restrict__ camp) {
+template <typename R, int MAT, int MINB>
+__global__ void __launch_bounds__(SHADE_BLOCK, MINB) k_shade_scatter(DevScene<R> sc, const PathRec<R>* __restrict__ in,
+                                                                      PathRec<R>* __restrict__ out, Control* __restrict__ ctl, int nxt,
+                                                                      const uint32_t* __restrict__ queue, uint64_t seed,
+                                                                      uint32_t max_depth) {
     const uint32_t n = ctl->queue_count[Q_LAMBERTIAN + MAT];
     if (n == 0) return;
-    const uint64_t seed = camp->seed;
-    const uint32_t max_depth = camp->c.max_depth;
     const bool cl = sc.clamp_colors != 0;
     const uint32_t n_round = (n + 31u) & ~31u;
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n_round; k += gridDim.x * blockDim.x) {
@@ -529,6 +536,8 @@ static DevScene<R> make_dev_scene(const SceneDeviceData& s) {
     d.clamp_colors = s.clamp_colors;
     d.node_slice = s.node_slice;
     if (const char* e = getenv("CRB_NODE_SLICE")) d.node_slice = atoi(e) > 0 ? atoi(e) : 8;
+    d.min_node_lanes = 12;
+    if (const char* e = getenv("CRB_MIN_LANES")) d.min_node_lanes = atoi(e);
     return d;
 }
 
@@ -565,6 +574,40 @@ int trace_batch_impl(const SceneDeviceData& s, const double* d_rays, size_t n, d
     k_trace_batch<R, EXACT><<<grid, TRACE_BLOCK, 0, stream>>>(sc, d_rays, (uint32_t)n, tmin, tmax, d_out, d_cursor);
     CRB_CUDA(cudaGetLastError());
     return CR_OK;
+}
+
+// Host evaluation of the launch-constant camera terms with the reference's operations (the library's
+// host code is compiled with -ffp-contract=off; IEEE add/mul/div/sqrt give the device's bits).
+//   current_time, shutter_length: ray_casting.rs:77-79;  basis: rendering_compute.rs:5-111
+template <typename R>
+static void host_camera_constants(const CrCamera& c, RaygenParams<R>& rp) {
+    struct H3 { R x, y, z; };
+    auto neg = [](H3 a) { return H3{-a.x, -a.y, -a.z}; };
+    auto add = [](H3 a, H3 b) { return H3{a.x + b.x, a.y + b.y, a.z + b.z}; };
+    auto sub = [&](H3 a, H3 b) { return add(a, neg(b)); };
+    auto mul = [](R s, H3 v) { return H3{s * v.x, s * v.y, s * v.z}; };
+    auto divs = [&](H3 v, R s) { return mul(R(1) / s, v); };
+    auto len2 = [](H3 v) { return v.x * v.x + v.y * v.y + v.z * v.z; };
+    auto cross = [](H3 v, H3 o) { return H3{v.y * o.z - v.z * o.y, v.z * o.x - v.x * o.z, v.x * o.y - v.y * o.x}; };
+    auto unit = [&](H3 v) { return divs(v, (R)std::sqrt(len2(v))); };
+    rp.current_time = (R)c.frame * (R(1) / (R)c.frame_rate);
+    rp.shutter_length = ((R)c.shutter_angle / R(360)) * (R(1) / (R)c.frame_rate);
+    const H3 from = {(R)c.look_from[0], (R)c.look_from[1], (R)c.look_from[2]};
+    const H3 at = {(R)c.look_at[0], (R)c.look_at[1], (R)c.look_at[2]};
+    const H3 vup = {(R)c.vup[0], (R)c.vup[1], (R)c.vup[2]};
+    const H3 w = unit(sub(from, at));
+    const H3 u = unit(cross(vup, w));
+    const H3 v = cross(w, u);
+    const H3 vu = mul((R)c.viewport_width, u);
+    const H3 vv = mul((R)c.viewport_height, neg(v));
+    const H3 pdu = divs(vu, (R)c.image_width);
+    const H3 pdv = divs(vv, (R)c.image_height);
+    const H3 ul = sub(sub(sub(from, mul((R)c.focus_dist, w)), divs(vu, R(2))), divs(vv, R(2)));
+    const H3 psl = add(ul, mul(R(0.5), add(pdu, pdv)));
+    const H3 du = mul((R)c.defocus_radius, u), dv = mul((R)c.defocus_radius, v);
+    const H3 src[6] = {from, psl, pdu, pdv, du, dv};
+    R* dst[6] = {rp.from, rp.psl, rp.pdu, rp.pdv, rp.du, rp.dv};
+    for (int k = 0; k < 6; ++k) { dst[k][0] = src[k].x; dst[k][1] = src[k].y; dst[k][2] = src[k].z; }
 }
 
 struct EventTimer {
@@ -690,12 +733,26 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
     TraceFn trace_fn = minb <= 4 ? CRB_PICK(4) : minb <= 6 ? CRB_PICK(6) : CRB_PICK(8);
 #undef CRB_PICK
     const int g_trace = persistent_grid(trace_fn, TRACE_BLOCK, s.num_sms);
-    const int g_gen = persistent_grid(k_raygen<R>, SHADE_BLOCK, s.num_sms);
+    int smb = 6;
+    if (const char* e = getenv("CRB_SHADE_MINB")) smb = atoi(e);
+    typedef void (*GenFn)(const Control*, const DevCamera*, const RaygenParams<R>, PathRec<R>*);
+    typedef void (*ScatFn)(DevScene<R>, const PathRec<R>*, PathRec<R>*, Control*, int, const uint32_t*, uint64_t, uint32_t);
+    GenFn gen_fn = smb <= 4 ? k_raygen<R, 4> : smb <= 6 ? k_raygen<R, 6> : k_raygen<R, 8>;
+    ScatFn lam_fn = smb <= 4 ? k_shade_scatter<R, CR_MAT_LAMBERTIAN, 4> : smb <= 6 ? k_shade_scatter<R, CR_MAT_LAMBERTIAN, 6> : k_shade_scatter<R, CR_MAT_LAMBERTIAN, 8>;
+    ScatFn met_fn = smb <= 4 ? k_shade_scatter<R, CR_MAT_METAL, 4> : smb <= 6 ? k_shade_scatter<R, CR_MAT_METAL, 6> : k_shade_scatter<R, CR_MAT_METAL, 8>;
+    ScatFn die_fn = smb <= 4 ? k_shade_scatter<R, CR_MAT_DIELECTRIC, 4> : smb <= 6 ? k_shade_scatter<R, CR_MAT_DIELECTRIC, 6> : k_shade_scatter<R, CR_MAT_DIELECTRIC, 8>;
+    RaygenParams<R> rp;
+    memset(&rp, 0, sizeof(rp));
+    rp.W = W; rp.rows_local = rows_local; rp.row_block = block; rp.row_rank = rank; rp.row_world = world;
+    rp.is_static = hcam.is_static; rp.lens = !(cam_in.defocus_angle <= 0.0) ? 1u : 0u; rp.small = total < 0xFFFFFFFFull ? 1u : 0u;
+    rp.seed = opts.seed;
+    host_camera_constants<R>(cam_in, rp);
+    const int g_gen = persistent_grid(gen_fn, SHADE_BLOCK, s.num_sms);
     const int g_miss = persistent_grid(k_shade_miss<R>, SHADE_BLOCK, s.num_sms);
     const int g_emit = persistent_grid(k_shade_emissive<R>, SHADE_BLOCK, s.num_sms);
-    const int g_lam = persistent_grid(k_shade_scatter<R, CR_MAT_LAMBERTIAN>, SHADE_BLOCK, s.num_sms);
-    const int g_met = persistent_grid(k_shade_scatter<R, CR_MAT_METAL>, SHADE_BLOCK, s.num_sms);
-    const int g_die = persistent_grid(k_shade_scatter<R, CR_MAT_DIELECTRIC>, SHADE_BLOCK, s.num_sms);
+    const int g_lam = persistent_grid(lam_fn, SHADE_BLOCK, s.num_sms);
+    const int g_met = persistent_grid(met_fn, SHADE_BLOCK, s.num_sms);
+    const int g_die = persistent_grid(die_fn, SHADE_BLOCK, s.num_sms);
 
     EventTimer tm;
     tm.on = opts.time_kernels != 0;
@@ -713,12 +770,8 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
     cudaEvent_t a;
     // prologue: camera basis (static cameras), plan + raygen fill side 0
     tm.begin(2, a);
-    if (hcam.is_static) {
-        k_camera_setup<R><<<1, 32, 0, stream>>>(d_cam);
-        ++launches;
-    }
     k_plan<<<1, 32, 0, stream>>>(ctl, 0, nullptr);
-    k_raygen<R><<<g_gen, SHADE_BLOCK, 0, stream>>>(ctl, d_cam, paths[0]);
+    gen_fn<<<g_gen, SHADE_BLOCK, 0, stream>>>(ctl, d_cam, rp, paths[0]);
     tm.end(2, a);
     launches += 2;
     uint64_t it = 0;
@@ -730,12 +783,12 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
         tm.end(0, a);
         tm.begin(1, a);
         k_shade_miss<R><<<g_miss, SHADE_BLOCK, 0, stream>>>(sc, paths[cur], ctl, queues + (size_t)Q_MISS * pool, fb, fb_scale);
-        k_shade_scatter<R, CR_MAT_LAMBERTIAN><<<g_lam, SHADE_BLOCK, 0, stream>>>(sc, paths[cur], paths[nxt], ctl, nxt,
-                                                                                  queues + (size_t)Q_LAMBERTIAN * pool, d_cam);
-        k_shade_scatter<R, CR_MAT_METAL><<<g_met, SHADE_BLOCK, 0, stream>>>(sc, paths[cur], paths[nxt], ctl, nxt,
-                                                                             queues + (size_t)Q_METAL * pool, d_cam);
-        k_shade_scatter<R, CR_MAT_DIELECTRIC><<<g_die, SHADE_BLOCK, 0, stream>>>(sc, paths[cur], paths[nxt], ctl, nxt,
-                                                                                  queues + (size_t)Q_DIELECTRIC * pool, d_cam);
+        lam_fn<<<g_lam, SHADE_BLOCK, 0, stream>>>(sc, paths[cur], paths[nxt], ctl, nxt, queues + (size_t)Q_LAMBERTIAN * pool, opts.seed,
+                                                  cam_in.max_depth);
+        met_fn<<<g_met, SHADE_BLOCK, 0, stream>>>(sc, paths[cur], paths[nxt], ctl, nxt, queues + (size_t)Q_METAL * pool, opts.seed,
+                                                  cam_in.max_depth);
+        die_fn<<<g_die, SHADE_BLOCK, 0, stream>>>(sc, paths[cur], paths[nxt], ctl, nxt, queues + (size_t)Q_DIELECTRIC * pool, opts.seed,
+                                                  cam_in.max_depth);
         launches += 5;
         if (!s.clamp_colors) {
             k_shade_emissive<R><<<g_emit, SHADE_BLOCK, 0, stream>>>(sc, paths[cur], ctl, queues + (size_t)Q_EMISSIVE * pool, fb,
@@ -745,7 +798,7 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
         tm.end(1, a);
         tm.begin(2, a);
         k_plan<<<1, 32, 0, stream>>>(ctl, nxt, nullptr);
-        k_raygen<R><<<g_gen, SHADE_BLOCK, 0, stream>>>(ctl, d_cam, paths[nxt]);
+        gen_fn<<<g_gen, SHADE_BLOCK, 0, stream>>>(ctl, d_cam, rp, paths[nxt]);
         tm.end(2, a);
         launches += 2;
         const int slot = (int)(it % RING);
