@@ -1,6 +1,6 @@
 #!/bin/bash
 run() {
-  python bench.py --steps 2 --warmup 3 --no-cpu-baseline 2>&1 | python -c "
+  python bench.py --steps 2 --warmup 3 --no-cpu-baseline "$@" 2>&1 | python -c "
 import json,sys
 for l in sys.stdin:
     if l.startswith('{'):
@@ -8,4 +8,4 @@ for l in sys.stdin:
 "
 }
 for smb in 4 6 8; do echo "SHADE_MINB=$smb"; CRB_NODE_SLICE=32 CRB_MIN_LANES=8 CRB_SHADE_MINB=$smb run; done
-for mb in 7; do echo "TRACE MINB=$mb"; CRB_NODE_SLICE=32 CRB_MIN_LANES=8 CRB_MINB=$mb run; done
+echo f32; CRB_NODE_SLICE=32 CRB_MIN_LANES=8 run --precision f32
