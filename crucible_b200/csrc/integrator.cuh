@@ -578,7 +578,7 @@ static DevScene<R> make_dev_scene(const SceneDeviceData& s) {
     d.clamp_colors = s.clamp_colors;
     d.node_slice = s.node_slice;
     if (const char* e = getenv("CRB_NODE_SLICE")) d.node_slice = atoi(e) > 0 ? atoi(e) : 8;
-    d.min_node_lanes = 12;
+    d.min_node_lanes = 8;
     if (const char* e = getenv("CRB_MIN_LANES")) d.min_node_lanes = atoi(e);
     return d;
 }

@@ -26,7 +26,7 @@ struct SceneDeviceData {
     float bsmall = 0.f;          // bound of the nodes without BIGBOX_BIT
     double max_radiance = 1.0;  // largest per-sample colour component (1 unless the scene holds an Emissive)
     int num_sms = 148;
-    int node_slice = 8;
+    int node_slice = 32;
 };
 
 // Grow-only device scratch owned by the CrScene (path pool, queues, fixed-point framebuffer).
