@@ -19,6 +19,19 @@ def frames_of_rank(n_frames: int, rank: int, world: int):
     return list(range(rank, n_frames, max(world, 1)))
 
 
+_ROW_INDEX_CACHE = {}
+
+
+def _row_index(height, row_block, r, world, device):
+    """Row indices of rank r as a device tensor (cached: building them costs a synchronous H2D copy)."""
+    key = (height, row_block, r, world, str(device))
+    t = _ROW_INDEX_CACHE.get(key)
+    if t is None:
+        t = torch.as_tensor(rows_of_rank(height, row_block, r, world), device=device, dtype=torch.long)
+        _ROW_INDEX_CACHE[key] = t
+    return t
+
+
 def gather_rows(local: torch.Tensor, height: int, row_block: int, rank: int, world: int, group=None, dst: int = 0):
     """Assemble the full [H][W][C] image on `dst` from each rank's packed rows.
 
@@ -39,8 +52,7 @@ def gather_rows(local: torch.Tensor, height: int, row_block: int, rank: int, wor
         dist.gather(send, gather_list=bufs, dst=dst, group=group)
         full = torch.empty((height,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
         for r in range(world):
-            rows = torch.as_tensor(rows_of_rank(height, row_block, r, world), device=local.device, dtype=torch.long)
-            full[rows] = bufs[r][: counts[r]]
+            full.index_copy_(0, _row_index(height, row_block, r, world, local.device), bufs[r][: counts[r]])
         return full
     dist.gather(send, gather_list=None, dst=dst, group=group)
     return None
