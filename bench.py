@@ -272,8 +272,15 @@ def main():
         dur_s = ms_trace * 1e-3 / max(my_iters, 1)
         achieved = per_seg_flops * seg_per_launch / dur_s / 1e12
         peak = f64p.value if args.precision == "f64" else f32p.value
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "trace_r01_traffic.json")
+        if args.precision == "f64" and os.path.exists(tpath):
+            tj = json.load(open(tpath))  # DRAM bytes of one ncu --set full capture, scaled to this run's segments per launch
+            traffic = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) / tj["rays_in_launch"] * seg_per_launch
+            traffic_src = tj["capture"]
         line["roofline"] = {"bound": "fp64" if args.precision == "f64" else "fp32", "kernel": "k_trace", "achieved": achieved, "peak": peak,
-                            "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": None,
+                            "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_source": traffic_src,
+                            "algorithmic_bytes_per_launch": per_seg_bytes * seg_per_launch,
                             "peak_source": "cr_measure_fma_peak (register-resident FMA micro-kernel, same run; MEASURED_PEAKS.json holds no FP32/FP64 vector peak)",
                             "flops_per_segment": per_seg_flops, "bytes_per_segment": per_seg_bytes, "segments_per_launch": seg_per_launch,
                             "avg_launch_ms": dur_s * 1e3, "kernel_share_of_step": ms_trace / (ms_total if world == 1 else sum(s["ms_total"] for s in stats)),
