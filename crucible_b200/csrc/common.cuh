@@ -120,22 +120,25 @@ struct DevScene {
 // ---- in-flight path record --------------------------------------------------------------------
 template <typename R>
 struct PathRec;
+// Field order = four 32 B sectors, grouped by consumer: trace reads A+B and writes t (A) and ref (B);
+// the miss shader reads only B+C; the scatter shaders read everything.
 template <>
 struct __align__(16) PathRec<double> {
-    double ox, oy, oz, dx, dy, dz;  // ray (direction NOT normalised, ray_casting.rs:102)
-    double tm, t;                   // ray time; closest-hit t written by trace
-    double tr, tg, tb;              // product of attenuations so far
-    uint32_t ref, bounce;           // closest-hit reference written by trace; hits so far
-    uint32_t pixel, sample;         // GLOBAL pixel index (RNG key), sample index
-    uint32_t fb, pad0;              // local framebuffer index
+    double ox, oy, oz, t;            // A: origin; closest-hit t written by trace
+    double dx, dy, dz;               // B: direction (NOT normalised, ray_casting.rs:102)
+    uint32_t fb, ref;                //    local framebuffer index; closest-hit reference written by trace
+    double tr, tg, tb;               // C: product of attenuations so far
+    uint32_t bounce, pad0;           //    hits so far
+    uint32_t pixel, sample;          // D: GLOBAL pixel index (RNG key), sample index
+    double tm;                       //    ray time (ray_casting.rs:84)
     double pad1, pad2;
 };
 template <>
 struct __align__(16) PathRec<float> {
-    float ox, oy, oz, dx, dy, dz;
-    float tm, t;
-    float tr, tg, tb;
+    float ox, oy, oz, t;             // A
+    float dx, dy, dz;
     uint32_t ref;
+    float tr, tg, tb, tm;            // B
     uint32_t pixel, sample, bounce, fb;
 };
 static_assert(sizeof(PathRec<double>) == 128, "f64 path record = one 128 B line");

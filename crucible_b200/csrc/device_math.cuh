@@ -267,19 +267,14 @@ template <typename R> struct HitInfo {
     bool front;
     int32_t material, mat_kind, prim_index, obj_id;
 };
-// want_uv = false skips get_sphere_uv (acos + atan2): the texture coordinates only reach image textures
-// (solid_color.rs:25-27 and checker_texture.rs:39-51 ignore u, v), so skipping them cannot change a result.
+// HitRecord geometry rebuilt from (ref, t).  want_uv = false skips get_sphere_uv (acos + atan2): the
+// texture coordinates only reach image textures (solid_color.rs:25-27 and checker_texture.rs:39-51
+// ignore u, v), so skipping them cannot change a result.
 template <typename R>
-__device__ __forceinline__ HitInfo<R> finalize_hit(const DevScene<R>& sc, uint32_t ref, R t, V3<R> o, V3<R> d, bool always_uv = true) {
+__device__ __forceinline__ HitInfo<R> finalize_geom(const DevScene<R>& sc, uint32_t ref, R t, V3<R> o, V3<R> d, bool want_uv) {
     HitInfo<R> h;
     const uint32_t kind = ref_kind(ref), idx = ref_index(ref);
-    const PrimMeta* mp = kind == CR_PRIM_SPHERE ? sc.meta[0] : (kind == CR_PRIM_TRIANGLE ? sc.meta[1] : sc.meta[2]);
-    const PrimMeta m = mp[idx];
-    h.material = m.material;
-    h.mat_kind = m.mat_kind & MATKIND_MASK;
-    const bool want_uv = always_uv || (m.mat_kind & MATKIND_NEEDS_UV) != 0;
-    h.prim_index = m.prim_index;
-    h.obj_id = m.obj_id;
+    h.material = h.mat_kind = h.prim_index = h.obj_id = -1;
     h.p = vadd(o, vmul(t, d));  // Ray::at, ray_casting.rs:53-59
     V3<R> n;
     if (kind == CR_PRIM_SPHERE) {
@@ -307,6 +302,19 @@ __device__ __forceinline__ HitInfo<R> finalize_hit(const DevScene<R>& sc, uint32
     }
     h.front = vdot(d, n) < R(0);  // objects/mod.rs:47-48
     h.n = h.front ? n : vneg(n);
+    return h;
+}
+// full record incl. the ids of SURVEY 8b (cr_trace_batch)
+template <typename R>
+__device__ __forceinline__ HitInfo<R> finalize_hit(const DevScene<R>& sc, uint32_t ref, R t, V3<R> o, V3<R> d) {
+    HitInfo<R> h = finalize_geom<R>(sc, ref, t, o, d, true);
+    const uint32_t kind = ref_kind(ref);
+    const PrimMeta* mp = kind == CR_PRIM_SPHERE ? sc.meta[0] : (kind == CR_PRIM_TRIANGLE ? sc.meta[1] : sc.meta[2]);
+    const PrimMeta m = mp[ref_index(ref)];
+    h.material = m.material;
+    h.mat_kind = m.mat_kind & MATKIND_MASK;
+    h.prim_index = m.prim_index;
+    h.obj_id = m.obj_id;
     return h;
 }
 

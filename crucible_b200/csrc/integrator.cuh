@@ -317,28 +317,30 @@ struct RenderTraceIO {
     const DevScene<R>& sc;
     PathRec<R>* paths;
     Control* ctl;
-    uint32_t* queues;
+    uint2* queues;
     uint32_t n, pool;
     __device__ __forceinline__ uint32_t count() const { return n; }
     __device__ __forceinline__ uint32_t* cursor() const { return &ctl->trace_next; }
     __device__ __forceinline__ void load(uint32_t i, V3<R>& o, V3<R>& d) const {
-        const PathRec<R>* p = paths + i;  // the first 48 (24) bytes of the record: origin + direction
+        const PathRec<R>* p = paths + i;  // sectors A and B of the record: origin + direction
         if constexpr (sizeof(R) == 8) {
             const double2 a = *reinterpret_cast<const double2*>(&p->ox);
-            const double2 b = *reinterpret_cast<const double2*>(&p->oz);
-            const double2 c = *reinterpret_cast<const double2*>(&p->dy);
-            o = {a.x, a.y, b.x};
-            d = {b.y, c.x, c.y};
+            const double b = p->oz;
+            const double2 c = *reinterpret_cast<const double2*>(&p->dx);
+            const double e = p->dz;
+            o = {a.x, a.y, b};
+            d = {c.x, c.y, e};
         } else {
             const float4 a = *reinterpret_cast<const float4*>(&p->ox);
-            const float2 b = *reinterpret_cast<const float2*>(&p->dy);
+            const float4 b = *reinterpret_cast<const float4*>(&p->dx);
             o = {a.x, a.y, a.z};
-            d = {a.w, b.x, b.y};
+            d = {b.x, b.y, b.z};
         }
     }
     __device__ __forceinline__ bool commit_needs_ray() const { return false; }
     __device__ __forceinline__ void commit(bool has, uint32_t i, uint32_t ref, R t, V3<R>, V3<R>) const {
         int q = -1;
+        uint32_t minfo = 0;  // material index (bits 0..23) | needs-uv (bit 31): saves the shaders a dependent load
         if (has) {
             paths[i].t = t;
             paths[i].ref = ref;
@@ -347,17 +349,19 @@ struct RenderTraceIO {
             } else {
                 const uint32_t kind = ref_kind(ref);
                 const PrimMeta* m = kind == CR_PRIM_SPHERE ? sc.meta[0] : (kind == CR_PRIM_TRIANGLE ? sc.meta[1] : sc.meta[2]);
-                q = (int)Q_LAMBERTIAN + (m[ref_index(ref)].mat_kind & MATKIND_MASK);
+                const PrimMeta pm = m[ref_index(ref)];
+                q = (int)Q_LAMBERTIAN + (pm.mat_kind & MATKIND_MASK);
+                minfo = (uint32_t)pm.material | ((pm.mat_kind & MATKIND_NEEDS_UV) ? 0x80000000u : 0u);
             }
         }
         const uint32_t pos = warp_enqueue(ctl->queue_count, q);
-        if (q >= 0) queues[(size_t)q * pool + pos] = i;
+        if (q >= 0) queues[(size_t)q * pool + pos] = make_uint2(i, minfo);
     }
 };
 
 template <typename R, bool EXACT, int REFILL, int MINB>
 __global__ void __launch_bounds__(TRACE_BLOCK, MINB) k_trace(DevScene<R> sc, PathRec<R>* __restrict__ paths, Control* __restrict__ ctl,
-                                                        int side, uint32_t* __restrict__ queues, uint32_t pool) {
+                                                        int side, uint2* __restrict__ queues, uint32_t pool) {
     RenderTraceIO<R> io{sc, paths, ctl, queues, ctl->n_in[side], pool};
     trace_persistent<R, EXACT, REFILL>(sc, R(0.001), Num<R>::inf(), io);  // ray_casting.rs:119
 }
@@ -387,16 +391,31 @@ __device__ __forceinline__ void store_path(PathRec<R>* p, const PathRec<R>& in) 
 // miss: ray_color's skybox arm; the path ends and thr * sky is accumulated
 template <typename R>
 __global__ void __launch_bounds__(SHADE_BLOCK, 8) k_shade_miss(DevScene<R> sc, const PathRec<R>* __restrict__ in,
-                                                             const Control* __restrict__ ctl, const uint32_t* __restrict__ queue,
+                                                             const Control* __restrict__ ctl, const uint2* __restrict__ queue,
                                                              unsigned long long* __restrict__ fb, double fb_scale) {
     const uint32_t n = ctl->queue_count[Q_MISS];
     const bool cl = sc.clamp_colors != 0;
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-        PathRec<R> p;
-        load_path(in + queue[k], p);
-        const V3<R> sky = sky_color<R>(sc, V3<R>{p.dx, p.dy, p.dz});
-        const V3<R> c = col_mul(V3<R>{p.tr, p.tg, p.tb}, sky, cl);
-        fb_add(fb, p.fb, (double)c.x, (double)c.y, (double)c.z, fb_scale);
+        const PathRec<R>* rec = in + queue[k].x;
+        V3<R> d, thr;
+        uint32_t fbi;
+        if constexpr (sizeof(R) == 8) {  // sectors B and C only: direction + fb, throughput
+            const double2 a = *reinterpret_cast<const double2*>(&rec->dx);
+            const int4 b = *reinterpret_cast<const int4*>(&rec->dz);
+            const double2 c = *reinterpret_cast<const double2*>(&rec->tr);
+            d = {a.x, a.y, __hiloint2double(b.y, b.x)};
+            fbi = (uint32_t)b.z;
+            thr = {c.x, c.y, rec->tb};
+        } else {
+            const float4 a = *reinterpret_cast<const float4*>(&rec->dx);
+            const float4 b = *reinterpret_cast<const float4*>(&rec->tr);
+            d = {a.x, a.y, a.z};
+            thr = {b.x, b.y, b.z};
+            fbi = rec->fb;
+        }
+        const V3<R> sky = sky_color<R>(sc, d);
+        const V3<R> c = col_mul(thr, sky, cl);
+        fb_add(fb, fbi, (double)c.x, (double)c.y, (double)c.z, fb_scale);
     }
 }
 
@@ -404,15 +423,14 @@ __global__ void __launch_bounds__(SHADE_BLOCK, 8) k_shade_miss(DevScene<R> sc, c
 template <typename R>
 __global__ void __launch_bounds__(SHADE_BLOCK) k_shade_emissive(DevScene<R> sc, const PathRec<R>* __restrict__ in,
                                                                  const Control* __restrict__ ctl,
-                                                                 const uint32_t* __restrict__ queue,
+                                                                 const uint2* __restrict__ queue,
                                                                  unsigned long long* __restrict__ fb, double fb_scale) {
     const uint32_t n = ctl->queue_count[Q_EMISSIVE];
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         PathRec<R> p;
-        load_path(in + queue[k], p);
-        const uint32_t kind = ref_kind(p.ref);
-        const PrimMeta m = (kind == CR_PRIM_SPHERE ? sc.meta[0] : (kind == CR_PRIM_TRIANGLE ? sc.meta[1] : sc.meta[2]))[ref_index(p.ref)];
-        const DevMaterial& mat = sc.mats[m.material];
+        const uint2 e = queue[k];
+        load_path(in + e.x, p);
+        const DevMaterial& mat = sc.mats[e.y & 0x00FFFFFFu];
         fb_add(fb, p.fb, (double)(p.tr * (R)mat.emit[0]), (double)(p.tg * (R)mat.emit[1]), (double)(p.tb * (R)mat.emit[2]),
                fb_scale);
     }
@@ -422,7 +440,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK) k_shade_emissive(DevScene<R> sc, 
 template <typename R, int MAT, int MINB>
 __global__ void __launch_bounds__(SHADE_BLOCK, MINB) k_shade_scatter(DevScene<R> sc, const PathRec<R>* __restrict__ in,
                                                                       PathRec<R>* __restrict__ out, Control* __restrict__ ctl, int nxt,
-                                                                      const uint32_t* __restrict__ queue, uint64_t seed,
+                                                                      const uint2* __restrict__ queue, uint64_t seed,
                                                                       uint32_t max_depth) {
     const uint32_t n = ctl->queue_count[Q_LAMBERTIAN + MAT];
     if (n == 0) return;
@@ -434,11 +452,12 @@ __global__ void __launch_bounds__(SHADE_BLOCK, MINB) k_shade_scatter(DevScene<R>
         bool alive = false;
         PathRec<R> p;
         if (k < n) {
-            load_path(in + queue[k], p);
+            const uint2 e = queue[k];
+            load_path(in + e.x, p);
             const V3<R> o = {p.ox, p.oy, p.oz}, d = {p.dx, p.dy, p.dz};
             // u, v are needed only when a Lambertian's texture tree reaches an image
-            const HitInfo<R> h = finalize_hit<R>(sc, p.ref, p.t, o, d, false);
-            const DevMaterial& mat = sc.mats[h.material];
+            const HitInfo<R> h = finalize_geom<R>(sc, p.ref, p.t, o, d, (e.y >> 31) != 0u);
+            const DevMaterial& mat = sc.mats[e.y & 0x00FFFFFFu];
             const uint32_t bounce = p.bounce + 1;  // this is the bounce-th hit of the path
             Rng<R> g(seed, p.pixel, p.sample, bounce);
             V3<R> att, nd;
@@ -720,7 +739,7 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
     const size_t o_cam = carve(sizeof(DevCamera));
     const size_t o_paths0 = carve((size_t)pool * sizeof(PathRec<R>));
     const size_t o_paths1 = carve((size_t)pool * sizeof(PathRec<R>));
-    const size_t o_queues = carve((size_t)pool * Q_COUNT * sizeof(uint32_t));
+    const size_t o_queues = carve((size_t)pool * Q_COUNT * sizeof(uint2));
     const size_t o_fb = carve((size_t)npix * 3 * sizeof(unsigned long long));
     int rc = ws.ensure(off, err);
     if (rc != CR_OK) return rc;
@@ -728,7 +747,7 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
     Control* ctl = reinterpret_cast<Control*>(base + o_ctl);
     DevCamera* d_cam = reinterpret_cast<DevCamera*>(base + o_cam);
     PathRec<R>* paths[2] = {reinterpret_cast<PathRec<R>*>(base + o_paths0), reinterpret_cast<PathRec<R>*>(base + o_paths1)};
-    uint32_t* queues = reinterpret_cast<uint32_t*>(base + o_queues);
+    uint2* queues = reinterpret_cast<uint2*>(base + o_queues);
     unsigned long long* fb = reinterpret_cast<unsigned long long*>(base + o_fb);
 
     if (!ws.pinned) {
@@ -764,7 +783,7 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
 
     const DevScene<R> sc = make_dev_scene<R>(s);
     // lane-refill threshold of the trace kernel (tuning knob; CRB_REFILL in the environment overrides)
-    typedef void (*TraceFn)(DevScene<R>, PathRec<R>*, Control*, int, uint32_t*, uint32_t);
+    typedef void (*TraceFn)(DevScene<R>, PathRec<R>*, Control*, int, uint2*, uint32_t);
     int refill = CRB_REFILL;
     if (const char* e = getenv("CRB_REFILL")) refill = atoi(e);
     int minb = 8;
@@ -778,7 +797,7 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
     int smb = 6;
     if (const char* e = getenv("CRB_SHADE_MINB")) smb = atoi(e);
     typedef void (*GenFn)(const Control*, const DevCamera*, const RaygenParams<R>, PathRec<R>*);
-    typedef void (*ScatFn)(DevScene<R>, const PathRec<R>*, PathRec<R>*, Control*, int, const uint32_t*, uint64_t, uint32_t);
+    typedef void (*ScatFn)(DevScene<R>, const PathRec<R>*, PathRec<R>*, Control*, int, const uint2*, uint64_t, uint32_t);
     GenFn gen_fn = smb <= 4 ? k_raygen<R, 4> : smb <= 6 ? k_raygen<R, 6> : k_raygen<R, 8>;
     ScatFn lam_fn = smb <= 4 ? k_shade_scatter<R, CR_MAT_LAMBERTIAN, 4> : smb <= 6 ? k_shade_scatter<R, CR_MAT_LAMBERTIAN, 6> : k_shade_scatter<R, CR_MAT_LAMBERTIAN, 8>;
     ScatFn met_fn = smb <= 4 ? k_shade_scatter<R, CR_MAT_METAL, 4> : smb <= 6 ? k_shade_scatter<R, CR_MAT_METAL, 6> : k_shade_scatter<R, CR_MAT_METAL, 8>;

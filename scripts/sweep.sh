@@ -7,5 +7,5 @@ for l in sys.stdin:
         d=json.loads(l); r=d['roofline']; print('  Msamples/s %.1f  ms/step %.2f trace %.2f shade %.2f gen %.2f frac %.3f'%(d['value'],d['ms_per_step'],r['ms_trace'],r['ms_shade'],r['ms_raygen'],r['frac']))
 "
 }
-for smb in 4 6 8; do echo "SHADE_MINB=$smb"; CRB_NODE_SLICE=32 CRB_MIN_LANES=8 CRB_SHADE_MINB=$smb run; done
-echo f32; CRB_NODE_SLICE=32 CRB_MIN_LANES=8 run --precision f32
+echo f64; run
+echo f32; run --precision f32
