@@ -157,3 +157,16 @@ def test_scene_mirror_matches_reference_api():
     assert c.viewport_width == c.viewport_height * (400 / 225)
     mv = demo_builder.book1_walkthrough(image_width=64, samples=1)
     assert mv.compute_frame_count() == 240 and mv.scene_cam.to_abi().n_from_keys == 12
+
+
+def test_c_example_links_against_the_abi(crlib):
+    """examples/c_abi.c uses the boundary from plain C; without a GPU it reports the missing device and
+    exits 0 (no CPU fallback), with one it traces and renders."""
+    with tempfile.TemporaryDirectory() as td:
+        exe = os.path.join(td, "c_abi")
+        lib_dir = os.path.join(ROOT, "crucible_b200")
+        subprocess.run(["gcc", os.path.join(ROOT, "examples", "c_abi.c"), "-I", os.path.join(ROOT, "include"), "-L", lib_dir,
+                        "-lcrucible_b200", "-lm", f"-Wl,-rpath,{lib_dir}", "-o", exe], check=True)
+        out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
+    assert "BVH: 1 nodes, depth 1, 2 primitives" in out
+    assert ("no CPU fallback" in out) or ("hit prim 1 at t = 0.5" in out)
