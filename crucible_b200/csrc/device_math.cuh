@@ -560,6 +560,7 @@ __device__ __forceinline__ void trace_persistent(const DevScene<R>& sc, R tmin, 
     uint32_t my = 0;
     int st = ST_IDLE;
     bool exhausted = false;
+    const bool small = n <= gridDim.x * blockDim.x;
     for (;;) {
         const uint32_t walking = __ballot_sync(0xffffffffu, st == ST_NODE || st == ST_EXACT || st == ST_LEAF);
         const int n_free = 32 - __popc(walking);
@@ -572,8 +573,14 @@ __device__ __forceinline__ void trace_persistent(const DevScene<R>& sc, R tmin, 
             if (st == ST_DONE) st = ST_IDLE;
             if (!exhausted) {
                 uint32_t base = 0;
-                if (lane == 0) base = atomicAdd(io.cursor(), (uint32_t)n_free);
-                base = __shfl_sync(0xffffffffu, base, 0);
+                if (small) {
+                    // few rays (the tail of a render): one static batch per warp, no atomic.  With thousands
+                    // of resident warps the shared cursor alone costs ~70 us per launch (ncu launch list).
+                    base = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32u;
+                } else {
+                    if (lane == 0) base = atomicAdd(io.cursor(), (uint32_t)n_free);
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                }
                 if (st == ST_IDLE) {
                     const uint32_t k = base + (uint32_t)__popc(~walking & ((1u << lane) - 1u));
                     if (k < n) {
@@ -584,7 +591,7 @@ __device__ __forceinline__ void trace_persistent(const DevScene<R>& sc, R tmin, 
                         st = (sc.n_nodes == 0u) ? ST_DONE : ST_NODE;
                     }
                 }
-                if (base + (uint32_t)n_free >= n) exhausted = true;
+                if (small || base + (uint32_t)n_free >= n) exhausted = true;
             }
             if (__ballot_sync(0xffffffffu, st != ST_IDLE) == 0u) break;  // nothing walking, nothing pending
         }

@@ -437,6 +437,63 @@ __global__ void __launch_bounds__(SHADE_BLOCK) k_shade_emissive(DevScene<R> sc, 
 }
 
 // scatter kernels: one per material so a warp runs one BSDF.  MAT selects the arm at compile time.
+// One scatter event (Materials::scatter, src/materials/mod.rs:23-29) on a path whose closest hit is
+// (p.ref, p.t): rebuilds the HitRecord, draws from the (pixel, sample, bounce) stream, and on survival
+// turns p into the scattered ray.  Shared by the material-sorted shade kernels and the tail kernel.
+template <typename R, int MAT>
+__device__ __forceinline__ bool scatter_path(const DevScene<R>& sc, PathRec<R>& p, uint32_t minfo, uint64_t seed, uint32_t max_depth) {
+    const bool cl = sc.clamp_colors != 0;
+    const V3<R> o = {p.ox, p.oy, p.oz}, d = {p.dx, p.dy, p.dz};
+    // u, v are needed only when a Lambertian's texture tree reaches an image
+    const HitInfo<R> h = finalize_geom<R>(sc, p.ref, p.t, o, d, (minfo >> 31) != 0u);
+    const DevMaterial& mat = sc.mats[minfo & 0x00FFFFFFu];
+    const uint32_t bounce = p.bounce + 1;  // this is the bounce-th hit of the path
+    Rng<R> g(seed, p.pixel, p.sample, bounce);
+    V3<R> att, nd;
+    bool alive;
+    if (MAT == CR_MAT_LAMBERTIAN) {  // lambertian.rs:40-61
+        V3<R> dir = vadd(h.n, random_unit_vector(g));
+        if (vnear_zero(dir)) dir = h.n;
+        nd = dir;
+        att = col_div(tex_value<R>(sc, mat.tex, h.u, h.v, h.p), (R)mat.scatter_prob, true);
+        alive = g.next() <= (R)mat.scatter_prob;
+    } else if (MAT == CR_MAT_METAL) {  // metal.rs:29-42
+        const V3<R> refl = vreflect(d, h.n);
+        nd = vadd(vunit(refl), vmul((R)mat.fuzz, random_unit_vector(g)));
+        att = {(R)mat.albedo[0], (R)mat.albedo[1], (R)mat.albedo[2]};
+        alive = vdot(nd, h.n) > R(0);
+    } else {  // dielectric.rs:30-55
+        att = {R(1), R(1), R(1)};
+        const R ri = h.front ? R(1) / (R)mat.ior : (R)mat.ior;
+        const V3<R> ud = vunit(d);
+        const R cos_theta = -(Num<R>::min_(vdot(ud, h.n), R(1)));
+        const R sin_theta = Num<R>::sqrt_(R(1) - cos_theta * cos_theta);
+        bool refl = ri * sin_theta > R(1);
+        if (!refl) {
+            R r0 = (R(1) - ri) / (R(1) + ri);
+            r0 = r0 * r0;
+            const R x = R(1) - cos_theta;
+            const R x2 = x * x;
+            const R x5 = x * (x2 * x2);
+            refl = (r0 + (R(1) - r0) * x5) > g.next();
+        }
+        nd = refl ? vreflect(ud, h.n) : vrefract(ud, h.n, ri);
+        alive = true;
+    }
+    // ray_color(depth == 0) returns black: a path that has used max_depth hits contributes nothing
+    if (bounce >= max_depth) alive = false;
+    if (alive) {
+        const V3<R> thr = col_mul(V3<R>{p.tr, p.tg, p.tb}, att, cl);
+        p.ox = h.p.x; p.oy = h.p.y; p.oz = h.p.z;
+        p.dx = nd.x; p.dy = nd.y; p.dz = nd.z;
+        p.tr = thr.x; p.tg = thr.y; p.tb = thr.z;
+        p.bounce = bounce;
+        p.ref = REF_MISS;
+    }
+    return alive;
+}
+
+// scatter kernels: one per material so a warp runs one BSDF; survivors are compacted into the other side
 template <typename R, int MAT, int MINB>
 __global__ void __launch_bounds__(SHADE_BLOCK, MINB) k_shade_scatter(DevScene<R> sc, const PathRec<R>* __restrict__ in,
                                                                       PathRec<R>* __restrict__ out, Control* __restrict__ ctl, int nxt,
@@ -446,7 +503,6 @@ __global__ void __launch_bounds__(SHADE_BLOCK, MINB) k_shade_scatter(DevScene<R>
     if (n == 0) return;
     __shared__ int4 s_tile[SHADE_BLOCK * (sizeof(PathRec<R>) / 16)];
     int4* tile = s_tile + (threadIdx.x >> 5) * 32 * (sizeof(PathRec<R>) / 16);
-    const bool cl = sc.clamp_colors != 0;
     const uint32_t n_round = (n + 31u) & ~31u;
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n_round; k += gridDim.x * blockDim.x) {
         bool alive = false;
@@ -454,52 +510,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK, MINB) k_shade_scatter(DevScene<R>
         if (k < n) {
             const uint2 e = queue[k];
             load_path(in + e.x, p);
-            const V3<R> o = {p.ox, p.oy, p.oz}, d = {p.dx, p.dy, p.dz};
-            // u, v are needed only when a Lambertian's texture tree reaches an image
-            const HitInfo<R> h = finalize_geom<R>(sc, p.ref, p.t, o, d, (e.y >> 31) != 0u);
-            const DevMaterial& mat = sc.mats[e.y & 0x00FFFFFFu];
-            const uint32_t bounce = p.bounce + 1;  // this is the bounce-th hit of the path
-            Rng<R> g(seed, p.pixel, p.sample, bounce);
-            V3<R> att, nd;
-            if (MAT == CR_MAT_LAMBERTIAN) {  // lambertian.rs:40-61
-                V3<R> dir = vadd(h.n, random_unit_vector(g));
-                if (vnear_zero(dir)) dir = h.n;
-                nd = dir;
-                att = col_div(tex_value<R>(sc, mat.tex, h.u, h.v, h.p), (R)mat.scatter_prob, true);
-                alive = g.next() <= (R)mat.scatter_prob;
-            } else if (MAT == CR_MAT_METAL) {  // metal.rs:29-42
-                const V3<R> refl = vreflect(d, h.n);
-                nd = vadd(vunit(refl), vmul((R)mat.fuzz, random_unit_vector(g)));
-                att = {(R)mat.albedo[0], (R)mat.albedo[1], (R)mat.albedo[2]};
-                alive = vdot(nd, h.n) > R(0);
-            } else {  // dielectric.rs:30-55
-                att = {R(1), R(1), R(1)};
-                const R ri = h.front ? R(1) / (R)mat.ior : (R)mat.ior;
-                const V3<R> ud = vunit(d);
-                const R cos_theta = -(Num<R>::min_(vdot(ud, h.n), R(1)));
-                const R sin_theta = Num<R>::sqrt_(R(1) - cos_theta * cos_theta);
-                bool refl = ri * sin_theta > R(1);
-                if (!refl) {
-                    R r0 = (R(1) - ri) / (R(1) + ri);
-                    r0 = r0 * r0;
-                    const R x = R(1) - cos_theta;
-                    const R x2 = x * x;
-                    const R x5 = x * (x2 * x2);
-                    refl = (r0 + (R(1) - r0) * x5) > g.next();
-                }
-                nd = refl ? vreflect(ud, h.n) : vrefract(ud, h.n, ri);
-                alive = true;
-            }
-            // ray_color(depth == 0) returns black: a path that has used max_depth hits contributes nothing
-            if (bounce >= max_depth) alive = false;
-            if (alive) {
-                const V3<R> thr = col_mul(V3<R>{p.tr, p.tg, p.tb}, att, cl);
-                p.ox = h.p.x; p.oy = h.p.y; p.oz = h.p.z;
-                p.dx = nd.x; p.dy = nd.y; p.dz = nd.z;
-                p.tr = thr.x; p.tg = thr.y; p.tb = thr.z;
-                p.bounce = bounce;
-                p.ref = REF_MISS;
-            }
+            alive = scatter_path<R, MAT>(sc, p, e.y, seed, max_depth);
         }
         const uint32_t amask = __ballot_sync(0xffffffffu, alive);
         if (amask != 0u) {  // warp-uniform
@@ -509,6 +520,58 @@ __global__ void __launch_bounds__(SHADE_BLOCK, MINB) k_shade_scatter(DevScene<R>
             warp_store_records<R>(tile, out + start, alive ? rank : -1, (int)__popc(amask), p);
         }
     }
+}
+
+// tail: when only a few thousand paths are left (and no camera samples), another ~25-45 wavefront iterations
+// of 8 launches each would be pure launch overhead.  One launch finishes them: each thread follows ITS path
+// to the end (trace, shade, trace, ...) with the same device routines, so every path is unchanged.
+template <typename R>
+__global__ void __launch_bounds__(SHADE_BLOCK, 4) k_tail(DevScene<R> sc, const PathRec<R>* __restrict__ paths, Control* __restrict__ ctl,
+                                                         int side, uint64_t seed, uint32_t max_depth,
+                                                         unsigned long long* __restrict__ fb, double fb_scale) {
+    const uint32_t n = ctl->n_in[side];
+    const bool cl = sc.clamp_colors != 0;
+    unsigned long long traced = 0;  // segments beyond each path's first (k_plan already counted that one)
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        PathRec<R> p;
+        load_path(paths + k, p);
+        for (bool first = true;; first = false) {
+            const V3<R> o = {p.ox, p.oy, p.oz}, d = {p.dx, p.dy, p.dz};
+            Trav<R> tv;
+            tv.init(o, d, R(0.001), Num<R>::inf(), sc.bsmall, sc.bmax);  // ray_casting.rs:119
+            int st = sc.n_nodes == 0u ? ST_DONE : ST_NODE;
+            while (st != ST_DONE) {
+                if (st == ST_NODE) st = tv.step_node(sc, R(0.001));
+                else if (st == ST_EXACT) st = tv.step_exact(sc, o, d, R(0.001));
+                else st = tv.leaf_certain_miss(sc) ? (tv.i >= sc.n_nodes ? (int)ST_DONE : (int)ST_NODE) : tv.step_leaf(sc, o, d, R(0.001));
+            }
+            if (!first) ++traced;
+            if (tv.best_ref == REF_MISS) {  // ray_casting.rs:133-151
+                const V3<R> c = col_mul(V3<R>{p.tr, p.tg, p.tb}, sky_color<R>(sc, d), cl);
+                fb_add(fb, p.fb, (double)c.x, (double)c.y, (double)c.z, fb_scale);
+                break;
+            }
+            p.ref = tv.best_ref;
+            p.t = tv.best_t;
+            const uint32_t kind = ref_kind(p.ref);
+            const PrimMeta pm = (kind == CR_PRIM_SPHERE ? sc.meta[0] : (kind == CR_PRIM_TRIANGLE ? sc.meta[1] : sc.meta[2]))[ref_index(p.ref)];
+            const uint32_t minfo = (uint32_t)pm.material | ((pm.mat_kind & MATKIND_NEEDS_UV) ? 0x80000000u : 0u);
+            const int mk = pm.mat_kind & MATKIND_MASK;
+            bool alive;
+            if (mk == CR_MAT_LAMBERTIAN) alive = scatter_path<R, CR_MAT_LAMBERTIAN>(sc, p, minfo, seed, max_depth);
+            else if (mk == CR_MAT_METAL) alive = scatter_path<R, CR_MAT_METAL>(sc, p, minfo, seed, max_depth);
+            else if (mk == CR_MAT_DIELECTRIC) alive = scatter_path<R, CR_MAT_DIELECTRIC>(sc, p, minfo, seed, max_depth);
+            else {  // EXTENSION emissive
+                const DevMaterial& mat = sc.mats[pm.material];
+                fb_add(fb, p.fb, (double)(p.tr * (R)mat.emit[0]), (double)(p.tg * (R)mat.emit[1]), (double)(p.tb * (R)mat.emit[2]), fb_scale);
+                alive = false;
+            }
+            if (!alive) break;
+        }
+    }
+    // ray segments traced here (CrStats.rays counts world.hit calls)
+    for (int off = 16; off > 0; off >>= 1) traced += __shfl_down_sync(0xffffffffu, traced, off);
+    if ((threadIdx.x & 31) == 0 && traced) atomicAdd(reinterpret_cast<unsigned long long*>(&ctl->rays_traced), traced);
 }
 
 // resolve: average_samples (ray_casting.rs:154-173) + Display for Color (utils.rs:422-438)
@@ -809,6 +872,9 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
     rp.seed = opts.seed;
     host_camera_constants<R>(cam_in, rp);
     const int g_gen = persistent_grid(gen_fn, SHADE_BLOCK, s.num_sms);
+    const int g_tail = persistent_grid(k_tail<R>, SHADE_BLOCK, s.num_sms);
+    uint32_t tail_n = 65536;
+    if (const char* e = getenv("CRB_TAIL")) tail_n = (uint32_t)atoi(e);
     const int g_miss = persistent_grid(k_shade_miss<R>, SHADE_BLOCK, s.num_sms);
     const int g_emit = persistent_grid(k_shade_emissive<R>, SHADE_BLOCK, s.num_sms);
     const int g_lam = persistent_grid(lam_fn, SHADE_BLOCK, s.num_sms);
@@ -869,7 +935,19 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
         if (it >= (uint64_t)LAG) {
             const int old = (int)((it - LAG) % RING);
             CRB_CUDA(cudaEventSynchronize(ring_ev[old]));
-            if (h_n_in[old] == 0) done = true;  // nothing left to trace after iteration it-LAG: later ones were no-ops
+            const uint32_t left = h_n_in[old];
+            if (left == 0) {
+                done = true;  // nothing left to trace after iteration it-LAG: later ones were no-ops
+            } else if (left < pool && left <= tail_n) {
+                // the pool is no longer full => every camera sample has been issued; a few thousand paths remain:
+                // one k_tail launch follows each of them to its end instead of ~25-45 more 8-launch iterations
+                const int side = (int)(it & 1);
+                tm.begin(0, a);
+                k_tail<R><<<g_tail, SHADE_BLOCK, 0, stream>>>(sc, paths[side], ctl, side, opts.seed, cam_in.max_depth, fb, fb_scale);
+                tm.end(0, a);
+                ++launches;
+                done = true;
+            }
         }
         if (it > 100000000ull) {
             err = "render: iteration limit";
