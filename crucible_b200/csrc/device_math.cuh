@@ -598,8 +598,11 @@ __device__ __forceinline__ void trace_persistent(const DevScene<R>& sc, R tmin, 
         // ---- NODE phase
         // (the slice ends early once fewer than MIN_NODE_LANES lanes still have a cheap step to do)
 #pragma unroll 1
-        for (int k = 0; k < NODE_SLICE; ++k) {
-            if (st == ST_NODE) st = tv.step_node(sc, tmin);
+        for (int k = 0; k < NODE_SLICE; k += 4) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (st == ST_NODE) st = tv.step_node(sc, tmin);
+            }
             if (__popc(__ballot_sync(0xffffffffu, st == ST_NODE)) < sc.min_node_lanes) break;
         }
         // ---- LEAF pre-filter: leaf nodes whose primitives are all certain misses need no f64 work

@@ -7,5 +7,4 @@ for l in sys.stdin:
         d=json.loads(l); r=d['roofline']; print('  Msamples/s %.1f  ms/step %.2f trace %.2f shade %.2f gen %.2f frac %.3f'%(d['value'],d['ms_per_step'],r['ms_trace'],r['ms_shade'],r['ms_raygen'],r['frac']))
 "
 }
-echo f64; run
-echo f32; run --precision f32
+for r in 8 16 24 32; do for ml in 4 8 12; do echo "REFILL=$r MIN_LANES=$ml"; CRB_REFILL=$r CRB_MIN_LANES=$ml run; done; done
