@@ -170,3 +170,40 @@ def test_c_example_links_against_the_abi(crlib):
         out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
     assert "BVH: 1 nodes, depth 1, 2 primitives" in out
     assert ("no CPU fallback" in out) or ("hit prim 1 at t = 0.5" in out)
+
+
+def _build_cpp_example(td):
+    exe = os.path.join(td, "render_book1")
+    lib_dir = os.path.join(ROOT, "crucible_b200")
+    subprocess.run(["g++", "-std=c++17", "-O1", os.path.join(ROOT, "examples", "render_book1.cpp"), "-I", os.path.join(ROOT, "include"),
+                    "-L", lib_dir, "-lcrucible_b200", f"-Wl,-rpath,{lib_dir}", "-o", exe], check=True)
+    return exe
+
+
+def test_cpp_host_mirror_builds_the_reference_tree(crlib):
+    """include/crucible.hpp: the C++ mirror of Scene / Camera / demo_images::book1_end_scene flattens into the
+    C ABI; 22x22 grid minus the exclusion zone + 4 spheres -> 511 nodes, depth 9."""
+    with tempfile.TemporaryDirectory() as td:
+        exe = _build_cpp_example(td)
+        out = subprocess.run([exe, "--describe-only", "--seed", "1"], check=True, capture_output=True, text=True).stdout
+        m = re.match(r"prims (\d+) nodes (\d+) depth (\d+) visible (\d+)", out)
+        assert m, out
+        prims, nodes, depth, vis = map(int, m.groups())
+        assert 470 <= prims <= 489 and vis == prims and depth in (9, 10) and nodes >= prims
+        if crlib.cr_device_count() == 0:  # no GPU: the render fails loudly, like Camera::render returning Err
+            r = subprocess.run([exe, "--width", "32", "--samples", "1"], capture_output=True, text=True)
+            assert r.returncode == 1 and "not available" in r.stderr
+
+
+@pytest.mark.gpu
+def test_cpp_host_mirror_renders_a_ppm(crlib, gpu_device):
+    with tempfile.TemporaryDirectory() as td:
+        exe = _build_cpp_example(td)
+        out = os.path.join(td, "img")
+        subprocess.run([exe, "--file", out, "--width", "160", "--samples", "8"], check=True, capture_output=True, text=True)
+        txt = open(out + ".ppm").read().split("\n")
+        assert txt[0] == "P3" and txt[1] == "160 90" and txt[2] == "255"
+        px = np.array([[int(v) for v in l.split()] for l in txt[3:3 + 160 * 90]])
+        assert px.shape == (160 * 90, 3) and px.min() >= 0 and px.max() <= 255
+        lum = ((px / 255.0) ** 2).mean()
+        assert 0.28 < lum < 0.48  # same scene family as samples/book1.png (mean linear luminance ~0.355)
