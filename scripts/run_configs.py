@@ -10,11 +10,11 @@ import numpy as np
 from crucible_b200 import abi, demo_builder
 from crucible_b200.gpu import GpuScene
 
-PLAN = {  # name: (builder kwargs, note)
-    "book1": (dict(image_width=1920, samples=100), "configs[0] full"),
-    "cornell": (dict(image_width=1024, samples=200), "configs[1] at 200 of 1000 spp"),
-    "teapot": (dict(image_width=1920, samples=64), "configs[2] at 64 of 256 spp"),
-    "instanced": (dict(image_width=3840, samples=8), "configs[3] at 8 of 64 spp"),
+PLAN = {  # name: (builder kwargs, note) — every BASELINE.json config at its FULL size
+    "book1": (dict(image_width=1920, samples=100), "configs[0] 1920x1080, 100 spp"),
+    "cornell": (dict(image_width=1024, samples=1000), "configs[1] 1024x1024, 1000 spp"),
+    "teapot": (dict(image_width=1920, samples=256), "configs[2] 1920x1080, 256 spp"),
+    "instanced": (dict(image_width=3840, samples=64), "configs[3] 3840x2160, 64 spp, 9 998 240 triangles"),
 }
 names = sys.argv[1:] or list(PLAN)
 for name in names:
