@@ -318,11 +318,10 @@ __device__ __forceinline__ HitInfo<R> finalize_hit(const DevScene<R>& sc, uint32
     return h;
 }
 
-// ---- closest hit: BVHWrapper::hit, src/objects/bvhwrapper.rs:97-126 as an explicit-stack DFS ------
+// ---- closest hit: BVHWrapper::hit, src/objects/bvhwrapper.rs:97-126 -------------------------------------
 // The recursion "left with (tmin,tmax), right with (tmin, left.t or tmax), prefer right" is a DFS with
 // ONE running closest-t: a later primitive only wins when strictly closer, inner boxes are tested with
 // the running interval at the time they are entered, leaves are tested with no box of their own.
-// EXACT = reference order (always left first).  !EXACT = near child first along the split axis.
 //
 // Branch-free box test for REGULAR rays (every origin/direction component finite, every 1/d finite and
 // non-zero).  For such rays t0, t1 are never NaN, so the reference's comparison form reduces to
@@ -546,7 +545,7 @@ struct Trav {
 // whole warp along for one lane.  Finished lanes are refilled (one atomic per warp) as soon as REFILL
 // of them are idle.  Each lane's own sequence of tests is the reference's, so is the result.
 //   IO::count() / cursor() / load(i,o,d) / commit(has,i,ref,t,o,d)  (commit is warp-synchronous)
-template <typename R, bool EXACT, int REFILL, typename IO>
+template <typename R, int REFILL, typename IO>
 __device__ __forceinline__ void trace_persistent(const DevScene<R>& sc, R tmin, R tmax, IO& io) {
     const int NODE_SLICE = sc.node_slice;
     const uint32_t n = io.count();

@@ -359,11 +359,11 @@ struct RenderTraceIO {
     }
 };
 
-template <typename R, bool EXACT, int REFILL, int MINB>
+template <typename R, int REFILL, int MINB>
 __global__ void __launch_bounds__(TRACE_BLOCK, MINB) k_trace(DevScene<R> sc, PathRec<R>* __restrict__ paths, Control* __restrict__ ctl,
                                                         int side, uint2* __restrict__ queues, uint32_t pool) {
     RenderTraceIO<R> io{sc, paths, ctl, queues, ctl->n_in[side], pool};
-    trace_persistent<R, EXACT, REFILL>(sc, R(0.001), Num<R>::inf(), io);  // ray_casting.rs:119
+    trace_persistent<R, REFILL>(sc, R(0.001), Num<R>::inf(), io);  // ray_casting.rs:119
 }
 
 // fixed-point accumulation: order independent => bit-reproducible for any schedule and GPU count
@@ -630,11 +630,11 @@ struct BatchTraceIO {
         out[i] = h;
     }
 };
-template <typename R, bool EXACT>
+template <typename R>
 __global__ void __launch_bounds__(TRACE_BLOCK) k_trace_batch(DevScene<R> sc, const double* __restrict__ rays, uint32_t n, double tmin,
                                                               double tmax, CrHit* __restrict__ out, uint32_t* __restrict__ cursor) {
     BatchTraceIO<R> io{sc, rays, out, cursor, n};
-    trace_persistent<R, EXACT, CRB_REFILL>(sc, (R)tmin, (R)tmax, io);
+    trace_persistent<R, CRB_REFILL>(sc, (R)tmin, (R)tmax, io);
 }
 
 // ---- host side: typed view of the scene + wavefront driver -----------------------------------------
@@ -689,13 +689,12 @@ int trace_batch_impl(const SceneDeviceData& s, const double* d_rays, size_t n, d
         err = "trace_batch: more than 2^32 rays in one call";
         return CR_ERR_LIMIT;
     }
-    constexpr bool EXACT = sizeof(R) == 8;
     const DevScene<R> sc = make_dev_scene<R>(s);
-    int grid = persistent_grid(k_trace_batch<R, EXACT>, TRACE_BLOCK, s.num_sms);
+    int grid = persistent_grid(k_trace_batch<R>, TRACE_BLOCK, s.num_sms);
     const size_t need = (n + TRACE_BLOCK - 1) / TRACE_BLOCK;
     if ((size_t)grid > need) grid = (int)need;
     CRB_CUDA(cudaMemsetAsync(d_cursor, 0, sizeof(uint32_t), stream));
-    k_trace_batch<R, EXACT><<<grid, TRACE_BLOCK, 0, stream>>>(sc, d_rays, (uint32_t)n, tmin, tmax, d_out, d_cursor);
+    k_trace_batch<R><<<grid, TRACE_BLOCK, 0, stream>>>(sc, d_rays, (uint32_t)n, tmin, tmax, d_out, d_cursor);
     CRB_CUDA(cudaGetLastError());
     return CR_OK;
 }
@@ -768,7 +767,6 @@ struct EventTimer {
 template <typename R>
 int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in, const CrRenderOpts& opts, void* d_out_rgb,
                 void* d_out_rgb8, int packed, cudaStream_t stream, CrStats* stats, std::string& err) {
-    constexpr bool EXACT = sizeof(R) == 8;
     const uint32_t W = cam_in.image_width, H = cam_in.image_height;
     const uint32_t world = opts.row_world <= 1 ? 1 : opts.row_world;
     const uint32_t block = opts.row_block == 0 ? 8 : opts.row_block;
@@ -852,8 +850,8 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
     int minb = 8;
     if (const char* e = getenv("CRB_MINB")) minb = atoi(e);
 #define CRB_PICK(MB)                                                                                                        \
-    (refill <= 8 ? k_trace<R, EXACT, 8, MB> : refill <= 16 ? k_trace<R, EXACT, 16, MB> : refill <= 24 ? k_trace<R, EXACT, 24, MB> \
-                                                                                                  : k_trace<R, EXACT, 32, MB>)
+    (refill <= 8 ? k_trace<R, 8, MB> : refill <= 16 ? k_trace<R, 16, MB> : refill <= 24 ? k_trace<R, 24, MB> \
+                                                                                                  : k_trace<R, 32, MB>)
     TraceFn trace_fn = minb <= 4 ? CRB_PICK(4) : minb <= 6 ? CRB_PICK(6) : CRB_PICK(8);
 #undef CRB_PICK
     const int g_trace = persistent_grid(trace_fn, TRACE_BLOCK, s.num_sms);
