@@ -397,6 +397,26 @@ __device__ __forceinline__ FilterRay make_filter_ray(V3<R> o, V3<R> d, V3<R> inv
     f.ok = regular && f.e_big < 3.0e37f && ax > 1.0e-30f && ay > 1.0e-30f && az > 1.0e-30f && f.o2 < 1.0e30f;
     return f;
 }
+// 48 B image of a FilterRay, written next to every path record by the kernel that PRODUCES the ray (raygen /
+// shade, where all lanes do it together) so that the trace kernel's lane refill is three 16 B loads instead of
+// six f64 loads, three f64 reciprocals and the bound arithmetic executed by a handful of lanes.
+struct __align__(16) FilterRec {
+    float f[12];
+};
+__device__ __forceinline__ FilterRec pack_filter(const FilterRay& r) {
+    FilterRec o;
+    o.f[0] = r.ox; o.f[1] = r.oy; o.f[2] = r.oz; o.f[3] = r.ix; o.f[4] = r.iy; o.f[5] = r.iz;
+    o.f[6] = r.dx; o.f[7] = r.dy; o.f[8] = r.dz; o.f[9] = r.e_small; o.f[10] = r.e_big;
+    o.f[11] = r.ok ? r.o2 : -1.0f;  // |o|^2 >= 0: a negative value marks "filters off"
+    return o;
+}
+__device__ __forceinline__ FilterRay unpack_filter(const FilterRec& o) {
+    FilterRay r;
+    r.ox = o.f[0]; r.oy = o.f[1]; r.oz = o.f[2]; r.ix = o.f[3]; r.iy = o.f[4]; r.iz = o.f[5];
+    r.dx = o.f[6]; r.dy = o.f[7]; r.dz = o.f[8]; r.e_small = o.f[9]; r.e_big = o.f[10]; r.o2 = o.f[11];
+    r.ok = o.f[11] >= 0.0f;
+    return r;
+}
 // f32 evaluation of the slab intervals (shared by the filter and by the f32 path's own box test)
 __device__ __forceinline__ void slab32(const NodeRec<float>& n, const FilterRay& f, float tmin, float best, float& lo, float& hi) {
     const float x0 = (n.xmin - f.ox) * f.ix, x1 = (n.xmax - f.ox) * f.ix;
@@ -451,13 +471,16 @@ struct Trav {
     R best_t;
     uint32_t best_ref, i, pl, pr;  // i = next node index; pl/pr = parked leaf primitives
 
-    __device__ __forceinline__ void init(V3<R> o, V3<R> d, R tmin, R tmax, float bsmall, float bmax) {
-        const V3<R> inv = {R(1) / d.x, R(1) / d.y, R(1) / d.z};  // adinv, bvh.rs:111
-        fr = make_filter_ray<R>(o, d, inv, tmin, tmax, bsmall, bmax);
+    __device__ __forceinline__ void init_from(const FilterRay& f, R tmax) {
+        fr = f;
         best_t = tmax;
         best_ref = REF_MISS;
         i = 0;
         pl = pr = REF_NONE;
+    }
+    __device__ __forceinline__ void init(V3<R> o, V3<R> d, R tmin, R tmax, float bsmall, float bmax) {
+        const V3<R> inv = {R(1) / d.x, R(1) / d.y, R(1) / d.z};  // adinv, bvh.rs:111
+        init_from(make_filter_ray<R>(o, d, inv, tmin, tmax, bsmall, bmax), tmax);
     }
     // the box test of node i has been decided
     __device__ __forceinline__ int after_box(bool hit, uint32_t wa, uint32_t wb, uint32_t n_nodes) {
@@ -544,7 +567,7 @@ struct Trav {
 // Parking the rare, expensive steps lets them run with several lanes at once instead of dragging the
 // whole warp along for one lane.  Finished lanes are refilled (one atomic per warp) as soon as REFILL
 // of them are idle.  Each lane's own sequence of tests is the reference's, so is the result.
-//   IO::count() / cursor() / load(i,o,d) / commit(has,i,ref,t,o,d)  (commit is warp-synchronous)
+//   IO::count() / cursor() / filter(i,tmin,tmax) / load(i,o,d) / commit(has,i,ref,t,o,d)  (commit is warp-synchronous)
 template <typename R, int REFILL, typename IO>
 __device__ __forceinline__ void trace_persistent(const DevScene<R>& sc, R tmin, R tmax, IO& io) {
     const int NODE_SLICE = sc.node_slice;
@@ -583,10 +606,8 @@ __device__ __forceinline__ void trace_persistent(const DevScene<R>& sc, R tmin, 
                 if (st == ST_IDLE) {
                     const uint32_t k = base + (uint32_t)__popc(~walking & ((1u << lane) - 1u));
                     if (k < n) {
-                        V3<R> o, d;
-                        io.load(k, o, d);
                         my = k;
-                        tv.init(o, d, tmin, tmax, sc.bsmall, sc.bmax);
+                        tv.init_from(io.filter(k, tmin, tmax), tmax);
                         st = (sc.n_nodes == 0u) ? ST_DONE : ST_NODE;
                     }
                 }

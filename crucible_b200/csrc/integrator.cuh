@@ -202,6 +202,15 @@ static __global__ void k_plan(Control* ctl, int nxt, uint32_t* host_n_in) {
 
 template <typename R>
 __device__ __forceinline__ void store_path(PathRec<R>* p, const PathRec<R>& in);
+// the producer of a ray (o, d) also writes its 48 B FilterRec (interval of ray_color: (0.001, inf), ray_casting.rs:119)
+template <typename R>
+__device__ __forceinline__ void store_filter(FilterRec* dst, V3<R> o, V3<R> d, float bsmall, float bmax) {
+    const V3<R> inv = {R(1) / d.x, R(1) / d.y, R(1) / d.z};  // adinv, bvh.rs:111
+    const FilterRec r = pack_filter(make_filter_ray<R>(o, d, inv, R(0.001), Num<R>::inf(), bsmall, bmax));
+    const int4* s = reinterpret_cast<const int4*>(&r);
+    int4* q = reinterpret_cast<int4*>(dst);
+    q[0] = s[0]; q[1] = s[1]; q[2] = s[2];
+}
 
 // Coalesced write of a warp's run of records.  A lane-private 128 B record written with 16 B stores at a
 // 128 B lane stride costs 32 L1 transactions per instruction and throttles the LSU (ncu: stall_lg was 53 % of
@@ -242,10 +251,12 @@ struct RaygenParams {
     uint64_t seed;
     R current_time, shutter_length;
     R from[3], psl[3], pdu[3], pdv[3], du[3], dv[3];
+    float bsmall, bmax;  // filter bounds of the committed scene (FilterRec is written with the ray)
 };
 template <typename R, int MINB>
 __global__ void __launch_bounds__(SHADE_BLOCK, MINB) k_raygen(const Control* __restrict__ ctl, const DevCamera* __restrict__ camp,
-                                                               const __grid_constant__ RaygenParams<R> rp, PathRec<R>* __restrict__ out) {
+                                                               const __grid_constant__ RaygenParams<R> rp, PathRec<R>* __restrict__ out,
+                                                               FilterRec* __restrict__ filt) {
     const uint32_t n = ctl->gen_count;
     if (n == 0) return;
     const uint32_t base = ctl->gen_base;
@@ -302,6 +313,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK, MINB) k_raygen(const Control* __r
         p.pixel = pixel;
         p.sample = sample;
         p.fb = lp;
+        store_filter<R>(filt + base + k, o, d, rp.bsmall, rp.bmax);
         }
         warp_store_records<R>(tile, out + base + k0, k < n ? (int)(k - k0) : -1, count, p);
     }
@@ -318,9 +330,17 @@ struct RenderTraceIO {
     PathRec<R>* paths;
     Control* ctl;
     uint2* queues;
+    const FilterRec* filt;
     uint32_t n, pool;
     __device__ __forceinline__ uint32_t count() const { return n; }
     __device__ __forceinline__ uint32_t* cursor() const { return &ctl->trace_next; }
+    __device__ __forceinline__ FilterRay filter(uint32_t i, R, R) const {  // written by the ray's producer
+        FilterRec r;
+        const int4* s = reinterpret_cast<const int4*>(filt + i);
+        int4* d = reinterpret_cast<int4*>(&r);
+        d[0] = s[0]; d[1] = s[1]; d[2] = s[2];
+        return unpack_filter(r);
+    }
     __device__ __forceinline__ void load(uint32_t i, V3<R>& o, V3<R>& d) const {
         const PathRec<R>* p = paths + i;  // sectors A and B of the record: origin + direction
         if constexpr (sizeof(R) == 8) {
@@ -361,8 +381,8 @@ struct RenderTraceIO {
 
 template <typename R, int REFILL, int MINB>
 __global__ void __launch_bounds__(TRACE_BLOCK, MINB) k_trace(DevScene<R> sc, PathRec<R>* __restrict__ paths, Control* __restrict__ ctl,
-                                                        int side, uint2* __restrict__ queues, uint32_t pool) {
-    RenderTraceIO<R> io{sc, paths, ctl, queues, ctl->n_in[side], pool};
+                                                        int side, uint2* __restrict__ queues, const FilterRec* __restrict__ filt, uint32_t pool) {
+    RenderTraceIO<R> io{sc, paths, ctl, queues, filt, ctl->n_in[side], pool};
     trace_persistent<R, REFILL>(sc, R(0.001), Num<R>::inf(), io);  // ray_casting.rs:119
 }
 
@@ -497,8 +517,8 @@ __device__ __forceinline__ bool scatter_path(const DevScene<R>& sc, PathRec<R>& 
 template <typename R, int MAT, int MINB>
 __global__ void __launch_bounds__(SHADE_BLOCK, MINB) k_shade_scatter(DevScene<R> sc, const PathRec<R>* __restrict__ in,
                                                                       PathRec<R>* __restrict__ out, Control* __restrict__ ctl, int nxt,
-                                                                      const uint2* __restrict__ queue, uint64_t seed,
-                                                                      uint32_t max_depth) {
+                                                                      const uint2* __restrict__ queue, FilterRec* __restrict__ filt_out,
+                                                                      uint64_t seed, uint32_t max_depth) {
     const uint32_t n = ctl->queue_count[Q_LAMBERTIAN + MAT];
     if (n == 0) return;
     __shared__ int4 s_tile[SHADE_BLOCK * (sizeof(PathRec<R>) / 16)];
@@ -517,6 +537,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK, MINB) k_shade_scatter(DevScene<R>
             const uint32_t pos = warp_append(&ctl->out_count[nxt], alive);
             const int rank = (int)__popc(amask & ((1u << (threadIdx.x & 31)) - 1u));
             const uint32_t start = __shfl_sync(0xffffffffu, pos - (uint32_t)rank, __ffs(amask) - 1);
+            if (alive) store_filter<R>(filt_out + pos, V3<R>{p.ox, p.oy, p.oz}, V3<R>{p.dx, p.dy, p.dz}, sc.bsmall, sc.bmax);
             warp_store_records<R>(tile, out + start, alive ? rank : -1, (int)__popc(amask), p);
         }
     }
@@ -607,6 +628,12 @@ struct BatchTraceIO {
     uint32_t n;
     __device__ __forceinline__ uint32_t count() const { return n; }
     __device__ __forceinline__ uint32_t* cursor() const { return cur; }
+    __device__ __forceinline__ FilterRay filter(uint32_t i, R tmin, R tmax) const {
+        V3<R> o, d;
+        load(i, o, d);
+        const V3<R> inv = {R(1) / d.x, R(1) / d.y, R(1) / d.z};  // adinv, bvh.rs:111
+        return make_filter_ray<R>(o, d, inv, tmin, tmax, sc.bsmall, sc.bmax);
+    }
     __device__ __forceinline__ void load(uint32_t i, V3<R>& o, V3<R>& d) const {
         const double* r = rays + 7ull * i;
         o = {(R)r[0], (R)r[1], (R)r[2]};
@@ -801,6 +828,8 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
     const size_t o_paths0 = carve((size_t)pool * sizeof(PathRec<R>));
     const size_t o_paths1 = carve((size_t)pool * sizeof(PathRec<R>));
     const size_t o_queues = carve((size_t)pool * Q_COUNT * sizeof(uint2));
+    const size_t o_filt0 = carve((size_t)pool * sizeof(FilterRec));
+    const size_t o_filt1 = carve((size_t)pool * sizeof(FilterRec));
     const size_t o_fb = carve((size_t)npix * 3 * sizeof(unsigned long long));
     int rc = ws.ensure(off, err);
     if (rc != CR_OK) return rc;
@@ -809,6 +838,7 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
     DevCamera* d_cam = reinterpret_cast<DevCamera*>(base + o_cam);
     PathRec<R>* paths[2] = {reinterpret_cast<PathRec<R>*>(base + o_paths0), reinterpret_cast<PathRec<R>*>(base + o_paths1)};
     uint2* queues = reinterpret_cast<uint2*>(base + o_queues);
+    FilterRec* filt[2] = {reinterpret_cast<FilterRec*>(base + o_filt0), reinterpret_cast<FilterRec*>(base + o_filt1)};
     unsigned long long* fb = reinterpret_cast<unsigned long long*>(base + o_fb);
 
     if (!ws.pinned) {
@@ -844,21 +874,21 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
 
     const DevScene<R> sc = make_dev_scene<R>(s);
     // lane-refill threshold of the trace kernel (tuning knob; CRB_REFILL in the environment overrides)
-    typedef void (*TraceFn)(DevScene<R>, PathRec<R>*, Control*, int, uint2*, uint32_t);
+    typedef void (*TraceFn)(DevScene<R>, PathRec<R>*, Control*, int, uint2*, const FilterRec*, uint32_t);
     int refill = CRB_REFILL;
     if (const char* e = getenv("CRB_REFILL")) refill = atoi(e);
     int minb = 8;
     if (const char* e = getenv("CRB_MINB")) minb = atoi(e);
 #define CRB_PICK(MB)                                                                                                        \
-    (refill <= 8 ? k_trace<R, 8, MB> : refill <= 16 ? k_trace<R, 16, MB> : refill <= 24 ? k_trace<R, 24, MB> \
+    (refill <= 4 ? k_trace<R, 4, MB> : refill <= 8 ? k_trace<R, 8, MB> : refill <= 12 ? k_trace<R, 12, MB> : refill <= 16 ? k_trace<R, 16, MB> : refill <= 24 ? k_trace<R, 24, MB> \
                                                                                                   : k_trace<R, 32, MB>)
     TraceFn trace_fn = minb <= 4 ? CRB_PICK(4) : minb <= 6 ? CRB_PICK(6) : CRB_PICK(8);
 #undef CRB_PICK
     const int g_trace = persistent_grid(trace_fn, TRACE_BLOCK, s.num_sms);
     int smb = 6;
     if (const char* e = getenv("CRB_SHADE_MINB")) smb = atoi(e);
-    typedef void (*GenFn)(const Control*, const DevCamera*, const RaygenParams<R>, PathRec<R>*);
-    typedef void (*ScatFn)(DevScene<R>, const PathRec<R>*, PathRec<R>*, Control*, int, const uint2*, uint64_t, uint32_t);
+    typedef void (*GenFn)(const Control*, const DevCamera*, const RaygenParams<R>, PathRec<R>*, FilterRec*);
+    typedef void (*ScatFn)(DevScene<R>, const PathRec<R>*, PathRec<R>*, Control*, int, const uint2*, FilterRec*, uint64_t, uint32_t);
     GenFn gen_fn = smb <= 4 ? k_raygen<R, 4> : smb <= 6 ? k_raygen<R, 6> : k_raygen<R, 8>;
     ScatFn lam_fn = smb <= 4 ? k_shade_scatter<R, CR_MAT_LAMBERTIAN, 4> : smb <= 6 ? k_shade_scatter<R, CR_MAT_LAMBERTIAN, 6> : k_shade_scatter<R, CR_MAT_LAMBERTIAN, 8>;
     ScatFn met_fn = smb <= 4 ? k_shade_scatter<R, CR_MAT_METAL, 4> : smb <= 6 ? k_shade_scatter<R, CR_MAT_METAL, 6> : k_shade_scatter<R, CR_MAT_METAL, 8>;
@@ -868,6 +898,8 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
     rp.W = W; rp.rows_local = rows_local; rp.row_block = block; rp.row_rank = rank; rp.row_world = world;
     rp.is_static = hcam.is_static; rp.lens = !(cam_in.defocus_angle <= 0.0) ? 1u : 0u; rp.small = total < 0xFFFFFFFFull ? 1u : 0u;
     rp.seed = opts.seed;
+    rp.bsmall = s.bsmall;
+    rp.bmax = s.bmax;
     host_camera_constants<R>(cam_in, rp);
     const int g_gen = persistent_grid(gen_fn, SHADE_BLOCK, s.num_sms);
     const int g_tail = persistent_grid(k_tail<R>, SHADE_BLOCK, s.num_sms);
@@ -896,7 +928,7 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
     // prologue: camera basis (static cameras), plan + raygen fill side 0
     tm.begin(2, a);
     k_plan<<<1, 32, 0, stream>>>(ctl, 0, nullptr);
-    gen_fn<<<g_gen, SHADE_BLOCK, 0, stream>>>(ctl, d_cam, rp, paths[0]);
+    gen_fn<<<g_gen, SHADE_BLOCK, 0, stream>>>(ctl, d_cam, rp, paths[0], filt[0]);
     tm.end(2, a);
     launches += 2;
     uint64_t it = 0;
@@ -904,16 +936,16 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
     while (!done) {
         const int cur = (int)(it & 1), nxt = cur ^ 1;
         tm.begin(0, a);
-        trace_fn<<<g_trace, TRACE_BLOCK, 0, stream>>>(sc, paths[cur], ctl, cur, queues, pool);
+        trace_fn<<<g_trace, TRACE_BLOCK, 0, stream>>>(sc, paths[cur], ctl, cur, queues, filt[cur], pool);
         tm.end(0, a);
         tm.begin(1, a);
         k_shade_miss<R><<<g_miss, SHADE_BLOCK, 0, stream>>>(sc, paths[cur], ctl, queues + (size_t)Q_MISS * pool, fb, fb_scale);
-        lam_fn<<<g_lam, SHADE_BLOCK, 0, stream>>>(sc, paths[cur], paths[nxt], ctl, nxt, queues + (size_t)Q_LAMBERTIAN * pool, opts.seed,
-                                                  cam_in.max_depth);
-        met_fn<<<g_met, SHADE_BLOCK, 0, stream>>>(sc, paths[cur], paths[nxt], ctl, nxt, queues + (size_t)Q_METAL * pool, opts.seed,
-                                                  cam_in.max_depth);
-        die_fn<<<g_die, SHADE_BLOCK, 0, stream>>>(sc, paths[cur], paths[nxt], ctl, nxt, queues + (size_t)Q_DIELECTRIC * pool, opts.seed,
-                                                  cam_in.max_depth);
+        lam_fn<<<g_lam, SHADE_BLOCK, 0, stream>>>(sc, paths[cur], paths[nxt], ctl, nxt, queues + (size_t)Q_LAMBERTIAN * pool, filt[nxt],
+                                                  opts.seed, cam_in.max_depth);
+        met_fn<<<g_met, SHADE_BLOCK, 0, stream>>>(sc, paths[cur], paths[nxt], ctl, nxt, queues + (size_t)Q_METAL * pool, filt[nxt],
+                                                  opts.seed, cam_in.max_depth);
+        die_fn<<<g_die, SHADE_BLOCK, 0, stream>>>(sc, paths[cur], paths[nxt], ctl, nxt, queues + (size_t)Q_DIELECTRIC * pool, filt[nxt],
+                                                  opts.seed, cam_in.max_depth);
         launches += 5;
         if (!s.clamp_colors) {
             k_shade_emissive<R><<<g_emit, SHADE_BLOCK, 0, stream>>>(sc, paths[cur], ctl, queues + (size_t)Q_EMISSIVE * pool, fb,
@@ -923,7 +955,7 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
         tm.end(1, a);
         tm.begin(2, a);
         k_plan<<<1, 32, 0, stream>>>(ctl, nxt, nullptr);
-        gen_fn<<<g_gen, SHADE_BLOCK, 0, stream>>>(ctl, d_cam, rp, paths[nxt]);
+        gen_fn<<<g_gen, SHADE_BLOCK, 0, stream>>>(ctl, d_cam, rp, paths[nxt], filt[nxt]);
         tm.end(2, a);
         launches += 2;
         const int slot = (int)(it % RING);
