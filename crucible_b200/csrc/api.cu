@@ -119,7 +119,7 @@ struct CrScene {
     size_t io_cap = 0;
 
     void free_device_scene() {
-        for (void* p : dev_allocs) cudaFree(p);
+        for (void* p : dev_allocs) cudaFreeAsync(p, stream);
         dev_allocs.clear();
         for (auto& im : images) {
             if (im.tex) cudaDestroyTextureObject(im.tex);
@@ -139,6 +139,48 @@ namespace {
 Workspace& device_workspace(int device) {
     static Workspace ws[64];
     return ws[device < 0 || device >= 64 ? 0 : device];
+}
+
+// Per-device facts, queried once per process: cudaGetDeviceProperties costs 3-50 ms per call on an 8-GPU box
+// (measured: it dominated the end-to-end step when every frame created its scene, as Scene::render_image does).
+struct DeviceInfo {
+    int state = 0;  // 0 = not queried, 1 = usable sm_100 device, -1 = unusable
+    int num_sms = 0;
+    std::string why;
+};
+DeviceInfo& device_info(int device) {
+    static DeviceInfo info[64];
+    static DeviceInfo bad;
+    if (device < 0 || device >= 64) {
+        bad.state = -1;
+        bad.why = "CUDA device " + std::to_string(device) + " not available";
+        return bad;
+    }
+    DeviceInfo& d = info[device];
+    if (d.state != 0) return d;
+    int n = 0;
+    cudaDeviceProp p;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || device >= n) {
+        cudaGetLastError();
+        d.state = -1;
+        d.why = "CUDA device " + std::to_string(device) + " not available";
+    } else if (cudaGetDeviceProperties(&p, device) != cudaSuccess || p.major != 10) {
+        cudaGetLastError();
+        d.state = -1;
+        d.why = "device is not sm_100 (this library ships sm_100a code only)";
+    } else {
+        d.state = 1;
+        d.num_sms = p.multiProcessorCount;
+        // scene buffers come from the device's stream-ordered pool and stay cached there between scenes:
+        // a per-frame scene rebuild then costs no cudaMalloc / cudaFree (each of which synchronises the device)
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t keep = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
+    return d;
 }
 
 // number of nodes BVHWrapper::help_generate creates for a span (bvhwrapper.rs:46-80)
@@ -222,9 +264,10 @@ int upload(CrScene* s, const std::vector<T>& host, void** out) {
     *out = nullptr;
     if (host.empty()) return CR_OK;
     void* d = nullptr;
-    API_CUDA(cudaMalloc(&d, host.size() * sizeof(T)));
+    API_CUDA(cudaMallocAsync(&d, host.size() * sizeof(T), s->stream));
     s->dev_allocs.push_back(d);
-    API_CUDA(cudaMemcpy(d, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
+    // pageable source: the call returns once the bytes are staged, so `host` may die with the caller's scope
+    API_CUDA(cudaMemcpyAsync(d, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice, s->stream));
     *out = d;
     return CR_OK;
 }
@@ -449,6 +492,8 @@ int upload_scene(CrScene* s) {
         if (rc != CR_OK) return rc;
         d.images = static_cast<DevImage*>(p);
     }
+    // the render may run on a caller-supplied stream: the scene is complete when commit returns
+    API_CUDA(cudaStreamSynchronize(s->stream));
     return CR_OK;
 }
 
@@ -522,31 +567,22 @@ int cr_device_count(void) {
         return 0;
     }
     int ok = 0;
-    for (int i = 0; i < n; ++i) {
-        cudaDeviceProp p;
-        if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major == 10) ++ok;
-    }
+    for (int i = 0; i < n && i < 64; ++i)
+        if (device_info(i).state == 1) ++ok;
     return ok;
 }
 
 CrScene* cr_scene_create(int device) {
     CrScene* s = new CrScene();
     if (device >= 0) {
-        int n = 0;
-        if (cudaGetDeviceCount(&n) != cudaSuccess || device >= n) {
-            cudaGetLastError();
-            g_err = "cr_scene_create: CUDA device " + std::to_string(device) + " not available";
-            delete s;
-            return nullptr;
-        }
-        cudaDeviceProp p;
-        if (cudaGetDeviceProperties(&p, device) != cudaSuccess || p.major != 10) {
-            g_err = "cr_scene_create: device is not sm_100 (this library ships sm_100a code only)";
+        const DeviceInfo& di = device_info(device);
+        if (di.state != 1) {
+            g_err = "cr_scene_create: " + di.why;
             delete s;
             return nullptr;
         }
         s->device = device;
-        s->num_sms = p.multiProcessorCount;
+        s->num_sms = di.num_sms;
         cudaSetDevice(device);
         if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) {
             g_err = "cr_scene_create: cudaStreamCreate failed";
@@ -562,10 +598,10 @@ void cr_scene_destroy(CrScene* s) {
     if (s->device >= 0) {
         cudaSetDevice(s->device);
         s->free_device_scene();
-        if (s->d_out_rgb) cudaFree(s->d_out_rgb);
-        if (s->d_out_rgb8) cudaFree(s->d_out_rgb8);
-        if (s->d_io) cudaFree(s->d_io);
-        if (s->stream) cudaStreamDestroy(s->stream);
+        if (s->d_out_rgb) cudaFreeAsync(s->d_out_rgb, s->stream);
+        if (s->d_out_rgb8) cudaFreeAsync(s->d_out_rgb8, s->stream);
+        if (s->d_io) cudaFreeAsync(s->d_io, s->stream);
+        if (s->stream) cudaStreamDestroy(s->stream);  // resources are released once the queued work has drained
     }
     delete s;
 }
@@ -758,10 +794,10 @@ int cr_trace_batch(CrScene* s, const double* rays, size_t n, double tmin, double
     const size_t bytes_in = n * 7 * sizeof(double), bytes_out = n * sizeof(CrHit);
     const size_t need = ((bytes_in + 255) & ~(size_t)255) + ((bytes_out + 255) & ~(size_t)255) + 256;
     if (need > s->io_cap) {
-        if (s->d_io) cudaFree(s->d_io);
+        if (s->d_io) cudaFreeAsync(s->d_io, s->stream);
         s->d_io = nullptr;
         s->io_cap = 0;
-        API_CUDA(cudaMalloc(&s->d_io, need));
+        API_CUDA(cudaMallocAsync(&s->d_io, need, s->stream));
         s->io_cap = need;
     }
     double* d_rays = static_cast<double*>(s->d_io);
@@ -818,12 +854,12 @@ int cr_render(CrScene* s, const CrCamera* cam, const CrRenderOpts* opts, double*
     if (stats) memset(stats, 0, sizeof(*stats));
     const size_t npix = (size_t)cam->image_width * cam->image_height;
     if (npix > s->out_cap) {
-        if (s->d_out_rgb) cudaFree(s->d_out_rgb);
-        if (s->d_out_rgb8) cudaFree(s->d_out_rgb8);
+        if (s->d_out_rgb) cudaFreeAsync(s->d_out_rgb, s->stream);
+        if (s->d_out_rgb8) cudaFreeAsync(s->d_out_rgb8, s->stream);
         s->d_out_rgb = s->d_out_rgb8 = nullptr;
         s->out_cap = 0;
-        API_CUDA(cudaMalloc(&s->d_out_rgb, npix * 3 * sizeof(double)));
-        API_CUDA(cudaMalloc(&s->d_out_rgb8, npix * 3));
+        API_CUDA(cudaMallocAsync(&s->d_out_rgb, npix * 3 * sizeof(double), s->stream));
+        API_CUDA(cudaMallocAsync(&s->d_out_rgb8, npix * 3, s->stream));
         s->out_cap = npix;
     }
     const bool sharded = opts->row_world > 1;

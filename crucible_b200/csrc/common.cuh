@@ -45,7 +45,7 @@ struct __align__(16) NodeRec<double> {
     uint32_t left, right, pad0, pad1;
 };
 template <>
-struct __align__(16) NodeRec<float> {
+struct __align__(32) NodeRec<float> {
     float xmin, xmax, ymin, ymax, zmin, zmax;
     uint32_t left, right;
 };
@@ -188,6 +188,21 @@ __device__ __forceinline__ T ldg_rec(const T* p) {
 #pragma unroll
     for (int i = 0; i < NWORDS; ++i) d[i] = __ldg(s + i);
     return out;
+}
+
+// One 256-bit read-only load (LDG.E.ENL2.256.CONSTANT, sm_100+) of a 32-byte f32 node: a divergent warp-wide
+// load costs one L1 wavefront per distinct line touched, so one 32 B load halves the L1 data-pipe work of two
+// 16 B loads of the same record (ncu: l1tex__data_pipe_lsu_wavefronts was 68 % of peak in k_trace).
+__device__ __forceinline__ NodeRec<float> ldg_node32(const NodeRec<float>* p) {
+#ifdef CRB_NO_LDG256
+    return ldg_rec<2>(p);
+#else
+    NodeRec<float> n;
+    asm("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(n.xmin), "=f"(n.xmax), "=f"(n.ymin), "=f"(n.ymax), "=f"(n.zmin), "=f"(n.zmax), "=r"(n.left), "=r"(n.right)
+        : "l"(p));
+    return n;
+#endif
 }
 
 }  // namespace crb

@@ -374,7 +374,18 @@ __device__ __forceinline__ bool is_finite(R x) {
 struct FilterRay {
     float ox, oy, oz, ix, iy, iz, dx, dy, dz;
     float e_small, e_big, o2;
+    // derived at lane refill (f64 path): the box filter evaluates every plane as ONE fused multiply-add,
+    //   t = fma(b, inv, -(o * inv)),  near/far chosen by the sign of inv through a (inv, 0) / (0, inv) pair:
+    //   near = fma(bmin, a0, fma(bmax, a1, -oi)),  far = fma(bmax, a0, fma(bmin, a1, -oi))
+    // (fma(x, 0, c) == c exactly for finite x), which moves the six per-axis min/max out of the ALU pipe.
+    float oix, oiy, oiz, ax0, ax1, ay0, ay1, az0, az1;
     bool ok;  // the ray is regular and representable in f32: filters may be used
+    __device__ __forceinline__ void derive() {
+        oix = ox * ix; oiy = oy * iy; oiz = oz * iz;
+        ax0 = fmaxf(ix, 0.f); ax1 = fminf(ix, 0.f);
+        ay0 = fmaxf(iy, 0.f); ay1 = fminf(iy, 0.f);
+        az0 = fmaxf(iz, 0.f); az1 = fminf(iz, 0.f);
+    }
 };
 static constexpr uint32_t BIGBOX_BIT = 1u << 27;
 static constexpr uint32_t INDEX_MASK = 0x07FFFFFFu;
@@ -386,15 +397,18 @@ __device__ __forceinline__ FilterRay make_filter_ray(V3<R> o, V3<R> d, V3<R> inv
     f.ix = (float)inv.x; f.iy = (float)inv.y; f.iz = (float)inv.z;
     f.dx = (float)d.x; f.dy = (float)d.y; f.dz = (float)d.z;
     const float ax = fabsf(f.ix), ay = fabsf(f.iy), az = fabsf(f.iz);
-    const float oo_x = fabsf(f.ox) * 5.9604645e-8f, oo_y = fabsf(f.oy) * 5.9604645e-8f, oo_z = fabsf(f.oz) * 5.9604645e-8f;
-    const float ks = bsmall * 1.1920929e-7f, kb = bmax * 1.1920929e-7f;  // B * 2^-23
+    const float u23 = 1.1920929e-7f;  // 2^-23
+    const float oo_x = fabsf(f.ox) * u23, oo_y = fabsf(f.oy) * u23, oo_z = fabsf(f.oz) * u23;
+    const float ks = bsmall * u23, kb = bmax * u23;  // B * 2^-23
     f.e_small = 2.5f * fmaxf(ax * (ks + oo_x), fmaxf(ay * (ks + oo_y), az * (ks + oo_z)));
     f.e_big = 2.5f * fmaxf(ax * (kb + oo_x), fmaxf(ay * (kb + oo_y), az * (kb + oo_z)));
     f.o2 = f.ox * f.ox + f.oy * f.oy + f.oz * f.oz;
     const bool regular = is_finite(o.x) && is_finite(o.y) && is_finite(o.z) && is_finite(inv.x) && is_finite(inv.y) &&
                          is_finite(inv.z) && inv.x != R(0) && inv.y != R(0) && inv.z != R(0) && !(tmin != tmin) && !(tmax != tmax);
     // skipped for irregular rays and when f32 cannot represent the ray (overflow / underflow)
-    f.ok = regular && f.e_big < 3.0e37f && ax > 1.0e-30f && ay > 1.0e-30f && az > 1.0e-30f && f.o2 < 1.0e30f;
+    f.derive();
+    f.ok = regular && f.e_big < 3.0e37f && ax > 1.0e-30f && ay > 1.0e-30f && az > 1.0e-30f && f.o2 < 1.0e30f &&
+           fabsf(f.oix) < 3.0e37f && fabsf(f.oiy) < 3.0e37f && fabsf(f.oiz) < 3.0e37f;
     return f;
 }
 // 48 B image of a FilterRay, written next to every path record by the kernel that PRODUCES the ray (raygen /
@@ -415,9 +429,10 @@ __device__ __forceinline__ FilterRay unpack_filter(const FilterRec& o) {
     r.ox = o.f[0]; r.oy = o.f[1]; r.oz = o.f[2]; r.ix = o.f[3]; r.iy = o.f[4]; r.iz = o.f[5];
     r.dx = o.f[6]; r.dy = o.f[7]; r.dz = o.f[8]; r.e_small = o.f[9]; r.e_big = o.f[10]; r.o2 = o.f[11];
     r.ok = o.f[11] >= 0.0f;
+    r.derive();
     return r;
 }
-// f32 evaluation of the slab intervals (shared by the filter and by the f32 path's own box test)
+// f32 evaluation of the slab intervals: the f32 path's own box test
 __device__ __forceinline__ void slab32(const NodeRec<float>& n, const FilterRay& f, float tmin, float best, float& lo, float& hi) {
     const float x0 = (n.xmin - f.ox) * f.ix, x1 = (n.xmax - f.ox) * f.ix;
     const float y0 = (n.ymin - f.oy) * f.iy, y1 = (n.ymax - f.oy) * f.iy;
@@ -425,12 +440,23 @@ __device__ __forceinline__ void slab32(const NodeRec<float>& n, const FilterRay&
     lo = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), tmin));
     hi = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), best));
 }
-// +1 = passes, -1 = fails, 0 = undecided (exact f64 test required)
+// Conservative filter of the f64 path: +1 = passes, -1 = fails, 0 = undecided (exact f64 test required).
+// Every plane distance is one FFMA, t32 = fl(b32 * inv32 - oi32) with oi32 = fl(o32 * inv32).  With u = 2^-24:
+// |b32 - b| <= 2u|b| (outward rounding), |inv32 - inv| <= u|inv|, |o32 - o| <= u|o|, two more roundings, so
+//     |t32 - t64| <= 1.01 |inv32| (|b| + |o32|) 2^-23 + 2.01 u |t64|.
+// e = 2.5 max_axis |inv32| (B + |o32|) 2^-23 (per ray, B = bound of the node class) and 2^-21 (|lo32| + |hi32|)
+// therefore bound the error of hi - lo with margin to spare.
 __device__ __forceinline__ int filter_box(const NodeRec<float>& n, const FilterRay& f, float tmin, float best) {
-    float lo, hi;
-    slab32(n, f, tmin, best, lo, hi);
+    const float nx = __fmaf_rn(n.xmin, f.ax0, __fmaf_rn(n.xmax, f.ax1, -f.oix));
+    const float fx = __fmaf_rn(n.xmax, f.ax0, __fmaf_rn(n.xmin, f.ax1, -f.oix));
+    const float ny = __fmaf_rn(n.ymin, f.ay0, __fmaf_rn(n.ymax, f.ay1, -f.oiy));
+    const float fy = __fmaf_rn(n.ymax, f.ay0, __fmaf_rn(n.ymin, f.ay1, -f.oiy));
+    const float nz = __fmaf_rn(n.zmin, f.az0, __fmaf_rn(n.zmax, f.az1, -f.oiz));
+    const float fz = __fmaf_rn(n.zmax, f.az0, __fmaf_rn(n.zmin, f.az1, -f.oiz));
+    const float lo = fmaxf(fmaxf(nx, ny), fmaxf(nz, tmin));
+    const float hi = fminf(fminf(fx, fy), fminf(fz, best));
     const float diff = hi - lo;
-    const float E = ((n.left & BIGBOX_BIT) ? f.e_big : f.e_small) + 4.7683716e-7f * (fabsf(lo) + fabsf(hi));
+    const float E = __fmaf_rn(fabsf(lo) + fabsf(hi), 4.7683716e-7f, (n.left & BIGBOX_BIT) ? f.e_big : f.e_small);
     if (diff > E) return 1;
     if (diff < -E) return -1;
     return 0;  // also NaN / inf
@@ -499,7 +525,7 @@ struct Trav {
     // When a leaf node is entered its primitives are pre-filtered: all definite misses => nothing to test.
     __device__ __forceinline__ int step_node(const DevScene<R>& sc, R tmin) {
         if (!fr.ok) return ST_EXACT;
-        const NodeRec<float> nf = ldg_rec<2>(sc.nodes32 + i);
+        const NodeRec<float> nf = ldg_node32(sc.nodes32 + i);
         bool hit;
         if constexpr (sizeof(R) == 8) {
             const int dec = filter_box(nf, fr, (float)tmin, (float)best_t);

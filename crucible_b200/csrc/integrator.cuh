@@ -335,6 +335,11 @@ struct RenderTraceIO {
     __device__ __forceinline__ uint32_t count() const { return n; }
     __device__ __forceinline__ uint32_t* cursor() const { return &ctl->trace_next; }
     __device__ __forceinline__ FilterRay filter(uint32_t i, R, R) const {  // written by the ray's producer
+#ifdef CRB_PREFETCH_L1
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(paths + i));
+#elif defined(CRB_PREFETCH_L2)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(paths + i));
+#endif
         FilterRec r;
         const int4* s = reinterpret_cast<const int4*>(filt + i);
         int4* d = reinterpret_cast<int4*>(&r);
