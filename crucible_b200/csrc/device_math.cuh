@@ -433,7 +433,8 @@ __device__ __forceinline__ FilterRay unpack_filter(const FilterRec& o) {
     return r;
 }
 // f32 evaluation of the slab intervals: the f32 path's own box test
-__device__ __forceinline__ void slab32(const NodeRec<float>& n, const FilterRay& f, float tmin, float best, float& lo, float& hi) {
+template <typename F>
+__device__ __forceinline__ void slab32(const NodeRec<float>& n, const F& f, float tmin, float best, float& lo, float& hi) {
     const float x0 = (n.xmin - f.ox) * f.ix, x1 = (n.xmax - f.ox) * f.ix;
     const float y0 = (n.ymin - f.oy) * f.iy, y1 = (n.ymax - f.oy) * f.iy;
     const float z0 = (n.zmin - f.oz) * f.iz, z1 = (n.zmax - f.oz) * f.iz;
@@ -446,7 +447,8 @@ __device__ __forceinline__ void slab32(const NodeRec<float>& n, const FilterRay&
 //     |t32 - t64| <= 1.01 |inv32| (|b| + |o32|) 2^-23 + 2.01 u |t64|.
 // e = 2.5 max_axis |inv32| (B + |o32|) 2^-23 (per ray, B = bound of the node class) and 2^-21 (|lo32| + |hi32|)
 // therefore bound the error of hi - lo with margin to spare.
-__device__ __forceinline__ int filter_box(const NodeRec<float>& n, const FilterRay& f, float tmin, float best) {
+template <typename F>
+__device__ __forceinline__ int filter_box(const NodeRec<float>& n, const F& f, float tmin, float best) {
     const float nx = __fmaf_rn(n.xmin, f.ax0, __fmaf_rn(n.xmax, f.ax1, -f.oix));
     const float fx = __fmaf_rn(n.xmax, f.ax0, __fmaf_rn(n.xmin, f.ax1, -f.oix));
     const float ny = __fmaf_rn(n.ymin, f.ay0, __fmaf_rn(n.ymax, f.ay1, -f.oiy));
@@ -461,8 +463,12 @@ __device__ __forceinline__ int filter_box(const NodeRec<float>& n, const FilterR
     if (diff < -E) return -1;
     return 0;  // also NaN / inf
 }
+// The part of a FilterRay the sphere pre-filter needs (kept out of the node loop's registers).
+struct PreRay {
+    float ox, oy, oz, dx, dy, dz, o2;
+};
 // true = Sphere::hit certainly returns None for this ray (f64 discriminant certainly negative)
-__device__ __forceinline__ bool sphere_definite_miss(const SphereRec<float>& s, const FilterRay& f) {
+__device__ __forceinline__ bool sphere_definite_miss(const SphereRec<float>& s, const PreRay& f) {
     const float ocx = s.cx - f.ox, ocy = s.cy - f.oy, ocz = s.cz - f.oz;
     const float a = f.dx * f.dx + f.dy * f.dy + f.dz * f.dz;
     const float h = f.dx * ocx + f.dy * ocy + f.dz * ocz;
@@ -478,6 +484,77 @@ __device__ __forceinline__ bool sphere_definite_miss(const SphereRec<float>& s, 
 // Lane states
 enum : int { ST_IDLE = 0, ST_NODE = 1, ST_EXACT = 2, ST_LEAF = 3, ST_DONE = 4 };
 
+// What the node loop keeps in registers per lane: the constants of the box test and nothing else.
+template <typename R> struct NodeRay;
+template <> struct NodeRay<double> {  // conservative filter: one FFMA per plane (filter_box)
+    float oix, oiy, oiz, ax0, ax1, ay0, ay1, az0, az1, e_small, e_big;
+    __device__ __forceinline__ void set(const FilterRay& f) {
+        oix = f.oix; oiy = f.oiy; oiz = f.oiz; ax0 = f.ax0; ax1 = f.ax1; ay0 = f.ay0; ay1 = f.ay1; az0 = f.az0; az1 = f.az1;
+        e_small = f.e_small; e_big = f.e_big;
+    }
+};
+template <> struct NodeRay<float> {  // the f32 path's own box test (slab32)
+    float ox, oy, oz, ix, iy, iz;
+    __device__ __forceinline__ void set(const FilterRay& f) { ox = f.ox; oy = f.oy; oz = f.oz; ix = f.ix; iy = f.iy; iz = f.iz; }
+};
+
+// Everything else a lane carries (closest hit, the ray's index, the f32 ray of the sphere pre-filter, the
+// R-precision ray of the exact / leaf steps) sits behind a Store.  RegStore = registers (k_tail: one thread
+// follows one path).  SmemStore = a per-CTA shared-memory table, SoA over the CTA's lanes so every access
+// is conflict free: the trace kernel is latency bound (ncu: 1.6 eligible warps per scheduler, long-scoreboard
+// the top stall), so the registers this frees buy resident warps, and the exact / leaf steps read their ray
+// at shared-memory latency instead of re-reading the path record from L2 / HBM.
+template <typename R>
+struct RegStore {
+    R bt;
+    uint32_t bref, idx;
+    PreRay pre;
+    V3<R> ro, rd;
+    __device__ __forceinline__ R best_t() const { return bt; }
+    __device__ __forceinline__ uint32_t best_ref() const { return bref; }
+    __device__ __forceinline__ void set_best(R t, uint32_t ref) { bt = t; bref = ref; }
+    __device__ __forceinline__ uint32_t my() const { return idx; }
+    __device__ __forceinline__ void set_my(uint32_t k) { idx = k; }
+    __device__ __forceinline__ void set_pre(const FilterRay& f) { pre = {f.ox, f.oy, f.oz, f.dx, f.dy, f.dz, f.o2}; }
+    __device__ __forceinline__ PreRay get_pre() const { return pre; }
+    __device__ __forceinline__ void set_ray(V3<R> o, V3<R> d) { ro = o; rd = d; }
+    __device__ __forceinline__ void get_ray(V3<R>& o, V3<R>& d) const { o = ro; d = rd; }
+};
+template <typename R, int BLOCK>
+struct LaneSlots {
+    R best_t[BLOCK];
+    R ray[6][BLOCK];
+    float pre[7][BLOCK];
+    uint32_t best_ref[BLOCK], my[BLOCK];
+};
+template <typename R, int BLOCK>
+struct SmemStore {
+    LaneSlots<R, BLOCK>* s;
+    __device__ __forceinline__ R best_t() const { return s->best_t[threadIdx.x]; }
+    __device__ __forceinline__ uint32_t best_ref() const { return s->best_ref[threadIdx.x]; }
+    __device__ __forceinline__ void set_best(R t, uint32_t ref) { s->best_t[threadIdx.x] = t; s->best_ref[threadIdx.x] = ref; }
+    __device__ __forceinline__ uint32_t my() const { return s->my[threadIdx.x]; }
+    __device__ __forceinline__ void set_my(uint32_t k) { s->my[threadIdx.x] = k; }
+    __device__ __forceinline__ void set_pre(const FilterRay& f) {
+        const int t = threadIdx.x;
+        s->pre[0][t] = f.ox; s->pre[1][t] = f.oy; s->pre[2][t] = f.oz; s->pre[3][t] = f.dx; s->pre[4][t] = f.dy; s->pre[5][t] = f.dz;
+        s->pre[6][t] = f.o2;
+    }
+    __device__ __forceinline__ PreRay get_pre() const {
+        const int t = threadIdx.x;
+        return {s->pre[0][t], s->pre[1][t], s->pre[2][t], s->pre[3][t], s->pre[4][t], s->pre[5][t], s->pre[6][t]};
+    }
+    __device__ __forceinline__ void set_ray(V3<R> o, V3<R> d) {
+        const int t = threadIdx.x;
+        s->ray[0][t] = o.x; s->ray[1][t] = o.y; s->ray[2][t] = o.z; s->ray[3][t] = d.x; s->ray[4][t] = d.y; s->ray[5][t] = d.z;
+    }
+    __device__ __forceinline__ void get_ray(V3<R>& o, V3<R>& d) const {
+        const int t = threadIdx.x;
+        o = {s->ray[0][t], s->ray[1][t], s->ray[2][t]};
+        d = {s->ray[3][t], s->ray[4][t], s->ray[5][t]};
+    }
+};
+
 // Stackless, threaded traversal.  The host flattens the reference tree in PREORDER, so the reference's
 // recursion (bvhwrapper.rs:97-126: box test, then left subtree, then right subtree, one running
 // closest t) visits nodes in increasing index order and a failed box test jumps to the node's SKIP
@@ -488,100 +565,114 @@ enum : int { ST_IDLE = 0, ST_NODE = 1, ST_EXACT = 2, ST_LEAF = 3, ST_DONE = 4 };
 // (a node built from a span of 1 or 2 holds its primitives directly, a node built from a span >= 3
 // has two node children: bvhwrapper.rs:57-74.)  Leaves are tested with no box of their own, left
 // first, right with the updated interval, strict comparisons — the reference's order.
-//
-// The per-lane state kept in registers across steps is deliberately small (f32 ray for the cheap steps,
-// closest hit, cursor); the f64 ray is re-read from the ray's record for the rare exact / leaf steps.
-template <typename R>
+template <typename R, typename Store>
 struct Trav {
-    FilterRay fr;
-    R best_t;
-    uint32_t best_ref, i, pl, pr;  // i = next node index; pl/pr = parked leaf primitives
+    NodeRay<R> nr;
+    Store store;
+    float best32;     // (float)best_t, refreshed whenever best_t changes
+    uint32_t i;       // next node index
+    uint32_t wa, wb;  // words of the node tested last; after ST_LEAF they are the parked leaf primitives
+    bool ok;          // the ray is regular and representable in f32: the cheap node step may be used
 
+    __device__ __forceinline__ int walk_state() const { return ok ? (int)ST_NODE : (int)ST_EXACT; }
     __device__ __forceinline__ void init_from(const FilterRay& f, R tmax) {
-        fr = f;
-        best_t = tmax;
-        best_ref = REF_MISS;
+        nr.set(f);
+        ok = f.ok;
+        store.set_pre(f);
+        store.set_best(tmax, REF_MISS);
+        best32 = (float)tmax;
         i = 0;
-        pl = pr = REF_NONE;
+        wa = wb = REF_NONE;
     }
     __device__ __forceinline__ void init(V3<R> o, V3<R> d, R tmin, R tmax, float bsmall, float bmax) {
         const V3<R> inv = {R(1) / d.x, R(1) / d.y, R(1) / d.z};  // adinv, bvh.rs:111
         init_from(make_filter_ray<R>(o, d, inv, tmin, tmax, bsmall, bmax), tmax);
     }
-    // the box test of node i has been decided
-    __device__ __forceinline__ int after_box(bool hit, uint32_t wa, uint32_t wb, uint32_t n_nodes) {
+    // the box test of node i (words wa, wb) has been decided
+    template <bool KNOWN_OK>
+    __device__ __forceinline__ int after_box(bool hit, uint32_t n_nodes) {
         const bool leafnode = ref_is_leaf(wa);
-        const uint32_t here = i;
-        i = (hit || leafnode) ? here + 1u : (wa & INDEX_MASK);
-        if (hit && leafnode) {
-            pl = wa & ~BIGBOX_BIT;
-            pr = wb;
-            return ST_LEAF;
-        }
-        return i >= n_nodes ? ST_DONE : ST_NODE;
+        i = (hit || leafnode) ? i + 1u : (wa & INDEX_MASK);
+        if (hit && leafnode) return ST_LEAF;
+        return i >= n_nodes ? (int)ST_DONE : (KNOWN_OK ? (int)ST_NODE : walk_state());
     }
-    // NODE step.  f64 path: conservative filter (may answer ST_EXACT); f32 path: the f32 box test itself
-    // (regular rays: min/max form == comparison form; irregular rays go to the comparison form in step_exact).
-    // When a leaf node is entered its primitives are pre-filtered: all definite misses => nothing to test.
+    // NODE step (precondition: ok).  f64 path: conservative filter (may answer ST_EXACT); f32 path: the f32 box
+    // test itself (regular rays: min/max form == comparison form; irregular rays use step_exact).
     __device__ __forceinline__ int step_node(const DevScene<R>& sc, R tmin) {
-        if (!fr.ok) return ST_EXACT;
         const NodeRec<float> nf = ldg_node32(sc.nodes32 + i);
+        wa = nf.left;
+        wb = nf.right;
         bool hit;
         if constexpr (sizeof(R) == 8) {
-            const int dec = filter_box(nf, fr, (float)tmin, (float)best_t);
+            const int dec = filter_box(nf, nr, (float)tmin, best32);
             if (dec == 0) return ST_EXACT;
             hit = dec > 0;
         } else {
             float lo, hi;
-            slab32(nf, fr, tmin, best_t, lo, hi);
+            slab32(nf, nr, tmin, best32, lo, hi);
             hit = hi > lo;
         }
-        return after_box(hit, nf.left, nf.right, sc.n_nodes);
+        return after_box<true>(hit, sc.n_nodes);
     }
-    // exact box test of node i in R arithmetic on the ray re-read from its record
+    // exact box test of node i in R arithmetic
     __device__ __forceinline__ int step_exact(const DevScene<R>& sc, V3<R> o, V3<R> d, R tmin) {
         const V3<R> inv = {R(1) / d.x, R(1) / d.y, R(1) / d.z};
         const NodeRec<R> n = ldg_rec<sizeof(NodeRec<R>) / 16>(sc.nodes + i);
-        const bool hit = fr.ok ? aabb_hit_regular(n, o, inv, inv.x > R(0), inv.y > R(0), inv.z > R(0), tmin, best_t)
-                               : aabb_hit(n, o, inv, tmin, best_t);
-        return after_box(hit, n.left, n.right, sc.n_nodes);
+        wa = n.left;
+        wb = n.right;
+        const R best = store.best_t();
+        const bool hit = ok ? aabb_hit_regular(n, o, inv, inv.x > R(0), inv.y > R(0), inv.z > R(0), tmin, best)
+                            : aabb_hit(n, o, inv, tmin, best);
+        return after_box<false>(hit, sc.n_nodes);
     }
-    __device__ __forceinline__ void test_prim(const DevScene<R>& sc, uint32_t ref, V3<R> o, V3<R> d, R a, R tmin) {
+    __device__ __forceinline__ uint32_t leaf_left() const { return wa & ~BIGBOX_BIT; }
+    __device__ __forceinline__ uint32_t leaf_right() const { return wb; }
+    static __device__ __forceinline__ bool test_prim(const DevScene<R>& sc, uint32_t ref, V3<R> o, V3<R> d, R a, R tmin, R best, R& t) {
         const uint32_t kind = ref_kind(ref), idx = ref_index(ref);
-        R t;
-        bool got;
         if (kind == CR_PRIM_SPHERE) {
             const SphereRec<R> s = ldg_rec<sizeof(SphereRec<R>) / 16>(sc.spheres + idx);
-            got = sphere_hit_t(s, o, d, a, tmin, best_t, t);
+            return sphere_hit_t(s, o, d, a, tmin, best, t);
         } else if (kind == CR_PRIM_TRIANGLE) {
             const TriRec<R> tr = ldg_rec<sizeof(TriRec<R>) / 16>(sc.tris + idx);
-            got = tri_hit_t(tr, o, d, tmin, best_t, t);
+            return tri_hit_t(tr, o, d, tmin, best, t);
         } else {
             const QuadRec<R> q = ldg_rec<sizeof(QuadRec<R>) / 16>(sc.quads + idx);
             R al, be;
-            got = quad_hit_t(q, o, d, tmin, best_t, t, al, be);
-        }
-        if (got) {
-            best_t = t;
-            best_ref = ref;
+            return quad_hit_t(q, o, d, tmin, best, t, al, be);
         }
     }
     // f64 path: are all primitives of the parked leaf node certain misses (nothing to test)?
     __device__ __forceinline__ bool leaf_certain_miss(const DevScene<R>& sc) const {
         if constexpr (sizeof(R) == 8) {
-            if (!fr.ok || ref_kind(pl) != CR_PRIM_SPHERE) return false;
-            if (!sphere_definite_miss(ldg_rec<1>(sc.spheres32 + ref_index(pl)), fr)) return false;
+            const uint32_t pl = leaf_left(), pr = leaf_right();
+            if (!ok || ref_kind(pl) != CR_PRIM_SPHERE) return false;
+            const PreRay pre = store.get_pre();
+            if (!sphere_definite_miss(ldg_rec<1>(sc.spheres32 + ref_index(pl)), pre)) return false;
             if (pr == REF_NONE) return true;
-            return ref_kind(pr) == CR_PRIM_SPHERE && sphere_definite_miss(ldg_rec<1>(sc.spheres32 + ref_index(pr)), fr);
+            return ref_kind(pr) == CR_PRIM_SPHERE && sphere_definite_miss(ldg_rec<1>(sc.spheres32 + ref_index(pr)), pre);
         } else {
             return false;
         }
     }
+    __device__ __forceinline__ int after_leaf(const DevScene<R>& sc) const { return i >= sc.n_nodes ? (int)ST_DONE : walk_state(); }
     __device__ __forceinline__ int step_leaf(const DevScene<R>& sc, V3<R> o, V3<R> d, R tmin) {
         const R a = vlen2(d);  // sphere.rs:74
-        test_prim(sc, pl, o, d, a, tmin);
-        if (pr != REF_NONE) test_prim(sc, pr, o, d, a, tmin);
-        return i >= sc.n_nodes ? ST_DONE : ST_NODE;
+        R best = store.best_t(), t;
+        uint32_t bref = REF_NONE;
+        const uint32_t pl = leaf_left(), pr = leaf_right();
+        if (test_prim(sc, pl, o, d, a, tmin, best, t)) {
+            best = t;
+            bref = pl;
+        }
+        if (pr != REF_NONE && test_prim(sc, pr, o, d, a, tmin, best, t)) {
+            best = t;
+            bref = pr;
+        }
+        if (bref != REF_NONE) {
+            store.set_best(best, bref);
+            best32 = (float)best;
+        }
+        return after_leaf(sc);
     }
 };
 
@@ -594,18 +685,17 @@ struct Trav {
 // whole warp along for one lane.  Finished lanes are refilled (one atomic per warp) as soon as REFILL
 // of them are idle.  Each lane's own sequence of tests is the reference's, so is the result.
 //   IO::count() / cursor() / filter(i,tmin,tmax) / load(i,o,d) / commit(has,i,ref,t,o,d)  (commit is warp-synchronous)
-template <typename R, int REFILL, typename IO>
-__device__ __forceinline__ void trace_persistent(const DevScene<R>& sc, R tmin, R tmax, IO& io) {
+template <typename R, int REFILL, int BLOCK, typename IO>
+__device__ __forceinline__ void trace_persistent(const DevScene<R>& sc, R tmin, R tmax, IO& io, LaneSlots<R, BLOCK>* slots) {
     const int NODE_SLICE = sc.node_slice;
     const uint32_t n = io.count();
     const int lane = threadIdx.x & 31;
-    Trav<R> tv;
-    tv.fr.ok = false;
+    Trav<R, SmemStore<R, BLOCK>> tv;
+    tv.store.s = slots;
+    tv.ok = false;
     tv.i = 0;
-    tv.pl = tv.pr = REF_NONE;
-    tv.best_ref = REF_MISS;
-    tv.best_t = tmax;
-    uint32_t my = 0;
+    tv.wa = tv.wb = REF_NONE;
+    tv.best32 = (float)tmax;
     int st = ST_IDLE;
     bool exhausted = false;
     const bool small = n <= gridDim.x * blockDim.x;
@@ -615,8 +705,15 @@ __device__ __forceinline__ void trace_persistent(const DevScene<R>& sc, R tmin, 
         if ((!exhausted && n_free >= REFILL) || walking == 0u) {  // warp-uniform
             {
                 V3<R> o = {R(0), R(0), R(0)}, d = {R(0), R(0), R(0)};
-                if (st == ST_DONE && io.commit_needs_ray()) io.load(my, o, d);
-                io.commit(st == ST_DONE, my, tv.best_ref, tv.best_t, o, d);
+                uint32_t my = 0, bref = REF_MISS;
+                R bt = tmax;
+                if (st == ST_DONE) {
+                    my = tv.store.my();
+                    bref = tv.store.best_ref();
+                    bt = tv.store.best_t();
+                    if (io.commit_needs_ray()) tv.store.get_ray(o, d);
+                }
+                io.commit(st == ST_DONE, my, bref, bt, o, d);
             }
             if (st == ST_DONE) st = ST_IDLE;
             if (!exhausted) {
@@ -632,9 +729,12 @@ __device__ __forceinline__ void trace_persistent(const DevScene<R>& sc, R tmin, 
                 if (st == ST_IDLE) {
                     const uint32_t k = base + (uint32_t)__popc(~walking & ((1u << lane) - 1u));
                     if (k < n) {
-                        my = k;
+                        tv.store.set_my(k);
+                        V3<R> o, d;
+                        io.load(k, o, d);  // the R-precision ray of the exact / leaf steps goes to the lane's slot
                         tv.init_from(io.filter(k, tmin, tmax), tmax);
-                        st = (sc.n_nodes == 0u) ? ST_DONE : ST_NODE;
+                        tv.store.set_ray(o, d);
+                        st = (sc.n_nodes == 0u) ? (int)ST_DONE : tv.walk_state();
                     }
                 }
                 if (small || base + (uint32_t)n_free >= n) exhausted = true;
@@ -652,12 +752,12 @@ __device__ __forceinline__ void trace_persistent(const DevScene<R>& sc, R tmin, 
             if (__popc(__ballot_sync(0xffffffffu, st == ST_NODE)) < sc.min_node_lanes) break;
         }
         // ---- LEAF pre-filter: leaf nodes whose primitives are all certain misses need no f64 work
-        if (st == ST_LEAF && tv.leaf_certain_miss(sc)) st = tv.i >= sc.n_nodes ? ST_DONE : ST_NODE;
-        // ---- EXACT + LEAF phases share one re-read of the f64 ray
+        if (st == ST_LEAF && tv.leaf_certain_miss(sc)) st = tv.after_leaf(sc);
+        // ---- EXACT + LEAF phases share one read of the lane's ray
         if (__any_sync(0xffffffffu, st == ST_EXACT || st == ST_LEAF)) {
             if (st == ST_EXACT || st == ST_LEAF) {
                 V3<R> o, d;
-                io.load(my, o, d);
+                tv.store.get_ray(o, d);
                 if (st == ST_EXACT) st = tv.step_exact(sc, o, d, tmin);
                 if (st == ST_LEAF) st = tv.step_leaf(sc, o, d, tmin);
             }

@@ -335,11 +335,6 @@ struct RenderTraceIO {
     __device__ __forceinline__ uint32_t count() const { return n; }
     __device__ __forceinline__ uint32_t* cursor() const { return &ctl->trace_next; }
     __device__ __forceinline__ FilterRay filter(uint32_t i, R, R) const {  // written by the ray's producer
-#ifdef CRB_PREFETCH_L1
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(paths + i));
-#elif defined(CRB_PREFETCH_L2)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(paths + i));
-#endif
         FilterRec r;
         const int4* s = reinterpret_cast<const int4*>(filt + i);
         int4* d = reinterpret_cast<int4*>(&r);
@@ -387,8 +382,9 @@ struct RenderTraceIO {
 template <typename R, int REFILL, int MINB>
 __global__ void __launch_bounds__(TRACE_BLOCK, MINB) k_trace(DevScene<R> sc, PathRec<R>* __restrict__ paths, Control* __restrict__ ctl,
                                                         int side, uint2* __restrict__ queues, const FilterRec* __restrict__ filt, uint32_t pool) {
+    __shared__ LaneSlots<R, TRACE_BLOCK> slots;
     RenderTraceIO<R> io{sc, paths, ctl, queues, filt, ctl->n_in[side], pool};
-    trace_persistent<R, REFILL>(sc, R(0.001), Num<R>::inf(), io);  // ray_casting.rs:119
+    trace_persistent<R, REFILL, TRACE_BLOCK>(sc, R(0.001), Num<R>::inf(), io, &slots);  // ray_casting.rs:119
 }
 
 // fixed-point accumulation: order independent => bit-reproducible for any schedule and GPU count
@@ -563,22 +559,22 @@ __global__ void __launch_bounds__(SHADE_BLOCK, 4) k_tail(DevScene<R> sc, const P
         load_path(paths + k, p);
         for (bool first = true;; first = false) {
             const V3<R> o = {p.ox, p.oy, p.oz}, d = {p.dx, p.dy, p.dz};
-            Trav<R> tv;
+            Trav<R, RegStore<R>> tv;
             tv.init(o, d, R(0.001), Num<R>::inf(), sc.bsmall, sc.bmax);  // ray_casting.rs:119
-            int st = sc.n_nodes == 0u ? ST_DONE : ST_NODE;
+            int st = sc.n_nodes == 0u ? (int)ST_DONE : tv.walk_state();
             while (st != ST_DONE) {
                 if (st == ST_NODE) st = tv.step_node(sc, R(0.001));
                 else if (st == ST_EXACT) st = tv.step_exact(sc, o, d, R(0.001));
-                else st = tv.leaf_certain_miss(sc) ? (tv.i >= sc.n_nodes ? (int)ST_DONE : (int)ST_NODE) : tv.step_leaf(sc, o, d, R(0.001));
+                else st = tv.leaf_certain_miss(sc) ? tv.after_leaf(sc) : tv.step_leaf(sc, o, d, R(0.001));
             }
             if (!first) ++traced;
-            if (tv.best_ref == REF_MISS) {  // ray_casting.rs:133-151
+            if (tv.store.best_ref() == REF_MISS) {  // ray_casting.rs:133-151
                 const V3<R> c = col_mul(V3<R>{p.tr, p.tg, p.tb}, sky_color<R>(sc, d), cl);
                 fb_add(fb, p.fb, (double)c.x, (double)c.y, (double)c.z, fb_scale);
                 break;
             }
-            p.ref = tv.best_ref;
-            p.t = tv.best_t;
+            p.ref = tv.store.best_ref();
+            p.t = tv.store.best_t();
             const uint32_t kind = ref_kind(p.ref);
             const PrimMeta pm = (kind == CR_PRIM_SPHERE ? sc.meta[0] : (kind == CR_PRIM_TRIANGLE ? sc.meta[1] : sc.meta[2]))[ref_index(p.ref)];
             const uint32_t minfo = (uint32_t)pm.material | ((pm.mat_kind & MATKIND_NEEDS_UV) ? 0x80000000u : 0u);
@@ -665,8 +661,9 @@ struct BatchTraceIO {
 template <typename R>
 __global__ void __launch_bounds__(TRACE_BLOCK) k_trace_batch(DevScene<R> sc, const double* __restrict__ rays, uint32_t n, double tmin,
                                                               double tmax, CrHit* __restrict__ out, uint32_t* __restrict__ cursor) {
+    __shared__ LaneSlots<R, TRACE_BLOCK> slots;
     BatchTraceIO<R> io{sc, rays, out, cursor, n};
-    trace_persistent<R, CRB_REFILL>(sc, (R)tmin, (R)tmax, io);
+    trace_persistent<R, CRB_REFILL, TRACE_BLOCK>(sc, (R)tmin, (R)tmax, io, &slots);
 }
 
 // ---- host side: typed view of the scene + wavefront driver -----------------------------------------
@@ -882,12 +879,12 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
     typedef void (*TraceFn)(DevScene<R>, PathRec<R>*, Control*, int, uint2*, const FilterRec*, uint32_t);
     int refill = CRB_REFILL;
     if (const char* e = getenv("CRB_REFILL")) refill = atoi(e);
-    int minb = 8;
+    int minb = 10;  // 48 registers, 40 resident warps per SM: the kernel is latency bound, occupancy pays (profiles/)
     if (const char* e = getenv("CRB_MINB")) minb = atoi(e);
 #define CRB_PICK(MB)                                                                                                        \
     (refill <= 4 ? k_trace<R, 4, MB> : refill <= 8 ? k_trace<R, 8, MB> : refill <= 12 ? k_trace<R, 12, MB> : refill <= 16 ? k_trace<R, 16, MB> : refill <= 24 ? k_trace<R, 24, MB> \
                                                                                                   : k_trace<R, 32, MB>)
-    TraceFn trace_fn = minb <= 4 ? CRB_PICK(4) : minb <= 6 ? CRB_PICK(6) : CRB_PICK(8);
+    TraceFn trace_fn = minb <= 4 ? CRB_PICK(4) : minb <= 6 ? CRB_PICK(6) : minb <= 8 ? CRB_PICK(8) : minb <= 10 ? CRB_PICK(10) : CRB_PICK(12);
 #undef CRB_PICK
     const int g_trace = persistent_grid(trace_fn, TRACE_BLOCK, s.num_sms);
     int smb = 6;
