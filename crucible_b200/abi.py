@@ -18,6 +18,7 @@ CR_PRIM_SPHERE, CR_PRIM_TRIANGLE, CR_PRIM_QUAD = 0, 1, 2
 CR_NERP, CR_LERP = 0, 1
 CR_PRECISION_F64, CR_PRECISION_F32 = 0, 1
 CR_MAX_CAM_KEYS = 32
+CR_PPM_P3, CR_PPM_P6 = 0, 1
 
 
 class CrMaterial(C.Structure):
@@ -92,6 +93,10 @@ SIGNATURES = {
     "cr_trace_batch": (C.c_int, [_P, _P, C.c_size_t, C.c_double, C.c_double, C.c_int, _P]),
     "cr_render": (C.c_int, [_P, C.POINTER(CrCamera), C.POINTER(CrRenderOpts), _P, _P, C.POINTER(CrStats)]),
     "cr_render_device": (C.c_int, [_P, C.POINTER(CrCamera), C.POINTER(CrRenderOpts), _P, _P, _P, C.POINTER(CrStats)]),
+    "cr_write_ppm": (C.c_int, [C.c_char_p, _P, C.c_uint32, C.c_uint32, C.c_int]),
+    "cr_render_to_file": (C.c_int, [_P, C.POINTER(CrCamera), C.POINTER(CrRenderOpts), C.c_char_p, C.c_int, C.POINTER(CrStats)]),
+    "cr_render_frames": (C.c_int, [_P, C.POINTER(CrCamera), C.POINTER(CrRenderOpts), C.c_uint32, C.c_uint32, C.c_uint32, C.c_char_p,
+                                   C.c_uint32, C.c_int, _P]),
     "cr_camera_point_at": (C.c_int, [_PD, _P, C.c_size_t, C.c_double, _PD]),
     "cr_measure_fma_peak": (C.c_int, [C.c_int, _PD, _PD]),
     "cr_philox4x32_10": (None, [_P, _P, _P]),

@@ -3,7 +3,10 @@
 // device upload, and the trace / render entry points.
 #include <algorithm>
 #include <cmath>
+#include <condition_variable>
 #include <cstdio>
+#include <deque>
+#include <mutex>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -890,6 +893,220 @@ int cr_render(CrScene* s, const CrCamera* cam, const CrRenderOpts* opts, double*
     }
     cudaEventDestroy(a);
     cudaEventDestroy(b);
+    return CR_OK;
+}
+
+// ---- Camera::render's file tail (camera/mod.rs:275-311) and Scene::render_movie's frame loop ----------
+namespace {
+
+struct DecimalLut {  // "0".."255" followed by the separator the caller appends
+    char txt[256][4];
+    uint8_t len[256];
+    DecimalLut() {
+        for (int v = 0; v < 256; ++v) len[v] = (uint8_t)snprintf(txt[v], 4, "%d", v);
+    }
+};
+
+// "{r} {g} {b}\n" for pixels [p0, p1) appended to out (Display for Color, utils.rs:436)
+void format_p3_rows(const uint8_t* rgb8, size_t p0, size_t p1, std::string& out) {
+    static const DecimalLut lut;
+    out.resize((p1 - p0) * 12);
+    char* w = &out[0];
+    for (size_t p = p0; p < p1; ++p) {
+        const uint8_t* c = rgb8 + 3 * p;
+        for (int k = 0; k < 3; ++k) {
+            const uint8_t v = c[k];
+            memcpy(w, lut.txt[v], 3);
+            w += lut.len[v];
+            *w++ = (k == 2) ? '\n' : ' ';
+        }
+    }
+    out.resize((size_t)(w - &out[0]));
+}
+
+int write_ppm_file(const char* path, const uint8_t* rgb8, uint32_t w, uint32_t h, int format) {
+    if (!path || (!rgb8 && w && h)) return fail(CR_ERR_INVALID, "null argument");
+    if (format != CR_PPM_P3 && format != CR_PPM_P6) return fail(CR_ERR_INVALID, "bad image format");
+    FILE* f = fopen(path, "wb");  // create or truncate, camera/mod.rs:275-280
+    if (!f) return fail(CR_ERR_INVALID, std::string("cannot open ") + path);
+    const size_t npix = (size_t)w * h;
+    bool ok = fprintf(f, "%s\n%u %u\n255\n", format == CR_PPM_P3 ? "P3" : "P6", w, h) > 0;
+    if (format == CR_PPM_P6) {
+        ok = ok && fwrite(rgb8, 1, npix * 3, f) == npix * 3;
+    } else {
+        unsigned nt = std::thread::hardware_concurrency();
+        nt = nt == 0 ? 1 : (nt > 8 ? 8 : nt);
+        if (npix < 65536) nt = 1;
+        std::vector<std::string> chunk(nt);
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nt; ++t) {
+            const size_t p0 = npix * t / nt, p1 = npix * (t + 1) / nt;
+            if (t + 1 == nt) format_p3_rows(rgb8, p0, p1, chunk[t]);
+            else th.emplace_back(format_p3_rows, rgb8, p0, p1, std::ref(chunk[t]));
+        }
+        for (auto& x : th) x.join();
+        for (unsigned t = 0; t < nt && ok; ++t) ok = fwrite(chunk[t].data(), 1, chunk[t].size(), f) == chunk[t].size();
+    }
+    ok = (fclose(f) == 0) && ok;
+    return ok ? CR_OK : fail(CR_ERR_INVALID, std::string("write failed: ") + path);
+}
+
+}  // namespace
+
+extern "C" int cr_write_ppm(const char* path, const uint8_t* rgb8, uint32_t w, uint32_t h, int format) {
+    return write_ppm_file(path, rgb8, w, h, format);
+}
+
+extern "C" int cr_render_to_file(CrScene* s, const CrCamera* cam, const CrRenderOpts* opts, const char* path, int format, CrStats* stats) {
+    if (!path) return fail(CR_ERR_INVALID, "null path");
+    if (format != CR_PPM_P3 && format != CR_PPM_P6) return fail(CR_ERR_INVALID, "bad image format");
+    if (opts && opts->row_world > 1) return fail(CR_ERR_INVALID, "cr_render_to_file renders whole images (row_world <= 1)");
+    int rc = check_camera(cam);
+    if (rc != CR_OK) return rc;
+    std::vector<uint8_t> img((size_t)cam->image_width * cam->image_height * 3);
+    rc = cr_render(s, cam, opts, nullptr, img.data(), stats);
+    if (rc != CR_OK) return rc;
+    return write_ppm_file(path, img.data(), cam->image_width, cam->image_height, format);
+}
+
+extern "C" int cr_render_frames(CrScene* s, const CrCamera* cam, const CrRenderOpts* opts, uint32_t first, uint32_t stride,
+                                uint32_t n_frames, const char* dir, uint32_t digits, int format, CrStats* stats) {
+    int rc = need_device(s);
+    if (rc != CR_OK) return rc;
+    if ((rc = check_camera(cam)) != CR_OK) return rc;
+    if (!opts || !dir) return fail(CR_ERR_INVALID, "null argument");
+    if (stride == 0) return fail(CR_ERR_INVALID, "stride must be positive");
+    if (opts->row_world > 1) return fail(CR_ERR_INVALID, "cr_render_frames shards whole frames (row_world <= 1)");
+    if (format != CR_PPM_P3 && format != CR_PPM_P6) return fail(CR_ERR_INVALID, "bad image format");
+    API_CUDA(cudaSetDevice(s->device));
+    const uint32_t W = cam->image_width, H = cam->image_height;
+    const size_t bytes = (size_t)W * H * 3;
+    constexpr int NBUF = 3;
+    uint8_t* dbuf[NBUF] = {nullptr, nullptr, nullptr};
+    uint8_t* hbuf[NBUF] = {nullptr, nullptr, nullptr};
+    cudaEvent_t copied[NBUF];
+    cudaStream_t copy_stream = nullptr;
+    bool busy[NBUF] = {false, false, false};
+    struct Job {
+        int buf;
+        uint32_t frame;
+    };
+    std::deque<Job> jobs;
+    std::mutex mu;
+    std::condition_variable cv;
+    bool closing = false;
+    int write_rc = CR_OK;
+    std::string write_err;
+
+    auto cleanup = [&]() {
+        for (int b = 0; b < NBUF; ++b) {
+            if (dbuf[b]) cudaFreeAsync(dbuf[b], s->stream);
+            if (hbuf[b]) cudaFreeHost(hbuf[b]);
+            cudaEventDestroy(copied[b]);
+        }
+        if (copy_stream) cudaStreamDestroy(copy_stream);
+    };
+    for (int b = 0; b < NBUF; ++b) copied[b] = nullptr;
+    for (int b = 0; b < NBUF; ++b) {
+        if (cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming) != cudaSuccess ||
+            cudaMallocAsync((void**)&dbuf[b], bytes, s->stream) != cudaSuccess ||
+            cudaHostAlloc((void**)&hbuf[b], bytes, cudaHostAllocDefault) != cudaSuccess) {
+            cudaGetLastError();
+            cleanup();
+            return fail(CR_ERR_CUDA, "cr_render_frames: buffer allocation failed");
+        }
+    }
+    if (cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        cleanup();
+        return fail(CR_ERR_CUDA, "cr_render_frames: cudaStreamCreate failed");
+    }
+
+    // writer: waits for a frame's bytes to land in pinned memory, formats and writes the file while the
+    // GPU traces the next frame
+    const int device = s->device;
+    std::thread writer([&]() {
+        cudaSetDevice(device);
+        for (;;) {
+            Job j;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return closing || !jobs.empty(); });
+                if (jobs.empty()) return;
+                j = jobs.front();
+                jobs.pop_front();
+            }
+            int r = CR_OK;
+            std::string e;
+            if (cudaEventSynchronize(copied[j.buf]) != cudaSuccess) {
+                r = CR_ERR_CUDA;
+                e = "cr_render_frames: device to host copy failed";
+            } else {
+                char name[64];
+                snprintf(name, sizeof(name), "/image%0*u.ppm", (int)digits, j.frame);  // scene/mod.rs:307-308
+                r = write_ppm_file((std::string(dir) + name).c_str(), hbuf[j.buf], W, H, format);
+                if (r != CR_OK) e = g_err;  // thread-local of the writer thread
+            }
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                busy[j.buf] = false;
+                if (r != CR_OK && write_rc == CR_OK) {
+                    write_rc = r;
+                    write_err = e;
+                }
+            }
+            cv.notify_all();
+        }
+    });
+
+    std::string err;
+    uint32_t k = 0;
+    for (uint32_t frame = first; frame < n_frames && rc == CR_OK; frame += stride, ++k) {
+        const int b = (int)(k % NBUF);
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return !busy[b]; });
+            if (write_rc != CR_OK) break;
+            busy[b] = true;
+        }
+        CrCamera c = *cam;
+        c.frame = cam->frame + frame;  // the loop counter names the file, Camera.frame advances from where it stood
+        CrStats st;
+        memset(&st, 0, sizeof(st));
+        rc = (opts->precision == CR_PRECISION_F32)
+                 ? render_impl<float>(s->dev, device_workspace(s->device), c, *opts, nullptr, dbuf[b], 0, s->stream, &st, err)
+                 : render_impl<double>(s->dev, device_workspace(s->device), c, *opts, nullptr, dbuf[b], 0, s->stream, &st, err);
+        if (rc != CR_OK) {
+            std::lock_guard<std::mutex> lk(mu);
+            busy[b] = false;
+            break;
+        }
+        if (stats) stats[k] = st;
+        // render_impl returns after its stream has drained: the copy can start at once on the second stream
+        if (cudaMemcpyAsync(hbuf[b], dbuf[b], bytes, cudaMemcpyDeviceToHost, copy_stream) != cudaSuccess ||
+            cudaEventRecord(copied[b], copy_stream) != cudaSuccess) {
+            rc = CR_ERR_CUDA;
+            err = "cr_render_frames: cudaMemcpyAsync failed";
+            std::lock_guard<std::mutex> lk(mu);
+            busy[b] = false;
+            break;
+        }
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            jobs.push_back({b, frame});
+        }
+        cv.notify_all();
+    }
+    {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return jobs.empty() && !busy[0] && !busy[1] && !busy[2]; });
+        closing = true;
+    }
+    cv.notify_all();
+    writer.join();
+    cudaStreamSynchronize(copy_stream);
+    cleanup();
+    if (rc != CR_OK) return fail(rc, err);
+    if (write_rc != CR_OK) return fail(write_rc, write_err);
     return CR_OK;
 }
 

@@ -7,6 +7,7 @@ device is present the calls raise.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -97,8 +98,16 @@ def rows_of_rank(height, row_block, rank, world):
     return j[(j // row_block) % max(world, 1) == rank] if world > 1 else j
 
 
-def write_ppm(fname, rgb8):
-    """P3 PPM exactly as Camera::render writes it (camera/mod.rs:286, 306-311): header, one "r g b" line per pixel."""
+def write_ppm(fname, rgb8, fmt=abi.CR_PPM_P3):
+    """The file tail of Camera::render (camera/mod.rs:275-311): P3 header, one "r g b" line per pixel
+    (`fmt=abi.CR_PPM_P6`: binary extension).  Formatting is done by the library (cr_write_ppm)."""
+    rgb8 = np.ascontiguousarray(rgb8, np.uint8)
+    h, w, _ = rgb8.shape
+    abi.check(abi.load().cr_write_ppm(os.fsencode(fname), rgb8.ctypes.data_as(C.c_void_p), w, h, int(fmt)))
+
+
+def write_ppm_python(fname, rgb8):
+    """Plain-Python statement of the same file format (tests compare cr_write_ppm against it)."""
     h, w, _ = rgb8.shape
     flat = rgb8.reshape(-1, 3)
     with open(fname, "w") as f:
@@ -107,28 +116,57 @@ def write_ppm(fname, rgb8):
         f.write("\n")
 
 
-def render_scene(scene: Scene, fname: str, device=0, seed=1, precision=abi.CR_PRECISION_F64, gpu_scene=None):
-    """Scene::render_scene (scene/mod.rs:283-347): BVH wrap per frame, Camera::render, `<fname>.ppm`;
-    movies render `ceil(duration * rate)` frames into `<fname>/artifacts/imageNNN.ppm`."""
-    import os
-
+def render_scene(scene: Scene, fname: str, device=0, seed=1, precision=abi.CR_PRECISION_F64, gpu_scene=None,
+                 fmt=abi.CR_PPM_P3, rank=0, world=1, make_movie=True):
+    """Scene::render_scene (scene/mod.rs:283-347).  Still: `Camera::render` into `<fname>.ppm`
+    (cr_render_to_file).  Movie: `ceil(duration * rate)` frames into `<fname>/artifacts/imageNNN.ppm`
+    through the pipelined frame loop (cr_render_frames; frames f % world == rank on this GPU), then the
+    reference's ffmpeg hand-off (movie_maker.rs:6-33) when `ffmpeg` exists.  Returns the per-frame stats."""
     own = gpu_scene is None
     gs = gpu_scene or GpuScene(scene.describe(), device)
     try:
+        cam = scene.scene_cam.to_abi()
+        opts = abi.CrRenderOpts(seed, precision, 0, 8, 0, 1, 0)
         if scene.duration is None:
-            _, rgb8, st = gs.render(scene.scene_cam.to_abi(), seed=seed, precision=precision, want_rgb=False)
-            write_ppm(fname + ".ppm", rgb8)
-            return [st]
-        os.makedirs(os.path.join(fname, "artifacts"))
+            st = abi.CrStats()
+            abi.check(gs.lib.cr_render_to_file(gs.handle, C.byref(cam), C.byref(opts), os.fsencode(fname + ".ppm"), int(fmt), C.byref(st)))
+            return [st.as_dict()]
+        art = os.path.join(fname, "artifacts")
+        if rank == 0:
+            os.makedirs(art)  # fs::create_dir panics when the directory exists (scene/mod.rs:296-298)
         frames = scene.compute_frame_count()
         digits = len(str(frames))
-        stats = []
-        for frame in range(frames):
-            _, rgb8, st = gs.render(scene.scene_cam.to_abi(), seed=seed, precision=precision, want_rgb=False)
-            write_ppm(os.path.join(fname, "artifacts", f"image{frame:0{digits}d}.ppm"), rgb8)
-            scene.scene_cam.next_frame()
-            stats.append(st)
+        stats = render_frames(gs, cam, art, frames, rank, world, seed, precision, fmt)
+        for _ in range(frames):
+            scene.scene_cam.next_frame()  # camera/mod.rs:160-162: the camera ends up past the last frame
+        if make_movie and world == 1:
+            make_mp4(scene.frame_rate, digits, fname)
         return stats
     finally:
         if own:
             gs.close()
+
+
+def render_frames(gs: GpuScene, cam: abi.CrCamera, artifacts_dir: str, frames: int, rank=0, world=1, seed=1,
+                  precision=abi.CR_PRECISION_F64, fmt=abi.CR_PPM_P3, pool_paths=0):
+    """Frames rank, rank+world, ... (< frames) of a movie through the pipelined loop (cr_render_frames)."""
+    opts = abi.CrRenderOpts(seed, precision, pool_paths, 8, 0, 1, 0)
+    n = len(range(rank, frames, max(world, 1)))
+    stats = (abi.CrStats * max(n, 1))()
+    abi.check(gs.lib.cr_render_frames(gs.handle, C.byref(cam), C.byref(opts), rank, max(world, 1), frames, os.fsencode(artifacts_dir),
+                                      len(str(frames)), int(fmt), C.cast(stats, C.c_void_p)))
+    return [stats[i].as_dict() for i in range(n)]
+
+
+def make_mp4(frame_rate, padding, fname):
+    """movie_maker::make_mp4 (scene/movie_maker.rs:6-33): the same ffmpeg command line; skipped (returns
+    False) when no ffmpeg binary is on PATH."""
+    import shutil
+    import subprocess
+
+    if shutil.which("ffmpeg") is None:
+        return False
+    subprocess.run(["ffmpeg", "-framerate", str(frame_rate), "-i", f"{fname}/artifacts/image%0{padding}d.ppm", "-vf",
+                    "scale=trunc(iw/2)*2:trunc(ih/2)*2", "-c:v", "libx264", "-pix_fmt", "yuv420p", "-crf", "25", f"{fname}/movie.mp4"],
+                   check=True)
+    return True

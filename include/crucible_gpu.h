@@ -229,6 +229,32 @@ int cr_render(CrScene*, const CrCamera*, const CrRenderOpts*, double* out_rgb, u
 int cr_render_device(CrScene*, const CrCamera*, const CrRenderOpts*, void* d_out_rgb,
                      void* d_out_rgb8, void* cuda_stream, CrStats* stats);
 
+/* ---- the file-writing tail of the path ---- */
+typedef enum CrImageFormat {
+    CR_PPM_P3 = 0, /* the reference's output: text PPM, camera/mod.rs:286,306-311 */
+    CR_PPM_P6 = 1  /* EXTENSION: binary PPM, same header fields, 3 bytes per pixel */
+} CrImageFormat;
+
+/* Writes [h][w][3] bytes exactly as Camera::render does (camera/mod.rs:275-311): the file is
+ * created or truncated, "P3\n{w} {h}\n255\n", then one "{r} {g} {b}\n" line per pixel, row-major.
+ * Formatting is table driven and split over host threads (the reference formats 2 M `Display`
+ * calls through a BufWriter). */
+int cr_write_ppm(const char* path, const uint8_t* rgb8, uint32_t w, uint32_t h, int format);
+
+/* Camera::render(&skybox, &world, fname) as a whole (camera/mod.rs:270-317): sample loop on the
+ * GPU, bytes to the host, file written.  Honors row sharding only when row_world <= 1. */
+int cr_render_to_file(CrScene*, const CrCamera*, const CrRenderOpts*, const char* path, int format,
+                      CrStats* stats);
+
+/* The frame loop of Scene::render_movie (scene/mod.rs:295-322) for a static world: renders the
+ * frames first, first+stride, ... (< n_frames) with Camera.frame = cam->frame + that index
+ * (Camera::next_frame, camera/mod.rs:160-162) into `<dir>/image{frame:0>digits}.ppm` (scene/mod.rs:307-311).
+ * `stride`/`first` shard whole frames over ranks.  The loop is pipelined: while frame k+1
+ * is traced, frame k is copied to pinned host memory on a second stream, formatted and written by
+ * a writer thread.  stats = array of ceil((n_frames-first)/stride) entries, or NULL. */
+int cr_render_frames(CrScene*, const CrCamera* cam, const CrRenderOpts*, uint32_t first, uint32_t stride,
+                     uint32_t n_frames, const char* dir, uint32_t digits, int format, CrStats* stats);
+
 /* ---- host helpers on the path ---- */
 /* TransformTimeline::combine_and_compute for a camera point (timeline/mod.rs:233-263):
  * out = init + sum of keyframe contributions at time t. */

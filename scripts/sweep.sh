@@ -1,11 +1,5 @@
 #!/bin/bash
-run() {
-  python bench.py --steps 2 --warmup 3 --no-cpu-baseline "$@" 2>&1 | python -c "
-import json,sys
-for l in sys.stdin:
-    if l.startswith('{'):
-        d=json.loads(l); r=d['roofline']; print('  Msamples/s %.1f  ms/step %.2f trace %.2f shade %.2f gen %.2f frac %.3f'%(d['value'],d['ms_per_step'],r['ms_trace'],r['ms_shade'],r['ms_raygen'],r['frac']))
-"
-}
-for r in 4 8 12 16 24; do for ml in 8; do echo "REFILL=$r MIN_LANES=$ml"; CRB_REFILL=$r CRB_MIN_LANES=$ml run; done; done
-echo "REFILL=8 MINB=6"; CRB_REFILL=8 CRB_MINB=6 run
+# Sweeps the trace-engine knobs (environment overrides read by render_impl / make_dev_scene).
+run() { python bench.py --steps 2 --warmup 3 --no-cpu-baseline "$@" 2>&1 | tail -1 | python scripts/benchline.py; }
+for ml in 4 8 12 16 20; do for r in 16 24; do echo "MIN_LANES=$ml REFILL=$r"; CRB_REFILL=$r CRB_MIN_LANES=$ml run; done; done
+for sl in 8 16 64; do echo "SLICE=$sl"; CRB_NODE_SLICE=$sl run; done
