@@ -44,6 +44,47 @@ def test_random_soups_f64_bit_exact(gpu_device, oracle, n_sph, n_tri, n_quad, se
     compare_hits(gs.trace_batch(rays, 2.0, 9.0), orc.trace_batch(rays, 2.0, 9.0))
 
 
+def _transformed(desc, scale, shift):
+    """The same soup scaled about the origin and moved: stresses the f32 filter's error bound (cancellation
+    in b*inv - o*inv grows with |o| / extent) while the f64 decision stays the reference's."""
+    out = SceneDesc()
+    out.materials, out.textures = desc.materials, desc.textures
+    shift = np.asarray(shift, float)
+    for kind, data, mat, oid in desc.batches:
+        d = data.copy() * scale
+        if kind == abi.CR_PRIM_SPHERE:
+            d[:, :3] += shift
+        else:
+            d[:, :3] += shift  # a / Q; the other two triples are vertices (triangles) or edge vectors (quads)
+            if kind == abi.CR_PRIM_TRIANGLE:
+                d[:, 3:6] += shift
+                d[:, 6:9] += shift
+        out.batches.append((kind, d, mat, oid))
+    return out
+
+
+@pytest.mark.parametrize("scale,shift", [(1.0, (1e4, -2e4, 3e4)), (1e-3, (5.0, 5.0, -5.0)), (1e3, (0.0, 0.0, 0.0)),
+                                         (1.0, (1e6, 1e6, 1e6)), (1e-2, (-300.0, 0.25, 1e3))])
+def test_filter_stays_conservative_far_from_the_origin(gpu_device, oracle, scale, shift):
+    base = random_scene(150, 1500, 40, 21)
+    desc = _transformed(base, scale, shift)
+    gs, orc = GpuScene(desc, gpu_device), oracle.OracleScene(desc)
+    lo, hi = scene_bounds(base)
+    rays = random_rays(120000, lo, hi, 77)
+    rays[:, :3] = rays[:, :3] * scale + np.asarray(shift)
+    # directions of very different magnitude: inv = 1/d spans many orders, t scales accordingly
+    rng = np.random.default_rng(9)
+    rays[:, 3:6] *= 10.0 ** rng.integers(-6, 7, size=(len(rays), 1))
+    tmin = 1e-3 * scale
+    got, exp = gs.trace_batch(rays, tmin, float("inf")), orc.trace_batch(rays, tmin, float("inf"))
+    compare_hits(got, exp)
+    assert (exp["prim_index"] >= 0).mean() > 0.02
+    # near-axis-parallel directions: one huge 1/d
+    rays2 = rays[:40000].copy()
+    rays2[:, 3 + np.arange(40000) % 3] *= 1e-12
+    compare_hits(gs.trace_batch(rays2, tmin, float("inf")), orc.trace_batch(rays2, tmin, float("inf")))
+
+
 def test_edge_cases_f64(gpu_device, oracle):
     # empty scene (the world is an empty HitList, bvhwrapper.rs:29-31)
     gs = GpuScene(SceneDesc(), gpu_device)
