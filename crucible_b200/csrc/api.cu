@@ -290,6 +290,9 @@ int upload_scene(CrScene* s) {
     SceneDeviceData& d = s->dev;
     d.num_sms = s->num_sms;
     d.n_nodes = (uint32_t)s->nodes.size();
+    d.n_prims[0] = (uint32_t)(s->spheres.size() / 4);
+    d.n_prims[1] = (uint32_t)(s->tris.size() / 9);
+    d.n_prims[2] = (uint32_t)(s->quads.size() / 9);
     d.sky_kind = s->sky_kind;
     d.sky_image = s->sky_image;
     d.clamp_colors = 1;

@@ -200,6 +200,13 @@ static __global__ void k_plan(Control* ctl, int nxt, uint32_t* host_n_in) {
     if (host_n_in) *host_n_in = n_in;
 }
 
+// rewinds the trace cursor and the material queues so the SAME wavefront can be traced again (variant timing)
+static __global__ void k_trace_rewind(Control* ctl) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    ctl->trace_next = 0;
+    for (int q = 0; q < Q_COUNT; ++q) ctl->queue_count[q] = 0;
+}
+
 template <typename R>
 __device__ __forceinline__ void store_path(PathRec<R>* p, const PathRec<R>& in);
 // the producer of a ray (o, d) also writes its 48 B FilterRec (interval of ray_color: (0.001, inf), ray_casting.rs:119)
@@ -793,6 +800,14 @@ struct EventTimer {
     }
 };
 
+// what the trace-variant choice depends on: the shape of the committed scene, not its coordinates
+static uint64_t scene_signature(const SceneDeviceData& s, int precision) {
+    uint64_t h = 1469598103934665603ull;
+    auto mix = [&](uint64_t v) { h = (h ^ v) * 1099511628211ull; };
+    mix(s.n_nodes); mix(s.n_prims[0]); mix(s.n_prims[1]); mix(s.n_prims[2]); mix((uint64_t)precision); mix((uint64_t)s.sky_kind);
+    return h;
+}
+
 template <typename R>
 int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in, const CrRenderOpts& opts, void* d_out_rgb,
                 void* d_out_rgb8, int packed, cudaStream_t stream, CrStats* stats, std::string& err) {
@@ -875,18 +890,23 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
     CRB_CUDA(cudaMemsetAsync(fb, 0, (size_t)npix * 3 * sizeof(unsigned long long), stream));
 
     const DevScene<R> sc = make_dev_scene<R>(s);
-    // lane-refill threshold of the trace kernel (tuning knob; CRB_REFILL in the environment overrides)
+    // Two register budgets of the same trace kernel: 64 registers / 32 warps per SM and 48 registers / 40 warps per
+    // SM.  The kernel is latency bound, so the extra warps win where the cheap node steps dominate (book1, meshes:
+    // +4 %); where the f64 exact / leaf steps dominate (thin padded boxes of the Cornell quads) the spills of the
+    // small budget lose 20 %.  Unless CRB_MINB pins one, the first large wavefront of a scene is traced with both
+    // (same rays, same result) and the faster one is kept; the choice is cached per device by scene signature.
     typedef void (*TraceFn)(DevScene<R>, PathRec<R>*, Control*, int, uint2*, const FilterRec*, uint32_t);
-    int refill = CRB_REFILL;
-    if (const char* e = getenv("CRB_REFILL")) refill = atoi(e);
-    int minb = 10;  // 48 registers, 40 resident warps per SM: the kernel is latency bound, occupancy pays (profiles/)
-    if (const char* e = getenv("CRB_MINB")) minb = atoi(e);
-#define CRB_PICK(MB)                                                                                                        \
-    (refill <= 4 ? k_trace<R, 4, MB> : refill <= 8 ? k_trace<R, 8, MB> : refill <= 12 ? k_trace<R, 12, MB> : refill <= 16 ? k_trace<R, 16, MB> : refill <= 24 ? k_trace<R, 24, MB> \
-                                                                                                  : k_trace<R, 32, MB>)
-    TraceFn trace_fn = minb <= 4 ? CRB_PICK(4) : minb <= 6 ? CRB_PICK(6) : minb <= 8 ? CRB_PICK(8) : minb <= 10 ? CRB_PICK(10) : CRB_PICK(12);
-#undef CRB_PICK
-    const int g_trace = persistent_grid(trace_fn, TRACE_BLOCK, s.num_sms);
+    TraceFn trace_variants[2] = {k_trace<R, CRB_REFILL, 8>, k_trace<R, CRB_REFILL, 10>};
+    const int trace_grids[2] = {persistent_grid(trace_variants[0], TRACE_BLOCK, s.num_sms),
+                                persistent_grid(trace_variants[1], TRACE_BLOCK, s.num_sms)};
+    const uint64_t signature = scene_signature(s, sizeof(R) == 8 ? 0 : 1);
+    int variant = ws.lookup_variant(signature);
+    if (const char* e = getenv("CRB_MINB")) variant = atoi(e) <= 8 ? 0 : 1;
+    const uint64_t tune_at = total >= 2ull * pool ? 1 : 0;  // the second wavefront mixes bounce rays with camera rays
+    bool tuning = variant < 0 && total >= (1ull << 20);
+    if (variant < 0) variant = 1;
+    TraceFn trace_fn = trace_variants[variant];
+    int g_trace = trace_grids[variant];
     int smb = 6;
     if (const char* e = getenv("CRB_SHADE_MINB")) smb = atoi(e);
     typedef void (*GenFn)(const Control*, const DevCamera*, const RaygenParams<R>, PathRec<R>*, FilterRec*);
@@ -937,9 +957,31 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
     bool done = (total == 0);
     while (!done) {
         const int cur = (int)(it & 1), nxt = cur ^ 1;
-        tm.begin(0, a);
-        trace_fn<<<g_trace, TRACE_BLOCK, 0, stream>>>(sc, paths[cur], ctl, cur, queues, filt[cur], pool);
-        tm.end(0, a);
+        if (tuning && it == tune_at) {
+            cudaEvent_t te[4];
+            for (auto& e : te) CRB_CUDA(cudaEventCreate(&e));
+            for (int v = 0; v < 2; ++v) {
+                CRB_CUDA(cudaEventRecord(te[2 * v], stream));
+                trace_variants[v]<<<trace_grids[v], TRACE_BLOCK, 0, stream>>>(sc, paths[cur], ctl, cur, queues, filt[cur], pool);
+                CRB_CUDA(cudaEventRecord(te[2 * v + 1], stream));
+                if (v == 0) k_trace_rewind<<<1, 32, 0, stream>>>(ctl);
+            }
+            launches += 2;
+            CRB_CUDA(cudaEventSynchronize(te[3]));
+            float ms[2] = {0.f, 0.f};
+            cudaEventElapsedTime(&ms[0], te[0], te[1]);
+            cudaEventElapsedTime(&ms[1], te[2], te[3]);
+            for (auto& e : te) cudaEventDestroy(e);
+            variant = ms[1] <= ms[0] ? 1 : 0;
+            ws.store_variant(signature, variant);
+            trace_fn = trace_variants[variant];
+            g_trace = trace_grids[variant];
+            tuning = false;
+        } else {
+            tm.begin(0, a);
+            trace_fn<<<g_trace, TRACE_BLOCK, 0, stream>>>(sc, paths[cur], ctl, cur, queues, filt[cur], pool);
+            tm.end(0, a);
+        }
         tm.begin(1, a);
         k_shade_miss<R><<<g_miss, SHADE_BLOCK, 0, stream>>>(sc, paths[cur], ctl, queues + (size_t)Q_MISS * pool, fb, fb_scale);
         lam_fn<<<g_lam, SHADE_BLOCK, 0, stream>>>(sc, paths[cur], paths[nxt], ctl, nxt, queues + (size_t)Q_LAMBERTIAN * pool, filt[nxt],

@@ -20,6 +20,7 @@ struct SceneDeviceData {
     DevTexture* texs = nullptr;
     DevImage* images = nullptr;
     uint32_t n_nodes = 0;
+    uint32_t n_prims[3] = {0, 0, 0};  // spheres, triangles, quads
     int32_t sky_kind = CR_SKY_DEFAULT, sky_image = -1;
     int32_t clamp_colors = 1;
     float bmax = 0.f;            // largest |coordinate| of the root box (f32, rounded up)
@@ -34,6 +35,22 @@ struct Workspace {
     void* ptr = nullptr;
     size_t bytes = 0;
     void* pinned = nullptr;  // 4 KiB of pinned host memory for control-block staging
+    // trace-kernel variant chosen by timing, per scene signature (render_impl)
+    uint64_t tuned_sig[16] = {0};
+    int tuned_variant[16] = {0};
+    int tuned_n = 0;
+    int lookup_variant(uint64_t sig) const {
+        for (int i = 0; i < tuned_n && i < 16; ++i)
+            if (tuned_sig[i] == sig) return tuned_variant[i];
+        return -1;
+    }
+    void store_variant(uint64_t sig, int v) {
+        const int i = tuned_n % 16;  // small ring: a process renders a handful of distinct scenes
+        tuned_sig[i] = sig;
+        tuned_variant[i] = v;
+        ++tuned_n;
+        if (tuned_n >= 32) tuned_n = 16;
+    }
     int ensure(size_t need, std::string& err) {
         if (need <= bytes) return CR_OK;
         if (ptr) cudaFree(ptr);
