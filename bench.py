@@ -91,6 +91,21 @@ def oracle_sample(desc, cam, row_step, threads=0):
     return st
 
 
+def hbm_view(alg_bytes_per_launch, dur_s, traffic):
+    peak, src = 6533.5, "fallback"
+    try:
+        mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        for k in ("hbm_gbs", "hbm_gbps", "hbm_copy_gbps"):
+            if k in mp:
+                peak, src = float(mp[k]), f"MEASURED_PEAKS.json:{k}"
+                break
+    except Exception:
+        pass
+    ach = alg_bytes_per_launch / dur_s / 1e9
+    return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": src,
+            "dram_gbps_measured": (traffic / dur_s / 1e9) if traffic else None}
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path, timed on the host cores.
     The reference is a Rust crate and no rustc/cargo exists here, so the timed code is the oracle port
@@ -273,7 +288,7 @@ def main():
         achieved = per_seg_flops * seg_per_launch / dur_s / 1e12
         peak = f64p.value if args.precision == "f64" else f32p.value
         traffic, traffic_src = None, None
-        tpath = os.path.join(ROOT, "profiles", "trace_r01_traffic.json")
+        tpath = os.path.join(ROOT, "profiles", "trace_r01c_traffic.json")
         if args.precision == "f64" and os.path.exists(tpath):
             tj = json.load(open(tpath))  # DRAM bytes of one ncu --set full capture, scaled to this run's segments per launch
             traffic = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) / tj["rays_in_launch"] * seg_per_launch
@@ -285,7 +300,11 @@ def main():
                             "flops_per_segment": per_seg_flops, "bytes_per_segment": per_seg_bytes, "segments_per_launch": seg_per_launch,
                             "avg_launch_ms": dur_s * 1e3, "kernel_share_of_step": ms_trace / (ms_total if world == 1 else sum(s["ms_total"] for s in stats)),
                             "ms_trace": ms_trace / args.steps, "ms_shade": ms_shade / args.steps, "ms_raygen": ms_gen / args.steps,
-                            "fp64_fma_peak_tflops": f64p.value, "fp32_fma_peak_tflops": f32p.value}
+                            "fp64_fma_peak_tflops": f64p.value, "fp32_fma_peak_tflops": f32p.value,
+                            # the same launches seen as a memory kernel: SURVEY 8d's algorithmic bytes against the measured HBM
+                            # copy peak.  The scene (16 KB of nodes) is cache resident, so this view only shows that HBM is NOT
+                            # the bound of this config (the DRAM traffic of the launch is `traffic`); it IS the bound of configs[3].
+                            "hbm_view": hbm_view(per_seg_bytes * seg_per_launch, dur_s, traffic)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
