@@ -765,4 +765,49 @@ __device__ __forceinline__ void trace_persistent(const DevScene<R>& sc, R tmin, 
     }
 }
 
+// Closest hit for ONE ray per lane, all 32 lanes of the warp together (no refill, no queues): the same NODE
+// slices and EXACT + LEAF phases as trace_persistent, so the rare expensive steps still run with several lanes
+// at once.  Used by the tail kernel, where a warp owns 32 paths from their current segment to their end.
+// Lanes with active == false only take part in the votes.  Returns the closest hit in (ref, t).
+template <typename R, int BLOCK>
+__device__ __forceinline__ void trace_warp_batch(const DevScene<R>& sc, R tmin, R tmax, bool active, V3<R> o, V3<R> d,
+                                                 LaneSlots<R, BLOCK>* slots, uint32_t& ref, R& t) {
+    Trav<R, SmemStore<R, BLOCK>> tv;
+    tv.store.s = slots;
+    tv.ok = false;
+    tv.i = 0;
+    tv.wa = tv.wb = REF_NONE;
+    tv.best32 = (float)tmax;
+    int st = ST_DONE;
+    if (active) {
+        const V3<R> inv = {R(1) / d.x, R(1) / d.y, R(1) / d.z};  // adinv, bvh.rs:111
+        tv.init_from(make_filter_ray<R>(o, d, inv, tmin, tmax, sc.bsmall, sc.bmax), tmax);
+        tv.store.set_ray(o, d);
+        st = (sc.n_nodes == 0u) ? (int)ST_DONE : tv.walk_state();
+    }
+    while (__any_sync(0xffffffffu, st != ST_DONE)) {
+#pragma unroll 1
+        for (int k = 0; k < sc.node_slice; k += 4) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (st == ST_NODE) st = tv.step_node(sc, tmin);
+            }
+            if (__popc(__ballot_sync(0xffffffffu, st == ST_NODE)) < sc.min_node_lanes) break;
+        }
+        if (st == ST_LEAF && tv.leaf_certain_miss(sc)) st = tv.after_leaf(sc);
+        if (st == ST_EXACT || st == ST_LEAF) {
+            V3<R> ro, rd;
+            tv.store.get_ray(ro, rd);
+            if (st == ST_EXACT) st = tv.step_exact(sc, ro, rd, tmin);
+            if (st == ST_LEAF) st = tv.step_leaf(sc, ro, rd, tmin);
+        }
+    }
+    ref = REF_MISS;
+    t = tmax;
+    if (active) {
+        ref = tv.store.best_ref();
+        t = tv.store.best_t();
+    }
+}
+
 }  // namespace crb

@@ -552,41 +552,43 @@ __global__ void __launch_bounds__(SHADE_BLOCK, MINB) k_shade_scatter(DevScene<R>
 }
 
 // tail: when only a few thousand paths are left (and no camera samples), another ~25-45 wavefront iterations
-// of 8 launches each would be pure launch overhead.  One launch finishes them: each thread follows ITS path
-// to the end (trace, shade, trace, ...) with the same device routines, so every path is unchanged.
+// of 8 launches each would be pure launch overhead.  One launch finishes them: a WARP owns 32 paths and follows
+// them to their end, alternating a warp-cooperative closest-hit (trace_warp_batch: the engine's phases) with the
+// scatter of every lane's own material, using the same device routines, so every path is unchanged.
+// (The first version gave each THREAD one path and its own traversal state machine: lanes in different states
+// serialised each other, 1.6 ms per frame at 11 % warps active, profiles/misc_r01c.md.)
 template <typename R>
-__global__ void __launch_bounds__(SHADE_BLOCK, 4) k_tail(DevScene<R> sc, const PathRec<R>* __restrict__ paths, Control* __restrict__ ctl,
+__global__ void __launch_bounds__(TRACE_BLOCK, 4) k_tail(DevScene<R> sc, const PathRec<R>* __restrict__ paths, Control* __restrict__ ctl,
                                                          int side, uint64_t seed, uint32_t max_depth,
                                                          unsigned long long* __restrict__ fb, double fb_scale) {
+    __shared__ LaneSlots<R, TRACE_BLOCK> slots;
     const uint32_t n = ctl->n_in[side];
     const bool cl = sc.clamp_colors != 0;
     unsigned long long traced = 0;  // segments beyond each path's first (k_plan already counted that one)
-    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const uint32_t n_round = (n + 31u) & ~31u;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n_round; k += gridDim.x * blockDim.x) {
         PathRec<R> p;
-        load_path(paths + k, p);
-        for (bool first = true;; first = false) {
+        bool alive = k < n;
+        if (alive) load_path(paths + k, p);
+        for (bool first = true; __any_sync(0xffffffffu, alive); first = false) {
             const V3<R> o = {p.ox, p.oy, p.oz}, d = {p.dx, p.dy, p.dz};
-            Trav<R, RegStore<R>> tv;
-            tv.init(o, d, R(0.001), Num<R>::inf(), sc.bsmall, sc.bmax);  // ray_casting.rs:119
-            int st = sc.n_nodes == 0u ? (int)ST_DONE : tv.walk_state();
-            while (st != ST_DONE) {
-                if (st == ST_NODE) st = tv.step_node(sc, R(0.001));
-                else if (st == ST_EXACT) st = tv.step_exact(sc, o, d, R(0.001));
-                else st = tv.leaf_certain_miss(sc) ? tv.after_leaf(sc) : tv.step_leaf(sc, o, d, R(0.001));
-            }
+            uint32_t ref;
+            R t;
+            trace_warp_batch<R, TRACE_BLOCK>(sc, R(0.001), Num<R>::inf(), alive, o, d, &slots, ref, t);  // ray_casting.rs:119
+            if (!alive) continue;
             if (!first) ++traced;
-            if (tv.store.best_ref() == REF_MISS) {  // ray_casting.rs:133-151
+            if (ref == REF_MISS) {  // ray_casting.rs:133-151
                 const V3<R> c = col_mul(V3<R>{p.tr, p.tg, p.tb}, sky_color<R>(sc, d), cl);
                 fb_add(fb, p.fb, (double)c.x, (double)c.y, (double)c.z, fb_scale);
-                break;
+                alive = false;
+                continue;
             }
-            p.ref = tv.store.best_ref();
-            p.t = tv.store.best_t();
+            p.ref = ref;
+            p.t = t;
             const uint32_t kind = ref_kind(p.ref);
             const PrimMeta pm = (kind == CR_PRIM_SPHERE ? sc.meta[0] : (kind == CR_PRIM_TRIANGLE ? sc.meta[1] : sc.meta[2]))[ref_index(p.ref)];
             const uint32_t minfo = (uint32_t)pm.material | ((pm.mat_kind & MATKIND_NEEDS_UV) ? 0x80000000u : 0u);
             const int mk = pm.mat_kind & MATKIND_MASK;
-            bool alive;
             if (mk == CR_MAT_LAMBERTIAN) alive = scatter_path<R, CR_MAT_LAMBERTIAN>(sc, p, minfo, seed, max_depth);
             else if (mk == CR_MAT_METAL) alive = scatter_path<R, CR_MAT_METAL>(sc, p, minfo, seed, max_depth);
             else if (mk == CR_MAT_DIELECTRIC) alive = scatter_path<R, CR_MAT_DIELECTRIC>(sc, p, minfo, seed, max_depth);
@@ -595,7 +597,6 @@ __global__ void __launch_bounds__(SHADE_BLOCK, 4) k_tail(DevScene<R> sc, const P
                 fb_add(fb, p.fb, (double)(p.tr * (R)mat.emit[0]), (double)(p.tg * (R)mat.emit[1]), (double)(p.tb * (R)mat.emit[2]), fb_scale);
                 alive = false;
             }
-            if (!alive) break;
         }
     }
     // ray segments traced here (CrStats.rays counts world.hit calls)
@@ -924,7 +925,7 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
     rp.bmax = s.bmax;
     host_camera_constants<R>(cam_in, rp);
     const int g_gen = persistent_grid(gen_fn, SHADE_BLOCK, s.num_sms);
-    const int g_tail = persistent_grid(k_tail<R>, SHADE_BLOCK, s.num_sms);
+    const int g_tail = persistent_grid(k_tail<R>, TRACE_BLOCK, s.num_sms);
     uint32_t tail_n = 65536;
     if (const char* e = getenv("CRB_TAIL")) tail_n = (uint32_t)atoi(e);
     const int g_miss = persistent_grid(k_shade_miss<R>, SHADE_BLOCK, s.num_sms);
@@ -1017,7 +1018,7 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
                 // one k_tail launch follows each of them to its end instead of ~25-45 more 8-launch iterations
                 const int side = (int)(it & 1);
                 tm.begin(0, a);
-                k_tail<R><<<g_tail, SHADE_BLOCK, 0, stream>>>(sc, paths[side], ctl, side, opts.seed, cam_in.max_depth, fb, fb_scale);
+                k_tail<R><<<g_tail, TRACE_BLOCK, 0, stream>>>(sc, paths[side], ctl, side, opts.seed, cam_in.max_depth, fb, fb_scale);
                 tm.end(0, a);
                 ++launches;
                 done = true;
