@@ -19,16 +19,20 @@ def frames_of_rank(n_frames: int, rank: int, world: int):
     return list(range(rank, n_frames, max(world, 1)))
 
 
-_ROW_INDEX_CACHE = {}
+_GATHER_MAP_CACHE = {}
 
 
-def _row_index(height, row_block, r, world, device):
-    """Row indices of rank r as a device tensor (cached: building them costs a synchronous H2D copy)."""
-    key = (height, row_block, r, world, str(device))
-    t = _ROW_INDEX_CACHE.get(key)
+def _gather_map(height, row_block, world, max_rows, device):
+    """For every global row j: its position in the stacked gather buffer [world][max_rows] (rank r's packed rows
+    are the rows with (j // row_block) % world == r in ascending order).  Cached device tensor."""
+    key = (height, row_block, world, max_rows, str(device))
+    t = _GATHER_MAP_CACHE.get(key)
     if t is None:
-        t = torch.as_tensor(rows_of_rank(height, row_block, r, world), device=device, dtype=torch.long)
-        _ROW_INDEX_CACHE[key] = t
+        j = np.arange(height)
+        r = (j // row_block) % world
+        pos = (j // (row_block * world)) * row_block + j % row_block
+        t = torch.as_tensor(r * max_rows + pos, device=device, dtype=torch.long)
+        _GATHER_MAP_CACHE[key] = t
     return t
 
 
@@ -36,7 +40,8 @@ def gather_rows(local: torch.Tensor, height: int, row_block: int, rank: int, wor
     """Assemble the full [H][W][C] image on `dst` from each rank's packed rows.
 
     `local` is [rows_local][W][C] holding rows (j // row_block) % world == rank in ascending order.
-    Returns the full tensor on dst, None elsewhere.  world == 1 returns `local` unchanged."""
+    Returns the full tensor on dst, None elsewhere.  world == 1 returns `local` unchanged.
+    One collective (gather into the slices of one stacked buffer) and ONE row-permutation kernel on dst."""
     if world <= 1:
         return local
     counts = [len(rows_of_rank(height, row_block, r, world)) for r in range(world)]
@@ -48,12 +53,10 @@ def gather_rows(local: torch.Tensor, height: int, row_block: int, rank: int, wor
         send[: local.shape[0]] = local
     send = send.contiguous()
     if rank == dst:
-        bufs = [torch.empty_like(send) for _ in range(world)]
-        dist.gather(send, gather_list=bufs, dst=dst, group=group)
-        full = torch.empty((height,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-        for r in range(world):
-            full.index_copy_(0, _row_index(height, row_block, r, world, local.device), bufs[r][: counts[r]])
-        return full
+        stacked = torch.empty((world, max_rows) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        dist.gather(send, gather_list=list(stacked.unbind(0)), dst=dst, group=group)
+        return stacked.view((world * max_rows,) + tuple(local.shape[1:])).index_select(
+            0, _gather_map(height, row_block, world, max_rows, local.device))
     dist.gather(send, gather_list=None, dst=dst, group=group)
     return None
 

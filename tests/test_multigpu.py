@@ -65,6 +65,21 @@ def test_gather_rows_gloo_world2():
     assert res[0][2] == [0, 2, 4, 6, 8] and res[1][2] == [1, 3, 5, 7, 9]
 
 
+@pytest.mark.parametrize("H,block,world", [(36, 8, 2), (1080, 8, 8), (37, 8, 3), (5, 8, 4), (64, 1, 3), (2160, 16, 5)])
+def test_gather_map_matches_row_sharding(H, block, world):
+    """The one-kernel assembly: position of every global row in the stacked [world][max_rows] gather buffer."""
+    from crucible_b200 import multigpu
+    from crucible_b200.gpu import rows_of_rank
+
+    counts = [len(rows_of_rank(H, block, r, world)) for r in range(world)]
+    max_rows = max(counts)
+    stacked = np.full((world, max_rows), -1, np.int64)
+    for r in range(world):
+        stacked[r, : counts[r]] = rows_of_rank(H, block, r, world)  # what rank r sends, padded
+    m = multigpu._gather_map(H, block, world, max_rows, "cpu").numpy()
+    assert np.array_equal(stacked.reshape(-1)[m], np.arange(H))
+
+
 def test_gather_rows_world1_is_identity():
     from crucible_b200 import multigpu
 
