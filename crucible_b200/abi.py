@@ -35,6 +35,10 @@ class CrKeyframe(C.Structure):
     _fields_ = [("t0", C.c_double), ("t1", C.c_double), ("delta", C.c_double), ("axis", C.c_int32), ("interp", C.c_int32)]
 
 
+class CrAnimKey(C.Structure):
+    _fields_ = [("t0", C.c_double), ("t1", C.c_double), ("a", C.c_double), ("b", C.c_double), ("kind", C.c_int32), ("interp", C.c_int32)]
+
+
 class CrCamera(C.Structure):
     _fields_ = [("image_width", C.c_uint32), ("image_height", C.c_uint32),
                 ("viewport_width", C.c_double), ("viewport_height", C.c_double),
@@ -87,6 +91,7 @@ SIGNATURES = {
     "cr_scene_set_textures": (C.c_int, [_P, _P, C.c_size_t]),
     "cr_scene_add_image": (C.c_int, [_P, _P, C.c_int, C.c_int]),
     "cr_scene_set_sky": (C.c_int, [_P, C.c_int, C.c_int]),
+    "cr_scene_set_keyframes": (C.c_int, [_P, C.c_size_t, C.c_int, _P, C.c_size_t]),
     "cr_scene_commit": (C.c_int, [_P]),
     "cr_scene_bvh_info": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]),
     "cr_scene_bvh_leaf_order": (C.c_int64, [_P, _P, C.c_size_t]),

@@ -9,6 +9,7 @@
 #include <mutex>
 #include <cstring>
 #include <limits>
+#include <map>
 #include <string>
 #include <thread>
 #include <vector>
@@ -106,6 +107,7 @@ struct CrScene {
     std::vector<CrTexture> texs;
     std::vector<HostImage> images;
     int sky_kind = CR_SKY_DEFAULT, sky_image = -1;
+    std::map<uint64_t, std::vector<CrAnimKey>> anim;  // (prim_index * 4 + point) -> keyframes in timeline order
     // built
     bool committed = false;
     std::vector<FlatNode> nodes;
@@ -498,6 +500,46 @@ int upload_scene(CrScene* s) {
         if (rc != CR_OK) return rc;
         d.images = static_cast<DevImage*>(p);
     }
+    // object keyframes: one concatenated key table + a track (range) per sphere and per triangle vertex
+    if (!s->anim.empty()) {
+        std::vector<CrAnimKey> keys;
+        std::vector<AnimTrack> st(s->spheres.size() / 4, AnimTrack{0u, 0u}), tt(s->tris.size() / 9 * 3, AnimTrack{0u, 0u});
+        std::vector<uint32_t> slot(s->tris.size() / 9, 0u);
+        std::vector<double> verts;
+        std::vector<char> tri_seen(s->tris.size() / 9, 0);
+        for (auto& kv : s->anim) {
+            if (kv.second.empty()) continue;
+            const size_t prim = (size_t)(kv.first >> 2);
+            const int point = (int)(kv.first & 3u);
+            const Element& e = s->elements[prim];
+            const AnimTrack tr{(uint32_t)keys.size(), (uint32_t)kv.second.size()};
+            keys.insert(keys.end(), kv.second.begin(), kv.second.end());
+            if (e.kind == CR_PRIM_SPHERE) {
+                st[e.idx] = tr;
+            } else {
+                tt[3 * (size_t)e.idx + (size_t)point] = tr;
+                if (!tri_seen[e.idx]) {
+                    tri_seen[e.idx] = 1;
+                    slot[e.idx] = (uint32_t)(verts.size() / 9);
+                    verts.insert(verts.end(), &s->tris[9 * (size_t)e.idx], &s->tris[9 * (size_t)e.idx] + 9);
+                }
+            }
+        }
+        if (!keys.empty()) {
+            void* p = nullptr;
+            int rc;
+            if ((rc = upload(s, keys, &p)) != CR_OK) return rc;
+            d.anim_keys = static_cast<CrAnimKey*>(p);
+            if ((rc = upload(s, st, &p)) != CR_OK) return rc;
+            d.sphere_track = static_cast<AnimTrack*>(p);
+            if ((rc = upload(s, tt, &p)) != CR_OK) return rc;
+            d.tri_track = static_cast<AnimTrack*>(p);
+            if ((rc = upload(s, slot, &p)) != CR_OK) return rc;
+            d.tri_anim_slot = static_cast<uint32_t*>(p);
+            if ((rc = upload(s, verts, &p)) != CR_OK) return rc;
+            d.tri_anim_verts = static_cast<double*>(p);
+        }
+    }
     // the render may run on a caller-supplied stream: the scene is complete when commit returns
     API_CUDA(cudaStreamSynchronize(s->stream));
     return CR_OK;
@@ -708,6 +750,24 @@ int cr_scene_set_sky(CrScene* s, int kind, int image) {
     if (!s || kind < CR_SKY_DEFAULT || kind > CR_SKY_BLACK) return fail(CR_ERR_INVALID, "bad sky kind");
     s->sky_kind = kind;
     s->sky_image = image;
+    s->committed = false;
+    return CR_OK;
+}
+
+int cr_scene_set_keyframes(CrScene* s, size_t prim_index, int point, const CrAnimKey* keys, size_t n) {
+    if (!s || (!keys && n)) return fail(CR_ERR_INVALID, "null argument");
+    if (prim_index >= s->elements.size()) return fail(CR_ERR_INVALID, "prim_index out of range");
+    const uint32_t kind = s->elements[prim_index].kind;
+    if (kind == CR_PRIM_QUAD) return fail(CR_ERR_INVALID, "quads (extension) cannot be animated");
+    if (point < 0 || point > (kind == CR_PRIM_SPHERE ? 0 : 2)) return fail(CR_ERR_INVALID, "point out of range for this primitive");
+    for (size_t i = 0; i < n; ++i) {
+        if (keys[i].kind < 0 || keys[i].kind > 3) return fail(CR_ERR_INVALID, "keyframe kind out of range");
+        // ScaleR can only be applied to Spheres (scene_animator.rs:140-150)
+        if (keys[i].kind == 3 && kind != CR_PRIM_SPHERE) return fail(CR_ERR_INVALID, "ScaleR can only be applied to Spheres");
+        if (keys[i].interp != CR_NERP && keys[i].interp != CR_LERP) return fail(CR_ERR_INVALID, "bad interpolation type");
+    }
+    std::vector<CrAnimKey>& dst = s->anim[((uint64_t)prim_index << 2) | (uint64_t)point];
+    dst.assign(keys, keys + n);
     s->committed = false;
     return CR_OK;
 }

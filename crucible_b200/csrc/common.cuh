@@ -96,6 +96,11 @@ struct DevImage {
     int32_t w, h;
 };
 
+// ---- object animation: evaluated keyframes (CrAnimKey) + one track (key range) per animated point --------
+struct AnimTrack {
+    uint32_t first, count;  // keys [first, first + count) of DevScene::anim_keys; count == 0 = static point
+};
+
 template <typename R>
 struct DevScene {
     const NodeRec<R>* nodes;
@@ -110,6 +115,11 @@ struct DevScene {
     const DevMaterial* mats;
     const DevTexture* texs;
     const DevImage* images;
+    const CrAnimKey* anim_keys;      // nullptr when nothing in the scene is animated
+    const AnimTrack* sphere_track;   // [n_spheres]
+    const AnimTrack* tri_track;      // [n_tris][3]: vertex timelines a, b, c
+    const uint32_t* tri_anim_slot;   // [n_tris]: row of tri_anim_verts for an animated triangle
+    const double* tri_anim_verts;    // [n_animated_tris][9]: construction vertices a, b, c
     uint32_t n_nodes;  // 0 when the world is the empty HitList (bvhwrapper.rs:29-31)
     int32_t sky_kind, sky_image;
     int32_t clamp_colors;  // 1 = reference Color semantics; 0 when the scene holds an Emissive (extension)

@@ -260,6 +260,73 @@ __device__ __forceinline__ bool quad_hit_t(const QuadRec<R>& q, V3<R> o, V3<R> d
     return true;
 }
 
+// ---- TransformTimeline::combine_and_compute for an object point (timeline/mod.rs:233-263) ---------------
+// p = construction position, radius = construction radius; every valid translate key adds its offset to its
+// axis in list order (`translate * translate_matrix`: 1*m + 0 + 0 + v*1 = m + v exactly), the last valid
+// radius key replaces the radius (`.filter(valid).next_back()`).  s = clamp(proportion(t), 0, 1) keeps NaN for a
+// zero-length interval exactly like f64::clamp.
+template <typename R>
+__host__ __device__ __forceinline__ void anim_eval(const CrAnimKey* keys, uint32_t first, uint32_t count, R t, R p[3], R& radius) {
+    for (uint32_t k = first; k < first + count; ++k) {
+        const R t0 = (R)keys[k].t0, t1 = (R)keys[k].t1;
+        if (!((t > t1) || (t0 <= t && t <= t1))) continue;
+        R s = (t - t0) / (t1 - t0);
+        s = s < R(0) ? R(0) : (s > R(1) ? R(1) : s);
+        const R a = (R)keys[k].a, b = (R)keys[k].b;
+        const int kind = keys[k].kind;
+        if (kind < 3) {
+            const R off = (keys[k].interp == CR_LERP) ? a * s : a;
+            p[kind] = off + p[kind];
+        } else {
+            radius = (keys[k].interp == CR_LERP) ? a + (b - a) * s : b;
+        }
+    }
+}
+// Sphere / triangle records at ray time tm: the stored record for static primitives (and static scenes),
+// the timelines evaluated at tm otherwise (Sphere::hit sphere.rs:67-70, Triangle::hit triangle.rs:91-100).
+// ANIM = false is the build static scenes run: no track lookups, no extra registers in the hot kernels.
+template <typename R, bool ANIM>
+__device__ __forceinline__ SphereRec<R> sphere_at(const DevScene<R>& sc, uint32_t idx, R tm) {
+    SphereRec<R> s = ldg_rec<sizeof(SphereRec<R>) / 16>(sc.spheres + idx);
+    if constexpr (!ANIM) return s;
+    if (sc.sphere_track != nullptr) {
+        const AnimTrack tr = sc.sphere_track[idx];
+        if (tr.count) {
+            R p[3] = {s.cx, s.cy, s.cz};
+            anim_eval<R>(sc.anim_keys, tr.first, tr.count, tm, p, s.r);
+            s.cx = p[0]; s.cy = p[1]; s.cz = p[2];
+        }
+    }
+    return s;
+}
+template <typename R, bool ANIM>
+__device__ __forceinline__ TriRec<R> tri_at(const DevScene<R>& sc, uint32_t idx, R tm) {
+    TriRec<R> t = ldg_rec<sizeof(TriRec<R>) / 16>(sc.tris + idx);
+    if constexpr (!ANIM) return t;
+    if (sc.tri_track != nullptr) {
+        const AnimTrack ta = sc.tri_track[3 * idx], tb = sc.tri_track[3 * idx + 1], tc = sc.tri_track[3 * idx + 2];
+        if (ta.count | tb.count | tc.count) {
+            // the record holds a, e1 = b - a, e2 = c - a of the construction vertices; b and c themselves are in the
+            // animated-vertex table (exact copies: b cannot be recovered from a + e1 bit for bit)
+            const double* v = sc.tri_anim_verts + 9ull * sc.tri_anim_slot[idx];
+            R a[3] = {(R)v[0], (R)v[1], (R)v[2]}, b[3] = {(R)v[3], (R)v[4], (R)v[5]}, c[3] = {(R)v[6], (R)v[7], (R)v[8]};
+            R unused = R(1);
+            anim_eval<R>(sc.anim_keys, ta.first, ta.count, tm, a, unused);
+            anim_eval<R>(sc.anim_keys, tb.first, tb.count, tm, b, unused);
+            anim_eval<R>(sc.anim_keys, tc.first, tc.count, tm, c, unused);
+            t.ax = a[0]; t.ay = a[1]; t.az = a[2];
+            t.e1x = b[0] + (-a[0]); t.e1y = b[1] + (-a[1]); t.e1z = b[2] + (-a[2]);  // triangle.rs:99-100
+            t.e2x = c[0] + (-a[0]); t.e2y = c[1] + (-a[1]); t.e2z = c[2] + (-a[2]);
+        }
+    }
+    return t;
+}
+template <typename R, bool ANIM>
+__device__ __forceinline__ bool sphere_is_animated(const DevScene<R>& sc, uint32_t idx) {
+    if constexpr (!ANIM) return false;
+    return sc.sphere_track != nullptr && sc.sphere_track[idx].count != 0u;
+}
+
 // ---- HitRecord (src/objects/mod.rs:21-87) rebuilt from (ref, t) -----------------------------------
 template <typename R> struct HitInfo {
     V3<R> p, n;
@@ -270,15 +337,15 @@ template <typename R> struct HitInfo {
 // HitRecord geometry rebuilt from (ref, t).  want_uv = false skips get_sphere_uv (acos + atan2): the
 // texture coordinates only reach image textures (solid_color.rs:25-27 and checker_texture.rs:39-51
 // ignore u, v), so skipping them cannot change a result.
-template <typename R>
-__device__ __forceinline__ HitInfo<R> finalize_geom(const DevScene<R>& sc, uint32_t ref, R t, V3<R> o, V3<R> d, bool want_uv) {
+template <typename R, bool ANIM>
+__device__ __forceinline__ HitInfo<R> finalize_geom(const DevScene<R>& sc, uint32_t ref, R t, V3<R> o, V3<R> d, bool want_uv, R tm) {
     HitInfo<R> h;
     const uint32_t kind = ref_kind(ref), idx = ref_index(ref);
     h.material = h.mat_kind = h.prim_index = h.obj_id = -1;
     h.p = vadd(o, vmul(t, d));  // Ray::at, ray_casting.rs:53-59
     V3<R> n;
     if (kind == CR_PRIM_SPHERE) {
-        SphereRec<R> s = ldg_rec<sizeof(SphereRec<R>) / 16>(sc.spheres + idx);
+        SphereRec<R> s = sphere_at<R, ANIM>(sc, idx, tm);
         n = vdiv(vsub(h.p, V3<R>{s.cx, s.cy, s.cz}), s.r);  // sphere.rs:96
         h.u = h.v = R(0);
         if (want_uv) {
@@ -288,7 +355,7 @@ __device__ __forceinline__ HitInfo<R> finalize_geom(const DevScene<R>& sc, uint3
             h.v = theta / Num<R>::pi();
         }
     } else if (kind == CR_PRIM_TRIANGLE) {
-        TriRec<R> tr = ldg_rec<sizeof(TriRec<R>) / 16>(sc.tris + idx);
+        TriRec<R> tr = tri_at<R, ANIM>(sc, idx, tm);
         n = vunit(vcross(V3<R>{tr.e1x, tr.e1y, tr.e1z}, V3<R>{tr.e2x, tr.e2y, tr.e2z}));  // triangle.rs:124 + safe_new
         h.u = R(0);  // triangle.rs:133-134
         h.v = R(0);
@@ -305,9 +372,9 @@ __device__ __forceinline__ HitInfo<R> finalize_geom(const DevScene<R>& sc, uint3
     return h;
 }
 // full record incl. the ids of SURVEY 8b (cr_trace_batch)
-template <typename R>
-__device__ __forceinline__ HitInfo<R> finalize_hit(const DevScene<R>& sc, uint32_t ref, R t, V3<R> o, V3<R> d) {
-    HitInfo<R> h = finalize_geom<R>(sc, ref, t, o, d, true);
+template <typename R, bool ANIM>
+__device__ __forceinline__ HitInfo<R> finalize_hit(const DevScene<R>& sc, uint32_t ref, R t, V3<R> o, V3<R> d, R tm) {
+    HitInfo<R> h = finalize_geom<R, ANIM>(sc, ref, t, o, d, true, tm);
     const uint32_t kind = ref_kind(ref);
     const PrimMeta* mp = kind == CR_PRIM_SPHERE ? sc.meta[0] : (kind == CR_PRIM_TRIANGLE ? sc.meta[1] : sc.meta[2]);
     const PrimMeta m = mp[ref_index(ref)];
@@ -510,6 +577,9 @@ struct RegStore {
     uint32_t bref, idx;
     PreRay pre;
     V3<R> ro, rd;
+    R tm;
+    __device__ __forceinline__ R time() const { return tm; }
+    __device__ __forceinline__ void set_time(R t) { tm = t; }
     __device__ __forceinline__ R best_t() const { return bt; }
     __device__ __forceinline__ uint32_t best_ref() const { return bref; }
     __device__ __forceinline__ void set_best(R t, uint32_t ref) { bt = t; bref = ref; }
@@ -520,16 +590,21 @@ struct RegStore {
     __device__ __forceinline__ void set_ray(V3<R> o, V3<R> d) { ro = o; rd = d; }
     __device__ __forceinline__ void get_ray(V3<R>& o, V3<R>& d) const { o = ro; d = rd; }
 };
-template <typename R, int BLOCK>
+// (10 CTAs x (11.5 KB + 1 KB reserved) = 125 KB sits just inside the 132 KB shared-memory carve-out; the ray time
+// of the animated builds lives in its own table so the static builds keep that L1 / shared split.)
+template <typename R, int BLOCK, bool ANIM>
 struct LaneSlots {
     R best_t[BLOCK];
+    R tm[ANIM ? BLOCK : 1];  // ray time (positions animated primitives)
     R ray[6][BLOCK];
     float pre[7][BLOCK];
     uint32_t best_ref[BLOCK], my[BLOCK];
 };
-template <typename R, int BLOCK>
+template <typename R, int BLOCK, bool ANIM>
 struct SmemStore {
-    LaneSlots<R, BLOCK>* s;
+    LaneSlots<R, BLOCK, ANIM>* s;
+    __device__ __forceinline__ R time() const { return s->tm[ANIM ? threadIdx.x : 0]; }
+    __device__ __forceinline__ void set_time(R t) { s->tm[ANIM ? threadIdx.x : 0] = t; }
     __device__ __forceinline__ R best_t() const { return s->best_t[threadIdx.x]; }
     __device__ __forceinline__ uint32_t best_ref() const { return s->best_ref[threadIdx.x]; }
     __device__ __forceinline__ void set_best(R t, uint32_t ref) { s->best_t[threadIdx.x] = t; s->best_ref[threadIdx.x] = ref; }
@@ -565,7 +640,7 @@ struct SmemStore {
 // (a node built from a span of 1 or 2 holds its primitives directly, a node built from a span >= 3
 // has two node children: bvhwrapper.rs:57-74.)  Leaves are tested with no box of their own, left
 // first, right with the updated interval, strict comparisons — the reference's order.
-template <typename R, typename Store>
+template <typename R, typename Store, bool ANIM>
 struct Trav {
     NodeRay<R> nr;
     Store store;
@@ -627,13 +702,14 @@ struct Trav {
     }
     __device__ __forceinline__ uint32_t leaf_left() const { return wa & ~BIGBOX_BIT; }
     __device__ __forceinline__ uint32_t leaf_right() const { return wb; }
-    static __device__ __forceinline__ bool test_prim(const DevScene<R>& sc, uint32_t ref, V3<R> o, V3<R> d, R a, R tmin, R best, R& t) {
+    static __device__ __forceinline__ bool test_prim(const DevScene<R>& sc, uint32_t ref, V3<R> o, V3<R> d, R a, R tmin, R best, R tm,
+                                                     R& t) {
         const uint32_t kind = ref_kind(ref), idx = ref_index(ref);
         if (kind == CR_PRIM_SPHERE) {
-            const SphereRec<R> s = ldg_rec<sizeof(SphereRec<R>) / 16>(sc.spheres + idx);
+            const SphereRec<R> s = sphere_at<R, ANIM>(sc, idx, tm);
             return sphere_hit_t(s, o, d, a, tmin, best, t);
         } else if (kind == CR_PRIM_TRIANGLE) {
-            const TriRec<R> tr = ldg_rec<sizeof(TriRec<R>) / 16>(sc.tris + idx);
+            const TriRec<R> tr = tri_at<R, ANIM>(sc, idx, tm);
             return tri_hit_t(tr, o, d, tmin, best, t);
         } else {
             const QuadRec<R> q = ldg_rec<sizeof(QuadRec<R>) / 16>(sc.quads + idx);
@@ -646,6 +722,9 @@ struct Trav {
         if constexpr (sizeof(R) == 8) {
             const uint32_t pl = leaf_left(), pr = leaf_right();
             if (!ok || ref_kind(pl) != CR_PRIM_SPHERE) return false;
+            // the pre-filter reads the construction-time f32 sphere: an animated one is always tested in full
+            if (sphere_is_animated<R, ANIM>(sc, ref_index(pl))) return false;
+            if (pr != REF_NONE && ref_kind(pr) == CR_PRIM_SPHERE && sphere_is_animated<R, ANIM>(sc, ref_index(pr))) return false;
             const PreRay pre = store.get_pre();
             if (!sphere_definite_miss(ldg_rec<1>(sc.spheres32 + ref_index(pl)), pre)) return false;
             if (pr == REF_NONE) return true;
@@ -658,13 +737,15 @@ struct Trav {
     __device__ __forceinline__ int step_leaf(const DevScene<R>& sc, V3<R> o, V3<R> d, R tmin) {
         const R a = vlen2(d);  // sphere.rs:74
         R best = store.best_t(), t;
+        R tm = R(0);
+        if constexpr (ANIM) tm = store.time();
         uint32_t bref = REF_NONE;
         const uint32_t pl = leaf_left(), pr = leaf_right();
-        if (test_prim(sc, pl, o, d, a, tmin, best, t)) {
+        if (test_prim(sc, pl, o, d, a, tmin, best, tm, t)) {
             best = t;
             bref = pl;
         }
-        if (pr != REF_NONE && test_prim(sc, pr, o, d, a, tmin, best, t)) {
+        if (pr != REF_NONE && test_prim(sc, pr, o, d, a, tmin, best, tm, t)) {
             best = t;
             bref = pr;
         }
@@ -685,12 +766,12 @@ struct Trav {
 // whole warp along for one lane.  Finished lanes are refilled (one atomic per warp) as soon as REFILL
 // of them are idle.  Each lane's own sequence of tests is the reference's, so is the result.
 //   IO::count() / cursor() / filter(i,tmin,tmax) / load(i,o,d) / commit(has,i,ref,t,o,d)  (commit is warp-synchronous)
-template <typename R, int REFILL, int BLOCK, typename IO>
-__device__ __forceinline__ void trace_persistent(const DevScene<R>& sc, R tmin, R tmax, IO& io, LaneSlots<R, BLOCK>* slots) {
+template <typename R, int REFILL, int BLOCK, bool ANIM, typename IO>
+__device__ __forceinline__ void trace_persistent(const DevScene<R>& sc, R tmin, R tmax, IO& io, LaneSlots<R, BLOCK, ANIM>* slots) {
     const int NODE_SLICE = sc.node_slice;
     const uint32_t n = io.count();
     const int lane = threadIdx.x & 31;
-    Trav<R, SmemStore<R, BLOCK>> tv;
+    Trav<R, SmemStore<R, BLOCK, ANIM>, ANIM> tv;
     tv.store.s = slots;
     tv.ok = false;
     tv.i = 0;
@@ -706,14 +787,17 @@ __device__ __forceinline__ void trace_persistent(const DevScene<R>& sc, R tmin, 
             {
                 V3<R> o = {R(0), R(0), R(0)}, d = {R(0), R(0), R(0)};
                 uint32_t my = 0, bref = REF_MISS;
-                R bt = tmax;
+                R bt = tmax, tm = R(0);
                 if (st == ST_DONE) {
                     my = tv.store.my();
                     bref = tv.store.best_ref();
                     bt = tv.store.best_t();
-                    if (io.commit_needs_ray()) tv.store.get_ray(o, d);
+                    if (io.commit_needs_ray()) {
+                        tv.store.get_ray(o, d);
+                        if constexpr (ANIM) tm = tv.store.time();
+                    }
                 }
-                io.commit(st == ST_DONE, my, bref, bt, o, d);
+                io.commit(st == ST_DONE, my, bref, bt, o, d, tm);
             }
             if (st == ST_DONE) st = ST_IDLE;
             if (!exhausted) {
@@ -734,6 +818,7 @@ __device__ __forceinline__ void trace_persistent(const DevScene<R>& sc, R tmin, 
                         io.load(k, o, d);  // the R-precision ray of the exact / leaf steps goes to the lane's slot
                         tv.init_from(io.filter(k, tmin, tmax), tmax);
                         tv.store.set_ray(o, d);
+                        if constexpr (ANIM) tv.store.set_time(io.time(k));
                         st = (sc.n_nodes == 0u) ? (int)ST_DONE : tv.walk_state();
                     }
                 }
@@ -769,10 +854,10 @@ __device__ __forceinline__ void trace_persistent(const DevScene<R>& sc, R tmin, 
 // slices and EXACT + LEAF phases as trace_persistent, so the rare expensive steps still run with several lanes
 // at once.  Used by the tail kernel, where a warp owns 32 paths from their current segment to their end.
 // Lanes with active == false only take part in the votes.  Returns the closest hit in (ref, t).
-template <typename R, int BLOCK>
-__device__ __forceinline__ void trace_warp_batch(const DevScene<R>& sc, R tmin, R tmax, bool active, V3<R> o, V3<R> d,
-                                                 LaneSlots<R, BLOCK>* slots, uint32_t& ref, R& t) {
-    Trav<R, SmemStore<R, BLOCK>> tv;
+template <typename R, int BLOCK, bool ANIM>
+__device__ __forceinline__ void trace_warp_batch(const DevScene<R>& sc, R tmin, R tmax, bool active, V3<R> o, V3<R> d, R tm,
+                                                 LaneSlots<R, BLOCK, ANIM>* slots, uint32_t& ref, R& t) {
+    Trav<R, SmemStore<R, BLOCK, ANIM>, ANIM> tv;
     tv.store.s = slots;
     tv.ok = false;
     tv.i = 0;
@@ -783,6 +868,7 @@ __device__ __forceinline__ void trace_warp_batch(const DevScene<R>& sc, R tmin, 
         const V3<R> inv = {R(1) / d.x, R(1) / d.y, R(1) / d.z};  // adinv, bvh.rs:111
         tv.init_from(make_filter_ray<R>(o, d, inv, tmin, tmax, sc.bsmall, sc.bmax), tmax);
         tv.store.set_ray(o, d);
+        if constexpr (ANIM) tv.store.set_time(tm);
         st = (sc.n_nodes == 0u) ? (int)ST_DONE : tv.walk_state();
     }
     while (__any_sync(0xffffffffu, st != ST_DONE)) {

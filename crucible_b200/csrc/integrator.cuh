@@ -364,8 +364,9 @@ struct RenderTraceIO {
             d = {b.x, b.y, b.z};
         }
     }
+    __device__ __forceinline__ R time(uint32_t i) const { return paths[i].tm; }  // ray_casting.rs:84
     __device__ __forceinline__ bool commit_needs_ray() const { return false; }
-    __device__ __forceinline__ void commit(bool has, uint32_t i, uint32_t ref, R t, V3<R>, V3<R>) const {
+    __device__ __forceinline__ void commit(bool has, uint32_t i, uint32_t ref, R t, V3<R>, V3<R>, R) const {
         int q = -1;
         uint32_t minfo = 0;  // material index (bits 0..23) | needs-uv (bit 31): saves the shaders a dependent load
         if (has) {
@@ -386,12 +387,12 @@ struct RenderTraceIO {
     }
 };
 
-template <typename R, int REFILL, int MINB>
+template <typename R, int REFILL, int MINB, bool ANIM>
 __global__ void __launch_bounds__(TRACE_BLOCK, MINB) k_trace(DevScene<R> sc, PathRec<R>* __restrict__ paths, Control* __restrict__ ctl,
                                                         int side, uint2* __restrict__ queues, const FilterRec* __restrict__ filt, uint32_t pool) {
-    __shared__ LaneSlots<R, TRACE_BLOCK> slots;
+    __shared__ LaneSlots<R, TRACE_BLOCK, ANIM> slots;
     RenderTraceIO<R> io{sc, paths, ctl, queues, filt, ctl->n_in[side], pool};
-    trace_persistent<R, REFILL, TRACE_BLOCK>(sc, R(0.001), Num<R>::inf(), io, &slots);  // ray_casting.rs:119
+    trace_persistent<R, REFILL, TRACE_BLOCK, ANIM>(sc, R(0.001), Num<R>::inf(), io, &slots);  // ray_casting.rs:119
 }
 
 // fixed-point accumulation: order independent => bit-reproducible for any schedule and GPU count
@@ -468,12 +469,12 @@ __global__ void __launch_bounds__(SHADE_BLOCK) k_shade_emissive(DevScene<R> sc, 
 // One scatter event (Materials::scatter, src/materials/mod.rs:23-29) on a path whose closest hit is
 // (p.ref, p.t): rebuilds the HitRecord, draws from the (pixel, sample, bounce) stream, and on survival
 // turns p into the scattered ray.  Shared by the material-sorted shade kernels and the tail kernel.
-template <typename R, int MAT>
+template <typename R, int MAT, bool ANIM>
 __device__ __forceinline__ bool scatter_path(const DevScene<R>& sc, PathRec<R>& p, uint32_t minfo, uint64_t seed, uint32_t max_depth) {
     const bool cl = sc.clamp_colors != 0;
     const V3<R> o = {p.ox, p.oy, p.oz}, d = {p.dx, p.dy, p.dz};
     // u, v are needed only when a Lambertian's texture tree reaches an image
-    const HitInfo<R> h = finalize_geom<R>(sc, p.ref, p.t, o, d, (minfo >> 31) != 0u);
+    const HitInfo<R> h = finalize_geom<R, ANIM>(sc, p.ref, p.t, o, d, (minfo >> 31) != 0u, p.tm);
     const DevMaterial& mat = sc.mats[minfo & 0x00FFFFFFu];
     const uint32_t bounce = p.bounce + 1;  // this is the bounce-th hit of the path
     Rng<R> g(seed, p.pixel, p.sample, bounce);
@@ -522,7 +523,7 @@ __device__ __forceinline__ bool scatter_path(const DevScene<R>& sc, PathRec<R>& 
 }
 
 // scatter kernels: one per material so a warp runs one BSDF; survivors are compacted into the other side
-template <typename R, int MAT, int MINB>
+template <typename R, int MAT, int MINB, bool ANIM>
 __global__ void __launch_bounds__(SHADE_BLOCK, MINB) k_shade_scatter(DevScene<R> sc, const PathRec<R>* __restrict__ in,
                                                                       PathRec<R>* __restrict__ out, Control* __restrict__ ctl, int nxt,
                                                                       const uint2* __restrict__ queue, FilterRec* __restrict__ filt_out,
@@ -538,7 +539,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK, MINB) k_shade_scatter(DevScene<R>
         if (k < n) {
             const uint2 e = queue[k];
             load_path(in + e.x, p);
-            alive = scatter_path<R, MAT>(sc, p, e.y, seed, max_depth);
+            alive = scatter_path<R, MAT, ANIM>(sc, p, e.y, seed, max_depth);
         }
         const uint32_t amask = __ballot_sync(0xffffffffu, alive);
         if (amask != 0u) {  // warp-uniform
@@ -557,11 +558,11 @@ __global__ void __launch_bounds__(SHADE_BLOCK, MINB) k_shade_scatter(DevScene<R>
 // scatter of every lane's own material, using the same device routines, so every path is unchanged.
 // (The first version gave each THREAD one path and its own traversal state machine: lanes in different states
 // serialised each other, 1.6 ms per frame at 11 % warps active, profiles/misc_r01c.md.)
-template <typename R>
+template <typename R, bool ANIM>
 __global__ void __launch_bounds__(TRACE_BLOCK, 4) k_tail(DevScene<R> sc, const PathRec<R>* __restrict__ paths, Control* __restrict__ ctl,
                                                          int side, uint64_t seed, uint32_t max_depth,
                                                          unsigned long long* __restrict__ fb, double fb_scale) {
-    __shared__ LaneSlots<R, TRACE_BLOCK> slots;
+    __shared__ LaneSlots<R, TRACE_BLOCK, ANIM> slots;
     const uint32_t n = ctl->n_in[side];
     const bool cl = sc.clamp_colors != 0;
     unsigned long long traced = 0;  // segments beyond each path's first (k_plan already counted that one)
@@ -574,7 +575,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK, 4) k_tail(DevScene<R> sc, const P
             const V3<R> o = {p.ox, p.oy, p.oz}, d = {p.dx, p.dy, p.dz};
             uint32_t ref;
             R t;
-            trace_warp_batch<R, TRACE_BLOCK>(sc, R(0.001), Num<R>::inf(), alive, o, d, &slots, ref, t);  // ray_casting.rs:119
+            trace_warp_batch<R, TRACE_BLOCK, ANIM>(sc, R(0.001), Num<R>::inf(), alive, o, d, p.tm, &slots, ref, t);  // ray_casting.rs:119
             if (!alive) continue;
             if (!first) ++traced;
             if (ref == REF_MISS) {  // ray_casting.rs:133-151
@@ -589,9 +590,9 @@ __global__ void __launch_bounds__(TRACE_BLOCK, 4) k_tail(DevScene<R> sc, const P
             const PrimMeta pm = (kind == CR_PRIM_SPHERE ? sc.meta[0] : (kind == CR_PRIM_TRIANGLE ? sc.meta[1] : sc.meta[2]))[ref_index(p.ref)];
             const uint32_t minfo = (uint32_t)pm.material | ((pm.mat_kind & MATKIND_NEEDS_UV) ? 0x80000000u : 0u);
             const int mk = pm.mat_kind & MATKIND_MASK;
-            if (mk == CR_MAT_LAMBERTIAN) alive = scatter_path<R, CR_MAT_LAMBERTIAN>(sc, p, minfo, seed, max_depth);
-            else if (mk == CR_MAT_METAL) alive = scatter_path<R, CR_MAT_METAL>(sc, p, minfo, seed, max_depth);
-            else if (mk == CR_MAT_DIELECTRIC) alive = scatter_path<R, CR_MAT_DIELECTRIC>(sc, p, minfo, seed, max_depth);
+            if (mk == CR_MAT_LAMBERTIAN) alive = scatter_path<R, CR_MAT_LAMBERTIAN, ANIM>(sc, p, minfo, seed, max_depth);
+            else if (mk == CR_MAT_METAL) alive = scatter_path<R, CR_MAT_METAL, ANIM>(sc, p, minfo, seed, max_depth);
+            else if (mk == CR_MAT_DIELECTRIC) alive = scatter_path<R, CR_MAT_DIELECTRIC, ANIM>(sc, p, minfo, seed, max_depth);
             else {  // EXTENSION emissive
                 const DevMaterial& mat = sc.mats[pm.material];
                 fb_add(fb, p.fb, (double)(p.tr * (R)mat.emit[0]), (double)(p.tg * (R)mat.emit[1]), (double)(p.tb * (R)mat.emit[2]), fb_scale);
@@ -628,7 +629,7 @@ static __global__ void k_resolve(const unsigned long long* __restrict__ fb, uint
 
 // trace_batch: Hittables::hit on caller-supplied rays, full HitRecord out.  Same traversal engine as
 // the render path.
-template <typename R>
+template <typename R, bool ANIM>
 struct BatchTraceIO {
     const DevScene<R>& sc;
     const double* rays;
@@ -648,15 +649,16 @@ struct BatchTraceIO {
         o = {(R)r[0], (R)r[1], (R)r[2]};
         d = {(R)r[3], (R)r[4], (R)r[5]};
     }
+    __device__ __forceinline__ R time(uint32_t i) const { return (R)rays[7ull * i + 6]; }
     __device__ __forceinline__ bool commit_needs_ray() const { return true; }
-    __device__ __forceinline__ void commit(bool has, uint32_t i, uint32_t ref, R t, V3<R> o, V3<R> d) const {
+    __device__ __forceinline__ void commit(bool has, uint32_t i, uint32_t ref, R t, V3<R> o, V3<R> d, R tm) const {
         if (!has) return;
         CrHit h;
         if (ref == REF_MISS) {
             h.prim_index = -1; h.obj_id = -1; h.front_face = 0; h.material = -1;
             h.t = 0.0; h.p[0] = h.p[1] = h.p[2] = 0.0; h.n[0] = h.n[1] = h.n[2] = 0.0; h.u = h.v = 0.0;
         } else {
-            const HitInfo<R> hi = finalize_hit<R>(sc, ref, t, o, d);
+            const HitInfo<R> hi = finalize_hit<R, ANIM>(sc, ref, t, o, d, tm);
             h.prim_index = hi.prim_index; h.obj_id = hi.obj_id; h.front_face = hi.front ? 1 : 0; h.material = hi.material;
             h.t = (double)t;
             h.p[0] = (double)hi.p.x; h.p[1] = (double)hi.p.y; h.p[2] = (double)hi.p.z;
@@ -666,12 +668,12 @@ struct BatchTraceIO {
         out[i] = h;
     }
 };
-template <typename R>
+template <typename R, bool ANIM>
 __global__ void __launch_bounds__(TRACE_BLOCK) k_trace_batch(DevScene<R> sc, const double* __restrict__ rays, uint32_t n, double tmin,
                                                               double tmax, CrHit* __restrict__ out, uint32_t* __restrict__ cursor) {
-    __shared__ LaneSlots<R, TRACE_BLOCK> slots;
-    BatchTraceIO<R> io{sc, rays, out, cursor, n};
-    trace_persistent<R, CRB_REFILL, TRACE_BLOCK>(sc, (R)tmin, (R)tmax, io, &slots);
+    __shared__ LaneSlots<R, TRACE_BLOCK, ANIM> slots;
+    BatchTraceIO<R, ANIM> io{sc, rays, out, cursor, n};
+    trace_persistent<R, CRB_REFILL, TRACE_BLOCK, ANIM>(sc, (R)tmin, (R)tmax, io, &slots);
 }
 
 // ---- host side: typed view of the scene + wavefront driver -----------------------------------------
@@ -689,6 +691,11 @@ static DevScene<R> make_dev_scene(const SceneDeviceData& s) {
     d.quads = reinterpret_cast<const QuadRec<R>*>(s.quads[k]);
     for (int i = 0; i < 3; ++i) d.meta[i] = s.meta[i];
     d.mats = s.mats;
+    d.anim_keys = s.anim_keys;
+    d.sphere_track = s.sphere_track;
+    d.tri_track = s.tri_track;
+    d.tri_anim_slot = s.tri_anim_slot;
+    d.tri_anim_verts = s.tri_anim_verts;
     d.texs = s.texs;
     d.images = s.images;
     d.n_nodes = s.n_nodes;
@@ -727,11 +734,12 @@ int trace_batch_impl(const SceneDeviceData& s, const double* d_rays, size_t n, d
         return CR_ERR_LIMIT;
     }
     const DevScene<R> sc = make_dev_scene<R>(s);
-    int grid = persistent_grid(k_trace_batch<R>, TRACE_BLOCK, s.num_sms);
+    auto kern = (s.anim_keys != nullptr) ? k_trace_batch<R, true> : k_trace_batch<R, false>;
+    int grid = persistent_grid(kern, TRACE_BLOCK, s.num_sms);
     const size_t need = (n + TRACE_BLOCK - 1) / TRACE_BLOCK;
     if ((size_t)grid > need) grid = (int)need;
     CRB_CUDA(cudaMemsetAsync(d_cursor, 0, sizeof(uint32_t), stream));
-    k_trace_batch<R><<<grid, TRACE_BLOCK, 0, stream>>>(sc, d_rays, (uint32_t)n, tmin, tmax, d_out, d_cursor);
+    kern<<<grid, TRACE_BLOCK, 0, stream>>>(sc, d_rays, (uint32_t)n, tmin, tmax, d_out, d_cursor);
     CRB_CUDA(cudaGetLastError());
     return CR_OK;
 }
@@ -897,14 +905,16 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
     // small budget lose 20 %.  Unless CRB_MINB pins one, the first large wavefront of a scene is traced with both
     // (same rays, same result) and the faster one is kept; the choice is cached per device by scene signature.
     typedef void (*TraceFn)(DevScene<R>, PathRec<R>*, Control*, int, uint2*, const FilterRec*, uint32_t);
-    TraceFn trace_variants[2] = {k_trace<R, CRB_REFILL, 8>, k_trace<R, CRB_REFILL, 10>};
+    const bool animated = s.anim_keys != nullptr;  // object keyframes: the builds that evaluate timelines at the ray time
+    TraceFn trace_variants[2] = {animated ? k_trace<R, CRB_REFILL, 8, true> : k_trace<R, CRB_REFILL, 8, false>,
+                                 animated ? k_trace<R, CRB_REFILL, 8, true> : k_trace<R, CRB_REFILL, 10, false>};
     const int trace_grids[2] = {persistent_grid(trace_variants[0], TRACE_BLOCK, s.num_sms),
                                 persistent_grid(trace_variants[1], TRACE_BLOCK, s.num_sms)};
     const uint64_t signature = scene_signature(s, sizeof(R) == 8 ? 0 : 1);
     int variant = ws.lookup_variant(signature);
     if (const char* e = getenv("CRB_MINB")) variant = atoi(e) <= 8 ? 0 : 1;
     const uint64_t tune_at = total >= 2ull * pool ? 1 : 0;  // the second wavefront mixes bounce rays with camera rays
-    bool tuning = variant < 0 && total >= (1ull << 20);
+    bool tuning = variant < 0 && total >= (1ull << 20) && !animated;
     if (variant < 0) variant = 1;
     TraceFn trace_fn = trace_variants[variant];
     int g_trace = trace_grids[variant];
@@ -913,9 +923,12 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
     typedef void (*GenFn)(const Control*, const DevCamera*, const RaygenParams<R>, PathRec<R>*, FilterRec*);
     typedef void (*ScatFn)(DevScene<R>, const PathRec<R>*, PathRec<R>*, Control*, int, const uint2*, FilterRec*, uint64_t, uint32_t);
     GenFn gen_fn = smb <= 4 ? k_raygen<R, 4> : smb <= 6 ? k_raygen<R, 6> : k_raygen<R, 8>;
-    ScatFn lam_fn = smb <= 4 ? k_shade_scatter<R, CR_MAT_LAMBERTIAN, 4> : smb <= 6 ? k_shade_scatter<R, CR_MAT_LAMBERTIAN, 6> : k_shade_scatter<R, CR_MAT_LAMBERTIAN, 8>;
-    ScatFn met_fn = smb <= 4 ? k_shade_scatter<R, CR_MAT_METAL, 4> : smb <= 6 ? k_shade_scatter<R, CR_MAT_METAL, 6> : k_shade_scatter<R, CR_MAT_METAL, 8>;
-    ScatFn die_fn = smb <= 4 ? k_shade_scatter<R, CR_MAT_DIELECTRIC, 4> : smb <= 6 ? k_shade_scatter<R, CR_MAT_DIELECTRIC, 6> : k_shade_scatter<R, CR_MAT_DIELECTRIC, 8>;
+    ScatFn lam_fn = animated ? k_shade_scatter<R, CR_MAT_LAMBERTIAN, 6, true>
+                              : (smb <= 4 ? k_shade_scatter<R, CR_MAT_LAMBERTIAN, 4, false> : smb <= 6 ? k_shade_scatter<R, CR_MAT_LAMBERTIAN, 6, false> : k_shade_scatter<R, CR_MAT_LAMBERTIAN, 8, false>);
+    ScatFn met_fn = animated ? k_shade_scatter<R, CR_MAT_METAL, 6, true>
+                              : (smb <= 4 ? k_shade_scatter<R, CR_MAT_METAL, 4, false> : smb <= 6 ? k_shade_scatter<R, CR_MAT_METAL, 6, false> : k_shade_scatter<R, CR_MAT_METAL, 8, false>);
+    ScatFn die_fn = animated ? k_shade_scatter<R, CR_MAT_DIELECTRIC, 6, true>
+                              : (smb <= 4 ? k_shade_scatter<R, CR_MAT_DIELECTRIC, 4, false> : smb <= 6 ? k_shade_scatter<R, CR_MAT_DIELECTRIC, 6, false> : k_shade_scatter<R, CR_MAT_DIELECTRIC, 8, false>);
     RaygenParams<R> rp;
     memset(&rp, 0, sizeof(rp));
     rp.W = W; rp.rows_local = rows_local; rp.row_block = block; rp.row_rank = rank; rp.row_world = world;
@@ -925,7 +938,8 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
     rp.bmax = s.bmax;
     host_camera_constants<R>(cam_in, rp);
     const int g_gen = persistent_grid(gen_fn, SHADE_BLOCK, s.num_sms);
-    const int g_tail = persistent_grid(k_tail<R>, TRACE_BLOCK, s.num_sms);
+    auto tail_fn = animated ? k_tail<R, true> : k_tail<R, false>;
+    const int g_tail = persistent_grid(tail_fn, TRACE_BLOCK, s.num_sms);
     uint32_t tail_n = 65536;
     if (const char* e = getenv("CRB_TAIL")) tail_n = (uint32_t)atoi(e);
     const int g_miss = persistent_grid(k_shade_miss<R>, SHADE_BLOCK, s.num_sms);
@@ -1018,7 +1032,7 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
                 // one k_tail launch follows each of them to its end instead of ~25-45 more 8-launch iterations
                 const int side = (int)(it & 1);
                 tm.begin(0, a);
-                k_tail<R><<<g_tail, TRACE_BLOCK, 0, stream>>>(sc, paths[side], ctl, side, opts.seed, cam_in.max_depth, fb, fb_scale);
+                tail_fn<<<g_tail, TRACE_BLOCK, 0, stream>>>(sc, paths[side], ctl, side, opts.seed, cam_in.max_depth, fb, fb_scale);
                 tm.end(0, a);
                 ++launches;
                 done = true;

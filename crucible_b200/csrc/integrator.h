@@ -19,6 +19,11 @@ struct SceneDeviceData {
     DevMaterial* mats = nullptr;
     DevTexture* texs = nullptr;
     DevImage* images = nullptr;
+    CrAnimKey* anim_keys = nullptr;
+    AnimTrack* sphere_track = nullptr;
+    AnimTrack* tri_track = nullptr;
+    uint32_t* tri_anim_slot = nullptr;
+    double* tri_anim_verts = nullptr;
     uint32_t n_nodes = 0;
     uint32_t n_prims[3] = {0, 0, 0};  // spheres, triangles, quads
     int32_t sky_kind = CR_SKY_DEFAULT, sky_image = -1;

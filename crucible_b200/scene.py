@@ -149,13 +149,31 @@ class _Transform:  # src/timeline/mod.rs:62-71
 class TransformTimeline:
     """Translate keyframes of src/timeline/{mod,transform_builder,helper_functions}.rs for a point."""
 
-    def __init__(self, start_pos):
+    def __init__(self, start_pos, start_scale=1.0):
         self.start_pos = np.asarray(start_pos, np.float64).copy()
+        self.start_scale = float(start_scale)
         self.translate: list[_Transform] = []  # excludes the Omni init entry (valid_time (-0.1,-0.1))
+        self.scale: list[_Transform] = []      # ScaleR keys: delta = start value, end = end value
 
     @staticmethod
     def new(start_pos, _start_rot=None, _start_scale=1.0):
-        return TransformTimeline(start_pos)
+        return TransformTimeline(start_pos, _start_scale)
+
+    @staticmethod
+    def new_sphere(start_pos, _start_rot, start_radius):  # timeline/mod.rs:178-223
+        return TransformTimeline(start_pos, start_radius)
+
+    def combine_and_compute_object(self, t):
+        """timeline/mod.rs:233-263 for an object point: (x, y, z, w) with w = the radius / scale entry; evaluated by
+        the oracle's restatement."""
+        from oracle import binding as oracle
+
+        keys = self.anim_keys()
+        arr = (abi.CrAnimKey * max(len(keys), 1))(*keys)
+        init = (abi.C.c_double * 4)(*self.start_pos, self.start_scale)
+        out = (abi.C.c_double * 4)()
+        oracle.load().orc_combine_and_compute(init, abi.C.cast(arr, abi.C.c_void_p), len(keys), float(t), out)
+        return np.array(list(out))
 
     def _translate(self, axis, x, keyframe, interp, space):
         # transform_builder.rs:348-469
@@ -191,6 +209,29 @@ class TransformTimeline:
         self.translate_x(p[0], keyframe, interp, space)
         self.translate_y(p[1], keyframe, interp, space)
         self.translate_z(p[2], keyframe, interp, space)
+
+    # ---- scale_sphere, transform_builder.rs:18-96 (spheres only; `start_scale` = construction radius)
+    def scale_sphere(self, r, keyframe, interp):
+        if not keyframe >= 0.0:
+            raise ValueError(f"Cannot add a keyframe before the animation start. You tried to add keyframe: {keyframe} in a r scaling")
+        # most_recent_matching_transform(keyframe, ScaleR): last entry (list order) whose interval ended before the keyframe
+        prev_end, prev_time = self.start_scale, 0.0  # the Omni init entry, valid_time (-0.1, -0.1)
+        for tf in reversed(self.scale):
+            if keyframe > tf.t1:
+                prev_end, prev_time = tf.end, max(tf.t1, 0.0)
+                break
+        if interp == InterpolationType.LERP:
+            t0, t1 = prev_time, float(keyframe)
+        else:
+            t0 = t1 = float(keyframe)
+        self.scale.append(_Transform(t0, t1, 3, float(prev_end), interp, float(r)))
+        self.scale.sort(key=lambda tf: tf.t0)  # sort_by(compare_start): stable
+
+    def anim_keys(self):
+        """The timeline beyond its init entries as CrAnimKey[] in evaluation order (translate list, then scale list)."""
+        keys = [abi.CrAnimKey(tf.t0, tf.t1, tf.delta, 0.0, tf.axis, tf.interp) for tf in self.translate]
+        keys += [abi.CrAnimKey(tf.t0, tf.t1, tf.delta, tf.end, 3, tf.interp) for tf in self.scale]
+        return keys
 
     def keyframes(self):
         out = (abi.CrKeyframe * abi.CR_MAX_CAM_KEYS)()
@@ -307,6 +348,7 @@ class SceneDesc:
     sky_kind: int = abi.CR_SKY_DEFAULT
     sky_image: int = -1
     hidden: list = field(default_factory=list)  # prim indices
+    animation: list = field(default_factory=list)  # (prim_index, point, [abi.CrAnimKey]) per animated point
 
     @property
     def n_prims(self):
@@ -340,6 +382,11 @@ class SceneDesc:
                 raise abi.CrucibleError(rc, f("last_error")().decode())
         for p in self.hidden:
             rc = f("scene_set_hidden")(handle, p, 1)
+            if rc < 0:
+                raise abi.CrucibleError(rc, f("last_error")().decode())
+        for prim, point, keys in self.animation:
+            arr = (abi.CrAnimKey * max(len(keys), 1))(*keys)
+            rc = f("scene_set_keyframes")(handle, prim, point, C.cast(arr, C.c_void_p), len(keys))
             if rc < 0:
                 raise abi.CrucibleError(rc, f("last_error")().decode())
         rc = f("scene_commit")(handle)
@@ -418,6 +465,7 @@ class Scene:
         self._aliases = {}  # IdVendor, scene/id_vendor.rs
         self._next_id = 0
         self._hidden_ids = set()
+        self._anim_ops = {}  # object id -> [(op, args...)] in call order (scene_animator.rs)
         self.sky_kind, self._sky_rgb8 = abi.CR_SKY_DEFAULT, None
 
     @staticmethod
@@ -500,6 +548,63 @@ class Scene:
         """Scene::load_spherical_skybox with the decoded image (RTWImage forces to_rgb8, img_loader.rs:28)."""
         self.sky_kind, self._sky_rgb8 = abi.CR_SKY_SPHERICAL, np.ascontiguousarray(rgb8, np.uint8)
 
+    # object animation bindings, scene_animator.rs:12-458.  The reference rewrites the timeline of every element
+    # carrying the alias' id; here the calls are logged per id and replayed per primitive point in describe().
+    def _check_and_get_alias(self, alias, invalid_types, error_msg):  # scene_animator.rs:13-31
+        if alias not in self._aliases:
+            raise ValueError(f"Could not find an object with the alias: `{alias}`. Are you sure you spelled it right?")
+        oid, otype = self._aliases[alias]
+        if otype in invalid_types:
+            raise ValueError(error_msg)
+        return oid
+
+    def scale_r(self, r, keyframe, it, alias):  # scene_animator.rs:140-175
+        oid = self._check_and_get_alias(alias, (ObjectType.Camera, ObjectType.Triangle, ObjectType.TriangleMesh, ObjectType.Quad),
+                                        "ScaleR can only be applied to Spheres")
+        self._anim_ops.setdefault(oid, []).append(("scale_r", float(r), float(keyframe), it))
+
+    def _translate_axis(self, axis, x, keyframe, it, space, alias):
+        oid = self._check_and_get_alias(alias, (ObjectType.Quad,), "quads (extension) cannot be animated")
+        self._anim_ops.setdefault(oid, []).append(("translate", axis, float(x), float(keyframe), it, space))
+
+    def translate_x(self, x, keyframe, it, space, alias):  # scene_animator.rs:231-282
+        self._translate_axis(0, x, keyframe, it, space, alias)
+
+    def translate_y(self, y, keyframe, it, space, alias):  # :284-335
+        self._translate_axis(1, y, keyframe, it, space, alias)
+
+    def translate_z(self, z, keyframe, it, space, alias):  # :337-388
+        self._translate_axis(2, z, keyframe, it, space, alias)
+
+    def translate_point(self, p, keyframe, it, space, alias):  # :390-458 -> translate_x, _y, _z on every point
+        for axis in range(3):
+            self._translate_axis(axis, p[axis], keyframe, it, space, alias)
+
+    def _animation(self):
+        """[(prim_index, point, [CrAnimKey])] for every animated point, replaying the logged calls on a
+        TransformTimeline built from that point's construction position (World-space deltas differ per vertex)."""
+        out = []
+        if not self._anim_ops:
+            return out
+        base = 0
+        for kind, data, _, oid in self._batches:
+            for oid_val in np.unique(oid):
+                ops = self._anim_ops.get(int(oid_val))
+                if not ops:
+                    continue
+                for row in np.nonzero(oid == oid_val)[0]:
+                    pts = [data[row, 0:3]] if kind == abi.CR_PRIM_SPHERE else [data[row, 0:3], data[row, 3:6], data[row, 6:9]]
+                    for point, pos in enumerate(pts):
+                        tl = TransformTimeline(pos, data[row, 3] if kind == abi.CR_PRIM_SPHERE else 1.0)
+                        for op in ops:
+                            if op[0] == "scale_r":
+                                tl.scale_sphere(op[1], op[2], op[3])
+                            else:
+                                tl._translate(op[1], op[2], op[3], op[4], op[5])
+                        out.append((base + int(row), point, tl.anim_keys()))
+            base += len(data)
+        return out
+
     # camera animation bindings, scene_animator.rs:460-552
     def cam_translate_point(self, p, keyframe, interp, space, which):
         tl = self.scene_cam.look_from_tl if which == "from" else self.scene_cam.look_at_tl
@@ -524,6 +629,7 @@ class Scene:
         d.textures = list(self._tables.textures)
         d.images = list(self._tables.images)
         d.sky_kind = self.sky_kind
+        d.animation = self._animation()
         if self._sky_rgb8 is not None:
             d.images.append(self._sky_rgb8)
             d.sky_image = len(d.images) - 1

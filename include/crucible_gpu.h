@@ -202,6 +202,26 @@ int cr_scene_set_textures(CrScene*, const CrTexture*, size_t n);
 int cr_scene_add_image(CrScene*, const uint8_t* rgb8, int w, int h);
 /* Scene::load_default_skybox / load_spherical_skybox, scene/mod.rs:146-156. */
 int cr_scene_set_sky(CrScene*, int kind, int image);
+/* ---- object animation: the keyframes of a primitive's TransformTimeline ---- */
+/* One keyframe of src/timeline/transform_builder.rs in evaluated form.  At ray time t a key is VALID when
+ * t > t1 or t0 <= t <= t1 (Interval::is_less || contains, timeline/mod.rs:239-243, 251-253), with
+ * s = clamp((t - t0) / (t1 - t0), 0, 1) (Transform::get_matrix_at_time, timeline/mod.rs:88-96):
+ *   kind 0,1,2 (translate_x/y/z, transform_builder.rs:348-713): every valid key ADDS  a*s (LERP) or a (NERP) to
+ *              that axis, in list order (the product of translate matrices, timeline/mod.rs:244-248);
+ *   kind 3     (scale_sphere, transform_builder.rs:18-96): the LAST valid key of the list gives the radius,
+ *              a + (b - a)*s (LERP) or b (NERP); with none valid the radius is the construction radius. */
+typedef struct CrAnimKey {
+    double t0, t1, a, b;
+    int32_t kind;   /* 0,1,2 = translate axis; 3 = sphere radius */
+    int32_t interp; /* CrInterp */
+} CrAnimKey;
+/* Replaces the keyframes of one point of a primitive: point 0 of a sphere (centre + radius), points 0,1,2 = the
+ * a, b, c vertex timelines of a triangle (triangle.rs:14-16).  Keys in the timeline's sorted order (the stable
+ * sort by interval start the builder applies after every insertion).  As in the reference, the BVH is built from
+ * the construction-time boxes (bvhwrapper.rs:47-50: `update_bb` results are never read), so a primitive that
+ * leaves its first box can only be hit through that box.  Quads (extension) are not animated. */
+int cr_scene_set_keyframes(CrScene*, size_t prim_index, int point, const CrAnimKey* keys, size_t n);
+
 /* BVHWrapper::new_wrapper (bvhwrapper.rs:15-94) reproduced on the host, then flattened
  * and uploaded.  Must be called after the last edit and before trace/render. */
 int cr_scene_commit(CrScene*);
@@ -212,7 +232,8 @@ int64_t cr_scene_bvh_leaf_order(const CrScene*, int32_t* out, size_t cap);
 
 /* ---- the hot path ---- */
 /* Replaces Hittables::hit (src/objects/mod.rs:118-125) on fixed ray batches.
- * rays = [n][7] (origin, direction, time); interval (tmin,tmax) open as Interval::surrounds. */
+ * rays = [n][7] (origin, direction, time); interval (tmin,tmax) open as Interval::surrounds.
+ * The ray time positions animated primitives (Sphere::hit / Triangle::hit evaluate their timelines at r.time()). */
 int cr_trace_batch(CrScene*, const double* rays, size_t n, double tmin, double tmax,
                    int precision, CrHit* out);
 

@@ -47,6 +47,9 @@ def load():
         getattr(lib, n).restype = C.c_int64
         getattr(lib, n).argtypes = [P, P, P, P, C.c_size_t]
     lib.orc_scene_set_hidden.argtypes = [P, C.c_size_t, C.c_int]
+    lib.orc_scene_set_keyframes.argtypes = [P, C.c_size_t, C.c_int, P, C.c_size_t]
+    lib.orc_combine_and_compute.argtypes = [P, P, C.c_size_t, C.c_double, P]
+    lib.orc_combine_and_compute.restype = None
     lib.orc_scene_set_materials.argtypes = [P, P, C.c_size_t]
     lib.orc_scene_set_textures.argtypes = [P, P, C.c_size_t]
     lib.orc_scene_add_image.argtypes = [P, P, C.c_int, C.c_int]

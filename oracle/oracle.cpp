@@ -242,14 +242,36 @@ struct Sphere {
     double r;
     int mat, obj_id, prim_index;
     bool hide;
-    Aabb bbox;
+    Aabb bbox;                   /* construction-time box: the BVH never sees update_bb (bvhwrapper.rs:47-50, 104-106) */
+    std::vector<CrAnimKey> keys; /* Sphere.timeline beyond its init entries (sphere.rs:18) */
 };
 struct Triangle {
     V3 a, b, c;
     int mat, obj_id, prim_index;
     bool hide;
     Aabb bbox;
+    std::vector<CrAnimKey> keys[3]; /* a_timeline, b_timeline, c_timeline (triangle.rs:14-16) */
 };
+
+/* TransformTimeline::combine_and_compute (timeline/mod.rs:233-263) for one point: every valid translate transform
+ * (valid_time.is_less(t) || contains(t)) multiplies its matrix in, which adds its entry to that axis; the last
+ * valid scale transform supplies w (the sphere radius).  get_matrix_at_time (timeline/mod.rs:88-96):
+ * scaled_time = proportion(t).clamp(0, 1).  Keys arrive in the timeline's sorted order. */
+static inline void combine_and_compute(const std::vector<CrAnimKey>& keys, double t, V3& p, double& w) {
+    for (const CrAnimKey& k : keys) {
+        if (!((t > k.t1) || (k.t0 <= t && t <= k.t1))) continue;
+        double s = (t - k.t0) / (k.t1 - k.t0); /* Interval::proportion, utils.rs:681-683 */
+        s = s < 0.0 ? 0.0 : (s > 1.0 ? 1.0 : s); /* f64::clamp keeps NaN */
+        if (k.kind < 3) {
+            double off = (k.interp == CR_LERP) ? k.a * s : k.a; /* transform_builder.rs:393-419 */
+            if (k.kind == 0) p.x = off + p.x;
+            else if (k.kind == 1) p.y = off + p.y;
+            else p.z = off + p.z;
+        } else {
+            w = (k.interp == CR_LERP) ? k.a + (k.b - k.a) * s : k.b; /* transform_builder.rs:44-58 */
+        }
+    }
+}
 struct Quad { /* EXTENSION */
     V3 q, u, v, normal, w;
     double d;
@@ -335,8 +357,11 @@ static inline void sphere_uv(V3 p, double& u, double& v) {
     v = theta / PI;
 }
 /* sphere.rs:61-105 (static timeline: combine_and_compute == (c, r), timeline/mod.rs:233-263) */
-static inline bool sphere_hit(const Sphere& s, const Ray& r, const Interval& ray_t, HitRecord& out) {
-    if (s.hide) return false;
+static inline bool sphere_hit(const Sphere& s0, const Ray& r, const Interval& ray_t, HitRecord& out) {
+    if (s0.hide) return false;
+    /* sphere.rs:67-70: position and radius from the timeline at the ray's time */
+    struct { V3 c; double r; int mat, prim_index, obj_id; } s = {s0.c, s0.r, s0.mat, s0.prim_index, s0.obj_id};
+    if (!s0.keys.empty()) combine_and_compute(s0.keys, r.tm, s.c, s.r);
     V3 oc = sub(s.c, r.o);
     double a = len2(r.d);
     double h = dot(r.d, oc);
@@ -360,9 +385,15 @@ static inline bool sphere_hit(const Sphere& s, const Ray& r, const Interval& ray
     return true;
 }
 /* triangle.rs:86-140 */
-static inline bool tri_hit(const Triangle& tr, const Ray& r, const Interval& ray_t, HitRecord& out) {
-    if (tr.hide) return false;
+static inline bool tri_hit(const Triangle& t0, const Ray& r, const Interval& ray_t, HitRecord& out) {
+    if (t0.hide) return false;
     const double EPS = std::numeric_limits<double>::epsilon(); /* f64::EPSILON */
+    /* triangle.rs:91-97: the three vertex timelines at the ray's time */
+    struct { V3 a, b, c; int mat, prim_index, obj_id; } tr = {t0.a, t0.b, t0.c, t0.mat, t0.prim_index, t0.obj_id};
+    double unused = 1.0;
+    if (!t0.keys[0].empty()) combine_and_compute(t0.keys[0], r.tm, tr.a, unused);
+    if (!t0.keys[1].empty()) combine_and_compute(t0.keys[1], r.tm, tr.b, unused);
+    if (!t0.keys[2].empty()) combine_and_compute(t0.keys[2], r.tm, tr.c, unused);
     V3 e1 = sub(tr.b, tr.a);
     V3 e2 = sub(tr.c, tr.a);
     V3 pv = cross(r.d, e2);
@@ -874,6 +905,24 @@ int64_t orc_scene_add_quads(OrcScene* h, const double* d, const int32_t* mat, co
     }
     sc.built = false;
     return first;
+}
+/* keyframes of one point of a primitive, in the timeline's sorted order (mirror of cr_scene_set_keyframes) */
+int orc_scene_set_keyframes(OrcScene* h, size_t prim, int point, const CrAnimKey* keys, size_t n) {
+    Scene& sc = *reinterpret_cast<Scene*>(h);
+    if (prim >= sc.elements.size()) return CR_ERR_INVALID;
+    Obj o = sc.elements[prim];
+    if (o.kind == O_SPHERE && point == 0) sc.spheres[o.idx].keys.assign(keys, keys + n);
+    else if (o.kind == O_TRI && point >= 0 && point <= 2) sc.tris[o.idx].keys[point].assign(keys, keys + n);
+    else return CR_ERR_INVALID;
+    return 0;
+}
+/* TransformTimeline::combine_and_compute on its own (timeline KATs): out = (x, y, z, w) */
+void orc_combine_and_compute(const double init[4], const CrAnimKey* keys, size_t n, double t, double out[4]) {
+    std::vector<CrAnimKey> v(keys, keys + n);
+    V3 p = {init[0], init[1], init[2]};
+    double w = init[3];
+    combine_and_compute(v, t, p, w);
+    out[0] = p.x; out[1] = p.y; out[2] = p.z; out[3] = w;
 }
 int orc_scene_set_hidden(OrcScene* h, size_t prim, int hide) {
     Scene& sc = *reinterpret_cast<Scene*>(h);
