@@ -410,24 +410,39 @@ class Scene {
     }
 
     // Scene::render_scene -> render_image -> Camera::render (scene/mod.rs:283-347, camera/mod.rs:270-317):
-    // rebuilds the BVH, renders on the GPU backend, writes "<fname>.ppm" (P3, one "r g b" line per pixel).
+    // rebuilds the BVH, renders on the GPU backend, writes "<fname>.ppm" (P3, one "r g b" line per pixel) --
+    // the library's cr_render_to_file does the sample loop, the copy back and the file.
     CrStats render_scene(const std::string& fname) {
         CrScene* s = flatten(scene_cam.device());
         const CrCamera cam = scene_cam.to_abi();
         CrRenderOpts opts{};
         opts.seed = scene_cam.seed();
-        std::vector<uint8_t> img((size_t)cam.image_width * cam.image_height * 3);
         CrStats st{};
-        const int rc = cr_render(s, &cam, &opts, nullptr, img.data(), &st);
+        const int rc = cr_render_to_file(s, &cam, &opts, (fname + ".ppm").c_str(), CR_PPM_P3, &st);
         const std::string err = rc ? cr_last_error() : "";
         cr_scene_destroy(s);
         if (rc) throw std::runtime_error("Render failed. " + err);
-        std::FILE* f = std::fopen((fname + ".ppm").c_str(), "w");
-        if (!f) throw std::runtime_error("cannot open " + fname + ".ppm");
-        std::fprintf(f, "P3\n%u %u\n255\n", cam.image_width, cam.image_height);
-        for (size_t p = 0; p < img.size(); p += 3) std::fprintf(f, "%u %u %u\n", img[p], img[p + 1], img[p + 2]);
-        std::fclose(f);
         std::fprintf(stderr, "Successful render! Image stored at: %s.ppm\n", fname.c_str());
+        return st;
+    }
+
+    // Scene::render_movie's frame loop (scene/mod.rs:295-322) for a static world: `frames` images into `dir`
+    // ("image{frame:0>digits}.ppm"), frame k+1 traced while frame k is copied, formatted and written.
+    // rank / world shard whole frames over GPUs.  The caller creates `dir` and runs ffmpeg as the reference does.
+    std::vector<CrStats> render_frames(const std::string& dir, uint32_t frames, uint32_t rank = 0, uint32_t world = 1,
+                                       int format = CR_PPM_P3) {
+        CrScene* s = flatten(scene_cam.device());
+        const CrCamera cam = scene_cam.to_abi();
+        CrRenderOpts opts{};
+        opts.seed = scene_cam.seed();
+        std::vector<CrStats> st((frames > rank ? (frames - rank + world - 1) / world : 0) + 1);
+        const uint32_t digits = (uint32_t)std::to_string(frames).size();
+        const int rc = cr_render_frames(s, &cam, &opts, rank, world, frames, dir.c_str(), digits, format, st.data());
+        const std::string err = rc ? cr_last_error() : "";
+        cr_scene_destroy(s);
+        if (rc) throw std::runtime_error("Render failed. " + err);
+        st.pop_back();
+        for (uint32_t f = 0; f < frames; ++f) scene_cam.next_frame();
         return st;
     }
 
