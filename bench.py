@@ -222,14 +222,20 @@ def main():
     pinned = torch.empty((H, W, 3), dtype=torch.float64).pin_memory()
     pinned8 = torch.empty((H, W, 3), dtype=torch.uint8).pin_memory()
 
+    pinned_np, pinned8_np = pinned.numpy(), pinned8.numpy()
+
     def e2e_step():
         g = GpuScene(desc, local)
-        full, full8, st = multigpu.render_sharded(g, cam, rank, world, seed=WORKLOAD["seed"], precision=precision,
-                                                  row_block=row_block, pool_paths=args.pool)
-        if rank == 0:
-            pinned.copy_(full, non_blocking=True)
-            pinned8.copy_(full8, non_blocking=True)
-        torch.cuda.synchronize()
+        if world == 1:
+            # the reference-facing call itself: cr_render with HOST buffers (H2D of the camera, D2H of both images inside)
+            g.render(cam, seed=WORKLOAD["seed"], precision=precision, pool_paths=args.pool, out_rgb=pinned_np, out_rgb8=pinned8_np)
+        else:
+            full, full8, st = multigpu.render_sharded(g, cam, rank, world, seed=WORKLOAD["seed"], precision=precision,
+                                                      row_block=row_block, pool_paths=args.pool)
+            if rank == 0:
+                pinned.copy_(full, non_blocking=True)
+                pinned8.copy_(full8, non_blocking=True)
+            torch.cuda.synchronize()
         g.close()
 
     e2e_step()
