@@ -19,6 +19,7 @@ CR_NERP, CR_LERP = 0, 1
 CR_PRECISION_F64, CR_PRECISION_F32 = 0, 1
 CR_MAX_CAM_KEYS = 32
 CR_PPM_P3, CR_PPM_P6 = 0, 1
+CR_BVH_AUTO, CR_BVH_HOST, CR_BVH_DEVICE = 0, 1, 2
 
 
 class CrMaterial(C.Structure):
@@ -68,6 +69,18 @@ class CrHit(C.Structure):
                 ("t", C.c_double), ("p", C.c_double * 3), ("n", C.c_double * 3), ("u", C.c_double), ("v", C.c_double)]
 
 
+class CrCommitInfo(C.Structure):
+    _fields_ = [("builder", C.c_int32), ("levels", C.c_uint32), ("ms_total", C.c_double), ("ms_build", C.c_double),
+                ("ms_pack", C.c_double), ("ms_h2d", C.c_double), ("ms_device", C.c_double), ("ms_d2h", C.c_double),
+                ("ms_upload", C.c_double)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+# numpy view of CrBvhNode[]
+BVH_NODE_DTYPE = [("lo", "<f8", (3,)), ("hi", "<f8", (3,)), ("left", "<u4"), ("right", "<u4"), ("axis", "<u4"), ("skip", "<u4")]
+
 # numpy view of CrHit[] (same layout, checked in tests)
 HIT_DTYPE = [("prim_index", "<i4"), ("obj_id", "<i4"), ("front_face", "<i4"), ("material", "<i4"), ("t", "<f8"),
              ("p", "<f8", (3,)), ("n", "<f8", (3,)), ("u", "<f8"), ("v", "<f8")]
@@ -92,7 +105,10 @@ SIGNATURES = {
     "cr_scene_add_image": (C.c_int, [_P, _P, C.c_int, C.c_int]),
     "cr_scene_set_sky": (C.c_int, [_P, C.c_int, C.c_int]),
     "cr_scene_set_keyframes": (C.c_int, [_P, C.c_size_t, C.c_int, _P, C.c_size_t]),
+    "cr_scene_set_bvh_builder": (C.c_int, [_P, C.c_int]),
     "cr_scene_commit": (C.c_int, [_P]),
+    "cr_scene_commit_info": (C.c_int, [_P, C.POINTER(CrCommitInfo)]),
+    "cr_scene_bvh_nodes": (C.c_int64, [_P, _P, C.c_size_t]),
     "cr_scene_bvh_info": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]),
     "cr_scene_bvh_leaf_order": (C.c_int64, [_P, _P, C.c_size_t]),
     "cr_trace_batch": (C.c_int, [_P, _P, C.c_size_t, C.c_double, C.c_double, C.c_int, _P]),

@@ -2,6 +2,7 @@
 // BVHWrapper::new_wrapper (src/objects/bvhwrapper.rs:15-94) and flattens it to preorder records,
 // device upload, and the trace / render entry points.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <condition_variable>
 #include <cstdio>
@@ -14,6 +15,7 @@
 #include <thread>
 #include <vector>
 
+#include "bvh_host.h"
 #include "integrator.h"
 
 using namespace crb;
@@ -33,62 +35,11 @@ int fail(int code, const std::string& msg) {
         if (e__ != cudaSuccess) return fail(CR_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
     } while (0)
 
-const double INF = std::numeric_limits<double>::infinity();
-
-// ---- host geometry in reference arithmetic (this file is compiled with -ffp-contract=off) ---------
-struct Box {  // Aabb, src/objects/bvh.rs:19-34; default = EMPTY intervals
-    double lo[3] = {INF, INF, INF};
-    double hi[3] = {-INF, -INF, -INF};
-};
-// Aabb::new_from_boxes / Interval::tight_enclose, bvh.rs:69-75, utils.rs:631-635
-inline Box box_union(const Box& a, const Box& b) {
-    Box r;
-    for (int k = 0; k < 3; ++k) {
-        r.lo[k] = (a.lo[k] <= b.lo[k]) ? a.lo[k] : b.lo[k];
-        r.hi[k] = (a.hi[k] >= b.hi[k]) ? a.hi[k] : b.hi[k];
-    }
-    return r;
-}
-// Aabb::new_from_points, bvh.rs:46-66
-inline Box box_from_points(const double a[3], const double b[3]) {
-    Box r;
-    for (int k = 0; k < 3; ++k) {
-        if (a[k] <= b[k]) {
-            r.lo[k] = a[k];
-            r.hi[k] = b[k];
-        } else {
-            r.lo[k] = b[k];
-            r.hi[k] = a[k];
-        }
-    }
-    return r;
-}
-// Aabb::longest_axis, bvh.rs:82-94
-inline int longest_axis(const Box& b) {
-    const double sx = b.hi[0] - b.lo[0], sy = b.hi[1] - b.lo[1], sz = b.hi[2] - b.lo[2];
-    if (sx > sy) return (sx > sz) ? 0 : 2;
-    if (sy > sz) return 1;
-    return 2;
-}
-
-struct Element {  // one entry of Scene.elements (scene/mod.rs:77), insertion order
-    uint32_t kind, idx;
-    bool hide;
-    Box box;
-};
-
 struct HostImage {
     int w, h;
     std::vector<uint8_t> rgb;
     cudaArray_t arr = nullptr;
     cudaTextureObject_t tex = 0;
-};
-
-struct FlatNode {
-    Box box;
-    uint32_t left, right, axis;  // children: node indices, or primitive refs for a leaf node
-    uint32_t lchild, rchild;     // node children (REF_NONE for a leaf node)
-    uint32_t skip;               // preorder index of the first node after this subtree
 };
 
 }  // namespace
@@ -114,6 +65,8 @@ struct CrScene {
     uint32_t root = REF_MISS;
     uint32_t max_depth = 0;
     uint64_t n_visible = 0;
+    int bvh_builder = CR_BVH_AUTO;
+    CrCommitInfo commit_info = {};
     // device
     SceneDeviceData dev;
     std::vector<void*> dev_allocs;
@@ -188,11 +141,6 @@ DeviceInfo& device_info(int device) {
     return d;
 }
 
-// number of nodes BVHWrapper::help_generate creates for a span (bvhwrapper.rs:46-80)
-uint64_t node_count(uint64_t span) {
-    if (span <= 2) return 1;
-    return 1 + node_count(span / 2) + node_count(span - span / 2);
-}
 
 struct Builder {
     CrScene& sc;
@@ -785,12 +733,40 @@ int cr_scene_commit(CrScene* s) {
     s->nodes.clear();
     s->root = REF_MISS;
     s->max_depth = 0;
+    using clk = std::chrono::steady_clock;
+    auto ms_since = [](clk::time_point a) { return std::chrono::duration<double, std::milli>(clk::now() - a).count(); };
+    const auto t_commit = clk::now();
+    s->commit_info = CrCommitInfo{};
+    s->commit_info.builder = CR_BVH_HOST;
+    if (s->bvh_builder == CR_BVH_DEVICE && s->device < 0) return fail(CR_ERR_NO_DEVICE, "CR_BVH_DEVICE needs a scene created on a CUDA device");
     if (!visible.empty()) {
         const uint64_t nn = node_count(visible.size());
         if (nn > REF_MAX_INDEX) return fail(CR_ERR_LIMIT, "BVH too large");
-        s->nodes.resize((size_t)nn);
-        Builder b{*s, visible, s->nodes};
-        s->max_depth = b.build(0, visible.size(), 0, 4);
+        bool on_device = s->bvh_builder == CR_BVH_DEVICE || (s->bvh_builder == CR_BVH_AUTO && s->device >= 0 && visible.size() >= 32768);
+        if (on_device) {
+            BvhBuildTimes bt;
+            std::string err;
+            rc = gpu_build_bvh(s->device, s->stream, s->elements, visible, s->nodes, s->max_depth, &bt, err);
+            if (rc == CR_ERR_INVALID && s->bvh_builder == CR_BVH_AUTO) {
+                on_device = false;  // NaN coordinates: only the recursion as written defines the result
+            } else if (rc != CR_OK) {
+                s->nodes.clear();
+                return fail(rc, err);
+            } else {
+                s->commit_info.builder = CR_BVH_DEVICE;
+                s->commit_info.ms_pack = bt.ms_pack;
+                s->commit_info.ms_h2d = bt.ms_h2d;
+                s->commit_info.ms_device = bt.ms_device;
+                s->commit_info.ms_d2h = bt.ms_d2h;
+            }
+        }
+        if (!on_device) {
+            s->nodes.resize((size_t)nn);
+            Builder b{*s, visible, s->nodes};
+            s->max_depth = b.build(0, visible.size(), 0, 4);
+        }
+        s->commit_info.levels = s->max_depth;
+        s->commit_info.ms_build = ms_since(t_commit);
         // new_from_vec (bvhwrapper.rs:34-44): the root box is re-derived from its two children
         FlatNode& r = s->nodes[0];
         auto child_box = [&](uint32_t ref) -> Box {
@@ -804,13 +780,48 @@ int cr_scene_commit(CrScene* s) {
     }
     s->committed = true;
     if (s->device >= 0) {
+        const auto t_upload = clk::now();
         rc = upload_scene(s);
         if (rc != CR_OK) {
             s->committed = false;
             return rc;
         }
+        s->commit_info.ms_upload = ms_since(t_upload);
     }
+    s->commit_info.ms_total = ms_since(t_commit);
     return CR_OK;
+}
+
+int cr_scene_set_bvh_builder(CrScene* s, int builder) {
+    if (!s || builder < CR_BVH_AUTO || builder > CR_BVH_DEVICE) return fail(CR_ERR_INVALID, "bad BVH builder");
+    s->bvh_builder = builder;
+    s->committed = false;
+    return CR_OK;
+}
+
+int cr_scene_commit_info(const CrScene* s, CrCommitInfo* out) {
+    if (!s || !out) return fail(CR_ERR_INVALID, "null argument");
+    if (!s->committed) return fail(CR_ERR_STATE, "scene not committed");
+    *out = s->commit_info;
+    return CR_OK;
+}
+
+int64_t cr_scene_bvh_nodes(const CrScene* s, CrBvhNode* out, size_t cap) {
+    if (!s || !s->committed) return fail(CR_ERR_STATE, "scene not committed");
+    const size_t n = std::min(cap, s->nodes.size());
+    for (size_t i = 0; out && i < n; ++i) {
+        const FlatNode& f = s->nodes[i];
+        CrBvhNode& o = out[i];
+        for (int k = 0; k < 3; ++k) {
+            o.lo[k] = f.box.lo[k];
+            o.hi[k] = f.box.hi[k];
+        }
+        o.left = f.left;
+        o.right = f.right;
+        o.axis = f.axis;
+        o.skip = f.skip;
+    }
+    return (int64_t)s->nodes.size();
 }
 
 int cr_scene_bvh_info(const CrScene* s, uint64_t* n_nodes, uint32_t* max_depth, uint64_t* n_visible) {

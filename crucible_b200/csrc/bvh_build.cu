@@ -1,0 +1,469 @@
+// bvh_build.cu — device build of the reference's BVH.
+//
+// BVHWrapper::help_generate (src/objects/bvhwrapper.rs:46-80) is a recursive median split: the box of a span is
+// the fold of its members' boxes (Aabb::new_from_boxes, bvh.rs:69-75), the span is STABLE-sorted by bbox.min on
+// the box's longest axis (box_compare, bvhwrapper.rs:82-94) and cut at span/2.  The host builder in api.cu runs
+// that recursion as written; this file builds the SAME tree (same nodes, same boxes bit for bit, same preorder
+// indices) level by level on the device:
+//
+//   * All spans of one level have sizes {m, m+1} (median split), so a level is a regular grid of (span, chunk)
+//     warp tasks; every node's preorder index and skip link follow from node_count() of at most four sizes per
+//     level, which the host passes by value.
+//   * "Stable sort of every span of the level" is ONE radix sort of the whole order array with the key
+//     (span start << rbits) | rank_axis(member): span starts keep the spans where they are, the rank orders the
+//     members, and the sort's stability supplies the reference's tie rule (equal keys keep their current order).
+//     rank_axis = dense rank of bbox.min[axis] over the whole scene (three sorts, once), with -0.0 == +0.0 as in
+//     f64::partial_cmp, so the per-level key is 2*ceil(log2 n) bits instead of 64 + 32.
+//   * The box fold `r = (r <= x) ? r : x` keeps the FIRST minimum in span order, which only matters for the sign
+//     of a zero; the reduction carries the position to reproduce even that.
+//
+// The radix sort and the prefix sum are CUB's (a library primitive, like cuBLAS for a plain GEMM); everything
+// else is below.  NaN coordinates have no total order: the caller keeps such scenes on the host builder.
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include <chrono>
+#include <map>
+
+#include "bvh_host.h"
+
+namespace crb {
+namespace {
+
+constexpr int CHUNK = 1024;       // members one warp folds
+constexpr int WARPS_PER_CTA = 8;  // 256 threads
+
+struct DevBox {
+    double lo[3], hi[3];
+};
+static_assert(sizeof(DevBox) == 48, "three 128-bit words");
+
+struct DevNode {  // FlatNode, field for field
+    double lo[3], hi[3];
+    uint32_t left, right, axis, lchild, rchild, skip;
+};
+static_assert(sizeof(DevNode) == sizeof(FlatNode), "the device writes FlatNode records");
+
+struct Seg {
+    uint32_t start, end, at;  // members order[start, end), preorder index of the node; start == end: empty slot
+};
+
+struct Partial {  // fold of one chunk: value and position of the first extremum, per box plane
+    double v[6];
+    uint32_t pos[6];
+};
+
+struct LevelConsts {
+    uint32_t m_hi;      // largest span of the level (spans are m_hi or m_hi - 1)
+    uint32_t nc_hi;     // node_count(m_hi)
+    uint32_t nc_lo;     // node_count(m_hi - 1)
+    uint32_t c0;        // smallest child span of the level
+    uint32_t nc_c0;     // node_count(c0)
+    uint32_t nc_c1;     // node_count(c0 + 1)
+    uint32_t chunks;    // warp tasks per span
+    uint32_t rbits;     // bits of a rank
+};
+
+// f64 -> u64 with the order of partial_cmp; -0.0 and +0.0 compare Equal there, so both map to +0.0's image
+__device__ __forceinline__ uint64_t order_key(double x) {
+    uint64_t b = (uint64_t)__double_as_longlong(x);
+    if ((b << 1) == 0) b = 0;
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+
+__device__ __forceinline__ double shfl_down_f64(double v, int off) { return __shfl_down_sync(0xffffffffu, v, off); }
+
+// lo planes keep the first minimum, hi planes the first maximum (Interval::tight_enclose, utils.rs:631-635,
+// folded left to right from Interval::EMPTY)
+struct Fold {
+    double v[6];
+    uint32_t pos[6];
+    __device__ void init() {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            v[k] = __longlong_as_double(0x7ff0000000000000ll);
+            v[3 + k] = __longlong_as_double(0xfff0000000000000ll);
+            pos[k] = pos[3 + k] = 0xffffffffu;
+        }
+    }
+    __device__ void add(int k, double x, uint32_t p) {  // k < 3: min, else max
+        const bool better = (k < 3) ? (x < v[k]) : (x > v[k]);
+        if (better || (x == v[k] && p < pos[k])) {
+            v[k] = x;
+            pos[k] = p;
+        }
+    }
+    __device__ void warp_reduce() {
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                const double ov = shfl_down_f64(v[k], off);
+                const uint32_t op = __shfl_down_sync(0xffffffffu, pos[k], off);
+                add(k, ov, op);
+            }
+        }
+    }
+};
+
+// Aabb::longest_axis, bvh.rs:82-94
+__device__ __forceinline__ int dev_longest_axis(const double* v) {
+    const double sx = v[3] - v[0], sy = v[4] - v[1], sz = v[5] - v[2];
+    if (sx > sy) return (sx > sz) ? 0 : 2;
+    if (sy > sz) return 1;
+    return 2;
+}
+
+// one node of the level: record, children slots, sort axis
+__device__ void emit_node(uint32_t slot, const Seg seg, const double* v, const LevelConsts lc, const uint32_t* __restrict__ order,
+                          const uint32_t* __restrict__ leafref, DevNode* __restrict__ nodes, Seg* __restrict__ next, uint8_t* __restrict__ seg_axis) {
+    const uint32_t span = seg.end - seg.start;
+    DevNode n;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        n.lo[k] = v[k];
+        n.hi[k] = v[3 + k];
+    }
+    const int axis = dev_longest_axis(v);
+    n.axis = (uint32_t)axis;
+    n.skip = seg.at + (span == lc.m_hi ? lc.nc_hi : lc.nc_lo);
+    n.lchild = n.rchild = REF_NONE;
+    Seg l = {0u, 0u, 0u}, r = {0u, 0u, 0u};
+    uint8_t ax = 0xff;
+    if (span == 1) {
+        n.left = leafref[order[seg.start]];
+        n.right = REF_NONE;
+    } else if (span == 2) {
+        n.left = leafref[order[seg.start]];
+        n.right = leafref[order[seg.start + 1]];
+    } else {
+        const uint32_t mid = seg.start + span / 2;
+        const uint32_t lspan = mid - seg.start;
+        const uint32_t l_at = seg.at + 1;
+        const uint32_t r_at = l_at + (lspan == lc.c0 ? lc.nc_c0 : lc.nc_c1);
+        n.left = n.lchild = l_at;
+        n.right = n.rchild = r_at;
+        l = {seg.start, mid, l_at};
+        r = {mid, seg.end, r_at};
+        ax = (uint8_t)axis;
+    }
+    nodes[seg.at] = n;
+    next[2 * slot] = l;
+    next[2 * slot + 1] = r;
+    seg_axis[slot] = ax;
+}
+
+// warp task (slot, chunk): fold the boxes of order[chunk]; with one chunk per span the node is emitted here
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_bvh_fold(const Seg* __restrict__ segs, uint32_t n_slots, const LevelConsts lc,
+                                                                  const uint32_t* __restrict__ order, const DevBox* __restrict__ boxes,
+                                                                  const uint32_t* __restrict__ leafref, Partial* __restrict__ partials,
+                                                                  DevNode* __restrict__ nodes, Seg* __restrict__ next, uint8_t* __restrict__ seg_axis) {
+    const uint64_t task = (uint64_t)blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
+    const uint32_t lane = threadIdx.x & 31;
+    if (task >= (uint64_t)n_slots * lc.chunks) return;
+    const uint32_t slot = (uint32_t)(task / lc.chunks), chunk = (uint32_t)(task % lc.chunks);
+    const Seg seg = segs[slot];
+    if (seg.start == seg.end) {
+        if (lc.chunks == 1 && lane == 0) {
+            next[2 * slot] = Seg{0u, 0u, 0u};
+            next[2 * slot + 1] = Seg{0u, 0u, 0u};
+            seg_axis[slot] = 0xff;
+        }
+        return;
+    }
+    Fold f;
+    f.init();
+    const uint64_t lo = (uint64_t)seg.start + (uint64_t)chunk * CHUNK;
+    const uint64_t hi = min((uint64_t)seg.end, lo + CHUNK);
+    for (uint64_t p = lo + lane; p < hi; p += 32) {
+        const uint32_t e = order[p];
+        const double2* b = reinterpret_cast<const double2*>(boxes + e);
+        const double2 w0 = __ldg(b), w1 = __ldg(b + 1), w2 = __ldg(b + 2);
+        f.add(0, w0.x, (uint32_t)p);
+        f.add(1, w0.y, (uint32_t)p);
+        f.add(2, w1.x, (uint32_t)p);
+        f.add(3, w1.y, (uint32_t)p);
+        f.add(4, w2.x, (uint32_t)p);
+        f.add(5, w2.y, (uint32_t)p);
+    }
+    f.warp_reduce();
+    if (lane != 0) return;
+    if (lc.chunks == 1) {
+        emit_node(slot, seg, f.v, lc, order, leafref, nodes, next, seg_axis);
+    } else {
+        Partial pr;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            pr.v[k] = f.v[k];
+            pr.pos[k] = f.pos[k];
+        }
+        partials[task] = pr;
+    }
+}
+
+// warp per slot: fold the chunk partials (several chunks per span), emit the node
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_bvh_emit(const Seg* __restrict__ segs, uint32_t n_slots, const LevelConsts lc,
+                                                                  const uint32_t* __restrict__ order, const uint32_t* __restrict__ leafref,
+                                                                  const Partial* __restrict__ partials, DevNode* __restrict__ nodes,
+                                                                  Seg* __restrict__ next, uint8_t* __restrict__ seg_axis) {
+    const uint32_t slot = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
+    const uint32_t lane = threadIdx.x & 31;
+    if (slot >= n_slots) return;
+    const Seg seg = segs[slot];
+    if (seg.start == seg.end) {
+        if (lane == 0) {
+            next[2 * slot] = Seg{0u, 0u, 0u};
+            next[2 * slot + 1] = Seg{0u, 0u, 0u};
+            seg_axis[slot] = 0xff;
+        }
+        return;
+    }
+    Fold f;
+    f.init();
+    const uint32_t used = (seg.end - seg.start + CHUNK - 1) / CHUNK;  // chunks of this span that hold members
+    for (uint32_t c = lane; c < used; c += 32) {
+        const Partial pr = partials[(uint64_t)slot * lc.chunks + c];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) f.add(k, pr.v[k], pr.pos[k]);
+    }
+    f.warp_reduce();
+    if (lane == 0) emit_node(slot, seg, f.v, lc, order, leafref, nodes, next, seg_axis);
+}
+
+// keys of the level's sort: positions outside a splitting span stay where they are
+__global__ void k_bvh_identity_keys(uint64_t* __restrict__ keys, uint32_t n, uint32_t rbits) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n) keys[p] = (uint64_t)p << rbits;
+}
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_bvh_span_keys(const Seg* __restrict__ segs, const uint8_t* __restrict__ seg_axis, uint32_t n_slots,
+                                                                       const LevelConsts lc, const uint32_t* __restrict__ order,
+                                                                       const uint32_t* __restrict__ rank, uint32_t n, uint64_t* __restrict__ keys) {
+    const uint64_t task = (uint64_t)blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
+    const uint32_t lane = threadIdx.x & 31;
+    if (task >= (uint64_t)n_slots * lc.chunks) return;
+    const uint32_t slot = (uint32_t)(task / lc.chunks), chunk = (uint32_t)(task % lc.chunks);
+    const uint32_t axis = seg_axis[slot];
+    if (axis > 2) return;  // empty slot or leaf node
+    const Seg seg = segs[slot];
+    const uint32_t* __restrict__ rk = rank + (uint64_t)axis * n;
+    const uint64_t lo = (uint64_t)seg.start + (uint64_t)chunk * CHUNK;
+    const uint64_t hi = min((uint64_t)seg.end, lo + CHUNK);
+    const uint64_t base = (uint64_t)seg.start << lc.rbits;
+    for (uint64_t p = lo + lane; p < hi; p += 32) keys[p] = base | rk[order[p]];
+}
+
+// ---- dense ranks of bbox.min per axis (once per build) ----
+__global__ void k_bvh_axis_keys(const DevBox* __restrict__ boxes, uint32_t n, int axis, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        keys[i] = order_key(boxes[i].lo[axis]);
+        vals[i] = i;
+    }
+}
+__global__ void k_bvh_heads(const uint64_t* __restrict__ sorted, uint32_t n, uint32_t* __restrict__ head) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) head[j] = (j > 0 && sorted[j] != sorted[j - 1]) ? 1u : 0u;
+}
+__global__ void k_bvh_scatter_rank(const uint32_t* __restrict__ scan, const uint32_t* __restrict__ vals, uint32_t n, uint32_t* __restrict__ rank) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) rank[vals[j]] = scan[j];
+}
+__global__ void k_bvh_iota(uint32_t* __restrict__ a, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = i;
+}
+
+struct NodeCounter {  // node_count with a memo: a level needs at most four sizes, each the half of an earlier one
+    std::map<uint64_t, uint64_t> memo;
+    uint64_t operator()(uint64_t span) {
+        if (span <= 2) return 1;
+        auto it = memo.find(span);
+        if (it != memo.end()) return it->second;
+        const uint64_t v = 1 + (*this)(span / 2) + (*this)(span - span / 2);
+        memo[span] = v;
+        return v;
+    }
+};
+
+struct DeviceBuffers {
+    cudaStream_t stream;
+    std::vector<void*> ptrs;
+    ~DeviceBuffers() {
+        for (void* p : ptrs) cudaFreeAsync(p, stream);
+    }
+    template <typename T>
+    cudaError_t alloc(T** out, size_t count) {
+        void* p = nullptr;
+        cudaError_t e = cudaMallocAsync(&p, (count ? count : 1) * sizeof(T), stream);
+        if (e == cudaSuccess) ptrs.push_back(p);
+        *out = static_cast<T*>(p);
+        return e;
+    }
+};
+
+uint32_t ceil_log2(uint64_t n) {
+    uint32_t b = 0;
+    while (((uint64_t)1 << b) < n) ++b;
+    return b;
+}
+
+}  // namespace
+
+#define BVH_CUDA(call)                                                                  \
+    do {                                                                                \
+        cudaError_t e__ = (call);                                                       \
+        if (e__ != cudaSuccess) {                                                       \
+            err = std::string("bvh device build: " #call ": ") + cudaGetErrorString(e__); \
+            return CR_ERR_CUDA;                                                         \
+        }                                                                               \
+    } while (0)
+
+int gpu_build_bvh(int device, void* cuda_stream, const std::vector<Element>& elements, const std::vector<uint32_t>& visible,
+                  std::vector<FlatNode>& nodes, uint32_t& max_depth, BvhBuildTimes* times, std::string& err) {
+    using clk = std::chrono::steady_clock;
+    const auto t_begin = clk::now();
+    const uint64_t n64 = visible.size();
+    if (n64 == 0) {
+        nodes.clear();
+        max_depth = 0;
+        return CR_OK;
+    }
+    if (n64 > REF_MAX_INDEX) {
+        err = "BVH too large";
+        return CR_ERR_LIMIT;
+    }
+    const uint32_t n = (uint32_t)n64;
+    cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+    BVH_CUDA(cudaSetDevice(device));
+
+    // ---- pack: boxes and leaf references in visible order ----
+    std::vector<DevBox> h_boxes(n);
+    std::vector<uint32_t> h_leaf(n);
+    for (uint32_t i = 0; i < n; ++i) {
+        const Element& e = elements[visible[i]];
+        for (int k = 0; k < 3; ++k) {
+            if (e.box.lo[k] != e.box.lo[k] || e.box.hi[k] != e.box.hi[k]) {
+                err = "NaN box coordinate: box_compare has no total order (use the host builder)";
+                return CR_ERR_INVALID;
+            }
+            h_boxes[i].lo[k] = e.box.lo[k];
+            h_boxes[i].hi[k] = e.box.hi[k];
+        }
+        h_leaf[i] = make_leaf(e.kind, e.idx);
+    }
+    const auto t_packed = clk::now();
+
+    NodeCounter node_count_memo;
+    const uint64_t total_nodes = node_count_memo(n);
+    const uint32_t rbits = ceil_log2(n), sbits = ceil_log2(n);
+    // slots of the widest level: spans halve until they are <= 2
+    uint32_t levels = 1;
+    for (uint64_t m = n; m > 2; m = (m + 1) / 2) ++levels;
+    const uint64_t max_slots = (uint64_t)1 << (levels - 1);
+    const uint64_t max_tasks = 3 * (n64 / CHUNK) + 64;  // only levels with several chunks per span write partials
+
+    DeviceBuffers buf{stream, {}};
+    DevBox* d_boxes;
+    uint32_t *d_leaf, *d_order[2], *d_rank, *d_scan, *d_vals;
+    uint64_t* d_keys[2];
+    DevNode* d_nodes;
+    Seg* d_segs[2];
+    uint8_t* d_axis;
+    Partial* d_partials;
+    void* d_temp;
+    BVH_CUDA(buf.alloc(&d_boxes, n));
+    BVH_CUDA(buf.alloc(&d_leaf, n));
+    BVH_CUDA(buf.alloc(&d_order[0], n));
+    BVH_CUDA(buf.alloc(&d_order[1], n));
+    BVH_CUDA(buf.alloc(&d_rank, (size_t)3 * n));
+    BVH_CUDA(buf.alloc(&d_scan, n));
+    BVH_CUDA(buf.alloc(&d_vals, n));
+    BVH_CUDA(buf.alloc(&d_keys[0], n));
+    BVH_CUDA(buf.alloc(&d_keys[1], n));
+    BVH_CUDA(buf.alloc(&d_nodes, total_nodes));
+    BVH_CUDA(buf.alloc(&d_segs[0], 2 * max_slots));
+    BVH_CUDA(buf.alloc(&d_segs[1], 2 * max_slots));
+    BVH_CUDA(buf.alloc(&d_axis, max_slots));
+    BVH_CUDA(buf.alloc(&d_partials, max_tasks));
+    size_t temp_sort = 0, temp_scan = 0;
+    BVH_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, temp_sort, d_keys[0], d_keys[1], d_order[0], d_order[1], (int64_t)n, 0, 64, stream));
+    BVH_CUDA(cub::DeviceScan::InclusiveSum(nullptr, temp_scan, d_scan, d_scan, (int64_t)n, stream));
+    size_t temp_bytes = std::max(temp_sort, temp_scan);
+    BVH_CUDA(buf.alloc(reinterpret_cast<uint8_t**>(&d_temp), temp_bytes));
+
+    BVH_CUDA(cudaMemcpyAsync(d_boxes, h_boxes.data(), (size_t)n * sizeof(DevBox), cudaMemcpyHostToDevice, stream));
+    BVH_CUDA(cudaMemcpyAsync(d_leaf, h_leaf.data(), (size_t)n * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+    BVH_CUDA(cudaStreamSynchronize(stream));  // h_boxes / h_leaf are pageable: their staging is over here
+    const auto t_h2d = clk::now();
+
+    const uint32_t tpb = 256, grid_n = (n + tpb - 1) / tpb;
+    // ---- dense ranks per axis ----
+    for (int axis = 0; axis < 3; ++axis) {
+        k_bvh_axis_keys<<<grid_n, tpb, 0, stream>>>(d_boxes, n, axis, d_keys[0], d_order[0]);
+        size_t tb = temp_bytes;
+        BVH_CUDA(cub::DeviceRadixSort::SortPairs(d_temp, tb, d_keys[0], d_keys[1], d_order[0], d_vals, (int64_t)n, 0, 64, stream));
+        k_bvh_heads<<<grid_n, tpb, 0, stream>>>(d_keys[1], n, d_scan);
+        tb = temp_bytes;
+        BVH_CUDA(cub::DeviceScan::InclusiveSum(d_temp, tb, d_scan, d_scan, (int64_t)n, stream));
+        k_bvh_scatter_rank<<<grid_n, tpb, 0, stream>>>(d_scan, d_vals, n, d_rank + (size_t)axis * n);
+    }
+    k_bvh_iota<<<grid_n, tpb, 0, stream>>>(d_order[0], n);
+    const Seg root = {0u, n, 0u};
+    BVH_CUDA(cudaMemcpyAsync(d_segs[0], &root, sizeof(Seg), cudaMemcpyHostToDevice, stream));
+    BVH_CUDA(cudaGetLastError());
+
+    // ---- levels ----
+    int cur = 0, ord = 0;
+    uint64_t n_slots = 1, m_hi = n;
+    uint32_t depth = 0;
+    for (;;) {
+        ++depth;
+        LevelConsts lc;
+        lc.m_hi = (uint32_t)m_hi;
+        lc.nc_hi = (uint32_t)node_count_memo(m_hi);
+        lc.nc_lo = (uint32_t)node_count_memo(m_hi - 1);
+        lc.c0 = (uint32_t)((m_hi - 1) / 2);
+        lc.nc_c0 = (uint32_t)node_count_memo(lc.c0);
+        lc.nc_c1 = (uint32_t)node_count_memo((uint64_t)lc.c0 + 1);
+        lc.chunks = (uint32_t)((m_hi + CHUNK - 1) / CHUNK);
+        lc.rbits = rbits;
+        const uint64_t tasks = n_slots * lc.chunks;
+        const uint32_t grid_tasks = (uint32_t)((tasks + WARPS_PER_CTA - 1) / WARPS_PER_CTA);
+        k_bvh_fold<<<grid_tasks, WARPS_PER_CTA * 32, 0, stream>>>(d_segs[cur], (uint32_t)n_slots, lc, d_order[ord], d_boxes, d_leaf, d_partials, d_nodes,
+                                                                  d_segs[cur ^ 1], d_axis);
+        if (lc.chunks > 1) {
+            const uint32_t grid_slots = (uint32_t)((n_slots + WARPS_PER_CTA - 1) / WARPS_PER_CTA);
+            k_bvh_emit<<<grid_slots, WARPS_PER_CTA * 32, 0, stream>>>(d_segs[cur], (uint32_t)n_slots, lc, d_order[ord], d_leaf, d_partials, d_nodes,
+                                                                      d_segs[cur ^ 1], d_axis);
+        }
+        if (m_hi <= 2) break;
+        k_bvh_identity_keys<<<grid_n, tpb, 0, stream>>>(d_keys[0], n, rbits);
+        k_bvh_span_keys<<<grid_tasks, WARPS_PER_CTA * 32, 0, stream>>>(d_segs[cur], d_axis, (uint32_t)n_slots, lc, d_order[ord], d_rank, n, d_keys[0]);
+        size_t tb = temp_bytes;
+        BVH_CUDA(cub::DeviceRadixSort::SortPairs(d_temp, tb, d_keys[0], d_keys[1], d_order[ord], d_order[ord ^ 1], (int64_t)n, 0, (int)(rbits + sbits), stream));
+        ord ^= 1;
+        cur ^= 1;
+        n_slots *= 2;
+        m_hi = (m_hi + 1) / 2;
+    }
+    BVH_CUDA(cudaGetLastError());
+    BVH_CUDA(cudaStreamSynchronize(stream));
+    const auto t_built = clk::now();
+
+    nodes.resize((size_t)total_nodes);
+    BVH_CUDA(cudaMemcpyAsync(static_cast<void*>(nodes.data()), d_nodes, (size_t)total_nodes * sizeof(DevNode), cudaMemcpyDeviceToHost, stream));
+    BVH_CUDA(cudaStreamSynchronize(stream));
+    max_depth = depth;
+    const auto t_end = clk::now();
+    if (times) {
+        auto ms = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+        times->ms_pack = ms(t_begin, t_packed);
+        times->ms_h2d = ms(t_packed, t_h2d);
+        times->ms_device = ms(t_h2d, t_built);
+        times->ms_d2h = ms(t_built, t_end);
+        times->levels = depth;
+    }
+    return CR_OK;
+}
+
+}  // namespace crb

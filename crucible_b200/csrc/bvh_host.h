@@ -1,0 +1,82 @@
+// bvh_host.h — host-side BVH build types shared by the C-ABI layer (api.cu: the reference-order host builder)
+// and the device builder (bvh_build.cu).  Geometry in reference arithmetic (src/objects/bvh.rs, bvhwrapper.rs).
+#pragma once
+#include <cstdint>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace crb {
+
+static const double INF = std::numeric_limits<double>::infinity();
+
+// ---- host geometry in reference arithmetic (this file is compiled with -ffp-contract=off) ---------
+struct Box {  // Aabb, src/objects/bvh.rs:19-34; default = EMPTY intervals
+    double lo[3] = {INF, INF, INF};
+    double hi[3] = {-INF, -INF, -INF};
+};
+// Aabb::new_from_boxes / Interval::tight_enclose, bvh.rs:69-75, utils.rs:631-635
+inline Box box_union(const Box& a, const Box& b) {
+    Box r;
+    for (int k = 0; k < 3; ++k) {
+        r.lo[k] = (a.lo[k] <= b.lo[k]) ? a.lo[k] : b.lo[k];
+        r.hi[k] = (a.hi[k] >= b.hi[k]) ? a.hi[k] : b.hi[k];
+    }
+    return r;
+}
+// Aabb::new_from_points, bvh.rs:46-66
+inline Box box_from_points(const double a[3], const double b[3]) {
+    Box r;
+    for (int k = 0; k < 3; ++k) {
+        if (a[k] <= b[k]) {
+            r.lo[k] = a[k];
+            r.hi[k] = b[k];
+        } else {
+            r.lo[k] = b[k];
+            r.hi[k] = a[k];
+        }
+    }
+    return r;
+}
+// Aabb::longest_axis, bvh.rs:82-94
+inline int longest_axis(const Box& b) {
+    const double sx = b.hi[0] - b.lo[0], sy = b.hi[1] - b.lo[1], sz = b.hi[2] - b.lo[2];
+    if (sx > sy) return (sx > sz) ? 0 : 2;
+    if (sy > sz) return 1;
+    return 2;
+}
+
+struct Element {  // one entry of Scene.elements (scene/mod.rs:77), insertion order
+    uint32_t kind, idx;
+    bool hide;
+    Box box;
+};
+
+struct FlatNode {
+    Box box;
+    uint32_t left, right, axis;  // children: node indices, or primitive refs for a leaf node
+    uint32_t lchild, rchild;     // node children (REF_NONE for a leaf node)
+    uint32_t skip;               // preorder index of the first node after this subtree
+};
+
+
+// number of nodes BVHWrapper::help_generate creates for a span (bvhwrapper.rs:46-80)
+inline uint64_t node_count(uint64_t span) {
+    if (span <= 2) return 1;
+    return 1 + node_count(span / 2) + node_count(span - span / 2);
+}
+
+struct BvhBuildTimes {  // wall-clock milliseconds of the phases of one device build
+    double ms_pack = 0, ms_h2d = 0, ms_device = 0, ms_d2h = 0;
+    uint32_t levels = 0;
+};
+
+// Device build of the SAME tree (bvh_build.cu): level-synchronous median split, one stable radix sort per level.
+// `nodes` is resized to node_count(visible.size()) and filled in preorder; returns CR_OK or an error code
+// (CR_ERR_INVALID when a box coordinate is NaN: box_compare has no total order then, the host builder handles it).
+int gpu_build_bvh(int device, void* cuda_stream, const std::vector<Element>& elements, const std::vector<uint32_t>& visible,
+                  std::vector<FlatNode>& nodes, uint32_t& max_depth, BvhBuildTimes* times, std::string& err);
+
+}  // namespace crb

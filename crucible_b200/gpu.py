@@ -16,7 +16,7 @@ from .scene import Scene, SceneDesc
 
 
 class GpuScene:
-    def __init__(self, desc: SceneDesc, device: int = 0):
+    def __init__(self, desc: SceneDesc, device: int = 0, bvh_builder: int = abi.CR_BVH_AUTO):
         self.lib = abi.load()
         self.device = device
         self.handle = self.lib.cr_scene_create(device)
@@ -24,6 +24,7 @@ class GpuScene:
             raise abi.CrucibleError(abi.CR_ERR_NO_DEVICE, self.lib.cr_last_error().decode())
         self.desc = desc
         try:
+            abi.check(self.lib.cr_scene_set_bvh_builder(self.handle, int(bvh_builder)))
             desc.apply(self.lib, self.handle, "cr_")
         except Exception:
             self.close()
@@ -57,6 +58,18 @@ class GpuScene:
         out = np.empty(n, np.int32)
         abi.check(self.lib.cr_scene_bvh_leaf_order(self.handle, out.ctypes.data_as(C.c_void_p), n))
         return out
+
+    def bvh_nodes(self):
+        """The committed BVH in preorder as a structured array (abi.BVH_NODE_DTYPE)."""
+        n = abi.check(self.lib.cr_scene_bvh_nodes(self.handle, None, 0))
+        out = np.zeros(n, dtype=abi.BVH_NODE_DTYPE)
+        abi.check(self.lib.cr_scene_bvh_nodes(self.handle, out.ctypes.data_as(C.c_void_p), n))
+        return out
+
+    def commit_info(self):
+        ci = abi.CrCommitInfo()
+        abi.check(self.lib.cr_scene_commit_info(self.handle, C.byref(ci)))
+        return ci.as_dict()
 
     # ---- Hittables::hit on a ray batch
     def trace_batch(self, rays, tmin=0.001, tmax=float("inf"), precision=abi.CR_PRECISION_F64):

@@ -222,9 +222,40 @@ typedef struct CrAnimKey {
  * leaves its first box can only be hit through that box.  Quads (extension) are not animated. */
 int cr_scene_set_keyframes(CrScene*, size_t prim_index, int point, const CrAnimKey* keys, size_t n);
 
-/* BVHWrapper::new_wrapper (bvhwrapper.rs:15-94) reproduced on the host, then flattened
+/* Where cr_scene_commit builds the BVH.  Both builders produce the SAME tree as
+ * BVHWrapper::help_generate (bvhwrapper.rs:46-94): same nodes in the same preorder, boxes bit for bit.
+ *   HOST   : the recursion as written (stable sort per span), host threads for the top levels;
+ *   DEVICE : level-synchronous build on the scene's GPU (one stable radix sort per tree level);
+ *   AUTO   : DEVICE for scenes with a device and >= 32768 visible primitives, HOST otherwise.
+ * (box_compare's NaN -> Equal branch, bvhwrapper.rs:92, is unreachable: non-finite coordinates are rejected
+ * when primitives are added.)
+ * CR_BVH_DEVICE on a scene without a device fails with CR_ERR_NO_DEVICE at commit. */
+typedef enum CrBvhBuilder { CR_BVH_AUTO = 0, CR_BVH_HOST = 1, CR_BVH_DEVICE = 2 } CrBvhBuilder;
+int cr_scene_set_bvh_builder(CrScene*, int builder);
+
+/* BVHWrapper::new_wrapper (bvhwrapper.rs:15-94) reproduced (see CrBvhBuilder), then flattened
  * and uploaded.  Must be called after the last edit and before trace/render. */
 int cr_scene_commit(CrScene*);
+/* Wall-clock breakdown of the last cr_scene_commit (milliseconds). */
+typedef struct CrCommitInfo {
+    int32_t builder;   /* CR_BVH_HOST or CR_BVH_DEVICE: the builder that ran */
+    uint32_t levels;   /* tree depth */
+    double ms_total;   /* whole commit */
+    double ms_build;   /* BVH build (DEVICE: pack + h2d + device + d2h below) */
+    double ms_pack, ms_h2d, ms_device, ms_d2h; /* DEVICE builder phases; 0 for HOST */
+    double ms_upload;  /* flatten to device records + H2D of the scene */
+} CrCommitInfo;
+int cr_scene_commit_info(const CrScene*, CrCommitInfo* out);
+/* One node of the committed BVH in preorder (tests compare the two builders bit for bit). */
+typedef struct CrBvhNode {
+    double lo[3], hi[3];  /* Aabb of the node (bvh.rs:19-23) */
+    uint32_t left, right; /* inner node: preorder indices of the children; leaf node: bit31 | kind << 29 | index
+                             of the primitive within its kind (right = 0x7FFFFFFF for a span-1 node) */
+    uint32_t axis;        /* longest axis of the box = sort axis (bvhwrapper.rs:52) */
+    uint32_t skip;        /* preorder index of the first node after this subtree */
+} CrBvhNode;
+/* Copies min(cap, n_nodes) nodes; returns n_nodes. */
+int64_t cr_scene_bvh_nodes(const CrScene*, CrBvhNode* out, size_t cap);
 /* Introspection of the committed BVH (tests): node count, max depth, leaf order. */
 int cr_scene_bvh_info(const CrScene*, uint64_t* n_nodes, uint32_t* max_depth, uint64_t* n_visible);
 /* DFS leaf order of the committed BVH as prim_index values (cap entries at most). */
