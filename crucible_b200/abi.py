@@ -109,6 +109,7 @@ SIGNATURES = {
     "cr_scene_commit": (C.c_int, [_P]),
     "cr_scene_commit_info": (C.c_int, [_P, C.POINTER(CrCommitInfo)]),
     "cr_scene_bvh_nodes": (C.c_int64, [_P, _P, C.c_size_t]),
+    "cr_scene_device_records": (C.c_int64, [_P, C.c_int, _P, C.c_size_t]),
     "cr_scene_bvh_info": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]),
     "cr_scene_bvh_leaf_order": (C.c_int64, [_P, _P, C.c_size_t]),
     "cr_trace_batch": (C.c_int, [_P, _P, C.c_size_t, C.c_double, C.c_double, C.c_int, _P]),

@@ -67,6 +67,9 @@ struct CrScene {
     uint64_t n_visible = 0;
     int bvh_builder = CR_BVH_AUTO;
     CrCommitInfo commit_info = {};
+    // device-built tree: FlatNode records on the device; `nodes` is then filled on demand (host_nodes)
+    void* d_flat_nodes = nullptr;
+    uint64_t n_nodes = 0;
     // device
     SceneDeviceData dev;
     std::vector<void*> dev_allocs;
@@ -76,6 +79,10 @@ struct CrScene {
     void* d_io = nullptr;  // trace_batch staging
     size_t io_cap = 0;
 
+    void free_flat_tree() {
+        if (d_flat_nodes) cudaFreeAsync(d_flat_nodes, stream);
+        d_flat_nodes = nullptr;
+    }
     void free_device_scene() {
         for (void* p : dev_allocs) cudaFreeAsync(p, stream);
         dev_allocs.clear();
@@ -239,7 +246,7 @@ int upload_scene(CrScene* s) {
     s->free_device_scene();
     SceneDeviceData& d = s->dev;
     d.num_sms = s->num_sms;
-    d.n_nodes = (uint32_t)s->nodes.size();
+    d.n_nodes = (uint32_t)s->n_nodes;
     d.n_prims[0] = (uint32_t)(s->spheres.size() / 4);
     d.n_prims[1] = (uint32_t)(s->tris.size() / 9);
     d.n_prims[2] = (uint32_t)(s->quads.size() / 9);
@@ -254,7 +261,19 @@ int upload_scene(CrScene* s) {
                 if (m.emit[k] > d.max_radiance) d.max_radiance = m.emit[k];
         }
     // nodes
-    {
+    if (s->d_flat_nodes) {
+        // device-built tree: the same flattening as below, by kernels (bvh_build.cu)
+        void *p64 = nullptr, *p32 = nullptr;
+        API_CUDA(cudaMallocAsync(&p64, s->n_nodes * sizeof(NodeRec<double>), s->stream));
+        s->dev_allocs.push_back(p64);
+        API_CUDA(cudaMallocAsync(&p32, s->n_nodes * sizeof(NodeRec<float>), s->stream));
+        s->dev_allocs.push_back(p32);
+        std::string err;
+        const int rc = gpu_flatten_nodes(s->device, s->stream, s->d_flat_nodes, s->n_nodes, p64, p32, &d.bmax, &d.bsmall, err);
+        if (rc != CR_OK) return fail(rc, err);
+        d.nodes[0] = p64;
+        d.nodes[1] = p32;
+    } else {
         std::vector<NodeRec<double>> n64(s->nodes.size());
         std::vector<NodeRec<float>> n32(s->nodes.size());
         for (size_t i = 0; i < s->nodes.size(); ++i) {
@@ -313,7 +332,19 @@ int upload_scene(CrScene* s) {
         if ((rc = upload(s, b, &d.spheres[1])) != CR_OK) return rc;
     }
     // triangles: a, e1 = b - a, e2 = c - a (triangle.rs:99-100; x - y == x + (-y) bit for bit)
-    {
+    if (s->commit_info.builder == CR_BVH_DEVICE && !s->tris.empty()) {
+        const size_t n = s->tris.size() / 9;
+        void *p64 = nullptr, *p32 = nullptr;
+        API_CUDA(cudaMallocAsync(&p64, n * sizeof(TriRec<double>), s->stream));
+        s->dev_allocs.push_back(p64);
+        API_CUDA(cudaMallocAsync(&p32, n * sizeof(TriRec<float>), s->stream));
+        s->dev_allocs.push_back(p32);
+        std::string err;
+        const int rc = gpu_flatten_tris(s->device, s->stream, s->tris.data(), n, p64, p32, err);
+        if (rc != CR_OK) return fail(rc, err);
+        d.tris[0] = p64;
+        d.tris[1] = p32;
+    } else {
         const size_t n = s->tris.size() / 9;
         std::vector<TriRec<double>> a(n);
         std::vector<TriRec<float>> b(n);
@@ -369,14 +400,18 @@ int upload_scene(CrScene* s) {
         if ((rc = upload(s, b, &d.quads[1])) != CR_OK) return rc;
     }
     // per-primitive metadata
+    std::vector<int32_t> kind_of_mat(s->mats.size());
+    for (size_t i = 0; i < s->mats.size(); ++i) {
+        const CrMaterial& cm = s->mats[i];
+        kind_of_mat[i] = cm.kind | ((cm.kind == CR_MAT_LAMBERTIAN && tex_needs_uv(s, cm.tex)) ? MATKIND_NEEDS_UV : 0);
+    }
     for (int k = 0; k < 3; ++k) {
         std::vector<PrimMeta> m(s->mat_of[k].size());
         for (size_t i = 0; i < m.size(); ++i) {
             m[i].material = s->mat_of[k][i];
             m[i].prim_index = s->prim_of[k][i];
             m[i].obj_id = s->obj_of[k][i];
-            const CrMaterial& cm = s->mats[(size_t)m[i].material];
-            m[i].mat_kind = cm.kind | ((cm.kind == CR_MAT_LAMBERTIAN && tex_needs_uv(s, cm.tex)) ? MATKIND_NEEDS_UV : 0);
+            m[i].mat_kind = kind_of_mat[(size_t)m[i].material];
         }
         void* p = nullptr;
         int rc = upload(s, m, &p);
@@ -594,6 +629,7 @@ void cr_scene_destroy(CrScene* s) {
     if (s->device >= 0) {
         cudaSetDevice(s->device);
         s->free_device_scene();
+        s->free_flat_tree();
         if (s->d_out_rgb) cudaFreeAsync(s->d_out_rgb, s->stream);
         if (s->d_out_rgb8) cudaFreeAsync(s->d_out_rgb8, s->stream);
         if (s->d_io) cudaFreeAsync(s->d_io, s->stream);
@@ -731,6 +767,11 @@ int cr_scene_commit(CrScene* s) {
         if (!s->elements[i].hide) visible.push_back(i);
     s->n_visible = visible.size();
     s->nodes.clear();
+    s->n_nodes = 0;
+    if (s->device >= 0) {
+        API_CUDA(cudaSetDevice(s->device));
+        s->free_flat_tree();
+    }
     s->root = REF_MISS;
     s->max_depth = 0;
     using clk = std::chrono::steady_clock;
@@ -739,44 +780,38 @@ int cr_scene_commit(CrScene* s) {
     s->commit_info = CrCommitInfo{};
     s->commit_info.builder = CR_BVH_HOST;
     if (s->bvh_builder == CR_BVH_DEVICE && s->device < 0) return fail(CR_ERR_NO_DEVICE, "CR_BVH_DEVICE needs a scene created on a CUDA device");
+    // DEVICE: tree build, record flattening and triangle set-up run as kernels; HOST: on the host, as written
+    const bool on_device = s->bvh_builder == CR_BVH_DEVICE || (s->bvh_builder == CR_BVH_AUTO && s->device >= 0 && visible.size() >= 32768);
+    if (on_device) s->commit_info.builder = CR_BVH_DEVICE;
     if (!visible.empty()) {
         const uint64_t nn = node_count(visible.size());
         if (nn > REF_MAX_INDEX) return fail(CR_ERR_LIMIT, "BVH too large");
-        bool on_device = s->bvh_builder == CR_BVH_DEVICE || (s->bvh_builder == CR_BVH_AUTO && s->device >= 0 && visible.size() >= 32768);
         if (on_device) {
             BvhBuildTimes bt;
             std::string err;
-            rc = gpu_build_bvh(s->device, s->stream, s->elements, visible, s->nodes, s->max_depth, &bt, err);
-            if (rc == CR_ERR_INVALID && s->bvh_builder == CR_BVH_AUTO) {
-                on_device = false;  // NaN coordinates: only the recursion as written defines the result
-            } else if (rc != CR_OK) {
-                s->nodes.clear();
-                return fail(rc, err);
-            } else {
-                s->commit_info.builder = CR_BVH_DEVICE;
-                s->commit_info.ms_pack = bt.ms_pack;
-                s->commit_info.ms_h2d = bt.ms_h2d;
-                s->commit_info.ms_device = bt.ms_device;
-                s->commit_info.ms_d2h = bt.ms_d2h;
-            }
-        }
-        if (!on_device) {
+            rc = gpu_build_bvh(s->device, s->stream, s->elements, visible, &s->d_flat_nodes, &s->n_nodes, s->max_depth, &bt, err);
+            if (rc != CR_OK) return fail(rc, err);
+            s->commit_info.ms_pack = bt.ms_pack;
+            s->commit_info.ms_h2d = bt.ms_h2d;
+            s->commit_info.ms_device = bt.ms_device;
+        } else {
             s->nodes.resize((size_t)nn);
+            s->n_nodes = nn;
             Builder b{*s, visible, s->nodes};
             s->max_depth = b.build(0, visible.size(), 0, 4);
+            // new_from_vec (bvhwrapper.rs:34-44): the root box is re-derived from its two children
+            FlatNode& r = s->nodes[0];
+            auto child_box = [&](uint32_t ref) -> Box {
+                if (ref_is_leaf(ref)) return s->elements[(size_t)s->prim_of[ref_kind(ref)][ref_index(ref)]].box;
+                return s->nodes[ref].box;
+            };
+            const Box lb = child_box(r.left);
+            const Box rb = (r.right == REF_NONE) ? lb : child_box(r.right);
+            r.box = box_union(lb, rb);
         }
+        s->root = 0;
         s->commit_info.levels = s->max_depth;
         s->commit_info.ms_build = ms_since(t_commit);
-        // new_from_vec (bvhwrapper.rs:34-44): the root box is re-derived from its two children
-        FlatNode& r = s->nodes[0];
-        auto child_box = [&](uint32_t ref) -> Box {
-            if (ref_is_leaf(ref)) return s->elements[(size_t)s->prim_of[ref_kind(ref)][ref_index(ref)]].box;
-            return s->nodes[ref].box;
-        };
-        const Box lb = child_box(r.left);
-        const Box rb = (r.right == REF_NONE) ? lb : child_box(r.right);
-        r.box = box_union(lb, rb);
-        s->root = 0;
     }
     s->committed = true;
     if (s->device >= 0) {
@@ -806,8 +841,20 @@ int cr_scene_commit_info(const CrScene* s, CrCommitInfo* out) {
     return CR_OK;
 }
 
+// host copy of the tree; a device-built tree is fetched the first time somebody looks at it
+static int host_nodes(const CrScene* cs) {
+    CrScene* s = const_cast<CrScene*>(cs);
+    if (!s->d_flat_nodes || s->nodes.size() == s->n_nodes) return CR_OK;
+    std::string err;
+    const int rc = gpu_fetch_flat_nodes(s->device, s->stream, s->d_flat_nodes, s->n_nodes, s->nodes, err);
+    return rc == CR_OK ? rc : fail(rc, err);
+}
+
 int64_t cr_scene_bvh_nodes(const CrScene* s, CrBvhNode* out, size_t cap) {
     if (!s || !s->committed) return fail(CR_ERR_STATE, "scene not committed");
+    if (!out || !cap) return (int64_t)s->n_nodes;
+    const int rc = host_nodes(s);
+    if (rc != CR_OK) return rc;
     const size_t n = std::min(cap, s->nodes.size());
     for (size_t i = 0; out && i < n; ++i) {
         const FlatNode& f = s->nodes[i];
@@ -824,9 +871,28 @@ int64_t cr_scene_bvh_nodes(const CrScene* s, CrBvhNode* out, size_t cap) {
     return (int64_t)s->nodes.size();
 }
 
+int64_t cr_scene_device_records(const CrScene* s, int which, void* out, size_t cap_bytes) {
+    if (!s || !s->committed) return fail(CR_ERR_STATE, "scene not committed");
+    if (s->device < 0) return fail(CR_ERR_NO_DEVICE, "the scene has no device copy");
+    if (which < 0 || which > 3) return fail(CR_ERR_INVALID, "which: 0 nodes f64, 1 nodes f32, 2 triangles f64, 3 triangles f32");
+    const size_t n_tris = s->tris.size() / 9;
+    const size_t bytes = which == 0   ? s->n_nodes * sizeof(NodeRec<double>)
+                         : which == 1 ? s->n_nodes * sizeof(NodeRec<float>)
+                         : which == 2 ? n_tris * sizeof(TriRec<double>)
+                                      : n_tris * sizeof(TriRec<float>);
+    const void* src = which < 2 ? s->dev.nodes[which] : s->dev.tris[which - 2];
+    const size_t n = std::min(bytes, cap_bytes);
+    if (out && n && src) {
+        API_CUDA(cudaSetDevice(s->device));
+        API_CUDA(cudaMemcpyAsync(out, src, n, cudaMemcpyDeviceToHost, s->stream));
+        API_CUDA(cudaStreamSynchronize(s->stream));
+    }
+    return (int64_t)bytes;
+}
+
 int cr_scene_bvh_info(const CrScene* s, uint64_t* n_nodes, uint32_t* max_depth, uint64_t* n_visible) {
     if (!s || !s->committed) return fail(CR_ERR_STATE, "scene not committed");
-    if (n_nodes) *n_nodes = s->nodes.size();
+    if (n_nodes) *n_nodes = s->n_nodes;
     if (max_depth) *max_depth = s->max_depth;
     if (n_visible) *n_visible = s->n_visible;
     return CR_OK;
@@ -836,6 +902,8 @@ int64_t cr_scene_bvh_leaf_order(const CrScene* s, int32_t* out, size_t cap) {
     if (!s || !s->committed) return fail(CR_ERR_STATE, "scene not committed");
     // preorder array + "left before right" == DFS leaf order; span-1 nodes list their primitive twice
     // in the reference (left == right), which this enumeration reproduces for comparison with the oracle
+    const int rc_nodes = host_nodes(s);
+    if (rc_nodes != CR_OK) return rc_nodes;
     std::vector<int32_t> order;
     std::vector<uint32_t> stack;
     if (s->root != REF_MISS) stack.push_back(s->root);

@@ -273,6 +273,108 @@ __global__ void k_bvh_iota(uint32_t* __restrict__ a, uint32_t n) {
     if (i < n) a[i] = i;
 }
 
+
+struct DevElement {  // Element (bvh_host.h), field for field: the staging array goes to the device as it is
+    uint32_t kind, idx;
+    uint8_t hide, pad[7];
+    double lo[3], hi[3];
+};
+static_assert(sizeof(DevElement) == sizeof(Element) && sizeof(Element) == 64, "Element is uploaded raw");
+
+// boxes and leaf references in visible order (`visible` == nullptr: nothing is hidden)
+__global__ void k_bvh_gather(const DevElement* __restrict__ el, const uint32_t* __restrict__ visible, uint32_t n, DevBox* __restrict__ boxes,
+                             uint32_t* __restrict__ leafref) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const DevElement e = el[visible ? visible[i] : i];
+    DevBox b;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        b.lo[k] = e.lo[k];
+        b.hi[k] = e.hi[k];
+    }
+    boxes[i] = b;
+    leafref[i] = make_leaf(e.kind, e.idx);
+}
+
+// BVHWrapper::new_from_vec (bvhwrapper.rs:34-44): the root box is re-derived from its two children
+// (Aabb::new_from_boxes on two boxes: `<=` / `>=` keep the LEFT operand on a tie)
+__global__ void k_bvh_root_box(DevNode* __restrict__ nodes, const uint32_t* __restrict__ order, const DevBox* __restrict__ boxes) {
+    DevNode r = nodes[0];
+    double l[6], q[6];
+    if (ref_is_leaf(r.left)) {
+        const DevBox a = boxes[order[0]];
+        const DevBox b = (r.right == REF_NONE) ? a : boxes[order[1]];
+        for (int k = 0; k < 3; ++k) {
+            l[k] = a.lo[k]; l[3 + k] = a.hi[k];
+            q[k] = b.lo[k]; q[3 + k] = b.hi[k];
+        }
+    } else {
+        const DevNode a = nodes[r.left], b = nodes[r.right];
+        for (int k = 0; k < 3; ++k) {
+            l[k] = a.lo[k]; l[3 + k] = a.hi[k];
+            q[k] = b.lo[k]; q[3 + k] = b.hi[k];
+        }
+    }
+    for (int k = 0; k < 3; ++k) {
+        nodes[0].lo[k] = (l[k] <= q[k]) ? l[k] : q[k];
+        nodes[0].hi[k] = (l[3 + k] >= q[3 + k]) ? l[3 + k] : q[3 + k];
+    }
+}
+
+// ---- flatten: FlatNode -> the trace kernels' records (what upload_scene does on the host for host-built trees) ----
+// per-node |coordinate| bound, rounded up to f32
+__global__ void k_node_bound(const DevNode* __restrict__ nodes, uint32_t n, float* __restrict__ nb) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double bm = 0.0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) bm = fmax(bm, fmax(fabs(nodes[i].lo[k]), fabs(nodes[i].hi[k])));
+    nb[i] = __double2float_ru(bm);
+}
+__global__ void k_flatten_nodes(const DevNode* __restrict__ nodes, const float* __restrict__ nb, uint32_t n, float bsmall,
+                                NodeRec<double>* __restrict__ n64, NodeRec<float>* __restrict__ n32) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const DevNode f = nodes[i];
+    // device words: inner = (skip link, axis), leaf node = (left primitive, right primitive); bit 27 = BIGBOX_BIT
+    const bool leafnode = ref_is_leaf(f.left);
+    const uint32_t big = nb[i] > bsmall ? (1u << 27) : 0u;
+    NodeRec<double> a;
+    a.xmin = f.lo[0]; a.xmax = f.hi[0];
+    a.ymin = f.lo[1]; a.ymax = f.hi[1];
+    a.zmin = f.lo[2]; a.zmax = f.hi[2];
+    a.left = (leafnode ? f.left : f.skip) | big;
+    a.right = leafnode ? f.right : f.axis;
+    a.pad0 = a.pad1 = 0;
+    NodeRec<float> b;  // boxes rounded OUTWARD
+    b.xmin = __double2float_rd(f.lo[0]); b.xmax = __double2float_ru(f.hi[0]);
+    b.ymin = __double2float_rd(f.lo[1]); b.ymax = __double2float_ru(f.hi[1]);
+    b.zmin = __double2float_rd(f.lo[2]); b.zmax = __double2float_ru(f.hi[2]);
+    b.left = a.left;
+    b.right = a.right;
+    n64[i] = a;
+    n32[i] = b;
+}
+// triangles: a, e1 = b - a, e2 = c - a (triangle.rs:99-100); the f32 record is the rounded f64 one
+__global__ void k_flatten_tris(const double* __restrict__ abc, uint32_t n, TriRec<double>* __restrict__ t64, TriRec<float>* __restrict__ t32) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double* p = abc + (size_t)9 * i;
+    TriRec<double> t;
+    t.ax = p[0]; t.ay = p[1]; t.az = p[2];
+    t.e1x = p[3] - p[0]; t.e1y = p[4] - p[1]; t.e1z = p[5] - p[2];
+    t.e2x = p[6] - p[0]; t.e2y = p[7] - p[1]; t.e2z = p[8] - p[2];
+    t.pad = 0.0;
+    TriRec<float> u;
+    u.ax = (float)t.ax; u.ay = (float)t.ay; u.az = (float)t.az;
+    u.e1x = (float)t.e1x; u.e1y = (float)t.e1y; u.e1z = (float)t.e1z;
+    u.e2x = (float)t.e2x; u.e2y = (float)t.e2y; u.e2z = (float)t.e2z;
+    u.pad0 = u.pad1 = u.pad2 = 0.f;
+    t64[i] = t;
+    t32[i] = u;
+}
+
 struct NodeCounter {  // node_count with a memo: a level needs at most four sizes, each the half of an earlier one
     std::map<uint64_t, uint64_t> memo;
     uint64_t operator()(uint64_t span) {
@@ -319,15 +421,14 @@ uint32_t ceil_log2(uint64_t n) {
     } while (0)
 
 int gpu_build_bvh(int device, void* cuda_stream, const std::vector<Element>& elements, const std::vector<uint32_t>& visible,
-                  std::vector<FlatNode>& nodes, uint32_t& max_depth, BvhBuildTimes* times, std::string& err) {
+                  void** d_nodes_out, uint64_t* n_nodes_out, uint32_t& max_depth, BvhBuildTimes* times, std::string& err) {
     using clk = std::chrono::steady_clock;
     const auto t_begin = clk::now();
     const uint64_t n64 = visible.size();
-    if (n64 == 0) {
-        nodes.clear();
-        max_depth = 0;
-        return CR_OK;
-    }
+    *d_nodes_out = nullptr;
+    *n_nodes_out = 0;
+    max_depth = 0;
+    if (n64 == 0) return CR_OK;
     if (n64 > REF_MAX_INDEX) {
         err = "BVH too large";
         return CR_ERR_LIMIT;
@@ -335,23 +436,6 @@ int gpu_build_bvh(int device, void* cuda_stream, const std::vector<Element>& ele
     const uint32_t n = (uint32_t)n64;
     cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
     BVH_CUDA(cudaSetDevice(device));
-
-    // ---- pack: boxes and leaf references in visible order ----
-    std::vector<DevBox> h_boxes(n);
-    std::vector<uint32_t> h_leaf(n);
-    for (uint32_t i = 0; i < n; ++i) {
-        const Element& e = elements[visible[i]];
-        for (int k = 0; k < 3; ++k) {
-            if (e.box.lo[k] != e.box.lo[k] || e.box.hi[k] != e.box.hi[k]) {
-                err = "NaN box coordinate: box_compare has no total order (use the host builder)";
-                return CR_ERR_INVALID;
-            }
-            h_boxes[i].lo[k] = e.box.lo[k];
-            h_boxes[i].hi[k] = e.box.hi[k];
-        }
-        h_leaf[i] = make_leaf(e.kind, e.idx);
-    }
-    const auto t_packed = clk::now();
 
     NodeCounter node_count_memo;
     const uint64_t total_nodes = node_count_memo(n);
@@ -363,14 +447,18 @@ int gpu_build_bvh(int device, void* cuda_stream, const std::vector<Element>& ele
     const uint64_t max_tasks = 3 * (n64 / CHUNK) + 64;  // only levels with several chunks per span write partials
 
     DeviceBuffers buf{stream, {}};
+    DevElement* d_elements;
     DevBox* d_boxes;
-    uint32_t *d_leaf, *d_order[2], *d_rank, *d_scan, *d_vals;
+    uint32_t *d_visible = nullptr, *d_leaf, *d_order[2], *d_rank, *d_scan, *d_vals;
     uint64_t* d_keys[2];
-    DevNode* d_nodes;
+    DevNode* d_nodes = nullptr;
     Seg* d_segs[2];
     uint8_t* d_axis;
     Partial* d_partials;
     void* d_temp;
+    const bool all_visible = visible.size() == elements.size();
+    BVH_CUDA(buf.alloc(&d_elements, elements.size()));
+    if (!all_visible) BVH_CUDA(buf.alloc(&d_visible, n));
     BVH_CUDA(buf.alloc(&d_boxes, n));
     BVH_CUDA(buf.alloc(&d_leaf, n));
     BVH_CUDA(buf.alloc(&d_order[0], n));
@@ -380,7 +468,6 @@ int gpu_build_bvh(int device, void* cuda_stream, const std::vector<Element>& ele
     BVH_CUDA(buf.alloc(&d_vals, n));
     BVH_CUDA(buf.alloc(&d_keys[0], n));
     BVH_CUDA(buf.alloc(&d_keys[1], n));
-    BVH_CUDA(buf.alloc(&d_nodes, total_nodes));
     BVH_CUDA(buf.alloc(&d_segs[0], 2 * max_slots));
     BVH_CUDA(buf.alloc(&d_segs[1], 2 * max_slots));
     BVH_CUDA(buf.alloc(&d_axis, max_slots));
@@ -390,13 +477,26 @@ int gpu_build_bvh(int device, void* cuda_stream, const std::vector<Element>& ele
     BVH_CUDA(cub::DeviceScan::InclusiveSum(nullptr, temp_scan, d_scan, d_scan, (int64_t)n, stream));
     size_t temp_bytes = std::max(temp_sort, temp_scan);
     BVH_CUDA(buf.alloc(reinterpret_cast<uint8_t**>(&d_temp), temp_bytes));
+    // the result outlives this call (the caller owns it)
+    BVH_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_nodes), total_nodes * sizeof(DevNode), stream));
+    struct NodesGuard {
+        DevNode*& p;
+        cudaStream_t st;
+        bool keep = false;
+        ~NodesGuard() {
+            if (!keep && p) cudaFreeAsync(p, st);
+        }
+    } guard{d_nodes, stream};
+    const auto t_alloc = clk::now();
 
-    BVH_CUDA(cudaMemcpyAsync(d_boxes, h_boxes.data(), (size_t)n * sizeof(DevBox), cudaMemcpyHostToDevice, stream));
-    BVH_CUDA(cudaMemcpyAsync(d_leaf, h_leaf.data(), (size_t)n * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
-    BVH_CUDA(cudaStreamSynchronize(stream));  // h_boxes / h_leaf are pageable: their staging is over here
+    // the staging arrays go up as they are (pageable: the copies return once the bytes are staged)
+    BVH_CUDA(cudaMemcpyAsync(d_elements, elements.data(), elements.size() * sizeof(Element), cudaMemcpyHostToDevice, stream));
+    if (!all_visible) BVH_CUDA(cudaMemcpyAsync(d_visible, visible.data(), (size_t)n * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+    const uint32_t tpb = 256, grid_n = (n + tpb - 1) / tpb;
+    k_bvh_gather<<<grid_n, tpb, 0, stream>>>(d_elements, d_visible, n, d_boxes, d_leaf);
+    BVH_CUDA(cudaStreamSynchronize(stream));
     const auto t_h2d = clk::now();
 
-    const uint32_t tpb = 256, grid_n = (n + tpb - 1) / tpb;
     // ---- dense ranks per axis ----
     for (int axis = 0; axis < 3; ++axis) {
         k_bvh_axis_keys<<<grid_n, tpb, 0, stream>>>(d_boxes, n, axis, d_keys[0], d_order[0]);
@@ -446,23 +546,79 @@ int gpu_build_bvh(int device, void* cuda_stream, const std::vector<Element>& ele
         n_slots *= 2;
         m_hi = (m_hi + 1) / 2;
     }
+    k_bvh_root_box<<<1, 1, 0, stream>>>(d_nodes, d_order[ord], d_boxes);
     BVH_CUDA(cudaGetLastError());
     BVH_CUDA(cudaStreamSynchronize(stream));
     const auto t_built = clk::now();
 
-    nodes.resize((size_t)total_nodes);
-    BVH_CUDA(cudaMemcpyAsync(static_cast<void*>(nodes.data()), d_nodes, (size_t)total_nodes * sizeof(DevNode), cudaMemcpyDeviceToHost, stream));
-    BVH_CUDA(cudaStreamSynchronize(stream));
+    guard.keep = true;
+    *d_nodes_out = d_nodes;
+    *n_nodes_out = total_nodes;
     max_depth = depth;
-    const auto t_end = clk::now();
     if (times) {
         auto ms = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
-        times->ms_pack = ms(t_begin, t_packed);
-        times->ms_h2d = ms(t_packed, t_h2d);
+        times->ms_pack = ms(t_begin, t_alloc);
+        times->ms_h2d = ms(t_alloc, t_h2d);
         times->ms_device = ms(t_h2d, t_built);
-        times->ms_d2h = ms(t_built, t_end);
+        times->ms_d2h = 0.0;
         times->levels = depth;
     }
+    return CR_OK;
+}
+
+int gpu_fetch_flat_nodes(int device, void* cuda_stream, const void* d_nodes, uint64_t n, std::vector<FlatNode>& out, std::string& err) {
+    cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+    BVH_CUDA(cudaSetDevice(device));
+    out.resize((size_t)n);
+    if (n == 0) return CR_OK;
+    BVH_CUDA(cudaMemcpyAsync(static_cast<void*>(out.data()), d_nodes, (size_t)n * sizeof(DevNode), cudaMemcpyDeviceToHost, stream));
+    BVH_CUDA(cudaStreamSynchronize(stream));
+    return CR_OK;
+}
+
+int gpu_flatten_nodes(int device, void* cuda_stream, const void* d_flat, uint64_t n64, void* d_n64, void* d_n32, float* bmax, float* bsmall,
+                      std::string& err) {
+    cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+    BVH_CUDA(cudaSetDevice(device));
+    *bmax = *bsmall = 0.f;
+    if (n64 == 0) return CR_OK;
+    const uint32_t n = (uint32_t)n64;
+    const uint32_t tpb = 256, grid_n = (n + tpb - 1) / tpb;
+    DeviceBuffers buf{stream, {}};
+    float *d_nb, *d_sorted;
+    void* d_temp;
+    BVH_CUDA(buf.alloc(&d_nb, n));
+    BVH_CUDA(buf.alloc(&d_sorted, n));
+    size_t temp_bytes = 0;
+    BVH_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, temp_bytes, d_nb, d_sorted, (int64_t)n, 0, 32, stream));
+    BVH_CUDA(buf.alloc(reinterpret_cast<uint8_t**>(&d_temp), temp_bytes));
+    const DevNode* flat = static_cast<const DevNode*>(d_flat);
+    k_node_bound<<<grid_n, tpb, 0, stream>>>(flat, n, d_nb);
+    BVH_CUDA(cub::DeviceRadixSort::SortKeys(d_temp, temp_bytes, d_nb, d_sorted, (int64_t)n, 0, 32, stream));
+    // the ~90 % smallest bounds share the tight filter constant, the rest get BIGBOX_BIT (as upload_scene does on the host)
+    const size_t k90 = (size_t)((n - 1) * 0.9);
+    float picks[2];
+    BVH_CUDA(cudaMemcpyAsync(&picks[0], d_sorted + k90, sizeof(float), cudaMemcpyDeviceToHost, stream));
+    BVH_CUDA(cudaMemcpyAsync(&picks[1], d_sorted + (n - 1), sizeof(float), cudaMemcpyDeviceToHost, stream));
+    BVH_CUDA(cudaStreamSynchronize(stream));
+    *bsmall = picks[0];
+    *bmax = picks[1];
+    k_flatten_nodes<<<grid_n, tpb, 0, stream>>>(flat, d_nb, n, *bsmall, static_cast<NodeRec<double>*>(d_n64), static_cast<NodeRec<float>*>(d_n32));
+    BVH_CUDA(cudaGetLastError());
+    return CR_OK;
+}
+
+int gpu_flatten_tris(int device, void* cuda_stream, const double* h_abc, uint64_t n64, void* d_t64, void* d_t32, std::string& err) {
+    cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+    BVH_CUDA(cudaSetDevice(device));
+    if (n64 == 0) return CR_OK;
+    const uint32_t n = (uint32_t)n64;
+    DeviceBuffers buf{stream, {}};
+    double* d_abc;
+    BVH_CUDA(buf.alloc(&d_abc, (size_t)9 * n));
+    BVH_CUDA(cudaMemcpyAsync(d_abc, h_abc, (size_t)9 * n * sizeof(double), cudaMemcpyHostToDevice, stream));
+    k_flatten_tris<<<(n + 255) / 256, 256, 0, stream>>>(d_abc, n, static_cast<TriRec<double>*>(d_t64), static_cast<TriRec<float>*>(d_t32));
+    BVH_CUDA(cudaGetLastError());
     return CR_OK;
 }
 

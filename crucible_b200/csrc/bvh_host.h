@@ -74,9 +74,16 @@ struct BvhBuildTimes {  // wall-clock milliseconds of the phases of one device b
 };
 
 // Device build of the SAME tree (bvh_build.cu): level-synchronous median split, one stable radix sort per level.
-// `nodes` is resized to node_count(visible.size()) and filled in preorder; returns CR_OK or an error code
-// (CR_ERR_INVALID when a box coordinate is NaN: box_compare has no total order then, the host builder handles it).
+// The FlatNode records stay ON THE DEVICE (*d_nodes, node_count(visible.size()) entries in preorder, root box already
+// re-derived as BVHWrapper::new_from_vec does); the caller owns the allocation (cudaFreeAsync on the same stream).
 int gpu_build_bvh(int device, void* cuda_stream, const std::vector<Element>& elements, const std::vector<uint32_t>& visible,
-                  std::vector<FlatNode>& nodes, uint32_t& max_depth, BvhBuildTimes* times, std::string& err);
+                  void** d_nodes, uint64_t* n_nodes, uint32_t& max_depth, BvhBuildTimes* times, std::string& err);
+// introspection: copies the device tree to the host
+int gpu_fetch_flat_nodes(int device, void* cuda_stream, const void* d_nodes, uint64_t n, std::vector<FlatNode>& out, std::string& err);
+// FlatNode (device) -> NodeRec<double> / NodeRec<float> (outward-rounded boxes, BIGBOX bit); returns the two filter bounds
+int gpu_flatten_nodes(int device, void* cuda_stream, const void* d_flat, uint64_t n, void* d_n64, void* d_n32, float* bmax, float* bsmall,
+                      std::string& err);
+// a,b,c (host, [n][9]) -> TriRec<double> / TriRec<float> on the device
+int gpu_flatten_tris(int device, void* cuda_stream, const double* h_abc, uint64_t n, void* d_t64, void* d_t32, std::string& err);
 
 }  // namespace crb

@@ -66,6 +66,13 @@ class GpuScene:
         abi.check(self.lib.cr_scene_bvh_nodes(self.handle, out.ctypes.data_as(C.c_void_p), n))
         return out
 
+    def device_records(self, which):
+        """Raw bytes of the flattened device records (0/1 = nodes f64/f32, 2/3 = triangles f64/f32)."""
+        n = abi.check(self.lib.cr_scene_device_records(self.handle, which, None, 0))
+        out = np.zeros(n, np.uint8)
+        abi.check(self.lib.cr_scene_device_records(self.handle, which, out.ctypes.data_as(C.c_void_p), n))
+        return out
+
     def commit_info(self):
         ci = abi.CrCommitInfo()
         abi.check(self.lib.cr_scene_commit_info(self.handle, C.byref(ci)))

@@ -256,6 +256,11 @@ typedef struct CrBvhNode {
 } CrBvhNode;
 /* Copies min(cap, n_nodes) nodes; returns n_nodes. */
 int64_t cr_scene_bvh_nodes(const CrScene*, CrBvhNode* out, size_t cap);
+/* The flattened records the trace kernels read, copied back from the device (tests compare the host and the
+ * device flattening byte for byte).  which: 0 = nodes f64 (64 B each: xmin,xmax,ymin,ymax,zmin,zmax, two words,
+ * padding), 1 = nodes f32 (32 B: the boxes rounded outward, the same two words), 2 = triangles f64 (80 B:
+ * a, e1 = b-a, e2 = c-a, padding), 3 = triangles f32 (48 B).  Copies min(cap_bytes, total); returns total bytes. */
+int64_t cr_scene_device_records(const CrScene*, int which, void* out, size_t cap_bytes);
 /* Introspection of the committed BVH (tests): node count, max depth, leaf order. */
 int cr_scene_bvh_info(const CrScene*, uint64_t* n_nodes, uint32_t* max_depth, uint64_t* n_visible);
 /* DFS leaf order of the committed BVH as prim_index values (cap entries at most). */

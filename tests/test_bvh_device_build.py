@@ -100,6 +100,10 @@ def assert_same_tree(desc, device):
             assert not len(bad), f"{len(bad)} boxes differ in {f}, first at {bad[0]}: host {a[f][bad[0]]} device {b[f][bad[0]]}"
         raise AssertionError("node arrays differ in padding only?")
     assert np.array_equal(host.bvh_leaf_order(), dev.bvh_leaf_order())
+    # what the trace kernels read: nodes (f64, outward-rounded f32, BIGBOX bits) and triangle records, flattened by
+    # the host loop for the host builder and by kernels for the device builder
+    for which in range(4):
+        assert np.array_equal(host.device_records(which), dev.device_records(which)), f"device records {which} differ"
     host.close()
     dev.close()
 
