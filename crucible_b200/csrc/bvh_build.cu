@@ -60,7 +60,8 @@ struct LevelConsts {
     uint32_t c0;        // smallest child span of the level
     uint32_t nc_c0;     // node_count(c0)
     uint32_t nc_c1;     // node_count(c0 + 1)
-    uint32_t chunks;    // warp tasks per span
+    uint32_t chunks;    // (span, chunk) tasks per span
+    uint32_t group;     // lanes that share one task: 32, or the power of two >= m_hi for the small spans of the deep levels
     uint32_t rbits;     // bits of a rank
 };
 
@@ -70,8 +71,6 @@ __device__ __forceinline__ uint64_t order_key(double x) {
     if ((b << 1) == 0) b = 0;
     return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
 }
-
-__device__ __forceinline__ double shfl_down_f64(double v, int off) { return __shfl_down_sync(0xffffffffu, v, off); }
 
 // lo planes keep the first minimum, hi planes the first maximum (Interval::tight_enclose, utils.rs:631-635,
 // folded left to right from Interval::EMPTY)
@@ -93,14 +92,17 @@ struct Fold {
             pos[k] = p;
         }
     }
-    __device__ void warp_reduce() {
+    // reduction over groups of `group` consecutive lanes (a power of two); the result is in the group's first lane
+    __device__ void group_reduce(uint32_t group) {
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) {
+            if ((uint32_t)off < group) {  // warp-uniform
 #pragma unroll
-            for (int k = 0; k < 6; ++k) {
-                const double ov = shfl_down_f64(v[k], off);
-                const uint32_t op = __shfl_down_sync(0xffffffffu, pos[k], off);
-                add(k, ov, op);
+                for (int k = 0; k < 6; ++k) {
+                    const double ov = __shfl_down_sync(0xffffffffu, v[k], off, group);
+                    const uint32_t op = __shfl_down_sync(0xffffffffu, pos[k], off, group);
+                    add(k, ov, op);
+                }
             }
         }
     }
@@ -153,41 +155,48 @@ __device__ void emit_node(uint32_t slot, const Seg seg, const double* v, const L
     seg_axis[slot] = ax;
 }
 
-// warp task (slot, chunk): fold the boxes of order[chunk]; with one chunk per span the node is emitted here
+// task (slot, chunk), run by `group` lanes: fold the boxes of order[chunk]; with one chunk per span the node is emitted here
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_bvh_fold(const Seg* __restrict__ segs, uint32_t n_slots, const LevelConsts lc,
                                                                   const uint32_t* __restrict__ order, const DevBox* __restrict__ boxes,
                                                                   const uint32_t* __restrict__ leafref, Partial* __restrict__ partials,
                                                                   DevNode* __restrict__ nodes, Seg* __restrict__ next, uint8_t* __restrict__ seg_axis) {
-    const uint64_t task = (uint64_t)blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
-    const uint32_t lane = threadIdx.x & 31;
-    if (task >= (uint64_t)n_slots * lc.chunks) return;
-    const uint32_t slot = (uint32_t)(task / lc.chunks), chunk = (uint32_t)(task % lc.chunks);
-    const Seg seg = segs[slot];
-    if (seg.start == seg.end) {
-        if (lc.chunks == 1 && lane == 0) {
+    const uint32_t group = lc.group, per_warp = 32u / group;
+    const uint64_t warp_id = (uint64_t)blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
+    const uint32_t lane = threadIdx.x & 31, sub = lane & (group - 1u);
+    const uint64_t n_tasks = (uint64_t)n_slots * lc.chunks;
+    if (warp_id * per_warp >= n_tasks) return;  // the whole warp (the shuffles below need every lane of a live warp)
+    const uint64_t task = warp_id * per_warp + lane / group;
+    const bool live = task < n_tasks;
+    const uint32_t slot = live ? (uint32_t)(task / lc.chunks) : 0u, chunk = live ? (uint32_t)(task % lc.chunks) : 0u;
+    const Seg seg = live ? segs[slot] : Seg{0u, 0u, 0u};
+    const bool empty = seg.start == seg.end;
+    Fold f;
+    f.init();
+    if (!empty) {
+        const uint64_t lo = (uint64_t)seg.start + (uint64_t)chunk * CHUNK;
+        const uint64_t hi = min((uint64_t)seg.end, lo + CHUNK);
+        for (uint64_t p = lo + sub; p < hi; p += group) {
+            const uint32_t e = order[p];
+            const double2* b = reinterpret_cast<const double2*>(boxes + e);
+            const double2 w0 = __ldg(b), w1 = __ldg(b + 1), w2 = __ldg(b + 2);
+            f.add(0, w0.x, (uint32_t)p);
+            f.add(1, w0.y, (uint32_t)p);
+            f.add(2, w1.x, (uint32_t)p);
+            f.add(3, w1.y, (uint32_t)p);
+            f.add(4, w2.x, (uint32_t)p);
+            f.add(5, w2.y, (uint32_t)p);
+        }
+    }
+    f.group_reduce(group);
+    if (sub != 0u || !live) return;
+    if (empty) {
+        if (lc.chunks == 1) {
             next[2 * slot] = Seg{0u, 0u, 0u};
             next[2 * slot + 1] = Seg{0u, 0u, 0u};
             seg_axis[slot] = 0xff;
         }
         return;
     }
-    Fold f;
-    f.init();
-    const uint64_t lo = (uint64_t)seg.start + (uint64_t)chunk * CHUNK;
-    const uint64_t hi = min((uint64_t)seg.end, lo + CHUNK);
-    for (uint64_t p = lo + lane; p < hi; p += 32) {
-        const uint32_t e = order[p];
-        const double2* b = reinterpret_cast<const double2*>(boxes + e);
-        const double2 w0 = __ldg(b), w1 = __ldg(b + 1), w2 = __ldg(b + 2);
-        f.add(0, w0.x, (uint32_t)p);
-        f.add(1, w0.y, (uint32_t)p);
-        f.add(2, w1.x, (uint32_t)p);
-        f.add(3, w1.y, (uint32_t)p);
-        f.add(4, w2.x, (uint32_t)p);
-        f.add(5, w2.y, (uint32_t)p);
-    }
-    f.warp_reduce();
-    if (lane != 0) return;
     if (lc.chunks == 1) {
         emit_node(slot, seg, f.v, lc, order, leafref, nodes, next, seg_axis);
     } else {
@@ -226,7 +235,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_bvh_emit(const Seg* __re
 #pragma unroll
         for (int k = 0; k < 6; ++k) f.add(k, pr.v[k], pr.pos[k]);
     }
-    f.warp_reduce();
+    f.group_reduce(32u);
     if (lane == 0) emit_node(slot, seg, f.v, lc, order, leafref, nodes, next, seg_axis);
 }
 
@@ -238,8 +247,10 @@ __global__ void k_bvh_identity_keys(uint64_t* __restrict__ keys, uint32_t n, uin
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_bvh_span_keys(const Seg* __restrict__ segs, const uint8_t* __restrict__ seg_axis, uint32_t n_slots,
                                                                        const LevelConsts lc, const uint32_t* __restrict__ order,
                                                                        const uint32_t* __restrict__ rank, uint32_t n, uint64_t* __restrict__ keys) {
-    const uint64_t task = (uint64_t)blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
-    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t group = lc.group, per_warp = 32u / group;
+    const uint64_t warp_id = (uint64_t)blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
+    const uint32_t lane = threadIdx.x & 31, sub = lane & (group - 1u);
+    const uint64_t task = warp_id * per_warp + lane / group;
     if (task >= (uint64_t)n_slots * lc.chunks) return;
     const uint32_t slot = (uint32_t)(task / lc.chunks), chunk = (uint32_t)(task % lc.chunks);
     const uint32_t axis = seg_axis[slot];
@@ -249,7 +260,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_bvh_span_keys(const Seg*
     const uint64_t lo = (uint64_t)seg.start + (uint64_t)chunk * CHUNK;
     const uint64_t hi = min((uint64_t)seg.end, lo + CHUNK);
     const uint64_t base = (uint64_t)seg.start << lc.rbits;
-    for (uint64_t p = lo + lane; p < hi; p += 32) keys[p] = base | rk[order[p]];
+    for (uint64_t p = lo + sub; p < hi; p += group) keys[p] = base | rk[order[p]];
 }
 
 // ---- dense ranks of bbox.min per axis (once per build) ----
@@ -526,9 +537,12 @@ int gpu_build_bvh(int device, void* cuda_stream, const std::vector<Element>& ele
         lc.nc_c0 = (uint32_t)node_count_memo(lc.c0);
         lc.nc_c1 = (uint32_t)node_count_memo((uint64_t)lc.c0 + 1);
         lc.chunks = (uint32_t)((m_hi + CHUNK - 1) / CHUNK);
+        lc.group = 32;
+        while (lc.group > 2 && lc.group / 2 >= m_hi) lc.group /= 2;  // deep levels: several small spans per warp
         lc.rbits = rbits;
         const uint64_t tasks = n_slots * lc.chunks;
-        const uint32_t grid_tasks = (uint32_t)((tasks + WARPS_PER_CTA - 1) / WARPS_PER_CTA);
+        const uint64_t warps = (tasks + 32 / lc.group - 1) / (32 / lc.group);
+        const uint32_t grid_tasks = (uint32_t)((warps + WARPS_PER_CTA - 1) / WARPS_PER_CTA);
         k_bvh_fold<<<grid_tasks, WARPS_PER_CTA * 32, 0, stream>>>(d_segs[cur], (uint32_t)n_slots, lc, d_order[ord], d_boxes, d_leaf, d_partials, d_nodes,
                                                                   d_segs[cur ^ 1], d_axis);
         if (lc.chunks > 1) {

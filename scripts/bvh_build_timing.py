@@ -10,19 +10,23 @@ import numpy as np
 from crucible_b200 import abi, demo_builder
 from crucible_b200.gpu import GpuScene
 
-for copies in [int(a) for a in sys.argv[1:]] or [30, 1582]:
+DEVICE_ONLY = "--device-only" in sys.argv  # profiling runs: skip the host builder and the comparison
+for copies in [int(a) for a in sys.argv[1:] if not a.startswith("--")] or [30, 1582]:
     grid = max(2, int(np.ceil(np.sqrt(copies))))
     sc = demo_builder.instanced_teapots(copies=copies, grid=grid)
     desc = sc.describe()
     out = {"copies": copies, "prims": desc.n_prims}
     trees = {}
-    for name, mode in (("device", abi.CR_BVH_DEVICE), ("host", abi.CR_BVH_HOST), ("device_again", abi.CR_BVH_DEVICE)):
+    modes = (("device", abi.CR_BVH_DEVICE), ("host", abi.CR_BVH_HOST), ("device_again", abi.CR_BVH_DEVICE))
+    for name, mode in modes[:1] if DEVICE_ONLY else modes:
         t0 = time.time()
         gs = GpuScene(desc, 0, bvh_builder=mode)
         out[name] = {k: round(v, 2) if isinstance(v, float) else v for k, v in gs.commit_info().items()}
         out[name]["wall_s_incl_staging"] = round(time.time() - t0, 2)
         out["bvh"] = gs.bvh_info()
-        trees[name] = gs.bvh_nodes()
+        if not DEVICE_ONLY:
+            trees[name] = gs.bvh_nodes()
         gs.close()
-    out["equal"] = bool(trees["device"].tobytes() == trees["host"].tobytes() == trees["device_again"].tobytes())
+    if not DEVICE_ONLY:
+        out["equal"] = bool(trees["device"].tobytes() == trees["host"].tobytes() == trees["device_again"].tobytes())
     print(json.dumps(out), flush=True)
