@@ -650,18 +650,23 @@ struct Trav {
     bool ok;          // the ray is regular and representable in f32: the cheap node step may be used
 
     __device__ __forceinline__ int walk_state() const { return ok ? (int)ST_NODE : (int)ST_EXACT; }
-    __device__ __forceinline__ void init_from(const FilterRay& f, R tmax) {
+    // Box tests of INNER nodes are pure culling (for regular rays).  IEEE subtraction, multiplication, min and max are
+    // monotone, a child's box lies inside its parent's exactly (Aabb::new_from_boxes is an exact min / max) and the
+    // running closest t only shrinks, so whenever the reference's Aabb::hit (bvh.rs:96-132) fails on a node it fails on
+    // every node of its subtree, for the interval of that moment and for every later one.  The primitives the reference
+    // tests are therefore exactly those of the LEAF nodes whose own box passes at the moment DFS order reaches them;
+    // what happens at inner nodes only decides how much work is skipped.  Two consequences used below:
+    //   - the root of a tree with more than one node is not tested at all (the walk starts at its left child);
+    //   - an inner node the f32 filter cannot decide is entered without the exact f64 test (step_node).
+    // Irregular rays (zero / NaN / inf components) keep the reference's test at every node.
+    __device__ __forceinline__ void init_from(const FilterRay& f, R tmax, uint32_t n_nodes) {
         nr.set(f);
         ok = f.ok;
         store.set_pre(f);
         store.set_best(tmax, REF_MISS);
         best32 = (float)tmax;
-        i = 0;
+        i = (f.ok && n_nodes > 1u) ? 1u : 0u;
         wa = wb = REF_NONE;
-    }
-    __device__ __forceinline__ void init(V3<R> o, V3<R> d, R tmin, R tmax, float bsmall, float bmax) {
-        const V3<R> inv = {R(1) / d.x, R(1) / d.y, R(1) / d.z};  // adinv, bvh.rs:111
-        init_from(make_filter_ray<R>(o, d, inv, tmin, tmax, bsmall, bmax), tmax);
     }
     // the box test of node i (words wa, wb) has been decided
     template <bool KNOWN_OK>
@@ -680,8 +685,8 @@ struct Trav {
         bool hit;
         if constexpr (sizeof(R) == 8) {
             const int dec = filter_box(nf, nr, (float)tmin, best32);
-            if (dec == 0) return ST_EXACT;
-            hit = dec > 0;
+            if (dec == 0 && ref_is_leaf(wa)) return ST_EXACT;  // only a leaf node's decision selects primitives
+            hit = dec >= 0;
         } else {
             float lo, hi;
             slab32(nf, nr, tmin, best32, lo, hi);
@@ -816,7 +821,7 @@ __device__ __forceinline__ void trace_persistent(const DevScene<R>& sc, R tmin, 
                         tv.store.set_my(k);
                         V3<R> o, d;
                         io.load(k, o, d);  // the R-precision ray of the exact / leaf steps goes to the lane's slot
-                        tv.init_from(io.filter(k, tmin, tmax), tmax);
+                        tv.init_from(io.filter(k, tmin, tmax), tmax, sc.n_nodes);
                         tv.store.set_ray(o, d);
                         if constexpr (ANIM) tv.store.set_time(io.time(k));
                         st = (sc.n_nodes == 0u) ? (int)ST_DONE : tv.walk_state();
@@ -866,7 +871,7 @@ __device__ __forceinline__ void trace_warp_batch(const DevScene<R>& sc, R tmin, 
     int st = ST_DONE;
     if (active) {
         const V3<R> inv = {R(1) / d.x, R(1) / d.y, R(1) / d.z};  // adinv, bvh.rs:111
-        tv.init_from(make_filter_ray<R>(o, d, inv, tmin, tmax, sc.bsmall, sc.bmax), tmax);
+        tv.init_from(make_filter_ray<R>(o, d, inv, tmin, tmax, sc.bsmall, sc.bmax), tmax, sc.n_nodes);
         tv.store.set_ray(o, d);
         if constexpr (ANIM) tv.store.set_time(tm);
         st = (sc.n_nodes == 0u) ? (int)ST_DONE : tv.walk_state();
