@@ -216,3 +216,83 @@ def test_rng_stream_is_counter_based(oracle):
     assert np.all((a >= 0) & (a < 1))
     u = oracle.rng_stream(1, 0, 0, 0, 200000)
     assert abs(u.mean() - 0.5) < 0.005 and abs(u.var() - 1 / 12) < 0.002
+
+
+# ---- the lemma behind the trace kernel's culling: Aabb::hit is monotone under box containment ----
+
+def _regular_ray(rng):
+    o = (rng.random(3) * 2 - 1) * 10.0 ** rng.integers(-3, 4)
+    d = (rng.random(3) * 2 - 1) * 10.0 ** rng.integers(-9, 10, 3)
+    d[d == 0.0] = 1e-300
+    return o, d
+
+
+def test_aabb_hit_is_monotone_under_containment(oracle):
+    """If the reference's box test (bvh.rs:96-132) fails on a box it fails on every box inside it, for the same or a
+    smaller tmax: subtraction, multiplication, min and max are monotone in IEEE arithmetic.  This is what allows the
+    trace kernel to treat inner-node tests as pure culling."""
+    rng = np.random.Generator(np.random.Philox(key=11))
+    checked = fails = 0
+    for case in range(20000):
+        o, d = _regular_ray(rng)
+        c = o + (rng.random(3) * 2 - 1) * 10.0 ** rng.integers(-2, 3)
+        half = rng.random(3) * 10.0 ** rng.integers(-6, 3)
+        plo, phi = c - half, c + half
+        mode = case % 4
+        if mode == 0:  # origin exactly on a parent plane, or one ulp either side of it
+            k = int(rng.integers(0, 3))
+            o[k] = [plo[k], phi[k], np.nextafter(plo[k], -np.inf), np.nextafter(phi[k], np.inf)][int(rng.integers(0, 4))]
+        # child: a sub-box (sometimes sharing planes with the parent, sometimes flat)
+        a, b = rng.random(3), rng.random(3)
+        clo = plo + (phi - plo) * np.minimum(a, b) * (rng.random(3) < 0.8)
+        chi = np.where(rng.random(3) < 0.2, phi, plo + (phi - plo) * np.maximum(a, b))
+        clo, chi = np.maximum(clo, plo), np.minimum(np.maximum(chi, clo), phi)
+        assert np.all(clo >= plo) and np.all(chi <= phi) and np.all(clo <= chi)
+        tmax_p = math.inf if rng.random() < 0.3 else float(rng.random() * 10.0 ** rng.integers(-2, 4))
+        tmax_c = tmax_p if rng.random() < 0.5 else float(tmax_p * rng.random()) if math.isfinite(tmax_p) else float(rng.random() * 100)
+        ray = (*o, *d, 0.0)
+        parent = oracle.aabb_hit((plo[0], phi[0], plo[1], phi[1], plo[2], phi[2]), ray, 0.001, tmax_p)
+        child = oracle.aabb_hit((clo[0], chi[0], clo[1], chi[1], clo[2], chi[2]), ray, 0.001, tmax_c)
+        assert parent or not child, f"case {case}: the parent box fails but a box inside it passes"
+        checked += 1
+        fails += not parent
+    assert fails > checked // 10  # the property is exercised: plenty of failing parents
+
+
+def test_closest_hit_needs_only_the_leaf_node_boxes(crlib, oracle):
+    """Consequence of the lemma: walking the LEAF nodes of the reference tree in DFS order and testing only their own
+    boxes (no inner node at all) gives the reference's closest hit, bit for bit."""
+    from scenes_util import random_scene, scene_bounds
+    from conftest import random_rays
+    from crucible_b200.gpu import GpuScene
+
+    d = random_scene(60, 80, 10, seed=21)
+    nodes = GpuScene(d, device=-1).bvh_nodes()
+    prims = {k: np.concatenate([b[1] for b in d.batches if b[0] == k]) for k in (0, 1, 2) if any(b[0] == k for b in d.batches)}
+    prim_index, n = {}, 0
+    counters = {0: 0, 1: 0, 2: 0}
+    for kind, data, _, _ in d.batches:
+        for _ in range(len(data)):
+            prim_index[(kind, counters[kind])] = n
+            counters[kind] += 1
+            n += 1
+    leaves = [nd for nd in nodes if nd["left"] & 0x80000000]
+    lo, hi = scene_bounds(d)
+    rays = random_rays(150, lo, hi, 5)
+    exp = oracle.OracleScene(d).trace_batch(rays)
+    for ray, e in zip(rays, exp):
+        best, win = math.inf, -1
+        for nd in leaves:
+            box = (nd["lo"][0], nd["hi"][0], nd["lo"][1], nd["hi"][1], nd["lo"][2], nd["hi"][2])
+            if not oracle.aabb_hit(box, tuple(ray), 0.001, best):
+                continue
+            for ref in (int(nd["left"]), int(nd["right"])):
+                if ref == 0x7FFFFFFF:
+                    continue
+                kind, idx = (ref >> 29) & 3, ref & 0x07FFFFFF
+                got, h = oracle.prim_hit(kind, tuple(prims[kind][idx]), tuple(ray), 0.001, best)
+                if got:
+                    best, win = float(h["t"]), prim_index[(kind, idx)]
+        assert win == e["prim_index"]
+        if win >= 0:
+            assert best == e["t"]
