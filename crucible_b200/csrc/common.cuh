@@ -125,6 +125,10 @@ struct DevScene {
     int32_t clamp_colors;  // 1 = reference Color semantics; 0 when the scene holds an Emissive (extension)
     int32_t node_slice;    // box tests per lane between two exact/leaf phases of the trace engine
     int32_t min_node_lanes;  // a node slice ends early when fewer lanes than this still have a cheap step
+    // an inner node the f32 filter cannot decide is entered untested (Trav::step_node) if its subtree has at most
+    // free_pass_nodes nodes, or if the box is wider than free_pass_k error bands in ray parameter on every axis
+    uint32_t free_pass_nodes;
+    float free_pass_k;
 };
 
 // ---- in-flight path record --------------------------------------------------------------------

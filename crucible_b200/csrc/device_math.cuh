@@ -530,6 +530,23 @@ __device__ __forceinline__ int filter_box(const NodeRec<float>& n, const F& f, f
     if (diff < -E) return -1;
     return 0;  // also NaN / inf
 }
+// Is the box, in ray parameter, wider on every axis than k times the filter's error band?  Then the band only matters
+// where the ray grazes the box's boundary and the ambiguity does not repeat in all of its descendants (rare path of
+// step_node: recomputes the planes instead of keeping them live in the node loop).
+template <typename F>
+__device__ __forceinline__ bool box_wider_than_band(const NodeRec<float>& n, const F& f, float tmin, float best, float k) {
+    const float nx = __fmaf_rn(n.xmin, f.ax0, __fmaf_rn(n.xmax, f.ax1, -f.oix));
+    const float fx = __fmaf_rn(n.xmax, f.ax0, __fmaf_rn(n.xmin, f.ax1, -f.oix));
+    const float ny = __fmaf_rn(n.ymin, f.ay0, __fmaf_rn(n.ymax, f.ay1, -f.oiy));
+    const float fy = __fmaf_rn(n.ymax, f.ay0, __fmaf_rn(n.ymin, f.ay1, -f.oiy));
+    const float nz = __fmaf_rn(n.zmin, f.az0, __fmaf_rn(n.zmax, f.az1, -f.oiz));
+    const float fz = __fmaf_rn(n.zmax, f.az0, __fmaf_rn(n.zmin, f.az1, -f.oiz));
+    const float lo = fmaxf(fmaxf(nx, ny), fmaxf(nz, tmin));
+    const float hi = fminf(fminf(fx, fy), fminf(fz, best));
+    const float E = __fmaf_rn(fabsf(lo) + fabsf(hi), 4.7683716e-7f, (n.left & BIGBOX_BIT) ? f.e_big : f.e_small);
+    const float w = fminf(fminf(fx - nx, fy - ny), fz - nz);
+    return E * k < w;  // false for NaN
+}
 // The part of a FilterRay the sphere pre-filter needs (kept out of the node loop's registers).
 struct PreRay {
     float ox, oy, oz, dx, dy, dz, o2;
@@ -657,7 +674,7 @@ struct Trav {
     // tests are therefore exactly those of the LEAF nodes whose own box passes at the moment DFS order reaches them;
     // what happens at inner nodes only decides how much work is skipped.  Two consequences used below:
     //   - the root of a tree with more than one node is not tested at all (the walk starts at its left child);
-    //   - an inner node the f32 filter cannot decide is entered without the exact f64 test (step_node).
+    //   - an inner node the f32 filter cannot decide may be entered without the exact f64 test (step_node).
     // Irregular rays (zero / NaN / inf components) keep the reference's test at every node.
     __device__ __forceinline__ void init_from(const FilterRay& f, R tmax, uint32_t n_nodes) {
         nr.set(f);
@@ -685,7 +702,15 @@ struct Trav {
         bool hit;
         if constexpr (sizeof(R) == 8) {
             const int dec = filter_box(nf, nr, (float)tmin, best32);
-            if (dec == 0 && ref_is_leaf(wa)) return ST_EXACT;  // only a leaf node's decision selects primitives
+            // only a leaf node's decision selects primitives; an undecided inner node with a small subtree is entered
+            // untested (at most free_pass_nodes cheap tests instead of one exact f64 test; unbounded, rays with a wide
+            // error band would walk whole subtrees the exact test culls: 8x slower on the 10 M-triangle scene)
+            if (dec == 0) {
+                if (ref_is_leaf(wa)) return ST_EXACT;
+                if ((wa & INDEX_MASK) - i > sc.free_pass_nodes &&
+                    !box_wider_than_band(ldg_node32(sc.nodes32 + i), nr, (float)tmin, best32, sc.free_pass_k))
+                    return ST_EXACT;
+            }
             hit = dec >= 0;
         } else {
             float lo, hi;

@@ -706,6 +706,10 @@ static DevScene<R> make_dev_scene(const SceneDeviceData& s) {
     if (const char* e = getenv("CRB_NODE_SLICE")) d.node_slice = atoi(e) > 0 ? atoi(e) : 8;
     d.min_node_lanes = 8;
     if (const char* e = getenv("CRB_MIN_LANES")) d.min_node_lanes = atoi(e);
+    d.free_pass_nodes = 31;
+    if (const char* e = getenv("CRB_FREE_PASS")) d.free_pass_nodes = (uint32_t)strtoul(e, nullptr, 10);
+    d.free_pass_k = 4.f;
+    if (const char* e = getenv("CRB_FREE_PASS_K")) d.free_pass_k = (float)atof(e);
     return d;
 }
 

@@ -17,8 +17,9 @@ for it in range(6):
     h = lib.cr_scene_create(0); t.append(time.perf_counter())
     lib.cr_scene_destroy(h); t.append(time.perf_counter())
     g = GpuScene(desc, 0); t.append(time.perf_counter())
-    full, full8, st = multigpu.render_sharded(g, cam, 0, 1, seed=1); t.append(time.perf_counter())
-    pinned.copy_(full, non_blocking=True); pinned8.copy_(full8, non_blocking=True); torch.cuda.synchronize(); t.append(time.perf_counter())
+    # the reference-facing call: cr_render with HOST buffers (what bench.py's e2e leg times at N=1)
+    _, _, st = g.render(cam, seed=1, out_rgb=pinned.numpy(), out_rgb8=pinned8.numpy()); t.append(time.perf_counter())
     g.close(); t.append(time.perf_counter())
-    names = ["create", "destroy", "GpuScene", "render", "d2h", "close"]
-    print(it, " ".join(f"{n}={1e3*(b-a):.2f}" for n, a, b in zip(names, t, t[1:])), f"gpu_ms={st['ms_total']:.2f}", flush=True)
+    names = ["create", "destroy", "GpuScene", "cr_render", "close"]
+    print(it, " ".join(f"{n}={1e3*(b-a):.2f}" for n, a, b in zip(names, t, t[1:])),
+          f"device_ms={st['ms_total']:.2f} h2d_ms={st['ms_h2d']:.2f} d2h_ms={st['ms_d2h']:.2f} launches={st['launches']}", flush=True)
