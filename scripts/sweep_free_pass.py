@@ -8,6 +8,8 @@ from crucible_b200.gpu import GpuScene
 
 SCENES = [("book1", dict(image_width=1920, samples=100)), ("teapot", dict(image_width=1920, samples=64)),
           ("cornell", dict(image_width=1024, samples=100)), ("instanced", dict(image_width=3840, samples=8))]
+if os.environ.get("SCENES"):
+    SCENES = [sc for sc in SCENES if sc[0] in os.environ["SCENES"].split()]
 VALUES = [int(v) for v in os.environ.get("VALUES", "0 3 7 31 1073741824").split()]
 KS = os.environ.get("KS", "").split()  # when given: sweep CRB_FREE_PASS_K at the first VALUE instead
 for name, kw in SCENES:
