@@ -129,7 +129,6 @@ struct DevScene {
     // free_pass_nodes nodes, or if the box is wider than free_pass_k error bands in ray parameter on every axis
     uint32_t free_pass_nodes;
     float free_pass_k;
-    int32_t park_min;  // the EXACT + LEAF phase runs once this many lanes are parked (or the node slice ran dry)
 };
 
 // ---- in-flight path record --------------------------------------------------------------------

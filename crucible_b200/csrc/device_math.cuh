@@ -868,10 +868,8 @@ __device__ __forceinline__ void trace_persistent(const DevScene<R>& sc, R tmin, 
         }
         // ---- LEAF pre-filter: leaf nodes whose primitives are all certain misses need no f64 work
         if (st == ST_LEAF && tv.leaf_certain_miss(sc)) st = tv.after_leaf(sc);
-        // ---- EXACT + LEAF phases share one read of the lane's ray.  The phase is expensive for the whole warp (f64 code,
-        // the node loop's registers spilled around it), so it waits until park_min lanes need it or the node work ran dry.
-        const uint32_t parked = __ballot_sync(0xffffffffu, st == ST_EXACT || st == ST_LEAF);
-        if (parked != 0u && (__popc(parked) >= sc.park_min || __popc(__ballot_sync(0xffffffffu, st == ST_NODE)) < max(sc.min_node_lanes, 1))) {
+        // ---- EXACT + LEAF phases share one read of the lane's ray
+        if (__any_sync(0xffffffffu, st == ST_EXACT || st == ST_LEAF)) {
             if (st == ST_EXACT || st == ST_LEAF) {
                 V3<R> o, d;
                 tv.store.get_ray(o, d);

@@ -708,8 +708,6 @@ static DevScene<R> make_dev_scene(const SceneDeviceData& s) {
     if (const char* e = getenv("CRB_MIN_LANES")) d.min_node_lanes = atoi(e);
     d.free_pass_nodes = 31;
     if (const char* e = getenv("CRB_FREE_PASS")) d.free_pass_nodes = (uint32_t)strtoul(e, nullptr, 10);
-    d.park_min = 1;
-    if (const char* e = getenv("CRB_PARK_MIN")) d.park_min = atoi(e);
     d.free_pass_k = 4.f;
     if (const char* e = getenv("CRB_FREE_PASS_K")) d.free_pass_k = (float)atof(e);
     return d;
