@@ -47,7 +47,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
@@ -55,9 +55,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
+        """Median / reasons over the samples taken in [t_begin, t_end] (the sampler is started before the warm-up so that
+        nvidia-smi's own start-up does not eat a short timed region)."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -67,7 +69,8 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = [r for t, r in self.rows if (t_begin is None or t >= t_begin) and (t_end is None or t <= t_end)]
+        for r in rows:
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
@@ -187,16 +190,17 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(max(args.warmup, 3)):
         step(False)
         flush.fill_(1)
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     stats = []
     barrier()
+    t_timed0 = time.perf_counter()
     for k in range(args.steps):
         ev[k][0].record()
         st, _ = step(True)
@@ -204,7 +208,7 @@ def main():
         stats.append(st)
         flush.fill_(k)  # L2 flush between timed iterations, outside the events
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_timed0, time.perf_counter()) if rank == 0 else None
     ms = sum(a.elapsed_time(b) for a, b in ev)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     agg = torch.tensor([sum(s["samples"] for s in stats), sum(s["rays"] for s in stats), sum(s["launches"] for s in stats),
@@ -294,7 +298,7 @@ def main():
         achieved = per_seg_flops * seg_per_launch / dur_s / 1e12
         peak = f64p.value if args.precision == "f64" else f32p.value
         traffic, traffic_src = None, None
-        tpath = os.path.join(ROOT, "profiles", "trace_r01c_traffic.json")
+        tpath = os.path.join(ROOT, "profiles", "trace_r01d_traffic.json")
         if args.precision == "f64" and os.path.exists(tpath):
             tj = json.load(open(tpath))  # DRAM bytes of one ncu --set full capture, scaled to this run's segments per launch
             traffic = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) / tj["rays_in_launch"] * seg_per_launch
