@@ -638,58 +638,82 @@ void cr_scene_destroy(CrScene* s) {
     delete s;
 }
 
+// Box of one primitive in reference arithmetic.
+static inline Box prim_box(uint32_t kind, const double* p) {
+    Box box;
+    if (kind == CR_PRIM_SPHERE) {
+        // sphere.rs:29-30: new_from_points(center - rvec, center + rvec); a - b == a + (-b)
+        const double lo[3] = {p[0] - p[3], p[1] - p[3], p[2] - p[3]};
+        const double hi[3] = {p[0] + p[3], p[1] + p[3], p[2] + p[3]};
+        box = box_from_points(lo, hi);
+    } else if (kind == CR_PRIM_TRIANGLE) {
+        // triangle.rs:48-62: a.min(b.min(c)) / a.max(b.max(c)) per axis (f64::min/max ignore NaN)
+        for (int k = 0; k < 3; ++k) {
+            box.lo[k] = std::fmin(p[k], std::fmin(p[3 + k], p[6 + k]));
+            box.hi[k] = std::fmax(p[k], std::fmax(p[3 + k], p[6 + k]));
+        }
+    } else {
+        // EXTENSION quad: box of both diagonals, sides thinner than 1e-4 padded (Interval::pad, utils.rs:624-627)
+        double quv[3], qu[3], qv[3];
+        for (int k = 0; k < 3; ++k) {
+            qu[k] = p[k] + p[3 + k];
+            qv[k] = p[k] + p[6 + k];
+            quv[k] = qu[k] + p[6 + k];
+        }
+        box = box_union(box_from_points(p, quv), box_from_points(qu, qv));
+        const double delta = 0.0001;
+        for (int k = 0; k < 3; ++k)
+            if (box.hi[k] - box.lo[k] < delta) {
+                const double pad = delta / 2.0;
+                box.lo[k] = box.lo[k] - pad;
+                box.hi[k] = box.hi[k] + pad;
+            }
+    }
+    return box;
+}
+
+// Appends n primitives of one kind (Scene::add_element / load_asset order).  The batch is validated first, so a
+// rejected batch leaves the scene untouched; the staging arrays grow once and big batches (meshes of millions
+// of triangles) are boxed by a few host threads.
 static int64_t add_prims(CrScene* s, uint32_t kind, const double* data, size_t stride, const int32_t* material,
                          const int32_t* obj_id, size_t n) {
     if (!s || (!data && n)) return fail(CR_ERR_INVALID, "null argument");
-    const int64_t first = (int64_t)s->elements.size();
-    if (s->elements.size() + n > REF_MAX_INDEX) return fail(CR_ERR_LIMIT, "too many primitives");
+    const size_t first = s->elements.size();
+    if (first + n > REF_MAX_INDEX) return fail(CR_ERR_LIMIT, "too many primitives");
+    for (size_t k = 0; k < n * stride; ++k)
+        if (!std::isfinite(data[k])) return fail(CR_ERR_INVALID, "non-finite primitive coordinate");
+    if (kind == CR_PRIM_SPHERE)
+        for (size_t i = 0; i < n; ++i)
+            if (!(data[4 * i + 3] >= 0.0)) return fail(CR_ERR_INVALID, "Cannot make a sphere with negative radius");  // sphere.rs:26
     std::vector<double>& store = kind == CR_PRIM_SPHERE ? s->spheres : (kind == CR_PRIM_TRIANGLE ? s->tris : s->quads);
-    for (size_t i = 0; i < n; ++i) {
-        const double* p = data + stride * i;
-        Element e;
-        e.kind = kind;
-        e.idx = (uint32_t)(store.size() / stride);
-        e.hide = false;
-        for (size_t k = 0; k < stride; ++k)
-            if (!std::isfinite(p[k])) return fail(CR_ERR_INVALID, "non-finite primitive coordinate");
-        if (kind == CR_PRIM_SPHERE) {
-            if (!(p[3] >= 0.0)) return fail(CR_ERR_INVALID, "Cannot make a sphere with negative radius");  // sphere.rs:26
-            // sphere.rs:29-30: new_from_points(center - rvec, center + rvec); a - b == a + (-b)
-            const double lo[3] = {p[0] - p[3], p[1] - p[3], p[2] - p[3]};
-            const double hi[3] = {p[0] + p[3], p[1] + p[3], p[2] + p[3]};
-            e.box = box_from_points(lo, hi);
-        } else if (kind == CR_PRIM_TRIANGLE) {
-            // triangle.rs:48-62: a.min(b.min(c)) / a.max(b.max(c)) per axis (f64::min/max ignore NaN)
-            for (int k = 0; k < 3; ++k) {
-                e.box.lo[k] = std::fmin(p[k], std::fmin(p[3 + k], p[6 + k]));
-                e.box.hi[k] = std::fmax(p[k], std::fmax(p[3 + k], p[6 + k]));
-            }
-        } else {
-            // EXTENSION quad: box of both diagonals, sides thinner than 1e-4 padded (Interval::pad, utils.rs:624-627)
-            double quv[3], qu[3], qv[3];
-            for (int k = 0; k < 3; ++k) {
-                qu[k] = p[k] + p[3 + k];
-                qv[k] = p[k] + p[6 + k];
-                quv[k] = qu[k] + p[6 + k];
-            }
-            Box b = box_union(box_from_points(p, quv), box_from_points(qu, qv));
-            const double delta = 0.0001;
-            for (int k = 0; k < 3; ++k)
-                if (b.hi[k] - b.lo[k] < delta) {
-                    const double pad = delta / 2.0;
-                    b.lo[k] = b.lo[k] - pad;
-                    b.hi[k] = b.hi[k] + pad;
-                }
-            e.box = b;
+    const size_t first_of_kind = store.size() / stride;
+    store.insert(store.end(), data, data + n * stride);
+    s->elements.resize(first + n);
+    s->mat_of[kind].resize(first_of_kind + n);
+    s->obj_of[kind].resize(first_of_kind + n);
+    s->prim_of[kind].resize(first_of_kind + n);
+    auto fill = [&](size_t a, size_t b) {
+        for (size_t i = a; i < b; ++i) {
+            Element& e = s->elements[first + i];
+            e.kind = kind;
+            e.idx = (uint32_t)(first_of_kind + i);
+            e.hide = false;
+            e.box = prim_box(kind, data + stride * i);
+            s->mat_of[kind][first_of_kind + i] = material ? material[i] : 0;
+            s->obj_of[kind][first_of_kind + i] = obj_id ? obj_id[i] : (int32_t)(first + i);
+            s->prim_of[kind][first_of_kind + i] = (int32_t)(first + i);
         }
-        store.insert(store.end(), p, p + stride);
-        s->mat_of[kind].push_back(material ? material[i] : 0);
-        s->obj_of[kind].push_back(obj_id ? obj_id[i] : (int32_t)s->elements.size());
-        s->prim_of[kind].push_back((int32_t)s->elements.size());
-        s->elements.push_back(e);
+    };
+    const size_t n_threads = n >= (1u << 18) ? std::min<size_t>(8, std::max(1u, std::thread::hardware_concurrency())) : 1;
+    if (n_threads <= 1) {
+        fill(0, n);
+    } else {
+        std::vector<std::thread> pool;
+        for (size_t t = 0; t < n_threads; ++t) pool.emplace_back(fill, n * t / n_threads, n * (t + 1) / n_threads);
+        for (auto& th : pool) th.join();
     }
     s->committed = false;
-    return first;
+    return (int64_t)first;
 }
 
 int64_t cr_scene_add_spheres(CrScene* s, const double* d, const int32_t* m, const int32_t* o, size_t n) {

@@ -207,3 +207,25 @@ def test_cpp_host_mirror_renders_a_ppm(crlib, gpu_device):
         assert px.shape == (160 * 90, 3) and px.min() >= 0 and px.max() <= 255
         lum = ((px / 255.0) ** 2).mean()
         assert 0.28 < lum < 0.48  # same scene family as samples/book1.png (mean linear luminance ~0.355)
+
+
+def test_rejected_batch_leaves_the_scene_untouched(crlib):
+    """A batch is validated before anything is appended (Sphere::new asserts, sphere.rs:26; non-finite coordinates)."""
+    lib = crlib
+    h = lib.cr_scene_create(-1)
+    good = np.array([[0.0, 0, 0, 1], [3.0, 0, 0, 1], [6.0, 0, 0, 1]])
+    assert lib.cr_scene_add_spheres(h, good.ctypes.data_as(C.c_void_p), None, None, 3) == 0
+    bad = good.copy()
+    bad[2, 3] = -1.0
+    assert lib.cr_scene_add_spheres(h, bad.ctypes.data_as(C.c_void_p), None, None, 3) == abi.CR_ERR_INVALID
+    assert b"negative radius" in lib.cr_last_error()
+    tri = np.arange(18, dtype=float).reshape(2, 9)
+    tri[1, 4] = np.inf
+    assert lib.cr_scene_add_triangles(h, tri.ctypes.data_as(C.c_void_p), None, None, 2) == abi.CR_ERR_INVALID
+    tri[1, 4] = 1.0
+    assert lib.cr_scene_add_triangles(h, tri.ctypes.data_as(C.c_void_p), None, None, 2) == 3  # first index of the batch
+    m = abi.CrMaterial(kind=abi.CR_MAT_METAL)
+    assert lib.cr_scene_set_materials(h, C.byref(m), 1) == 0 and lib.cr_scene_commit(h) == 0
+    n, d, v = C.c_uint64(), C.c_uint32(), C.c_uint64()
+    assert lib.cr_scene_bvh_info(h, C.byref(n), C.byref(d), C.byref(v)) == 0 and v.value == 5
+    lib.cr_scene_destroy(h)
