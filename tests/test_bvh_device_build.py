@@ -200,3 +200,40 @@ def test_instanced_mesh_device_build_and_trace(gpu_device, oracle):
     lo, hi = scene_bounds(d)
     rays = random_rays(20000, lo, hi, 42)
     compare_hits(gs.trace_batch(rays), orc.trace_batch(rays))
+
+
+def test_device_records_need_a_device(crlib):
+    gs = GpuScene(random_scene(5, 5, 0, 1), device=-1)
+    with pytest.raises(abi.CrucibleError) as e:
+        gs.device_records(0)
+    assert e.value.code == abi.CR_ERR_NO_DEVICE
+    ci = gs.commit_info()
+    assert ci["builder"] == abi.CR_BVH_HOST and ci["levels"] == gs.bvh_info()["max_depth"] and ci["ms_upload"] == 0.0
+    assert ci["ms_total"] >= ci["ms_build"] >= 0.0
+
+
+@pytest.mark.gpu
+def test_config4_full_size_builders_agree(gpu_device):
+    """BASELINE config 4 at FULL size (1582 teapots = 9 998 240 triangles + 65 spheres, 11.6 M nodes, depth 24): the
+    device-built tree and the flattened records equal the host recursion's byte for byte, and the commit is faster."""
+    d = demo_builder.instanced_teapots(copies=1582, grid=40).describe()
+    dev = GpuScene(d, gpu_device, bvh_builder=abi.CR_BVH_DEVICE)
+    info = dev.bvh_info()
+    assert info == {"n_nodes": 11608001, "max_depth": 24, "n_visible": 9998305}
+    nodes_dev = dev.bvh_nodes()
+    recs_dev = [dev.device_records(w) for w in (0, 1)]
+    t_dev = dev.commit_info()["ms_total"]
+    dev.close()
+    host = GpuScene(d, gpu_device, bvh_builder=abi.CR_BVH_HOST)
+    assert host.bvh_info() == info
+    assert np.array_equal(host.bvh_nodes().view(np.uint8), nodes_dev.view(np.uint8))
+    for w in (0, 1):
+        assert np.array_equal(host.device_records(w), recs_dev[w])
+    assert t_dev < host.commit_info()["ms_total"]
+    # preorder invariants, vectorised: skip links bound every subtree, inner nodes point at i + 1
+    inner = (nodes_dev["left"] & REF_LEAF) == 0
+    idx = np.arange(len(nodes_dev), dtype=np.int64)
+    assert np.all(nodes_dev["left"][inner] == idx[inner] + 1)
+    assert np.all(nodes_dev["skip"][~inner] == idx[~inner] + 1)
+    assert np.all(nodes_dev["skip"][inner] > nodes_dev["right"][inner]) and nodes_dev["skip"][0] == len(nodes_dev)
+    host.close()
