@@ -26,8 +26,8 @@
  *     operation (no FMA contraction, reference traversal order): closest-hit
  *     `prim_index` and `front_face` are bit-exact, t / normal / uv differ only
  *     through libm (acos/atan2/asin) by a few ulp.
- *   - CR_PRECISION_F32 is the fast path (f32 boxes and primitives, near-first
- *     traversal); it is statistically equivalent, not bit-exact.
+ *   - CR_PRECISION_F32 is the fast path (the same reference-order traversal on f32
+ *     boxes and primitives, FMA allowed); it is statistically equivalent, not bit-exact.
  */
 #ifndef CRUCIBLE_GPU_H
 #define CRUCIBLE_GPU_H
