@@ -1,4 +1,4 @@
-// integrator_f32.cu — the fast instantiation (R = float, near-first traversal, FMA allowed) and the
+// integrator_f32.cu — the fast instantiation (R = float, reference-order traversal, FMA allowed) and the
 // FMA-peak micro-kernels used as roofline denominators.
 #include <cstring>
 
