@@ -280,9 +280,8 @@ def main():
         cpu = None
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            t0 = time.time()
-            probe = oracle_sample(desc, cam, 120, threads)
-            rate = probe["samples"] / max(time.time() - t0, 1e-6)
+            probe = oracle_sample(desc, cam, 120, threads)  # 9 rows: sizes the sample for ~15 s of CPU work
+            rate = probe["samples"] / max(probe["seconds"], 1e-6)
             row_step = int(max(1, min(120, round(total_samples_per_step / max(rate * 15.0, 1.0)))))
             ost = oracle_sample(desc, cam, row_step, threads)
             cpu = ost
