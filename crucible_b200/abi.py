@@ -94,6 +94,7 @@ SIGNATURES = {
     "cr_device_count": (C.c_int, []),
     "cr_scene_create": (_P, [C.c_int]),
     "cr_scene_destroy": (None, [_P]),
+    "cr_device_trim": (C.c_int, [C.c_int]),
     "cr_last_error": (C.c_char_p, []),
     "cr_version": (C.c_char_p, []),
     "cr_scene_add_spheres": (C.c_int64, [_P, _P, _P, _P, C.c_size_t]),
@@ -120,6 +121,7 @@ SIGNATURES = {
     "cr_render_frames": (C.c_int, [_P, C.POINTER(CrCamera), C.POINTER(CrRenderOpts), C.c_uint32, C.c_uint32, C.c_uint32, C.c_char_p,
                                    C.c_uint32, C.c_int, _P]),
     "cr_camera_point_at": (C.c_int, [_PD, _P, C.c_size_t, C.c_double, _PD]),
+    "cr_anim_point_at": (C.c_int, [_PD, _P, C.c_size_t, C.c_double, _PD]),
     "cr_measure_fma_peak": (C.c_int, [C.c_int, _PD, _PD]),
     "cr_philox4x32_10": (None, [_P, _P, _P]),
 }

@@ -100,11 +100,17 @@ namespace {
 
 // One grow-only scratch arena per device, shared by every scene of the process (path pool, queues,
 // fixed-point framebuffer): a second render, or a second scene, reuses the memory instead of paying
-// cudaMalloc for gigabytes again.  Guarded by the "one host thread drives one device" contract.
-Workspace& device_workspace(int device) {
-    static Workspace ws[64];
-    return ws[device < 0 || device >= 64 ? 0 : device];
+// cudaMalloc for gigabytes again.  `mu` serialises the renders of one device (the arena is shared) and guards
+// cr_device_trim; different devices render concurrently (cr_render_multi drives one host thread per device).
+struct DeviceSlot {
+    std::mutex mu;
+    Workspace ws;
+};
+DeviceSlot& device_slot(int device) {
+    static DeviceSlot slots[64];
+    return slots[device < 0 || device >= 64 ? 0 : device];
 }
+Workspace& device_workspace(int device) { return device_slot(device).ws; }
 
 // Per-device facts, queried once per process: cudaGetDeviceProperties costs 3-50 ms per call on an 8-GPU box
 // (measured: it dominated the end-to-end step when every frame created its scene, as Scene::render_image does).
@@ -116,6 +122,8 @@ struct DeviceInfo {
 DeviceInfo& device_info(int device) {
     static DeviceInfo info[64];
     static DeviceInfo bad;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);  // first calls may come from several host threads
     if (device < 0 || device >= 64) {
         bad.state = -1;
         bad.why = "CUDA device " + std::to_string(device) + " not available";
@@ -127,23 +135,24 @@ DeviceInfo& device_info(int device) {
     cudaDeviceProp p;
     if (cudaGetDeviceCount(&n) != cudaSuccess || device >= n) {
         cudaGetLastError();
-        d.state = -1;
         d.why = "CUDA device " + std::to_string(device) + " not available";
+        d.state = -1;
     } else if (cudaGetDeviceProperties(&p, device) != cudaSuccess || p.major != 10) {
         cudaGetLastError();
-        d.state = -1;
         d.why = "device is not sm_100 (this library ships sm_100a code only)";
+        d.state = -1;
     } else {
-        d.state = 1;
         d.num_sms = p.multiProcessorCount;
         // scene buffers come from the device's stream-ordered pool and stay cached there between scenes:
-        // a per-frame scene rebuild then costs no cudaMalloc / cudaFree (each of which synchronises the device)
+        // a per-frame scene rebuild then costs no cudaMalloc / cudaFree (each of which synchronises the device).
+        // cr_device_trim() gives the memory back and restores the default threshold.
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
             uint64_t keep = UINT64_MAX;
             cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
         }
         cudaGetLastError();
+        d.state = 1;  // published last: the fields above are complete when another thread sees it
     }
     return d;
 }
@@ -530,6 +539,8 @@ int upload_scene(CrScene* s) {
 
 int validate(CrScene* s) {
     const int nm = (int)s->mats.size(), nt = (int)s->texs.size(), ni = (int)s->images.size();
+    // the shading queues carry the material index in 24 bits (bit 31 = "needs u, v"), integrator.cuh RenderTraceIO::commit
+    if (s->mats.size() > (1u << 24)) return fail(CR_ERR_LIMIT, "more than 16 777 216 materials");
     for (int k = 0; k < 3; ++k)
         for (int32_t m : s->mat_of[k])
             if (m < 0 || m >= nm) return fail(CR_ERR_INVALID, "primitive references material " + std::to_string(m) + " of " + std::to_string(nm));
@@ -622,6 +633,26 @@ CrScene* cr_scene_create(int device) {
         }
     }
     return s;
+}
+
+int cr_device_trim(int device) {
+    const DeviceInfo& di = device_info(device);
+    if (di.state != 1) return fail(CR_ERR_NO_DEVICE, di.why);
+    DeviceSlot& slot = device_slot(device);
+    std::lock_guard<std::mutex> lk(slot.mu);
+    API_CUDA(cudaSetDevice(device));
+    API_CUDA(cudaDeviceSynchronize());
+    slot.ws.release();
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t keep = 0;  // the CUDA default: cached blocks go back to the driver at the next synchronisation
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        cudaMemPoolTrimTo(pool, 0);
+        keep = UINT64_MAX;  // later scenes of this process cache again
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
+    return CR_OK;
 }
 
 void cr_scene_destroy(CrScene* s) {
@@ -769,9 +800,14 @@ int cr_scene_set_keyframes(CrScene* s, size_t prim_index, int point, const CrAni
     if (kind == CR_PRIM_QUAD) return fail(CR_ERR_INVALID, "quads (extension) cannot be animated");
     if (point < 0 || point > (kind == CR_PRIM_SPHERE ? 0 : 2)) return fail(CR_ERR_INVALID, "point out of range for this primitive");
     for (size_t i = 0; i < n; ++i) {
-        if (keys[i].kind < 0 || keys[i].kind > 3) return fail(CR_ERR_INVALID, "keyframe kind out of range");
+        if (keys[i].kind < 0 || keys[i].kind > 6) return fail(CR_ERR_INVALID, "keyframe kind out of range");
         // ScaleR can only be applied to Spheres (scene_animator.rs:140-150)
         if (keys[i].kind == 3 && kind != CR_PRIM_SPHERE) return fail(CR_ERR_INVALID, "ScaleR can only be applied to Spheres");
+        // scale_x / scale_y / scale_z reject spheres (scene_animator.rs:38-41, 72-75, 106-109)
+        if (keys[i].kind >= 4 && kind == CR_PRIM_SPHERE)
+            return fail(CR_ERR_INVALID, keys[i].kind == 4   ? "ScaleX cannot apply to Spheres"
+                                        : keys[i].kind == 5 ? "ScaleY cannot apply to Spheres"
+                                                            : "ScaleZ cannot apply to Spheres");
         if (keys[i].interp != CR_NERP && keys[i].interp != CR_LERP) return fail(CR_ERR_INVALID, "bad interpolation type");
     }
     std::vector<CrAnimKey>& dst = s->anim[((uint64_t)prim_index << 2) | (uint64_t)point];
@@ -1004,6 +1040,7 @@ int cr_render_device(CrScene* s, const CrCamera* cam, const CrRenderOpts* opts, 
     if (stats) memset(stats, 0, sizeof(*stats));
     cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : s->stream;
     std::string err;
+    std::lock_guard<std::mutex> device_lock(device_slot(s->device).mu);
     // device variant: rows of this rank are written PACKED ([rows_local][W][3]) so the result is the
     // NCCL gather send buffer as is
     rc = (opts->precision == CR_PRECISION_F32)
@@ -1031,6 +1068,7 @@ int cr_render(CrScene* s, const CrCamera* cam, const CrRenderOpts* opts, double*
         API_CUDA(cudaMallocAsync(&s->d_out_rgb8, npix * 3, s->stream));
         s->out_cap = npix;
     }
+    std::lock_guard<std::mutex> device_lock(device_slot(s->device).mu);
     const bool sharded = opts->row_world > 1;
     if (sharded) {
         // untouched rows must stay untouched on the host: start from the caller's buffers
@@ -1168,9 +1206,10 @@ extern "C" int cr_render_frames(CrScene* s, const CrCamera* cam, const CrRenderO
         for (int b = 0; b < NBUF; ++b) {
             if (dbuf[b]) cudaFreeAsync(dbuf[b], s->stream);
             if (hbuf[b]) cudaFreeHost(hbuf[b]);
-            cudaEventDestroy(copied[b]);
+            if (copied[b]) cudaEventDestroy(copied[b]);
         }
         if (copy_stream) cudaStreamDestroy(copy_stream);
+        cudaGetLastError();  // a failed allocation above must not surface in the next call's error check
     };
     for (int b = 0; b < NBUF; ++b) copied[b] = nullptr;
     for (int b = 0; b < NBUF; ++b) {
@@ -1238,9 +1277,12 @@ extern "C" int cr_render_frames(CrScene* s, const CrCamera* cam, const CrRenderO
         c.frame = cam->frame + frame;  // the loop counter names the file, Camera.frame advances from where it stood
         CrStats st;
         memset(&st, 0, sizeof(st));
-        rc = (opts->precision == CR_PRECISION_F32)
-                 ? render_impl<float>(s->dev, device_workspace(s->device), c, *opts, nullptr, dbuf[b], 0, s->stream, &st, err)
-                 : render_impl<double>(s->dev, device_workspace(s->device), c, *opts, nullptr, dbuf[b], 0, s->stream, &st, err);
+        {
+            std::lock_guard<std::mutex> device_lock(device_slot(s->device).mu);
+            rc = (opts->precision == CR_PRECISION_F32)
+                     ? render_impl<float>(s->dev, device_workspace(s->device), c, *opts, nullptr, dbuf[b], 0, s->stream, &st, err)
+                     : render_impl<double>(s->dev, device_workspace(s->device), c, *opts, nullptr, dbuf[b], 0, s->stream, &st, err);
+        }
         if (rc != CR_OK) {
             std::lock_guard<std::mutex> lk(mu);
             busy[b] = false;
@@ -1293,6 +1335,21 @@ int cr_camera_point_at(const double init[3], const CrKeyframe* keys, size_t n, d
     out[0] = p[0];
     out[1] = p[1];
     out[2] = p[2];
+    return CR_OK;
+}
+
+// TransformTimeline::combine_and_compute for an object point, timeline/mod.rs:233-263: the routine the trace / shade
+// kernels run at the ray's time (anim_eval, common.cuh), compiled here for the host (no FMA contraction)
+int cr_anim_point_at(const double init[4], const CrAnimKey* keys, size_t n, double t, double out[4]) {
+    if (!init || !out || (!keys && n)) return fail(CR_ERR_INVALID, "null argument");
+    if (n > 0xFFFFFFFFull) return fail(CR_ERR_LIMIT, "too many keyframes");
+    for (size_t i = 0; i < n; ++i) {
+        if (keys[i].kind < 0 || keys[i].kind > 6) return fail(CR_ERR_INVALID, "keyframe kind out of range");
+        if (keys[i].interp != CR_NERP && keys[i].interp != CR_LERP) return fail(CR_ERR_INVALID, "bad interpolation type");
+    }
+    double p[3] = {init[0], init[1], init[2]}, w = init[3];
+    anim_eval<double>(keys, 0u, (uint32_t)n, t, p, w);
+    out[0] = p[0]; out[1] = p[1]; out[2] = p[2]; out[3] = w;
     return CR_OK;
 }
 

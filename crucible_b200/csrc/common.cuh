@@ -101,6 +101,51 @@ struct AnimTrack {
     uint32_t first, count;  // keys [first, first + count) of DevScene::anim_keys; count == 0 = static point
 };
 
+// ---- TransformTimeline::combine_and_compute for an object point (timeline/mod.rs:233-263) ---------------
+// p = construction position, w = construction radius (spheres) / 1.0.  Every valid translate key adds its offset to
+// its axis in list order (`translate * translate_matrix`: 1*m + 0 + 0 + v*1 = m + v exactly).  Of the scale keys only
+// the LAST valid one of the list counts (`.filter(valid).next_back()`, :251-257) and its matrix multiplies the
+// translated point:
+//   kind 3 scale_sphere diag(1,1,1,v)  (transform_builder.rs:62-80)    -> w = v
+//   kind 4 scale_x      diag(v,1,1,1)  (:146-164)                      -> x = v*x
+//   kind 5 scale_y      row 1 = (v,1,0,0): the reference writes v into the WRONG slot (:229-246) -> y = v*x + y
+//   kind 6 scale_z      diag(1,1,v,1)  (:312-330)                      -> z = v*z
+// (rows are dot products summed left to right; the 0 * finite terms add exact zeros).  With no valid scale key the
+// init matrix applies: diag(1,1,1,r) for spheres, diag(1,1,1,1) for Triangle::new's timelines (triangle.rs:24-26).
+// s = clamp(proportion(t), 0, 1) keeps NaN for a zero-length interval exactly like f64::clamp.
+template <typename R>
+__host__ __device__ __forceinline__ void anim_eval(const CrAnimKey* keys, uint32_t first, uint32_t count, R t, R p[3], R& radius) {
+    int skind = -1;
+    R sv = R(0);
+    for (uint32_t k = first; k < first + count; ++k) {
+        const R t0 = (R)keys[k].t0, t1 = (R)keys[k].t1;
+        if (!((t > t1) || (t0 <= t && t <= t1))) continue;
+        R s = (t - t0) / (t1 - t0);
+        s = s < R(0) ? R(0) : (s > R(1) ? R(1) : s);
+        const R a = (R)keys[k].a, b = (R)keys[k].b;
+        const int kind = keys[k].kind;
+        if (kind < 3) {
+            const R off = (keys[k].interp == CR_LERP) ? a * s : a;
+            p[kind] = off + p[kind];
+        } else {
+            skind = kind;
+            sv = (keys[k].interp == CR_LERP) ? a + (b - a) * s : b;
+        }
+    }
+    if (skind == 3) {
+        radius = sv;
+    } else if (skind == 4) {
+        p[0] = sv * p[0];
+        radius = R(1);
+    } else if (skind == 5) {
+        p[1] = sv * p[0] + p[1];
+        radius = R(1);
+    } else if (skind == 6) {
+        p[2] = sv * p[2];
+        radius = R(1);
+    }
+}
+
 template <typename R>
 struct DevScene {
     const NodeRec<R>* nodes;

@@ -260,28 +260,6 @@ __device__ __forceinline__ bool quad_hit_t(const QuadRec<R>& q, V3<R> o, V3<R> d
     return true;
 }
 
-// ---- TransformTimeline::combine_and_compute for an object point (timeline/mod.rs:233-263) ---------------
-// p = construction position, radius = construction radius; every valid translate key adds its offset to its
-// axis in list order (`translate * translate_matrix`: 1*m + 0 + 0 + v*1 = m + v exactly), the last valid
-// radius key replaces the radius (`.filter(valid).next_back()`).  s = clamp(proportion(t), 0, 1) keeps NaN for a
-// zero-length interval exactly like f64::clamp.
-template <typename R>
-__host__ __device__ __forceinline__ void anim_eval(const CrAnimKey* keys, uint32_t first, uint32_t count, R t, R p[3], R& radius) {
-    for (uint32_t k = first; k < first + count; ++k) {
-        const R t0 = (R)keys[k].t0, t1 = (R)keys[k].t1;
-        if (!((t > t1) || (t0 <= t && t <= t1))) continue;
-        R s = (t - t0) / (t1 - t0);
-        s = s < R(0) ? R(0) : (s > R(1) ? R(1) : s);
-        const R a = (R)keys[k].a, b = (R)keys[k].b;
-        const int kind = keys[k].kind;
-        if (kind < 3) {
-            const R off = (keys[k].interp == CR_LERP) ? a * s : a;
-            p[kind] = off + p[kind];
-        } else {
-            radius = (keys[k].interp == CR_LERP) ? a + (b - a) * s : b;
-        }
-    }
-}
 // Sphere / triangle records at ray time tm: the stored record for static primitives (and static scenes),
 // the timelines evaluated at tm otherwise (Sphere::hit sphere.rs:67-70, Triangle::hit triangle.rs:91-100).
 // ANIM = false is the build static scenes run: no track lookups, no extra registers in the hot kernels.

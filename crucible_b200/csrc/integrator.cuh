@@ -782,10 +782,30 @@ static void host_camera_constants(const CrCamera& c, RaygenParams<R>& rp) {
     for (int k = 0; k < 6; ++k) { dst[k][0] = src[k].x; dst[k][1] = src[k].y; dst[k][2] = src[k].z; }
 }
 
+// events created by one call: destroyed on every exit path (an early CRB_CUDA return used to leak them)
+struct EventBag {
+    std::vector<cudaEvent_t> ev;
+    ~EventBag() {
+        for (cudaEvent_t e : ev) cudaEventDestroy(e);
+    }
+    cudaError_t make(cudaEvent_t* e, unsigned flags = cudaEventDefault) {
+        const cudaError_t r = cudaEventCreateWithFlags(e, flags);
+        if (r == cudaSuccess) ev.push_back(*e);
+        return r;
+    }
+};
+
 struct EventTimer {
     bool on;
     cudaStream_t st;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> spans[4];
+    ~EventTimer() {
+        for (auto& v : spans)
+            for (auto& p : v) {
+                cudaEventDestroy(p.first);
+                cudaEventDestroy(p.second);
+            }
+    }
     void begin(int cls, cudaEvent_t& a) {
         if (!on) return;
         cudaEventCreate(&a);
@@ -888,12 +908,16 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
     hcam.is_static = (cam_in.n_from_keys == 0 && cam_in.n_at_keys == 0) ? 1u : 0u;
     Control hctl;
     memset(&hctl, 0, sizeof(hctl));
-    hctl.total_samples = total;
+    // ray_color(depth == 0) returns black BEFORE world.hit (ray_casting.rs:113-116): a max_depth 0 camera casts no ray
+    // at all, the image is black and CrStats.rays is 0
+    const uint64_t issue = cam_in.max_depth == 0 ? 0 : total;
+    hctl.total_samples = issue;
     hctl.pool = pool;
 
+    EventBag events;
     cudaEvent_t ev_begin, ev_end;
-    CRB_CUDA(cudaEventCreate(&ev_begin));
-    CRB_CUDA(cudaEventCreate(&ev_end));
+    CRB_CUDA(events.make(&ev_begin));
+    CRB_CUDA(events.make(&ev_end));
     CRB_CUDA(cudaEventRecord(ev_begin, stream));
     // staging copies come from pinned memory so they are truly asynchronous
     char* pin = static_cast<char*>(ws.pinned);
@@ -965,7 +989,7 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
     uint32_t* d_n_in_ring = reinterpret_cast<uint32_t*>(pin + 3584);  // plan writes through zero-copy? no: device copy below
     (void)d_n_in_ring;
     cudaEvent_t ring_ev[RING];
-    for (int i = 0; i < RING; ++i) CRB_CUDA(cudaEventCreateWithFlags(&ring_ev[i], cudaEventDisableTiming));
+    for (int i = 0; i < RING; ++i) CRB_CUDA(events.make(&ring_ev[i], cudaEventDisableTiming));
 
     cudaEvent_t a;
     // prologue: camera basis (static cameras), plan + raygen fill side 0
@@ -975,12 +999,12 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
     tm.end(2, a);
     launches += 2;
     uint64_t it = 0;
-    bool done = (total == 0);
+    bool done = (issue == 0);
     while (!done) {
         const int cur = (int)(it & 1), nxt = cur ^ 1;
         if (tuning && it == tune_at) {
             cudaEvent_t te[4];
-            for (auto& e : te) CRB_CUDA(cudaEventCreate(&e));
+            for (auto& e : te) CRB_CUDA(events.make(&e));
             for (int v = 0; v < 2; ++v) {
                 CRB_CUDA(cudaEventRecord(te[2 * v], stream));
                 trace_variants[v]<<<trace_grids[v], TRACE_BLOCK, 0, stream>>>(sc, paths[cur], ctl, cur, queues, filt[cur], pool);
@@ -992,7 +1016,6 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
             float ms[2] = {0.f, 0.f};
             cudaEventElapsedTime(&ms[0], te[0], te[1]);
             cudaEventElapsedTime(&ms[1], te[2], te[3]);
-            for (auto& e : te) cudaEventDestroy(e);
             variant = ms[1] <= ms[0] ? 1 : 0;
             ws.store_variant(signature, variant);
             trace_fn = trace_variants[variant];
@@ -1066,7 +1089,6 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
     CRB_CUDA(cudaEventRecord(ev_end, stream));
     CRB_CUDA(cudaEventSynchronize(ev_end));
     CRB_CUDA(cudaGetLastError());
-    for (int i = 0; i < RING; ++i) cudaEventDestroy(ring_ev[i]);
     if (stats) {
         Control fin;
         memcpy(&fin, pin, sizeof(fin));
@@ -1084,8 +1106,6 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
     } else {
         for (int c = 0; c < 4; ++c) tm.total(c);
     }
-    cudaEventDestroy(ev_begin);
-    cudaEventDestroy(ev_end);
     return CR_OK;
 }
 

@@ -164,15 +164,13 @@ class TransformTimeline:
         return TransformTimeline(start_pos, start_radius)
 
     def combine_and_compute_object(self, t):
-        """timeline/mod.rs:233-263 for an object point: (x, y, z, w) with w = the radius / scale entry; evaluated by
-        the oracle's restatement."""
-        from oracle import binding as oracle
-
+        """timeline/mod.rs:233-263 for an object point: (x, y, z, w) with w = the radius / scale entry, through the
+        library's host evaluator (cr_anim_point_at: the routine the kernels run at the ray's time)."""
         keys = self.anim_keys()
         arr = (abi.CrAnimKey * max(len(keys), 1))(*keys)
         init = (abi.C.c_double * 4)(*self.start_pos, self.start_scale)
         out = (abi.C.c_double * 4)()
-        oracle.load().orc_combine_and_compute(init, abi.C.cast(arr, abi.C.c_void_p), len(keys), float(t), out)
+        abi.check(abi.load().cr_anim_point_at(init, abi.C.cast(arr, abi.C.c_void_p), len(keys), float(t), out))
         return np.array(list(out))
 
     def _translate(self, axis, x, keyframe, interp, space):
@@ -210,27 +208,49 @@ class TransformTimeline:
         self.translate_y(p[1], keyframe, interp, space)
         self.translate_z(p[2], keyframe, interp, space)
 
-    # ---- scale_sphere, transform_builder.rs:18-96 (spheres only; `start_scale` = construction radius)
-    def scale_sphere(self, r, keyframe, interp):
+    # ---- scale_sphere / scale_x / scale_y / scale_z, transform_builder.rs:18-346 (`start_scale` = the construction
+    # radius of a sphere, 1.0 for Triangle::new's timelines).  kind 3 = ScaleR, 4 / 5 / 6 = ScaleX / ScaleY / ScaleZ.
+    _SCALE_NAMES = {3: "r", 4: "x", 5: "y", 6: "z"}
+
+    def _scale(self, kind, value, keyframe, interp):
         if not keyframe >= 0.0:
-            raise ValueError(f"Cannot add a keyframe before the animation start. You tried to add keyframe: {keyframe} in a r scaling")
-        # most_recent_matching_transform(keyframe, ScaleR): last entry (list order) whose interval ended before the keyframe
-        prev_end, prev_time = self.start_scale, 0.0  # the Omni init entry, valid_time (-0.1, -0.1)
+            raise ValueError("Cannot add a keyframe before the animation start. You tried to add keyframe: "
+                             f"{keyframe} in a {self._SCALE_NAMES[kind]} scaling")
+        # most_recent_matching_transform(keyframe, kind) (helper_functions.rs:42-93): last entry in LIST order whose
+        # interval ended before the keyframe and whose type is this one or Omni (the init entry, valid_time (-0.1, -0.1))
+        prev_end, prev_time = self.start_scale, 0.0
         for tf in reversed(self.scale):
-            if keyframe > tf.t1:
+            if keyframe > tf.t1 and tf.axis == kind:
                 prev_end, prev_time = tf.end, max(tf.t1, 0.0)
                 break
         if interp == InterpolationType.LERP:
             t0, t1 = prev_time, float(keyframe)
         else:
             t0 = t1 = float(keyframe)
-        self.scale.append(_Transform(t0, t1, 3, float(prev_end), interp, float(r)))
+        self.scale.append(_Transform(t0, t1, kind, float(prev_end), interp, float(value)))
         self.scale.sort(key=lambda tf: tf.t0)  # sort_by(compare_start): stable
+
+    def scale_sphere(self, r, keyframe, interp):  # :18-96
+        self._scale(3, r, keyframe, interp)
+
+    def scale_x(self, x, keyframe, interp):  # :101-180
+        self._scale(4, x, keyframe, interp)
+
+    def scale_y(self, y, keyframe, interp):  # :186-265 (the matrix carries the value in row 1, column 0: :229-246)
+        self._scale(5, y, keyframe, interp)
+
+    def scale_z(self, z, keyframe, interp):  # :271-346
+        self._scale(6, z, keyframe, interp)
+
+    def scale_point(self, p, keyframe, interp):  # :729-733
+        self.scale_x(p[0], keyframe, interp)
+        self.scale_y(p[1], keyframe, interp)
+        self.scale_z(p[2], keyframe, interp)
 
     def anim_keys(self):
         """The timeline beyond its init entries as CrAnimKey[] in evaluation order (translate list, then scale list)."""
         keys = [abi.CrAnimKey(tf.t0, tf.t1, tf.delta, 0.0, tf.axis, tf.interp) for tf in self.translate]
-        keys += [abi.CrAnimKey(tf.t0, tf.t1, tf.delta, tf.end, 3, tf.interp) for tf in self.scale]
+        keys += [abi.CrAnimKey(tf.t0, tf.t1, tf.delta, tf.end, tf.axis, tf.interp) for tf in self.scale]
         return keys
 
     def keyframes(self):
@@ -518,6 +538,8 @@ class Scene:
         oid = self._vend_id(alias, ObjectType.TriangleMesh)
         v = scale * np.asarray(vertices, np.float64) + np.asarray(shift, np.float64)
         f = np.asarray(faces, np.int64) - 1
+        if f.size and (f.min() < 0 or f.max() >= len(v)):  # obj_loader.rs indexes vertices[i - 1]: out of range panics
+            raise IndexError("face index out of range (OBJ face indices are 1-based)")
         tris = np.concatenate([v[f[:, 0]], v[f[:, 1]], v[f[:, 2]]], axis=1)
         self._append(abi.CR_PRIM_TRIANGLE, tris, self._tables.material(mat), oid)
 
@@ -563,6 +585,28 @@ class Scene:
                                         "ScaleR can only be applied to Spheres")
         self._anim_ops.setdefault(oid, []).append(("scale_r", float(r), float(keyframe), it))
 
+    def _scale_axis(self, name, kind, v, keyframe, it, alias):  # scene_animator.rs:38-138
+        # `invalid_types = [ObjectType::Sphere]`; only Triangle elements carrying the id are rewritten (:50-63)
+        oid = self._check_and_get_alias(alias, (ObjectType.Sphere, ObjectType.Quad), f"{name} cannot apply to Spheres")
+        self._anim_ops.setdefault(oid, []).append(("scale", kind, float(v), float(keyframe), it))
+
+    def scale_x(self, x, keyframe, it, alias):  # scene_animator.rs:38-67
+        self._scale_axis("ScaleX", 4, x, keyframe, it, alias)
+
+    def scale_y(self, y, keyframe, it, alias):  # :72-101
+        self._scale_axis("ScaleY", 5, y, keyframe, it, alias)
+
+    def scale_z(self, z, keyframe, it, alias):  # :106-135
+        self._scale_axis("ScaleZ", 6, z, keyframe, it, alias)
+
+    def scale_point(self, p, keyframe, it, alias):  # :187-214 -> scale_x, scale_y, scale_z on every vertex timeline
+        oid = self._check_and_get_alias(alias, (ObjectType.Sphere, ObjectType.Quad), "ScaleAll cannot apply to Spheres")
+        for kind in (4, 5, 6):
+            self._anim_ops.setdefault(oid, []).append(("scale", kind, float(p[kind - 4]), float(keyframe), it))
+
+    def scale_all_uniform(self, v, keyframe, it, alias):  # :217-219
+        self.scale_point(Point3(v, v, v), keyframe, it, alias)
+
     def _translate_axis(self, axis, x, keyframe, it, space, alias):
         oid = self._check_and_get_alias(alias, (ObjectType.Quad,), "quads (extension) cannot be animated")
         self._anim_ops.setdefault(oid, []).append(("translate", axis, float(x), float(keyframe), it, space))
@@ -599,6 +643,8 @@ class Scene:
                         for op in ops:
                             if op[0] == "scale_r":
                                 tl.scale_sphere(op[1], op[2], op[3])
+                            elif op[0] == "scale":
+                                tl._scale(op[1], op[2], op[3], op[4])
                             else:
                                 tl._translate(op[1], op[2], op[3], op[4], op[5])
                         out.append((base + int(row), point, tl.anim_keys()))

@@ -177,6 +177,12 @@ typedef struct CrHit {
 /* Number of usable sm_100 devices (0 when CUDA is unavailable). */
 int cr_device_count(void);
 CrScene* cr_scene_create(int device);
+/* Releases what the library caches on `device` between calls: the wavefront arena shared by the scenes of the process
+ * (path pool, queues, framebuffer: up to ~25 GB at the default pool of 64 M paths), its pinned staging block, and the
+ * blocks held by the device's stream-ordered memory pool.  Safe to call between renders (it waits for the device);
+ * the next render allocates again.  The reference has nothing to release: its worker pool dies with Camera::render
+ * (camera/mod.rs:299-303). */
+int cr_device_trim(int device);
 void cr_scene_destroy(CrScene*);
 const char* cr_last_error(void);
 const char* cr_version(void);
@@ -196,6 +202,7 @@ int64_t cr_scene_add_quads(CrScene*, const double* quv, const int32_t* material,
                            const int32_t* obj_id, size_t n);
 /* Scene::hide_element / show_element, scene/mod.rs:232-281 (per primitive). */
 int cr_scene_set_hidden(CrScene*, size_t prim_index, int hide);
+/* At most 2^24 materials (CR_ERR_LIMIT at commit beyond that). */
 int cr_scene_set_materials(CrScene*, const CrMaterial*, size_t n);
 int cr_scene_set_textures(CrScene*, const CrTexture*, size_t n);
 /* RTWImage (asset_loader/img_loader.rs:9-13): rgb8 = [h][w][3]; returns the image index. */
@@ -208,11 +215,18 @@ int cr_scene_set_sky(CrScene*, int kind, int image);
  * s = clamp((t - t0) / (t1 - t0), 0, 1) (Transform::get_matrix_at_time, timeline/mod.rs:88-96):
  *   kind 0,1,2 (translate_x/y/z, transform_builder.rs:348-713): every valid key ADDS  a*s (LERP) or a (NERP) to
  *              that axis, in list order (the product of translate matrices, timeline/mod.rs:244-248);
- *   kind 3     (scale_sphere, transform_builder.rs:18-96): the LAST valid key of the list gives the radius,
- *              a + (b - a)*s (LERP) or b (NERP); with none valid the radius is the construction radius. */
+ *   kind 3..6  (scale keys): only the LAST valid scale key of the list counts (timeline/mod.rs:251-257); its value
+ *              is v = a + (b - a)*s (LERP) or b (NERP) and its matrix multiplies the translated point (x, y, z):
+ *       3 = scale_sphere (transform_builder.rs:18-96)   diag(1,1,1,v): the radius becomes v (spheres only);
+ *       4 = scale_x (:101-180)  diag(v,1,1,1): x' = v*x            (triangle vertices only, scene_animator.rs:38-41)
+ *       5 = scale_y (:186-265)  the reference writes v into row 1, column 0 (:229-246): y' = v*x + y, reproduced;
+ *       6 = scale_z (:271-346)  diag(1,1,v,1): z' = v*z.
+ *     With no valid scale key the construction radius / the identity applies.  Because only the last valid key
+ *     counts, scale_point / scale_all_uniform (:729-733, scene_animator.rs:187-219), which push an x, a y and a z key
+ *     with the same interval, end up scaling z only: reference behaviour, reproduced. */
 typedef struct CrAnimKey {
     double t0, t1, a, b;
-    int32_t kind;   /* 0,1,2 = translate axis; 3 = sphere radius */
+    int32_t kind;   /* 0,1,2 = translate axis; 3 = sphere radius; 4,5,6 = scale x, y, z */
     int32_t interp; /* CrInterp */
 } CrAnimKey;
 /* Replaces the keyframes of one point of a primitive: point 0 of a sphere (centre + radius), points 0,1,2 = the
@@ -316,6 +330,11 @@ int cr_render_frames(CrScene*, const CrCamera* cam, const CrRenderOpts*, uint32_
 /* TransformTimeline::combine_and_compute for a camera point (timeline/mod.rs:233-263):
  * out = init + sum of keyframe contributions at time t. */
 int cr_camera_point_at(const double init[3], const CrKeyframe* keys, size_t n, double t, double out[3]);
+/* TransformTimeline::combine_and_compute for an OBJECT point (timeline/mod.rs:233-263): init = (x, y, z, w) with
+ * w = the construction radius of a sphere or 1.0 for a triangle vertex (TransformTimeline::new_sphere / ::new,
+ * timeline/mod.rs:129-223); keys as for cr_scene_set_keyframes; out = (x, y, z, w) at time t.  The host copy of the
+ * routine Sphere::hit / Triangle::hit evaluate on the device (sphere.rs:67-70, triangle.rs:91-97). */
+int cr_anim_point_at(const double init[4], const CrAnimKey* keys, size_t n, double t, double out[4]);
 /* FP64 / FP32 FMA peak of the device measured with a register-resident micro-kernel
  * (roofline denominators that MEASURED_PEAKS.json does not hold). TFLOP/s. */
 int cr_measure_fma_peak(int device, double* fp64_tflops, double* fp32_tflops);

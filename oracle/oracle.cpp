@@ -254,10 +254,20 @@ struct Triangle {
 };
 
 /* TransformTimeline::combine_and_compute (timeline/mod.rs:233-263) for one point: every valid translate transform
- * (valid_time.is_less(t) || contains(t)) multiplies its matrix in, which adds its entry to that axis; the last
- * valid scale transform supplies w (the sphere radius).  get_matrix_at_time (timeline/mod.rs:88-96):
- * scaled_time = proportion(t).clamp(0, 1).  Keys arrive in the timeline's sorted order. */
+ * (valid_time.is_less(t) || contains(t)) multiplies its matrix in, which adds its entry to that axis; of the scale
+ * transforms only the LAST valid one of the list is used (`.filter(..).next_back()`, :251-257) and its matrix
+ * multiplies the translated point (combined = scale * translate, :260-261; rows are dot products summed left to
+ * right, the 0 * finite terms add exact zeros):
+ *   kind 3 scale_sphere  diag(1,1,1,v)            (transform_builder.rs:62-80)   w = v
+ *   kind 4 scale_x       diag(v,1,1,1)            (:146-164)                      x = v*x, w = 1
+ *   kind 5 scale_y       row 1 = (v, 1, 0, 0)     (:229-246: v sits in the wrong slot)  y = v*x + y, w = 1
+ *   kind 6 scale_z       diag(1,1,v,1)            (:312-330)                      z = v*z, w = 1
+ * get_matrix_at_time (timeline/mod.rs:88-96): scaled_time = proportion(t).clamp(0, 1); a LERP scale entry is
+ * start + (end - start) * scaled_time (transform_builder.rs:44-48, 128-132), a NERP one the end value.
+ * Keys arrive in the timeline's sorted order. */
 static inline void combine_and_compute(const std::vector<CrAnimKey>& keys, double t, V3& p, double& w) {
+    int skind = -1;
+    double sv = 0.0;
     for (const CrAnimKey& k : keys) {
         if (!((t > k.t1) || (k.t0 <= t && t <= k.t1))) continue;
         double s = (t - k.t0) / (k.t1 - k.t0); /* Interval::proportion, utils.rs:681-683 */
@@ -268,8 +278,21 @@ static inline void combine_and_compute(const std::vector<CrAnimKey>& keys, doubl
             else if (k.kind == 1) p.y = off + p.y;
             else p.z = off + p.z;
         } else {
-            w = (k.interp == CR_LERP) ? k.a + (k.b - k.a) * s : k.b; /* transform_builder.rs:44-58 */
+            skind = k.kind;
+            sv = (k.interp == CR_LERP) ? k.a + (k.b - k.a) * s : k.b;
         }
+    }
+    if (skind == 3) {
+        w = sv;
+    } else if (skind == 4) {
+        p.x = sv * p.x;
+        w = 1.0;
+    } else if (skind == 5) {
+        p.y = sv * p.x + p.y;
+        w = 1.0;
+    } else if (skind == 6) {
+        p.z = sv * p.z;
+        w = 1.0;
     }
 }
 struct Quad { /* EXTENSION */
@@ -318,6 +341,7 @@ struct Scene {
     /* built world */
     std::vector<Node> nodes;
     Obj world = {O_LIST, -1}; /* empty HitList */
+    std::vector<uint32_t> leaf_rank; /* MODEL only: DFS rank of (leaf node, slot), for the order-free tie rule */
     bool built = false;
 
     const Aabb& bbox_of(const Obj& o) const {
@@ -492,6 +516,122 @@ static inline bool brute_hit(const Scene& sc, const Ray& r, const Interval& ray_
     return list_hit(sc, sc.elements, r, ray_t, out, cn);
 }
 
+/* ------------------------------------------------------------------ MODEL: order-free closest hit
+ * NOT reference code.  The reference's closest hit (bvhwrapper.rs:97-126) has an order-free description (DESIGN.md
+ * 5.1b) that the product's near-first trace kernel relies on; this is that description executed on the CPU so that
+ * property tests can compare it with the reference-order traversal above, ray by ray.
+ *   cand(P)   = the root Sphere::hit / Triangle::hit / quad_hit select for P on the interval (tmin, tmax): it does not
+ *               depend on the running closest t, only its acceptance does;
+ *   near(L)   = entry parameter of P's leaf-node box in the reference's own slab arithmetic (bvh.rs:96-132);
+ *   P regular = L's box is hit on (tmin, +inf) and near(L) <= cand(P).
+ * If no IRREGULAR primitive (cand(P) < near(L): rounding put the hit before its own box) has cand <= the smallest
+ * regular cand, the reference returns the DFS-first regular minimiser W.  W is found in ANY visiting order; here:
+ * nearer child first by the sign of the ray direction on the node's longest axis, subtrees culled when their box
+ * entry exceeds best + margin.  A ray that meets an irregular candidate is flagged (the product re-traces it in
+ * reference order).  cn.node counts the box tests of THIS traversal. */
+struct OrderFree {
+    double best;
+    Obj win;
+    uint32_t win_rank;
+    bool has, irregular;
+    double margin;
+};
+/* reference slab arithmetic on (tmin, +inf): returns false when the box is missed; near/far as the reference computes */
+static inline bool aabb_span(const Aabb& b, const Ray& r, double tmin, double& near_t, double& far_t) {
+    const double o[3] = {r.o.x, r.o.y, r.o.z};
+    const double d[3] = {r.d.x, r.d.y, r.d.z};
+    double lo = tmin, hi = INF;
+    for (int ax = 0; ax < 3; ++ax) {
+        const Interval& iv = axis_interval(b, ax);
+        double adinv = 1.0 / d[ax];
+        double t0 = (iv.min - o[ax]) * adinv;
+        double t1 = (iv.max - o[ax]) * adinv;
+        if (t0 < t1) {
+            lo = (t0 > lo) ? t0 : lo;
+            hi = (t1 < hi) ? t1 : hi;
+        } else {
+            lo = (t1 > lo) ? t1 : lo;
+            hi = (t0 < hi) ? t0 : hi;
+        }
+        if (hi <= lo) return false;
+    }
+    near_t = lo; /* = max(tmin, entry) */
+    far_t = hi;
+    return true;
+}
+static void order_free_visit(const Scene& sc, const Obj& o, const Ray& r, double tmin, double tmax, OrderFree& st, Counters& cn) {
+    const Node& n = sc.nodes[o.idx];
+    cn.node++;
+    double near_t, far_t;
+    if (!aabb_span(n.bbox, r, tmin, near_t, far_t)) return;
+    if (near_t > st.best + st.margin) return; /* culling only: conservative */
+    if (n.left.kind == O_NODE) {
+        const int ax = longest_axis(n.bbox);
+        const double dax = ax == 0 ? r.d.x : (ax == 1 ? r.d.y : r.d.z);
+        const bool left_first = dax >= 0.0; /* children are sorted by bbox.min on this axis (bvhwrapper.rs:66-73) */
+        order_free_visit(sc, left_first ? n.left : n.right, r, tmin, tmax, st, cn);
+        order_free_visit(sc, left_first ? n.right : n.left, r, tmin, tmax, st, cn);
+        return;
+    }
+    /* leaf node: left primitive, then right (span-1 nodes hold the same primitive twice: tested once) */
+    const bool same = n.left.kind == n.right.kind && n.left.idx == n.right.idx;
+    for (int k = 0; k < (same ? 1 : 2); ++k) {
+        const Obj& p = k == 0 ? n.left : n.right;
+        HitRecord h;
+        if (!obj_hit(sc, p, r, Interval{tmin, tmax}, h, cn)) continue;
+        if (!(h.t < st.best || (st.has && h.t == st.best))) continue;
+        /* the candidate matters: is it regular? (near_t already includes tmin <= cand) */
+        if (h.t < near_t) {
+            st.irregular = true;
+            continue;
+        }
+        const uint32_t dfs = sc.leaf_rank[(size_t)2 * o.idx + k]; /* DFS position: equal cands keep the DFS-first one */
+        if (h.t < st.best || dfs < st.win_rank) {
+            st.best = h.t;
+            st.win = p;
+            st.win_rank = dfs;
+            st.has = true;
+        }
+    }
+}
+static void assign_leaf_ranks(Scene& sc, const Obj& o, uint32_t& next) {
+    if (o.kind != O_NODE) return;
+    const Node& n = sc.nodes[o.idx];
+    if (n.left.kind == O_NODE) {
+        assign_leaf_ranks(sc, n.left, next);
+        assign_leaf_ranks(sc, n.right, next);
+    } else {
+        sc.leaf_rank[(size_t)2 * o.idx] = next++;
+        sc.leaf_rank[(size_t)2 * o.idx + 1] = next++;
+    }
+}
+/* returns: 1 hit, 0 miss, -1 flagged irregular (caller falls back to world_hit) */
+static inline int order_free_hit(const Scene& sc, const Ray& r, double tmin, double tmax, double margin_k, HitRecord& out, Counters& cn) {
+    cn.rays++;
+    if (sc.world.kind != O_NODE) return 0;
+    const double dl = std::sqrt(len2(r.d));
+    const double oo = std::fabs(r.o.x) + std::fabs(r.o.y) + std::fabs(r.o.z);
+    const Aabb& rb = sc.nodes[sc.world.idx].bbox;
+    double B = 0.0;
+    for (int ax = 0; ax < 3; ++ax) {
+        const Interval& iv = axis_interval(rb, ax);
+        B = std::max(B, std::max(std::fabs(iv.min), std::fabs(iv.max)));
+    }
+    OrderFree st;
+    st.best = tmax;
+    st.win = {O_LIST, -1};
+    st.win_rank = 0xFFFFFFFFu;
+    st.has = false;
+    st.irregular = false;
+    st.margin = margin_k * (oo + 3.0 * B) / dl;
+    order_free_visit(sc, sc.world, r, tmin, tmax, st, cn);
+    if (st.irregular) return -1;
+    if (!st.has) return 0;
+    Counters dummy;
+    obj_hit(sc, st.win, r, Interval{tmin, tmax}, out, dummy);
+    return 1;
+}
+
 /* ------------------------------------------------------------------ bvhwrapper.rs : build */
 /* bvhwrapper.rs:82-94 */
 static inline bool box_less(const Scene& sc, const Obj& a, const Obj& b, int axis) {
@@ -541,6 +681,11 @@ static void build_world(Scene& sc) {
         Node& n = sc.nodes[root.idx];
         n.bbox = aabb_union(sc.bbox_of(n.left), sc.bbox_of(n.right)); /* new_from_vec, :38-41 */
         sc.world = root;
+    }
+    sc.leaf_rank.assign(2 * sc.nodes.size(), 0u);
+    {
+        uint32_t next = 0;
+        assign_leaf_ranks(sc, sc.world, next);
     }
     sc.built = true;
 }
@@ -1030,7 +1175,9 @@ static void fill_hit(const HitRecord& h, bool got, CrHit& o) {
     o.v = h.v;
 }
 
-/* Hittables::hit on a ray batch.  mode 0 = built world (BVH), 1 = brute-force flat list.
+static double g_order_free_margin = 9.5367431640625e-07; /* 2^-20, the product's margin factor */
+extern "C" void orc_set_order_free_margin(double k) { g_order_free_margin = k; }
+/* Hittables::hit on a ray batch.  mode 0 = built world (BVH), 1 = brute-force flat list, 2 = order-free MODEL.
  * counters (optional) = [n][4] u32: aabb tests, sphere tests, triangle tests, quad tests. */
 int orc_trace_batch(const OrcScene* h, const double* rays, size_t n, double tmin, double tmax, int mode, CrHit* out,
                     uint32_t* counters, int nthreads) {
@@ -1052,8 +1199,19 @@ int orc_trace_batch(const OrcScene* h, const double* rays, size_t n, double tmin
                 Ray r = {{p[0], p[1], p[2]}, {p[3], p[4], p[5]}, p[6]};
                 HitRecord hr;
                 Counters cn;
-                bool got = (mode == 0) ? world_hit(sc, r, Interval{tmin, tmax}, hr, cn)
-                                       : brute_hit(sc, r, Interval{tmin, tmax}, hr, cn);
+                bool got;
+                if (mode >= 2) { /* MODEL of the order-free traversal; counters[3] = 0xFFFFFFFF marks a flagged ray */
+                    const int rc = order_free_hit(sc, r, tmin, tmax, g_order_free_margin, hr, cn);
+                    got = rc > 0;
+                    if (rc < 0) {
+                        Counters c2;
+                        got = world_hit(sc, r, Interval{tmin, tmax}, hr, c2);
+                        cn.quad = 0xFFFFFFFFu;
+                    }
+                } else {
+                    got = (mode == 0) ? world_hit(sc, r, Interval{tmin, tmax}, hr, cn)
+                                      : brute_hit(sc, r, Interval{tmin, tmax}, hr, cn);
+                }
                 fill_hit(hr, got, out[i]);
                 if (counters) {
                     counters[4 * i + 0] = (uint32_t)cn.node;

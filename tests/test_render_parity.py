@@ -93,8 +93,18 @@ def test_depth_limit_and_single_sample(gpu_device, oracle):
     assert np.abs(rgb - ref).max() <= TOL_F64
     sc.scene_cam.set_max_depth(0)  # ray_color(depth 0) is black without tracing
     cam = sc.scene_cam.to_abi()
-    ref0, _, _ = orc.render(cam, seed=1)
-    assert ref0.max() == 0.0
+    ref0, _, ost0 = orc.render(cam, seed=1)
+    assert ref0.max() == 0.0 and ost0["rays"] == 0
+    for prec in (abi.CR_PRECISION_F64, abi.CR_PRECISION_F32):
+        rgb0, rgb8_0, st0 = gs.render(cam, seed=1, precision=prec)  # no sky, no ray: ray_casting.rs:113-116
+        assert rgb0.max() == 0.0 and rgb8_0.max() == 0 and st0["rays"] == 0 and st0["samples"] == 64 * 36
+    # the cached arena can be given back between renders and the next render allocates again
+    abi.check(abi.load().cr_device_trim(gpu_device))
+    sc.scene_cam.set_max_depth(3)
+    cam = sc.scene_cam.to_abi()
+    rgb3, _, _ = gs.render(cam, seed=1)
+    ref3, _, _ = orc.render(cam, seed=1)
+    assert np.abs(rgb3 - ref3).max() <= TOL_F64
 
 
 def test_f32_render_statistical_parity(gpu_device, oracle):
