@@ -20,6 +20,7 @@ CR_PRECISION_F64, CR_PRECISION_F32 = 0, 1
 CR_MAX_CAM_KEYS = 32
 CR_PPM_P3, CR_PPM_P6 = 0, 1
 CR_BVH_AUTO, CR_BVH_HOST, CR_BVH_DEVICE = 0, 1, 2
+CR_RENDER_GLOBAL_ROWS = 1
 
 
 class CrMaterial(C.Structure):
@@ -52,7 +53,8 @@ class CrCamera(C.Structure):
 
 class CrRenderOpts(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("precision", C.c_int32), ("pool_paths", C.c_uint32),
-                ("row_block", C.c_uint32), ("row_rank", C.c_uint32), ("row_world", C.c_uint32), ("time_kernels", C.c_uint32)]
+                ("row_block", C.c_uint32), ("row_rank", C.c_uint32), ("row_world", C.c_uint32), ("time_kernels", C.c_uint32),
+                ("flags", C.c_uint32)]
 
 
 class CrStats(C.Structure):
@@ -116,6 +118,11 @@ SIGNATURES = {
     "cr_trace_batch": (C.c_int, [_P, _P, C.c_size_t, C.c_double, C.c_double, C.c_int, _P]),
     "cr_render": (C.c_int, [_P, C.POINTER(CrCamera), C.POINTER(CrRenderOpts), _P, _P, C.POINTER(CrStats)]),
     "cr_render_device": (C.c_int, [_P, C.POINTER(CrCamera), C.POINTER(CrRenderOpts), _P, _P, _P, C.POINTER(CrStats)]),
+    "cr_scene_replicate": (_P, [_P, C.c_int]),
+    "cr_render_multi": (C.c_int, [_P, C.c_int, C.POINTER(CrCamera), C.POINTER(CrRenderOpts), _P, _P, _P]),
+    "cr_shared_buffer_create": (C.c_int, [C.c_int, C.c_size_t, C.POINTER(C.c_void_p), _P]),
+    "cr_shared_buffer_open": (C.c_int, [C.c_int, _P, C.POINTER(C.c_void_p)]),
+    "cr_shared_buffer_close": (C.c_int, [C.c_int, _P, C.c_int]),
     "cr_write_ppm": (C.c_int, [C.c_char_p, _P, C.c_uint32, C.c_uint32, C.c_int]),
     "cr_render_to_file": (C.c_int, [_P, C.POINTER(CrCamera), C.POINTER(CrRenderOpts), C.c_char_p, C.c_int, C.POINTER(CrStats)]),
     "cr_render_frames": (C.c_int, [_P, C.POINTER(CrCamera), C.POINTER(CrRenderOpts), C.c_uint32, C.c_uint32, C.c_uint32, C.c_char_p,

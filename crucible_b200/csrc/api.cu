@@ -78,6 +78,10 @@ struct CrScene {
     size_t out_cap = 0;
     void* d_io = nullptr;  // trace_batch staging
     size_t io_cap = 0;
+    // cr_render_multi: the assembled image on this (the first) device; plain cudaMalloc so that peers can map it
+    void* d_multi_rgb = nullptr;
+    void* d_multi_rgb8 = nullptr;
+    size_t multi_cap = 0;
 
     void free_flat_tree() {
         if (d_flat_nodes) cudaFreeAsync(d_flat_nodes, stream);
@@ -664,6 +668,8 @@ void cr_scene_destroy(CrScene* s) {
         if (s->d_out_rgb) cudaFreeAsync(s->d_out_rgb, s->stream);
         if (s->d_out_rgb8) cudaFreeAsync(s->d_out_rgb8, s->stream);
         if (s->d_io) cudaFreeAsync(s->d_io, s->stream);
+        if (s->d_multi_rgb) cudaFree(s->d_multi_rgb);
+        if (s->d_multi_rgb8) cudaFree(s->d_multi_rgb8);
         if (s->stream) cudaStreamDestroy(s->stream);  // resources are released once the queued work has drained
     }
     delete s;
@@ -1043,9 +1049,10 @@ int cr_render_device(CrScene* s, const CrCamera* cam, const CrRenderOpts* opts, 
     std::lock_guard<std::mutex> device_lock(device_slot(s->device).mu);
     // device variant: rows of this rank are written PACKED ([rows_local][W][3]) so the result is the
     // NCCL gather send buffer as is
+    const int packed = (opts->flags & CR_RENDER_GLOBAL_ROWS) ? 0 : 1;
     rc = (opts->precision == CR_PRECISION_F32)
-             ? render_impl<float>(s->dev, device_workspace(s->device), *cam, *opts, d_out_rgb, d_out_rgb8, 1, st, stats, err)
-             : render_impl<double>(s->dev, device_workspace(s->device), *cam, *opts, d_out_rgb, d_out_rgb8, 1, st, stats, err);
+             ? render_impl<float>(s->dev, device_workspace(s->device), *cam, *opts, d_out_rgb, d_out_rgb8, packed, st, stats, err)
+             : render_impl<double>(s->dev, device_workspace(s->device), *cam, *opts, d_out_rgb, d_out_rgb8, packed, st, stats, err);
     if (rc != CR_OK) return fail(rc, err);
     return CR_OK;
 }
@@ -1097,6 +1104,212 @@ int cr_render(CrScene* s, const CrCamera* cam, const CrRenderOpts* opts, double*
     }
     cudaEventDestroy(a);
     cudaEventDestroy(b);
+    return CR_OK;
+}
+
+// ---- multi-GPU behind the boundary (SURVEY 8b cr_init(devices, n), 8e) -------------------------------------------
+extern "C" CrScene* cr_scene_replicate(const CrScene* src, int device) {
+    if (!src) {
+        g_err = "cr_scene_replicate: null scene";
+        return nullptr;
+    }
+    CrScene* s = cr_scene_create(device);
+    if (!s) return nullptr;
+    s->elements = src->elements;
+    s->spheres = src->spheres;
+    s->tris = src->tris;
+    s->quads = src->quads;
+    for (int k = 0; k < 3; ++k) {
+        s->mat_of[k] = src->mat_of[k];
+        s->obj_of[k] = src->obj_of[k];
+        s->prim_of[k] = src->prim_of[k];
+    }
+    s->mats = src->mats;
+    s->texs = src->texs;
+    for (const HostImage& im : src->images) {
+        HostImage c;
+        c.w = im.w;
+        c.h = im.h;
+        c.rgb = im.rgb;
+        s->images.push_back(std::move(c));
+    }
+    s->sky_kind = src->sky_kind;
+    s->sky_image = src->sky_image;
+    s->anim = src->anim;
+    s->bvh_builder = src->bvh_builder;
+    if (cr_scene_commit(s) != CR_OK) {
+        const std::string keep = g_err;
+        cr_scene_destroy(s);
+        g_err = keep;
+        return nullptr;
+    }
+    return s;
+}
+
+extern "C" int cr_render_multi(CrScene* const* replicas, int n, const CrCamera* cam, const CrRenderOpts* opts, double* out_rgb,
+                               uint8_t* out_rgb8, CrStats* stats) {
+    if (!replicas || n < 1 || n > 64) return fail(CR_ERR_INVALID, "cr_render_multi: 1..64 replicas");
+    int rc;
+    for (int i = 0; i < n; ++i) {
+        if ((rc = need_device(replicas[i])) != CR_OK) return rc;
+        for (int j = 0; j < i; ++j)
+            if (replicas[j]->device == replicas[i]->device) return fail(CR_ERR_INVALID, "cr_render_multi: two replicas on one device");
+    }
+    if ((rc = check_camera(cam)) != CR_OK) return rc;
+    if (!opts) return fail(CR_ERR_INVALID, "null opts");
+    CrScene* s0 = replicas[0];
+    const int dev0 = s0->device;
+    const size_t npix = (size_t)cam->image_width * cam->image_height;
+    API_CUDA(cudaSetDevice(dev0));
+    if (npix > s0->multi_cap) {
+        if (s0->d_multi_rgb) cudaFree(s0->d_multi_rgb);
+        if (s0->d_multi_rgb8) cudaFree(s0->d_multi_rgb8);
+        s0->d_multi_rgb = s0->d_multi_rgb8 = nullptr;
+        s0->multi_cap = 0;
+        API_CUDA(cudaMalloc(&s0->d_multi_rgb, npix * 3 * sizeof(double)));
+        API_CUDA(cudaMalloc(&s0->d_multi_rgb8, npix * 3));
+        s0->multi_cap = npix;
+    }
+    // can every other device store into device 0's memory?  (NVLink / NVSwitch: yes)
+    std::vector<char> direct((size_t)n, 1);
+    for (int i = 1; i < n; ++i) {
+        int can = 0;
+        API_CUDA(cudaDeviceCanAccessPeer(&can, replicas[i]->device, dev0));
+        if (can) {
+            API_CUDA(cudaSetDevice(replicas[i]->device));
+            const cudaError_t e = cudaDeviceEnablePeerAccess(dev0, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) can = 0;
+            cudaGetLastError();
+        }
+        direct[(size_t)i] = (char)can;
+    }
+    const uint32_t W = cam->image_width, H = cam->image_height;
+    const uint32_t block = opts->row_block == 0 ? 8 : opts->row_block;
+    std::vector<int> rcs((size_t)n, CR_OK);
+    std::vector<std::string> errs((size_t)n);
+    std::vector<CrStats> st((size_t)n);
+    auto work = [&](int i) {
+        CrScene* s = replicas[i];
+        std::string& err = errs[(size_t)i];
+        auto cuda_ok = [&](cudaError_t e, const char* what) {
+            if (e == cudaSuccess) return true;
+            rcs[(size_t)i] = CR_ERR_CUDA;
+            err = std::string(what) + ": " + cudaGetErrorString(e);
+            return false;
+        };
+        if (!cuda_ok(cudaSetDevice(s->device), "cudaSetDevice")) return;
+        CrRenderOpts o = *opts;
+        o.row_block = block;
+        o.row_rank = (uint32_t)i;
+        o.row_world = (uint32_t)n;
+        memset(&st[(size_t)i], 0, sizeof(CrStats));
+        void* d_rgb = out_rgb ? s0->d_multi_rgb : nullptr;
+        void* d_rgb8 = out_rgb8 ? s0->d_multi_rgb8 : nullptr;
+        int packed = 0;
+        if (!direct[(size_t)i]) {
+            // no peer mapping: render packed rows locally, then copy each row block to its place on device 0
+            uint32_t rows_local = 0;
+            for (uint32_t j = 0; j < H; ++j)
+                if ((j / block) % (uint32_t)n == (uint32_t)i) ++rows_local;
+            const size_t lp = (size_t)rows_local * W;
+            if (lp > s->out_cap) {
+                if (s->d_out_rgb) cudaFreeAsync(s->d_out_rgb, s->stream);
+                if (s->d_out_rgb8) cudaFreeAsync(s->d_out_rgb8, s->stream);
+                s->d_out_rgb = s->d_out_rgb8 = nullptr;
+                s->out_cap = 0;
+                if (!cuda_ok(cudaMallocAsync(&s->d_out_rgb, lp * 3 * sizeof(double), s->stream), "cudaMallocAsync")) return;
+                if (!cuda_ok(cudaMallocAsync(&s->d_out_rgb8, lp * 3, s->stream), "cudaMallocAsync")) return;
+                s->out_cap = lp;
+            }
+            d_rgb = out_rgb ? s->d_out_rgb : nullptr;
+            d_rgb8 = out_rgb8 ? s->d_out_rgb8 : nullptr;
+            packed = 1;
+        }
+        {
+            std::lock_guard<std::mutex> device_lock(device_slot(s->device).mu);
+            rcs[(size_t)i] = (o.precision == CR_PRECISION_F32)
+                                 ? render_impl<float>(s->dev, device_workspace(s->device), *cam, o, d_rgb, d_rgb8, packed, s->stream, &st[(size_t)i], err)
+                                 : render_impl<double>(s->dev, device_workspace(s->device), *cam, o, d_rgb, d_rgb8, packed, s->stream, &st[(size_t)i], err);
+        }
+        if (rcs[(size_t)i] != CR_OK || !packed) return;
+        uint32_t lrow = 0;
+        for (uint32_t j0 = 0; j0 < H; j0 += block) {
+            if ((j0 / block) % (uint32_t)n != (uint32_t)i) continue;
+            const uint32_t rows = std::min(block, H - j0);
+            const size_t src = (size_t)lrow * W * 3, dst = (size_t)j0 * W * 3, cnt = (size_t)rows * W * 3;
+            if (out_rgb && !cuda_ok(cudaMemcpyPeerAsync(static_cast<double*>(s0->d_multi_rgb) + dst, dev0, static_cast<double*>(d_rgb) + src,
+                                                        s->device, cnt * sizeof(double), s->stream), "cudaMemcpyPeerAsync")) return;
+            if (out_rgb8 && !cuda_ok(cudaMemcpyPeerAsync(static_cast<uint8_t*>(s0->d_multi_rgb8) + dst, dev0, static_cast<uint8_t*>(d_rgb8) + src,
+                                                         s->device, cnt, s->stream), "cudaMemcpyPeerAsync")) return;
+            lrow += rows;
+        }
+        cuda_ok(cudaStreamSynchronize(s->stream), "cudaStreamSynchronize");
+    };
+    {
+        std::vector<std::thread> th;
+        for (int i = 1; i < n; ++i) th.emplace_back(work, i);
+        work(0);
+        for (auto& t : th) t.join();
+    }
+    for (int i = 0; i < n; ++i)
+        if (rcs[(size_t)i] != CR_OK) return fail(rcs[(size_t)i], "replica " + std::to_string(i) + ": " + errs[(size_t)i]);
+    // every replica's stream has drained, so every peer store has landed: one device-to-host copy of the assembled image
+    API_CUDA(cudaSetDevice(dev0));
+    cudaEvent_t a, b;
+    API_CUDA(cudaEventCreate(&a));
+    API_CUDA(cudaEventCreate(&b));
+    API_CUDA(cudaEventRecord(a, s0->stream));
+    if (out_rgb) API_CUDA(cudaMemcpyAsync(out_rgb, s0->d_multi_rgb, npix * 3 * sizeof(double), cudaMemcpyDeviceToHost, s0->stream));
+    if (out_rgb8) API_CUDA(cudaMemcpyAsync(out_rgb8, s0->d_multi_rgb8, npix * 3, cudaMemcpyDeviceToHost, s0->stream));
+    API_CUDA(cudaEventRecord(b, s0->stream));
+    API_CUDA(cudaEventSynchronize(b));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    st[0].ms_d2h = ms;
+    if (stats)
+        for (int i = 0; i < n; ++i) stats[i] = st[(size_t)i];
+    return CR_OK;
+}
+
+extern "C" int cr_shared_buffer_create(int device, size_t bytes, void** dptr, unsigned char handle[64]) {
+    if (!dptr || !handle || bytes == 0) return fail(CR_ERR_INVALID, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "the ABI ships the IPC handle as 64 bytes");
+    const DeviceInfo& di = device_info(device);
+    if (di.state != 1) return fail(CR_ERR_NO_DEVICE, di.why);
+    API_CUDA(cudaSetDevice(device));
+    void* p = nullptr;
+    API_CUDA(cudaMalloc(&p, bytes));
+    cudaIpcMemHandle_t h;
+    const cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        return fail(CR_ERR_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e));
+    }
+    memcpy(handle, &h, 64);
+    *dptr = p;
+    return CR_OK;
+}
+extern "C" int cr_shared_buffer_open(int device, const unsigned char handle[64], void** dptr) {
+    if (!dptr || !handle) return fail(CR_ERR_INVALID, "null argument");
+    const DeviceInfo& di = device_info(device);
+    if (di.state != 1) return fail(CR_ERR_NO_DEVICE, di.why);
+    API_CUDA(cudaSetDevice(device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    void* p = nullptr;
+    API_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    *dptr = p;
+    return CR_OK;
+}
+extern "C" int cr_shared_buffer_close(int device, void* dptr, int owner) {
+    if (!dptr) return CR_OK;
+    const DeviceInfo& di = device_info(device);
+    if (di.state != 1) return fail(CR_ERR_NO_DEVICE, di.why);
+    API_CUDA(cudaSetDevice(device));
+    if (owner) API_CUDA(cudaFree(dptr));
+    else API_CUDA(cudaIpcCloseMemHandle(dptr));
     return CR_OK;
 }
 

@@ -259,7 +259,8 @@ CONFIGS = {
     "cornell": lambda **kw: cornell_box(image_width=kw.get("image_width", 1024), samples=kw.get("samples", 1000)),
     "teapot": lambda **kw: load_teapot(image_width=kw.get("image_width", 1920), samples=kw.get("samples", 256)),
     "instanced": lambda **kw: instanced_teapots(image_width=kw.get("image_width", 3840), samples=kw.get("samples", 64),
-                                                copies=kw.get("copies", 1582)),
+                                                copies=kw.get("copies", 1582), grid=kw.get("grid", 40),
+                                                spacing=kw.get("spacing", 4.0)),
     "walkthrough": lambda **kw: book1_walkthrough(image_width=kw.get("image_width", 1920), samples=kw.get("samples", 64),
                                                   seed=kw.get("seed", 1)),
 }

@@ -35,6 +35,15 @@ class GpuScene:
             self.lib.cr_scene_destroy(self.handle)
             self.handle = None
 
+    def replicate(self, device: int) -> "GpuScene":
+        """A committed copy of this scene on another device (cr_scene_replicate): the replicas of cr_render_multi."""
+        h = self.lib.cr_scene_replicate(self.handle, device)
+        if not h:
+            raise abi.CrucibleError(abi.CR_ERR_CUDA, self.lib.cr_last_error().decode())
+        other = object.__new__(GpuScene)
+        other.lib, other.device, other.handle, other.desc = self.lib, device, h, self.desc
+        return other
+
     def __del__(self):
         try:
             self.close()
@@ -104,12 +113,37 @@ class GpuScene:
 
     # ---- device variant: packed rows of this rank into caller-owned device memory, on the caller's stream
     def render_device(self, cam: abi.CrCamera, d_out_rgb: int, d_out_rgb8: int, stream: int = 0, seed=1,
-                      precision=abi.CR_PRECISION_F64, pool_paths=0, row_block=8, row_rank=0, row_world=1, time_kernels=False):
-        opts = abi.CrRenderOpts(seed, precision, pool_paths, row_block, row_rank, row_world, 1 if time_kernels else 0)
+                      precision=abi.CR_PRECISION_F64, pool_paths=0, row_block=8, row_rank=0, row_world=1, time_kernels=False,
+                      global_rows=False):
+        """global_rows: the outputs are full [H][W][3] images (possibly on another device / in another process' buffer)
+        and this rank's rows are stored at their global position (CR_RENDER_GLOBAL_ROWS)."""
+        opts = abi.CrRenderOpts(seed, precision, pool_paths, row_block, row_rank, row_world, 1 if time_kernels else 0,
+                                abi.CR_RENDER_GLOBAL_ROWS if global_rows else 0)
         st = abi.CrStats()
         abi.check(self.lib.cr_render_device(self.handle, C.byref(cam), C.byref(opts), C.c_void_p(d_out_rgb or None),
                                             C.c_void_p(d_out_rgb8 or None), C.c_void_p(stream or None), C.byref(st)))
         return st.as_dict()
+
+
+def render_multi(replicas, cam: abi.CrCamera, seed=1, precision=abi.CR_PRECISION_F64, pool_paths=0, row_block=8,
+                 time_kernels=False, want_rgb=True, want_rgb8=True, out_rgb=None, out_rgb8=None):
+    """Camera::render over several devices of ONE process (cr_render_multi): `replicas` = GpuScene copies of one scene on
+    different devices (GpuScene.replicate); rows are sharded in interleaved blocks, every device's resolve kernel stores
+    its rows into the image on replicas[0]'s device, one device-to-host copy.  Returns (rgb, rgb8, [stats per replica])."""
+    H, W = cam.image_height, cam.image_width
+    if want_rgb and out_rgb is None:
+        out_rgb = np.zeros((H, W, 3), np.float64)
+    if want_rgb8 and out_rgb8 is None:
+        out_rgb8 = np.zeros((H, W, 3), np.uint8)
+    n = len(replicas)
+    handles = (C.c_void_p * n)(*[r.handle for r in replicas])
+    opts = abi.CrRenderOpts(seed, precision, pool_paths, row_block, 0, 1, 1 if time_kernels else 0, 0)
+    stats = (abi.CrStats * n)()
+    abi.check(replicas[0].lib.cr_render_multi(handles, n, C.byref(cam), C.byref(opts),
+                                               out_rgb.ctypes.data_as(C.c_void_p) if out_rgb is not None else None,
+                                               out_rgb8.ctypes.data_as(C.c_void_p) if out_rgb8 is not None else None,
+                                               C.cast(stats, C.c_void_p)))
+    return out_rgb, out_rgb8, [stats[i].as_dict() for i in range(n)]
 
 
 def rows_of_rank(height, row_block, rank, world):

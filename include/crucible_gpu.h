@@ -144,7 +144,13 @@ typedef struct CrRenderOpts {
      * bit-identical to a single-GPU render. */
     uint32_t row_block, row_rank, row_world;
     uint32_t time_kernels; /* 1 = bracket every kernel class with CUDA events (CrStats.ms_*) */
+    uint32_t flags;        /* CR_RENDER_* bits */
 } CrRenderOpts;
+/* cr_render_device only: d_out_rgb / d_out_rgb8 are FULL [H][W][3] images and this rank's rows are written at their
+ * global position (default: the rank's rows packed, [rows_local][W][3]).  The image may live on ANOTHER device
+ * (peer-mapped memory, or a buffer opened with cr_shared_buffer_open): the resolve kernel then stores its rows
+ * straight into that device's memory over NVLink, which is the whole framebuffer gather of SURVEY 8e. */
+#define CR_RENDER_GLOBAL_ROWS 1u
 
 typedef struct CrStats {
     uint64_t samples;      /* camera samples generated (W*H*spp over the rows rendered) */
@@ -299,6 +305,30 @@ int cr_render(CrScene*, const CrCamera*, const CrRenderOpts*, double* out_rgb, u
  * after the stream has drained.  Used by the multi-GPU driver, which gathers rows over NCCL. */
 int cr_render_device(CrScene*, const CrCamera*, const CrRenderOpts*, void* d_out_rgb,
                      void* d_out_rgb8, void* cuda_stream, CrStats* stats);
+
+/* ---- multi-GPU behind the boundary (the `cr_init` over a device list, and 8e) ----
+ * Stills shard by interleaved row blocks, the scene is replicated, and the only exchange is the framebuffer: every
+ * device's resolve kernel writes its rows directly into the image on the first device (peer stores over NVLink /
+ * NVSwitch; block copies when two devices cannot map each other), followed by ONE device-to-host copy.  The RNG is
+ * keyed by the global pixel index, so the image is bit-identical to a single-device cr_render. */
+/* A committed copy of `src` on another device (same primitives, materials, images, sky, keyframes, hidden flags and
+ * BVH builder; the copy builds its own tree, which is the same tree).  NULL on failure. */
+CrScene* cr_scene_replicate(const CrScene* src, int device);
+/* Camera::render's sample loop over n devices from ONE host thread's point of view (the call drives one worker
+ * thread per device).  replicas[i] must be committed copies of one scene on n DIFFERENT devices; replicas[0]'s
+ * device assembles the image.  opts->row_rank / row_world are ignored (set per replica); opts->row_block = rows per
+ * interleaved block (0 = 8).  out_rgb / out_rgb8 as for cr_render (either may be NULL).  stats: n entries or NULL
+ * (entry i = replica i; ms_d2h of entry 0 = the final copy). */
+int cr_render_multi(CrScene* const* replicas, int n, const CrCamera*, const CrRenderOpts*, double* out_rgb,
+                    uint8_t* out_rgb8, CrStats* stats);
+/* One process per GPU (torchrun-style launch): the rank that assembles the image creates a device buffer other
+ * processes can map, ships the 64-byte handle to them by any means (a torch.distributed broadcast in
+ * crucible_b200.multigpu), and every rank renders with CR_RENDER_GLOBAL_ROWS into it through cr_render_device.
+ * create: cudaMalloc + cudaIpcGetMemHandle on `device`; open: cudaIpcOpenMemHandle in the calling process for use
+ * from `device`; close: owner != 0 frees the allocation, owner == 0 unmaps it. */
+int cr_shared_buffer_create(int device, size_t bytes, void** dptr, unsigned char handle[64]);
+int cr_shared_buffer_open(int device, const unsigned char handle[64], void** dptr);
+int cr_shared_buffer_close(int device, void* dptr, int owner);
 
 /* ---- the file-writing tail of the path ---- */
 typedef enum CrImageFormat {

@@ -1305,7 +1305,9 @@ int orc_render(const OrcScene* h, const CrCamera* cam_in, uint64_t seed, uint32_
  *  kind 0: pixel-centre primary rays (offset 0, no lens, time = frame time), n must be W*H
  *  kind 1: first-bounce rays: sample (pixel = k % (W*H), sample = k / (W*H)) of the camera stream,
  *          traced and scattered once; a ray that misses / is absorbed is replaced by its camera ray.
- *  kind 2: the camera sample rays themselves (jitter, lens, shutter). */
+ *  kind 2: the camera sample rays themselves (jitter, lens, shutter).
+ *  kind 3: as kind 1 with the pixels spread over the whole image (pixel = k * 2654435761 mod W*H), so that a batch
+ *          smaller than the image still sees the whole scene. */
 int orc_gen_rays(const OrcScene* h, const CrCamera* cam_in, uint64_t seed, int kind, size_t n, double* out) {
     const Scene& sc = *reinterpret_cast<const Scene*>(h);
     Cam cam;
@@ -1314,6 +1316,7 @@ int orc_gen_rays(const OrcScene* h, const CrCamera* cam_in, uint64_t seed, int k
     Counters cn;
     for (size_t k = 0; k < n; ++k) {
         uint32_t pixel = (uint32_t)(k % wh), sample = (uint32_t)(k / wh);
+        if (kind == 3) pixel = (uint32_t)(((uint64_t)k * 2654435761ull) % wh);
         uint32_t i = pixel % cam.c.image_width, j = pixel / cam.c.image_width;
         Ray r;
         if (kind == 0) {
@@ -1324,7 +1327,7 @@ int orc_gen_rays(const OrcScene* h, const CrCamera* cam_in, uint64_t seed, int k
         } else {
             Rng g(seed, pixel, sample, 0);
             r = cam.sample_ray(i, j, g);
-            if (kind == 1) {
+            if (kind == 1 || kind == 3) {
                 if (!sc.built) return CR_ERR_STATE;
                 HitRecord hr;
                 if (world_hit(sc, r, Interval{0.001, INF}, hr, cn)) {
