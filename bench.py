@@ -1,14 +1,15 @@
 #!/usr/bin/env python
-"""bench.py — BASELINE.json's metric on BASELINE.json's config.
+"""bench.py — BASELINE.json's metric (Msamples/s, Mrays/s) on BASELINE.json's configs.
 
-  python bench.py --gpus N --steps K --warmup W            # the CUDA path (this repo)
-  python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host cores
+  python bench.py --gpus N --steps K --warmup W [--config book1|cornell|teapot|instanced|walkthrough]
+  python bench.py --impl reference ...          # the reference algorithm (oracle port) on the host cores
 
-A "step" is one full pass of the hot path over one batch of synthetic input: one `Camera::render` of the
-seeded book1 end scene at 1920x1080, 100 spp, max depth 50 (207.36 M camera samples).  For N > 1 the same
-image is sharded by interleaved row blocks over the ranks (strong scaling; the only exchange is the NCCL
-framebuffer gather).  Timing: CUDA events around every step on the launching stream, L2 flushed between
-steps, max over ranks.
+A "step" is one full pass of the hot path over one batch of synthetic input: one `Camera::render` of the seeded scene
+at the config's full resolution / spp / depth (default config: book1 1920x1080, 100 spp, depth 50 = 207.36 M camera
+samples; `walkthrough`: 24 consecutive frames of the 240-frame movie).  For N > 1 a still is sharded by interleaved
+row blocks over the ranks (strong scaling; the only exchange is the framebuffer: every rank's resolve kernel stores
+its rows into rank 0's image over NVLink), a movie by whole frames (no exchange).  Timing: CUDA events around every
+step on the launching stream, L2 flushed between steps, max over ranks.
 """
 from __future__ import annotations
 
@@ -25,8 +26,23 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOAD = dict(scene="book1", image_width=1920, samples=100, seed=1)
-WORKLOAD_NAME = "book1 end scene 1920x1080, 100 spp, max depth 50 (BASELINE configs[0]; the config the metric is quoted on)"
+# BASELINE.json configs[0..4].  `bound`: what SURVEY 8d names as the roofline of the trace kernel on that config.
+CONFIGS = {
+    "book1": dict(kw=dict(image_width=1920, samples=100, seed=1), bound="fp64",
+                  title="book1 end scene 1920x1080, 100 spp, max depth 50 (BASELINE configs[0]; the config the metric is quoted on)"),
+    "cornell": dict(kw=dict(image_width=1024, samples=1000), bound="fp64",
+                    title="Cornell box of quads + emissive light 1024x1024, 1000 spp, max depth 50 (BASELINE configs[1])"),
+    "teapot": dict(kw=dict(image_width=1920, samples=256), bound="fp64",
+                   title="teapot.obj mesh + spherical sky 1920x1080, 256 spp, max depth 50 (BASELINE configs[2])"),
+    "instanced": dict(kw=dict(image_width=3840, samples=64), bound="hbm",
+                      title="9 998 240 flattened teapot triangles + earthmap textures 3840x2160, 64 spp, max depth 50 (BASELINE configs[3])"),
+    "walkthrough": dict(kw=dict(image_width=1920, samples=64, seed=1), bound="fp64", frames_per_step=24,
+                        title="book1 walk-through 1920x1080, 64 spp, max depth 50: 24 consecutive frames of the 240-frame movie per step "
+                              "(BASELINE configs[4]), whole frames sharded over the ranks"),
+}
+TRAFFIC_FILES = {"book1": "trace_book1_traffic.json", "instanced": "trace_cfg4_traffic.json", "cornell": "trace_cornell_traffic.json",
+                 "teapot": "trace_teapot_traffic.json"}
+SEED = 1
 
 
 def dist_env():
@@ -83,30 +99,53 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def oracle_sample(desc, cam, row_step, threads=0):
-    """The CPU path (oracle port of the reference algorithm) on a bounded sample: every row_step-th row of
-    the same image at full spp.  Returns (stats dict, per-segment traversal counters)."""
+def build_config(name, samples=0):
+    from crucible_b200 import demo_builder
+
+    cfg = CONFIGS[name]
+    kw = dict(cfg["kw"])
+    if samples:
+        kw["samples"] = samples
+    sc = demo_builder.CONFIGS[name](**kw)
+    return cfg, sc, sc.describe(), sc.scene_cam.to_abi()
+
+
+_ORACLE_SCENES = {}
+
+
+def oracle_sample(desc, cam, row_step, threads=0, first_row=0):
+    """The CPU path (oracle port of the reference algorithm) on a bounded sample: rows first_row, first_row + row_step, ...
+    of the same image at full spp.  Returns the oracle's stats (samples, rays, seconds, traversal counters)."""
     from oracle import binding as oracle
 
-    orc = oracle.OracleScene(desc)
+    orc = _ORACLE_SCENES.get(id(desc))
+    if orc is None:
+        orc = _ORACLE_SCENES[id(desc)] = oracle.OracleScene(desc)  # config 4: the oracle builds its tree on one core (~70 s, untimed)
     threads = threads or (os.cpu_count() or 1)
-    _, _, st = orc.render(cam, seed=WORKLOAD["seed"], rows=(0, cam.image_height, row_step), threads=threads, want_rgb8=False)
+    _, _, st = orc.render(cam, seed=SEED, rows=(first_row, cam.image_height, row_step), threads=threads, want_rgb8=False)
     return st
 
 
-def hbm_view(alg_bytes_per_launch, dur_s, traffic):
-    peak, src = 6533.5, "fallback"
+def sized_oracle_sample(desc, cam, seconds, threads):
+    """Probe with the two rows at 1/3 and 2/3 of the image height, then size an evenly spread row sample for about
+    `seconds` of CPU work (at least one row: Cornell's 1000 spp make a single row 1 M samples)."""
+    H, W = cam.image_height, cam.image_width
+    probe = oracle_sample(desc, cam, max(1, H // 3), threads, first_row=H // 3)
+    rate = probe["samples"] / max(probe["seconds"], 1e-6)
+    n_rows = max(1.0, rate * seconds / (W * cam.samples))
+    row_step = int(max(1, min(H, round(H / n_rows))))
+    return oracle_sample(desc, cam, row_step, threads, first_row=row_step // 2), row_step
+
+
+def measured_hbm_peak():
+    peak, src = 6650.0, "fallback (B200_PROFILING.md)"
     try:
         mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        for k in ("hbm_gbs", "hbm_gbps", "hbm_copy_gbps"):
-            if k in mp:
-                peak, src = float(mp[k]), f"MEASURED_PEAKS.json:{k}"
-                break
+        if "hbm_gbs" in mp:
+            peak, src = float(mp["hbm_gbs"]), "MEASURED_PEAKS.json:hbm_gbs"
     except Exception:
         pass
-    ach = alg_bytes_per_launch / dur_s / 1e9
-    return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": src,
-            "dram_gbps_measured": (traffic / dur_s / 1e9) if traffic else None}
+    return peak, src
 
 
 def run_reference(args):
@@ -116,29 +155,23 @@ def run_reference(args):
     rank, world, _ = dist_env()
     if rank != 0:
         return
-    from crucible_b200 import demo_builder
-
-    sc = demo_builder.book1_end_scene(image_width=WORKLOAD["image_width"], samples=WORKLOAD["samples"], seed=WORKLOAD["seed"])
-    desc, cam = sc.describe(), sc.scene_cam.to_abi()
+    cfg, sc, desc, cam = build_config(args.config, args.samples)
     threads = os.cpu_count() or 1
-    # size the sample so that one step is roughly 5-10 s of wall time on this box
-    t0 = time.time()
-    st = oracle_sample(desc, cam, 120, threads)
-    rate = st["samples"] / max(time.time() - t0, 1e-6)
-    row_step = int(max(1, min(120, round(cam.image_height * cam.image_width * cam.samples / max(rate * 6.0, 1.0)))))
+    H, W = cam.image_height, cam.image_width
+    st, row_step = sized_oracle_sample(desc, cam, 6.0, threads)  # one step = roughly 6 s of wall time on this box
     for _ in range(args.warmup):
-        oracle_sample(desc, cam, max(row_step, 60), threads)
+        oracle_sample(desc, cam, max(row_step, H // 2), threads, first_row=H // 2)
     secs, samples, rays = 0.0, 0, 0
     for _ in range(args.steps):
-        st = oracle_sample(desc, cam, row_step, threads)
+        st = oracle_sample(desc, cam, row_step, threads, first_row=row_step // 2)
         secs += st["seconds"]
         samples += st["samples"]
         rays += st["rays"]
     val = samples / secs / 1e6
-    sample_desc = f"rows j % {row_step} == 0 of the 1920x1080x100spp job ({samples // args.steps} samples per step)"
+    sample_desc = f"rows j % {row_step} == {row_step // 2} of the {W}x{H}x{cam.samples}spp job ({samples // args.steps} samples per step)"
     line = {"impl": "reference", "metric": "Msamples/s", "value": val, "unit": "Msamples/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": WORKLOAD_NAME, "sample": sample_desc},
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": cfg["title"], "sample": sample_desc},
             "mrays_per_s": rays / secs / 1e6,
             "cpu_baseline": {"value": val, "unit": "Msamples/s", "cores": threads, "kind": "port", "sample": sample_desc},
             "e2e": {"value": val, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -151,9 +184,11 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="crucible_b200")
+    ap.add_argument("--config", default="book1", choices=list(CONFIGS))
     ap.add_argument("--precision", default="f64", choices=["f64", "f32"])
     ap.add_argument("--pool", type=int, default=0)
-    ap.add_argument("--samples", type=int, default=WORKLOAD["samples"], help="debug only: a reduced-spp run is NOT the headline")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="N > 1 framebuffer exchange (crucible_b200.multigpu)")
+    ap.add_argument("--samples", type=int, default=0, help="debug only: a reduced-spp run is NOT the headline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -162,8 +197,8 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from crucible_b200 import abi, demo_builder, multigpu
-    from crucible_b200.gpu import GpuScene, rows_of_rank
+    from crucible_b200 import abi, multigpu
+    from crucible_b200.gpu import GpuScene
 
     rank, world, local = dist_env()
     assert torch.cuda.is_available(), "bench.py needs a B200: crucible_b200 has no CPU fallback"
@@ -173,17 +208,37 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     precision = abi.CR_PRECISION_F64 if args.precision == "f64" else abi.CR_PRECISION_F32
 
-    sc = demo_builder.book1_end_scene(image_width=WORKLOAD["image_width"], samples=args.samples, seed=WORKLOAD["seed"])
-    desc, cam = sc.describe(), sc.scene_cam.to_abi()
+    cfg, sc, desc, cam = build_config(args.config, args.samples)
     H, W = cam.image_height, cam.image_width
+    movie = "frames_per_step" in cfg
+    fps = cfg.get("frames_per_step", 1)
     gs = GpuScene(desc, local)
     row_block = 8
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    frame_buf = torch.empty((H, W, 3), dtype=torch.uint8, device=dev) if movie else None
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    step_no = [0]
+
+    def add_stats(acc, st):
+        for k, v in st.items():
+            acc[k] = acc.get(k, 0) + v
+        return acc
 
     def step(time_kernels):
-        full, full8, st = multigpu.render_sharded(gs, cam, rank, world, seed=WORKLOAD["seed"], precision=precision,
-                                                  row_block=row_block, pool_paths=args.pool, time_kernels=time_kernels)
-        return st, full8
+        """One pass of the hot path over one batch, outputs left in device memory (bytes: what Camera::render consumes)."""
+        if not movie:
+            _, full8, st = multigpu.render_sharded(gs, cam, rank, world, seed=SEED, precision=precision, row_block=row_block,
+                                                   pool_paths=args.pool, time_kernels=time_kernels, want_rgb=False, exchange=args.exchange)
+            return st
+        first = (step_no[0] * fps) % 240
+        step_no[0] += 1
+        acc = {}
+        for f in range(first + rank, first + fps, world):  # whole frames: frame f -> rank f % world within the step
+            cam.frame = f
+            add_stats(acc, gs.render_device(cam, 0, frame_buf.data_ptr(), stream=stream, seed=SEED, precision=precision,
+                                            pool_paths=args.pool, time_kernels=time_kernels, global_rows=True))
+        cam.frame = 0
+        return acc
 
     def barrier():
         if world > 1:
@@ -203,7 +258,7 @@ def main():
     t_timed0 = time.perf_counter()
     for k in range(args.steps):
         ev[k][0].record()
-        st, _ = step(True)
+        st = step(True)
         ev[k][1].record()
         stats.append(st)
         flush.fill_(k)  # L2 flush between timed iterations, outside the events
@@ -211,33 +266,36 @@ def main():
     clocks = sampler.stop(t_timed0, time.perf_counter()) if rank == 0 else None
     ms = sum(a.elapsed_time(b) for a, b in ev)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    agg = torch.tensor([sum(s["samples"] for s in stats), sum(s["rays"] for s in stats), sum(s["launches"] for s in stats),
-                        sum(s["iterations"] for s in stats)], dtype=torch.float64, device=dev)
+    agg = torch.tensor([sum(s.get("samples", 0) for s in stats), sum(s.get("rays", 0) for s in stats), sum(s.get("launches", 0) for s in stats),
+                        sum(s.get("iterations", 0) for s in stats)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(agg, op=dist.ReduceOp.SUM)
     ms_total = float(t.item())
     samples, rays, launches, iters = (float(x) for x in agg.tolist())
 
-    # ---- e2e: the public API with HOST buffers.  Every step: scene description -> cr_scene_* (host BVH build
-    # as Scene::render_image does per frame, scene/mod.rs:333) -> H2D -> render -> gather -> D2H of the image.
-    h2d = sum(b[1].nbytes + b[2].nbytes + b[3].nbytes for b in desc.batches) + abi.C.sizeof(abi.CrCamera)
-    d2h = H * W * 3 * (8 + 1)
-    pinned = torch.empty((H, W, 3), dtype=torch.float64).pin_memory()
+    # ---- e2e: the public API with HOST buffers.  Every step: scene description -> cr_scene_* (BVH build as
+    # Scene::render_image does, scene/mod.rs:333) -> H2D -> render -> framebuffer exchange -> D2H of the bytes the
+    # reference writes to its PPM (camera/mod.rs:306-311).
+    h2d = sum(b[1].nbytes + b[2].nbytes + b[3].nbytes for b in desc.batches) + sum(im.nbytes for im in desc.images) + abi.C.sizeof(abi.CrCamera)
+    d2h = H * W * 3 * (fps if movie else 1)
     pinned8 = torch.empty((H, W, 3), dtype=torch.uint8).pin_memory()
-
-    pinned_np, pinned8_np = pinned.numpy(), pinned8.numpy()
+    pinned8_np = pinned8.numpy()
 
     def e2e_step():
         g = GpuScene(desc, local)
-        if world == 1:
-            # the reference-facing call itself: cr_render with HOST buffers (H2D of the camera, D2H of both images inside)
-            g.render(cam, seed=WORKLOAD["seed"], precision=precision, pool_paths=args.pool, out_rgb=pinned_np, out_rgb8=pinned8_np)
+        if movie:
+            for f in range(rank, fps, world):
+                cam.frame = f
+                g.render(cam, seed=SEED, precision=precision, pool_paths=args.pool, want_rgb=False, out_rgb8=pinned8_np)
+            cam.frame = 0
+        elif world == 1:
+            # the reference-facing call itself: cr_render with HOST buffers (H2D of the camera, D2H of the image inside)
+            g.render(cam, seed=SEED, precision=precision, pool_paths=args.pool, want_rgb=False, out_rgb8=pinned8_np)
         else:
-            full, full8, st = multigpu.render_sharded(g, cam, rank, world, seed=WORKLOAD["seed"], precision=precision,
-                                                      row_block=row_block, pool_paths=args.pool)
+            _, full8, st = multigpu.render_sharded(g, cam, rank, world, seed=SEED, precision=precision, row_block=row_block,
+                                                   pool_paths=args.pool, want_rgb=False, exchange=args.exchange)
             if rank == 0:
-                pinned.copy_(full, non_blocking=True)
                 pinned8.copy_(full8, non_blocking=True)
             torch.cuda.synchronize()
         g.close()
@@ -255,65 +313,68 @@ def main():
     e2e_s = float(te.item())
 
     if rank == 0:
-        total_samples_per_step = H * W * cam.samples
+        total_samples_per_step = H * W * cam.samples * fps
         value = samples / (ms_total * 1e-3) / 1e6
+        par = f"frames x{world}" if movie else f"rows x{world} (blocks of {row_block}), exchange {args.exchange if world > 1 else 'none'}"
         line = {"metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-                "config": {"workload": WORKLOAD_NAME, "parallelism": f"rows x{world} (blocks of {row_block})", "l2": "flushed between steps (256 MiB write)",
-                           "seed": WORKLOAD["seed"], "samples_per_step": total_samples_per_step, "spp": cam.samples},
+                "config": {"workload": cfg["title"], "name": args.config, "parallelism": par, "l2": "flushed between steps (256 MiB write)",
+                           "seed": SEED, "samples_per_step": total_samples_per_step, "spp": cam.samples, "output": "rgb8 bytes (device resident for `value`)"},
                 "mrays_per_s": rays / (ms_total * 1e-3) / 1e6,
                 "rays_per_sample": rays / samples,
                 "clocks": clocks,
                 "e2e": {"value": total_samples_per_step * args.steps / e2e_s / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h},
                 "gpu_launches": int(launches)}
-        # ---- roofline of the dominant kernel (k_trace): algorithmic flops per ray segment from the oracle's
+        # ---- roofline of the dominant kernel (k_trace): algorithmic work per ray segment from the oracle's
         # reference-order traversal counters, segments per launch from the run, duration from events
-        ms_trace = sum(s["ms_trace"] for s in stats)
-        ms_shade = sum(s["ms_shade"] for s in stats)
-        ms_gen = sum(s["ms_raygen"] for s in stats)
-        my_iters = sum(s["iterations"] for s in stats)
-        my_rays = sum(s["rays"] for s in stats)
+        ms_trace = sum(s.get("ms_trace", 0) for s in stats)
+        ms_shade = sum(s.get("ms_shade", 0) for s in stats)
+        ms_gen = sum(s.get("ms_raygen", 0) for s in stats)
+        my_iters = sum(s.get("iterations", 0) for s in stats)
+        my_rays = sum(s.get("rays", 0) for s in stats)
+        my_ms = sum(s.get("ms_total", 0) for s in stats)
         f64p, f32p = abi.C.c_double(), abi.C.c_double()
         abi.check(abi.load().cr_measure_fma_peak(local, abi.C.byref(f64p), abi.C.byref(f32p)))
-        cpu = None
+        threads = os.cpu_count() or 1
         if not args.no_cpu_baseline:
-            threads = os.cpu_count() or 1
-            probe = oracle_sample(desc, cam, 120, threads)  # 9 rows: sizes the sample for ~15 s of CPU work
-            rate = probe["samples"] / max(probe["seconds"], 1e-6)
-            row_step = int(max(1, min(120, round(total_samples_per_step / max(rate * 15.0, 1.0)))))
-            ost = oracle_sample(desc, cam, row_step, threads)
-            cpu = ost
-            line["cpu_baseline"] = {"value": ost["samples"] / ost["seconds"] / 1e6, "unit": "Msamples/s", "cores": threads, "kind": "port",
-                                    "sample": f"rows j % {row_step} == 0 of the same 1920x1080x{cam.samples}spp job ({ost['samples']} samples, {ost['seconds']:.1f} s)",
-                                    "mrays_per_s": ost["rays"] / ost["seconds"] / 1e6}
+            cpu, row_step = sized_oracle_sample(desc, cam, 15.0, threads)  # ~15 s of CPU work
+            line["cpu_baseline"] = {"value": cpu["samples"] / cpu["seconds"] / 1e6, "unit": "Msamples/s", "cores": threads, "kind": "port",
+                                    "sample": f"rows j % {row_step} == {row_step // 2} of the same {W}x{H}x{cam.samples}spp job ({cpu['samples']} samples, {cpu['seconds']:.1f} s)",
+                                    "mrays_per_s": cpu["rays"] / cpu["seconds"] / 1e6}
         else:
-            cpu = oracle_sample(desc, cam, 120, os.cpu_count() or 1)
-        per_seg_flops = (24.0 * cpu["node_tests"] + 40.0 * cpu["sphere_tests"] + 50.0 * cpu["tri_tests"]) / cpu["rays"] + 60.0
-        per_seg_bytes = (32.0 * cpu["node_tests"] + 16.0 * cpu["sphere_tests"] + 36.0 * cpu["tri_tests"]) / cpu["rays"] + 16.0
+            cpu = oracle_sample(desc, cam, max(1, H // 3), threads, first_row=H // 3)
+        # flops = 24 N_node + 40 N_sph + 50 N_tri + 60, bytes = 32 N_node + 16 N_sph + 36 N_tri + 16 per segment;
+        # the Quad extension is counted as 45 flop / 64 B per test (plane + two cross-dot products; f32 record)
+        per_seg_flops = (24.0 * cpu["node_tests"] + 40.0 * cpu["sphere_tests"] + 50.0 * cpu["tri_tests"] + 45.0 * cpu["quad_tests"]) / cpu["rays"] + 60.0
+        per_seg_bytes = (32.0 * cpu["node_tests"] + 16.0 * cpu["sphere_tests"] + 36.0 * cpu["tri_tests"] + 64.0 * cpu["quad_tests"]) / cpu["rays"] + 16.0
         seg_per_launch = my_rays / max(my_iters, 1)
         dur_s = ms_trace * 1e-3 / max(my_iters, 1)
-        achieved = per_seg_flops * seg_per_launch / dur_s / 1e12
-        peak = f64p.value if args.precision == "f64" else f32p.value
         traffic, traffic_src = None, None
-        tpath = os.path.join(ROOT, "profiles", "trace_r01d_traffic.json")
-        if args.precision == "f64" and os.path.exists(tpath):
+        tpath = os.path.join(ROOT, "profiles", TRAFFIC_FILES.get(args.config, ""))
+        if args.precision == "f64" and os.path.isfile(tpath):
             tj = json.load(open(tpath))  # DRAM bytes of one ncu --set full capture, scaled to this run's segments per launch
             traffic = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) / tj["rays_in_launch"] * seg_per_launch
             traffic_src = tj["capture"]
-        line["roofline"] = {"bound": "fp64" if args.precision == "f64" else "fp32", "kernel": "k_trace", "achieved": achieved, "peak": peak,
-                            "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_source": traffic_src,
-                            "algorithmic_bytes_per_launch": per_seg_bytes * seg_per_launch,
-                            "peak_source": "cr_measure_fma_peak (register-resident FMA micro-kernel, same run; MEASURED_PEAKS.json holds no FP32/FP64 vector peak)",
-                            "flops_per_segment": per_seg_flops, "bytes_per_segment": per_seg_bytes, "segments_per_launch": seg_per_launch,
-                            "avg_launch_ms": dur_s * 1e3, "kernel_share_of_step": ms_trace / (ms_total if world == 1 else sum(s["ms_total"] for s in stats)),
-                            "ms_trace": ms_trace / args.steps, "ms_shade": ms_shade / args.steps, "ms_raygen": ms_gen / args.steps,
-                            "fp64_fma_peak_tflops": f64p.value, "fp32_fma_peak_tflops": f32p.value,
-                            # the same launches seen as a memory kernel: SURVEY 8d's algorithmic bytes against the measured HBM
-                            # copy peak.  The scene (16 KB of nodes) is cache resident, so this view only shows that HBM is NOT
-                            # the bound of this config (the DRAM traffic of the launch is `traffic`); it IS the bound of configs[3].
-                            "hbm_view": hbm_view(per_seg_bytes * seg_per_launch, dur_s, traffic)}
+        fma_peak = f64p.value if args.precision == "f64" else f32p.value
+        flops_ach = per_seg_flops * seg_per_launch / dur_s / 1e12
+        hbm_peak, hbm_src = measured_hbm_peak()
+        bytes_ach = per_seg_bytes * seg_per_launch / dur_s / 1e9
+        fp_view = {"bound": "fp64" if args.precision == "f64" else "fp32", "achieved": flops_ach, "peak": fma_peak, "unit": "TFLOP/s",
+                   "frac": flops_ach / fma_peak if fma_peak else None,
+                   "peak_source": "cr_measure_fma_peak (register-resident FMA micro-kernel, same run; MEASURED_PEAKS.json holds no FP32/FP64 vector peak)"}
+        hbm_view = {"bound": "hbm", "achieved": bytes_ach, "peak": hbm_peak, "unit": "GB/s", "frac": bytes_ach / hbm_peak, "peak_source": hbm_src,
+                    "dram_gbps_measured": (traffic / dur_s / 1e9) if traffic else None}
+        # configs 0-2, 4: the scene is cache resident => the bound SURVEY 8d names is the FP issue rate; config 3 (11.6 M nodes,
+        # 1.1 GB of node + triangle records) => HBM.  The other view is reported next to it.
+        main_view, other = (hbm_view, fp_view) if cfg["bound"] == "hbm" else (fp_view, hbm_view)
+        line["roofline"] = dict(main_view, kernel="k_trace", traffic=traffic, traffic_source=traffic_src,
+                                algorithmic_bytes_per_launch=per_seg_bytes * seg_per_launch, flops_per_segment=per_seg_flops,
+                                bytes_per_segment=per_seg_bytes, segments_per_launch=seg_per_launch, avg_launch_ms=dur_s * 1e3,
+                                kernel_share_of_step=ms_trace / max(my_ms, 1e-9), ms_trace=ms_trace / args.steps, ms_shade=ms_shade / args.steps,
+                                ms_raygen=ms_gen / args.steps, fp64_fma_peak_tflops=f64p.value, fp32_fma_peak_tflops=f32p.value)
+        line["roofline"]["fp_view" if cfg["bound"] == "hbm" else "hbm_view"] = other
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -96,6 +96,21 @@ struct DevImage {
     int32_t w, h;
 };
 
+// ---- search tree of the order-free trace engine (fast_tree.h builds it, fast_trace.cuh walks it) ------------
+// Device record: the boxes of BOTH children (so one 64 B load serves both tests and the near-first choice).
+// child word: bit 31 clear = inner node index; bit 31 set = leaf: bits 0..27 = first entry of the leaf-primitive
+// table, bits 28..29 = number of entries - 1.  FAST_EMPTY = no child (a never-hit box).
+struct FastHalf {
+    float xmin, xmax, ymin, ymax, zmin, zmax;
+    uint32_t child, pad;
+};
+struct alignas(64) FastNodeRec {
+    FastHalf c[2];
+};
+static_assert(sizeof(FastNodeRec) == 64, "fast node = 64 B");
+static constexpr uint32_t FAST_LEAF = 0x80000000u;
+static constexpr uint32_t FAST_EMPTY = 0xFFFFFFFFu;
+
 // ---- object animation: evaluated keyframes (CrAnimKey) + one track (key range) per animated point --------
 struct AnimTrack {
     uint32_t first, count;  // keys [first, first + count) of DevScene::anim_keys; count == 0 = static point
@@ -165,6 +180,10 @@ struct DevScene {
     const AnimTrack* tri_track;      // [n_tris][3]: vertex timelines a, b, c
     const uint32_t* tri_anim_slot;   // [n_tris]: row of tri_anim_verts for an animated triangle
     const double* tri_anim_verts;    // [n_animated_tris][9]: construction vertices a, b, c
+    const FastNodeRec* fast_nodes;  // search tree of the order-free engine (nullptr: reference-order traversal only)
+    const uint2* fast_prims;        // its leaf-primitive table: (primitive ref, reference leaf node << 1 | slot = DFS rank)
+    float fast_margin_k;            // culling margin factor (fast_trace.cuh)
+    int32_t refill;                 // lanes idle before a warp fetches new rays
     uint32_t n_nodes;  // 0 when the world is the empty HitList (bvhwrapper.rs:29-31)
     int32_t sky_kind, sky_image;
     int32_t clamp_colors;  // 1 = reference Color semantics; 0 when the scene holds an Emissive (extension)
@@ -211,7 +230,7 @@ struct Control {
     uint32_t trace_next;     // warp-level work fetch cursor of the trace kernel
     uint32_t gen_base;       // raygen: first free record of the target side
     uint32_t gen_count;      // raygen: records to generate
-    uint32_t pad0;
+    uint32_t retry_count;    // order-free engine: rays handed back to the reference-order kernel this iteration
     uint64_t gen_first;      // raygen: first global sample id
     uint64_t next_sample;    // samples handed out so far
     uint64_t total_samples;  // npix_local * spp
@@ -220,6 +239,8 @@ struct Control {
     uint32_t queue_next[Q_COUNT];
     uint32_t pool;
     uint32_t iteration;
+    uint32_t retry_next;     // work cursor of the reference-order kernel over the retry list
+    uint32_t retry_total;    // rays re-traced in reference order over the whole render (CrStats-level diagnostics)
 };
 
 // ---- camera as the kernels see it ----------------------------------------------------------------

@@ -1,0 +1,310 @@
+// fast_trace.cuh — the order-free closest-hit engine (static scenes, regular rays).
+//
+// What it computes.  BVHWrapper::hit (src/objects/bvhwrapper.rs:97-126) visits the leaves of the reference tree in DFS
+// order with ONE running closest t; a primitive P is tested when its leaf-node box L(P) passes Aabb::hit
+// (src/objects/bvh.rs:96-132) on (tmin, closest so far) and replaces the closest hit when its root is strictly closer.
+// Write cand(P) for the root Sphere::hit / Triangle::hit select for P (sphere.rs:84-92, triangle.rs:118-121: the choice
+// does not depend on the running closest t, only the acceptance does) and near(L) for the entry parameter of L's box in
+// the reference's own slab arithmetic.  Inner-node tests only cull (Trav, device_math.cuh), so:
+//     P is tested      <=>  L(P) is hit on (tmin, inf)  and  closest so far > max(tmin, near(L(P)))
+//     P is accepted    <=>  P is tested  and  cand(P) < closest so far.
+// Call P REGULAR when L(P) is hit and near(L(P)) <= cand(P).  If W is the DFS-first minimiser of cand over the regular
+// primitives and no IRREGULAR primitive (cand(P) < near(L(P)): rounding put the hit in front of its own box) has
+// cand(P) <= cand(W), the reference returns exactly W: everything it can have accepted before reaching W is farther,
+// so W's leaf is entered and W accepted; nothing later is strictly closer (the oracle carries a CPU
+// model of this search, oracle.cpp order_free_hit, which tests/test_oracle_properties.py compares with the reference-
+// order traversal ray by ray).  W does not depend on the ORDER of the search, so the search runs near-first with early
+// termination over a good tree of its own (fast_tree.h) instead of the reference's median split.
+//
+// What stays exact.  Every candidate is the reference's f64 arithmetic (the same sphere_hit_t / tri_hit_t / quad_hit_t as
+// the reference-order engine); a candidate that would become the closest hit is checked against its REFERENCE leaf-node
+// box in the reference's slab arithmetic: box missed => the reference never tests it => ignored; cand < near => the ray
+// is handed to the reference-order kernel (retry list); otherwise it is accepted, ties going to the lower DFS rank.
+// The search tree's f32 boxes and the culling rule are conservative and never decide a hit.
+//
+// The one assumption.  A subtree is culled when its box entry exceeds closest + margin, margin =
+// 2^-20 (|o|_1 + 3 B) / |d| (B = largest scene coordinate): an irregular candidate can only be missed if its computed root
+// lies more than `margin` in front of its own primitive's box.  Sphere roots err by at most 2^-25 (|oc| + r) / |d| (the
+// discriminant's cancellation), quad roots by ulps of the plane equation, so the margin has a factor > 30 to spare;
+// a triangle root can err by more only when |det| < ~1e-8 |e1||e2||d| (a ray within 1e-8 rad of the triangle's plane
+// that still passes the u, v tests).  DESIGN.md 5.1b quantifies this; CR_RENDER_REFERENCE_ORDER / CR_TRACE_REFERENCE_ORDER
+// select the reference-order engine, which needs no such assumption.
+#pragma once
+#include "device_math.cuh"
+
+namespace crb {
+
+enum : int { FS_IDLE = 0, FS_INNER = 1, FS_LEAF = 2, FS_DONE = 3, FS_RETRY = 4 };
+static constexpr int FAST_STACK = 64;
+
+template <typename R, int BLOCK>
+struct FastSlots {  // per-CTA lane table, SoA over the lanes (conflict free), as LaneSlots of the reference-order engine
+    R best_t[BLOCK];
+    R ray[6][BLOCK];
+    float pre[7][BLOCK];
+    uint32_t best_ref[BLOCK], best_rank[BLOCK], my[BLOCK];
+};
+
+// Conservative f32 slab test of one child box: entry `lo` (clamped to tmin) and "certainly missed or beyond the
+// closest hit + margin".  Planes as single FFMAs (filter_box, device_math.cuh); the error bound E is the filter's.
+struct FastRay {
+    float oix, oiy, oiz, ax0, ax1, ay0, ay1, az0, az1, e;
+};
+__device__ __forceinline__ bool fast_child_fails(const NodeRec<float>& n, const FastRay& f, float tmin, float best_m, float& lo_lb) {
+    const float nx = __fmaf_rn(n.xmin, f.ax0, __fmaf_rn(n.xmax, f.ax1, -f.oix));
+    const float fx = __fmaf_rn(n.xmax, f.ax0, __fmaf_rn(n.xmin, f.ax1, -f.oix));
+    const float ny = __fmaf_rn(n.ymin, f.ay0, __fmaf_rn(n.ymax, f.ay1, -f.oiy));
+    const float fy = __fmaf_rn(n.ymax, f.ay0, __fmaf_rn(n.ymin, f.ay1, -f.oiy));
+    const float nz = __fmaf_rn(n.zmin, f.az0, __fmaf_rn(n.zmax, f.az1, -f.oiz));
+    const float fz = __fmaf_rn(n.zmax, f.az0, __fmaf_rn(n.zmin, f.az1, -f.oiz));
+    const float lo = fmaxf(fmaxf(nx, ny), fmaxf(nz, tmin));
+    const float hi = fminf(fminf(fx, fy), fminf(fz, best_m));
+    const float E = __fmaf_rn(fabsf(lo) + fabsf(hi), 4.7683716e-7f, f.e);
+    lo_lb = lo - E;                 // lower bound of the true entry parameter
+    return (hi - lo) < -E;          // NaN / inf => false => the child is visited (culling must stay conservative)
+}
+
+// The reference's Aabb::hit on (tmin, +inf) for a regular ray (aabb_hit_regular, device_math.cuh): hit? and the entry
+// parameter max(tmin, near) as the reference computes it.
+template <typename R>
+__device__ __forceinline__ bool ref_box_span(const NodeRec<R>& n, V3<R> o, V3<R> inv, R tmin, R& entry) {
+    const bool px = inv.x > R(0), py = inv.y > R(0), pz = inv.z > R(0);
+    const R x0 = (n.xmin - o.x) * inv.x, x1 = (n.xmax - o.x) * inv.x;
+    const R y0 = (n.ymin - o.y) * inv.y, y1 = (n.ymax - o.y) * inv.y;
+    const R z0 = (n.zmin - o.z) * inv.z, z1 = (n.zmax - o.z) * inv.z;
+    const R lx = px ? x0 : x1, hx = px ? x1 : x0;
+    const R ly = py ? y0 : y1, hy = py ? y1 : y0;
+    const R lz = pz ? z0 : z1, hz = pz ? z1 : z0;
+    R lo = (lx > tmin) ? lx : tmin;
+    R hi = hx;
+    lo = (ly > lo) ? ly : lo;
+    hi = (hy < hi) ? hy : hi;
+    lo = (lz > lo) ? lz : lo;
+    hi = (hz < hi) ? hz : hi;
+    entry = lo;
+    return hi > lo;
+}
+
+template <typename R, int BLOCK>
+struct FastTrav {
+    FastRay fr;
+    FastSlots<R, BLOCK>* s;
+    float best_m;    // (float) closest hit, rounded up, + margin
+    float margin;
+    uint32_t cur;    // inner node index, or the parked leaf word (FS_LEAF)
+    int sp;
+    uint32_t stk_ref[FAST_STACK];
+    float stk_lo[FAST_STACK];
+
+    __device__ __forceinline__ void init_from(const FilterRay& f, R tmax, float margin_k, float bmax) {
+        fr.oix = f.oix; fr.oiy = f.oiy; fr.oiz = f.oiz;
+        fr.ax0 = f.ax0; fr.ax1 = f.ax1; fr.ay0 = f.ay0; fr.ay1 = f.ay1; fr.az0 = f.az0; fr.az1 = f.az1;
+        fr.e = f.e_big;
+        const int t = threadIdx.x;
+        s->pre[0][t] = f.ox; s->pre[1][t] = f.oy; s->pre[2][t] = f.oz; s->pre[3][t] = f.dx; s->pre[4][t] = f.dy; s->pre[5][t] = f.dz;
+        s->pre[6][t] = f.o2;
+        s->best_t[t] = tmax;
+        s->best_ref[t] = REF_MISS;
+        s->best_rank[t] = 0xFFFFFFFFu;
+        // margin = k (|o|_1 + 3 B) / |d|  (an overflowing or zero |d|^2 gives inf: no culling by distance, still correct)
+        const float d2 = f.dx * f.dx + f.dy * f.dy + f.dz * f.dz;
+        margin = margin_k * (fabsf(f.ox) + fabsf(f.oy) + fabsf(f.oz) + 3.0f * bmax) * rsqrtf(d2) * 1.0001f;
+        if (!(margin >= 0.f)) margin = __int_as_float(0x7f800000);
+        best_m = __double2float_ru((double)tmax) + margin;
+        cur = 0u;
+        sp = 0;
+    }
+    __device__ __forceinline__ void set_ray(V3<R> o, V3<R> d) {
+        const int t = threadIdx.x;
+        s->ray[0][t] = o.x; s->ray[1][t] = o.y; s->ray[2][t] = o.z; s->ray[3][t] = d.x; s->ray[4][t] = d.y; s->ray[5][t] = d.z;
+    }
+    __device__ __forceinline__ void get_ray(V3<R>& o, V3<R>& d) const {
+        const int t = threadIdx.x;
+        o = {s->ray[0][t], s->ray[1][t], s->ray[2][t]};
+        d = {s->ray[3][t], s->ray[4][t], s->ray[5][t]};
+    }
+    // next node from the stack (entries whose box entry lies beyond the closest hit + margin are dropped)
+    __device__ __forceinline__ int pop() {
+        while (sp > 0) {
+            --sp;
+            if (!(stk_lo[sp] > best_m)) {
+                cur = stk_ref[sp];
+                return (cur & FAST_LEAF) ? (int)FS_LEAF : (int)FS_INNER;
+            }
+        }
+        return FS_DONE;
+    }
+    // INNER step: both child boxes from one 64 B record, nearer child first
+    __device__ __forceinline__ int step_inner(const DevScene<R>& sc, float tmin) {
+        const NodeRec<float>* half = reinterpret_cast<const NodeRec<float>*>(sc.fast_nodes + cur);
+        const NodeRec<float> a = ldg_node32(half), b = ldg_node32(half + 1);
+        float la, lb;
+        const bool ha = !fast_child_fails(a, fr, tmin, best_m, la) && a.left != FAST_EMPTY;
+        const bool hb = !fast_child_fails(b, fr, tmin, best_m, lb) && b.left != FAST_EMPTY;
+        if (ha && hb) {
+            const bool a_first = !(lb < la);
+            if (sp < FAST_STACK) {  // the builder bounds the depth (FAST_MAX_DEPTH): always true
+                stk_ref[sp] = a_first ? b.left : a.left;
+                stk_lo[sp] = a_first ? lb : la;
+                ++sp;
+            }
+            cur = a_first ? a.left : b.left;
+        } else if (ha) {
+            cur = a.left;
+        } else if (hb) {
+            cur = b.left;
+        } else {
+            return pop();
+        }
+        return (cur & FAST_LEAF) ? (int)FS_LEAF : (int)FS_INNER;
+    }
+    __device__ __forceinline__ uint32_t leaf_first() const { return cur & 0x0FFFFFFFu; }
+    __device__ __forceinline__ uint32_t leaf_count() const { return ((cur >> 28) & 3u) + 1u; }
+    // f64 path: every primitive of the parked leaf is a sphere whose f64 discriminant is certainly negative
+    __device__ __forceinline__ bool leaf_certain_miss(const DevScene<R>& sc) const {
+        if constexpr (sizeof(R) == 8) {
+            const uint32_t first = leaf_first(), cnt = leaf_count();
+            const int t = threadIdx.x;
+            const PreRay pre = {s->pre[0][t], s->pre[1][t], s->pre[2][t], s->pre[3][t], s->pre[4][t], s->pre[5][t], s->pre[6][t]};
+            for (uint32_t k = 0; k < cnt; ++k) {
+                const uint32_t ref = __ldg(&sc.fast_prims[first + k].x);
+                if (ref_kind(ref) != CR_PRIM_SPHERE) return false;
+                if (!sphere_definite_miss(ldg_rec<1>(sc.spheres32 + ref_index(ref)), pre)) return false;
+            }
+            return true;
+        } else {
+            return false;
+        }
+    }
+    // LEAF step: candidates in the reference's arithmetic; a candidate that would become the closest hit is checked
+    // against its reference leaf-node box (regularity).  Returns the next state (FS_RETRY: hand the ray back).
+    __device__ __forceinline__ int step_leaf(const DevScene<R>& sc, V3<R> o, V3<R> d, R tmin, R tmax) {
+        const int t = threadIdx.x;
+        const R a = vlen2(d);  // sphere.rs:74
+        R best = s->best_t[t];
+        uint32_t brank = s->best_rank[t], bref = REF_NONE;
+        const uint32_t first = leaf_first(), cnt = leaf_count();
+        for (uint32_t k = 0; k < cnt; ++k) {
+            const uint2 e = __ldg(&sc.fast_prims[first + k]);
+            R c;
+            if (!Trav<R, RegStore<R>, false>::test_prim(sc, e.x, o, d, a, tmin, tmax, R(0), c)) continue;
+            if constexpr (sizeof(R) == 8) {
+                if (!(c < best || (c == best && e.y < brank))) continue;
+                const NodeRec<R> n = ldg_rec<sizeof(NodeRec<R>) / 16>(sc.nodes + (e.y >> 1));
+                const V3<R> inv = {R(1) / d.x, R(1) / d.y, R(1) / d.z};  // adinv, bvh.rs:111
+                R entry;
+                if (!ref_box_span(n, o, inv, tmin, entry)) continue;  // the reference never tests this primitive
+                if (c < entry) return FS_RETRY;                        // irregular candidate: reference order decides
+            } else {
+                if (!(c < best)) continue;  // f32 path: statistical parity only
+            }
+            best = c;
+            brank = e.y;
+            bref = e.x;
+        }
+        if (bref != REF_NONE) {
+            s->best_t[t] = best;
+            s->best_ref[t] = bref;
+            s->best_rank[t] = brank;
+            best_m = __double2float_ru((double)best) + margin;
+        }
+        return pop();
+    }
+};
+
+// Warp-persistent driver: the same schedule as trace_persistent (device_math.cuh) — INNER slices of cheap f32 steps,
+// then one LEAF phase for the parked lanes — with the exact box phase gone (the search tree never decides anything).
+//   IO::count() / cursor() / filter(i,tmin,tmax) / load(i,o,d) / commit(has,i,ref,t,o,d,tm)   (commit is warp-synchronous)
+// Rays the engine cannot decide (irregular rays: zero / NaN / inf components; rays that met an irregular candidate) are
+// appended to retry_list; the reference-order kernel traces them afterwards.
+static __device__ __forceinline__ uint32_t fast_warp_append(uint32_t* counter, bool pred) {
+    const uint32_t mask = __ballot_sync(0xffffffffu, pred);
+    if (mask == 0) return 0;
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(mask) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    return base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
+}
+
+template <typename R, int BLOCK, typename IO>
+__device__ __forceinline__ void fast_trace_persistent(const DevScene<R>& sc, R tmin, R tmax, IO& io, FastSlots<R, BLOCK>* slots,
+                                                      uint32_t* retry_list, uint32_t* retry_count) {
+    const int NODE_SLICE = sc.node_slice;
+    const int REFILL = sc.refill;
+    const uint32_t n = io.count();
+    const int lane = threadIdx.x & 31;
+    const float tmin32 = (float)tmin;
+    FastTrav<R, BLOCK> tv;
+    tv.s = slots;
+    tv.cur = 0u;
+    tv.sp = 0;
+    tv.best_m = 0.f;
+    tv.margin = 0.f;
+    int st = FS_IDLE;
+    bool exhausted = false;
+    const bool small = n <= gridDim.x * blockDim.x;
+    for (;;) {
+        const uint32_t walking = __ballot_sync(0xffffffffu, st == FS_INNER || st == FS_LEAF);
+        const int n_free = 32 - __popc(walking);
+        if ((!exhausted && n_free >= REFILL) || walking == 0u) {  // warp-uniform
+            {
+                V3<R> o = {R(0), R(0), R(0)}, d = {R(0), R(0), R(0)};
+                uint32_t my = 0, bref = REF_MISS;
+                R bt = tmax;
+                if (st == FS_DONE || st == FS_RETRY) {
+                    my = slots->my[threadIdx.x];
+                    bref = slots->best_ref[threadIdx.x];
+                    bt = slots->best_t[threadIdx.x];
+                    if (io.commit_needs_ray()) tv.get_ray(o, d);
+                }
+                io.commit(st == FS_DONE, my, bref, bt, o, d, R(0));
+                const uint32_t pos = fast_warp_append(retry_count, st == FS_RETRY);
+                if (st == FS_RETRY) retry_list[pos] = my;
+            }
+            if (st == FS_DONE || st == FS_RETRY) st = FS_IDLE;
+            if (!exhausted) {
+                uint32_t base = 0;
+                if (small) {
+                    base = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32u;
+                } else {
+                    if (lane == 0) base = atomicAdd(io.cursor(), (uint32_t)n_free);
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                }
+                if (st == FS_IDLE) {
+                    const uint32_t k = base + (uint32_t)__popc(~walking & ((1u << lane) - 1u));
+                    if (k < n) {
+                        slots->my[threadIdx.x] = k;
+                        V3<R> o, d;
+                        io.load(k, o, d);
+                        const FilterRay f = io.filter(k, tmin, tmax);
+                        tv.init_from(f, tmax, sc.fast_margin_k, sc.bmax);
+                        tv.set_ray(o, d);
+                        st = f.ok ? (int)FS_INNER : (int)FS_RETRY;  // irregular rays keep the reference's test at every node
+                    }
+                }
+                if (small || base + (uint32_t)n_free >= n) exhausted = true;
+            }
+            if (__ballot_sync(0xffffffffu, st != FS_IDLE) == 0u) break;
+        }
+#pragma unroll 1
+        for (int k = 0; k < NODE_SLICE; k += 4) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (st == FS_INNER) st = tv.step_inner(sc, tmin32);
+            }
+            if (__popc(__ballot_sync(0xffffffffu, st == FS_INNER)) < sc.min_node_lanes) break;
+        }
+        if (st == FS_LEAF && tv.leaf_certain_miss(sc)) st = tv.pop();
+        if (__any_sync(0xffffffffu, st == FS_LEAF)) {
+            if (st == FS_LEAF) {
+                V3<R> o, d;
+                tv.get_ray(o, d);
+                st = tv.step_leaf(sc, o, d, tmin, tmax);
+            }
+        }
+    }
+}
+
+}  // namespace crb

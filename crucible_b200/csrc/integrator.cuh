@@ -6,11 +6,13 @@
 // worker pool of src/camera/cpu_threading.rs:25-115.
 #pragma once
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <string>
 #include <vector>
 
 #include "device_math.cuh"
+#include "fast_trace.cuh"
 #include "integrator.h"
 
 namespace crb {
@@ -195,6 +197,9 @@ static __global__ void k_plan(Control* ctl, int nxt, uint32_t* host_n_in) {
     ctl->rays_traced += n_in;
     ctl->out_count[nxt ^ 1] = 0;
     ctl->trace_next = 0;
+    ctl->retry_total += ctl->retry_count;
+    ctl->retry_count = 0;
+    ctl->retry_next = 0;
     for (int q = 0; q < Q_COUNT; ++q) ctl->queue_count[q] = 0;
     ctl->iteration++;
     if (host_n_in) *host_n_in = n_in;
@@ -204,6 +209,8 @@ static __global__ void k_plan(Control* ctl, int nxt, uint32_t* host_n_in) {
 static __global__ void k_trace_rewind(Control* ctl) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     ctl->trace_next = 0;
+    ctl->retry_count = 0;
+    ctl->retry_next = 0;
     for (int q = 0; q < Q_COUNT; ++q) ctl->queue_count[q] = 0;
 }
 
@@ -339,17 +346,20 @@ struct RenderTraceIO {
     uint2* queues;
     const FilterRec* filt;
     uint32_t n, pool;
+    const uint32_t* remap;  // non-null: work item k is path remap[k] (the retry list of the order-free engine)
+    uint32_t* cur;
     __device__ __forceinline__ uint32_t count() const { return n; }
-    __device__ __forceinline__ uint32_t* cursor() const { return &ctl->trace_next; }
-    __device__ __forceinline__ FilterRay filter(uint32_t i, R, R) const {  // written by the ray's producer
+    __device__ __forceinline__ uint32_t* cursor() const { return cur; }
+    __device__ __forceinline__ uint32_t path_of(uint32_t k) const { return remap ? remap[k] : k; }
+    __device__ __forceinline__ FilterRay filter(uint32_t k, R, R) const {  // written by the ray's producer
         FilterRec r;
-        const int4* s = reinterpret_cast<const int4*>(filt + i);
+        const int4* s = reinterpret_cast<const int4*>(filt + path_of(k));
         int4* d = reinterpret_cast<int4*>(&r);
         d[0] = s[0]; d[1] = s[1]; d[2] = s[2];
         return unpack_filter(r);
     }
-    __device__ __forceinline__ void load(uint32_t i, V3<R>& o, V3<R>& d) const {
-        const PathRec<R>* p = paths + i;  // sectors A and B of the record: origin + direction
+    __device__ __forceinline__ void load(uint32_t k, V3<R>& o, V3<R>& d) const {
+        const PathRec<R>* p = paths + path_of(k);  // sectors A and B of the record: origin + direction
         if constexpr (sizeof(R) == 8) {
             const double2 a = *reinterpret_cast<const double2*>(&p->ox);
             const double b = p->oz;
@@ -364,12 +374,14 @@ struct RenderTraceIO {
             d = {b.x, b.y, b.z};
         }
     }
-    __device__ __forceinline__ R time(uint32_t i) const { return paths[i].tm; }  // ray_casting.rs:84
+    __device__ __forceinline__ R time(uint32_t k) const { return paths[path_of(k)].tm; }  // ray_casting.rs:84
     __device__ __forceinline__ bool commit_needs_ray() const { return false; }
-    __device__ __forceinline__ void commit(bool has, uint32_t i, uint32_t ref, R t, V3<R>, V3<R>, R) const {
+    __device__ __forceinline__ void commit(bool has, uint32_t k, uint32_t ref, R t, V3<R>, V3<R>, R) const {
         int q = -1;
         uint32_t minfo = 0;  // material index (bits 0..23) | needs-uv (bit 31): saves the shaders a dependent load
+        uint32_t i = 0;
         if (has) {
+            i = path_of(k);
             paths[i].t = t;
             paths[i].ref = ref;
             if (ref == REF_MISS) {
@@ -387,12 +399,26 @@ struct RenderTraceIO {
     }
 };
 
+// remap == nullptr: the whole wavefront of side `side`; otherwise the retry list the order-free kernel left behind
 template <typename R, int REFILL, int MINB, bool ANIM>
 __global__ void __launch_bounds__(TRACE_BLOCK, MINB) k_trace(DevScene<R> sc, PathRec<R>* __restrict__ paths, Control* __restrict__ ctl,
-                                                        int side, uint2* __restrict__ queues, const FilterRec* __restrict__ filt, uint32_t pool) {
+                                                        int side, uint2* __restrict__ queues, const FilterRec* __restrict__ filt, uint32_t pool,
+                                                        const uint32_t* __restrict__ remap) {
     __shared__ LaneSlots<R, TRACE_BLOCK, ANIM> slots;
-    RenderTraceIO<R> io{sc, paths, ctl, queues, filt, ctl->n_in[side], pool};
+    RenderTraceIO<R> io{sc, paths, ctl, queues, filt, remap ? ctl->retry_count : ctl->n_in[side], pool, remap,
+                        remap ? &ctl->retry_next : &ctl->trace_next};
+    if (io.n == 0u) return;
     trace_persistent<R, REFILL, TRACE_BLOCK, ANIM>(sc, R(0.001), Num<R>::inf(), io, &slots);  // ray_casting.rs:119
+}
+
+// The order-free engine over the wavefront (fast_trace.cuh); undecidable rays go to retry_list for k_trace above.
+template <typename R, int MINB>
+__global__ void __launch_bounds__(TRACE_BLOCK, MINB) k_trace_fast(DevScene<R> sc, PathRec<R>* __restrict__ paths, Control* __restrict__ ctl,
+                                                             int side, uint2* __restrict__ queues, const FilterRec* __restrict__ filt,
+                                                             uint32_t pool, uint32_t* __restrict__ retry_list) {
+    __shared__ FastSlots<R, TRACE_BLOCK> slots;
+    RenderTraceIO<R> io{sc, paths, ctl, queues, filt, ctl->n_in[side], pool, nullptr, &ctl->trace_next};
+    fast_trace_persistent<R, TRACE_BLOCK>(sc, R(0.001), Num<R>::inf(), io, &slots, retry_list, &ctl->retry_count);
 }
 
 // fixed-point accumulation: order independent => bit-reproducible for any schedule and GPU count
@@ -636,22 +662,24 @@ struct BatchTraceIO {
     CrHit* out;
     uint32_t* cur;
     uint32_t n;
+    const uint32_t* remap;  // non-null: work item k is ray remap[k] (retry list of the order-free engine)
     __device__ __forceinline__ uint32_t count() const { return n; }
     __device__ __forceinline__ uint32_t* cursor() const { return cur; }
-    __device__ __forceinline__ FilterRay filter(uint32_t i, R tmin, R tmax) const {
+    __device__ __forceinline__ uint32_t ray_of(uint32_t k) const { return remap ? remap[k] : k; }
+    __device__ __forceinline__ FilterRay filter(uint32_t k, R tmin, R tmax) const {
         V3<R> o, d;
-        load(i, o, d);
+        load(k, o, d);
         const V3<R> inv = {R(1) / d.x, R(1) / d.y, R(1) / d.z};  // adinv, bvh.rs:111
         return make_filter_ray<R>(o, d, inv, tmin, tmax, sc.bsmall, sc.bmax);
     }
-    __device__ __forceinline__ void load(uint32_t i, V3<R>& o, V3<R>& d) const {
-        const double* r = rays + 7ull * i;
+    __device__ __forceinline__ void load(uint32_t k, V3<R>& o, V3<R>& d) const {
+        const double* r = rays + 7ull * ray_of(k);
         o = {(R)r[0], (R)r[1], (R)r[2]};
         d = {(R)r[3], (R)r[4], (R)r[5]};
     }
-    __device__ __forceinline__ R time(uint32_t i) const { return (R)rays[7ull * i + 6]; }
+    __device__ __forceinline__ R time(uint32_t k) const { return (R)rays[7ull * ray_of(k) + 6]; }
     __device__ __forceinline__ bool commit_needs_ray() const { return true; }
-    __device__ __forceinline__ void commit(bool has, uint32_t i, uint32_t ref, R t, V3<R> o, V3<R> d, R tm) const {
+    __device__ __forceinline__ void commit(bool has, uint32_t k, uint32_t ref, R t, V3<R> o, V3<R> d, R tm) const {
         if (!has) return;
         CrHit h;
         if (ref == REF_MISS) {
@@ -665,15 +693,26 @@ struct BatchTraceIO {
             h.n[0] = (double)hi.n.x; h.n[1] = (double)hi.n.y; h.n[2] = (double)hi.n.z;
             h.u = (double)hi.u; h.v = (double)hi.v;
         }
-        out[i] = h;
+        out[ray_of(k)] = h;
     }
 };
+// cursor[0] = work cursor, cursor[1] = retry count (written by the order-free kernel), cursor[2] = retry work cursor
 template <typename R, bool ANIM>
 __global__ void __launch_bounds__(TRACE_BLOCK) k_trace_batch(DevScene<R> sc, const double* __restrict__ rays, uint32_t n, double tmin,
-                                                              double tmax, CrHit* __restrict__ out, uint32_t* __restrict__ cursor) {
+                                                              double tmax, CrHit* __restrict__ out, uint32_t* __restrict__ cursor,
+                                                              const uint32_t* __restrict__ remap) {
     __shared__ LaneSlots<R, TRACE_BLOCK, ANIM> slots;
-    BatchTraceIO<R, ANIM> io{sc, rays, out, cursor, n};
+    BatchTraceIO<R, ANIM> io{sc, rays, out, remap ? cursor + 2 : cursor, remap ? cursor[1] : n, remap};
+    if (io.n == 0u) return;
     trace_persistent<R, CRB_REFILL, TRACE_BLOCK, ANIM>(sc, (R)tmin, (R)tmax, io, &slots);
+}
+template <typename R>
+__global__ void __launch_bounds__(TRACE_BLOCK) k_trace_batch_fast(DevScene<R> sc, const double* __restrict__ rays, uint32_t n, double tmin,
+                                                                   double tmax, CrHit* __restrict__ out, uint32_t* __restrict__ cursor,
+                                                                   uint32_t* __restrict__ retry_list) {
+    __shared__ FastSlots<R, TRACE_BLOCK> slots;
+    BatchTraceIO<R, false> io{sc, rays, out, cursor, n, nullptr};
+    fast_trace_persistent<R, TRACE_BLOCK>(sc, (R)tmin, (R)tmax, io, &slots, retry_list, cursor + 1);
 }
 
 // ---- host side: typed view of the scene + wavefront driver -----------------------------------------
@@ -698,6 +737,12 @@ static DevScene<R> make_dev_scene(const SceneDeviceData& s) {
     d.tri_anim_verts = s.tri_anim_verts;
     d.texs = s.texs;
     d.images = s.images;
+    d.fast_nodes = reinterpret_cast<const FastNodeRec*>(s.fast_nodes);
+    d.fast_prims = reinterpret_cast<const uint2*>(s.fast_prims);
+    d.fast_margin_k = 9.5367431640625e-07f;  // 2^-20 (fast_trace.cuh)
+    if (const char* e = getenv("CRB_FAST_MARGIN")) d.fast_margin_k = (float)atof(e);
+    d.refill = CRB_REFILL;
+    if (const char* e = getenv("CRB_REFILL_RT")) d.refill = atoi(e) > 0 && atoi(e) <= 32 ? atoi(e) : CRB_REFILL;
     d.n_nodes = s.n_nodes;
     d.sky_kind = s.sky_kind;
     d.sky_image = s.sky_image;
@@ -722,6 +767,15 @@ static DevScene<R> make_dev_scene(const SceneDeviceData& s) {
         }                                                                                     \
     } while (0)
 
+// The order-free engine serves static scenes that have a search tree; object keyframes (primitives leave their
+// construction-time boxes, which only the reference tree's semantics cover) and explicit requests keep reference order.
+static bool use_fast_engine(const SceneDeviceData& s, int reference_order) {
+    if (const char* e = getenv("CRB_TRAVERSAL")) {
+        if (e[0] == 'r') return false;
+    }
+    return !reference_order && s.fast_nodes != nullptr && s.anim_keys == nullptr && s.n_nodes != 0u;
+}
+
 template <typename F>
 static int persistent_grid(F kernel, int block, int num_sms) {
     int per_sm = 0;
@@ -729,21 +783,34 @@ static int persistent_grid(F kernel, int block, int num_sms) {
     return per_sm * num_sms;  // a whole number of resident CTAs per SM (148 SMs on B200)
 }
 
+// d_cursor: 4 words (work cursor, retry count, retry cursor, spare); d_retry: n words (order-free engine only)
 template <typename R>
 int trace_batch_impl(const SceneDeviceData& s, const double* d_rays, size_t n, double tmin, double tmax, CrHit* d_out,
-                     uint32_t* d_cursor, cudaStream_t stream, std::string& err) {
+                     uint32_t* d_cursor, uint32_t* d_retry, int reference_order, uint32_t* h_retried, cudaStream_t stream, std::string& err) {
+    if (h_retried) *h_retried = 0;
     if (n == 0) return CR_OK;
     if (n > 0xFFFFFF00ull) {
         err = "trace_batch: more than 2^32 rays in one call";
         return CR_ERR_LIMIT;
     }
     const DevScene<R> sc = make_dev_scene<R>(s);
-    auto kern = (s.anim_keys != nullptr) ? k_trace_batch<R, true> : k_trace_batch<R, false>;
+    const bool animated = s.anim_keys != nullptr;
+    auto kern = animated ? k_trace_batch<R, true> : k_trace_batch<R, false>;
     int grid = persistent_grid(kern, TRACE_BLOCK, s.num_sms);
     const size_t need = (n + TRACE_BLOCK - 1) / TRACE_BLOCK;
     if ((size_t)grid > need) grid = (int)need;
-    CRB_CUDA(cudaMemsetAsync(d_cursor, 0, sizeof(uint32_t), stream));
-    kern<<<grid, TRACE_BLOCK, 0, stream>>>(sc, d_rays, (uint32_t)n, tmin, tmax, d_out, d_cursor);
+    CRB_CUDA(cudaMemsetAsync(d_cursor, 0, 4 * sizeof(uint32_t), stream));
+    const bool fast = use_fast_engine(s, reference_order) && d_retry != nullptr;
+    if (fast) {
+        int gf = persistent_grid(k_trace_batch_fast<R>, TRACE_BLOCK, s.num_sms);
+        if ((size_t)gf > need) gf = (int)need;
+        k_trace_batch_fast<R><<<gf, TRACE_BLOCK, 0, stream>>>(sc, d_rays, (uint32_t)n, tmin, tmax, d_out, d_cursor, d_retry);
+        // the rays it could not decide, in reference order (usually none: the launch then returns at once)
+        kern<<<std::min(grid, s.num_sms * 2), TRACE_BLOCK, 0, stream>>>(sc, d_rays, (uint32_t)n, tmin, tmax, d_out, d_cursor, d_retry);
+        if (h_retried) CRB_CUDA(cudaMemcpyAsync(h_retried, d_cursor + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    } else {
+        kern<<<grid, TRACE_BLOCK, 0, stream>>>(sc, d_rays, (uint32_t)n, tmin, tmax, d_out, d_cursor, nullptr);
+    }
     CRB_CUDA(cudaGetLastError());
     return CR_OK;
 }
@@ -1000,6 +1067,7 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
     launches += 2;
     uint64_t it = 0;
     bool done = (issue == 0);
+    const bool log_waves = getenv("CRB_LOG_WAVES") != nullptr;  // debug: wavefront sizes (pairs an ncu capture with its ray count)
     while (!done) {
         const int cur = (int)(it & 1), nxt = cur ^ 1;
         if (tuning && it == tune_at) {
@@ -1054,6 +1122,8 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
             const int old = (int)((it - LAG) % RING);
             CRB_CUDA(cudaEventSynchronize(ring_ev[old]));
             const uint32_t left = h_n_in[old];
+            if (log_waves) fprintf(stderr, "crucible_b200 wave %llu: %u paths enter iteration %llu\n", (unsigned long long)(it - LAG),
+                                   left, (unsigned long long)(it - LAG + 1));
             if (left == 0) {
                 done = true;  // nothing left to trace after iteration it-LAG: later ones were no-ops
             } else if (left < pool && left <= tail_n) {

@@ -135,7 +135,7 @@ class OracleScene:
         out = np.zeros(len(rays), dtype=abi.HIT_DTYPE)
         cn = np.zeros((len(rays), 4), np.uint32) if counters else None
         threads = threads or (os.cpu_count() or 1)
-        rc = self.lib.orc_trace_batch(self.handle, _p(rays), len(rays), tmin, tmax, 2 if order_free else (1 if brute else 0), _p(out),
+        rc = self.lib.orc_trace_batch(self.handle, _p(rays), len(rays), tmin, tmax, int(order_free) + 1 if order_free else (1 if brute else 0), _p(out),
                                       _p(cn) if counters else None, threads)
         assert rc == 0, self.lib.orc_last_error().decode()
         return (out, cn) if counters else out

@@ -342,6 +342,7 @@ struct Scene {
     std::vector<Node> nodes;
     Obj world = {O_LIST, -1}; /* empty HitList */
     std::vector<uint32_t> leaf_rank; /* MODEL only: DFS rank of (leaf node, slot), for the order-free tie rule */
+    struct FastTree* fast = nullptr; /* MODEL only: built on demand (orc_trace_batch mode 3) */
     bool built = false;
 
     const Aabb& bbox_of(const Obj& o) const {
@@ -594,6 +595,139 @@ static void order_free_visit(const Scene& sc, const Obj& o, const Ray& r, double
         }
     }
 }
+/* ---- MODEL, part 2: the same order-free search over a DIFFERENT tree.  Because the result does not depend on the visiting
+ * order, the search may use any conservative structure over the primitives; the reference tree is only needed for the
+ * leaf-node box of a candidate (regularity) and its DFS rank (ties).  FastTree = binned-SAH binary BVH over the
+ * construction-time primitive boxes, built here to measure how many box tests a good tree saves. */
+struct FastNode {
+    Aabb box;
+    int left, right;   /* children (inner) */
+    int first, count;  /* primitive range (leaf) */
+};
+struct FastTree {
+    std::vector<FastNode> nodes;
+    std::vector<Obj> prims;                       /* leaf order */
+    std::vector<uint32_t> ref_leaf, ref_rank;     /* per entry of prims: reference leaf node, DFS rank */
+};
+static inline double half_area(const Aabb& b) {
+    const double x = b.x.max - b.x.min, y = b.y.max - b.y.min, z = b.z.max - b.z.min;
+    return x * y + y * z + z * x;
+}
+static int fast_build(const Scene& sc, FastTree& ft, std::vector<int>& idx, int lo, int hi, const std::vector<Aabb>& pb, const std::vector<V3>& pc) {
+    FastNode n;
+    n.box = AABB_EMPTY;
+    Aabb cb = AABB_EMPTY;
+    for (int i = lo; i < hi; ++i) {
+        n.box = aabb_union(n.box, pb[idx[i]]);
+        cb = aabb_union(cb, aabb_from_points(pc[idx[i]], pc[idx[i]]));
+    }
+    n.left = n.right = -1;
+    n.first = lo;
+    n.count = hi - lo;
+    const int me = (int)ft.nodes.size();
+    ft.nodes.push_back(n);
+    if (hi - lo <= 2) return me;
+    const int ax = longest_axis(cb);
+    const Interval& ci = axis_interval(cb, ax);
+    const double ext = ci.max - ci.min;
+    int mid = (lo + hi) / 2;
+    auto key = [&](int p) { return ax == 0 ? pc[p].x : (ax == 1 ? pc[p].y : pc[p].z); };
+    if (ext > 0.0) {
+        const int NB = 16;
+        Aabb bb[NB];
+        int bc[NB];
+        for (int b = 0; b < NB; ++b) { bb[b] = AABB_EMPTY; bc[b] = 0; }
+        auto bin = [&](int p) { int b = (int)((key(p) - ci.min) / ext * NB); return b < 0 ? 0 : (b >= NB ? NB - 1 : b); };
+        for (int i = lo; i < hi; ++i) { int b = bin(idx[i]); bb[b] = aabb_union(bb[b], pb[idx[i]]); bc[b]++; }
+        double best = 1e300; int bs = -1;
+        Aabb la[NB]; int lc[NB];
+        Aabb acc = AABB_EMPTY; int cnt = 0;
+        for (int b = 0; b < NB; ++b) { acc = aabb_union(acc, bb[b]); cnt += bc[b]; la[b] = acc; lc[b] = cnt; }
+        acc = AABB_EMPTY; cnt = 0;
+        for (int b = NB - 1; b > 0; --b) {
+            acc = aabb_union(acc, bb[b]); cnt += bc[b];
+            if (lc[b - 1] == 0 || cnt == 0) continue;
+            const double c = half_area(la[b - 1]) * lc[b - 1] + half_area(acc) * cnt;
+            if (c < best) { best = c; bs = b; }
+        }
+        if (bs > 0) {
+            int m = (int)(std::partition(idx.begin() + lo, idx.begin() + hi, [&](int p) { return bin(p) < bs; }) - idx.begin());
+            if (m > lo && m < hi) mid = m;
+            else std::nth_element(idx.begin() + lo, idx.begin() + mid, idx.begin() + hi, [&](int a, int b) { return key(a) < key(b); });
+        } else {
+            std::nth_element(idx.begin() + lo, idx.begin() + mid, idx.begin() + hi, [&](int a, int b) { return key(a) < key(b); });
+        }
+    }
+    const int l = fast_build(sc, ft, idx, lo, mid, pb, pc);
+    const int r = fast_build(sc, ft, idx, mid, hi, pb, pc);
+    ft.nodes[me].left = l;
+    ft.nodes[me].right = r;
+    ft.nodes[me].count = 0;
+    return me;
+}
+static void fast_tree_build(const Scene& sc, FastTree& ft) {
+    /* primitives of the reference tree's leaf nodes, with their leaf node and DFS rank */
+    std::vector<Obj> prims;
+    std::vector<uint32_t> leaf, rank;
+    for (size_t ni = 0; ni < sc.nodes.size(); ++ni) {
+        const Node& n = sc.nodes[ni];
+        if (n.left.kind == O_NODE) continue;
+        const bool same = n.left.kind == n.right.kind && n.left.idx == n.right.idx;
+        for (int k = 0; k < (same ? 1 : 2); ++k) {
+            prims.push_back(k == 0 ? n.left : n.right);
+            leaf.push_back((uint32_t)ni);
+            rank.push_back(sc.leaf_rank[2 * ni + k]);
+        }
+    }
+    std::vector<Aabb> pb(prims.size());
+    std::vector<V3> pc(prims.size());
+    for (size_t i = 0; i < prims.size(); ++i) {
+        pb[i] = sc.bbox_of(prims[i]);
+        pc[i] = {0.5 * (pb[i].x.min + pb[i].x.max), 0.5 * (pb[i].y.min + pb[i].y.max), 0.5 * (pb[i].z.min + pb[i].z.max)};
+    }
+    std::vector<int> idx(prims.size());
+    for (size_t i = 0; i < idx.size(); ++i) idx[i] = (int)i;
+    ft.nodes.clear();
+    ft.nodes.reserve(prims.size());
+    if (!prims.empty()) fast_build(sc, ft, idx, 0, (int)prims.size(), pb, pc);
+    ft.prims.resize(prims.size());
+    ft.ref_leaf.resize(prims.size());
+    ft.ref_rank.resize(prims.size());
+    for (size_t i = 0; i < idx.size(); ++i) {
+        ft.prims[i] = prims[idx[i]];
+        ft.ref_leaf[i] = leaf[idx[i]];
+        ft.ref_rank[i] = rank[idx[i]];
+    }
+}
+static void fast_visit(const Scene& sc, const FastTree& ft, int ni, const Ray& r, double tmin, double tmax, OrderFree& st, Counters& cn) {
+    const FastNode& n = ft.nodes[ni];
+    if (n.count > 0) {
+        for (int i = n.first; i < n.first + n.count; ++i) {
+            HitRecord h;
+            if (!obj_hit(sc, ft.prims[i], r, Interval{tmin, tmax}, h, cn)) continue;
+            if (!(h.t < st.best || (st.has && h.t == st.best))) continue;
+            double near_t, far_t; /* the candidate matters: consult the REFERENCE leaf-node box */
+            if (!aabb_span(sc.nodes[ft.ref_leaf[i]].bbox, r, tmin, near_t, far_t)) continue; /* the reference never tests it */
+            if (h.t < near_t) { st.irregular = true; continue; }
+            if (h.t < st.best || ft.ref_rank[i] < st.win_rank) {
+                st.best = h.t; st.win = ft.prims[i]; st.win_rank = ft.ref_rank[i]; st.has = true;
+            }
+        }
+        return;
+    }
+    double nl, fl, nr, fr;
+    cn.node += 2;
+    bool hl = aabb_span(ft.nodes[n.left].box, r, tmin, nl, fl) && nl <= st.best + st.margin;
+    bool hr = aabb_span(ft.nodes[n.right].box, r, tmin, nr, fr) && nr <= st.best + st.margin;
+    if (hl && hr) {
+        const bool lf = nl <= nr;
+        fast_visit(sc, ft, lf ? n.left : n.right, r, tmin, tmax, st, cn);
+        const double nn = lf ? nr : nl;
+        if (nn <= st.best + st.margin) fast_visit(sc, ft, lf ? n.right : n.left, r, tmin, tmax, st, cn);
+    } else if (hl) fast_visit(sc, ft, n.left, r, tmin, tmax, st, cn);
+    else if (hr) fast_visit(sc, ft, n.right, r, tmin, tmax, st, cn);
+}
+
 static void assign_leaf_ranks(Scene& sc, const Obj& o, uint32_t& next) {
     if (o.kind != O_NODE) return;
     const Node& n = sc.nodes[o.idx];
@@ -606,7 +740,7 @@ static void assign_leaf_ranks(Scene& sc, const Obj& o, uint32_t& next) {
     }
 }
 /* returns: 1 hit, 0 miss, -1 flagged irregular (caller falls back to world_hit) */
-static inline int order_free_hit(const Scene& sc, const Ray& r, double tmin, double tmax, double margin_k, HitRecord& out, Counters& cn) {
+static inline int order_free_hit(const Scene& sc, const Ray& r, double tmin, double tmax, double margin_k, HitRecord& out, Counters& cn, const FastTree* ft = nullptr) {
     cn.rays++;
     if (sc.world.kind != O_NODE) return 0;
     const double dl = std::sqrt(len2(r.d));
@@ -624,7 +758,13 @@ static inline int order_free_hit(const Scene& sc, const Ray& r, double tmin, dou
     st.has = false;
     st.irregular = false;
     st.margin = margin_k * (oo + 3.0 * B) / dl;
-    order_free_visit(sc, sc.world, r, tmin, tmax, st, cn);
+    if (ft) {
+        double n0, f0;
+        cn.node++;
+        if (!ft->nodes.empty() && aabb_span(ft->nodes[0].box, r, tmin, n0, f0)) fast_visit(sc, *ft, 0, r, tmin, tmax, st, cn);
+    } else {
+        order_free_visit(sc, sc.world, r, tmin, tmax, st, cn);
+    }
     if (st.irregular) return -1;
     if (!st.has) return 0;
     Counters dummy;
@@ -682,6 +822,8 @@ static void build_world(Scene& sc) {
         n.bbox = aabb_union(sc.bbox_of(n.left), sc.bbox_of(n.right)); /* new_from_vec, :38-41 */
         sc.world = root;
     }
+    delete sc.fast; /* MODEL tree of the previous build */
+    sc.fast = nullptr;
     sc.leaf_rank.assign(2 * sc.nodes.size(), 0u);
     {
         uint32_t next = 0;
@@ -1187,6 +1329,11 @@ int orc_trace_batch(const OrcScene* h, const double* rays, size_t n, double tmin
         return CR_ERR_STATE;
     }
     if (nthreads < 1) nthreads = 1;
+    if (mode == 3 && !sc.fast) {
+        Scene& msc = const_cast<Scene&>(sc);
+        msc.fast = new FastTree();
+        fast_tree_build(sc, *msc.fast);
+    }
     std::atomic<size_t> next{0};
     auto work = [&]() {
         const size_t chunk = 4096;
@@ -1201,7 +1348,7 @@ int orc_trace_batch(const OrcScene* h, const double* rays, size_t n, double tmin
                 Counters cn;
                 bool got;
                 if (mode >= 2) { /* MODEL of the order-free traversal; counters[3] = 0xFFFFFFFF marks a flagged ray */
-                    const int rc = order_free_hit(sc, r, tmin, tmax, g_order_free_margin, hr, cn);
+                    const int rc = order_free_hit(sc, r, tmin, tmax, g_order_free_margin, hr, cn, mode == 3 ? sc.fast : nullptr);
                     got = rc > 0;
                     if (rc < 0) {
                         Counters c2;

@@ -148,3 +148,43 @@ def test_animation_frames_sharded(gpu_device, oracle):
         ref, ref8, _ = orc.render(cam, seed=4)
         assert (got[f] != ref8).mean() < 0.01  # bytes differ only at razor-edge values (see test_render_parity)
     assert not np.array_equal(got[0], got[11])  # the camera really moved
+
+
+@pytest.mark.gpu
+def test_render_multi_equals_single_render(gpu_device, crlib):
+    """cr_render_multi over every visible device (one replica per device, rows stored into the first device's image by
+    each device's resolve kernel): bit-identical to cr_render on one device.  With one device this still exercises
+    cr_scene_replicate and the global-row device output."""
+    from crucible_b200 import abi, demo_builder, gpu
+    from crucible_b200.gpu import GpuScene, rows_of_rank
+
+    sc = demo_builder.load_teapot(image_width=128, samples=3)
+    gs = GpuScene(sc.describe(), gpu_device)
+    cam = sc.scene_cam.to_abi()
+    full, full8, st = gs.render(cam, seed=12)
+    n = min(crlib.cr_device_count(), 8)
+    replicas = [gs] + [gs.replicate(d) for d in range(1, n)]
+    assert replicas[-1].bvh_info() == gs.bvh_info()
+    rgb, rgb8, stats = gpu.render_multi(replicas, cam, seed=12)
+    assert np.array_equal(rgb, full) and np.array_equal(rgb8, full8)
+    assert sum(s["rays"] for s in stats) == st["rays"] and len(stats) == n
+    _, only8, _ = gpu.render_multi(replicas, cam, seed=12, want_rgb=False)  # bytes only: what Camera::render consumes
+    assert np.array_equal(only8, full8)
+    # a replica on the same device is a second, independent scene handle
+    twin = gs.replicate(gpu_device)
+    a, _, _ = twin.render(cam, seed=12)
+    assert np.array_equal(a, full)
+    with pytest.raises(abi.CrucibleError, match="two replicas on one device"):
+        gpu.render_multi([gs, twin], cam, seed=12)
+    # global-row device output of one shard: the other rows stay untouched
+    H, W = cam.image_height, cam.image_width
+    buf = torch.full((H, W, 3), -1.0, dtype=torch.float64, device="cuda")
+    gs.render_device(cam, buf.data_ptr(), 0, stream=torch.cuda.current_stream().cuda_stream, seed=12, row_rank=1, row_world=3,
+                     global_rows=True)
+    rows = rows_of_rank(H, 8, 1, 3)
+    out = buf.cpu().numpy()
+    assert np.array_equal(out[rows], full[rows])
+    rest = np.setdiff1d(np.arange(H), rows)
+    assert (out[rest] == -1.0).all()
+    for r in replicas[1:] + [twin]:
+        r.close()
