@@ -21,6 +21,8 @@ CR_MAX_CAM_KEYS = 32
 CR_PPM_P3, CR_PPM_P6 = 0, 1
 CR_BVH_AUTO, CR_BVH_HOST, CR_BVH_DEVICE = 0, 1, 2
 CR_RENDER_GLOBAL_ROWS = 1
+CR_RENDER_REFERENCE_ORDER = 2
+CR_TRACE_REFERENCE_ORDER = 0x100
 
 
 class CrMaterial(C.Structure):
@@ -60,7 +62,7 @@ class CrRenderOpts(C.Structure):
 class CrStats(C.Structure):
     _fields_ = [("samples", C.c_uint64), ("rays", C.c_uint64), ("iterations", C.c_uint64), ("launches", C.c_uint64),
                 ("ms_total", C.c_double), ("ms_trace", C.c_double), ("ms_shade", C.c_double), ("ms_raygen", C.c_double),
-                ("ms_resolve", C.c_double), ("ms_h2d", C.c_double), ("ms_d2h", C.c_double)]
+                ("ms_resolve", C.c_double), ("ms_h2d", C.c_double), ("ms_d2h", C.c_double), ("retried_rays", C.c_uint64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -74,7 +76,7 @@ class CrHit(C.Structure):
 class CrCommitInfo(C.Structure):
     _fields_ = [("builder", C.c_int32), ("levels", C.c_uint32), ("ms_total", C.c_double), ("ms_build", C.c_double),
                 ("ms_pack", C.c_double), ("ms_h2d", C.c_double), ("ms_device", C.c_double), ("ms_d2h", C.c_double),
-                ("ms_upload", C.c_double)]
+                ("ms_upload", C.c_double), ("ms_search_tree", C.c_double)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -116,6 +118,7 @@ SIGNATURES = {
     "cr_scene_bvh_info": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]),
     "cr_scene_bvh_leaf_order": (C.c_int64, [_P, _P, C.c_size_t]),
     "cr_trace_batch": (C.c_int, [_P, _P, C.c_size_t, C.c_double, C.c_double, C.c_int, _P]),
+    "cr_scene_last_retried": (C.c_int64, [_P]),
     "cr_render": (C.c_int, [_P, C.POINTER(CrCamera), C.POINTER(CrRenderOpts), _P, _P, C.POINTER(CrStats)]),
     "cr_render_device": (C.c_int, [_P, C.POINTER(CrCamera), C.POINTER(CrRenderOpts), _P, _P, _P, C.POINTER(CrStats)]),
     "cr_scene_replicate": (_P, [_P, C.c_int]),

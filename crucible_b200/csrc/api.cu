@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "bvh_host.h"
+#include "fast_tree.h"
 #include "integrator.h"
 
 using namespace crb;
@@ -78,6 +79,7 @@ struct CrScene {
     size_t out_cap = 0;
     void* d_io = nullptr;  // trace_batch staging
     size_t io_cap = 0;
+    int64_t last_retried = 0;  // rays of the last cr_trace_batch the order-free engine handed back
     // cr_render_multi: the assembled image on this (the first) device; plain cudaMalloc so that peers can map it
     void* d_multi_rgb = nullptr;
     void* d_multi_rgb8 = nullptr;
@@ -252,6 +254,61 @@ bool tex_needs_uv(const CrScene* s, int tex, int depth = 0) {
     if (t.kind == CR_TEX_IMAGE) return true;
     if (t.kind == CR_TEX_CHECKER) return tex_needs_uv(s, t.even, depth + 1) || tex_needs_uv(s, t.odd, depth + 1);
     return false;
+}
+
+// ---- search tree of the order-free engine: per primitive, its REFERENCE leaf node and slot (= DFS rank) ----------
+// A leaf node of the committed reference tree holds one or two primitive refs in its two words (common.cuh); the map is
+// read off the device copy, so it serves host-built and device-built trees alike.
+__device__ __forceinline__ uint32_t prim_slot(uint32_t ref, uint32_t off_tri, uint32_t off_quad) {
+    const uint32_t k = ref_kind(ref);
+    return (k == CR_PRIM_SPHERE ? 0u : (k == CR_PRIM_TRIANGLE ? off_tri : off_quad)) + ref_index(ref);
+}
+__global__ void k_fast_leafmap(const NodeRec<double>* __restrict__ nodes, uint32_t n_nodes, uint32_t* __restrict__ map, uint32_t off_tri,
+                               uint32_t off_quad) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_nodes; i += gridDim.x * blockDim.x) {
+        const uint32_t wa = nodes[i].left, wb = nodes[i].right;
+        if (!ref_is_leaf(wa)) continue;
+        map[prim_slot(wa, off_tri, off_quad)] = 2u * i;
+        if (wb != REF_NONE) map[prim_slot(wb, off_tri, off_quad)] = 2u * i + 1u;
+    }
+}
+__global__ void k_fast_fill(uint2* __restrict__ prims, uint32_t n, const uint32_t* __restrict__ map, uint32_t off_tri, uint32_t off_quad) {
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x)
+        prims[j].y = map[prim_slot(prims[j].x, off_tri, off_quad)];
+}
+
+// Builds the search tree over the visible primitives on the host (fast_tree.h), uploads it and fills the DFS ranks.
+int upload_search_tree(CrScene* s, const std::vector<uint32_t>& visible) {
+    SceneDeviceData& d = s->dev;
+    d.fast_nodes = d.fast_prims = nullptr;
+    if (visible.empty() || !s->anim.empty() || getenv("CRB_NO_SEARCH_TREE")) return CR_OK;
+    FastTreeHost ft;
+    build_fast_tree(s->elements, visible, ft);
+    std::vector<uint2> table(ft.leaf_prims.size());
+    for (size_t i = 0; i < table.size(); ++i) {
+        const Element& e = s->elements[ft.leaf_prims[i]];
+        table[i] = make_uint2(make_leaf(e.kind, e.idx), 0u);
+    }
+    void *dn = nullptr, *dp = nullptr, *dm = nullptr;
+    int rc;
+    if ((rc = upload(s, ft.nodes, &dn)) != CR_OK) return rc;
+    if ((rc = upload(s, table, &dp)) != CR_OK) return rc;
+    const uint32_t off_tri = d.n_prims[0], off_quad = d.n_prims[0] + d.n_prims[1];
+    const size_t n_all = (size_t)d.n_prims[0] + d.n_prims[1] + d.n_prims[2];
+    API_CUDA(cudaMallocAsync(&dm, std::max<size_t>(n_all, 1) * sizeof(uint32_t), s->stream));
+    const int threads = 256;
+    const int g1 = (int)std::min<size_t>(((size_t)d.n_nodes + threads - 1) / threads, (size_t)s->num_sms * 16);
+    const int g2 = (int)std::min<size_t>((table.size() + threads - 1) / threads, (size_t)s->num_sms * 16);
+    k_fast_leafmap<<<std::max(g1, 1), threads, 0, s->stream>>>(static_cast<const NodeRec<double>*>(d.nodes[0]), d.n_nodes,
+                                                               static_cast<uint32_t*>(dm), off_tri, off_quad);
+    k_fast_fill<<<std::max(g2, 1), threads, 0, s->stream>>>(static_cast<uint2*>(dp), (uint32_t)table.size(), static_cast<const uint32_t*>(dm), off_tri,
+                                                            off_quad);
+    API_CUDA(cudaGetLastError());
+    API_CUDA(cudaFreeAsync(dm, s->stream));
+    API_CUDA(cudaStreamSynchronize(s->stream));  // `ft` and `table` die with this scope
+    d.fast_nodes = dn;
+    d.fast_prims = dp;
+    return CR_OK;
 }
 
 int upload_scene(CrScene* s) {
@@ -888,6 +945,13 @@ int cr_scene_commit(CrScene* s) {
             return rc;
         }
         s->commit_info.ms_upload = ms_since(t_upload);
+        const auto t_search = clk::now();
+        rc = upload_search_tree(s, visible);
+        if (rc != CR_OK) {
+            s->committed = false;
+            return rc;
+        }
+        s->commit_info.ms_search_tree = ms_since(t_search);
     }
     s->commit_info.ms_total = ms_since(t_commit);
     return CR_OK;
@@ -995,15 +1059,19 @@ int64_t cr_scene_bvh_leaf_order(const CrScene* s, int32_t* out, size_t cap) {
     return (int64_t)order.size();
 }
 
-int cr_trace_batch(CrScene* s, const double* rays, size_t n, double tmin, double tmax, int precision, CrHit* out) {
+int cr_trace_batch(CrScene* s, const double* rays, size_t n, double tmin, double tmax, int precision_flags, CrHit* out) {
     int rc = need_device(s);
     if (rc != CR_OK) return rc;
     if ((!rays || !out) && n) return fail(CR_ERR_INVALID, "null argument");
-    if (precision != CR_PRECISION_F64 && precision != CR_PRECISION_F32) return fail(CR_ERR_INVALID, "bad precision");
+    const int precision = precision_flags & 0xff, reference_order = (precision_flags & CR_TRACE_REFERENCE_ORDER) ? 1 : 0;
+    if ((precision != CR_PRECISION_F64 && precision != CR_PRECISION_F32) || (precision_flags & ~(0xff | CR_TRACE_REFERENCE_ORDER)))
+        return fail(CR_ERR_INVALID, "bad precision");
+    s->last_retried = 0;
     if (n == 0) return CR_OK;
     API_CUDA(cudaSetDevice(s->device));
-    const size_t bytes_in = n * 7 * sizeof(double), bytes_out = n * sizeof(CrHit);
-    const size_t need = ((bytes_in + 255) & ~(size_t)255) + ((bytes_out + 255) & ~(size_t)255) + 256;
+    auto pad = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t bytes_in = n * 7 * sizeof(double), bytes_out = n * sizeof(CrHit), bytes_retry = n * sizeof(uint32_t);
+    const size_t need = pad(bytes_in) + pad(bytes_out) + pad(bytes_retry) + 256;
     if (need > s->io_cap) {
         if (s->d_io) cudaFreeAsync(s->d_io, s->stream);
         s->d_io = nullptr;
@@ -1011,17 +1079,27 @@ int cr_trace_batch(CrScene* s, const double* rays, size_t n, double tmin, double
         API_CUDA(cudaMallocAsync(&s->d_io, need, s->stream));
         s->io_cap = need;
     }
-    double* d_rays = static_cast<double*>(s->d_io);
-    CrHit* d_out = reinterpret_cast<CrHit*>(static_cast<char*>(s->d_io) + ((bytes_in + 255) & ~(size_t)255));
-    uint32_t* d_cursor = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(d_out) + ((bytes_out + 255) & ~(size_t)255));
+    char* base = static_cast<char*>(s->d_io);
+    double* d_rays = reinterpret_cast<double*>(base);
+    CrHit* d_out = reinterpret_cast<CrHit*>(base + pad(bytes_in));
+    uint32_t* d_retry = reinterpret_cast<uint32_t*>(base + pad(bytes_in) + pad(bytes_out));
+    uint32_t* d_cursor = reinterpret_cast<uint32_t*>(base + pad(bytes_in) + pad(bytes_out) + pad(bytes_retry));
     API_CUDA(cudaMemcpyAsync(d_rays, rays, bytes_in, cudaMemcpyHostToDevice, s->stream));
     std::string err;
-    rc = (precision == CR_PRECISION_F64) ? trace_batch_impl<double>(s->dev, d_rays, n, tmin, tmax, d_out, d_cursor, s->stream, err)
-                                         : trace_batch_impl<float>(s->dev, d_rays, n, tmin, tmax, d_out, d_cursor, s->stream, err);
+    uint32_t retried = 0;
+    rc = (precision == CR_PRECISION_F64)
+             ? trace_batch_impl<double>(s->dev, d_rays, n, tmin, tmax, d_out, d_cursor, d_retry, reference_order, &retried, s->stream, err)
+             : trace_batch_impl<float>(s->dev, d_rays, n, tmin, tmax, d_out, d_cursor, d_retry, reference_order, &retried, s->stream, err);
     if (rc != CR_OK) return fail(rc, err);
     API_CUDA(cudaMemcpyAsync(out, d_out, bytes_out, cudaMemcpyDeviceToHost, s->stream));
     API_CUDA(cudaStreamSynchronize(s->stream));
+    s->last_retried = (int64_t)retried;
     return CR_OK;
+}
+
+int64_t cr_scene_last_retried(const CrScene* s) {
+    if (!s) return fail(CR_ERR_INVALID, "null scene");
+    return s->last_retried;
 }
 
 static int check_camera(const CrCamera* c) {

@@ -76,7 +76,6 @@ struct Builder {
         uint32_t d = max_depth.load();
         while (depth > d && !max_depth.compare_exchange_weak(d, depth)) {}
         // split
-        Box cb;
         float cmin[3] = {3e38f, 3e38f, 3e38f}, cmax[3] = {-3e38f, -3e38f, -3e38f};
         for (uint32_t i = lo; i < hi; ++i) {
             const uint32_t v = idx[i];

@@ -949,6 +949,7 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
     const size_t o_queues = carve((size_t)pool * Q_COUNT * sizeof(uint2));
     const size_t o_filt0 = carve((size_t)pool * sizeof(FilterRec));
     const size_t o_filt1 = carve((size_t)pool * sizeof(FilterRec));
+    const size_t o_retry = carve((size_t)pool * sizeof(uint32_t));
     const size_t o_fb = carve((size_t)npix * 3 * sizeof(unsigned long long));
     int rc = ws.ensure(off, err);
     if (rc != CR_OK) return rc;
@@ -959,6 +960,7 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
     uint2* queues = reinterpret_cast<uint2*>(base + o_queues);
     FilterRec* filt[2] = {reinterpret_cast<FilterRec*>(base + o_filt0), reinterpret_cast<FilterRec*>(base + o_filt1)};
     unsigned long long* fb = reinterpret_cast<unsigned long long*>(base + o_fb);
+    uint32_t* retry_list = reinterpret_cast<uint32_t*>(base + o_retry);
 
     if (!ws.pinned) {
         CRB_CUDA(cudaHostAlloc(&ws.pinned, 4096, cudaHostAllocDefault));
@@ -1001,8 +1003,15 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
     // +4 %); where the f64 exact / leaf steps dominate (thin padded boxes of the Cornell quads) the spills of the
     // small budget lose 20 %.  Unless CRB_MINB pins one, the first large wavefront of a scene is traced with both
     // (same rays, same result) and the faster one is kept; the choice is cached per device by scene signature.
-    typedef void (*TraceFn)(DevScene<R>, PathRec<R>*, Control*, int, uint2*, const FilterRec*, uint32_t);
+    typedef void (*TraceFn)(DevScene<R>, PathRec<R>*, Control*, int, uint2*, const FilterRec*, uint32_t, const uint32_t*);
     const bool animated = s.anim_keys != nullptr;  // object keyframes: the builds that evaluate timelines at the ray time
+    // Static scenes with a search tree run the order-free engine (fast_trace.cuh); the rays it hands back are traced by
+    // the reference-order kernel in a second, small launch.  CR_RENDER_REFERENCE_ORDER keeps reference order throughout.
+    const bool fast = use_fast_engine(s, (opts.flags & CR_RENDER_REFERENCE_ORDER) != 0u);
+    int fmb = 8;
+    if (const char* e = getenv("CRB_FAST_MINB")) fmb = atoi(e);
+    auto fast_fn = fmb <= 6 ? k_trace_fast<R, 6> : (fmb <= 8 ? k_trace_fast<R, 8> : k_trace_fast<R, 10>);
+    const int g_fast = persistent_grid(fast_fn, TRACE_BLOCK, s.num_sms);
     TraceFn trace_variants[2] = {animated ? k_trace<R, CRB_REFILL, 8, true> : k_trace<R, CRB_REFILL, 8, false>,
                                  animated ? k_trace<R, CRB_REFILL, 8, true> : k_trace<R, CRB_REFILL, 10, false>};
     const int trace_grids[2] = {persistent_grid(trace_variants[0], TRACE_BLOCK, s.num_sms),
@@ -1011,7 +1020,7 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
     int variant = ws.lookup_variant(signature);
     if (const char* e = getenv("CRB_MINB")) variant = atoi(e) <= 8 ? 0 : 1;
     const uint64_t tune_at = total >= 2ull * pool ? 1 : 0;  // the second wavefront mixes bounce rays with camera rays
-    bool tuning = variant < 0 && total >= (1ull << 20) && !animated;
+    bool tuning = variant < 0 && total >= (1ull << 20) && !animated && !fast;
     if (variant < 0) variant = 1;
     TraceFn trace_fn = trace_variants[variant];
     int g_trace = trace_grids[variant];
@@ -1075,7 +1084,7 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
             for (auto& e : te) CRB_CUDA(events.make(&e));
             for (int v = 0; v < 2; ++v) {
                 CRB_CUDA(cudaEventRecord(te[2 * v], stream));
-                trace_variants[v]<<<trace_grids[v], TRACE_BLOCK, 0, stream>>>(sc, paths[cur], ctl, cur, queues, filt[cur], pool);
+                trace_variants[v]<<<trace_grids[v], TRACE_BLOCK, 0, stream>>>(sc, paths[cur], ctl, cur, queues, filt[cur], pool, nullptr);
                 CRB_CUDA(cudaEventRecord(te[2 * v + 1], stream));
                 if (v == 0) k_trace_rewind<<<1, 32, 0, stream>>>(ctl);
             }
@@ -1091,7 +1100,13 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
             tuning = false;
         } else {
             tm.begin(0, a);
-            trace_fn<<<g_trace, TRACE_BLOCK, 0, stream>>>(sc, paths[cur], ctl, cur, queues, filt[cur], pool);
+            if (fast) {
+                fast_fn<<<g_fast, TRACE_BLOCK, 0, stream>>>(sc, paths[cur], ctl, cur, queues, filt[cur], pool, retry_list);
+                trace_variants[0]<<<s.num_sms * 2, TRACE_BLOCK, 0, stream>>>(sc, paths[cur], ctl, cur, queues, filt[cur], pool, retry_list);
+                ++launches;
+            } else {
+                trace_fn<<<g_trace, TRACE_BLOCK, 0, stream>>>(sc, paths[cur], ctl, cur, queues, filt[cur], pool, nullptr);
+            }
             tm.end(0, a);
         }
         tm.begin(1, a);
@@ -1166,6 +1181,7 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
         cudaEventElapsedTime(&ms, ev_begin, ev_end);
         stats->samples = total;
         stats->rays = fin.rays_traced;
+        stats->retried_rays = (uint64_t)fin.retry_total + fin.retry_count;
         stats->iterations = it;
         stats->launches = launches;
         stats->ms_total = ms;

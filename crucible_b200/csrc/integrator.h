@@ -24,6 +24,8 @@ struct SceneDeviceData {
     AnimTrack* tri_track = nullptr;
     uint32_t* tri_anim_slot = nullptr;
     double* tri_anim_verts = nullptr;
+    void* fast_nodes = nullptr;  // search tree of the order-free engine (FastNodeRec[]), nullptr = none
+    void* fast_prims = nullptr;  // its leaf-primitive table (uint2[])
     uint32_t n_nodes = 0;
     uint32_t n_prims[3] = {0, 0, 0};  // spheres, triangles, quads
     int32_t sky_kind = CR_SKY_DEFAULT, sky_image = -1;
@@ -83,7 +85,7 @@ int render_impl(const SceneDeviceData&, Workspace&, const CrCamera&, const CrRen
                 int packed, cudaStream_t, CrStats*, std::string& err);
 template <typename R>
 int trace_batch_impl(const SceneDeviceData&, const double* d_rays, size_t n, double tmin, double tmax, CrHit* d_out,
-                     uint32_t* d_cursor, cudaStream_t, std::string& err);
+                     uint32_t* d_cursor, uint32_t* d_retry, int reference_order, uint32_t* h_retried, cudaStream_t, std::string& err);
 
 // FMA micro-benchmarks (roofline denominators); defined in integrator_f32.cu
 int measure_fma_peak(int num_sms, double* fp64_tflops, double* fp32_tflops, std::string& err);

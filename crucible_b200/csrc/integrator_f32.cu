@@ -7,8 +7,8 @@
 namespace crb {
 template int render_impl<float>(const SceneDeviceData&, Workspace&, const CrCamera&, const CrRenderOpts&, void*, void*, int,
                                 cudaStream_t, CrStats*, std::string&);
-template int trace_batch_impl<float>(const SceneDeviceData&, const double*, size_t, double, double, CrHit*, uint32_t*, cudaStream_t,
-                                     std::string&);
+template int trace_batch_impl<float>(const SceneDeviceData&, const double*, size_t, double, double, CrHit*, uint32_t*, uint32_t*, int,
+                                      uint32_t*, cudaStream_t, std::string&);
 
 // Register-resident FMA chains: 8 independent accumulators per thread, 2 flops per FMA.
 template <typename T>

@@ -8,6 +8,6 @@
 namespace crb {
 template int render_impl<double>(const SceneDeviceData&, Workspace&, const CrCamera&, const CrRenderOpts&, void*, void*, int,
                                  cudaStream_t, CrStats*, std::string&);
-template int trace_batch_impl<double>(const SceneDeviceData&, const double*, size_t, double, double, CrHit*, uint32_t*, cudaStream_t,
-                                      std::string&);
+template int trace_batch_impl<double>(const SceneDeviceData&, const double*, size_t, double, double, CrHit*, uint32_t*, uint32_t*, int,
+                                      uint32_t*, cudaStream_t, std::string&);
 }  // namespace crb

@@ -88,23 +88,30 @@ class GpuScene:
         return ci.as_dict()
 
     # ---- Hittables::hit on a ray batch
-    def trace_batch(self, rays, tmin=0.001, tmax=float("inf"), precision=abi.CR_PRECISION_F64):
+    def trace_batch(self, rays, tmin=0.001, tmax=float("inf"), precision=abi.CR_PRECISION_F64, reference_order=False):
+        """reference_order: the reference's own DFS throughout (CR_TRACE_REFERENCE_ORDER) instead of the order-free
+        engine + reference-order retries.  `last_retried()` tells how many rays the order-free engine handed back."""
         rays = np.ascontiguousarray(rays, np.float64)
         assert rays.ndim == 2 and rays.shape[1] == 7, "rays = [n][7] (origin, direction, time)"
         out = np.zeros(len(rays), dtype=abi.HIT_DTYPE)
+        flags = int(precision) | (abi.CR_TRACE_REFERENCE_ORDER if reference_order else 0)
         abi.check(self.lib.cr_trace_batch(self.handle, rays.ctypes.data_as(C.c_void_p), len(rays), float(tmin), float(tmax),
-                                          int(precision), out.ctypes.data_as(C.c_void_p)))
+                                          flags, out.ctypes.data_as(C.c_void_p)))
         return out
+
+    def last_retried(self):
+        return int(self.lib.cr_scene_last_retried(self.handle))
 
     # ---- Camera::render sample loop, host buffers (H2D of the camera, D2H of the framebuffer inside)
     def render(self, cam: abi.CrCamera, seed=1, precision=abi.CR_PRECISION_F64, pool_paths=0, row_block=8, row_rank=0,
-               row_world=1, time_kernels=False, want_rgb=True, want_rgb8=True, out_rgb=None, out_rgb8=None):
+               row_world=1, time_kernels=False, want_rgb=True, want_rgb8=True, out_rgb=None, out_rgb8=None, reference_order=False):
         H, W = cam.image_height, cam.image_width
         if want_rgb and out_rgb is None:
             out_rgb = np.zeros((H, W, 3), np.float64)
         if want_rgb8 and out_rgb8 is None:
             out_rgb8 = np.zeros((H, W, 3), np.uint8)
-        opts = abi.CrRenderOpts(seed, precision, pool_paths, row_block, row_rank, row_world, 1 if time_kernels else 0)
+        opts = abi.CrRenderOpts(seed, precision, pool_paths, row_block, row_rank, row_world, 1 if time_kernels else 0,
+                                abi.CR_RENDER_REFERENCE_ORDER if reference_order else 0)
         st = abi.CrStats()
         abi.check(self.lib.cr_render(self.handle, C.byref(cam), C.byref(opts),
                                      out_rgb.ctypes.data_as(C.c_void_p) if out_rgb is not None else None,
@@ -114,11 +121,11 @@ class GpuScene:
     # ---- device variant: packed rows of this rank into caller-owned device memory, on the caller's stream
     def render_device(self, cam: abi.CrCamera, d_out_rgb: int, d_out_rgb8: int, stream: int = 0, seed=1,
                       precision=abi.CR_PRECISION_F64, pool_paths=0, row_block=8, row_rank=0, row_world=1, time_kernels=False,
-                      global_rows=False):
+                      global_rows=False, reference_order=False):
         """global_rows: the outputs are full [H][W][3] images (possibly on another device / in another process' buffer)
         and this rank's rows are stored at their global position (CR_RENDER_GLOBAL_ROWS)."""
         opts = abi.CrRenderOpts(seed, precision, pool_paths, row_block, row_rank, row_world, 1 if time_kernels else 0,
-                                abi.CR_RENDER_GLOBAL_ROWS if global_rows else 0)
+                                (abi.CR_RENDER_GLOBAL_ROWS if global_rows else 0) | (abi.CR_RENDER_REFERENCE_ORDER if reference_order else 0))
         st = abi.CrStats()
         abi.check(self.lib.cr_render_device(self.handle, C.byref(cam), C.byref(opts), C.c_void_p(d_out_rgb or None),
                                             C.c_void_p(d_out_rgb8 or None), C.c_void_p(stream or None), C.byref(st)))

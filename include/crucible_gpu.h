@@ -151,6 +151,12 @@ typedef struct CrRenderOpts {
  * (peer-mapped memory, or a buffer opened with cr_shared_buffer_open): the resolve kernel then stores its rows
  * straight into that device's memory over NVLink, which is the whole framebuffer gather of SURVEY 8e. */
 #define CR_RENDER_GLOBAL_ROWS 1u
+/* Closest hits in the reference's own traversal order throughout (BVHWrapper::hit, bvhwrapper.rs:97-126: DFS over the
+ * reference tree).  Default for static scenes is the order-free engine: the same hits found by a near-first search over
+ * a tree of its own, every candidate confirmed against its reference leaf-node box, undecidable rays re-traced in
+ * reference order (DESIGN.md 5.1b states the one numerical assumption this rests on).  Scenes with object keyframes
+ * always use reference order. */
+#define CR_RENDER_REFERENCE_ORDER 2u
 
 typedef struct CrStats {
     uint64_t samples;      /* camera samples generated (W*H*spp over the rows rendered) */
@@ -163,6 +169,7 @@ typedef struct CrStats {
     double ms_raygen;      /* time_kernels=1: plan + raygen */
     double ms_resolve;
     double ms_h2d, ms_d2h; /* host-buffer entry points only */
+    uint64_t retried_rays; /* order-free engine: ray segments handed back to the reference-order kernel */
 } CrStats;
 
 /* Result of a closest-hit query: the fields of HitRecord (src/objects/mod.rs:21-29)
@@ -264,6 +271,7 @@ typedef struct CrCommitInfo {
     double ms_build;   /* BVH build (DEVICE: pack + h2d + device + d2h below) */
     double ms_pack, ms_h2d, ms_device, ms_d2h; /* DEVICE builder phases; 0 for HOST */
     double ms_upload;  /* flatten to device records + H2D of the scene */
+    double ms_search_tree; /* build + upload of the order-free engine's search tree (0 when the scene has none) */
 } CrCommitInfo;
 int cr_scene_commit_info(const CrScene*, CrCommitInfo* out);
 /* One node of the committed BVH in preorder (tests compare the two builders bit for bit). */
@@ -292,6 +300,11 @@ int64_t cr_scene_bvh_leaf_order(const CrScene*, int32_t* out, size_t cap);
  * The ray time positions animated primitives (Sphere::hit / Triangle::hit evaluate their timelines at r.time()). */
 int cr_trace_batch(CrScene*, const double* rays, size_t n, double tmin, double tmax,
                    int precision, CrHit* out);
+/* `precision` of cr_trace_batch = CrPrecision, optionally OR-ed with this bit: reference traversal order throughout
+ * (see CR_RENDER_REFERENCE_ORDER). */
+#define CR_TRACE_REFERENCE_ORDER 0x100
+/* Rays of the last cr_trace_batch on this scene that the order-free engine handed back to the reference-order kernel. */
+int64_t cr_scene_last_retried(const CrScene*);
 
 /* Replaces thread_setup .. join of Camera::render (camera/mod.rs:284-303): one averaged
  * linear colour per pixel, row-major j then i (camera/mod.rs:306-311).
