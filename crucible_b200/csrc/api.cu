@@ -282,6 +282,21 @@ int upload_search_tree(CrScene* s, const std::vector<uint32_t>& visible) {
     SceneDeviceData& d = s->dev;
     d.fast_nodes = d.fast_prims = nullptr;
     if (visible.empty() || !s->anim.empty() || getenv("CRB_NO_SEARCH_TREE")) return CR_OK;
+    // large scenes: linear BVH built on the device from the records just uploaded (search_tree.cu); small ones: binned SAH here
+    bool on_device = visible.size() >= 32768;
+    if (const char* e = getenv("CRB_SEARCH_TREE")) on_device = e[0] == 'l' && visible.size() >= 3;
+    if (on_device) {
+        void *dn = nullptr, *dp = nullptr;
+        uint32_t depth = 0;
+        std::string err;
+        const int rc = gpu_build_search_tree(d, s->stream, (uint32_t)visible.size(), &dn, &dp, &depth, err);
+        if (rc != CR_OK) return fail(rc, err);
+        if (dn) s->dev_allocs.push_back(dn);
+        if (dp) s->dev_allocs.push_back(dp);
+        d.fast_nodes = dn;
+        d.fast_prims = dp;
+        return CR_OK;
+    }
     FastTreeHost ft;
     build_fast_tree(s->elements, visible, ft);
     std::vector<uint2> table(ft.leaf_prims.size());

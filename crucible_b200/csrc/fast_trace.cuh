@@ -35,31 +35,44 @@
 namespace crb {
 
 enum : int { FS_IDLE = 0, FS_INNER = 1, FS_LEAF = 2, FS_DONE = 3, FS_RETRY = 4 };
-static constexpr int FAST_STACK = 64;
+static constexpr int FAST_STACK = 64;       // the builder bounds the tree depth (FAST_MAX_DEPTH)
+static constexpr int FAST_SMEM_LEVELS = 12;  // stack levels kept in shared memory; deeper ones (rare) in local memory
 
+// Per-CTA lane table, SoA over the lanes (conflict free), as LaneSlots of the reference-order engine, plus the bottom of
+// every lane's traversal stack: lanes of a warp sit at different stack depths, so a local-memory stack costs one L1
+// wavefront per distinct depth and access (ncu: 52 % of the kernel's L1 data-pipe traffic); [level][lane] in shared
+// memory is one conflict-free wavefront whatever the depths.
 template <typename R, int BLOCK>
-struct FastSlots {  // per-CTA lane table, SoA over the lanes (conflict free), as LaneSlots of the reference-order engine
+struct FastSlots {
     R best_t[BLOCK];
     R ray[6][BLOCK];
     float pre[7][BLOCK];
     uint32_t best_ref[BLOCK], best_rank[BLOCK], my[BLOCK];
+    uint32_t stk_ref[FAST_SMEM_LEVELS][BLOCK];
+    float stk_lo[FAST_SMEM_LEVELS][BLOCK];
 };
 
-// Conservative f32 slab test of one child box: entry `lo` (clamped to tmin) and "certainly missed or beyond the
-// closest hit + margin".  Planes as single FFMAs (filter_box, device_math.cuh); the error bound E is the filter's.
+// Conservative f32 slab test of one child box: a lower bound of the entry parameter (clamped to tmin) and "certainly
+// missed, or entered beyond the closest hit + margin".  Planes as single FFMAs (filter_box, device_math.cuh).  The
+// rounding error of a plane distance, 1.01 |inv| (|b| + |o|) 2^-23 + 2^-22 |t| (device_math.cuh), is applied PER AXIS:
+// the near planes are moved down and the far planes up by e_k = 1.3 |inv_k| (B + |o_k|) 2^-23 (folded into the FFMA's
+// constant), so a direction that is almost parallel to one axis (|inv_k| huge) only loses the culling of that axis.
+// (With one bound for all three axes such a ray could cull nothing and walked the whole tree.)
 struct FastRay {
-    float oix, oiy, oiz, ax0, ax1, ay0, ay1, az0, az1, e;
+    float on_x, on_y, on_z;  // o*inv + e: constant of the near planes
+    float of_x, of_y, of_z;  // o*inv - e: constant of the far planes
+    float ax0, ax1, ay0, ay1, az0, az1;
 };
 __device__ __forceinline__ bool fast_child_fails(const NodeRec<float>& n, const FastRay& f, float tmin, float best_m, float& lo_lb) {
-    const float nx = __fmaf_rn(n.xmin, f.ax0, __fmaf_rn(n.xmax, f.ax1, -f.oix));
-    const float fx = __fmaf_rn(n.xmax, f.ax0, __fmaf_rn(n.xmin, f.ax1, -f.oix));
-    const float ny = __fmaf_rn(n.ymin, f.ay0, __fmaf_rn(n.ymax, f.ay1, -f.oiy));
-    const float fy = __fmaf_rn(n.ymax, f.ay0, __fmaf_rn(n.ymin, f.ay1, -f.oiy));
-    const float nz = __fmaf_rn(n.zmin, f.az0, __fmaf_rn(n.zmax, f.az1, -f.oiz));
-    const float fz = __fmaf_rn(n.zmax, f.az0, __fmaf_rn(n.zmin, f.az1, -f.oiz));
+    const float nx = __fmaf_rn(n.xmin, f.ax0, __fmaf_rn(n.xmax, f.ax1, -f.on_x));
+    const float fx = __fmaf_rn(n.xmax, f.ax0, __fmaf_rn(n.xmin, f.ax1, -f.of_x));
+    const float ny = __fmaf_rn(n.ymin, f.ay0, __fmaf_rn(n.ymax, f.ay1, -f.on_y));
+    const float fy = __fmaf_rn(n.ymax, f.ay0, __fmaf_rn(n.ymin, f.ay1, -f.of_y));
+    const float nz = __fmaf_rn(n.zmin, f.az0, __fmaf_rn(n.zmax, f.az1, -f.on_z));
+    const float fz = __fmaf_rn(n.zmax, f.az0, __fmaf_rn(n.zmin, f.az1, -f.of_z));
     const float lo = fmaxf(fmaxf(nx, ny), fmaxf(nz, tmin));
     const float hi = fminf(fminf(fx, fy), fminf(fz, best_m));
-    const float E = __fmaf_rn(fabsf(lo) + fabsf(hi), 4.7683716e-7f, f.e);
+    const float E = (fabsf(lo) + fabsf(hi)) * 4.7683716e-7f;  // the relative part of the plane error, 2^-21 (|lo| + |hi|)
     lo_lb = lo - E;                 // lower bound of the true entry parameter
     return (hi - lo) < -E;          // NaN / inf => false => the child is visited (culling must stay conservative)
 }
@@ -93,13 +106,26 @@ struct FastTrav {
     float margin;
     uint32_t cur;    // inner node index, or the parked leaf word (FS_LEAF)
     int sp;
-    uint32_t stk_ref[FAST_STACK];
-    float stk_lo[FAST_STACK];
+    uint32_t deep_ref[FAST_STACK - FAST_SMEM_LEVELS];  // stack levels beyond the shared-memory part
+    float deep_lo[FAST_STACK - FAST_SMEM_LEVELS];
+    __device__ __forceinline__ void push(uint32_t ref, float lo) {
+        if (sp < FAST_SMEM_LEVELS) {
+            s->stk_ref[sp][threadIdx.x] = ref;
+            s->stk_lo[sp][threadIdx.x] = lo;
+        } else if (sp < FAST_STACK) {
+            deep_ref[sp - FAST_SMEM_LEVELS] = ref;
+            deep_lo[sp - FAST_SMEM_LEVELS] = lo;
+        }
+        ++sp;
+    }
 
     __device__ __forceinline__ void init_from(const FilterRay& f, R tmax, float margin_k, float bmax) {
-        fr.oix = f.oix; fr.oiy = f.oiy; fr.oiz = f.oiz;
+        const float k23 = 1.3f * 1.1920929e-7f;  // 1.3 * 2^-23
+        const float ex = fabsf(f.ix) * (bmax + fabsf(f.ox)) * k23, ey = fabsf(f.iy) * (bmax + fabsf(f.oy)) * k23,
+                    ez = fabsf(f.iz) * (bmax + fabsf(f.oz)) * k23;
+        fr.on_x = f.oix + ex; fr.on_y = f.oiy + ey; fr.on_z = f.oiz + ez;
+        fr.of_x = f.oix - ex; fr.of_y = f.oiy - ey; fr.of_z = f.oiz - ez;
         fr.ax0 = f.ax0; fr.ax1 = f.ax1; fr.ay0 = f.ay0; fr.ay1 = f.ay1; fr.az0 = f.az0; fr.az1 = f.az1;
-        fr.e = f.e_big;
         const int t = threadIdx.x;
         s->pre[0][t] = f.ox; s->pre[1][t] = f.oy; s->pre[2][t] = f.oz; s->pre[3][t] = f.dx; s->pre[4][t] = f.dy; s->pre[5][t] = f.dz;
         s->pre[6][t] = f.o2;
@@ -127,8 +153,9 @@ struct FastTrav {
     __device__ __forceinline__ int pop() {
         while (sp > 0) {
             --sp;
-            if (!(stk_lo[sp] > best_m)) {
-                cur = stk_ref[sp];
+            const float lo = sp < FAST_SMEM_LEVELS ? s->stk_lo[sp][threadIdx.x] : deep_lo[sp - FAST_SMEM_LEVELS];
+            if (!(lo > best_m)) {
+                cur = sp < FAST_SMEM_LEVELS ? s->stk_ref[sp][threadIdx.x] : deep_ref[sp - FAST_SMEM_LEVELS];
                 return (cur & FAST_LEAF) ? (int)FS_LEAF : (int)FS_INNER;
             }
         }
@@ -143,11 +170,7 @@ struct FastTrav {
         const bool hb = !fast_child_fails(b, fr, tmin, best_m, lb) && b.left != FAST_EMPTY;
         if (ha && hb) {
             const bool a_first = !(lb < la);
-            if (sp < FAST_STACK) {  // the builder bounds the depth (FAST_MAX_DEPTH): always true
-                stk_ref[sp] = a_first ? b.left : a.left;
-                stk_lo[sp] = a_first ? lb : la;
-                ++sp;
-            }
+            push(a_first ? b.left : a.left, a_first ? lb : la);
             cur = a_first ? a.left : b.left;
         } else if (ha) {
             cur = a.left;
@@ -164,14 +187,12 @@ struct FastTrav {
     __device__ __forceinline__ bool leaf_certain_miss(const DevScene<R>& sc) const {
         if constexpr (sizeof(R) == 8) {
             const uint32_t first = leaf_first(), cnt = leaf_count();
+            const uint32_t r0 = __ldg(&sc.fast_prims[first].x), r1 = cnt > 1u ? __ldg(&sc.fast_prims[first + 1u].x) : r0;
+            if (ref_kind(r0) != CR_PRIM_SPHERE || ref_kind(r1) != CR_PRIM_SPHERE) return false;  // before touching the lane table
             const int t = threadIdx.x;
             const PreRay pre = {s->pre[0][t], s->pre[1][t], s->pre[2][t], s->pre[3][t], s->pre[4][t], s->pre[5][t], s->pre[6][t]};
-            for (uint32_t k = 0; k < cnt; ++k) {
-                const uint32_t ref = __ldg(&sc.fast_prims[first + k].x);
-                if (ref_kind(ref) != CR_PRIM_SPHERE) return false;
-                if (!sphere_definite_miss(ldg_rec<1>(sc.spheres32 + ref_index(ref)), pre)) return false;
-            }
-            return true;
+            if (!sphere_definite_miss(ldg_rec<1>(sc.spheres32 + ref_index(r0)), pre)) return false;
+            return cnt == 1u || sphere_definite_miss(ldg_rec<1>(sc.spheres32 + ref_index(r1)), pre);
         } else {
             return false;
         }

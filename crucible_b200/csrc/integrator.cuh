@@ -1007,8 +1007,8 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
     const bool animated = s.anim_keys != nullptr;  // object keyframes: the builds that evaluate timelines at the ray time
     // Static scenes with a search tree run the order-free engine (fast_trace.cuh); the rays it hands back are traced by
     // the reference-order kernel in a second, small launch.  CR_RENDER_REFERENCE_ORDER keeps reference order throughout.
-    const bool fast = use_fast_engine(s, (opts.flags & CR_RENDER_REFERENCE_ORDER) != 0u);
-    int fmb = 8;
+    const bool fast_ok = use_fast_engine(s, (opts.flags & CR_RENDER_REFERENCE_ORDER) != 0u);
+    int fmb = 6;  // 80 registers, no spills, 6 CTAs x 24.5 KB of lane tables + stacks per SM
     if (const char* e = getenv("CRB_FAST_MINB")) fmb = atoi(e);
     auto fast_fn = fmb <= 6 ? k_trace_fast<R, 6> : (fmb <= 8 ? k_trace_fast<R, 8> : k_trace_fast<R, 10>);
     const int g_fast = persistent_grid(fast_fn, TRACE_BLOCK, s.num_sms);
@@ -1016,14 +1016,35 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
                                  animated ? k_trace<R, CRB_REFILL, 8, true> : k_trace<R, CRB_REFILL, 10, false>};
     const int trace_grids[2] = {persistent_grid(trace_variants[0], TRACE_BLOCK, s.num_sms),
                                 persistent_grid(trace_variants[1], TRACE_BLOCK, s.num_sms)};
-    const uint64_t signature = scene_signature(s, sizeof(R) == 8 ? 0 : 1);
+    // Three ways to trace a wavefront, all with the reference's results: the reference-order kernel at two register budgets
+    // (0: 64 registers, 1: 48 registers / more warps) and the order-free engine (2).  Which is fastest depends on the scene
+    // (meshes: the order-free engine by 1.3-2.6x; a few hundred spheres or 18 quads: reference order), so the first mixed
+    // wavefront of a scene is traced with every candidate (same rays, same result, k_trace_rewind between) and the
+    // fastest kept; the choice is cached per device by scene signature.  CRB_TRAVERSAL / CRB_MINB pin a candidate.
+    const uint64_t signature = scene_signature(s, (sizeof(R) == 8 ? 0 : 1) | (fast_ok ? 2 : 0));
     int variant = ws.lookup_variant(signature);
     if (const char* e = getenv("CRB_MINB")) variant = atoi(e) <= 8 ? 0 : 1;
+    if (const char* e = getenv("CRB_TRAVERSAL")) {
+        if (e[0] == 'f' && fast_ok) variant = 2;
+    }
+    if (variant == 2 && !fast_ok) variant = -1;
+    int cands[3], n_cands = 0;
+    cands[n_cands++] = 0;
+    if (!animated) cands[n_cands++] = 1;
+    if (fast_ok) cands[n_cands++] = 2;
     const uint64_t tune_at = total >= 2ull * pool ? 1 : 0;  // the second wavefront mixes bounce rays with camera rays
-    bool tuning = variant < 0 && total >= (1ull << 20) && !animated && !fast;
-    if (variant < 0) variant = 1;
-    TraceFn trace_fn = trace_variants[variant];
-    int g_trace = trace_grids[variant];
+    bool tuning = variant < 0 && total >= (1ull << 20) && n_cands > 1;
+    if (variant < 0) variant = fast_ok ? 2 : (animated ? 0 : 1);
+    auto launch_trace = [&](int v, int cur) {
+        if (v == 2) {
+            fast_fn<<<g_fast, TRACE_BLOCK, 0, stream>>>(sc, paths[cur], ctl, cur, queues, filt[cur], pool, retry_list);
+            // the rays it could not decide, in reference order (usually none: the launch returns at once)
+            trace_variants[0]<<<s.num_sms * 2, TRACE_BLOCK, 0, stream>>>(sc, paths[cur], ctl, cur, queues, filt[cur], pool, retry_list);
+            return 2;
+        }
+        trace_variants[v]<<<trace_grids[v], TRACE_BLOCK, 0, stream>>>(sc, paths[cur], ctl, cur, queues, filt[cur], pool, nullptr);
+        return 1;
+    };
     int smb = 6;
     if (const char* e = getenv("CRB_SHADE_MINB")) smb = atoi(e);
     typedef void (*GenFn)(const Control*, const DevCamera*, const RaygenParams<R>, PathRec<R>*, FilterRec*);
@@ -1080,33 +1101,30 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
     while (!done) {
         const int cur = (int)(it & 1), nxt = cur ^ 1;
         if (tuning && it == tune_at) {
-            cudaEvent_t te[4];
+            cudaEvent_t te[6];
             for (auto& e : te) CRB_CUDA(events.make(&e));
-            for (int v = 0; v < 2; ++v) {
-                CRB_CUDA(cudaEventRecord(te[2 * v], stream));
-                trace_variants[v]<<<trace_grids[v], TRACE_BLOCK, 0, stream>>>(sc, paths[cur], ctl, cur, queues, filt[cur], pool, nullptr);
-                CRB_CUDA(cudaEventRecord(te[2 * v + 1], stream));
-                if (v == 0) k_trace_rewind<<<1, 32, 0, stream>>>(ctl);
+            for (int c = 0; c < n_cands; ++c) {
+                CRB_CUDA(cudaEventRecord(te[2 * c], stream));
+                launches += launch_trace(cands[c], cur);
+                CRB_CUDA(cudaEventRecord(te[2 * c + 1], stream));
+                if (c + 1 < n_cands) k_trace_rewind<<<1, 32, 0, stream>>>(ctl);
             }
-            launches += 2;
-            CRB_CUDA(cudaEventSynchronize(te[3]));
-            float ms[2] = {0.f, 0.f};
-            cudaEventElapsedTime(&ms[0], te[0], te[1]);
-            cudaEventElapsedTime(&ms[1], te[2], te[3]);
-            variant = ms[1] <= ms[0] ? 1 : 0;
+            CRB_CUDA(cudaEventSynchronize(te[2 * n_cands - 1]));
+            float best_ms = 0.f;
+            for (int c = 0; c < n_cands; ++c) {
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, te[2 * c], te[2 * c + 1]);
+                if (c == 0 || ms < best_ms) {
+                    best_ms = ms;
+                    variant = cands[c];
+                }
+            }
             ws.store_variant(signature, variant);
-            trace_fn = trace_variants[variant];
-            g_trace = trace_grids[variant];
             tuning = false;
+            launches += n_cands - 2;  // the rewinds; one trace launch is part of the five counted below
         } else {
             tm.begin(0, a);
-            if (fast) {
-                fast_fn<<<g_fast, TRACE_BLOCK, 0, stream>>>(sc, paths[cur], ctl, cur, queues, filt[cur], pool, retry_list);
-                trace_variants[0]<<<s.num_sms * 2, TRACE_BLOCK, 0, stream>>>(sc, paths[cur], ctl, cur, queues, filt[cur], pool, retry_list);
-                ++launches;
-            } else {
-                trace_fn<<<g_trace, TRACE_BLOCK, 0, stream>>>(sc, paths[cur], ctl, cur, queues, filt[cur], pool, nullptr);
-            }
+            launches += launch_trace(variant, cur) - 1;
             tm.end(0, a);
         }
         tm.begin(1, a);

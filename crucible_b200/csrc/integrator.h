@@ -87,6 +87,10 @@ template <typename R>
 int trace_batch_impl(const SceneDeviceData&, const double* d_rays, size_t n, double tmin, double tmax, CrHit* d_out,
                      uint32_t* d_cursor, uint32_t* d_retry, int reference_order, uint32_t* h_retried, cudaStream_t, std::string& err);
 
+// Device build of the order-free engine's search tree for large scenes (search_tree.cu)
+int gpu_build_search_tree(const SceneDeviceData& d, cudaStream_t stream, uint32_t n_visible, void** d_fast_nodes, void** d_fast_prims,
+                          uint32_t* depth, std::string& err);
+
 // FMA micro-benchmarks (roofline denominators); defined in integrator_f32.cu
 int measure_fma_peak(int num_sms, double* fp64_tflops, double* fp32_tflops, std::string& err);
 
