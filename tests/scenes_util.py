@@ -103,3 +103,16 @@ def compare_hits(got, exp, rtol=1e-5, exact_t=True):
     # u, v go through acos/atan2 (libm vs CUDA: a few ulp)
     assert np.all(np.abs(got["u"][hit] - exp["u"][hit]) <= rtol)
     assert np.all(np.abs(got["v"][hit] - exp["v"][hit]) <= rtol)
+
+
+def compare_both_engines(gs, exp, rays, tmin=0.001, tmax=float("inf"), max_retried=None):
+    """The same batch through the order-free engine (default) and through the reference-order kernel
+    (CR_TRACE_REFERENCE_ORDER): both must reproduce the oracle's records.  Returns (hits of the default engine, number of
+    rays the order-free engine handed back to the reference-order kernel)."""
+    got = gs.trace_batch(rays, tmin, tmax)
+    retried = gs.last_retried()
+    compare_hits(got, exp)
+    compare_hits(gs.trace_batch(rays, tmin, tmax, reference_order=True), exp)
+    if max_retried is not None:
+        assert retried <= max_retried, f"{retried} rays went back to the reference-order kernel"
+    return got, retried

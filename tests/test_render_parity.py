@@ -43,6 +43,10 @@ def test_f64_render_matches_oracle_path_by_path(gpu_device, oracle, name, kw):
     ref, ref8, ost = orc.render(cam, seed=3)
     assert st["rays"] == ost["rays"], "the GPU traced a different number of ray segments than the reference recursion"
     assert st["samples"] == ost["samples"]
+    # the order-free engine traced this render (small renders are not tuned); reference order gives the same image bit for bit
+    rgb_ro, rgb8_ro, st_ro = gs.render(cam, seed=3, reference_order=True)
+    assert np.array_equal(rgb_ro, rgb) and np.array_equal(rgb8_ro, rgb8) and st_ro["rays"] == st["rays"] and st_ro["retried_rays"] == 0
+    assert st["retried_rays"] <= st["rays"] // 10000
     if name == "teapot":
         # the spherical sky goes through atan2/asin (CUDA vs glibc, few ulp): a texel can flip on a boundary
         bad = np.abs(rgb - ref).max(axis=2) > TOL_F64
