@@ -106,8 +106,10 @@ struct FastTrav {
     float margin;
     uint32_t cur;    // inner node index, or the parked leaf word (FS_LEAF)
     int sp;
-    uint32_t deep_ref[FAST_STACK - FAST_SMEM_LEVELS];  // stack levels beyond the shared-memory part
-    float deep_lo[FAST_STACK - FAST_SMEM_LEVELS];
+    // stack levels beyond the shared-memory part: two thread-local arrays OUTSIDE this struct (a dynamically indexed member
+    // would force the whole struct, hot ray constants included, into local memory: 7 LDL per inner step, measured)
+    uint32_t* deep_ref;
+    float* deep_lo;
     __device__ __forceinline__ void push(uint32_t ref, float lo) {
         if (sp < FAST_SMEM_LEVELS) {
             s->stk_ref[sp][threadIdx.x] = ref;
@@ -257,8 +259,12 @@ __device__ __forceinline__ void fast_trace_persistent(const DevScene<R>& sc, R t
     const uint32_t n = io.count();
     const int lane = threadIdx.x & 31;
     const float tmin32 = (float)tmin;
+    uint32_t deep_ref[FAST_STACK - FAST_SMEM_LEVELS];
+    float deep_lo[FAST_STACK - FAST_SMEM_LEVELS];
     FastTrav<R, BLOCK> tv;
     tv.s = slots;
+    tv.deep_ref = deep_ref;
+    tv.deep_lo = deep_lo;
     tv.cur = 0u;
     tv.sp = 0;
     tv.best_m = 0.f;

@@ -1008,9 +1008,11 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
     // Static scenes with a search tree run the order-free engine (fast_trace.cuh); the rays it hands back are traced by
     // the reference-order kernel in a second, small launch.  CR_RENDER_REFERENCE_ORDER keeps reference order throughout.
     const bool fast_ok = use_fast_engine(s, (opts.flags & CR_RENDER_REFERENCE_ORDER) != 0u);
-    int fmb = 6;  // 80 registers, no spills, 6 CTAs x 24.5 KB of lane tables + stacks per SM
+    // f64: 96 registers and NO spills (5 CTAs = 20 warps per SM) beats every higher-occupancy build that spills (measured 4-10 %);
+    // f32: no build spills, the 8-CTA one (63 registers) has the most warps
+    int fmb = sizeof(R) == 8 ? 5 : 8;
     if (const char* e = getenv("CRB_FAST_MINB")) fmb = atoi(e);
-    auto fast_fn = fmb <= 6 ? k_trace_fast<R, 6> : (fmb <= 8 ? k_trace_fast<R, 8> : k_trace_fast<R, 10>);
+    auto fast_fn = fmb <= 3 ? k_trace_fast<R, 3> : fmb <= 4 ? k_trace_fast<R, 4> : fmb <= 5 ? k_trace_fast<R, 5> : fmb <= 6 ? k_trace_fast<R, 6> : fmb <= 7 ? k_trace_fast<R, 7> : k_trace_fast<R, 8>;
     const int g_fast = persistent_grid(fast_fn, TRACE_BLOCK, s.num_sms);
     TraceFn trace_variants[2] = {animated ? k_trace<R, CRB_REFILL, 8, true> : k_trace<R, CRB_REFILL, 8, false>,
                                  animated ? k_trace<R, CRB_REFILL, 8, true> : k_trace<R, CRB_REFILL, 10, false>};
