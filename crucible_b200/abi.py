@@ -18,7 +18,7 @@ CR_PRIM_SPHERE, CR_PRIM_TRIANGLE, CR_PRIM_QUAD = 0, 1, 2
 CR_NERP, CR_LERP = 0, 1
 CR_PRECISION_F64, CR_PRECISION_F32 = 0, 1
 CR_MAX_CAM_KEYS = 32
-CR_PPM_P3, CR_PPM_P6 = 0, 1
+CR_PPM_P3, CR_PPM_P6, CR_PNG = 0, 1, 2
 CR_BVH_AUTO, CR_BVH_HOST, CR_BVH_DEVICE = 0, 1, 2
 CR_RENDER_GLOBAL_ROWS = 1
 CR_RENDER_REFERENCE_ORDER = 2
@@ -127,6 +127,8 @@ SIGNATURES = {
     "cr_shared_buffer_open": (C.c_int, [C.c_int, _P, C.POINTER(C.c_void_p)]),
     "cr_shared_buffer_close": (C.c_int, [C.c_int, _P, C.c_int]),
     "cr_write_ppm": (C.c_int, [C.c_char_p, _P, C.c_uint32, C.c_uint32, C.c_int]),
+    "cr_scene_save": (C.c_int, [_P, C.c_char_p]),
+    "cr_scene_load": (_P, [C.c_char_p, C.c_int]),
     "cr_render_to_file": (C.c_int, [_P, C.POINTER(CrCamera), C.POINTER(CrRenderOpts), C.c_char_p, C.c_int, C.POINTER(CrStats)]),
     "cr_render_frames": (C.c_int, [_P, C.POINTER(CrCamera), C.POINTER(CrRenderOpts), C.c_uint32, C.c_uint32, C.c_uint32, C.c_char_p,
                                    C.c_uint32, C.c_int, _P]),

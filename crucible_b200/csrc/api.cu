@@ -15,6 +15,8 @@
 #include <thread>
 #include <vector>
 
+#include <zlib.h>
+
 #include "bvh_host.h"
 #include "fast_tree.h"
 #include "integrator.h"
@@ -1200,6 +1202,174 @@ int cr_render(CrScene* s, const CrCamera* cam, const CrRenderOpts* opts, double*
     return CR_OK;
 }
 
+// ---- scene export file: "CRSCENE1", then counted little-endian sections of the staging arrays ----------
+extern "C++" {
+namespace {
+struct FileWriter {
+    FILE* f;
+    bool ok = true;
+    void raw(const void* p, size_t n) { ok = ok && (n == 0 || fwrite(p, 1, n, f) == n); }
+    void u64(uint64_t v) { raw(&v, 8); }
+    template <typename T>
+    void vec(const std::vector<T>& v) {
+        u64(v.size());
+        raw(v.data(), v.size() * sizeof(T));
+    }
+};
+struct FileReader {
+    FILE* f;
+    bool ok = true;
+    void raw(void* p, size_t n) { ok = ok && (n == 0 || fread(p, 1, n, f) == n); }
+    uint64_t u64() {
+        uint64_t v = 0;
+        raw(&v, 8);
+        return v;
+    }
+    template <typename T>
+    void vec(std::vector<T>& v, uint64_t limit) {
+        const uint64_t n = u64();
+        if (!ok || n > limit) {
+            ok = false;
+            return;
+        }
+        v.resize((size_t)n);
+        raw(v.data(), (size_t)n * sizeof(T));
+    }
+};
+struct SavedElement {  // Element without the box (recomputed on load with the reference's arithmetic)
+    uint32_t kind, idx, hide, pad;
+};
+}  // namespace
+}  // extern "C++"
+
+extern "C" int cr_scene_save(const CrScene* s, const char* path) {
+    if (!s || !path) return fail(CR_ERR_INVALID, "null argument");
+    FILE* f = fopen(path, "wb");
+    if (!f) return fail(CR_ERR_INVALID, std::string("cannot open ") + path);
+    FileWriter w{f};
+    w.raw("CRSCENE1", 8);
+    std::vector<SavedElement> el(s->elements.size());
+    for (size_t i = 0; i < el.size(); ++i) el[i] = {s->elements[i].kind, s->elements[i].idx, s->elements[i].hide ? 1u : 0u, 0u};
+    w.vec(el);
+    w.vec(s->spheres);
+    w.vec(s->tris);
+    w.vec(s->quads);
+    for (int k = 0; k < 3; ++k) {
+        w.vec(s->mat_of[k]);
+        w.vec(s->obj_of[k]);
+    }
+    w.vec(s->mats);
+    w.vec(s->texs);
+    w.u64(s->images.size());
+    for (const HostImage& im : s->images) {
+        w.u64((uint64_t)im.w);
+        w.u64((uint64_t)im.h);
+        w.vec(im.rgb);
+    }
+    w.u64((uint64_t)(int64_t)s->sky_kind);
+    w.u64((uint64_t)(int64_t)s->sky_image);
+    w.u64((uint64_t)s->bvh_builder);
+    w.u64(s->anim.size());
+    for (const auto& kv : s->anim) {
+        w.u64(kv.first);
+        w.vec(kv.second);
+    }
+    const bool ok = (fclose(f) == 0) && w.ok;
+    return ok ? CR_OK : fail(CR_ERR_INVALID, std::string("write failed: ") + path);
+}
+
+extern "C" CrScene* cr_scene_load(const char* path, int device) {
+    if (!path) {
+        g_err = "cr_scene_load: null path";
+        return nullptr;
+    }
+    FILE* f = fopen(path, "rb");
+    if (!f) {
+        g_err = std::string("cr_scene_load: cannot open ") + path;
+        return nullptr;
+    }
+    CrScene* s = cr_scene_create(device);
+    if (!s) {
+        fclose(f);
+        return nullptr;
+    }
+    FileReader r{f};
+    char magic[8] = {0};
+    r.raw(magic, 8);
+    const uint64_t LIM = (uint64_t)REF_MAX_INDEX * 9;
+    std::vector<SavedElement> el;
+    if (r.ok && memcmp(magic, "CRSCENE1", 8) == 0) {
+        r.vec(el, REF_MAX_INDEX);
+        r.vec(s->spheres, LIM);
+        r.vec(s->tris, LIM);
+        r.vec(s->quads, LIM);
+        for (int k = 0; k < 3; ++k) {
+            r.vec(s->mat_of[k], REF_MAX_INDEX);
+            r.vec(s->obj_of[k], REF_MAX_INDEX);
+        }
+        r.vec(s->mats, 1u << 24);
+        r.vec(s->texs, 1u << 24);
+        const uint64_t n_img = r.u64();
+        for (uint64_t i = 0; r.ok && i < n_img && i < (1u << 20); ++i) {
+            HostImage im;
+            im.w = (int)r.u64();
+            im.h = (int)r.u64();
+            r.vec(im.rgb, 1ull << 34);
+            if (r.ok && (im.w <= 0 || im.h <= 0 || im.rgb.size() != (size_t)im.w * im.h * 3)) r.ok = false;
+            s->images.push_back(std::move(im));
+        }
+        s->sky_kind = (int)(int64_t)r.u64();
+        s->sky_image = (int)(int64_t)r.u64();
+        s->bvh_builder = (int)r.u64();
+        const uint64_t n_anim = r.u64();
+        for (uint64_t i = 0; r.ok && i < n_anim && i < LIM; ++i) {
+            const uint64_t key = r.u64();
+            r.vec(s->anim[key], 1u << 20);
+        }
+    } else {
+        r.ok = false;
+    }
+    fclose(f);
+    // consistency of what was read, then the per-primitive tables the add calls would have built
+    const size_t n_of[3] = {s->spheres.size() / 4, s->tris.size() / 9, s->quads.size() / 9};
+    bool ok = r.ok && s->spheres.size() % 4 == 0 && s->tris.size() % 9 == 0 && s->quads.size() % 9 == 0 &&
+              el.size() == n_of[0] + n_of[1] + n_of[2] && s->bvh_builder >= CR_BVH_AUTO && s->bvh_builder <= CR_BVH_DEVICE;
+    for (int k = 0; ok && k < 3; ++k) ok = s->mat_of[k].size() == n_of[k] && s->obj_of[k].size() == n_of[k];
+    if (ok) {
+        for (int k = 0; k < 3; ++k) s->prim_of[k].assign(n_of[k], -1);
+        s->elements.resize(el.size());
+        for (size_t i = 0; ok && i < el.size(); ++i) {
+            const SavedElement& e = el[i];
+            if (e.kind > CR_PRIM_QUAD || e.idx >= n_of[e.kind] || s->prim_of[e.kind][e.idx] != -1) {
+                ok = false;
+                break;
+            }
+            const std::vector<double>& store = e.kind == CR_PRIM_SPHERE ? s->spheres : (e.kind == CR_PRIM_TRIANGLE ? s->tris : s->quads);
+            const size_t stride = e.kind == CR_PRIM_SPHERE ? 4 : 9;
+            for (size_t c = 0; c < stride; ++c)
+                if (!std::isfinite(store[stride * e.idx + c])) ok = false;
+            Element& dst = s->elements[i];
+            dst.kind = e.kind;
+            dst.idx = e.idx;
+            dst.hide = e.hide != 0;
+            dst.box = prim_box(e.kind, &store[stride * e.idx]);
+            s->prim_of[e.kind][e.idx] = (int32_t)i;
+        }
+    }
+    if (!ok) {
+        cr_scene_destroy(s);
+        g_err = std::string("cr_scene_load: ") + path + " is not a valid scene file";
+        return nullptr;
+    }
+    if (cr_scene_commit(s) != CR_OK) {
+        const std::string keep = g_err;
+        cr_scene_destroy(s);
+        g_err = keep;
+        return nullptr;
+    }
+    return s;
+}
+
 // ---- multi-GPU behind the boundary (SURVEY 8b cr_init(devices, n), 8e) -------------------------------------------
 extern "C" CrScene* cr_scene_replicate(const CrScene* src, int device) {
     if (!src) {
@@ -1434,9 +1604,86 @@ void format_p3_rows(const uint8_t* rgb8, size_t p0, size_t p1, std::string& out)
     out.resize((size_t)(w - &out[0]));
 }
 
+// EXTENSION: 8-bit RGB PNG.  Rows with filter type 0, split into bands that host threads deflate
+// independently (zlib level 1; every band but the last ends with a sync flush, so the concatenation is one valid zlib
+// stream: header from the first band, Adler-32 of the whole image appended), chunks IHDR / IDAT / IEND with CRC-32.
+void png_chunk(std::vector<uint8_t>& out, const char type[4], const uint8_t* data, size_t n) {
+    auto be32 = [&](uint32_t v) {
+        out.push_back((uint8_t)(v >> 24)); out.push_back((uint8_t)(v >> 16)); out.push_back((uint8_t)(v >> 8)); out.push_back((uint8_t)v);
+    };
+    be32((uint32_t)n);
+    const size_t at = out.size();
+    out.insert(out.end(), type, type + 4);
+    if (n) out.insert(out.end(), data, data + n);
+    be32((uint32_t)crc32(0L, out.data() + at, (uInt)(n + 4)));
+}
+int write_png_file(const char* path, const uint8_t* rgb8, uint32_t w, uint32_t h) {
+    if (w == 0 || h == 0) return fail(CR_ERR_INVALID, "empty image");
+    const size_t stride = (size_t)w * 3;
+    unsigned nt = std::thread::hardware_concurrency();
+    nt = nt == 0 ? 1 : (nt > 8 ? 8 : nt);
+    if ((size_t)w * h < 65536 || h < nt) nt = 1;
+    std::vector<std::vector<uint8_t>> band(nt);
+    std::vector<int> rc(nt, Z_OK);
+    std::vector<uLong> adler(nt, 1), band_len(nt, 0);
+    auto work = [&](unsigned t) {
+        const uint32_t r0 = (uint32_t)((uint64_t)h * t / nt), r1 = (uint32_t)((uint64_t)h * (t + 1) / nt);
+        std::vector<uint8_t> raw((size_t)(r1 - r0) * (stride + 1));
+        for (uint32_t r = r0; r < r1; ++r) {
+            uint8_t* dst = raw.data() + (size_t)(r - r0) * (stride + 1);
+            dst[0] = 0;  // filter type 0 (None)
+            memcpy(dst + 1, rgb8 + (size_t)r * stride, stride);
+        }
+        adler[t] = adler32(1L, raw.data(), (uInt)raw.size());
+        band_len[t] = (uLong)raw.size();
+        z_stream zs;
+        memset(&zs, 0, sizeof(zs));
+        if (deflateInit2(&zs, 1, Z_DEFLATED, t == 0 ? 15 : -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) {  // band 0 carries the zlib header
+            rc[t] = Z_MEM_ERROR;
+            return;
+        }
+        band[t].resize(deflateBound(&zs, (uLong)raw.size()) + 64);
+        zs.next_in = raw.data();
+        zs.avail_in = (uInt)raw.size();
+        zs.next_out = band[t].data();
+        zs.avail_out = (uInt)band[t].size();
+        const int r = deflate(&zs, t + 1 == nt ? Z_FINISH : Z_FULL_FLUSH);
+        if (r != (t + 1 == nt ? Z_STREAM_END : Z_OK)) rc[t] = Z_BUF_ERROR;
+        size_t produced = band[t].size() - zs.avail_out;
+        if (t == 0 && nt == 1 && produced >= 4) produced -= 4;  // single band: zlib appended its own Adler-32; ours follows below
+        band[t].resize(produced);
+        deflateEnd(&zs);
+    };
+    {
+        std::vector<std::thread> th;
+        for (unsigned t = 1; t < nt; ++t) th.emplace_back(work, t);
+        work(0);
+        for (auto& x : th) x.join();
+    }
+    for (unsigned t = 0; t < nt; ++t)
+        if (rc[t] != Z_OK) return fail(CR_ERR_INVALID, "PNG: deflate failed");
+    uLong ad = adler[0];
+    for (unsigned t = 1; t < nt; ++t) ad = adler32_combine(ad, adler[t], (z_off_t)band_len[t]);
+    std::vector<uint8_t> idat;
+    for (unsigned t = 0; t < nt; ++t) idat.insert(idat.end(), band[t].begin(), band[t].end());
+    idat.push_back((uint8_t)(ad >> 24)); idat.push_back((uint8_t)(ad >> 16)); idat.push_back((uint8_t)(ad >> 8)); idat.push_back((uint8_t)ad);
+    std::vector<uint8_t> out = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A};
+    uint8_t ihdr[13] = {(uint8_t)(w >> 24), (uint8_t)(w >> 16), (uint8_t)(w >> 8), (uint8_t)w, (uint8_t)(h >> 24), (uint8_t)(h >> 16), (uint8_t)(h >> 8), (uint8_t)h,
+                        8, 2, 0, 0, 0};  // 8 bits per sample, colour type 2 (RGB), deflate, adaptive filtering, no interlace
+    png_chunk(out, "IHDR", ihdr, 13);
+    png_chunk(out, "IDAT", idat.data(), idat.size());
+    png_chunk(out, "IEND", nullptr, 0);
+    FILE* f = fopen(path, "wb");
+    if (!f) return fail(CR_ERR_INVALID, std::string("cannot open ") + path);
+    bool ok = fwrite(out.data(), 1, out.size(), f) == out.size();
+    ok = (fclose(f) == 0) && ok;
+    return ok ? CR_OK : fail(CR_ERR_INVALID, std::string("write failed: ") + path);
+}
+
 int write_ppm_file(const char* path, const uint8_t* rgb8, uint32_t w, uint32_t h, int format) {
     if (!path || (!rgb8 && w && h)) return fail(CR_ERR_INVALID, "null argument");
-    if (format != CR_PPM_P3 && format != CR_PPM_P6) return fail(CR_ERR_INVALID, "bad image format");
+    if (format != CR_PPM_P3 && format != CR_PPM_P6 && format != CR_PNG) return fail(CR_ERR_INVALID, "bad image format");
+    if (format == CR_PNG) return write_png_file(path, rgb8, w, h);
     FILE* f = fopen(path, "wb");  // create or truncate, camera/mod.rs:275-280
     if (!f) return fail(CR_ERR_INVALID, std::string("cannot open ") + path);
     const size_t npix = (size_t)w * h;
@@ -1469,7 +1716,7 @@ extern "C" int cr_write_ppm(const char* path, const uint8_t* rgb8, uint32_t w, u
 
 extern "C" int cr_render_to_file(CrScene* s, const CrCamera* cam, const CrRenderOpts* opts, const char* path, int format, CrStats* stats) {
     if (!path) return fail(CR_ERR_INVALID, "null path");
-    if (format != CR_PPM_P3 && format != CR_PPM_P6) return fail(CR_ERR_INVALID, "bad image format");
+    if (format != CR_PPM_P3 && format != CR_PPM_P6 && format != CR_PNG) return fail(CR_ERR_INVALID, "bad image format");
     if (opts && opts->row_world > 1) return fail(CR_ERR_INVALID, "cr_render_to_file renders whole images (row_world <= 1)");
     int rc = check_camera(cam);
     if (rc != CR_OK) return rc;
@@ -1487,7 +1734,7 @@ extern "C" int cr_render_frames(CrScene* s, const CrCamera* cam, const CrRenderO
     if (!opts || !dir) return fail(CR_ERR_INVALID, "null argument");
     if (stride == 0) return fail(CR_ERR_INVALID, "stride must be positive");
     if (opts->row_world > 1) return fail(CR_ERR_INVALID, "cr_render_frames shards whole frames (row_world <= 1)");
-    if (format != CR_PPM_P3 && format != CR_PPM_P6) return fail(CR_ERR_INVALID, "bad image format");
+    if (format != CR_PPM_P3 && format != CR_PPM_P6 && format != CR_PNG) return fail(CR_ERR_INVALID, "bad image format");
     API_CUDA(cudaSetDevice(s->device));
     const uint32_t W = cam->image_width, H = cam->image_height;
     const size_t bytes = (size_t)W * H * 3;
@@ -1553,7 +1800,7 @@ extern "C" int cr_render_frames(CrScene* s, const CrCamera* cam, const CrRenderO
                 e = "cr_render_frames: device to host copy failed";
             } else {
                 char name[64];
-                snprintf(name, sizeof(name), "/image%0*u.ppm", (int)digits, j.frame);  // scene/mod.rs:307-308
+                snprintf(name, sizeof(name), "/image%0*u.%s", (int)digits, j.frame, format == CR_PNG ? "png" : "ppm");  // scene/mod.rs:307-308
                 r = write_ppm_file((std::string(dir) + name).c_str(), hbuf[j.buf], W, H, format);
                 if (r != CR_OK) e = g_err;  // thread-local of the writer thread
             }

@@ -35,6 +35,21 @@ class GpuScene:
             self.lib.cr_scene_destroy(self.handle)
             self.handle = None
 
+    def save(self, path):
+        """The scene export file (cr_scene_save): everything this scene was given, one binary file."""
+        abi.check(self.lib.cr_scene_save(self.handle, os.fsencode(path)))
+
+    @staticmethod
+    def load(path, device: int = 0) -> "GpuScene":
+        """A committed scene from an export file (cr_scene_load)."""
+        lib = abi.load()
+        h = lib.cr_scene_load(os.fsencode(path), device)
+        if not h:
+            raise abi.CrucibleError(abi.CR_ERR_INVALID, lib.cr_last_error().decode())
+        other = object.__new__(GpuScene)
+        other.lib, other.device, other.handle, other.desc = lib, device, h, None
+        return other
+
     def replicate(self, device: int) -> "GpuScene":
         """A committed copy of this scene on another device (cr_scene_replicate): the replicas of cr_render_multi."""
         h = self.lib.cr_scene_replicate(self.handle, device)
@@ -161,7 +176,7 @@ def rows_of_rank(height, row_block, rank, world):
 
 def write_ppm(fname, rgb8, fmt=abi.CR_PPM_P3):
     """The file tail of Camera::render (camera/mod.rs:275-311): P3 header, one "r g b" line per pixel
-    (`fmt=abi.CR_PPM_P6`: binary extension).  Formatting is done by the library (cr_write_ppm)."""
+    (`fmt=abi.CR_PPM_P6`: binary PPM, `abi.CR_PNG`: PNG — extensions).  Formatting is done by the library (cr_write_ppm)."""
     rgb8 = np.ascontiguousarray(rgb8, np.uint8)
     h, w, _ = rgb8.shape
     abi.check(abi.load().cr_write_ppm(os.fsencode(fname), rgb8.ctypes.data_as(C.c_void_p), w, h, int(fmt)))

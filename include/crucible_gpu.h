@@ -346,7 +346,8 @@ int cr_shared_buffer_close(int device, void* dptr, int owner);
 /* ---- the file-writing tail of the path ---- */
 typedef enum CrImageFormat {
     CR_PPM_P3 = 0, /* the reference's output: text PPM, camera/mod.rs:286,306-311 */
-    CR_PPM_P6 = 1  /* EXTENSION: binary PPM, same header fields, 3 bytes per pixel */
+    CR_PPM_P6 = 1, /* EXTENSION: binary PPM, same header fields, 3 bytes per pixel */
+    CR_PNG = 2     /* EXTENSION: 8-bit RGB PNG (zlib deflate, filter 0), the same bytes as the PPM */
 } CrImageFormat;
 
 /* Writes [h][w][3] bytes exactly as Camera::render does (camera/mod.rs:275-311): the file is
@@ -354,6 +355,15 @@ typedef enum CrImageFormat {
  * Formatting is table driven and split over host threads (the reference formats 2 M `Display`
  * calls through a BufWriter). */
 int cr_write_ppm(const char* path, const uint8_t* rgb8, uint32_t w, uint32_t h, int format);
+
+/* ---- scene export file ----
+ * The reference can only hand a scene to its renderer inside one process (Scene -> BVHWrapper -> Camera::render,
+ * scene/mod.rs:332-347).  cr_scene_save writes everything a CrScene was given — primitives in insertion order with their
+ * materials, ids and hidden flags, material / texture / image tables, sky, object keyframes, BVH builder choice — to one
+ * little-endian binary file ("CRSCENE1" + counted sections); cr_scene_load rebuilds and COMMITS the scene on `device`
+ * (-1 = host only).  A scene saved, loaded and rendered gives the image of the original, bit for bit. */
+int cr_scene_save(const CrScene*, const char* path);
+CrScene* cr_scene_load(const char* path, int device);
 
 /* Camera::render(&skybox, &world, fname) as a whole (camera/mod.rs:270-317): sample loop on the
  * GPU, bytes to the host, file written.  Honors row sharding only when row_world <= 1. */
