@@ -62,7 +62,8 @@ class CrRenderOpts(C.Structure):
 class CrStats(C.Structure):
     _fields_ = [("samples", C.c_uint64), ("rays", C.c_uint64), ("iterations", C.c_uint64), ("launches", C.c_uint64),
                 ("ms_total", C.c_double), ("ms_trace", C.c_double), ("ms_shade", C.c_double), ("ms_raygen", C.c_double),
-                ("ms_resolve", C.c_double), ("ms_h2d", C.c_double), ("ms_d2h", C.c_double), ("retried_rays", C.c_uint64)]
+                ("ms_resolve", C.c_double), ("ms_h2d", C.c_double), ("ms_d2h", C.c_double), ("retried_rays", C.c_uint64),
+                ("trace_engine", C.c_uint32), ("reserved", C.c_uint32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -1202,6 +1202,7 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
         stats->samples = total;
         stats->rays = fin.rays_traced;
         stats->retried_rays = (uint64_t)fin.retry_total + fin.retry_count;
+        stats->trace_engine = (uint32_t)variant;
         stats->iterations = it;
         stats->launches = launches;
         stats->ms_total = ms;
