@@ -36,7 +36,7 @@ namespace crb {
 
 enum : int { FS_IDLE = 0, FS_INNER = 1, FS_LEAF = 2, FS_DONE = 3, FS_RETRY = 4 };
 static constexpr int FAST_STACK = 64;       // the builder bounds the tree depth (FAST_MAX_DEPTH)
-static constexpr int FAST_SMEM_LEVELS = 12;  // stack levels kept in shared memory; deeper ones (rare) in local memory
+static constexpr int FAST_SMEM_LEVELS = 8;  // stack levels kept in shared memory; deeper ones (rare) in local memory
 
 // Per-CTA lane table, SoA over the lanes (conflict free), as LaneSlots of the reference-order engine, plus the bottom of
 // every lane's traversal stack: lanes of a warp sit at different stack depths, so a local-memory stack costs one L1
@@ -47,6 +47,10 @@ struct FastSlots {
     R best_t[BLOCK];
     R ray[6][BLOCK];
     float pre[7][BLOCK];
+    // the box-test constants of the lane's ray (FastRay in 9 words: o*inv, the per-axis error band, 1/d).  They are read
+    // into registers at the start of every INNER slice and are dead in the LEAF phase, so the f64 leaf arithmetic does
+    // not push them into local memory (the 64-register build used to reload 4 of them per inner step)
+    float fray[9][BLOCK];
     uint32_t best_ref[BLOCK], best_rank[BLOCK], my[BLOCK];
     uint32_t stk_ref[FAST_SMEM_LEVELS][BLOCK];
     float stk_lo[FAST_SMEM_LEVELS][BLOCK];
@@ -100,7 +104,6 @@ __device__ __forceinline__ bool ref_box_span(const NodeRec<R>& n, V3<R> o, V3<R>
 
 template <typename R, int BLOCK>
 struct FastTrav {
-    FastRay fr;
     FastSlots<R, BLOCK>* s;
     float best_m;    // (float) closest hit, rounded up, + margin
     float margin;
@@ -125,10 +128,10 @@ struct FastTrav {
         const float k23 = 1.3f * 1.1920929e-7f;  // 1.3 * 2^-23
         const float ex = fabsf(f.ix) * (bmax + fabsf(f.ox)) * k23, ey = fabsf(f.iy) * (bmax + fabsf(f.oy)) * k23,
                     ez = fabsf(f.iz) * (bmax + fabsf(f.oz)) * k23;
-        fr.on_x = f.oix + ex; fr.on_y = f.oiy + ey; fr.on_z = f.oiz + ez;
-        fr.of_x = f.oix - ex; fr.of_y = f.oiy - ey; fr.of_z = f.oiz - ez;
-        fr.ax0 = f.ax0; fr.ax1 = f.ax1; fr.ay0 = f.ay0; fr.ay1 = f.ay1; fr.az0 = f.az0; fr.az1 = f.az1;
         const int t = threadIdx.x;
+        s->fray[0][t] = f.oix; s->fray[1][t] = f.oiy; s->fray[2][t] = f.oiz;
+        s->fray[3][t] = ex; s->fray[4][t] = ey; s->fray[5][t] = ez;
+        s->fray[6][t] = f.ix; s->fray[7][t] = f.iy; s->fray[8][t] = f.iz;
         s->pre[0][t] = f.ox; s->pre[1][t] = f.oy; s->pre[2][t] = f.oz; s->pre[3][t] = f.dx; s->pre[4][t] = f.dy; s->pre[5][t] = f.dz;
         s->pre[6][t] = f.o2;
         s->best_t[t] = tmax;
@@ -151,6 +154,20 @@ struct FastTrav {
         o = {s->ray[0][t], s->ray[1][t], s->ray[2][t]};
         d = {s->ray[3][t], s->ray[4][t], s->ray[5][t]};
     }
+    // the lane's box-test constants, from the lane table (start of an INNER slice)
+    __device__ __forceinline__ FastRay load_fray() const {
+        const int t = threadIdx.x;
+        FastRay fr;
+        const float oix = s->fray[0][t], oiy = s->fray[1][t], oiz = s->fray[2][t];
+        const float ex = s->fray[3][t], ey = s->fray[4][t], ez = s->fray[5][t];
+        const float ix = s->fray[6][t], iy = s->fray[7][t], iz = s->fray[8][t];
+        fr.on_x = oix + ex; fr.on_y = oiy + ey; fr.on_z = oiz + ez;
+        fr.of_x = oix - ex; fr.of_y = oiy - ey; fr.of_z = oiz - ez;
+        fr.ax0 = fmaxf(ix, 0.f); fr.ax1 = fminf(ix, 0.f);  // FilterRay::derive
+        fr.ay0 = fmaxf(iy, 0.f); fr.ay1 = fminf(iy, 0.f);
+        fr.az0 = fmaxf(iz, 0.f); fr.az1 = fminf(iz, 0.f);
+        return fr;
+    }
     // next node from the stack (entries whose box entry lies beyond the closest hit + margin are dropped)
     __device__ __forceinline__ int pop() {
         while (sp > 0) {
@@ -164,7 +181,7 @@ struct FastTrav {
         return FS_DONE;
     }
     // INNER step: both child boxes from one 64 B record, nearer child first
-    __device__ __forceinline__ int step_inner(const DevScene<R>& sc, float tmin) {
+    __device__ __forceinline__ int step_inner(const DevScene<R>& sc, const FastRay& fr, float tmin) {
         const NodeRec<float>* half = reinterpret_cast<const NodeRec<float>*>(sc.fast_nodes + cur);
         const NodeRec<float> a = ldg_node32(half), b = ldg_node32(half + 1);
         float la, lb;
@@ -288,7 +305,7 @@ __device__ __forceinline__ void fast_trace_persistent(const DevScene<R>& sc, R t
                 }
                 io.commit(st == FS_DONE, my, bref, bt, o, d, R(0));
                 const uint32_t pos = fast_warp_append(retry_count, st == FS_RETRY);
-                if (st == FS_RETRY) retry_list[pos] = my;
+                if (st == FS_RETRY) retry_list[pos] = io.item(my);
             }
             if (st == FS_DONE || st == FS_RETRY) st = FS_IDLE;
             if (!exhausted) {
@@ -315,13 +332,16 @@ __device__ __forceinline__ void fast_trace_persistent(const DevScene<R>& sc, R t
             }
             if (__ballot_sync(0xffffffffu, st != FS_IDLE) == 0u) break;
         }
+        if (__any_sync(0xffffffffu, st == FS_INNER)) {
+            const FastRay fr = tv.load_fray();
 #pragma unroll 1
-        for (int k = 0; k < NODE_SLICE; k += 4) {
+            for (int k = 0; k < NODE_SLICE; k += 4) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (st == FS_INNER) st = tv.step_inner(sc, tmin32);
+                for (int u = 0; u < 4; ++u) {
+                    if (st == FS_INNER) st = tv.step_inner(sc, fr, tmin32);
+                }
+                if (__popc(__ballot_sync(0xffffffffu, st == FS_INNER)) < sc.min_node_lanes) break;
             }
-            if (__popc(__ballot_sync(0xffffffffu, st == FS_INNER)) < sc.min_node_lanes) break;
         }
         if (st == FS_LEAF && tv.leaf_certain_miss(sc)) st = tv.pop();
         if (__any_sync(0xffffffffu, st == FS_LEAF)) {

@@ -351,25 +351,26 @@ struct RenderTraceIO {
     __device__ __forceinline__ uint32_t count() const { return n; }
     __device__ __forceinline__ uint32_t* cursor() const { return cur; }
     __device__ __forceinline__ uint32_t path_of(uint32_t k) const { return remap ? remap[k] : k; }
+    __device__ __forceinline__ uint32_t item(uint32_t k) const { return path_of(k); }  // what the retry list holds
     __device__ __forceinline__ FilterRay filter(uint32_t k, R, R) const {  // written by the ray's producer
         FilterRec r;
         const int4* s = reinterpret_cast<const int4*>(filt + path_of(k));
         int4* d = reinterpret_cast<int4*>(&r);
-        d[0] = s[0]; d[1] = s[1]; d[2] = s[2];
+        d[0] = __ldcs(s); d[1] = __ldcs(s + 1); d[2] = __ldcs(s + 2);  // streamed once: keep the L1 for the scene
         return unpack_filter(r);
     }
     __device__ __forceinline__ void load(uint32_t k, V3<R>& o, V3<R>& d) const {
         const PathRec<R>* p = paths + path_of(k);  // sectors A and B of the record: origin + direction
         if constexpr (sizeof(R) == 8) {
-            const double2 a = *reinterpret_cast<const double2*>(&p->ox);
-            const double b = p->oz;
-            const double2 c = *reinterpret_cast<const double2*>(&p->dx);
-            const double e = p->dz;
+            const double2 a = __ldcs(reinterpret_cast<const double2*>(&p->ox));
+            const double b = __ldcs(&p->oz);
+            const double2 c = __ldcs(reinterpret_cast<const double2*>(&p->dx));
+            const double e = __ldcs(&p->dz);
             o = {a.x, a.y, b};
             d = {c.x, c.y, e};
         } else {
-            const float4 a = *reinterpret_cast<const float4*>(&p->ox);
-            const float4 b = *reinterpret_cast<const float4*>(&p->dx);
+            const float4 a = __ldcs(reinterpret_cast<const float4*>(&p->ox));
+            const float4 b = __ldcs(reinterpret_cast<const float4*>(&p->dx));
             o = {a.x, a.y, a.z};
             d = {b.x, b.y, b.z};
         }
@@ -382,8 +383,8 @@ struct RenderTraceIO {
         uint32_t i = 0;
         if (has) {
             i = path_of(k);
-            paths[i].t = t;
-            paths[i].ref = ref;
+            __stcs(&paths[i].t, t);
+            __stcs(&paths[i].ref, ref);
             if (ref == REF_MISS) {
                 q = Q_MISS;
             } else {
@@ -395,7 +396,7 @@ struct RenderTraceIO {
             }
         }
         const uint32_t pos = warp_enqueue(ctl->queue_count, q);
-        if (q >= 0) queues[(size_t)q * pool + pos] = make_uint2(i, minfo);
+        if (q >= 0) __stcs(&queues[(size_t)q * pool + pos], make_uint2(i, minfo));
     }
 };
 
@@ -666,6 +667,7 @@ struct BatchTraceIO {
     __device__ __forceinline__ uint32_t count() const { return n; }
     __device__ __forceinline__ uint32_t* cursor() const { return cur; }
     __device__ __forceinline__ uint32_t ray_of(uint32_t k) const { return remap ? remap[k] : k; }
+    __device__ __forceinline__ uint32_t item(uint32_t k) const { return ray_of(k); }
     __device__ __forceinline__ FilterRay filter(uint32_t k, R tmin, R tmax) const {
         V3<R> o, d;
         load(k, o, d);
@@ -1008,9 +1010,11 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
     // Static scenes with a search tree run the order-free engine (fast_trace.cuh); the rays it hands back are traced by
     // the reference-order kernel in a second, small launch.  CR_RENDER_REFERENCE_ORDER keeps reference order throughout.
     const bool fast_ok = use_fast_engine(s, (opts.flags & CR_RENDER_REFERENCE_ORDER) != 0u);
-    // f64: 96 registers and NO spills (5 CTAs = 20 warps per SM) beats every higher-occupancy build that spills (measured 4-10 %);
-    // f32: no build spills, the 8-CTA one (63 registers) has the most warps
-    int fmb = sizeof(R) == 8 ? 5 : 8;
+    // f64: 72 registers / 7 CTAs = 28 warps per SM.  The box-test constants of a lane live in the lane table between INNER
+    // slices (fast_trace.cuh), so this budget keeps the inner loop free of local-memory traffic; measured against the
+    // 96-register / 5-CTA build: book1 -3 %, teapot -5 %, 10 M triangles -15 % trace time.  8 CTAs (64 registers, 200 KB of
+    // lane tables, 56 KB of L1 left) lose 15 %.  f32: no build spills, the 8-CTA one (63 registers) has the most warps
+    int fmb = sizeof(R) == 8 ? 7 : 8;
     if (const char* e = getenv("CRB_FAST_MINB")) fmb = atoi(e);
     auto fast_fn = fmb <= 3 ? k_trace_fast<R, 3> : fmb <= 4 ? k_trace_fast<R, 4> : fmb <= 5 ? k_trace_fast<R, 5> : fmb <= 6 ? k_trace_fast<R, 6> : fmb <= 7 ? k_trace_fast<R, 7> : k_trace_fast<R, 8>;
     const int g_fast = persistent_grid(fast_fn, TRACE_BLOCK, s.num_sms);
@@ -1097,6 +1101,7 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
     gen_fn<<<g_gen, SHADE_BLOCK, 0, stream>>>(ctl, d_cam, rp, paths[0], filt[0]);
     tm.end(2, a);
     launches += 2;
+
     uint64_t it = 0;
     bool done = (issue == 0);
     const bool log_waves = getenv("CRB_LOG_WAVES") != nullptr;  // debug: wavefront sizes (pairs an ncu capture with its ray count)
@@ -1149,6 +1154,7 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
         gen_fn<<<g_gen, SHADE_BLOCK, 0, stream>>>(ctl, d_cam, rp, paths[nxt], filt[nxt]);
         tm.end(2, a);
         launches += 2;
+
         const int slot = (int)(it % RING);
         CRB_CUDA(cudaMemcpyAsync((void*)(h_n_in + slot), &ctl->n_in[nxt], sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
         CRB_CUDA(cudaEventRecord(ring_ev[slot], stream));
