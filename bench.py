@@ -374,7 +374,7 @@ def main():
                                 bytes_per_segment=per_seg_bytes, segments_per_launch=seg_per_launch, avg_launch_ms=dur_s * 1e3,
                                 kernel_share_of_step=ms_trace / max(my_ms, 1e-9), ms_trace=ms_trace / args.steps, ms_shade=ms_shade / args.steps,
                                 ms_raygen=ms_gen / args.steps,
-                                trace_engine={0: "reference order, 64 registers", 1: "reference order, 48 registers", 2: "order-free"}.get(stats[-1].get("trace_engine"), None) if stats else None,
+                                trace_engine={0: "reference order, 64 registers", 1: "reference order, 48 registers", 2: "order-free", 3: "order-free, search tree in shared memory"}.get(stats[-1].get("trace_engine"), None) if stats else None,
                                 retried_rays=sum(s.get("retried_rays", 0) for s in stats), fp64_fma_peak_tflops=f64p.value, fp32_fma_peak_tflops=f32p.value)
         line["roofline"]["fp_view" if cfg["bound"] == "hbm" else "hbm_view"] = other
         print(json.dumps(line), flush=True)

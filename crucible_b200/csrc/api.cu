@@ -283,6 +283,7 @@ __global__ void k_fast_fill(uint2* __restrict__ prims, uint32_t n, const uint32_
 int upload_search_tree(CrScene* s, const std::vector<uint32_t>& visible) {
     SceneDeviceData& d = s->dev;
     d.fast_nodes = d.fast_prims = nullptr;
+    d.n_fast_nodes = d.n_fast_prims = 0;
     if (visible.empty() || !s->anim.empty() || getenv("CRB_NO_SEARCH_TREE")) return CR_OK;
     // large scenes: linear BVH built on the device from the records just uploaded (search_tree.cu); small ones: binned SAH here
     bool on_device = visible.size() >= 32768;
@@ -325,6 +326,8 @@ int upload_search_tree(CrScene* s, const std::vector<uint32_t>& visible) {
     API_CUDA(cudaStreamSynchronize(s->stream));  // `ft` and `table` die with this scope
     d.fast_nodes = dn;
     d.fast_prims = dp;
+    d.n_fast_nodes = (uint32_t)ft.nodes.size();
+    d.n_fast_prims = (uint32_t)table.size();
     return CR_OK;
 }
 

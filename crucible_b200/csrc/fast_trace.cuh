@@ -102,9 +102,43 @@ __device__ __forceinline__ bool ref_box_span(const NodeRec<R>& n, V3<R> o, V3<R>
     return hi > lo;
 }
 
-template <typename R, int BLOCK>
+// Small scenes: the whole search tree (inner records, leaf-primitive table, f32 spheres of the pre-filter) is copied into
+// the CTA's shared memory once per launch (k_trace_fast_smem: ONE 896-thread CTA per SM, 176 KB of lane tables + up to
+// 50 KB of tree).  A divergent node fetch then costs shared-memory latency (~30 cycles, no tag stage) instead of an L1
+// hit (~40) or, for the third of the node loads that missed the L1 (ncu, book1), an L2 round trip.  Shared addresses are
+// 32-bit window offsets; the records are read-only after the copy, so plain (non-volatile) ld.shared is safe.
+struct SmemTree {
+    uint32_t nodes, prims, spheres32;  // shared-window byte addresses
+};
+static __device__ __forceinline__ NodeRec<float> lds_node32(uint32_t addr) {
+    NodeRec<float> n;
+    asm("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=f"(n.xmin), "=f"(n.xmax), "=f"(n.ymin), "=f"(n.ymax) : "r"(addr));
+    asm("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4+16];" : "=f"(n.zmin), "=f"(n.zmax), "=r"(n.left), "=r"(n.right) : "r"(addr));
+    return n;
+}
+static __device__ __forceinline__ uint2 lds_u2(uint32_t addr) {
+    uint2 v;
+    asm("ld.shared.v2.b32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+static __device__ __forceinline__ SphereRec<float> lds_sphere32(uint32_t addr) {
+    SphereRec<float> s;
+    asm("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=f"(s.cx), "=f"(s.cy), "=f"(s.cz), "=f"(s.r) : "r"(addr));
+    return s;
+}
+
+template <typename R, int BLOCK, bool SMEM>
 struct FastTrav {
     FastSlots<R, BLOCK>* s;
+    SmemTree tree;  // SMEM builds only
+    __device__ __forceinline__ uint2 leaf_entry(const DevScene<R>& sc, uint32_t k) const {
+        if constexpr (SMEM) return lds_u2(tree.prims + k * 8u);
+        else return __ldg(&sc.fast_prims[k]);
+    }
+    __device__ __forceinline__ SphereRec<float> sphere32(const DevScene<R>& sc, uint32_t idx) const {
+        if constexpr (SMEM) return lds_sphere32(tree.spheres32 + idx * 16u);
+        else return ldg_rec<1>(sc.spheres32 + idx);
+    }
     float best_m;    // (float) closest hit, rounded up, + margin
     float margin;
     uint32_t cur;    // inner node index, or the parked leaf word (FS_LEAF)
@@ -182,8 +216,15 @@ struct FastTrav {
     }
     // INNER step: both child boxes from one 64 B record, nearer child first
     __device__ __forceinline__ int step_inner(const DevScene<R>& sc, const FastRay& fr, float tmin) {
-        const NodeRec<float>* half = reinterpret_cast<const NodeRec<float>*>(sc.fast_nodes + cur);
-        const NodeRec<float> a = ldg_node32(half), b = ldg_node32(half + 1);
+        NodeRec<float> a, b;
+        if constexpr (SMEM) {
+            a = lds_node32(tree.nodes + cur * 64u);
+            b = lds_node32(tree.nodes + cur * 64u + 32u);
+        } else {
+            const NodeRec<float>* half = reinterpret_cast<const NodeRec<float>*>(sc.fast_nodes + cur);
+            a = ldg_node32(half);
+            b = ldg_node32(half + 1);
+        }
         float la, lb;
         const bool ha = !fast_child_fails(a, fr, tmin, best_m, la) && a.left != FAST_EMPTY;
         const bool hb = !fast_child_fails(b, fr, tmin, best_m, lb) && b.left != FAST_EMPTY;
@@ -206,12 +247,12 @@ struct FastTrav {
     __device__ __forceinline__ bool leaf_certain_miss(const DevScene<R>& sc) const {
         if constexpr (sizeof(R) == 8) {
             const uint32_t first = leaf_first(), cnt = leaf_count();
-            const uint32_t r0 = __ldg(&sc.fast_prims[first].x), r1 = cnt > 1u ? __ldg(&sc.fast_prims[first + 1u].x) : r0;
+            const uint32_t r0 = leaf_entry(sc, first).x, r1 = cnt > 1u ? leaf_entry(sc, first + 1u).x : r0;
             if (ref_kind(r0) != CR_PRIM_SPHERE || ref_kind(r1) != CR_PRIM_SPHERE) return false;  // before touching the lane table
             const int t = threadIdx.x;
             const PreRay pre = {s->pre[0][t], s->pre[1][t], s->pre[2][t], s->pre[3][t], s->pre[4][t], s->pre[5][t], s->pre[6][t]};
-            if (!sphere_definite_miss(ldg_rec<1>(sc.spheres32 + ref_index(r0)), pre)) return false;
-            return cnt == 1u || sphere_definite_miss(ldg_rec<1>(sc.spheres32 + ref_index(r1)), pre);
+            if (!sphere_definite_miss(sphere32(sc, ref_index(r0)), pre)) return false;
+            return cnt == 1u || sphere_definite_miss(sphere32(sc, ref_index(r1)), pre);
         } else {
             return false;
         }
@@ -225,7 +266,7 @@ struct FastTrav {
         uint32_t brank = s->best_rank[t], bref = REF_NONE;
         const uint32_t first = leaf_first(), cnt = leaf_count();
         for (uint32_t k = 0; k < cnt; ++k) {
-            const uint2 e = __ldg(&sc.fast_prims[first + k]);
+            const uint2 e = leaf_entry(sc, first + k);
             R c;
             if (!Trav<R, RegStore<R>, false>::test_prim(sc, e.x, o, d, a, tmin, tmax, R(0), c)) continue;
             if constexpr (sizeof(R) == 8) {
@@ -268,9 +309,9 @@ static __device__ __forceinline__ uint32_t fast_warp_append(uint32_t* counter, b
     return base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
 }
 
-template <typename R, int BLOCK, typename IO>
+template <typename R, int BLOCK, bool SMEM, typename IO>
 __device__ __forceinline__ void fast_trace_persistent(const DevScene<R>& sc, R tmin, R tmax, IO& io, FastSlots<R, BLOCK>* slots,
-                                                      uint32_t* retry_list, uint32_t* retry_count) {
+                                                      uint32_t* retry_list, uint32_t* retry_count, SmemTree tree = SmemTree{0u, 0u, 0u}) {
     const int NODE_SLICE = sc.node_slice;
     const int REFILL = sc.refill;
     const uint32_t n = io.count();
@@ -278,8 +319,9 @@ __device__ __forceinline__ void fast_trace_persistent(const DevScene<R>& sc, R t
     const float tmin32 = (float)tmin;
     uint32_t deep_ref[FAST_STACK - FAST_SMEM_LEVELS];
     float deep_lo[FAST_STACK - FAST_SMEM_LEVELS];
-    FastTrav<R, BLOCK> tv;
+    FastTrav<R, BLOCK, SMEM> tv;
     tv.s = slots;
+    tv.tree = tree;
     tv.deep_ref = deep_ref;
     tv.deep_lo = deep_lo;
     tv.cur = 0u;

@@ -419,7 +419,43 @@ __global__ void __launch_bounds__(TRACE_BLOCK, MINB) k_trace_fast(DevScene<R> sc
                                                              uint32_t pool, uint32_t* __restrict__ retry_list) {
     __shared__ FastSlots<R, TRACE_BLOCK> slots;
     RenderTraceIO<R> io{sc, paths, ctl, queues, filt, ctl->n_in[side], pool, nullptr, &ctl->trace_next};
-    fast_trace_persistent<R, TRACE_BLOCK>(sc, R(0.001), Num<R>::inf(), io, &slots, retry_list, &ctl->retry_count);
+    fast_trace_persistent<R, TRACE_BLOCK, false>(sc, R(0.001), Num<R>::inf(), io, &slots, retry_list, &ctl->retry_count);
+}
+
+// Small scenes: the same engine with the search tree in shared memory (SmemTree, fast_trace.cuh).  One CTA of 28 warps
+// per SM (the 72-register budget of the default build) so that the SM holds one copy of the tree.
+static constexpr int FAST_BIG_BLOCK = 896;
+static constexpr size_t FAST_SMEM_LIMIT = 227u * 1024u;
+template <typename R>
+static size_t fast_smem_bytes(uint32_t n_fast_nodes, uint32_t n_fast_prims, uint32_t n_spheres) {
+    auto up = [](size_t b) { return (b + 127) & ~(size_t)127; };
+    return up(sizeof(FastSlots<R, FAST_BIG_BLOCK>)) + up((size_t)n_fast_nodes * 64) + up((size_t)n_fast_prims * 8) + up((size_t)n_spheres * 16);
+}
+template <typename R>
+__global__ void __launch_bounds__(FAST_BIG_BLOCK, 1) k_trace_fast_smem(DevScene<R> sc, PathRec<R>* __restrict__ paths, Control* __restrict__ ctl,
+                                                                       int side, uint2* __restrict__ queues, const FilterRec* __restrict__ filt,
+                                                                       uint32_t pool, uint32_t* __restrict__ retry_list, uint32_t n_fast_nodes,
+                                                                       uint32_t n_fast_prims, uint32_t n_spheres) {
+    extern __shared__ __align__(128) unsigned char fast_smem[];
+    auto up = [](uint32_t b) { return (b + 127u) & ~127u; };
+    FastSlots<R, FAST_BIG_BLOCK>* slots = reinterpret_cast<FastSlots<R, FAST_BIG_BLOCK>*>(fast_smem);
+    const uint32_t o_nodes = up((uint32_t)sizeof(FastSlots<R, FAST_BIG_BLOCK>)), o_prims = o_nodes + up(n_fast_nodes * 64u),
+                   o_sph = o_prims + up(n_fast_prims * 8u);
+    {
+        int4* dn = reinterpret_cast<int4*>(fast_smem + o_nodes);
+        const int4* sn = reinterpret_cast<const int4*>(sc.fast_nodes);
+        for (uint32_t i = threadIdx.x; i < n_fast_nodes * 4u; i += blockDim.x) dn[i] = __ldg(sn + i);
+        uint2* dp = reinterpret_cast<uint2*>(fast_smem + o_prims);
+        for (uint32_t i = threadIdx.x; i < n_fast_prims; i += blockDim.x) dp[i] = __ldg(sc.fast_prims + i);
+        int4* ds = reinterpret_cast<int4*>(fast_smem + o_sph);
+        const int4* ss = reinterpret_cast<const int4*>(sc.spheres32);
+        for (uint32_t i = threadIdx.x; i < n_spheres; i += blockDim.x) ds[i] = __ldg(ss + i);
+    }
+    __syncthreads();
+    const uint32_t base = (uint32_t)__cvta_generic_to_shared(fast_smem);
+    RenderTraceIO<R> io{sc, paths, ctl, queues, filt, ctl->n_in[side], pool, nullptr, &ctl->trace_next};
+    fast_trace_persistent<R, FAST_BIG_BLOCK, true>(sc, R(0.001), Num<R>::inf(), io, slots, retry_list, &ctl->retry_count,
+                                                   SmemTree{base + o_nodes, base + o_prims, base + o_sph});
 }
 
 // fixed-point accumulation: order independent => bit-reproducible for any schedule and GPU count
@@ -714,7 +750,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK) k_trace_batch_fast(DevScene<R> sc
                                                                    uint32_t* __restrict__ retry_list) {
     __shared__ FastSlots<R, TRACE_BLOCK> slots;
     BatchTraceIO<R, false> io{sc, rays, out, cursor, n, nullptr};
-    fast_trace_persistent<R, TRACE_BLOCK>(sc, (R)tmin, (R)tmax, io, &slots, retry_list, cursor + 1);
+    fast_trace_persistent<R, TRACE_BLOCK, false>(sc, (R)tmin, (R)tmax, io, &slots, retry_list, cursor + 1);
 }
 
 // ---- host side: typed view of the scene + wavefront driver -----------------------------------------
@@ -1034,14 +1070,33 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
         if (e[0] == 'f' && fast_ok) variant = 2;
     }
     if (variant == 2 && !fast_ok) variant = -1;
+    // (3: the order-free engine with the search tree in shared memory, for scenes small enough)
+    const size_t smem_need = fast_smem_bytes<R>(s.n_fast_nodes, s.n_fast_prims, s.n_prims[0]);
+    bool smem_ok = fast_ok && s.n_fast_nodes != 0u && smem_need <= FAST_SMEM_LIMIT;
+    if (smem_ok && cudaFuncSetAttribute(k_trace_fast_smem<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_need) != cudaSuccess) {
+        cudaGetLastError();
+        smem_ok = false;
+    }
+    if (const char* e = getenv("CRB_TRAVERSAL")) {
+        if (e[0] == 's' && smem_ok) variant = 3;
+    }
+    if (variant == 3 && !smem_ok) variant = -1;
+    // the shared-memory build is the order-free engine with cheaper node fetches (A/B on one box: book1 -7 %, Cornell -4 %
+    // trace time), so where it fits it stands in for candidate 2 instead of being timed against it on one wavefront
     int cands[3], n_cands = 0;
     cands[n_cands++] = 0;
     if (!animated) cands[n_cands++] = 1;
-    if (fast_ok) cands[n_cands++] = 2;
+    if (fast_ok) cands[n_cands++] = smem_ok ? 3 : 2;
     const uint64_t tune_at = total >= 2ull * pool ? 1 : 0;  // the second wavefront mixes bounce rays with camera rays
     bool tuning = variant < 0 && total >= (1ull << 20) && n_cands > 1;
-    if (variant < 0) variant = fast_ok ? 2 : (animated ? 0 : 1);
+    if (variant < 0) variant = fast_ok ? (smem_ok ? 3 : 2) : (animated ? 0 : 1);
     auto launch_trace = [&](int v, int cur) {
+        if (v == 3) {
+            k_trace_fast_smem<R><<<s.num_sms, FAST_BIG_BLOCK, smem_need, stream>>>(sc, paths[cur], ctl, cur, queues, filt[cur], pool, retry_list,
+                                                                                  s.n_fast_nodes, s.n_fast_prims, s.n_prims[0]);
+            trace_variants[0]<<<s.num_sms * 2, TRACE_BLOCK, 0, stream>>>(sc, paths[cur], ctl, cur, queues, filt[cur], pool, retry_list);
+            return 2;
+        }
         if (v == 2) {
             fast_fn<<<g_fast, TRACE_BLOCK, 0, stream>>>(sc, paths[cur], ctl, cur, queues, filt[cur], pool, retry_list);
             // the rays it could not decide, in reference order (usually none: the launch returns at once)

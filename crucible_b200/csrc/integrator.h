@@ -26,6 +26,7 @@ struct SceneDeviceData {
     double* tri_anim_verts = nullptr;
     void* fast_nodes = nullptr;  // search tree of the order-free engine (FastNodeRec[]), nullptr = none
     void* fast_prims = nullptr;  // its leaf-primitive table (uint2[])
+    uint32_t n_fast_nodes = 0, n_fast_prims = 0;  // host-built search trees only (0: the tree was built on the device)
     uint32_t n_nodes = 0;
     uint32_t n_prims[3] = {0, 0, 0};  // spheres, triangles, quads
     int32_t sky_kind = CR_SKY_DEFAULT, sky_image = -1;

@@ -170,7 +170,8 @@ typedef struct CrStats {
     double ms_resolve;
     double ms_h2d, ms_d2h; /* host-buffer entry points only */
     uint64_t retried_rays; /* order-free engine: ray segments handed back to the reference-order kernel */
-    uint32_t trace_engine; /* what traced the wavefronts: 0 / 1 = reference-order kernel at 64 / 48 registers, 2 = order-free engine */
+    uint32_t trace_engine; /* what traced the wavefronts: 0 / 1 = reference-order kernel at 64 / 48 registers, 2 = order-free engine,
+                              3 = order-free engine with the search tree in shared memory (small scenes) */
     uint32_t reserved;
 } CrStats;
 

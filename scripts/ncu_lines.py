@@ -13,11 +13,18 @@ import tempfile
 
 rep, lib, pat = sys.argv[1], sys.argv[2], sys.argv[3]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
-raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "sass", "--csv"], capture_output=True, text=True).stdout
+# the first launch whose name matches `pat` (a report may hold several kernels)
+raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "sass", "--csv", "--kernel-name", "regex:" + pat, "--launch-count", "1"],
+                     capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 kname = rows[0][1]
 hdr = rows[1]
-data = [dict(zip(hdr, r)) for r in rows[2:] if len(r) == len(hdr)]
+body = rows[2:]
+for i, r in enumerate(body):  # a report with several matching launches repeats the table: keep the first
+    if r and r[0] == "Kernel Name":
+        body = body[:i]
+        break
+data = [dict(zip(hdr, r)) for r in body if len(r) == len(hdr)]
 base = int(data[0]["Address"], 16)
 mangled_hint = re.sub(r"[^A-Za-z0-9_]", "", kname.split("(")[0].split("::")[-1].split("<")[0])
 with tempfile.TemporaryDirectory() as td:

@@ -56,6 +56,29 @@ def test_f64_render_matches_oracle_path_by_path(gpu_device, oracle, name, kw):
         assert_bytes_match(rgb, rgb8, ref, ref8)
 
 
+@pytest.mark.parametrize("name,kw", [("book1", dict(image_width=160, samples=8)), ("cornell", dict(image_width=96, samples=16))])
+def test_every_trace_engine_gives_the_same_image(gpu_device, oracle, name, kw, monkeypatch):
+    """The four ways to trace a wavefront (reference order at two register budgets, the order-free engine with its search
+    tree in global or in shared memory) are pinned one after the other: same image bit for bit, same ray count."""
+    sc = demo_builder.CONFIGS[name](**kw)
+    gs, orc, cam = _both(sc, gpu_device, oracle)
+    ref, _, ost = orc.render(cam, seed=5)
+    images = {}
+    for env, engine in (({"CRB_TRAVERSAL": "r", "CRB_MINB": "8"}, 0), ({"CRB_TRAVERSAL": "r", "CRB_MINB": "10"}, 1),
+                        ({"CRB_TRAVERSAL": "f"}, 2), ({"CRB_TRAVERSAL": "s"}, 3)):
+        for k in ("CRB_TRAVERSAL", "CRB_MINB"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        rgb, _, st = gs.render(cam, seed=5)
+        assert st["trace_engine"] == engine, (env, st["trace_engine"])
+        assert st["rays"] == ost["rays"]
+        images[engine] = rgb
+    for engine in (1, 2, 3):
+        assert np.array_equal(images[engine], images[0]), engine
+    assert np.abs(images[3] - ref).max() <= TOL_F64
+
+
 def test_f64_render_is_reproducible_and_pool_independent(gpu_device, oracle):
     sc = demo_builder.book1_end_scene(image_width=128, samples=6)
     gs, orc, cam = _both(sc, gpu_device, oracle)
