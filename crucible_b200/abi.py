@@ -59,6 +59,11 @@ class CrRenderOpts(C.Structure):
                 ("flags", C.c_uint32)]
 
 
+CR_GROUP_HITLIST, CR_GROUP_BVH = 0, 1
+# SceneDesc.batches markers (not ABI values): a nested element opens / closes between primitive batches
+GROUP_BEGIN, GROUP_END = -1, -2
+
+
 class CrStats(C.Structure):
     _fields_ = [("samples", C.c_uint64), ("rays", C.c_uint64), ("iterations", C.c_uint64), ("launches", C.c_uint64),
                 ("ms_total", C.c_double), ("ms_trace", C.c_double), ("ms_shade", C.c_double), ("ms_raygen", C.c_double),
@@ -105,6 +110,8 @@ SIGNATURES = {
     "cr_scene_add_spheres": (C.c_int64, [_P, _P, _P, _P, C.c_size_t]),
     "cr_scene_add_triangles": (C.c_int64, [_P, _P, _P, _P, C.c_size_t]),
     "cr_scene_add_quads": (C.c_int64, [_P, _P, _P, _P, C.c_size_t]),
+    "cr_scene_begin_group": (C.c_int, [_P, C.c_int]),
+    "cr_scene_end_group": (C.c_int, [_P]),
     "cr_scene_set_hidden": (C.c_int, [_P, C.c_size_t, C.c_int]),
     "cr_scene_set_materials": (C.c_int, [_P, _P, C.c_size_t]),
     "cr_scene_set_textures": (C.c_int, [_P, _P, C.c_size_t]),

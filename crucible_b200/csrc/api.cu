@@ -62,12 +62,22 @@ struct CrScene {
     std::vector<HostImage> images;
     int sky_kind = CR_SKY_DEFAULT, sky_image = -1;
     std::map<uint64_t, std::vector<CrAnimKey>> anim;  // (prim_index * 4 + point) -> keyframes in timeline order
+    // nested elements (Scene::add_element accepts Hittables::HitList / BVHWrapper, scene/mod.rs:160-166).  A member is an
+    // element index, or GROUP_MEMBER | group id.  `top` (the top-level member list) exists once the scene has a group.
+    struct Group {
+        int32_t kind, parent;
+        std::vector<uint32_t> members;
+    };
+    std::vector<Group> groups;
+    std::vector<int32_t> open_groups;
+    std::vector<uint32_t> top;
     // built
     bool committed = false;
     std::vector<FlatNode> nodes;
     uint32_t root = REF_MISS;
     uint32_t max_depth = 0;
     uint64_t n_visible = 0;
+    std::vector<int32_t> leaf_order_grouped;  // scenes with groups: primitives in visiting order (GroupEmitter)
     int bvh_builder = CR_BVH_AUTO;
     CrCommitInfo commit_info = {};
     // device-built tree: FlatNode records on the device; `nodes` is then filled on demand (host_nodes)
@@ -225,6 +235,143 @@ struct Builder {
     }
 };
 
+// ---- scenes with nested elements ---------------------------------------------------------------------------------------
+// The reference's world is a tree of Hittables: BVHWrapper nodes (box test, left, right: bvhwrapper.rs:97-126), HitLists
+// (linear scan with ONE shrinking interval and no box test: hitlist.rs:52-65) and primitives.  A nested BVHWrapper met as
+// a leaf of its parent's tree tests its own box and recurses, i.e. it behaves as if its subtree were grafted into the
+// parent; a nested HitList is a run of members visited in order.  Both flatten into the SAME preorder array the stackless
+// walk already uses: box nodes with a skip link, and "always pass" leaf nodes (FLAT_ALWAYS_PASS) holding one or two
+// consecutive list members, which the walk enters without a box test.  A span-1 node stores its element twice
+// (bvhwrapper.rs:57-59); the second visit runs with the interval closed at the first visit's hit and can accept nothing
+// (every primitive it reaches was reached, with a wider interval, by the first), so the element is emitted once.
+static constexpr uint32_t GROUP_MEMBER = 0x80000000u;
+struct GroupEmitter {
+    CrScene& sc;
+    std::vector<FlatNode>& out;
+    std::vector<Box> gbox;           // box of every group as its parent sees it
+    std::vector<int32_t> leaf_order; // primitives in visiting order
+    uint32_t max_depth = 0;
+
+    bool is_group(uint32_t m) const { return (m & GROUP_MEMBER) != 0; }
+    const Box& box_of(uint32_t m) const { return is_group(m) ? gbox[m & ~GROUP_MEMBER] : sc.elements[m].box; }
+    uint32_t leaf_ref(uint32_t e) const { return make_leaf(sc.elements[e].kind, sc.elements[e].idx); }
+    // BVHWrapper::new_wrapper keeps nested lists / wrappers and the primitives that are not hidden (bvhwrapper.rs:16-27)
+    std::vector<uint32_t> visible_of(const std::vector<uint32_t>& members) const {
+        std::vector<uint32_t> v;
+        for (uint32_t m : members)
+            if (is_group(m) || !sc.elements[m].hide) v.push_back(m);
+        return v;
+    }
+    // Boxes, innermost groups first (a nested group always has a larger id than its parent).  HitList::add folds the
+    // members' boxes in insertion order, hidden ones included (hitlist.rs:27-30); a wrapper's box is its root's, the union
+    // of its visible members (bvhwrapper.rs:38-41, 47-50; min / max are exact, so the grouping of the fold does not matter).
+    void compute_boxes() {
+        gbox.assign(sc.groups.size(), Box());
+        for (size_t g = sc.groups.size(); g-- > 0;) {
+            const CrScene::Group& grp = sc.groups[g];
+            Box b;
+            for (uint32_t m : grp.members) {
+                if (grp.kind == CR_GROUP_BVH && !is_group(m) && sc.elements[m].hide) continue;
+                b = box_union(b, box_of(m));
+            }
+            gbox[g] = b;
+        }
+    }
+    void note_depth(uint32_t d) { max_depth = std::max(max_depth, d); }
+    void emit_always_pass(uint32_t e0, uint32_t e1, uint32_t depth) {
+        FlatNode n;
+        n.box = sc.elements[e0].box;
+        if (e1 != REF_NONE) n.box = box_union(n.box, sc.elements[e1].box);  // informational: never tested
+        n.left = leaf_ref(e0);
+        n.right = e1 == REF_NONE ? REF_NONE : leaf_ref(e1);
+        n.axis = FLAT_ALWAYS_PASS;
+        n.lchild = n.rchild = REF_NONE;
+        n.skip = (uint32_t)out.size() + 1u;
+        out.push_back(n);
+        leaf_order.push_back(sc.prim_of[sc.elements[e0].kind][sc.elements[e0].idx]);
+        if (e1 != REF_NONE) leaf_order.push_back(sc.prim_of[sc.elements[e1].kind][sc.elements[e1].idx]);
+        note_depth(depth);
+    }
+    // one element met without a box of its own: a member of a HitList, or a child of a box node that is not a plain node
+    void emit_item(uint32_t m, uint32_t depth) {
+        if (!is_group(m)) {
+            if (!sc.elements[m].hide) emit_always_pass(m, REF_NONE, depth);  // Sphere::hit / Triangle::hit return None when hidden
+            return;
+        }
+        const CrScene::Group& grp = sc.groups[m & ~GROUP_MEMBER];
+        if (grp.kind == CR_GROUP_BVH) {
+            std::vector<uint32_t> vis = visible_of(grp.members);
+            if (!vis.empty()) emit_bvh(vis, 0, vis.size(), depth);  // empty: the empty HitList of bvhwrapper.rs:29-31
+            return;
+        }
+        // HitList::hit: members in order, one shrinking interval; two consecutive primitives share a leaf node
+        for (size_t i = 0; i < grp.members.size(); ++i) {
+            const uint32_t a = grp.members[i];
+            if (is_group(a)) {
+                emit_item(a, depth + 1);
+                continue;
+            }
+            if (sc.elements[a].hide) continue;
+            uint32_t b = REF_NONE;
+            size_t j = i + 1;
+            while (j < grp.members.size() && !is_group(grp.members[j]) && sc.elements[grp.members[j]].hide) ++j;
+            if (j < grp.members.size() && !is_group(grp.members[j])) {
+                b = grp.members[j];
+                i = j;
+            }
+            emit_always_pass(a, b, depth + 1);
+        }
+    }
+    // BVHWrapper::help_generate (bvhwrapper.rs:46-80) over elements that may be nested
+    void emit_bvh(std::vector<uint32_t>& items, size_t start, size_t end, uint32_t depth) {
+        Box bbox;
+        for (size_t i = start; i < end; ++i) bbox = box_union(bbox, box_of(items[i]));
+        const int axis = longest_axis(bbox);
+        const size_t span = end - start;
+        const uint32_t at = (uint32_t)out.size();
+        FlatNode n;
+        n.box = bbox;
+        n.axis = (uint32_t)axis;
+        n.lchild = n.rchild = REF_NONE;
+        n.left = n.right = REF_NONE;
+        out.push_back(n);
+        note_depth(depth);
+        if (span <= 2) {
+            const uint32_t a = items[start], b = span == 2 ? items[start + 1] : REF_NONE;
+            if (!is_group(a) && (b == REF_NONE || !is_group(b))) {  // the plain leaf node
+                n.left = leaf_ref(a);
+                n.right = b == REF_NONE ? REF_NONE : leaf_ref(b);
+                leaf_order.push_back(sc.prim_of[sc.elements[a].kind][sc.elements[a].idx]);
+                if (b != REF_NONE) leaf_order.push_back(sc.prim_of[sc.elements[b].kind][sc.elements[b].idx]);
+            } else {
+                n.axis |= FLAT_GROUP_NODE;
+                n.left = n.lchild = at + 1u;
+                emit_item(a, depth + 1);
+                if (b != REF_NONE) {
+                    n.right = n.rchild = (uint32_t)out.size();
+                    emit_item(b, depth + 1);
+                }
+            }
+        } else {
+            struct Key {
+                double k;
+                uint32_t m;
+            };
+            std::vector<Key> keys(span);
+            for (size_t i = 0; i < span; ++i) keys[i] = {box_of(items[start + i]).lo[axis], items[start + i]};
+            std::stable_sort(keys.begin(), keys.end(), [](const Key& x, const Key& y) { return x.k < y.k; });  // box_compare, :82-94
+            for (size_t i = 0; i < span; ++i) items[start + i] = keys[i].m;
+            const size_t mid = start + span / 2;
+            n.left = n.lchild = at + 1u;
+            emit_bvh(items, start, mid, depth + 1);
+            n.right = n.rchild = (uint32_t)out.size();
+            emit_bvh(items, mid, end, depth + 1);
+        }
+        n.skip = (uint32_t)out.size();
+        out[at] = n;
+    }
+};
+
 inline float f32_down(double x) {
     float f = (float)x;
     if ((double)f > x) f = std::nextafterf(f, -std::numeric_limits<float>::infinity());
@@ -284,7 +431,7 @@ int upload_search_tree(CrScene* s, const std::vector<uint32_t>& visible) {
     SceneDeviceData& d = s->dev;
     d.fast_nodes = d.fast_prims = nullptr;
     d.n_fast_nodes = d.n_fast_prims = 0;
-    if (visible.empty() || !s->anim.empty() || getenv("CRB_NO_SEARCH_TREE")) return CR_OK;
+    if (visible.empty() || !s->anim.empty() || !s->groups.empty() || getenv("CRB_NO_SEARCH_TREE")) return CR_OK;
     // large scenes: linear BVH built on the device from the records just uploaded (search_tree.cu); small ones: binned SAH here
     bool on_device = visible.size() >= 32768;
     if (const char* e = getenv("CRB_SEARCH_TREE")) on_device = e[0] == 'l' && visible.size() >= 3;
@@ -343,6 +490,7 @@ int upload_scene(CrScene* s) {
     d.sky_kind = s->sky_kind;
     d.sky_image = s->sky_image;
     d.clamp_colors = 1;
+    d.strict_boxes = s->groups.empty() ? 0 : 1;
     d.max_radiance = 1.0;
     for (auto& m : s->mats)
         if (m.kind == CR_MAT_EMISSIVE) {
@@ -375,12 +523,20 @@ int upload_scene(CrScene* s) {
             // device words: inner = (skip link, axis), leaf node = (left primitive, right primitive)
             const bool leafnode = ref_is_leaf(n.left);
             a.left = leafnode ? n.left : n.skip;
-            a.right = leafnode ? n.right : n.axis;
+            a.right = leafnode ? n.right : (n.axis & 3u);
             a.pad0 = a.pad1 = 0;
             NodeRec<float>& b = n32[i];
             b.xmin = f32_down(n.box.lo[0]); b.xmax = f32_up(n.box.hi[0]);
             b.ymin = f32_down(n.box.lo[1]); b.ymax = f32_up(n.box.hi[1]);
             b.zmin = f32_down(n.box.lo[2]); b.zmax = f32_up(n.box.hi[2]);
+            bool finite = true;
+            for (int k = 0; k < 3; ++k) finite = finite && std::isfinite(n.box.lo[k]) && std::isfinite(n.box.hi[k]);
+            if ((n.axis & FLAT_ALWAYS_PASS) || !finite) {
+                // no box test (member of a nested HitList), or the empty box of an empty nested list: the f32 copy is NaN, so
+                // the conservative filter answers "undecided" and the walk looks at the node's flag / the exact f64 box
+                if (n.axis & FLAT_ALWAYS_PASS) a.left |= ALWAYS_PASS_BIT;
+                b.xmin = b.xmax = b.ymin = b.ymax = b.zmin = b.zmax = std::numeric_limits<float>::quiet_NaN();
+            }
             b.left = a.left;
             b.right = a.right;
         }
@@ -389,7 +545,7 @@ int upload_scene(CrScene* s) {
         for (size_t i = 0; i < s->nodes.size(); ++i) {
             double bm = 0.0;
             for (int k = 0; k < 3; ++k) bm = std::max(bm, std::max(std::fabs(s->nodes[i].box.lo[k]), std::fabs(s->nodes[i].box.hi[k])));
-            nb[i] = f32_up(bm);
+            nb[i] = std::isfinite(bm) ? f32_up(bm) : 0.f;  // an empty nested list has the empty box (+inf, -inf): never filtered
         }
         d.bmax = nb.empty() ? 0.f : *std::max_element(nb.begin(), nb.end());
         d.bsmall = d.bmax;
@@ -826,8 +982,33 @@ static int64_t add_prims(CrScene* s, uint32_t kind, const double* data, size_t s
         for (size_t t = 0; t < n_threads; ++t) pool.emplace_back(fill, n * t / n_threads, n * (t + 1) / n_threads);
         for (auto& th : pool) th.join();
     }
+    if (!s->groups.empty()) {  // member lists exist once the scene has a group
+        std::vector<uint32_t>& dst = s->open_groups.empty() ? s->top : s->groups[(size_t)s->open_groups.back()].members;
+        for (size_t i = 0; i < n; ++i) dst.push_back((uint32_t)(first + i));
+    }
     s->committed = false;
     return (int64_t)first;
+}
+
+int cr_scene_begin_group(CrScene* s, int kind) {
+    if (!s || (kind != CR_GROUP_HITLIST && kind != CR_GROUP_BVH)) return fail(CR_ERR_INVALID, "bad group kind");
+    if (s->groups.size() >= 0x7FFFFFFEu) return fail(CR_ERR_LIMIT, "too many groups");
+    if (s->groups.empty()) {  // everything added so far is a top-level element
+        s->top.resize(s->elements.size());
+        for (size_t i = 0; i < s->top.size(); ++i) s->top[i] = (uint32_t)i;
+    }
+    const int32_t id = (int32_t)s->groups.size();
+    const int32_t parent = s->open_groups.empty() ? -1 : s->open_groups.back();
+    (parent < 0 ? s->top : s->groups[(size_t)parent].members).push_back(GROUP_MEMBER | (uint32_t)id);
+    s->groups.push_back(CrScene::Group{kind, parent, {}});
+    s->open_groups.push_back(id);
+    s->committed = false;
+    return id;
+}
+int cr_scene_end_group(CrScene* s) {
+    if (!s || s->open_groups.empty()) return fail(CR_ERR_STATE, "cr_scene_end_group without an open group");
+    s->open_groups.pop_back();
+    return CR_OK;
 }
 
 int64_t cr_scene_add_spheres(CrScene* s, const double* d, const int32_t* m, const int32_t* o, size_t n) {
@@ -903,11 +1084,15 @@ int cr_scene_commit(CrScene* s) {
     if (!s) return fail(CR_ERR_INVALID, "null scene");
     int rc = validate(s);
     if (rc != CR_OK) return rc;
+    if (!s->open_groups.empty()) return fail(CR_ERR_STATE, "a group is still open (cr_scene_end_group missing)");
+    const bool grouped = !s->groups.empty();
     // BVHWrapper::new_wrapper: drop hidden primitives, empty -> empty HitList (bvhwrapper.rs:16-31)
     std::vector<uint32_t> visible;
-    visible.reserve(s->elements.size());
-    for (uint32_t i = 0; i < (uint32_t)s->elements.size(); ++i)
-        if (!s->elements[i].hide) visible.push_back(i);
+    if (!grouped) {
+        visible.reserve(s->elements.size());
+        for (uint32_t i = 0; i < (uint32_t)s->elements.size(); ++i)
+            if (!s->elements[i].hide) visible.push_back(i);
+    }
     s->n_visible = visible.size();
     s->nodes.clear();
     s->n_nodes = 0;
@@ -924,9 +1109,24 @@ int cr_scene_commit(CrScene* s) {
     s->commit_info.builder = CR_BVH_HOST;
     if (s->bvh_builder == CR_BVH_DEVICE && s->device < 0) return fail(CR_ERR_NO_DEVICE, "CR_BVH_DEVICE needs a scene created on a CUDA device");
     // DEVICE: tree build, record flattening and triangle set-up run as kernels; HOST: on the host, as written
-    const bool on_device = s->bvh_builder == CR_BVH_DEVICE || (s->bvh_builder == CR_BVH_AUTO && s->device >= 0 && visible.size() >= 32768);
+    const bool on_device = !grouped && (s->bvh_builder == CR_BVH_DEVICE || (s->bvh_builder == CR_BVH_AUTO && s->device >= 0 && visible.size() >= 32768));
     if (on_device) s->commit_info.builder = CR_BVH_DEVICE;
-    if (!visible.empty()) {
+    s->leaf_order_grouped.clear();
+    if (grouped) {
+        // nested elements: one preorder array for the whole Hittables tree (GroupEmitter), built on the host
+        GroupEmitter em{*s, s->nodes};
+        em.compute_boxes();
+        std::vector<uint32_t> vis = em.visible_of(s->top);
+        if (!vis.empty()) em.emit_bvh(vis, 0, vis.size(), 1);
+        if (s->nodes.size() > REF_MAX_INDEX) return fail(CR_ERR_LIMIT, "BVH too large");
+        s->n_nodes = s->nodes.size();
+        s->max_depth = em.max_depth;
+        s->n_visible = em.leaf_order.size();
+        s->leaf_order_grouped.swap(em.leaf_order);
+        if (s->n_nodes) s->root = 0;
+        s->commit_info.levels = s->max_depth;
+        s->commit_info.ms_build = ms_since(t_commit);
+    } else if (!visible.empty()) {
         const uint64_t nn = node_count(visible.size());
         if (nn > REF_MAX_INDEX) return fail(CR_ERR_LIMIT, "BVH too large");
         if (on_device) {
@@ -1052,6 +1252,11 @@ int64_t cr_scene_bvh_leaf_order(const CrScene* s, int32_t* out, size_t cap) {
     if (!s || !s->committed) return fail(CR_ERR_STATE, "scene not committed");
     // preorder array + "left before right" == DFS leaf order; span-1 nodes list their primitive twice
     // in the reference (left == right), which this enumeration reproduces for comparison with the oracle
+    if (!s->groups.empty()) {  // nested elements: the order the walk visits the primitives in (each once)
+        const size_t n = std::min(cap, s->leaf_order_grouped.size());
+        if (out && n) memcpy(out, s->leaf_order_grouped.data(), n * sizeof(int32_t));
+        return (int64_t)s->leaf_order_grouped.size();
+    }
     const int rc_nodes = host_nodes(s);
     if (rc_nodes != CR_OK) return rc_nodes;
     std::vector<int32_t> order;
@@ -1277,6 +1482,17 @@ extern "C" int cr_scene_save(const CrScene* s, const char* path) {
         w.u64(kv.first);
         w.vec(kv.second);
     }
+    // nested elements (optional trailing section: files without groups end here)
+    if (!s->groups.empty()) {
+        w.raw("GROUPS01", 8);
+        w.u64(s->groups.size());
+        for (const CrScene::Group& g : s->groups) {
+            w.u64((uint64_t)(int64_t)g.kind);
+            w.u64((uint64_t)(int64_t)g.parent);
+            w.vec(g.members);
+        }
+        w.vec(s->top);
+    }
     const bool ok = (fclose(f) == 0) && w.ok;
     return ok ? CR_OK : fail(CR_ERR_INVALID, std::string("write failed: ") + path);
 }
@@ -1329,6 +1545,22 @@ extern "C" CrScene* cr_scene_load(const char* path, int device) {
             const uint64_t key = r.u64();
             r.vec(s->anim[key], 1u << 20);
         }
+        char tag[8] = {0};
+        if (r.ok && fread(tag, 1, 8, f) == 8) {  // optional: nested elements
+            if (memcmp(tag, "GROUPS01", 8) != 0) r.ok = false;
+            const uint64_t n_groups = r.ok ? r.u64() : 0;
+            if (n_groups > 0x7FFFFFFEull) r.ok = false;
+            for (uint64_t g = 0; r.ok && g < n_groups; ++g) {
+                CrScene::Group grp;
+                grp.kind = (int32_t)(int64_t)r.u64();
+                grp.parent = (int32_t)(int64_t)r.u64();
+                r.vec(grp.members, (uint64_t)REF_MAX_INDEX * 2);
+                if (grp.kind != CR_GROUP_HITLIST && grp.kind != CR_GROUP_BVH) r.ok = false;
+                if (grp.parent < -1 || grp.parent >= (int64_t)g) r.ok = false;
+                s->groups.push_back(std::move(grp));
+            }
+            r.vec(s->top, (uint64_t)REF_MAX_INDEX * 2);
+        }
     } else {
         r.ok = false;
     }
@@ -1358,6 +1590,27 @@ extern "C" CrScene* cr_scene_load(const char* path, int device) {
             dst.box = prim_box(e.kind, &store[stride * e.idx]);
             s->prim_of[e.kind][e.idx] = (int32_t)i;
         }
+    }
+    if (ok && !s->groups.empty()) {
+        // every element and every group is a member of exactly one list, nested groups come after their parent
+        std::vector<char> seen_e(s->elements.size(), 0), seen_g(s->groups.size(), 0);
+        auto check = [&](const std::vector<uint32_t>& members, int64_t owner) {
+            for (uint32_t m : members) {
+                if (m & GROUP_MEMBER) {
+                    const uint32_t g = m & ~GROUP_MEMBER;
+                    if (g >= s->groups.size() || seen_g[g] || (int64_t)g <= owner || s->groups[g].parent != (int32_t)owner) return false;
+                    seen_g[g] = 1;
+                } else {
+                    if (m >= s->elements.size() || seen_e[m]) return false;
+                    seen_e[m] = 1;
+                }
+            }
+            return true;
+        };
+        ok = check(s->top, -1);
+        for (size_t g = 0; ok && g < s->groups.size(); ++g) ok = check(s->groups[g].members, (int64_t)g);
+        for (size_t i = 0; ok && i < seen_e.size(); ++i) ok = seen_e[i] != 0;
+        for (size_t g = 0; ok && g < seen_g.size(); ++g) ok = seen_g[g] != 0;
     }
     if (!ok) {
         cr_scene_destroy(s);
@@ -1403,6 +1656,8 @@ extern "C" CrScene* cr_scene_replicate(const CrScene* src, int device) {
     s->sky_image = src->sky_image;
     s->anim = src->anim;
     s->bvh_builder = src->bvh_builder;
+    s->groups = src->groups;
+    s->top = src->top;
     if (cr_scene_commit(s) != CR_OK) {
         const std::string keep = g_err;
         cr_scene_destroy(s);

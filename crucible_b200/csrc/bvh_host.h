@@ -54,9 +54,12 @@ struct Element {  // one entry of Scene.elements (scene/mod.rs:77), insertion or
     Box box;
 };
 
+static constexpr uint32_t FLAT_ALWAYS_PASS = 0x100u;  // FlatNode::axis flag: member of a nested HitList, no box test (api.cu GroupEmitter)
+static constexpr uint32_t FLAT_GROUP_NODE = 0x200u;   // FlatNode::axis flag: box node whose children are nested elements, not plain nodes
+
 struct FlatNode {
     Box box;
-    uint32_t left, right, axis;  // children: node indices, or primitive refs for a leaf node
+    uint32_t left, right, axis;  // children: node indices, or primitive refs for a leaf node (axis: bits 0..1 + FLAT_* flags)
     uint32_t lchild, rchild;     // node children (REF_NONE for a leaf node)
     uint32_t skip;               // preorder index of the first node after this subtree
 };

@@ -29,6 +29,9 @@ __host__ __device__ inline uint32_t make_leaf(uint32_t kind, uint32_t idx) { ret
 __host__ __device__ inline bool ref_is_leaf(uint32_t r) { return (r & REF_LEAF) != 0; }
 __host__ __device__ inline uint32_t ref_kind(uint32_t r) { return (r >> 29) & 3u; }
 __host__ __device__ inline uint32_t ref_index(uint32_t r) { return r & 0x07FFFFFFu; }
+// bit 28 of a leaf node's first word: the node has NO box test (a member of a nested HitList, hitlist.rs:52-65: the list
+// scans its objects without looking at their boxes).  The walk always "passes" such a node and tests its primitives.
+static constexpr uint32_t ALWAYS_PASS_BIT = 1u << 28;
 static constexpr uint32_t REF_MAX_INDEX = 0x07FFFFFEu;  // bit 27 of a node's first word = BIGBOX_BIT (device_math.cuh)
 
 static constexpr int MAX_TEX_NEST = 8;
@@ -193,6 +196,7 @@ struct DevScene {
     // free_pass_nodes nodes, or if the box is wider than free_pass_k error bands in ray parameter on every axis
     uint32_t free_pass_nodes;
     float free_pass_k;
+    int32_t strict_boxes;  // scene with nested elements: every box node decides (no root skip, no free pass)
 };
 
 // ---- in-flight path record --------------------------------------------------------------------

@@ -653,6 +653,9 @@ struct Trav {
     // what happens at inner nodes only decides how much work is skipped.  Two consequences used below:
     //   - the root of a tree with more than one node is not tested at all (the walk starts at its left child);
     //   - an inner node the f32 filter cannot decide may be entered without the exact f64 test (step_node).
+    // Neither holds for a scene with nested HitLists: their members are tested with no box of their own, so the box node
+    // above them is the one that selects them.  Such scenes set DevScene::strict_boxes: the walk starts at the root (the
+    // caller passes n_nodes = 1) and every undecided box gets the exact test (free_pass_nodes = 0, free_pass_k = inf).
     // Irregular rays (zero / NaN / inf components) keep the reference's test at every node.
     __device__ __forceinline__ void init_from(const FilterRay& f, R tmax, uint32_t n_nodes) {
         nr.set(f);
@@ -684,6 +687,7 @@ struct Trav {
             // untested (at most free_pass_nodes cheap tests instead of one exact f64 test; unbounded, rays with a wide
             // error band would walk whole subtrees the exact test culls: 8x slower on the 10 M-triangle scene)
             if (dec == 0) {
+                if (wa & ALWAYS_PASS_BIT) return after_box<true>(true, sc.n_nodes);  // member of a nested HitList: no box test
                 if (ref_is_leaf(wa)) return ST_EXACT;
                 if ((wa & INDEX_MASK) - i > sc.free_pass_nodes &&
                     !box_wider_than_band(ldg_node32(sc.nodes32 + i), nr, (float)tmin, best32, sc.free_pass_k))
@@ -693,7 +697,7 @@ struct Trav {
         } else {
             float lo, hi;
             slab32(nf, nr, tmin, best32, lo, hi);
-            hit = hi > lo;
+            hit = hi > lo || (wa & ALWAYS_PASS_BIT) != 0u;
         }
         return after_box<true>(hit, sc.n_nodes);
     }
@@ -704,11 +708,12 @@ struct Trav {
         wa = n.left;
         wb = n.right;
         const R best = store.best_t();
-        const bool hit = ok ? aabb_hit_regular(n, o, inv, inv.x > R(0), inv.y > R(0), inv.z > R(0), tmin, best)
-                            : aabb_hit(n, o, inv, tmin, best);
+        const bool hit = (wa & ALWAYS_PASS_BIT) ? true
+                                                : (ok ? aabb_hit_regular(n, o, inv, inv.x > R(0), inv.y > R(0), inv.z > R(0), tmin, best)
+                                                      : aabb_hit(n, o, inv, tmin, best));
         return after_box<false>(hit, sc.n_nodes);
     }
-    __device__ __forceinline__ uint32_t leaf_left() const { return wa & ~BIGBOX_BIT; }
+    __device__ __forceinline__ uint32_t leaf_left() const { return wa & ~(BIGBOX_BIT | ALWAYS_PASS_BIT); }
     __device__ __forceinline__ uint32_t leaf_right() const { return wb; }
     static __device__ __forceinline__ bool test_prim(const DevScene<R>& sc, uint32_t ref, V3<R> o, V3<R> d, R a, R tmin, R best, R tm,
                                                      R& t) {
@@ -824,7 +829,7 @@ __device__ __forceinline__ void trace_persistent(const DevScene<R>& sc, R tmin, 
                         tv.store.set_my(k);
                         V3<R> o, d;
                         io.load(k, o, d);  // the R-precision ray of the exact / leaf steps goes to the lane's slot
-                        tv.init_from(io.filter(k, tmin, tmax), tmax, sc.n_nodes);
+                        tv.init_from(io.filter(k, tmin, tmax), tmax, sc.strict_boxes ? 1u : sc.n_nodes);
                         tv.store.set_ray(o, d);
                         if constexpr (ANIM) tv.store.set_time(io.time(k));
                         st = (sc.n_nodes == 0u) ? (int)ST_DONE : tv.walk_state();
@@ -874,7 +879,7 @@ __device__ __forceinline__ void trace_warp_batch(const DevScene<R>& sc, R tmin, 
     int st = ST_DONE;
     if (active) {
         const V3<R> inv = {R(1) / d.x, R(1) / d.y, R(1) / d.z};  // adinv, bvh.rs:111
-        tv.init_from(make_filter_ray<R>(o, d, inv, tmin, tmax, sc.bsmall, sc.bmax), tmax, sc.n_nodes);
+        tv.init_from(make_filter_ray<R>(o, d, inv, tmin, tmax, sc.bsmall, sc.bmax), tmax, sc.strict_boxes ? 1u : sc.n_nodes);
         tv.store.set_ray(o, d);
         if constexpr (ANIM) tv.store.set_time(tm);
         st = (sc.n_nodes == 0u) ? (int)ST_DONE : tv.walk_state();

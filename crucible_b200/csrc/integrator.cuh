@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <limits>
 #include <string>
 #include <vector>
 
@@ -793,6 +794,11 @@ static DevScene<R> make_dev_scene(const SceneDeviceData& s) {
     if (const char* e = getenv("CRB_FREE_PASS")) d.free_pass_nodes = (uint32_t)strtoul(e, nullptr, 10);
     d.free_pass_k = 4.f;
     if (const char* e = getenv("CRB_FREE_PASS_K")) d.free_pass_k = (float)atof(e);
+    d.strict_boxes = s.strict_boxes;
+    if (s.strict_boxes) {
+        d.free_pass_nodes = 0u;
+        d.free_pass_k = std::numeric_limits<float>::infinity();
+    }
     return d;
 }
 

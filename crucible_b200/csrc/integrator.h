@@ -36,6 +36,7 @@ struct SceneDeviceData {
     double max_radiance = 1.0;  // largest per-sample colour component (1 unless the scene holds an Emissive)
     int num_sms = 148;
     int node_slice = 32;
+    int strict_boxes = 0;  // nested elements (cr_scene_begin_group): see DevScene::strict_boxes
 };
 
 // Grow-only device scratch owned by the CrScene (path pool, queues, fixed-point framebuffer).

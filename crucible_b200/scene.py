@@ -128,6 +128,25 @@ class Quad:  # EXTENSION
 
 
 # ------------------------------------------------------------------ timeline (translate part)
+class HitList:  # src/objects/hitlist.rs:6-31: a nested element, built with add()
+    def __init__(self, objs=()):
+        self.objs = []
+        for o in objs:
+            self.add(o)
+
+    def add(self, obj):
+        self.objs.append(obj)
+
+
+class BVHWrapper:  # src/objects/bvhwrapper.rs:15-44
+    def __init__(self, hitlist):
+        self.list = hitlist
+
+    @staticmethod
+    def new_wrapper(hitlist):
+        return BVHWrapper(hitlist)
+
+
 class InterpolationType:
     NERP, LERP = abi.CR_NERP, abi.CR_LERP
 
@@ -372,7 +391,15 @@ class SceneDesc:
 
     @property
     def n_prims(self):
-        return sum(len(b[1]) for b in self.batches)
+        return sum(len(b[1]) for b in self.batches if b[0] >= 0)
+
+    def begin_group(self, kind):
+        """A nested element (Hittables::HitList / BVHWrapper as one scene element): the batches up to the matching
+        end_group() are its members."""
+        self.batches.append((abi.GROUP_BEGIN, np.zeros((0, 1)), np.array([kind], np.int32), np.zeros(0, np.int32)))
+
+    def end_group(self):
+        self.batches.append((abi.GROUP_END, np.zeros((0, 1)), np.zeros(0, np.int32), np.zeros(0, np.int32)))
 
     def apply(self, lib, handle, prefix):
         """Push the description through a C ABI with the cr_scene_* shape (the product's, or the oracle's)."""
@@ -381,6 +408,11 @@ class SceneDesc:
         add = {abi.CR_PRIM_SPHERE: "scene_add_spheres", abi.CR_PRIM_TRIANGLE: "scene_add_triangles",
                abi.CR_PRIM_QUAD: "scene_add_quads"}
         for kind, data, mat, oid in self.batches:
+            if kind in (abi.GROUP_BEGIN, abi.GROUP_END):
+                rc = f("scene_begin_group")(handle, int(mat[0])) if kind == abi.GROUP_BEGIN else f("scene_end_group")(handle)
+                if rc < 0:
+                    raise abi.CrucibleError(rc, f("last_error")().decode())
+                continue
             data = np.ascontiguousarray(data, np.float64)
             mat = np.ascontiguousarray(mat, np.int32)
             oid = np.ascontiguousarray(oid, np.int32)
@@ -521,8 +553,30 @@ class Scene:
             oid = self._vend_id(alias, ObjectType.Quad)
             self._append(abi.CR_PRIM_QUAD, np.concatenate([element.q, element.u, element.v]),
                          self._tables.material(element.mat), oid)
+        elif isinstance(element, (HitList, BVHWrapper)):
+            # scene/mod.rs:160-166: the element is stored as it is: no id is vended, its members keep id 0 (Sphere::new)
+            self._append_nested(element)
         else:
-            raise TypeError("add_element expects a Sphere, Triangle or Quad")
+            raise TypeError("add_element expects a Sphere, Triangle, Quad, HitList or BVHWrapper")
+
+    def _append_nested(self, element):
+        if isinstance(element, BVHWrapper):
+            kind, members = abi.CR_GROUP_BVH, element.list.objs
+        else:
+            kind, members = abi.CR_GROUP_HITLIST, element.objs
+        self._batches.append([abi.GROUP_BEGIN, np.zeros((0, 1)), np.array([kind], np.int32), np.zeros(0, np.int32)])
+        for m in members:
+            if isinstance(m, Sphere):
+                self._append(abi.CR_PRIM_SPHERE, np.concatenate([m.center, [m.radius]]), self._tables.material(m.mat), 0)
+            elif isinstance(m, Triangle):
+                self._append(abi.CR_PRIM_TRIANGLE, np.concatenate([m.a, m.b, m.c]), self._tables.material(m.mat), 0)
+            elif isinstance(m, Quad):
+                self._append(abi.CR_PRIM_QUAD, np.concatenate([m.q, m.u, m.v]), self._tables.material(m.mat), 0)
+            elif isinstance(m, (HitList, BVHWrapper)):
+                self._append_nested(m)
+            else:
+                raise TypeError("a nested list holds Spheres, Triangles, Quads, HitLists or BVHWrappers")
+        self._batches.append([abi.GROUP_END, np.zeros((0, 1)), np.zeros(0, np.int32), np.zeros(0, np.int32)])
 
     def add_spheres(self, centers_radii, mats, alias_prefix):
         """Batch form of add_element for generated scenes: one alias/id per sphere, insertion order kept."""
@@ -630,8 +684,13 @@ class Scene:
         out = []
         if not self._anim_ops:
             return out
-        base = 0
+        base, depth = 0, 0
         for kind, data, _, oid in self._batches:
+            # the scene's id-based calls only see top-level elements (scene_animator.rs:44-59 passes nested ones through)
+            depth += 1 if kind == abi.GROUP_BEGIN else (-1 if kind == abi.GROUP_END else 0)
+            if kind < 0 or depth > 0:
+                base += len(data)
+                continue
             for oid_val in np.unique(oid):
                 ops = self._anim_ops.get(int(oid_val))
                 if not ops:
@@ -680,10 +739,12 @@ class Scene:
             d.images.append(self._sky_rgb8)
             d.sky_image = len(d.images) - 1
         if self._hidden_ids:
-            base = 0
-            for _, data, _, oid in self._batches:
-                hid = np.nonzero(np.isin(oid, list(self._hidden_ids)))[0]
-                d.hidden.extend((base + hid).tolist())
+            base, depth = 0, 0
+            for kind, data, _, oid in self._batches:
+                depth += 1 if kind == abi.GROUP_BEGIN else (-1 if kind == abi.GROUP_END else 0)
+                if kind >= 0 and depth == 0:  # hide_element matches top-level elements only (scene/mod.rs:246-262)
+                    hid = np.nonzero(np.isin(oid, list(self._hidden_ids)))[0]
+                    d.hidden.extend((base + hid).tolist())
                 base += len(data)
         return d
 

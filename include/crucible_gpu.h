@@ -216,6 +216,19 @@ int64_t cr_scene_add_triangles(CrScene*, const double* abc, const int32_t* mater
 /* EXTENSION: quads Q,u,v = [n][9]. */
 int64_t cr_scene_add_quads(CrScene*, const double* quv, const int32_t* material,
                            const int32_t* obj_id, size_t n);
+/* ---- nested elements: Scene::add_element also takes a whole Hittables::HitList or Hittables::BVHWrapper as ONE element
+ *      (scene/mod.rs:160-166).  Primitives added between cr_scene_begin_group and the matching cr_scene_end_group are the
+ *      members of that element, in call order; groups nest.  Members keep flat prim_index values in call order.
+ *        CR_GROUP_HITLIST : HitList built with HitList::add (hitlist.rs:27-30): hit() scans the members in order with one
+ *                           shrinking interval and no box test (hitlist.rs:52-65); a hidden member never hits
+ *                           (sphere.rs:62, triangle.rs:87) but still widens the list's box.
+ *        CR_GROUP_BVH     : BVHWrapper::new_wrapper over the members (bvhwrapper.rs:15-44): hidden primitives are dropped,
+ *                           the rest get their own median-split tree, which the enclosing tree meets as one leaf.
+ *      The enclosing BVH sorts and boxes a group like any other element (its bounding_box()).  Scenes with groups use the
+ *      reference-order engine and the host BVH builder.  cr_scene_begin_group returns the group id (>= 0). ---- */
+typedef enum CrGroupKind { CR_GROUP_HITLIST = 0, CR_GROUP_BVH = 1 } CrGroupKind;
+int cr_scene_begin_group(CrScene*, int kind);
+int cr_scene_end_group(CrScene*);
 /* Scene::hide_element / show_element, scene/mod.rs:232-281 (per primitive). */
 int cr_scene_set_hidden(CrScene*, size_t prim_index, int hide);
 /* At most 2^24 materials (CR_ERR_LIMIT at commit beyond that). */

@@ -46,6 +46,8 @@ def load():
     for n in ("orc_scene_add_spheres", "orc_scene_add_triangles", "orc_scene_add_quads"):
         getattr(lib, n).restype = C.c_int64
         getattr(lib, n).argtypes = [P, P, P, P, C.c_size_t]
+    lib.orc_scene_begin_group.argtypes = [P, C.c_int]
+    lib.orc_scene_end_group.argtypes = [P]
     lib.orc_scene_set_hidden.argtypes = [P, C.c_size_t, C.c_int]
     lib.orc_scene_set_keyframes.argtypes = [P, C.c_size_t, C.c_int, P, C.c_size_t]
     lib.orc_combine_and_compute.argtypes = [P, P, C.c_size_t, C.c_double, P]

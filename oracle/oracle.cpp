@@ -307,7 +307,7 @@ struct Image {
     std::vector<uint8_t> rgb;
 };
 
-enum ObjKind { O_SPHERE = 0, O_TRI = 1, O_QUAD = 2, O_NODE = 3, O_LIST = 4 };
+enum ObjKind { O_SPHERE = 0, O_TRI = 1, O_QUAD = 2, O_NODE = 3, O_LIST = 4, O_GROUP = 5 /* a nested element before the build */ };
 struct Obj {
     int kind, idx;
 };
@@ -332,7 +332,25 @@ struct Scene {
     std::vector<Sphere> spheres;
     std::vector<Triangle> tris;
     std::vector<Quad> quads;
-    std::vector<Obj> elements; /* Scene.elements / HitList.objs in insertion order */
+    std::vector<Obj> elements; /* every primitive in insertion order (prim_index); without groups == Scene.elements */
+    /* nested elements (scene/mod.rs:160-166: add_element takes a whole HitList / BVHWrapper): the description ... */
+    struct GroupDef {
+        int kind; /* CR_GROUP_HITLIST / CR_GROUP_BVH */
+        std::vector<Obj> members;
+    };
+    std::vector<GroupDef> gdefs;
+    std::vector<int> open;
+    std::vector<Obj> top; /* Scene.elements once a group exists: primitives and O_GROUP entries */
+    /* ... and the built HitLists (hitlist.rs:6-9) */
+    struct ListObj {
+        std::vector<Obj> objs;
+        Aabb bbox;
+    };
+    std::vector<ListObj> lists;
+    void note_added(Obj o) {
+        if (gdefs.empty()) return;
+        (open.empty() ? top : gdefs[(size_t)open.back()].members).push_back(o);
+    }
     std::vector<CrMaterial> mats;
     std::vector<CrTexture> texs;
     std::vector<Image> images;
@@ -350,6 +368,7 @@ struct Scene {
             case O_SPHERE: return spheres[o.idx].bbox;
             case O_TRI: return tris[o.idx].bbox;
             case O_QUAD: return quads[o.idx].bbox;
+            case O_LIST: return o.idx < 0 ? AABB_EMPTY : lists[(size_t)o.idx].bbox; /* HitList::default(): Aabb::default() */
             default: return nodes[o.idx].bbox;
         }
     }
@@ -505,7 +524,9 @@ static bool obj_hit(const Scene& sc, const Obj& o, const Ray& r, const Interval&
         case O_TRI: cn.tri++; return tri_hit(sc.tris[o.idx], r, ray_t, out);
         case O_QUAD: cn.quad++; return quad_hit(sc.quads[o.idx], r, ray_t, out);
         case O_NODE: return node_hit(sc, sc.nodes[o.idx], r, ray_t, out, cn);
-        default: return false; /* empty HitList (bvhwrapper.rs:29-31) */
+        case O_LIST: /* nested HitList (hitlist.rs:52-65); idx -1 = the empty HitList of bvhwrapper.rs:29-31 */
+            return o.idx >= 0 && list_hit(sc, sc.lists[(size_t)o.idx].objs, r, ray_t, out, cn);
+        default: return false;
     }
 }
 static inline bool world_hit(const Scene& sc, const Ray& r, const Interval& ray_t, HitRecord& out, Counters& cn) {
@@ -804,30 +825,51 @@ static Obj help_generate(Scene& sc, std::vector<Obj>& objects, size_t start, siz
     sc.nodes.push_back(n);
     return {O_NODE, (int)sc.nodes.size() - 1};
 }
-/* bvhwrapper.rs:15-44 */
-static void build_world(Scene& sc) {
-    sc.nodes.clear();
+static Obj resolve_element(Scene& sc, const Obj& o);
+/* BVHWrapper::new_wrapper, bvhwrapper.rs:15-44: hidden primitives dropped, nested lists / wrappers kept */
+static Obj new_wrapper(Scene& sc, const std::vector<Obj>& objs) {
     std::vector<Obj> visible;
-    for (const Obj& o : sc.elements) {
+    for (const Obj& o : objs) {
         bool hide = (o.kind == O_SPHERE) ? sc.spheres[o.idx].hide
                     : (o.kind == O_TRI)  ? sc.tris[o.idx].hide
-                                         : sc.quads[o.idx].hide;
-        if (!hide) visible.push_back(o);
+                    : (o.kind == O_QUAD) ? sc.quads[o.idx].hide
+                                         : false;
+        if (!hide) visible.push_back(resolve_element(sc, o));
     }
-    if (visible.empty()) {
-        sc.world = {O_LIST, -1};
-    } else {
-        Obj root = help_generate(sc, visible, 0, visible.size());
-        Node& n = sc.nodes[root.idx];
-        n.bbox = aabb_union(sc.bbox_of(n.left), sc.bbox_of(n.right)); /* new_from_vec, :38-41 */
-        sc.world = root;
+    if (visible.empty()) return {O_LIST, -1};
+    Obj root = help_generate(sc, visible, 0, visible.size());
+    const Aabb fixed = aabb_union(sc.bbox_of(sc.nodes[root.idx].left), sc.bbox_of(sc.nodes[root.idx].right)); /* new_from_vec, :38-41 */
+    sc.nodes[root.idx].bbox = fixed;
+    return root;
+}
+/* a nested element as the caller built it before Scene::add_element: HitList::add per member (hitlist.rs:27-30), or
+ * BVHWrapper::new_wrapper over the members */
+static Obj resolve_element(Scene& sc, const Obj& o) {
+    if (o.kind != O_GROUP) return o;
+    const int kind = sc.gdefs[(size_t)o.idx].kind;
+    const std::vector<Obj> members = sc.gdefs[(size_t)o.idx].members;
+    if (kind == CR_GROUP_BVH) return new_wrapper(sc, members);
+    Scene::ListObj l;
+    l.bbox = AABB_EMPTY;
+    for (const Obj& m : members) {
+        const Obj r = resolve_element(sc, m);
+        l.objs.push_back(r);
+        l.bbox = aabb_union(l.bbox, sc.bbox_of(r));
     }
+    sc.lists.push_back(l);
+    return {O_LIST, (int)sc.lists.size() - 1};
+}
+/* Scene::render_image: BVHWrapper::new_wrapper(self.elements.clone()), scene/mod.rs:333 */
+static void build_world(Scene& sc) {
+    sc.nodes.clear();
+    sc.lists.clear();
+    sc.world = new_wrapper(sc, sc.gdefs.empty() ? sc.elements : sc.top);
     delete sc.fast; /* MODEL tree of the previous build */
     sc.fast = nullptr;
     sc.leaf_rank.assign(2 * sc.nodes.size(), 0u);
     {
         uint32_t next = 0;
-        assign_leaf_ranks(sc, sc.world, next);
+        if (sc.gdefs.empty()) assign_leaf_ranks(sc, sc.world, next); /* the order-free MODEL covers flat scenes only */
     }
     sc.built = true;
 }
@@ -1134,6 +1176,7 @@ int64_t orc_scene_add_spheres(OrcScene* h, const double* d, const int32_t* mat, 
         s.bbox = aabb_from_points(sub(s.c, rv), add(s.c, rv)); /* sphere.rs:29-30 */
         sc.spheres.push_back(s);
         sc.elements.push_back({O_SPHERE, (int)sc.spheres.size() - 1});
+        sc.note_added(sc.elements.back());
     }
     sc.built = false;
     return first;
@@ -1157,6 +1200,7 @@ int64_t orc_scene_add_triangles(OrcScene* h, const double* d, const int32_t* mat
         t.bbox.z = {rmin(t.a.z, rmin(t.b.z, t.c.z)), rmax(t.a.z, rmax(t.b.z, t.c.z))};
         sc.tris.push_back(t);
         sc.elements.push_back({O_TRI, (int)sc.tris.size() - 1});
+        sc.note_added(sc.elements.back());
     }
     sc.built = false;
     return first;
@@ -1189,9 +1233,30 @@ int64_t orc_scene_add_quads(OrcScene* h, const double* d, const int32_t* mat, co
         q.bbox = bb;
         sc.quads.push_back(q);
         sc.elements.push_back({O_QUAD, (int)sc.quads.size() - 1});
+        sc.note_added(sc.elements.back());
     }
     sc.built = false;
     return first;
+}
+/* nested elements (mirror of cr_scene_begin_group / cr_scene_end_group) */
+int orc_scene_begin_group(OrcScene* h, int kind) {
+    Scene& sc = *reinterpret_cast<Scene*>(h);
+    if (kind != CR_GROUP_HITLIST && kind != CR_GROUP_BVH) return CR_ERR_INVALID;
+    if (sc.gdefs.empty()) sc.top = sc.elements; /* everything added so far is a top-level element */
+    const int id = (int)sc.gdefs.size();
+    Scene::GroupDef g;
+    g.kind = kind;
+    (sc.open.empty() ? sc.top : sc.gdefs[(size_t)sc.open.back()].members).push_back({O_GROUP, id});
+    sc.gdefs.push_back(g);
+    sc.open.push_back(id);
+    sc.built = false;
+    return id;
+}
+int orc_scene_end_group(OrcScene* h) {
+    Scene& sc = *reinterpret_cast<Scene*>(h);
+    if (sc.open.empty()) return CR_ERR_STATE;
+    sc.open.pop_back();
+    return 0;
 }
 /* keyframes of one point of a primitive, in the timeline's sorted order (mirror of cr_scene_set_keyframes) */
 int orc_scene_set_keyframes(OrcScene* h, size_t prim, int point, const CrAnimKey* keys, size_t n) {
@@ -1261,6 +1326,10 @@ static void leaf_order(const Scene& sc, const Obj& o, std::vector<int32_t>& out,
         case O_NODE:
             leaf_order(sc, sc.nodes[o.idx].left, out, depth + 1, maxd);
             leaf_order(sc, sc.nodes[o.idx].right, out, depth + 1, maxd);
+            break;
+        case O_LIST:
+            if (o.idx >= 0)
+                for (const Obj& m : sc.lists[(size_t)o.idx].objs) leaf_order(sc, m, out, depth + 1, maxd);
             break;
         default: break;
     }
