@@ -245,6 +245,7 @@ struct Control {
     uint32_t iteration;
     uint32_t retry_next;     // work cursor of the reference-order kernel over the retry list
     uint32_t retry_total;    // rays re-traced in reference order over the whole render (CrStats-level diagnostics)
+    uint32_t tail_go;        // set by k_plan: every camera sample is issued and few paths remain: k_tail finishes them now
 };
 
 // ---- camera as the kernels see it ----------------------------------------------------------------

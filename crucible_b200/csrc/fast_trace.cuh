@@ -396,4 +396,59 @@ __device__ __forceinline__ void fast_trace_persistent(const DevScene<R>& sc, R t
     }
 }
 
+// Closest hit for ONE ray per lane with the order-free engine, all 32 lanes of the warp together (no refill, no queues):
+// the tail kernel's trace step.  Lanes with active == false only take part in the votes.  Returns the closest hit in
+// (ref, t); `retry` = the lane's ray must be traced in reference order instead (irregular ray or irregular candidate).
+template <typename R, int BLOCK>
+__device__ __forceinline__ void fast_trace_warp_batch(const DevScene<R>& sc, R tmin, R tmax, bool active, V3<R> o, V3<R> d,
+                                                      FastSlots<R, BLOCK>* slots, uint32_t& ref, R& t, bool& retry) {
+    uint32_t deep_ref[FAST_STACK - FAST_SMEM_LEVELS];
+    float deep_lo[FAST_STACK - FAST_SMEM_LEVELS];
+    FastTrav<R, BLOCK, false> tv;
+    tv.s = slots;
+    tv.tree = SmemTree{0u, 0u, 0u};
+    tv.deep_ref = deep_ref;
+    tv.deep_lo = deep_lo;
+    tv.cur = 0u;
+    tv.sp = 0;
+    tv.best_m = 0.f;
+    tv.margin = 0.f;
+    const float tmin32 = (float)tmin;
+    int st = FS_DONE;
+    if (active) {
+        const V3<R> inv = {R(1) / d.x, R(1) / d.y, R(1) / d.z};  // adinv, bvh.rs:111
+        const FilterRay f = make_filter_ray<R>(o, d, inv, tmin, tmax, sc.bsmall, sc.bmax);
+        tv.init_from(f, tmax, sc.fast_margin_k, sc.bmax);
+        tv.set_ray(o, d);
+        st = f.ok ? (int)FS_INNER : (int)FS_RETRY;
+    }
+    while (__any_sync(0xffffffffu, st == FS_INNER || st == FS_LEAF)) {
+        if (__any_sync(0xffffffffu, st == FS_INNER)) {
+            const FastRay fr = tv.load_fray();
+#pragma unroll 1
+            for (int k = 0; k < sc.node_slice; k += 4) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (st == FS_INNER) st = tv.step_inner(sc, fr, tmin32);
+                }
+                // one ray per lane and nothing to refill: keep stepping while any lane still has a cheap step
+                if (!__any_sync(0xffffffffu, st == FS_INNER)) break;
+            }
+        }
+        if (st == FS_LEAF && tv.leaf_certain_miss(sc)) st = tv.pop();
+        if (st == FS_LEAF) {
+            V3<R> ro, rd;
+            tv.get_ray(ro, rd);
+            st = tv.step_leaf(sc, ro, rd, tmin, tmax);
+        }
+    }
+    retry = st == FS_RETRY;
+    ref = REF_MISS;
+    t = tmax;
+    if (active && !retry) {
+        ref = slots->best_ref[threadIdx.x];
+        t = slots->best_t[threadIdx.x];
+    }
+}
+
 }  // namespace crb

@@ -183,7 +183,10 @@ __host__ __device__ inline uint32_t local_to_global_row(uint32_t lr, uint32_t bl
 // ---- kernels --------------------------------------------------------------------------------------
 // plan: single thread.  Closes iteration `side`->`nxt`: survivors are already in side nxt; decide how
 // many camera samples top the pool up, publish the trace size of the next iteration, reset cursors.
-static __global__ void k_plan(Control* ctl, int nxt, uint32_t* host_n_in) {
+// tail_n != 0: when every camera sample has been issued and at most tail_n paths are left, hand them to k_tail (launched
+// right after raygen in every late iteration; the decision is taken HERE, on the device, so the hand-over does not wait
+// for the host's lagged view of the wavefront size).
+static __global__ void k_plan(Control* ctl, int nxt, uint32_t* host_n_in, uint32_t tail_n) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     const uint32_t survivors = ctl->out_count[nxt];
     const uint64_t remaining = ctl->total_samples - ctl->next_sample;
@@ -203,7 +206,14 @@ static __global__ void k_plan(Control* ctl, int nxt, uint32_t* host_n_in) {
     ctl->retry_next = 0;
     for (int q = 0; q < Q_COUNT; ++q) ctl->queue_count[q] = 0;
     ctl->iteration++;
+    ctl->tail_go = (tail_n != 0u && ctl->next_sample >= ctl->total_samples && n_in != 0u && n_in <= tail_n) ? 1u : 0u;
     if (host_n_in) *host_n_in = n_in;
+}
+// after k_tail: the wavefront of side `side` is finished, later iterations find nothing to do
+static __global__ void k_tail_finish(Control* ctl, int side) {
+    if (threadIdx.x != 0 || blockIdx.x != 0 || !ctl->tail_go) return;
+    ctl->n_in[side] = 0;
+    ctl->tail_go = 0;
 }
 
 // rewinds the trace cursor and the material queues so the SAME wavefront can be traced again (variant timing)
@@ -438,6 +448,7 @@ __global__ void __launch_bounds__(FAST_BIG_BLOCK, 1) k_trace_fast_smem(DevScene<
                                                                        uint32_t pool, uint32_t* __restrict__ retry_list, uint32_t n_fast_nodes,
                                                                        uint32_t n_fast_prims, uint32_t n_spheres) {
     extern __shared__ __align__(128) unsigned char fast_smem[];
+    if (ctl->n_in[side] == 0u) return;  // nothing to trace: skip the copy of the tree
     auto up = [](uint32_t b) { return (b + 127u) & ~127u; };
     FastSlots<R, FAST_BIG_BLOCK>* slots = reinterpret_cast<FastSlots<R, FAST_BIG_BLOCK>*>(fast_smem);
     const uint32_t o_nodes = up((uint32_t)sizeof(FastSlots<R, FAST_BIG_BLOCK>)), o_prims = o_nodes + up(n_fast_nodes * 64u),
@@ -622,11 +633,15 @@ __global__ void __launch_bounds__(SHADE_BLOCK, MINB) k_shade_scatter(DevScene<R>
 // scatter of every lane's own material, using the same device routines, so every path is unchanged.
 // (The first version gave each THREAD one path and its own traversal state machine: lanes in different states
 // serialised each other, 1.6 ms per frame at 11 % warps active, profiles/misc_r01c.md.)
-template <typename R, bool ANIM>
+// FAST: the trace step is the order-free engine's (static scenes with a search tree); a lane whose ray it hands back
+// is traced by the reference-order walk in the same bounce.
+template <typename R, bool ANIM, bool FAST>
 __global__ void __launch_bounds__(TRACE_BLOCK, 4) k_tail(DevScene<R> sc, const PathRec<R>* __restrict__ paths, Control* __restrict__ ctl,
                                                          int side, uint64_t seed, uint32_t max_depth,
                                                          unsigned long long* __restrict__ fb, double fb_scale) {
     __shared__ LaneSlots<R, TRACE_BLOCK, ANIM> slots;
+    __shared__ FastSlots<R, FAST ? TRACE_BLOCK : 1> fslots;
+    if (!ctl->tail_go) return;  // k_plan decides (device side) when the tail takes over
     const uint32_t n = ctl->n_in[side];
     const bool cl = sc.clamp_colors != 0;
     unsigned long long traced = 0;  // segments beyond each path's first (k_plan already counted that one)
@@ -639,7 +654,21 @@ __global__ void __launch_bounds__(TRACE_BLOCK, 4) k_tail(DevScene<R> sc, const P
             const V3<R> o = {p.ox, p.oy, p.oz}, d = {p.dx, p.dy, p.dz};
             uint32_t ref;
             R t;
-            trace_warp_batch<R, TRACE_BLOCK, ANIM>(sc, R(0.001), Num<R>::inf(), alive, o, d, p.tm, &slots, ref, t);  // ray_casting.rs:119
+            if constexpr (FAST) {
+                bool retry;
+                fast_trace_warp_batch<R, TRACE_BLOCK>(sc, R(0.001), Num<R>::inf(), alive, o, d, &fslots, ref, t, retry);
+                if (__any_sync(0xffffffffu, retry)) {
+                    uint32_t ref2;
+                    R t2;
+                    trace_warp_batch<R, TRACE_BLOCK, ANIM>(sc, R(0.001), Num<R>::inf(), retry, o, d, p.tm, &slots, ref2, t2);
+                    if (retry) {
+                        ref = ref2;
+                        t = t2;
+                    }
+                }
+            } else {
+                trace_warp_batch<R, TRACE_BLOCK, ANIM>(sc, R(0.001), Num<R>::inf(), alive, o, d, p.tm, &slots, ref, t);  // ray_casting.rs:119
+            }
             if (!alive) continue;
             if (!first) ++traced;
             if (ref == REF_MISS) {  // ray_casting.rs:133-151
@@ -1132,8 +1161,10 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
     rp.bmax = s.bmax;
     host_camera_constants<R>(cam_in, rp);
     const int g_gen = persistent_grid(gen_fn, SHADE_BLOCK, s.num_sms);
-    auto tail_fn = animated ? k_tail<R, true> : k_tail<R, false>;
-    const int g_tail = persistent_grid(tail_fn, TRACE_BLOCK, s.num_sms);
+    auto tail_fn = animated ? k_tail<R, true, false> : k_tail<R, false, false>;
+    auto tail_fast_fn = fast_ok ? k_tail<R, false, true> : tail_fn;  // the order-free engine's trace step inside the tail
+    const int g_tail = std::min(persistent_grid(tail_fn, TRACE_BLOCK, s.num_sms), persistent_grid(tail_fast_fn, TRACE_BLOCK, s.num_sms));
+    bool samples_out = total <= (uint64_t)pool;  // every camera sample issued by the prologue?
     uint32_t tail_n = 65536;
     if (const char* e = getenv("CRB_TAIL")) tail_n = (uint32_t)atoi(e);
     const int g_miss = persistent_grid(k_shade_miss<R>, SHADE_BLOCK, s.num_sms);
@@ -1158,13 +1189,14 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
     cudaEvent_t a;
     // prologue: camera basis (static cameras), plan + raygen fill side 0
     tm.begin(2, a);
-    k_plan<<<1, 32, 0, stream>>>(ctl, 0, nullptr);
+    k_plan<<<1, 32, 0, stream>>>(ctl, 0, nullptr, 0u);
     gen_fn<<<g_gen, SHADE_BLOCK, 0, stream>>>(ctl, d_cam, rp, paths[0], filt[0]);
     tm.end(2, a);
     launches += 2;
 
     uint64_t it = 0;
     bool done = (issue == 0);
+    bool small_wave = false;
     const bool log_waves = getenv("CRB_LOG_WAVES") != nullptr;  // debug: wavefront sizes (pairs an ncu capture with its ray count)
     while (!done) {
         const int cur = (int)(it & 1), nxt = cur ^ 1;
@@ -1192,7 +1224,8 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
             launches += n_cands - 2;  // the rewinds; one trace launch is part of the five counted below
         } else {
             tm.begin(0, a);
-            launches += launch_trace(variant, cur) - 1;
+            // (small wavefronts: the 43 us floor of the shared-memory build — tree copy, 896-thread CTAs — is not worth it)
+            launches += launch_trace(variant == 3 && small_wave ? 2 : variant, cur) - 1;
             tm.end(0, a);
         }
         tm.begin(1, a);
@@ -1211,10 +1244,21 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
         }
         tm.end(1, a);
         tm.begin(2, a);
-        k_plan<<<1, 32, 0, stream>>>(ctl, nxt, nullptr);
+        k_plan<<<1, 32, 0, stream>>>(ctl, nxt, nullptr, tail_n);
         gen_fn<<<g_gen, SHADE_BLOCK, 0, stream>>>(ctl, d_cam, rp, paths[nxt], filt[nxt]);
         tm.end(2, a);
         launches += 2;
+        if (samples_out && tail_n != 0u) {
+            // When the pool is no longer full every camera sample has been issued; from then on each iteration offers
+            // the wavefront to k_tail, which returns at once until k_plan finds at most tail_n paths left: then ONE launch
+            // follows each of them to its end instead of ~25-45 more 8-launch iterations, and the iterations still in
+            // flight find an empty wavefront.
+            tm.begin(0, a);
+            (variant >= 2 ? tail_fast_fn : tail_fn)<<<g_tail, TRACE_BLOCK, 0, stream>>>(sc, paths[nxt], ctl, nxt, opts.seed, cam_in.max_depth, fb, fb_scale);
+            k_tail_finish<<<1, 32, 0, stream>>>(ctl, nxt);
+            tm.end(0, a);
+            launches += 2;
+        }
 
         const int slot = (int)(it % RING);
         CRB_CUDA(cudaMemcpyAsync((void*)(h_n_in + slot), &ctl->n_in[nxt], sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
@@ -1226,18 +1270,9 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
             const uint32_t left = h_n_in[old];
             if (log_waves) fprintf(stderr, "crucible_b200 wave %llu: %u paths enter iteration %llu\n", (unsigned long long)(it - LAG),
                                    left, (unsigned long long)(it - LAG + 1));
-            if (left == 0) {
-                done = true;  // nothing left to trace after iteration it-LAG: later ones were no-ops
-            } else if (left < pool && left <= tail_n) {
-                // the pool is no longer full => every camera sample has been issued; a few thousand paths remain:
-                // one k_tail launch follows each of them to its end instead of ~25-45 more 8-launch iterations
-                const int side = (int)(it & 1);
-                tm.begin(0, a);
-                tail_fn<<<g_tail, TRACE_BLOCK, 0, stream>>>(sc, paths[side], ctl, side, opts.seed, cam_in.max_depth, fb, fb_scale);
-                tm.end(0, a);
-                ++launches;
-                done = true;
-            }
+            if (left < pool) samples_out = true;
+            small_wave = left < (1u << 18);
+            if (left == 0) done = true;  // nothing left to trace after iteration it-LAG (k_tail took over, or every path ended)
         }
         if (it > 100000000ull) {
             err = "render: iteration limit";

@@ -6,7 +6,8 @@ import torch
 from crucible_b200 import abi, demo_builder, multigpu
 from crucible_b200.gpu import GpuScene
 
-sc = demo_builder.book1_end_scene(image_width=1920, samples=int(os.environ.get("SPP", "100")), seed=1)
+kw = {"samples": int(os.environ["SPP"])} if "SPP" in os.environ else {}
+sc = demo_builder.CONFIGS[os.environ.get("CONFIG", "book1")](**kw)
 desc, cam = sc.describe(), sc.scene_cam.to_abi()
 H, W = cam.image_height, cam.image_width
 pinned = torch.empty((H, W, 3), dtype=torch.float64).pin_memory()
@@ -17,9 +18,11 @@ for it in range(6):
     h = lib.cr_scene_create(0); t.append(time.perf_counter())
     lib.cr_scene_destroy(h); t.append(time.perf_counter())
     g = GpuScene(desc, 0); t.append(time.perf_counter())
+    ci = g.commit_info()
     # the reference-facing call: cr_render with HOST buffers (what bench.py's e2e leg times at N=1)
     _, _, st = g.render(cam, seed=1, out_rgb=pinned.numpy(), out_rgb8=pinned8.numpy()); t.append(time.perf_counter())
     g.close(); t.append(time.perf_counter())
     names = ["create", "destroy", "GpuScene", "cr_render", "close"]
     print(it, " ".join(f"{n}={1e3*(b-a):.2f}" for n, a, b in zip(names, t, t[1:])),
-          f"device_ms={st['ms_total']:.2f} h2d_ms={st['ms_h2d']:.2f} d2h_ms={st['ms_d2h']:.2f} launches={st['launches']}", flush=True)
+          f"device_ms={st['ms_total']:.2f} h2d_ms={st['ms_h2d']:.2f} d2h_ms={st['ms_d2h']:.2f} launches={st['launches']}",
+          {k: round(v, 2) for k, v in ci.items() if k.startswith("ms_")}, flush=True)

@@ -15,7 +15,19 @@ import numpy as np
 import golden
 from oracle import binding as oracle
 
-for name in sys.argv[1:] or list(golden.CONFIGS):
+names = sys.argv[1:] or list(golden.CONFIGS) + ["nested"]
+if "nested" in names:  # nested elements: leaf order + 2048 seeded random rays of tests/scenes_util.nested_scene(1)
+    from conftest import random_rays
+    from scenes_util import nested_scene, scene_bounds
+
+    names.remove("nested")
+    d = nested_scene(1)
+    orc = oracle.OracleScene(d)
+    lo, hi = scene_bounds(d)
+    rays = random_rays(2048, lo, hi, 77)
+    np.savez_compressed(golden.path("nested"), rays=rays, hits=orc.trace_batch(rays), leaf_order=orc.bvh_leaf_order())
+    print("nested", os.path.getsize(golden.path("nested")), "bytes")
+for name in names:
     sc = golden.build(name)
     desc, cam = sc.describe(), sc.scene_cam.to_abi()
     orc = oracle.OracleScene(desc)

@@ -75,5 +75,32 @@ def kernel(src, dst):
     print(open(dst).read())
 
 
+def bykernel(src, dst):
+    """One column per DISTINCT kernel of an ncu --csv --page raw log (the launch that ran longest), for the all-kernels pass
+    of scripts/profile_all.py."""
+    rows = list(csv.reader(open(src)))
+    hdr = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
+    h, units, data = rows[hdr], rows[hdr + 1], rows[hdr + 2:]
+    ki, di = h.index("Kernel Name"), h.index("gpu__time_duration.sum")
+    best, count, total = collections.OrderedDict(), collections.Counter(), collections.Counter()
+    for r in data:
+        if len(r) != len(h):
+            continue
+        name = r[ki].split("(")[0].replace("void ", "").replace("crb::", "")
+        t = float(r[di].replace(",", ""))
+        count[name] += 1
+        total[name] += t
+        if name not in best or t > float(best[name][di].replace(",", "")):
+            best[name] = r
+    with open(dst, "w") as f:
+        f.write(f"ncu pass over every kernel: {src} (python scripts/profile_all.py; per kernel the launch that ran longest)\n\n")
+        short = [m for m in METRICS if m in h]
+        f.write("| kernel | launches | total " + units[di] + " | " + " | ".join(m.split(".")[0].replace("smsp__average_warps_issue_stalled_", "stall_").replace("_per_issue_active", "") for m in short) + " |\n")
+        f.write("|---|---:|---:|" + "---:|" * len(short) + "\n")
+        for name, r in best.items():
+            f.write(f"| {name} | {count[name]} | {total[name]:.0f} | " + " | ".join(r[h.index(m)] for m in short) + " |\n")
+    print(open(dst).read()[:3000])
+
+
 if __name__ == "__main__":
-    {"launches": launches, "kernel": kernel}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "kernel": kernel, "bykernel": bykernel}[sys.argv[1]](sys.argv[2], sys.argv[3])

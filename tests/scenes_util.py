@@ -68,9 +68,59 @@ def random_scene(n_sph=0, n_tri=0, n_quad=0, seed=0, extent=10.0, kinds=(0, 1, 2
     return d
 
 
+def nested_scene(seed, n=160, hidden=True):
+    """Top-level primitives mixed with: a HitList of spheres and triangles (one member hidden), a BVHWrapper of 40
+    primitives (one hidden), a HitList that holds a BVHWrapper and a HitList, an empty HitList and a single-member wrapper."""
+    base = random_scene(n, n // 2, 12, seed)
+    prims = []  # (kind, row, mat, oid) in insertion order
+    for kind, data, mat, oid in base.batches:
+        for i in range(len(data)):
+            prims.append((kind, data[i], int(mat[i]), int(oid[i])))
+    rng = np.random.Generator(np.random.Philox(key=seed + 1000))
+    rng.shuffle(prims)
+    d = SceneDesc()
+    d.materials, d.textures = base.materials, base.textures
+    it = iter(prims)
+
+    def take(k):
+        for _ in range(k):
+            kind, row, mat, oid = next(it)
+            d.batches.append((kind, row[None, :], np.array([mat], np.int32), np.array([oid], np.int32)))
+
+    take(30)
+    d.begin_group(abi.CR_GROUP_HITLIST)
+    take(9)
+    d.end_group()
+    take(25)
+    d.begin_group(abi.CR_GROUP_BVH)
+    take(40)
+    d.end_group()
+    d.begin_group(abi.CR_GROUP_HITLIST)
+    take(3)
+    d.begin_group(abi.CR_GROUP_BVH)
+    take(17)
+    d.end_group()
+    take(1)
+    d.begin_group(abi.CR_GROUP_HITLIST)
+    take(4)
+    d.end_group()
+    d.end_group()
+    d.begin_group(abi.CR_GROUP_HITLIST)  # empty list: the empty box, never hit
+    d.end_group()
+    d.begin_group(abi.CR_GROUP_BVH)
+    take(1)
+    d.end_group()
+    take(len(prims) - 30 - 9 - 25 - 40 - 3 - 17 - 1 - 4 - 1)
+    if hidden:
+        d.hidden = [3, 33, 70, 110, 131]  # top level, inside the first list, inside the wrapper, nested wrapper, inner list
+    return d
+
+
 def scene_bounds(desc):
     lo, hi = np.full(3, np.inf), np.full(3, -np.inf)
     for kind, data, _, _ in desc.batches:
+        if kind < 0:  # group markers
+            continue
         if kind == abi.CR_PRIM_SPHERE:
             pts = [data[:, :3] - data[:, 3:4], data[:, :3] + data[:, 3:4]]
         elif kind == abi.CR_PRIM_TRIANGLE:

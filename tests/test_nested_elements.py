@@ -13,55 +13,8 @@ from crucible_b200 import abi, demo_builder
 from crucible_b200.gpu import GpuScene
 from crucible_b200.scene import BVHWrapper, Color, HitList, Lambertian, Metal, Point3, Scene, SolidColor, Sphere, Triangle
 from conftest import random_rays
-from scenes_util import _mats, compare_hits, random_scene, scene_bounds
-
-
-def nested_scene(seed, n=160, hidden=True):
-    """Top-level primitives mixed with: a HitList of spheres and triangles (one member hidden), a BVHWrapper of 40
-    primitives (one hidden), a HitList that holds a BVHWrapper and a HitList, an empty HitList and a single-member wrapper."""
-    base = random_scene(n, n // 2, 12, seed)
-    prims = []  # (kind, row, mat, oid) in insertion order
-    for kind, data, mat, oid in base.batches:
-        for i in range(len(data)):
-            prims.append((kind, data[i], int(mat[i]), int(oid[i])))
-    rng = np.random.Generator(np.random.Philox(key=seed + 1000))
-    rng.shuffle(prims)
-    d = type(base)()
-    d.materials, d.textures = base.materials, base.textures
-    it = iter(prims)
-
-    def take(k):
-        for _ in range(k):
-            kind, row, mat, oid = next(it)
-            d.batches.append((kind, row[None, :], np.array([mat], np.int32), np.array([oid], np.int32)))
-
-    take(30)
-    d.begin_group(abi.CR_GROUP_HITLIST)
-    take(9)
-    d.end_group()
-    take(25)
-    d.begin_group(abi.CR_GROUP_BVH)
-    take(40)
-    d.end_group()
-    d.begin_group(abi.CR_GROUP_HITLIST)
-    take(3)
-    d.begin_group(abi.CR_GROUP_BVH)
-    take(17)
-    d.end_group()
-    take(1)
-    d.begin_group(abi.CR_GROUP_HITLIST)
-    take(4)
-    d.end_group()
-    d.end_group()
-    d.begin_group(abi.CR_GROUP_HITLIST)  # empty list: the empty box, never hit
-    d.end_group()
-    d.begin_group(abi.CR_GROUP_BVH)
-    take(1)
-    d.end_group()
-    take(len(prims) - 30 - 9 - 25 - 40 - 3 - 17 - 1 - 4 - 1)
-    if hidden:
-        d.hidden = [3, 33, 70, 110, 131]  # top level, inside the first list, inside the wrapper, nested wrapper, inner list
-    return d
+import golden
+from scenes_util import compare_hits, nested_scene, random_scene, scene_bounds
 
 
 def _dedupe(order):
@@ -91,6 +44,16 @@ def test_oracle_nested_hit_equals_the_flat_list(oracle):
     assert np.array_equal(a["prim_index"] >= 0, b["prim_index"] >= 0)
     hit = a["prim_index"] >= 0
     assert np.array_equal(a["t"][hit], b["t"][hit])
+
+
+def test_oracle_reproduces_the_frozen_nested_fixture(oracle):
+    """tests/golden/nested.npz (scripts/make_golden.py nested): an edit to the oracle's nested-element code cannot move the pin silently."""
+    z = golden.load("nested")
+    orc = oracle.OracleScene(nested_scene(1))
+    assert np.array_equal(orc.bvh_leaf_order(), z["leaf_order"])
+    got = orc.trace_batch(z["rays"])
+    for f in ("prim_index", "obj_id", "front_face", "material", "t", "p", "n", "u", "v"):
+        assert np.array_equal(got[f], z["hits"][f]), f
 
 
 def test_group_call_order_errors(crlib):
@@ -152,6 +115,9 @@ def test_nested_trace_is_bit_exact(gpu_device, oracle, seed):
     exp = orc.trace_batch(rays)
     got = gs.trace_batch(rays)
     compare_hits(got, exp)
+    if seed == 1:  # the frozen oracle records
+        z = golden.load("nested")
+        compare_hits(gs.trace_batch(z["rays"]), z["hits"])
     assert gs.last_retried() == 0  # scenes with nested elements stay on the reference-order engine
     assert (exp["prim_index"] >= 0).mean() > 0.05
     for p in d.hidden:
