@@ -53,6 +53,7 @@ struct CrScene {
     cudaStream_t stream = nullptr;
     // staging
     std::vector<Element> elements;
+    size_t boxed = 0;  // elements[0, boxed) have their box; the rest get it at commit (ensure_boxes: all host threads at once)
     std::vector<double> spheres;  // [n][4]
     std::vector<double> tris;     // [n][9] a,b,c
     std::vector<double> quads;    // [n][9] Q,u,v
@@ -962,25 +963,17 @@ static int64_t add_prims(CrScene* s, uint32_t kind, const double* data, size_t s
     s->mat_of[kind].resize(first_of_kind + n);
     s->obj_of[kind].resize(first_of_kind + n);
     s->prim_of[kind].resize(first_of_kind + n);
-    auto fill = [&](size_t a, size_t b) {
-        for (size_t i = a; i < b; ++i) {
-            Element& e = s->elements[first + i];
-            e.kind = kind;
-            e.idx = (uint32_t)(first_of_kind + i);
-            e.hide = false;
-            e.box = prim_box(kind, data + stride * i);
-            s->mat_of[kind][first_of_kind + i] = material ? material[i] : 0;
-            s->obj_of[kind][first_of_kind + i] = obj_id ? obj_id[i] : (int32_t)(first + i);
-            s->prim_of[kind][first_of_kind + i] = (int32_t)(first + i);
-        }
-    };
-    const size_t n_threads = n >= (1u << 18) ? std::min<size_t>(8, std::max(1u, std::thread::hardware_concurrency())) : 1;
-    if (n_threads <= 1) {
-        fill(0, n);
-    } else {
-        std::vector<std::thread> pool;
-        for (size_t t = 0; t < n_threads; ++t) pool.emplace_back(fill, n * t / n_threads, n * (t + 1) / n_threads);
-        for (auto& th : pool) th.join();
+    // the boxes (Sphere::new / Triangle::new, sphere.rs:29-30, triangle.rs:27-35) are computed at commit, for every new
+    // element at once and on all host threads: a mesh scene arrives as thousands of add calls (Scene::load_asset adds one
+    // mesh per call), and boxing them call by call on one thread cost 1.6 s of the 10 M-triangle scene's 2 s staging
+    for (size_t i = 0; i < n; ++i) {
+        Element& e = s->elements[first + i];
+        e.kind = kind;
+        e.idx = (uint32_t)(first_of_kind + i);
+        e.hide = false;
+        s->mat_of[kind][first_of_kind + i] = material ? material[i] : 0;
+        s->obj_of[kind][first_of_kind + i] = obj_id ? obj_id[i] : (int32_t)(first + i);
+        s->prim_of[kind][first_of_kind + i] = (int32_t)(first + i);
     }
     if (!s->groups.empty()) {  // member lists exist once the scene has a group
         std::vector<uint32_t>& dst = s->open_groups.empty() ? s->top : s->groups[(size_t)s->open_groups.back()].members;
@@ -1080,10 +1073,34 @@ int cr_scene_set_keyframes(CrScene* s, size_t prim_index, int point, const CrAni
     return CR_OK;
 }
 
+// Boxes of the elements added since the last commit, in parallel.
+static void ensure_boxes(CrScene* s) {
+    const size_t a0 = s->boxed, a1 = s->elements.size();
+    if (a0 >= a1) return;
+    auto fill = [&](size_t a, size_t b) {
+        for (size_t i = a; i < b; ++i) {
+            Element& e = s->elements[i];
+            const std::vector<double>& store = e.kind == CR_PRIM_SPHERE ? s->spheres : (e.kind == CR_PRIM_TRIANGLE ? s->tris : s->quads);
+            e.box = prim_box(e.kind, &store[(size_t)(e.kind == CR_PRIM_SPHERE ? 4 : 9) * e.idx]);
+        }
+    };
+    const size_t n = a1 - a0;
+    const size_t n_threads = n >= (1u << 16) ? std::min<size_t>(16, std::max(1u, std::thread::hardware_concurrency())) : 1;
+    if (n_threads <= 1) {
+        fill(a0, a1);
+    } else {
+        std::vector<std::thread> pool;
+        for (size_t t = 0; t < n_threads; ++t) pool.emplace_back(fill, a0 + n * t / n_threads, a0 + n * (t + 1) / n_threads);
+        for (auto& th : pool) th.join();
+    }
+    s->boxed = a1;
+}
+
 int cr_scene_commit(CrScene* s) {
     if (!s) return fail(CR_ERR_INVALID, "null scene");
     int rc = validate(s);
     if (rc != CR_OK) return rc;
+    ensure_boxes(s);
     if (!s->open_groups.empty()) return fail(CR_ERR_STATE, "a group is still open (cr_scene_end_group missing)");
     const bool grouped = !s->groups.empty();
     // BVHWrapper::new_wrapper: drop hidden primitives, empty -> empty HitList (bvhwrapper.rs:16-31)

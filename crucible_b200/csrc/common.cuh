@@ -290,4 +290,10 @@ __device__ __forceinline__ NodeRec<float> ldg_node32(const NodeRec<float>* p) {
 #endif
 }
 
+// Streamed-once loads (path / filter records at a lane refill): evict-first, so the lines of the scene stay resident.
+// (ld.global.L1::no_allocate was measured too: 4 % SLOWER on book1 and Cornell — the refill's second access to the same
+// record line, direction after origin, then misses.)
+__device__ __forceinline__ int4 ld_stream16(const void* p) { return __ldcs(reinterpret_cast<const int4*>(p)); }
+__device__ __forceinline__ double ld_stream8(const double* p) { return __ldcs(p); }
+
 }  // namespace crb

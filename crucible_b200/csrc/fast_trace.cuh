@@ -36,24 +36,23 @@ namespace crb {
 
 enum : int { FS_IDLE = 0, FS_INNER = 1, FS_LEAF = 2, FS_DONE = 3, FS_RETRY = 4 };
 static constexpr int FAST_STACK = 64;       // the builder bounds the tree depth (FAST_MAX_DEPTH)
-static constexpr int FAST_SMEM_LEVELS = 8;  // stack levels kept in shared memory; deeper ones (rare) in local memory
+static constexpr int FAST_SMEM_LEVELS = 8;  // stack levels kept in shared memory (template default); deeper ones (rare) in local memory
 
 // Per-CTA lane table, SoA over the lanes (conflict free), as LaneSlots of the reference-order engine, plus the bottom of
 // every lane's traversal stack: lanes of a warp sit at different stack depths, so a local-memory stack costs one L1
 // wavefront per distinct depth and access (ncu: 52 % of the kernel's L1 data-pipe traffic); [level][lane] in shared
 // memory is one conflict-free wavefront whatever the depths.
-template <typename R, int BLOCK>
+template <typename R, int BLOCK, int LEVELS = FAST_SMEM_LEVELS>
 struct FastSlots {
     R best_t[BLOCK];
-    R ray[6][BLOCK];
-    float pre[7][BLOCK];
+    R ray[6][BLOCK];  // (the f32 ray of the sphere pre-filter is converted from this one when a leaf needs it)
     // the box-test constants of the lane's ray (FastRay in 9 words: o*inv, the per-axis error band, 1/d).  They are read
     // into registers at the start of every INNER slice and are dead in the LEAF phase, so the f64 leaf arithmetic does
     // not push them into local memory (the 64-register build used to reload 4 of them per inner step)
     float fray[9][BLOCK];
     uint32_t best_ref[BLOCK], best_rank[BLOCK], my[BLOCK];
-    uint32_t stk_ref[FAST_SMEM_LEVELS][BLOCK];
-    float stk_lo[FAST_SMEM_LEVELS][BLOCK];
+    uint32_t stk_ref[LEVELS][BLOCK];
+    float stk_lo[LEVELS][BLOCK];
 };
 
 // Conservative f32 slab test of one child box: a lower bound of the entry parameter (clamped to tmin) and "certainly
@@ -109,7 +108,28 @@ __device__ __forceinline__ bool ref_box_span(const NodeRec<R>& n, V3<R> o, V3<R>
 // 32-bit window offsets; the records are read-only after the copy, so plain (non-volatile) ld.shared is safe.
 struct SmemTree {
     uint32_t nodes, prims, spheres32;  // shared-window byte addresses
+    // the primitive records of the leaf tests (R precision) and, per leaf-table entry, the box of the primitive's
+    // REFERENCE leaf node (the candidate confirmation): with these the kernel reads no scene data from global memory
+    uint32_t spheres, tris, quads, leafbox;
 };
+// box of a reference leaf node, padded to whole 16 B words
+template <typename R> struct __align__(16) LeafBox {
+    R xmin, xmax, ymin, ymax, zmin, zmax;
+    R pad[sizeof(R) == 8 ? 0 + 0 : 2];
+};
+template <> struct __align__(16) LeafBox<double> {
+    double xmin, xmax, ymin, ymax, zmin, zmax;
+};
+template <typename T>
+static __device__ __forceinline__ T lds_rec(uint32_t addr) {
+    static_assert(sizeof(T) % 16 == 0, "record = whole 16 B words");
+    T out;
+    uint4* d = reinterpret_cast<uint4*>(&out);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(T) / 16); ++i)
+        asm("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(d[i].x), "=r"(d[i].y), "=r"(d[i].z), "=r"(d[i].w) : "r"(addr + 16u * (uint32_t)i));
+    return out;
+}
 static __device__ __forceinline__ NodeRec<float> lds_node32(uint32_t addr) {
     NodeRec<float> n;
     asm("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=f"(n.xmin), "=f"(n.xmax), "=f"(n.ymin), "=f"(n.ymax) : "r"(addr));
@@ -127,9 +147,9 @@ static __device__ __forceinline__ SphereRec<float> lds_sphere32(uint32_t addr) {
     return s;
 }
 
-template <typename R, int BLOCK, bool SMEM>
+template <typename R, int BLOCK, bool SMEM, int LEVELS = FAST_SMEM_LEVELS>
 struct FastTrav {
-    FastSlots<R, BLOCK>* s;
+    FastSlots<R, BLOCK, LEVELS>* s;
     SmemTree tree;  // SMEM builds only
     __device__ __forceinline__ uint2 leaf_entry(const DevScene<R>& sc, uint32_t k) const {
         if constexpr (SMEM) return lds_u2(tree.prims + k * 8u);
@@ -148,12 +168,12 @@ struct FastTrav {
     uint32_t* deep_ref;
     float* deep_lo;
     __device__ __forceinline__ void push(uint32_t ref, float lo) {
-        if (sp < FAST_SMEM_LEVELS) {
+        if (sp < LEVELS) {
             s->stk_ref[sp][threadIdx.x] = ref;
             s->stk_lo[sp][threadIdx.x] = lo;
         } else if (sp < FAST_STACK) {
-            deep_ref[sp - FAST_SMEM_LEVELS] = ref;
-            deep_lo[sp - FAST_SMEM_LEVELS] = lo;
+            deep_ref[sp - LEVELS] = ref;
+            deep_lo[sp - LEVELS] = lo;
         }
         ++sp;
     }
@@ -166,8 +186,6 @@ struct FastTrav {
         s->fray[0][t] = f.oix; s->fray[1][t] = f.oiy; s->fray[2][t] = f.oiz;
         s->fray[3][t] = ex; s->fray[4][t] = ey; s->fray[5][t] = ez;
         s->fray[6][t] = f.ix; s->fray[7][t] = f.iy; s->fray[8][t] = f.iz;
-        s->pre[0][t] = f.ox; s->pre[1][t] = f.oy; s->pre[2][t] = f.oz; s->pre[3][t] = f.dx; s->pre[4][t] = f.dy; s->pre[5][t] = f.dz;
-        s->pre[6][t] = f.o2;
         s->best_t[t] = tmax;
         s->best_ref[t] = REF_MISS;
         s->best_rank[t] = 0xFFFFFFFFu;
@@ -206,9 +224,9 @@ struct FastTrav {
     __device__ __forceinline__ int pop() {
         while (sp > 0) {
             --sp;
-            const float lo = sp < FAST_SMEM_LEVELS ? s->stk_lo[sp][threadIdx.x] : deep_lo[sp - FAST_SMEM_LEVELS];
+            const float lo = sp < LEVELS ? s->stk_lo[sp][threadIdx.x] : deep_lo[sp - LEVELS];
             if (!(lo > best_m)) {
-                cur = sp < FAST_SMEM_LEVELS ? s->stk_ref[sp][threadIdx.x] : deep_ref[sp - FAST_SMEM_LEVELS];
+                cur = sp < LEVELS ? s->stk_ref[sp][threadIdx.x] : deep_ref[sp - LEVELS];
                 return (cur & FAST_LEAF) ? (int)FS_LEAF : (int)FS_INNER;
             }
         }
@@ -250,7 +268,11 @@ struct FastTrav {
             const uint32_t r0 = leaf_entry(sc, first).x, r1 = cnt > 1u ? leaf_entry(sc, first + 1u).x : r0;
             if (ref_kind(r0) != CR_PRIM_SPHERE || ref_kind(r1) != CR_PRIM_SPHERE) return false;  // before touching the lane table
             const int t = threadIdx.x;
-            const PreRay pre = {s->pre[0][t], s->pre[1][t], s->pre[2][t], s->pre[3][t], s->pre[4][t], s->pre[5][t], s->pre[6][t]};
+            // FilterRay's f32 copy of the ray (make_filter_ray), rebuilt from the lane's R-precision ray
+            PreRay pre;
+            pre.ox = (float)s->ray[0][t]; pre.oy = (float)s->ray[1][t]; pre.oz = (float)s->ray[2][t];
+            pre.dx = (float)s->ray[3][t]; pre.dy = (float)s->ray[4][t]; pre.dz = (float)s->ray[5][t];
+            pre.o2 = pre.ox * pre.ox + pre.oy * pre.oy + pre.oz * pre.oz;
             if (!sphere_definite_miss(sphere32(sc, ref_index(r0)), pre)) return false;
             return cnt == 1u || sphere_definite_miss(sphere32(sc, ref_index(r1)), pre);
         } else {
@@ -268,10 +290,30 @@ struct FastTrav {
         for (uint32_t k = 0; k < cnt; ++k) {
             const uint2 e = leaf_entry(sc, first + k);
             R c;
-            if (!Trav<R, RegStore<R>, false>::test_prim(sc, e.x, o, d, a, tmin, tmax, R(0), c)) continue;
+            if constexpr (SMEM) {
+                const uint32_t kind = ref_kind(e.x), idx = ref_index(e.x);
+                bool hit;
+                if (kind == CR_PRIM_SPHERE) {
+                    hit = sphere_hit_t(lds_rec<SphereRec<R>>(tree.spheres + idx * (uint32_t)sizeof(SphereRec<R>)), o, d, a, tmin, tmax, c);
+                } else if (kind == CR_PRIM_TRIANGLE) {
+                    hit = tri_hit_t(lds_rec<TriRec<R>>(tree.tris + idx * (uint32_t)sizeof(TriRec<R>)), o, d, tmin, tmax, c);
+                } else {
+                    R al, be;
+                    hit = quad_hit_t(lds_rec<QuadRec<R>>(tree.quads + idx * (uint32_t)sizeof(QuadRec<R>)), o, d, tmin, tmax, c, al, be);
+                }
+                if (!hit) continue;
+            } else {
+                if (!Trav<R, RegStore<R>, false>::test_prim(sc, e.x, o, d, a, tmin, tmax, R(0), c)) continue;
+            }
             if constexpr (sizeof(R) == 8) {
                 if (!(c < best || (c == best && e.y < brank))) continue;
-                const NodeRec<R> n = ldg_rec<sizeof(NodeRec<R>) / 16>(sc.nodes + (e.y >> 1));
+                NodeRec<R> n;
+                if constexpr (SMEM) {
+                    const LeafBox<R> lb = lds_rec<LeafBox<R>>(tree.leafbox + (first + k) * (uint32_t)sizeof(LeafBox<R>));
+                    n.xmin = lb.xmin; n.xmax = lb.xmax; n.ymin = lb.ymin; n.ymax = lb.ymax; n.zmin = lb.zmin; n.zmax = lb.zmax;
+                } else {
+                    n = ldg_rec<sizeof(NodeRec<R>) / 16>(sc.nodes + (e.y >> 1));
+                }
                 const V3<R> inv = {R(1) / d.x, R(1) / d.y, R(1) / d.z};  // adinv, bvh.rs:111
                 R entry;
                 if (!ref_box_span(n, o, inv, tmin, entry)) continue;  // the reference never tests this primitive
@@ -309,17 +351,17 @@ static __device__ __forceinline__ uint32_t fast_warp_append(uint32_t* counter, b
     return base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
 }
 
-template <typename R, int BLOCK, bool SMEM, typename IO>
-__device__ __forceinline__ void fast_trace_persistent(const DevScene<R>& sc, R tmin, R tmax, IO& io, FastSlots<R, BLOCK>* slots,
-                                                      uint32_t* retry_list, uint32_t* retry_count, SmemTree tree = SmemTree{0u, 0u, 0u}) {
+template <typename R, int BLOCK, bool SMEM, int LEVELS = FAST_SMEM_LEVELS, typename IO>
+__device__ __forceinline__ void fast_trace_persistent(const DevScene<R>& sc, R tmin, R tmax, IO& io, FastSlots<R, BLOCK, LEVELS>* slots,
+                                                      uint32_t* retry_list, uint32_t* retry_count, SmemTree tree = SmemTree{}) {
     const int NODE_SLICE = sc.node_slice;
     const int REFILL = sc.refill;
     const uint32_t n = io.count();
     const int lane = threadIdx.x & 31;
     const float tmin32 = (float)tmin;
-    uint32_t deep_ref[FAST_STACK - FAST_SMEM_LEVELS];
-    float deep_lo[FAST_STACK - FAST_SMEM_LEVELS];
-    FastTrav<R, BLOCK, SMEM> tv;
+    uint32_t deep_ref[FAST_STACK - LEVELS];
+    float deep_lo[FAST_STACK - LEVELS];
+    FastTrav<R, BLOCK, SMEM, LEVELS> tv;
     tv.s = slots;
     tv.tree = tree;
     tv.deep_ref = deep_ref;
@@ -406,7 +448,7 @@ __device__ __forceinline__ void fast_trace_warp_batch(const DevScene<R>& sc, R t
     float deep_lo[FAST_STACK - FAST_SMEM_LEVELS];
     FastTrav<R, BLOCK, false> tv;
     tv.s = slots;
-    tv.tree = SmemTree{0u, 0u, 0u};
+    tv.tree = SmemTree{};
     tv.deep_ref = deep_ref;
     tv.deep_lo = deep_lo;
     tv.cur = 0u;

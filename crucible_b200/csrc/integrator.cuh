@@ -367,23 +367,23 @@ struct RenderTraceIO {
         FilterRec r;
         const int4* s = reinterpret_cast<const int4*>(filt + path_of(k));
         int4* d = reinterpret_cast<int4*>(&r);
-        d[0] = __ldcs(s); d[1] = __ldcs(s + 1); d[2] = __ldcs(s + 2);  // streamed once: keep the L1 for the scene
+        d[0] = ld_stream16(s); d[1] = ld_stream16(s + 1); d[2] = ld_stream16(s + 2);  // streamed once: keep the L1 for the scene
         return unpack_filter(r);
     }
     __device__ __forceinline__ void load(uint32_t k, V3<R>& o, V3<R>& d) const {
         const PathRec<R>* p = paths + path_of(k);  // sectors A and B of the record: origin + direction
         if constexpr (sizeof(R) == 8) {
-            const double2 a = __ldcs(reinterpret_cast<const double2*>(&p->ox));
-            const double b = __ldcs(&p->oz);
-            const double2 c = __ldcs(reinterpret_cast<const double2*>(&p->dx));
-            const double e = __ldcs(&p->dz);
-            o = {a.x, a.y, b};
-            d = {c.x, c.y, e};
+            const int4 a = ld_stream16(&p->ox);
+            const double b = ld_stream8(&p->oz);
+            const int4 c = ld_stream16(&p->dx);
+            const double e = ld_stream8(&p->dz);
+            o = {__hiloint2double(a.y, a.x), __hiloint2double(a.w, a.z), b};
+            d = {__hiloint2double(c.y, c.x), __hiloint2double(c.w, c.z), e};
         } else {
-            const float4 a = __ldcs(reinterpret_cast<const float4*>(&p->ox));
-            const float4 b = __ldcs(reinterpret_cast<const float4*>(&p->dx));
-            o = {a.x, a.y, a.z};
-            d = {b.x, b.y, b.z};
+            const int4 a = ld_stream16(&p->ox);
+            const int4 b = ld_stream16(&p->dx);
+            o = {__int_as_float(a.x), __int_as_float(a.y), __int_as_float(a.z)};
+            d = {__int_as_float(b.x), __int_as_float(b.y), __int_as_float(b.z)};
         }
     }
     __device__ __forceinline__ R time(uint32_t k) const { return paths[path_of(k)].tm; }  // ray_casting.rs:84
@@ -436,38 +436,64 @@ __global__ void __launch_bounds__(TRACE_BLOCK, MINB) k_trace_fast(DevScene<R> sc
 // Small scenes: the same engine with the search tree in shared memory (SmemTree, fast_trace.cuh).  One CTA of 28 warps
 // per SM (the 72-register budget of the default build) so that the SM holds one copy of the tree.
 static constexpr int FAST_BIG_BLOCK = 896;
+static constexpr int FAST_BIG_LEVELS = 6;  // stack levels per lane in the lane table (deeper: local memory)
 static constexpr size_t FAST_SMEM_LIMIT = 227u * 1024u;
+struct FastSmemLayout {
+    uint32_t nodes, prims, spheres32, spheres, tris, quads, leafbox, total;
+};
 template <typename R>
-static size_t fast_smem_bytes(uint32_t n_fast_nodes, uint32_t n_fast_prims, uint32_t n_spheres) {
-    auto up = [](size_t b) { return (b + 127) & ~(size_t)127; };
-    return up(sizeof(FastSlots<R, FAST_BIG_BLOCK>)) + up((size_t)n_fast_nodes * 64) + up((size_t)n_fast_prims * 8) + up((size_t)n_spheres * 16);
+static __host__ __device__ FastSmemLayout fast_smem_layout(uint32_t n_fast_nodes, uint32_t n_fast_prims, uint32_t n_sph, uint32_t n_tri, uint32_t n_quad) {
+    auto up = [](uint32_t b) { return (b + 127u) & ~127u; };
+    FastSmemLayout l;
+    l.nodes = up((uint32_t)sizeof(FastSlots<R, FAST_BIG_BLOCK, FAST_BIG_LEVELS>));
+    l.prims = l.nodes + up(n_fast_nodes * 64u);
+    l.spheres32 = l.prims + up(n_fast_prims * 8u);
+    l.spheres = l.spheres32 + up(n_sph * 16u);
+    l.tris = l.spheres + up(n_sph * (uint32_t)sizeof(SphereRec<R>));
+    l.quads = l.tris + up(n_tri * (uint32_t)sizeof(TriRec<R>));
+    l.leafbox = l.quads + up(n_quad * (uint32_t)sizeof(QuadRec<R>));
+    l.total = l.leafbox + up(n_fast_prims * (uint32_t)sizeof(LeafBox<R>));
+    return l;
 }
 template <typename R>
 __global__ void __launch_bounds__(FAST_BIG_BLOCK, 1) k_trace_fast_smem(DevScene<R> sc, PathRec<R>* __restrict__ paths, Control* __restrict__ ctl,
                                                                        int side, uint2* __restrict__ queues, const FilterRec* __restrict__ filt,
                                                                        uint32_t pool, uint32_t* __restrict__ retry_list, uint32_t n_fast_nodes,
-                                                                       uint32_t n_fast_prims, uint32_t n_spheres) {
+                                                                       uint32_t n_fast_prims, uint32_t n_sph, uint32_t n_tri, uint32_t n_quad) {
     extern __shared__ __align__(128) unsigned char fast_smem[];
     if (ctl->n_in[side] == 0u) return;  // nothing to trace: skip the copy of the tree
-    auto up = [](uint32_t b) { return (b + 127u) & ~127u; };
-    FastSlots<R, FAST_BIG_BLOCK>* slots = reinterpret_cast<FastSlots<R, FAST_BIG_BLOCK>*>(fast_smem);
-    const uint32_t o_nodes = up((uint32_t)sizeof(FastSlots<R, FAST_BIG_BLOCK>)), o_prims = o_nodes + up(n_fast_nodes * 64u),
-                   o_sph = o_prims + up(n_fast_prims * 8u);
+    typedef FastSlots<R, FAST_BIG_BLOCK, FAST_BIG_LEVELS> Slots;
+    Slots* slots = reinterpret_cast<Slots*>(fast_smem);
+    const FastSmemLayout l = fast_smem_layout<R>(n_fast_nodes, n_fast_prims, n_sph, n_tri, n_quad);
     {
-        int4* dn = reinterpret_cast<int4*>(fast_smem + o_nodes);
-        const int4* sn = reinterpret_cast<const int4*>(sc.fast_nodes);
-        for (uint32_t i = threadIdx.x; i < n_fast_nodes * 4u; i += blockDim.x) dn[i] = __ldg(sn + i);
-        uint2* dp = reinterpret_cast<uint2*>(fast_smem + o_prims);
-        for (uint32_t i = threadIdx.x; i < n_fast_prims; i += blockDim.x) dp[i] = __ldg(sc.fast_prims + i);
-        int4* ds = reinterpret_cast<int4*>(fast_smem + o_sph);
-        const int4* ss = reinterpret_cast<const int4*>(sc.spheres32);
-        for (uint32_t i = threadIdx.x; i < n_spheres; i += blockDim.x) ds[i] = __ldg(ss + i);
+        auto copy16 = [&](uint32_t dst_off, const void* src, uint32_t n16) {
+            int4* d = reinterpret_cast<int4*>(fast_smem + dst_off);
+            const int4* s = reinterpret_cast<const int4*>(src);
+            for (uint32_t i = threadIdx.x; i < n16; i += blockDim.x) d[i] = __ldg(s + i);
+        };
+        copy16(l.nodes, sc.fast_nodes, n_fast_nodes * 4u);
+        uint2* dp = reinterpret_cast<uint2*>(fast_smem + l.prims);
+        LeafBox<R>* db = reinterpret_cast<LeafBox<R>*>(fast_smem + l.leafbox);
+        for (uint32_t i = threadIdx.x; i < n_fast_prims; i += blockDim.x) {
+            const uint2 e = __ldg(sc.fast_prims + i);
+            dp[i] = e;
+            const NodeRec<R>* n = sc.nodes + (e.y >> 1);  // the primitive's reference leaf node: its box confirms candidates
+            LeafBox<R> b;
+            b.xmin = n->xmin; b.xmax = n->xmax; b.ymin = n->ymin; b.ymax = n->ymax; b.zmin = n->zmin; b.zmax = n->zmax;
+            db[i] = b;
+        }
+        copy16(l.spheres32, sc.spheres32, n_sph);
+        copy16(l.spheres, sc.spheres, n_sph * (uint32_t)(sizeof(SphereRec<R>) / 16));
+        copy16(l.tris, sc.tris, n_tri * (uint32_t)(sizeof(TriRec<R>) / 16));
+        copy16(l.quads, sc.quads, n_quad * (uint32_t)(sizeof(QuadRec<R>) / 16));
     }
     __syncthreads();
     const uint32_t base = (uint32_t)__cvta_generic_to_shared(fast_smem);
     RenderTraceIO<R> io{sc, paths, ctl, queues, filt, ctl->n_in[side], pool, nullptr, &ctl->trace_next};
-    fast_trace_persistent<R, FAST_BIG_BLOCK, true>(sc, R(0.001), Num<R>::inf(), io, slots, retry_list, &ctl->retry_count,
-                                                   SmemTree{base + o_nodes, base + o_prims, base + o_sph});
+    SmemTree tree;
+    tree.nodes = base + l.nodes; tree.prims = base + l.prims; tree.spheres32 = base + l.spheres32; tree.spheres = base + l.spheres;
+    tree.tris = base + l.tris; tree.quads = base + l.quads; tree.leafbox = base + l.leafbox;
+    fast_trace_persistent<R, FAST_BIG_BLOCK, true, FAST_BIG_LEVELS>(sc, R(0.001), Num<R>::inf(), io, slots, retry_list, &ctl->retry_count, tree);
 }
 
 // fixed-point accumulation: order independent => bit-reproducible for any schedule and GPU count
@@ -1093,11 +1119,15 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
                                  animated ? k_trace<R, CRB_REFILL, 8, true> : k_trace<R, CRB_REFILL, 10, false>};
     const int trace_grids[2] = {persistent_grid(trace_variants[0], TRACE_BLOCK, s.num_sms),
                                 persistent_grid(trace_variants[1], TRACE_BLOCK, s.num_sms)};
-    // Three ways to trace a wavefront, all with the reference's results: the reference-order kernel at two register budgets
-    // (0: 64 registers, 1: 48 registers / more warps) and the order-free engine (2).  Which is fastest depends on the scene
-    // (meshes: the order-free engine by 1.3-2.6x; a few hundred spheres or 18 quads: reference order), so the first mixed
-    // wavefront of a scene is traced with every candidate (same rays, same result, k_trace_rewind between) and the
-    // fastest kept; the choice is cached per device by scene signature.  CRB_TRAVERSAL / CRB_MINB pin a candidate.
+    // Four ways to trace a wavefront, all with the reference's results: the reference-order kernel at two register budgets
+    // (0: 64 registers, 1: 48 registers / more warps), the order-free engine (2) and its shared-memory build for small
+    // scenes (3).  On every BASELINE config the order-free engine wins on mixed wavefronts (book1 1.3x, Cornell 1.3x, teapot
+    // 1.5x, 10 M triangles 2.7x); only a wavefront of pure camera rays favours reference order, which made a one-wavefront
+    // timing pick the wrong engine for short renders.  So: scenes with a search tree use the order-free engine (shared-memory
+    // build when it fits) and fall back to reference order only if it hands back more than 5 % of its rays; scenes without
+    // one (object keyframes, nested elements, CR_RENDER_REFERENCE_ORDER) time the two reference-order builds on their first
+    // mixed wavefront (same rays, same result, k_trace_rewind between) and cache the choice per device by scene signature.
+    // CRB_TRAVERSAL / CRB_MINB pin a candidate.
     const uint64_t signature = scene_signature(s, (sizeof(R) == 8 ? 0 : 1) | (fast_ok ? 2 : 0));
     int variant = ws.lookup_variant(signature);
     if (const char* e = getenv("CRB_MINB")) variant = atoi(e) <= 8 ? 0 : 1;
@@ -1106,7 +1136,7 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
     }
     if (variant == 2 && !fast_ok) variant = -1;
     // (3: the order-free engine with the search tree in shared memory, for scenes small enough)
-    const size_t smem_need = fast_smem_bytes<R>(s.n_fast_nodes, s.n_fast_prims, s.n_prims[0]);
+    const size_t smem_need = fast_smem_layout<R>(s.n_fast_nodes, s.n_fast_prims, s.n_prims[0], s.n_prims[1], s.n_prims[2]).total;
     bool smem_ok = fast_ok && s.n_fast_nodes != 0u && smem_need <= FAST_SMEM_LIMIT;
     if (smem_ok && cudaFuncSetAttribute(k_trace_fast_smem<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_need) != cudaSuccess) {
         cudaGetLastError();
@@ -1116,19 +1146,17 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
         if (e[0] == 's' && smem_ok) variant = 3;
     }
     if (variant == 3 && !smem_ok) variant = -1;
-    // the shared-memory build is the order-free engine with cheaper node fetches (A/B on one box: book1 -7 %, Cornell -4 %
-    // trace time), so where it fits it stands in for candidate 2 instead of being timed against it on one wavefront
-    int cands[3], n_cands = 0;
+    int cands[2], n_cands = 0;
     cands[n_cands++] = 0;
     if (!animated) cands[n_cands++] = 1;
-    if (fast_ok) cands[n_cands++] = smem_ok ? 3 : 2;
+    if (fast_ok && variant < 0) variant = smem_ok ? 3 : 2;
     const uint64_t tune_at = total >= 2ull * pool ? 1 : 0;  // the second wavefront mixes bounce rays with camera rays
     bool tuning = variant < 0 && total >= (1ull << 20) && n_cands > 1;
     if (variant < 0) variant = fast_ok ? (smem_ok ? 3 : 2) : (animated ? 0 : 1);
     auto launch_trace = [&](int v, int cur) {
         if (v == 3) {
             k_trace_fast_smem<R><<<s.num_sms, FAST_BIG_BLOCK, smem_need, stream>>>(sc, paths[cur], ctl, cur, queues, filt[cur], pool, retry_list,
-                                                                                  s.n_fast_nodes, s.n_fast_prims, s.n_prims[0]);
+                                                                                  s.n_fast_nodes, s.n_fast_prims, s.n_prims[0], s.n_prims[1], s.n_prims[2]);
             trace_variants[0]<<<s.num_sms * 2, TRACE_BLOCK, 0, stream>>>(sc, paths[cur], ctl, cur, queues, filt[cur], pool, retry_list);
             return 2;
         }
@@ -1181,6 +1209,8 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
     // GPU always has work queued while the host decides whether the render is finished
     constexpr int RING = 8, LAG = 3;
     volatile uint32_t* h_n_in = reinterpret_cast<volatile uint32_t*>(pin + 3584);
+    volatile uint32_t* h_retried = reinterpret_cast<volatile uint32_t*>(pin + 3584 + 64);  // retry_total as of the same iteration
+    uint64_t traced_known = 0;
     uint32_t* d_n_in_ring = reinterpret_cast<uint32_t*>(pin + 3584);  // plan writes through zero-copy? no: device copy below
     (void)d_n_in_ring;
     cudaEvent_t ring_ev[RING];
@@ -1201,7 +1231,7 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
     while (!done) {
         const int cur = (int)(it & 1), nxt = cur ^ 1;
         if (tuning && it == tune_at) {
-            cudaEvent_t te[6];
+            cudaEvent_t te[4];
             for (auto& e : te) CRB_CUDA(events.make(&e));
             for (int c = 0; c < n_cands; ++c) {
                 CRB_CUDA(cudaEventRecord(te[2 * c], stream));
@@ -1262,6 +1292,7 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
 
         const int slot = (int)(it % RING);
         CRB_CUDA(cudaMemcpyAsync((void*)(h_n_in + slot), &ctl->n_in[nxt], sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+        if (variant >= 2) CRB_CUDA(cudaMemcpyAsync((void*)(h_retried + slot), &ctl->retry_total, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
         CRB_CUDA(cudaEventRecord(ring_ev[slot], stream));
         ++it;
         if (it >= (uint64_t)LAG) {
@@ -1272,6 +1303,10 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
                                    left, (unsigned long long)(it - LAG + 1));
             if (left < pool) samples_out = true;
             small_wave = left < (1u << 18);
+            traced_known += left;
+            // safety valve: a scene whose rays the order-free engine keeps handing back (irregular rays: exact zero direction
+            // components, e.g. axis-parallel beams between axis-aligned mirrors) is better off in reference order throughout
+            if (variant >= 2 && traced_known >= (1u << 16) && (uint64_t)h_retried[old] * 20u > traced_known) variant = animated ? 0 : 1;
             if (left == 0) done = true;  // nothing left to trace after iteration it-LAG (k_tail took over, or every path ended)
         }
         if (it > 100000000ull) {

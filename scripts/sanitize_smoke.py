@@ -36,3 +36,22 @@ with tempfile.TemporaryDirectory() as tmp:
     g = GpuScene(sc.describe(), 0)
     gpu.render_frames(g, sc.scene_cam.to_abi(), tmp, 3, 0, 1, seed=1, fmt=abi.CR_PPM_P6)
 print("sanitize smoke ok:", st["rays"], "rays")
+# round 2: every trace engine pinned in turn (order-free in shared / global memory, reference order), nested elements
+import os
+
+from scenes_util import nested_scene
+
+sc = demo_builder.book1_end_scene(image_width=96, samples=3, seed=1)
+gs, cam = GpuScene(sc.describe(), 0), sc.scene_cam.to_abi()
+for env in ({"CRB_TRAVERSAL": "s"}, {"CRB_TRAVERSAL": "f"}, {"CRB_TRAVERSAL": "r", "CRB_MINB": "8"}, {"CRB_TRAVERSAL": "r", "CRB_MINB": "10"}):
+    for k in ("CRB_TRAVERSAL", "CRB_MINB"):
+        os.environ.pop(k, None)
+    os.environ.update(env)
+    img, _, st2 = gs.render(cam, seed=1)
+    assert np.array_equal(img, r64), env
+for k in ("CRB_TRAVERSAL", "CRB_MINB"):
+    os.environ.pop(k, None)
+n = GpuScene(nested_scene(1), 0)
+n.trace_batch(rays)
+n.render(cam, seed=1)
+print("round-2 engines ok")

@@ -28,6 +28,13 @@ def test_library_exports_every_declared_symbol(crlib):
     assert b"sm_100a" in crlib.cr_version()
 
 
+def test_integration_doc_binds_every_entry_point():
+    """INTEGRATION.md shows the reference-side binding (the Rust `extern "C"` block): it names exactly the header's entry points."""
+    declared = set(re.findall(r"\b(cr_[a-z0-9_]+)\s*\(", open(HEADER).read()))
+    bound = set(re.findall(r"pub fn (cr_[a-z0-9_]+)\(", open(os.path.join(ROOT, "INTEGRATION.md")).read()))
+    assert bound == declared, bound ^ declared
+
+
 def test_ctypes_layout_matches_header():
     structs = {"CrMaterial": abi.CrMaterial, "CrTexture": abi.CrTexture, "CrKeyframe": abi.CrKeyframe, "CrCamera": abi.CrCamera,
                "CrRenderOpts": abi.CrRenderOpts, "CrStats": abi.CrStats, "CrHit": abi.CrHit}
