@@ -130,7 +130,10 @@ def sized_oracle_sample(desc, cam, seconds, threads):
     """Probe with the two rows at 1/3 and 2/3 of the image height, then size an evenly spread row sample for about
     `seconds` of CPU work (at least one row: Cornell's 1000 spp make a single row 1 M samples)."""
     H, W = cam.image_height, cam.image_width
-    probe = oracle_sample(desc, cam, max(1, H // 3), threads, first_row=H // 3)
+    # the probe needs a row per thread and more, or it measures thread start-up (two rows on 16 threads
+    # underestimated the rate 4x and the sized sample then ran 1.7 s instead of 15 s)
+    probe_step = max(1, H // max(2 * threads, 8))
+    probe = oracle_sample(desc, cam, probe_step, threads, first_row=probe_step // 2)
     rate = probe["samples"] / max(probe["seconds"], 1e-6)
     n_rows = max(1.0, rate * seconds / (W * cam.samples))
     row_step = int(max(1, min(H, round(H / n_rows))))
