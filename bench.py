@@ -381,7 +381,9 @@ def main():
                         "survey_8d_view": hbm_view}
             hbm_view = line_hbm
         main_view, other = (hbm_view, fp_view) if cfg["bound"] == "hbm" else (fp_view, hbm_view)
-        line["roofline"] = dict(main_view, kernel="k_trace", traffic=traffic, traffic_source=traffic_src,
+        kernel_name = {0: "k_trace (reference order, 64 registers)", 1: "k_trace (reference order, 48 registers)", 2: "k_trace_fast", 3: "k_trace_fast_smem"}.get(
+            stats[-1].get("trace_engine") if stats else None, "k_trace")
+        line["roofline"] = dict(main_view, kernel=kernel_name, traffic=traffic, traffic_source=traffic_src,
                                 algorithmic_bytes_per_launch=per_seg_bytes * seg_per_launch, flops_per_segment=per_seg_flops,
                                 bytes_per_segment=per_seg_bytes, segments_per_launch=seg_per_launch, avg_launch_ms=dur_s * 1e3,
                                 kernel_share_of_step=ms_trace / max(my_ms, 1e-9), ms_trace=ms_trace / args.steps, ms_shade=ms_shade / args.steps,
