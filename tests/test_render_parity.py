@@ -79,6 +79,27 @@ def test_every_trace_engine_gives_the_same_image(gpu_device, oracle, name, kw, m
     assert np.abs(images[3] - ref).max() <= TOL_F64
 
 
+@pytest.mark.parametrize("seed,n_sph,n_tri,n_quad", [(11, 120, 0, 0), (12, 40, 150, 10), (13, 0, 260, 0), (14, 5, 5, 30), (15, 300, 200, 24)])
+def test_random_small_scenes_through_the_shared_memory_build(gpu_device, oracle, seed, n_sph, n_tri, n_quad):
+    """Mixed primitive soups small enough for k_trace_fast_smem (every record of the scene in shared memory): the default
+    render uses that build, equals the reference-order render bit for bit and the oracle to 1e-11, at two pool sizes."""
+    from scenes_util import random_scene
+
+    d = random_scene(n_sph, n_tri, n_quad, seed)
+    cam = demo_builder.book1_end_scene(image_width=112, samples=6).scene_cam
+    cam.look_from, cam.look_at = np.array([16.0, 7.0, 21.0]), np.array([0.0, 0.0, 0.0])
+    cam = cam.to_abi()
+    gs, orc = GpuScene(d, gpu_device), oracle.OracleScene(d)
+    rgb, _, st = gs.render(cam, seed=seed)
+    assert st["trace_engine"] == 3 and st["retried_rays"] <= st["rays"] // 1000
+    ref, _, ost = orc.render(cam, seed=seed)
+    assert st["rays"] == ost["rays"]
+    assert np.abs(rgb - ref).max() <= TOL_F64
+    ro, _, _ = gs.render(cam, seed=seed, reference_order=True)
+    small, _, _ = gs.render(cam, seed=seed, pool_paths=2048)
+    assert np.array_equal(ro, rgb) and np.array_equal(small, rgb)
+
+
 def test_f64_render_is_reproducible_and_pool_independent(gpu_device, oracle):
     sc = demo_builder.book1_end_scene(image_width=128, samples=6)
     gs, orc, cam = _both(sc, gpu_device, oracle)
