@@ -107,6 +107,7 @@ SIGNATURES = {
     "cr_device_trim": (C.c_int, [C.c_int]),
     "cr_last_error": (C.c_char_p, []),
     "cr_version": (C.c_char_p, []),
+    "cr_scene_reserve": (C.c_int, [_P, C.c_size_t, C.c_size_t, C.c_size_t]),
     "cr_scene_add_spheres": (C.c_int64, [_P, _P, _P, _P, C.c_size_t]),
     "cr_scene_add_triangles": (C.c_int64, [_P, _P, _P, _P, C.c_size_t]),
     "cr_scene_add_quads": (C.c_int64, [_P, _P, _P, _P, C.c_size_t]),

@@ -19,6 +19,7 @@
 
 #include "bvh_host.h"
 #include "fast_tree.h"
+#include "h2d_staged.h"
 #include "integrator.h"
 
 using namespace crb;
@@ -40,7 +41,7 @@ int fail(int code, const std::string& msg) {
 
 struct HostImage {
     int w, h;
-    std::vector<uint8_t> rgb;
+    HostVec<uint8_t> rgb;  // a 4096 x 2048 sky is 25 MB: cached block (host_pool.h)
     cudaArray_t arr = nullptr;
     cudaTextureObject_t tex = 0;
 };
@@ -52,12 +53,12 @@ struct CrScene {
     int num_sms = 148;
     cudaStream_t stream = nullptr;
     // staging
-    std::vector<Element> elements;
+    ElementVec elements;  // the big staging arrays are HostVec: their blocks are cached between scenes (host_pool.h)
     size_t boxed = 0;  // elements[0, boxed) have their box; the rest get it at commit (ensure_boxes: all host threads at once)
-    std::vector<double> spheres;  // [n][4]
-    std::vector<double> tris;     // [n][9] a,b,c
-    std::vector<double> quads;    // [n][9] Q,u,v
-    std::vector<int32_t> mat_of[3], obj_of[3], prim_of[3];
+    HostVec<double> spheres;  // [n][4]
+    HostVec<double> tris;     // [n][9] a,b,c
+    HostVec<double> quads;    // [n][9] Q,u,v
+    HostVec<int32_t> mat_of[3], obj_of[3], prim_of[3];
     std::vector<CrMaterial> mats;
     std::vector<CrTexture> texs;
     std::vector<HostImage> images;
@@ -384,15 +385,30 @@ inline float f32_up(double x) {
     return f;
 }
 
-template <typename T>
-int upload(CrScene* s, const std::vector<T>& host, void** out) {
+// fn(a, b) over [0, n) in contiguous ranges, on up to 16 host threads when n is large (staging passes over millions of
+// primitives); small n runs on the caller's thread.
+template <typename F>
+void parallel_ranges(size_t n, F fn) {
+    const size_t n_threads = n >= (1u << 16) ? std::min<size_t>(16, std::max(1u, std::thread::hardware_concurrency())) : 1;
+    if (n_threads <= 1) {
+        fn((size_t)0, n);
+        return;
+    }
+    std::vector<std::thread> pool;
+    for (size_t t = 1; t < n_threads; ++t) pool.emplace_back(fn, n * t / n_threads, n * (t + 1) / n_threads);
+    fn((size_t)0, n / n_threads);
+    for (auto& th : pool) th.join();
+}
+
+template <typename T, typename A>
+int upload(CrScene* s, const std::vector<T, A>& host, void** out) {
     *out = nullptr;
     if (host.empty()) return CR_OK;
     void* d = nullptr;
     API_CUDA(cudaMallocAsync(&d, host.size() * sizeof(T), s->stream));
     s->dev_allocs.push_back(d);
     // pageable source: the call returns once the bytes are staged, so `host` may die with the caller's scope
-    API_CUDA(cudaMemcpyAsync(d, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice, s->stream));
+    API_CUDA(StagedCopier::copy(s->device, d, host.data(), host.size() * sizeof(T), s->stream));  // big arrays: several host threads
     *out = d;
     return CR_OK;
 }
@@ -653,13 +669,15 @@ int upload_scene(CrScene* s) {
         kind_of_mat[i] = cm.kind | ((cm.kind == CR_MAT_LAMBERTIAN && tex_needs_uv(s, cm.tex)) ? MATKIND_NEEDS_UV : 0);
     }
     for (int k = 0; k < 3; ++k) {
-        std::vector<PrimMeta> m(s->mat_of[k].size());
-        for (size_t i = 0; i < m.size(); ++i) {
-            m[i].material = s->mat_of[k][i];
-            m[i].prim_index = s->prim_of[k][i];
-            m[i].obj_id = s->obj_of[k][i];
-            m[i].mat_kind = kind_of_mat[(size_t)m[i].material];
-        }
+        HostVec<PrimMeta> m(s->mat_of[k].size());  // 160 MB for 10 M triangles: a cached block, filled on all host threads
+        parallel_ranges(m.size(), [&](size_t a, size_t b) {
+            for (size_t i = a; i < b; ++i) {
+                m[i].material = s->mat_of[k][i];
+                m[i].prim_index = s->prim_of[k][i];
+                m[i].obj_id = s->obj_of[k][i];
+                m[i].mat_kind = kind_of_mat[(size_t)m[i].material];
+            }
+        });
         void* p = nullptr;
         int rc = upload(s, m, &p);
         if (rc != CR_OK) return rc;
@@ -703,8 +721,10 @@ int upload_scene(CrScene* s) {
         std::vector<DevImage> di(s->images.size());
         for (size_t i = 0; i < di.size(); ++i) {
             HostImage& im = s->images[i];
-            std::vector<uchar4> px((size_t)im.w * im.h);
-            for (size_t k = 0; k < px.size(); ++k) px[k] = make_uchar4(im.rgb[3 * k], im.rgb[3 * k + 1], im.rgb[3 * k + 2], 255);
+            HostVec<uchar4> px((size_t)im.w * im.h);  // cached block, converted on all host threads (a sky image: 8 M texels)
+            parallel_ranges(px.size(), [&](size_t a, size_t b) {
+                for (size_t k = a; k < b; ++k) px[k] = make_uchar4(im.rgb[3 * k], im.rgb[3 * k + 1], im.rgb[3 * k + 2], 255);
+            });
             cudaChannelFormatDesc fmt = cudaCreateChannelDesc<uchar4>();
             API_CUDA(cudaMallocArray(&im.arr, &fmt, (size_t)im.w, (size_t)im.h));
             API_CUDA(cudaMemcpy2DToArray(im.arr, 0, 0, px.data(), (size_t)im.w * sizeof(uchar4), (size_t)im.w * sizeof(uchar4),
@@ -874,6 +894,10 @@ CrScene* cr_scene_create(int device) {
 }
 
 int cr_device_trim(int device) {
+    if (device < 0) {  // host-only scenes (cr_scene_create(-1)): only the staging cache exists
+        HostBlockPool::instance().trim();
+        return CR_OK;
+    }
     const DeviceInfo& di = device_info(device);
     if (di.state != 1) return fail(CR_ERR_NO_DEVICE, di.why);
     DeviceSlot& slot = device_slot(device);
@@ -881,6 +905,7 @@ int cr_device_trim(int device) {
     API_CUDA(cudaSetDevice(device));
     API_CUDA(cudaDeviceSynchronize());
     slot.ws.release();
+    HostBlockPool::instance().trim();  // host staging blocks cached between scenes (host_pool.h)
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
         uint64_t keep = 0;  // the CUDA default: cached blocks go back to the driver at the next synchronisation
@@ -951,29 +976,48 @@ static int64_t add_prims(CrScene* s, uint32_t kind, const double* data, size_t s
     if (!s || (!data && n)) return fail(CR_ERR_INVALID, "null argument");
     const size_t first = s->elements.size();
     if (first + n > REF_MAX_INDEX) return fail(CR_ERR_LIMIT, "too many primitives");
-    for (size_t k = 0; k < n * stride; ++k)
-        if (!std::isfinite(data[k])) return fail(CR_ERR_INVALID, "non-finite primitive coordinate");
+    {  // all coordinates finite: exponent field != 0x7ff, as a branch-free integer reduction (vectorises; a mesh world arrives
+       // as 1.4 GB through this loop)
+        uint64_t bad = 0;
+        for (size_t k = 0; k < n * stride; ++k) {
+            uint64_t bits;
+            std::memcpy(&bits, &data[k], sizeof bits);
+            bad |= (uint64_t)(((bits >> 52) & 0x7ffu) == 0x7ffu);
+        }
+        if (bad) return fail(CR_ERR_INVALID, "non-finite primitive coordinate");
+    }
     if (kind == CR_PRIM_SPHERE)
         for (size_t i = 0; i < n; ++i)
             if (!(data[4 * i + 3] >= 0.0)) return fail(CR_ERR_INVALID, "Cannot make a sphere with negative radius");  // sphere.rs:26
-    std::vector<double>& store = kind == CR_PRIM_SPHERE ? s->spheres : (kind == CR_PRIM_TRIANGLE ? s->tris : s->quads);
+    HostVec<double>& store = kind == CR_PRIM_SPHERE ? s->spheres : (kind == CR_PRIM_TRIANGLE ? s->tris : s->quads);
     const size_t first_of_kind = store.size() / stride;
-    store.insert(store.end(), data, data + n * stride);
-    s->elements.resize(first + n);
-    s->mat_of[kind].resize(first_of_kind + n);
-    s->obj_of[kind].resize(first_of_kind + n);
-    s->prim_of[kind].resize(first_of_kind + n);
-    // the boxes (Sphere::new / Triangle::new, sphere.rs:29-30, triangle.rs:27-35) are computed at commit, for every new
+    HostVec<int32_t>&mo = s->mat_of[kind], &oo = s->obj_of[kind], &po = s->prim_of[kind];
+    // The boxes (Sphere::new / Triangle::new, sphere.rs:29-30, triangle.rs:27-35) are computed at commit, for every new
     // element at once and on all host threads: a mesh scene arrives as thousands of add calls (Scene::load_asset adds one
-    // mesh per call), and boxing them call by call on one thread cost 1.6 s of the 10 M-triangle scene's 2 s staging
-    for (size_t i = 0; i < n; ++i) {
-        Element& e = s->elements[first + i];
-        e.kind = kind;
-        e.idx = (uint32_t)(first_of_kind + i);
-        e.hide = false;
-        s->mat_of[kind][first_of_kind + i] = material ? material[i] : 0;
-        s->obj_of[kind][first_of_kind + i] = obj_id ? obj_id[i] : (int32_t)(first + i);
-        s->prim_of[kind][first_of_kind + i] = (int32_t)(first + i);
+    // mesh per call), and boxing them call by call on one thread cost 1.6 s of the 10 M-triangle scene's 2 s staging.
+    // Every staging array is written ONCE here (no resize-then-fill: 1.5 GB pass through this function for that scene).
+    try {
+        store.insert(store.end(), data, data + n * stride);
+        for (size_t i = 0; i < n; ++i) {
+            Element e;
+            e.kind = kind;
+            e.idx = (uint32_t)(first_of_kind + i);
+            e.hide = false;
+            s->elements.push_back(e);
+        }
+        if (material) mo.insert(mo.end(), material, material + n);
+        else mo.resize(first_of_kind + n, 0);
+        if (obj_id) oo.insert(oo.end(), obj_id, obj_id + n);
+        else
+            for (size_t i = 0; i < n; ++i) oo.push_back((int32_t)(first + i));
+        for (size_t i = 0; i < n; ++i) po.push_back((int32_t)(first + i));
+    } catch (const std::bad_alloc&) {  // leave the scene as it was
+        store.resize(first_of_kind * stride);
+        s->elements.resize(first);
+        mo.resize(first_of_kind);
+        oo.resize(first_of_kind);
+        po.resize(first_of_kind);
+        return fail(CR_ERR_INVALID, "out of host memory while staging primitives");
     }
     if (!s->groups.empty()) {  // member lists exist once the scene has a group
         std::vector<uint32_t>& dst = s->open_groups.empty() ? s->top : s->groups[(size_t)s->open_groups.back()].members;
@@ -981,6 +1025,27 @@ static int64_t add_prims(CrScene* s, uint32_t kind, const double* data, size_t s
     }
     s->committed = false;
     return (int64_t)first;
+}
+
+int cr_scene_reserve(CrScene* s, size_t n_spheres, size_t n_triangles, size_t n_quads) {
+    if (!s) return fail(CR_ERR_INVALID, "null scene");
+    const size_t add[3] = {n_spheres, n_triangles, n_quads};
+    const size_t total = n_spheres + n_triangles + n_quads;
+    if (s->elements.size() + total > REF_MAX_INDEX) return fail(CR_ERR_LIMIT, "too many primitives");
+    try {
+        s->elements.reserve(s->elements.size() + total);
+        s->spheres.reserve(s->spheres.size() + 4 * n_spheres);
+        s->tris.reserve(s->tris.size() + 9 * n_triangles);
+        s->quads.reserve(s->quads.size() + 9 * n_quads);
+        for (int k = 0; k < 3; ++k) {
+            s->mat_of[k].reserve(s->mat_of[k].size() + add[k]);
+            s->obj_of[k].reserve(s->obj_of[k].size() + add[k]);
+            s->prim_of[k].reserve(s->prim_of[k].size() + add[k]);
+        }
+    } catch (const std::bad_alloc&) {
+        return fail(CR_ERR_INVALID, "cr_scene_reserve: out of host memory");
+    }
+    return CR_OK;
 }
 
 int cr_scene_begin_group(CrScene* s, int kind) {
@@ -1080,19 +1145,11 @@ static void ensure_boxes(CrScene* s) {
     auto fill = [&](size_t a, size_t b) {
         for (size_t i = a; i < b; ++i) {
             Element& e = s->elements[i];
-            const std::vector<double>& store = e.kind == CR_PRIM_SPHERE ? s->spheres : (e.kind == CR_PRIM_TRIANGLE ? s->tris : s->quads);
+            const HostVec<double>& store = e.kind == CR_PRIM_SPHERE ? s->spheres : (e.kind == CR_PRIM_TRIANGLE ? s->tris : s->quads);
             e.box = prim_box(e.kind, &store[(size_t)(e.kind == CR_PRIM_SPHERE ? 4 : 9) * e.idx]);
         }
     };
-    const size_t n = a1 - a0;
-    const size_t n_threads = n >= (1u << 16) ? std::min<size_t>(16, std::max(1u, std::thread::hardware_concurrency())) : 1;
-    if (n_threads <= 1) {
-        fill(a0, a1);
-    } else {
-        std::vector<std::thread> pool;
-        for (size_t t = 0; t < n_threads; ++t) pool.emplace_back(fill, a0 + n * t / n_threads, a0 + n * (t + 1) / n_threads);
-        for (auto& th : pool) th.join();
-    }
+    parallel_ranges(a1 - a0, [&](size_t a, size_t b) { fill(a0 + a, a0 + b); });
     s->boxed = a1;
 }
 
@@ -1435,8 +1492,8 @@ struct FileWriter {
     bool ok = true;
     void raw(const void* p, size_t n) { ok = ok && (n == 0 || fwrite(p, 1, n, f) == n); }
     void u64(uint64_t v) { raw(&v, 8); }
-    template <typename T>
-    void vec(const std::vector<T>& v) {
+    template <typename T, typename A>
+    void vec(const std::vector<T, A>& v) {
         u64(v.size());
         raw(v.data(), v.size() * sizeof(T));
     }
@@ -1450,8 +1507,8 @@ struct FileReader {
         raw(&v, 8);
         return v;
     }
-    template <typename T>
-    void vec(std::vector<T>& v, uint64_t limit) {
+    template <typename T, typename A>
+    void vec(std::vector<T, A>& v, uint64_t limit) {
         const uint64_t n = u64();
         if (!ok || n > limit) {
             ok = false;
@@ -1596,7 +1653,7 @@ extern "C" CrScene* cr_scene_load(const char* path, int device) {
                 ok = false;
                 break;
             }
-            const std::vector<double>& store = e.kind == CR_PRIM_SPHERE ? s->spheres : (e.kind == CR_PRIM_TRIANGLE ? s->tris : s->quads);
+            const HostVec<double>& store = e.kind == CR_PRIM_SPHERE ? s->spheres : (e.kind == CR_PRIM_TRIANGLE ? s->tris : s->quads);
             const size_t stride = e.kind == CR_PRIM_SPHERE ? 4 : 9;
             for (size_t c = 0; c < stride; ++c)
                 if (!std::isfinite(store[stride * e.idx + c])) ok = false;

@@ -26,6 +26,7 @@
 #include <map>
 
 #include "bvh_host.h"
+#include "h2d_staged.h"
 
 namespace crb {
 namespace {
@@ -431,7 +432,7 @@ uint32_t ceil_log2(uint64_t n) {
         }                                                                               \
     } while (0)
 
-int gpu_build_bvh(int device, void* cuda_stream, const std::vector<Element>& elements, const std::vector<uint32_t>& visible,
+int gpu_build_bvh(int device, void* cuda_stream, const ElementVec& elements, const std::vector<uint32_t>& visible,
                   void** d_nodes_out, uint64_t* n_nodes_out, uint32_t& max_depth, BvhBuildTimes* times, std::string& err) {
     using clk = std::chrono::steady_clock;
     const auto t_begin = clk::now();
@@ -501,7 +502,7 @@ int gpu_build_bvh(int device, void* cuda_stream, const std::vector<Element>& ele
     const auto t_alloc = clk::now();
 
     // the staging arrays go up as they are (pageable: the copies return once the bytes are staged)
-    BVH_CUDA(cudaMemcpyAsync(d_elements, elements.data(), elements.size() * sizeof(Element), cudaMemcpyHostToDevice, stream));
+    BVH_CUDA(StagedCopier::copy(device, d_elements, elements.data(), elements.size() * sizeof(Element), stream));  // 640 MB for 10 M triangles
     if (!all_visible) BVH_CUDA(cudaMemcpyAsync(d_visible, visible.data(), (size_t)n * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
     const uint32_t tpb = 256, grid_n = (n + tpb - 1) / tpb;
     k_bvh_gather<<<grid_n, tpb, 0, stream>>>(d_elements, d_visible, n, d_boxes, d_leaf);
@@ -630,7 +631,7 @@ int gpu_flatten_tris(int device, void* cuda_stream, const double* h_abc, uint64_
     DeviceBuffers buf{stream, {}};
     double* d_abc;
     BVH_CUDA(buf.alloc(&d_abc, (size_t)9 * n));
-    BVH_CUDA(cudaMemcpyAsync(d_abc, h_abc, (size_t)9 * n * sizeof(double), cudaMemcpyHostToDevice, stream));
+    BVH_CUDA(StagedCopier::copy(device, d_abc, h_abc, (size_t)9 * n * sizeof(double), stream));
     k_flatten_tris<<<(n + 255) / 256, 256, 0, stream>>>(d_abc, n, static_cast<TriRec<double>*>(d_t64), static_cast<TriRec<float>*>(d_t32));
     BVH_CUDA(cudaGetLastError());
     return CR_OK;

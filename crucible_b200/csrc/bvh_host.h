@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "host_pool.h"
 
 namespace crb {
 
@@ -53,6 +54,7 @@ struct Element {  // one entry of Scene.elements (scene/mod.rs:77), insertion or
     bool hide;
     Box box;
 };
+typedef HostVec<Element> ElementVec;  // 64 B per primitive: 640 MB for the 10 M-triangle scene, cached between scenes (host_pool.h)
 
 static constexpr uint32_t FLAT_ALWAYS_PASS = 0x100u;  // FlatNode::axis flag: member of a nested HitList, no box test (api.cu GroupEmitter)
 static constexpr uint32_t FLAT_GROUP_NODE = 0x200u;   // FlatNode::axis flag: box node whose children are nested elements, not plain nodes
@@ -79,7 +81,7 @@ struct BvhBuildTimes {  // wall-clock milliseconds of the phases of one device b
 // Device build of the SAME tree (bvh_build.cu): level-synchronous median split, one stable radix sort per level.
 // The FlatNode records stay ON THE DEVICE (*d_nodes, node_count(visible.size()) entries in preorder, root box already
 // re-derived as BVHWrapper::new_from_vec does); the caller owns the allocation (cudaFreeAsync on the same stream).
-int gpu_build_bvh(int device, void* cuda_stream, const std::vector<Element>& elements, const std::vector<uint32_t>& visible,
+int gpu_build_bvh(int device, void* cuda_stream, const ElementVec& elements, const std::vector<uint32_t>& visible,
                   void** d_nodes, uint64_t* n_nodes, uint32_t& max_depth, BvhBuildTimes* times, std::string& err);
 // introspection: copies the device tree to the host
 int gpu_fetch_flat_nodes(int device, void* cuda_stream, const void* d_nodes, uint64_t n, std::vector<FlatNode>& out, std::string& err);

@@ -61,7 +61,7 @@ inline void set_empty(FastHalf& h) {
 }
 
 struct Builder {
-    const std::vector<Element>& elements;
+    const ElementVec& elements;
     const std::vector<uint32_t>& visible;
     std::vector<uint32_t> idx;      // permutation of [0, visible.size())
     std::vector<float> cx, cy, cz;  // centroids (f32 is plenty for binning)
@@ -164,7 +164,7 @@ struct Builder {
 }  // namespace fast_detail
 
 // elements[visible[i]] are the primitives of the committed world (hidden ones already dropped).
-inline void build_fast_tree(const std::vector<Element>& elements, const std::vector<uint32_t>& visible, FastTreeHost& out) {
+inline void build_fast_tree(const ElementVec& elements, const std::vector<uint32_t>& visible, FastTreeHost& out) {
     using namespace fast_detail;
     const uint32_t n = (uint32_t)visible.size();
     out.nodes.clear();

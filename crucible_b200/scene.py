@@ -407,6 +407,11 @@ class SceneDesc:
         f = lambda name: getattr(lib, prefix + name)
         add = {abi.CR_PRIM_SPHERE: "scene_add_spheres", abi.CR_PRIM_TRIANGLE: "scene_add_triangles",
                abi.CR_PRIM_QUAD: "scene_add_quads"}
+        if hasattr(lib, prefix + "scene_reserve"):  # size hint: the staging arrays grow once (the oracle has no such call)
+            counts = [sum(len(b[1]) for b in self.batches if b[0] == k) for k in (abi.CR_PRIM_SPHERE, abi.CR_PRIM_TRIANGLE, abi.CR_PRIM_QUAD)]
+            rc = f("scene_reserve")(handle, *counts)
+            if rc < 0:
+                raise abi.CrucibleError(rc, f("last_error")().decode())
         for kind, data, mat, oid in self.batches:
             if kind in (abi.GROUP_BEGIN, abi.GROUP_END):
                 rc = f("scene_begin_group")(handle, int(mat[0])) if kind == abi.GROUP_BEGIN else f("scene_end_group")(handle)

@@ -195,7 +195,8 @@ int cr_device_count(void);
 CrScene* cr_scene_create(int device);
 /* Releases what the library caches on `device` between calls: the wavefront arena shared by the scenes of the process
  * (path pool, queues, framebuffer: up to ~25 GB at the default pool of 64 M paths), its pinned staging block, and the
- * blocks held by the device's stream-ordered memory pool.  Safe to call between renders (it waits for the device);
+ * blocks held by the device's stream-ordered memory pool, and the host staging blocks cached between scenes
+ * (cr_scene_reserve).  Safe to call between renders (it waits for the device);
  * the next render allocates again.  The reference has nothing to release: its worker pool dies with Camera::render
  * (camera/mod.rs:299-303). */
 int cr_device_trim(int device);
@@ -207,6 +208,12 @@ const char* cr_version(void);
  *      src/scene/mod.rs:75-82, 159-230).  Each call APPENDS to the flat element list in
  *      call order, exactly like Scene::add_element / load_asset, and returns the index of
  *      the first appended primitive (>= 0) or a negative CrStatus. ---- */
+/* Optional size hint before a run of cr_scene_add_* calls: room for this many MORE primitives of each kind, so that the
+ * staging arrays grow once (Scene::load_asset adds one mesh per call, scene/mod.rs:211-229: a 10 M-triangle world arrives
+ * as ~1 600 calls).  The reference's Vec::push has no counterpart of its own; a flattener that walks a finished
+ * Hittables tree knows the totals.  Staging blocks of 1 MB and more are cached by the library between scenes (a per-frame
+ * rebuild, Scene::render_image scene/mod.rs:332-347, then touches mapped memory); cr_device_trim releases them. */
+int cr_scene_reserve(CrScene*, size_t n_spheres, size_t n_triangles, size_t n_quads);
 /* Sphere::new, sphere.rs:25-39: cxyz_r = [n][4] (centre, radius >= 0). */
 int64_t cr_scene_add_spheres(CrScene*, const double* cxyz_r, const int32_t* material,
                              const int32_t* obj_id, size_t n);

@@ -252,3 +252,47 @@ def test_rejected_batch_leaves_the_scene_untouched(crlib):
     n, d, v = C.c_uint64(), C.c_uint32(), C.c_uint64()
     assert lib.cr_scene_bvh_info(h, C.byref(n), C.byref(d), C.byref(v)) == 0 and v.value == 5
     lib.cr_scene_destroy(h)
+
+
+def test_reserve_and_cached_staging_blocks_change_nothing(crlib):
+    """cr_scene_reserve is only a size hint, and the staging blocks the library caches between scenes (host_pool.h: a
+    per-frame rebuild as Scene::render_image does it, scene/mod.rs:332-347) come back clean: a mesh world staged call by
+    call, with and without the hint, three scenes in a row, commits to the same tree every time."""
+    lib = crlib
+    rng = np.random.default_rng(5)
+    n_batches, per = 40, 6320  # 40 meshes of teapot size: 18 MB of vertices, 16 MB of elements (pooled blocks)
+    batches = [(rng.uniform(-50, 50, (per, 1, 3)) + rng.uniform(-1, 1, (per, 3, 3))).reshape(per, 9) for _ in range(n_batches)]
+    mats = [np.full(per, k % 3, np.int32) for k in range(n_batches)]
+    sph = np.array([[0.0, -1000.0, 0.0, 1000.0]])
+    m = (abi.CrMaterial * 3)(abi.CrMaterial(kind=abi.CR_MAT_LAMBERTIAN, scatter_prob=1.0), abi.CrMaterial(kind=abi.CR_MAT_METAL), abi.CrMaterial(kind=abi.CR_MAT_DIELECTRIC, ior=1.5))
+    t = abi.CrTexture(kind=abi.CR_TEX_SOLID)
+
+    def build(hint):
+        h = lib.cr_scene_create(-1)
+        if hint:
+            assert lib.cr_scene_reserve(h, 1, n_batches * per, 0) == 0
+        first = 0
+        assert lib.cr_scene_add_spheres(h, sph.ctypes.data_as(C.c_void_p), None, None, 1) == 0
+        for b, mm in zip(batches, mats):
+            first = lib.cr_scene_add_triangles(h, b.ctypes.data_as(C.c_void_p), mm.ctypes.data_as(C.c_void_p), None, per)
+        assert first == 1 + (n_batches - 1) * per
+        assert lib.cr_scene_set_materials(h, C.cast(m, C.c_void_p), 3) == 0 and lib.cr_scene_set_textures(h, C.byref(t), 1) == 0
+        assert lib.cr_scene_set_bvh_builder(h, abi.CR_BVH_HOST) == 0 and lib.cr_scene_commit(h) == 0
+        n = lib.cr_scene_bvh_nodes(h, None, 0)
+        nodes = np.zeros(n, dtype=abi.BVH_NODE_DTYPE)
+        assert lib.cr_scene_bvh_nodes(h, nodes.ctypes.data_as(C.c_void_p), n) == n
+        k = lib.cr_scene_bvh_leaf_order(h, None, 0)
+        order = np.empty(k, np.int32)
+        assert lib.cr_scene_bvh_leaf_order(h, order.ctypes.data_as(C.c_void_p), k) == k
+        lib.cr_scene_destroy(h)
+        return nodes.tobytes(), order
+
+    ref_nodes, ref_order = build(False)
+    assert len(np.unique(ref_order)) == 1 + n_batches * per  # every primitive reached (span-1 nodes list theirs twice)
+    for hint in (True, False, True):
+        nodes, order = build(hint)
+        assert nodes == ref_nodes and np.array_equal(order, ref_order)
+    assert lib.cr_device_trim(-1) == 0  # host-only: releases the cached staging blocks
+    nodes, order = build(True)
+    assert nodes == ref_nodes and np.array_equal(order, ref_order)
+    assert lib.cr_scene_reserve(None, 1, 1, 1) == abi.CR_ERR_INVALID
