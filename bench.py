@@ -285,8 +285,12 @@ def main():
     pinned8 = torch.empty((H, W, 3), dtype=torch.uint8).pin_memory()
     pinned8_np = pinned8.numpy()
 
+    e2e_trace = os.environ.get("BENCH_E2E_TRACE") and rank == 0
+
     def e2e_step():
+        ta = time.perf_counter()
         g = GpuScene(desc, local)
+        tb = time.perf_counter()
         if movie:
             for f in range(rank, fps, world):
                 cam.frame = f
@@ -301,7 +305,10 @@ def main():
             if rank == 0:
                 pinned8.copy_(full8, non_blocking=True)
             torch.cuda.synchronize()
+        tc = time.perf_counter()
         g.close()
+        if e2e_trace:
+            print(f"e2e step: scene {1e3 * (tb - ta):.1f} ms, render {1e3 * (tc - tb):.1f} ms, close {1e3 * (time.perf_counter() - tc):.1f} ms", file=sys.stderr, flush=True)
 
     e2e_step()
     barrier()

@@ -46,6 +46,64 @@ struct HostImage {
     cudaTextureObject_t tex = 0;
 };
 
+// CUDA arrays (+ their point-sampled texture objects) of destroyed scenes, per device, by size.  A caller that rebuilds its
+// scene every frame (Scene::render_image, scene/mod.rs:332-347) would otherwise pay cudaMallocArray / cudaFreeArray for a 32 MB
+// sky image per frame; measured on the teapot config, cudaFreeArray inside cr_scene_destroy took 0.6 ... 256 ms (it unmaps
+// device memory and synchronises the device) and made the end-to-end rate jump between 1270 and 2040 Msamples/s from run to
+// run.  Only the ALLOCATION is reused: every scene uploads its texels again.  cr_device_trim frees the cache.
+struct CachedArray {
+    int w, h;
+    cudaArray_t arr;
+    cudaTextureObject_t tex;
+};
+struct ImageArrayCache {
+    static constexpr size_t MAX_BYTES = (size_t)1 << 30;
+    std::mutex mu;
+    std::vector<CachedArray> free_list;
+    size_t bytes = 0;
+    bool take(int w, int h, cudaArray_t* arr, cudaTextureObject_t* tex) {
+        std::lock_guard<std::mutex> lk(mu);
+        for (size_t i = 0; i < free_list.size(); ++i)
+            if (free_list[i].w == w && free_list[i].h == h) {
+                *arr = free_list[i].arr;
+                *tex = free_list[i].tex;
+                bytes -= (size_t)w * h * 4;
+                free_list.erase(free_list.begin() + (long)i);
+                return true;
+            }
+        return false;
+    }
+    // the caller has made sure no work that reads the array is still in flight
+    void give(int w, int h, cudaArray_t arr, cudaTextureObject_t tex) {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            if (bytes + (size_t)w * h * 4 <= MAX_BYTES) {
+                free_list.push_back(CachedArray{w, h, arr, tex});
+                bytes += (size_t)w * h * 4;
+                return;
+            }
+        }
+        if (tex) cudaDestroyTextureObject(tex);
+        if (arr) cudaFreeArray(arr);
+    }
+    void trim() {
+        std::vector<CachedArray> gone;
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            gone.swap(free_list);
+            bytes = 0;
+        }
+        for (auto& c : gone) {
+            if (c.tex) cudaDestroyTextureObject(c.tex);
+            if (c.arr) cudaFreeArray(c.arr);
+        }
+    }
+};
+ImageArrayCache& image_cache(int device) {
+    static ImageArrayCache* c = new ImageArrayCache[64];  // never destroyed (CUDA objects must not be freed after the runtime)
+    return c[device < 0 || device >= 64 ? 0 : device];
+}
+
 }  // namespace
 
 struct CrScene {
@@ -106,9 +164,17 @@ struct CrScene {
     void free_device_scene() {
         for (void* p : dev_allocs) cudaFreeAsync(p, stream);
         dev_allocs.clear();
+        bool drained = false;
         for (auto& im : images) {
-            if (im.tex) cudaDestroyTextureObject(im.tex);
-            if (im.arr) cudaFreeArray(im.arr);
+            if (im.arr) {
+                // a render of this scene may still be in flight on a caller's stream (cr_render_device is asynchronous);
+                // cudaFreeArray used to wait for it implicitly
+                if (!drained) cudaDeviceSynchronize();
+                drained = true;
+                image_cache(device).give(im.w, im.h, im.arr, im.tex);
+            } else if (im.tex) {
+                cudaDestroyTextureObject(im.tex);
+            }
             im.tex = 0;
             im.arr = nullptr;
         }
@@ -721,26 +787,40 @@ int upload_scene(CrScene* s) {
         std::vector<DevImage> di(s->images.size());
         for (size_t i = 0; i < di.size(); ++i) {
             HostImage& im = s->images[i];
+            static const bool prof = getenv("CRB_PROFILE_COMMIT") != nullptr;
+            const auto tp0 = std::chrono::steady_clock::now();
             HostVec<uchar4> px((size_t)im.w * im.h);  // cached block, converted on all host threads (a sky image: 8 M texels)
             parallel_ranges(px.size(), [&](size_t a, size_t b) {
                 for (size_t k = a; k < b; ++k) px[k] = make_uchar4(im.rgb[3 * k], im.rgb[3 * k + 1], im.rgb[3 * k + 2], 255);
             });
-            cudaChannelFormatDesc fmt = cudaCreateChannelDesc<uchar4>();
-            API_CUDA(cudaMallocArray(&im.arr, &fmt, (size_t)im.w, (size_t)im.h));
+            const auto tp1 = std::chrono::steady_clock::now();
+            const bool reused = image_cache(s->device).take(im.w, im.h, &im.arr, &im.tex);
+            if (!reused) {
+                cudaChannelFormatDesc fmt = cudaCreateChannelDesc<uchar4>();
+                API_CUDA(cudaMallocArray(&im.arr, &fmt, (size_t)im.w, (size_t)im.h));
+            }
+            const auto tp2 = std::chrono::steady_clock::now();
             API_CUDA(cudaMemcpy2DToArray(im.arr, 0, 0, px.data(), (size_t)im.w * sizeof(uchar4), (size_t)im.w * sizeof(uchar4),
                                          (size_t)im.h, cudaMemcpyHostToDevice));
-            cudaResourceDesc res;
-            memset(&res, 0, sizeof(res));
-            res.resType = cudaResourceTypeArray;
-            res.res.array.array = im.arr;
-            cudaTextureDesc td;
-            memset(&td, 0, sizeof(td));
-            td.addressMode[0] = cudaAddressModeClamp;
-            td.addressMode[1] = cudaAddressModeClamp;
-            td.filterMode = cudaFilterModePoint;
-            td.readMode = cudaReadModeElementType;
-            td.normalizedCoords = 0;
-            API_CUDA(cudaCreateTextureObject(&im.tex, &res, &td, nullptr));
+            if (prof) {
+                const auto tp3 = std::chrono::steady_clock::now();
+                auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+                fprintf(stderr, "crucible_b200 image %dx%d: convert %.2f ms, cudaMallocArray %.2f ms, copy %.2f ms\n", im.w, im.h, ms(tp0, tp1), ms(tp1, tp2), ms(tp2, tp3));
+            }
+            if (!im.tex) {
+                cudaResourceDesc res;
+                memset(&res, 0, sizeof(res));
+                res.resType = cudaResourceTypeArray;
+                res.res.array.array = im.arr;
+                cudaTextureDesc td;
+                memset(&td, 0, sizeof(td));
+                td.addressMode[0] = cudaAddressModeClamp;
+                td.addressMode[1] = cudaAddressModeClamp;
+                td.filterMode = cudaFilterModePoint;
+                td.readMode = cudaReadModeElementType;
+                td.normalizedCoords = 0;
+                API_CUDA(cudaCreateTextureObject(&im.tex, &res, &td, nullptr));
+            }
             di[i].tex = im.tex;
             di[i].w = im.w;
             di[i].h = im.h;
@@ -905,6 +985,7 @@ int cr_device_trim(int device) {
     API_CUDA(cudaSetDevice(device));
     API_CUDA(cudaDeviceSynchronize());
     slot.ws.release();
+    image_cache(device).trim();
     HostBlockPool::instance().trim();  // host staging blocks cached between scenes (host_pool.h)
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -921,17 +1002,25 @@ int cr_device_trim(int device) {
 void cr_scene_destroy(CrScene* s) {
     if (!s) return;
     if (s->device >= 0) {
+        static const bool prof = getenv("CRB_PROFILE_COMMIT") != nullptr;
+        auto ms = [](std::chrono::steady_clock::time_point a) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a).count(); };
+        const auto t0 = std::chrono::steady_clock::now();
         cudaSetDevice(s->device);
         s->free_device_scene();
         s->free_flat_tree();
+        const double ms_scene = ms(t0);
         if (s->d_out_rgb) cudaFreeAsync(s->d_out_rgb, s->stream);
         if (s->d_out_rgb8) cudaFreeAsync(s->d_out_rgb8, s->stream);
         if (s->d_io) cudaFreeAsync(s->d_io, s->stream);
         if (s->d_multi_rgb) cudaFree(s->d_multi_rgb);
         if (s->d_multi_rgb8) cudaFree(s->d_multi_rgb8);
+        const double ms_bufs = ms(t0);
         if (s->stream) cudaStreamDestroy(s->stream);  // resources are released once the queued work has drained
+        if (prof) fprintf(stderr, "crucible_b200 destroy: device scene %.2f ms, buffers %.2f ms, stream %.2f ms\n", ms_scene, ms_bufs - ms_scene, ms(t0) - ms_bufs);
     }
+    const auto t1 = std::chrono::steady_clock::now();
     delete s;
+    if (getenv("CRB_PROFILE_COMMIT")) fprintf(stderr, "crucible_b200 destroy: host %.2f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count());
 }
 
 // Box of one primitive in reference arithmetic.

@@ -108,6 +108,12 @@ __device__ __forceinline__ bool ref_box_span(const NodeRec<R>& n, V3<R> o, V3<R>
 // 32-bit window offsets; the records are read-only after the copy, so plain (non-volatile) ld.shared is safe.
 struct SmemTree {
     uint32_t nodes, prims, spheres32;  // shared-window byte addresses
+    // Byte stride of the 64 B node records.  At 64 the four LDS.128 of an INNER step address bank group (4 cur + j) mod 8:
+    // for a fixed j only TWO of the eight 16 B bank groups, so the lanes of a warp that sit on different nodes conflict
+    // (ncu, book1: 4.1 wavefronts per LDS.128 where the distinct addresses needed 2.6; the node fetches are 55 % of the
+    // kernel's shared-memory wavefronts).  At 80 the group is (5 cur + j) mod 8, a bijection of cur mod 8: distinct nodes
+    // spread over all banks, with the same base + immediate addressing (no extra instruction), for 25 % more node memory.
+    uint32_t node_stride;
     // the primitive records of the leaf tests (R precision) and, per leaf-table entry, the box of the primitive's
     // REFERENCE leaf node (the candidate confirmation): with these the kernel reads no scene data from global memory
     uint32_t spheres, tris, quads, leafbox;
@@ -236,8 +242,9 @@ struct FastTrav {
     __device__ __forceinline__ int step_inner(const DevScene<R>& sc, const FastRay& fr, float tmin) {
         NodeRec<float> a, b;
         if constexpr (SMEM) {
-            a = lds_node32(tree.nodes + cur * 64u);
-            b = lds_node32(tree.nodes + cur * 64u + 32u);
+            const uint32_t na = tree.nodes + cur * tree.node_stride;
+            a = lds_node32(na);
+            b = lds_node32(na + 32u);
         } else {
             const NodeRec<float>* half = reinterpret_cast<const NodeRec<float>*>(sc.fast_nodes + cur);
             a = ldg_node32(half);

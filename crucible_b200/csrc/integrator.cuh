@@ -442,11 +442,12 @@ struct FastSmemLayout {
     uint32_t nodes, prims, spheres32, spheres, tris, quads, leafbox, total;
 };
 template <typename R>
-static __host__ __device__ FastSmemLayout fast_smem_layout(uint32_t n_fast_nodes, uint32_t n_fast_prims, uint32_t n_sph, uint32_t n_tri, uint32_t n_quad) {
+static __host__ __device__ FastSmemLayout fast_smem_layout(uint32_t n_fast_nodes, uint32_t n_fast_prims, uint32_t n_sph, uint32_t n_tri, uint32_t n_quad,
+                                                           uint32_t node_stride = 64u) {
     auto up = [](uint32_t b) { return (b + 127u) & ~127u; };
     FastSmemLayout l;
     l.nodes = up((uint32_t)sizeof(FastSlots<R, FAST_BIG_BLOCK, FAST_BIG_LEVELS>));
-    l.prims = l.nodes + up(n_fast_nodes * 64u);
+    l.prims = l.nodes + up(n_fast_nodes * node_stride);
     l.spheres32 = l.prims + up(n_fast_prims * 8u);
     l.spheres = l.spheres32 + up(n_sph * 16u);
     l.tris = l.spheres + up(n_sph * (uint32_t)sizeof(SphereRec<R>));
@@ -459,19 +460,25 @@ template <typename R>
 __global__ void __launch_bounds__(FAST_BIG_BLOCK, 1) k_trace_fast_smem(DevScene<R> sc, PathRec<R>* __restrict__ paths, Control* __restrict__ ctl,
                                                                        int side, uint2* __restrict__ queues, const FilterRec* __restrict__ filt,
                                                                        uint32_t pool, uint32_t* __restrict__ retry_list, uint32_t n_fast_nodes,
-                                                                       uint32_t n_fast_prims, uint32_t n_sph, uint32_t n_tri, uint32_t n_quad) {
+                                                                       uint32_t n_fast_prims, uint32_t n_sph, uint32_t n_tri, uint32_t n_quad,
+                                                                       uint32_t node_stride) {
     extern __shared__ __align__(128) unsigned char fast_smem[];
     if (ctl->n_in[side] == 0u) return;  // nothing to trace: skip the copy of the tree
     typedef FastSlots<R, FAST_BIG_BLOCK, FAST_BIG_LEVELS> Slots;
     Slots* slots = reinterpret_cast<Slots*>(fast_smem);
-    const FastSmemLayout l = fast_smem_layout<R>(n_fast_nodes, n_fast_prims, n_sph, n_tri, n_quad);
+    const FastSmemLayout l = fast_smem_layout<R>(n_fast_nodes, n_fast_prims, n_sph, n_tri, n_quad, node_stride);
     {
         auto copy16 = [&](uint32_t dst_off, const void* src, uint32_t n16) {
             int4* d = reinterpret_cast<int4*>(fast_smem + dst_off);
             const int4* s = reinterpret_cast<const int4*>(src);
             for (uint32_t i = threadIdx.x; i < n16; i += blockDim.x) d[i] = __ldg(s + i);
         };
-        copy16(l.nodes, sc.fast_nodes, n_fast_nodes * 4u);
+        {  // 64 B node records at a stride of node_stride bytes (80: see SmemTree::node_stride)
+            int4* d = reinterpret_cast<int4*>(fast_smem + l.nodes);
+            const int4* s = reinterpret_cast<const int4*>(sc.fast_nodes);
+            const uint32_t per = node_stride >> 4;
+            for (uint32_t i = threadIdx.x; i < n_fast_nodes * 4u; i += blockDim.x) d[(i >> 2) * per + (i & 3u)] = __ldg(s + i);
+        }
         uint2* dp = reinterpret_cast<uint2*>(fast_smem + l.prims);
         LeafBox<R>* db = reinterpret_cast<LeafBox<R>*>(fast_smem + l.leafbox);
         for (uint32_t i = threadIdx.x; i < n_fast_prims; i += blockDim.x) {
@@ -491,6 +498,7 @@ __global__ void __launch_bounds__(FAST_BIG_BLOCK, 1) k_trace_fast_smem(DevScene<
     const uint32_t base = (uint32_t)__cvta_generic_to_shared(fast_smem);
     RenderTraceIO<R> io{sc, paths, ctl, queues, filt, ctl->n_in[side], pool, nullptr, &ctl->trace_next};
     SmemTree tree;
+    tree.node_stride = node_stride;
     tree.nodes = base + l.nodes; tree.prims = base + l.prims; tree.spheres32 = base + l.spheres32; tree.spheres = base + l.spheres;
     tree.tris = base + l.tris; tree.quads = base + l.quads; tree.leafbox = base + l.leafbox;
     fast_trace_persistent<R, FAST_BIG_BLOCK, true, FAST_BIG_LEVELS>(sc, R(0.001), Num<R>::inf(), io, slots, retry_list, &ctl->retry_count, tree);
@@ -1136,7 +1144,12 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
     }
     if (variant == 2 && !fast_ok) variant = -1;
     // (3: the order-free engine with the search tree in shared memory, for scenes small enough)
-    const size_t smem_need = fast_smem_layout<R>(s.n_fast_nodes, s.n_fast_prims, s.n_prims[0], s.n_prims[1], s.n_prims[2]).total;
+    // node records at a stride of 80 B when that still fits (conflict-free LDS.128 of a warp's divergent node fetches:
+    // SmemTree::node_stride), else packed at 64 B.  CRB_NODE_STRIDE pins one (A/B).
+    uint32_t node_stride = 80u;
+    if (const char* e = getenv("CRB_NODE_STRIDE")) node_stride = atoi(e) == 64 ? 64u : 80u;
+    if (fast_smem_layout<R>(s.n_fast_nodes, s.n_fast_prims, s.n_prims[0], s.n_prims[1], s.n_prims[2], node_stride).total > FAST_SMEM_LIMIT) node_stride = 64u;
+    const size_t smem_need = fast_smem_layout<R>(s.n_fast_nodes, s.n_fast_prims, s.n_prims[0], s.n_prims[1], s.n_prims[2], node_stride).total;
     bool smem_ok = fast_ok && s.n_fast_nodes != 0u && smem_need <= FAST_SMEM_LIMIT;
     if (smem_ok && cudaFuncSetAttribute(k_trace_fast_smem<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_need) != cudaSuccess) {
         cudaGetLastError();
@@ -1156,7 +1169,7 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
     auto launch_trace = [&](int v, int cur) {
         if (v == 3) {
             k_trace_fast_smem<R><<<s.num_sms, FAST_BIG_BLOCK, smem_need, stream>>>(sc, paths[cur], ctl, cur, queues, filt[cur], pool, retry_list,
-                                                                                  s.n_fast_nodes, s.n_fast_prims, s.n_prims[0], s.n_prims[1], s.n_prims[2]);
+                                                                                  s.n_fast_nodes, s.n_fast_prims, s.n_prims[0], s.n_prims[1], s.n_prims[2], node_stride);
             trace_variants[0]<<<s.num_sms * 2, TRACE_BLOCK, 0, stream>>>(sc, paths[cur], ctl, cur, queues, filt[cur], pool, retry_list);
             return 2;
         }

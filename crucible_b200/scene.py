@@ -412,17 +412,23 @@ class SceneDesc:
             rc = f("scene_reserve")(handle, *counts)
             if rc < 0:
                 raise abi.CrucibleError(rc, f("last_error")().decode())
+        cache = self.__dict__.setdefault("_c_args", {})
         for kind, data, mat, oid in self.batches:
             if kind in (abi.GROUP_BEGIN, abi.GROUP_END):
                 rc = f("scene_begin_group")(handle, int(mat[0])) if kind == abi.GROUP_BEGIN else f("scene_end_group")(handle)
                 if rc < 0:
                     raise abi.CrucibleError(rc, f("last_error")().decode())
                 continue
-            data = np.ascontiguousarray(data, np.float64)
-            mat = np.ascontiguousarray(mat, np.int32)
-            oid = np.ascontiguousarray(oid, np.int32)
-            rc = f(add[kind])(handle, data.ctypes.data_as(C.c_void_p), mat.ctypes.data_as(C.c_void_p),
-                              oid.ctypes.data_as(C.c_void_p), len(data))
+            # the converted arrays and their pointers are kept with the batch: a mesh world is ~1 600 batches, and a caller
+            # that rebuilds the scene every frame (Scene::render_image) would pay numpy / ctypes bookkeeping for each again
+            key = id(data)
+            hit = cache.get(key)
+            if hit is None or hit[0] is not data:
+                cd, cm, co = np.ascontiguousarray(data, np.float64), np.ascontiguousarray(mat, np.int32), np.ascontiguousarray(oid, np.int32)
+                hit = (data, cd, cm, co, cd.ctypes.data_as(C.c_void_p), cm.ctypes.data_as(C.c_void_p), co.ctypes.data_as(C.c_void_p))
+                if cd is data and cm is mat and co is oid:  # only views of the batch's own memory are kept (no stale copies)
+                    cache[key] = hit
+            rc = f(add[kind])(handle, hit[4], hit[5], hit[6], len(data))
             if rc < 0:
                 raise abi.CrucibleError(rc, f(("last_error"))().decode())
         for im in self.images:
