@@ -192,6 +192,7 @@ struct DevScene {
     int32_t clamp_colors;  // 1 = reference Color semantics; 0 when the scene holds an Emissive (extension)
     int32_t node_slice;    // box tests per lane between two exact/leaf phases of the trace engine
     int32_t min_node_lanes;  // a node slice ends early when fewer lanes than this still have a cheap step
+    int32_t rec_bypass_l1;   // trace kernels over a scene in global memory: path / filter records are loaded past the L1
     // an inner node the f32 filter cannot decide is entered untested (Trav::step_node) if its subtree has at most
     // free_pass_nodes nodes, or if the box is wider than free_pass_k error bands in ray parameter on every axis
     uint32_t free_pass_nodes;
@@ -202,29 +203,50 @@ struct DevScene {
 // ---- in-flight path record --------------------------------------------------------------------
 template <typename R>
 struct PathRec;
-// Field order = four 32 B sectors, grouped by consumer: trace reads A+B and writes t (A) and ref (B);
-// the miss shader reads only B+C; the scatter shaders read everything.
+// f64: two 64 B halves = two DRAM atoms, grouped by consumer.  The first half is everything the trace kernels read (origin,
+// direction, ray time); they never WRITE the record: the closest hit travels in the material queue (HitEntry below), so a
+// traced ray costs one 64 B read instead of the read, a read-for-ownership of the partially written sectors and their
+// write-back (ncu, round 2g: 225 B read + 75 B written per ray).  The second half is everything the miss and emissive
+// shaders read — throughput, framebuffer index and a COPY of the direction (sky lookup) — so a path that leaves the scene
+// costs one 64 B read; the scatter shaders read and write whole records.
 template <>
 struct __align__(16) PathRec<double> {
-    double ox, oy, oz, t;            // A: origin; closest-hit t written by trace
-    double dx, dy, dz;               // B: direction (NOT normalised, ray_casting.rs:102)
-    uint32_t fb, ref;                //    local framebuffer index; closest-hit reference written by trace
-    double tr, tg, tb;               // C: product of attenuations so far
-    uint32_t bounce, pad0;           //    hits so far
-    uint32_t pixel, sample;          // D: GLOBAL pixel index (RNG key), sample index
-    double tm;                       //    ray time (ray_casting.rs:84)
-    double pad1, pad2;
+    double ox, oy, oz;               // origin
+    double dx, dy, dz;               // direction (NOT normalised, ray_casting.rs:102)
+    double tm;                       // ray time (ray_casting.rs:84)
+    uint32_t pad0, pad1;
+    double tr, tg, tb;               // product of attenuations so far
+    double dx2, dy2, dz2;            // == dx, dy, dz (written together with them)
+    uint32_t pixel, sample;          // GLOBAL pixel index (RNG key), sample index
+    uint32_t bounce, fb;             // hits so far; local framebuffer index
 };
 template <>
-struct __align__(16) PathRec<float> {
-    float ox, oy, oz, t;             // A
+struct __align__(16) PathRec<float> {  // 64 B = one atom
+    float ox, oy, oz, tm;
     float dx, dy, dz;
-    uint32_t ref;
-    float tr, tg, tb, tm;            // B
-    uint32_t pixel, sample, bounce, fb;
+    uint32_t bounce;
+    float tr, tg, tb;
+    uint32_t fb;
+    uint32_t pixel, sample, pad0, pad1;
 };
 static_assert(sizeof(PathRec<double>) == 128, "f64 path record = one 128 B line");
 static_assert(sizeof(PathRec<float>) == 64, "f32 path record = half a line");
+// Closest hit of a path that goes to a scatter shader; entry k of material queue q sits at hits[(q - Q_LAMBERTIAN) * pool + k],
+// written by the trace kernel together with the queue entry (contiguous, warp-aggregated appends: full sectors, no
+// read-modify-write).  The miss and emissive queues need none.
+template <typename R>
+struct HitEntry;
+template <>
+struct __align__(16) HitEntry<double> {
+    double t;
+    uint32_t ref, pad;
+};
+template <>
+struct __align__(8) HitEntry<float> {
+    float t;
+    uint32_t ref;
+};
+static constexpr int HIT_QUEUES = 3;  // lambertian, metal, dielectric
 
 // ---- wavefront control block (device resident, one per render) -----------------------------------
 struct Control {

@@ -265,6 +265,15 @@ __device__ __forceinline__ void warp_store_records(int4* tile, PathRec<R>* dst, 
     __syncwarp();
 }
 
+// direction of a record (the f64 record keeps a second copy next to the throughput: PathRec, common.cuh)
+template <typename R>
+__device__ __forceinline__ void set_dir(PathRec<R>& p, V3<R> d) {
+    p.dx = d.x; p.dy = d.y; p.dz = d.z;
+    if constexpr (sizeof(R) == 8) {
+        p.dx2 = d.x; p.dy2 = d.y; p.dz2 = d.z;
+    }
+}
+
 // raygen: persistent grid-stride over the samples the plan handed out.  Sample-major order
 // (g = sample * npix + pixel) keeps neighbouring lanes on neighbouring pixels.  Everything that is
 // constant for the launch arrives BY VALUE (constant bank, no load latency): for a keyframe-free camera
@@ -329,15 +338,14 @@ __global__ void __launch_bounds__(SHADE_BLOCK, MINB) k_raygen(const Control* __r
             camera_sample<R>(*camp, i, j, rng, o, d, tm);
         }
         p.ox = o.x; p.oy = o.y; p.oz = o.z;
-        p.dx = d.x; p.dy = d.y; p.dz = d.z;
+        set_dir(p, d);
         p.tm = tm;
-        p.t = R(0);
         p.tr = R(1); p.tg = R(1); p.tb = R(1);
-        p.ref = REF_MISS;
         p.bounce = 0;
         p.pixel = pixel;
         p.sample = sample;
         p.fb = lp;
+        p.pad0 = p.pad1 = 0;
         store_filter<R>(filt + base + k, o, d, rp.bsmall, rp.bmax);
         }
         warp_store_records<R>(tile, out + base + k0, k < n ? (int)(k - k0) : -1, count, p);
@@ -352,13 +360,20 @@ __global__ void __launch_bounds__(SHADE_BLOCK, MINB) k_raygen(const Control* __r
 template <typename R>
 struct RenderTraceIO {
     const DevScene<R>& sc;
-    PathRec<R>* paths;
+    const PathRec<R>* paths;  // read only: the closest hit goes to the material queue
     Control* ctl;
-    uint2* queues;
+    uint2* queues;  // Q_COUNT queues of `pool` entries, then HIT_QUEUES arrays of `pool` HitEntry<R>
     const FilterRec* filt;
     uint32_t n, pool;
     const uint32_t* remap;  // non-null: work item k is path remap[k] (the retry list of the order-free engine)
     uint32_t* cur;
+    // Record loads that do not allocate in L1 (ld.global.cg).  The trace kernels used to WRITE the closest hit into the record
+    // they had just read, which as a side effect threw the streamed line out of the L1; since the hit travels in the queue the
+    // lines stayed and pushed the scene out: teapot (1.4 MB of tree + triangles against ~77 KB of L1 per SM) lost 6 points of
+    // L1 hit rate and 37 % on its big wavefronts (ncu, gpurun_out/r02q_teapot_*.csv).  The shared-memory build keeps its
+    // scene out of the L1 and keeps the allocating streaming loads (one miss per record instead of three L2 requests).
+    bool bypass_l1;
+    __device__ __forceinline__ int4 ld_rec16(const void* p) const { return bypass_l1 ? __ldcg(reinterpret_cast<const int4*>(p)) : ld_stream16(p); }
     __device__ __forceinline__ uint32_t count() const { return n; }
     __device__ __forceinline__ uint32_t* cursor() const { return cur; }
     __device__ __forceinline__ uint32_t path_of(uint32_t k) const { return remap ? remap[k] : k; }
@@ -367,21 +382,20 @@ struct RenderTraceIO {
         FilterRec r;
         const int4* s = reinterpret_cast<const int4*>(filt + path_of(k));
         int4* d = reinterpret_cast<int4*>(&r);
-        d[0] = ld_stream16(s); d[1] = ld_stream16(s + 1); d[2] = ld_stream16(s + 2);  // streamed once: keep the L1 for the scene
+        d[0] = ld_rec16(s); d[1] = ld_rec16(s + 1); d[2] = ld_rec16(s + 2);  // streamed once: keep the L1 for the scene
         return unpack_filter(r);
     }
     __device__ __forceinline__ void load(uint32_t k, V3<R>& o, V3<R>& d) const {
-        const PathRec<R>* p = paths + path_of(k);  // sectors A and B of the record: origin + direction
+        const PathRec<R>* p = paths + path_of(k);  // first 48 B of the record: origin + direction
         if constexpr (sizeof(R) == 8) {
-            const int4 a = ld_stream16(&p->ox);
-            const double b = ld_stream8(&p->oz);
-            const int4 c = ld_stream16(&p->dx);
-            const double e = ld_stream8(&p->dz);
-            o = {__hiloint2double(a.y, a.x), __hiloint2double(a.w, a.z), b};
-            d = {__hiloint2double(c.y, c.x), __hiloint2double(c.w, c.z), e};
+            const int4 a = ld_rec16(&p->ox);
+            const int4 b = ld_rec16(&p->oz);
+            const int4 c = ld_rec16(&p->dy);
+            o = {__hiloint2double(a.y, a.x), __hiloint2double(a.w, a.z), __hiloint2double(b.y, b.x)};
+            d = {__hiloint2double(b.w, b.z), __hiloint2double(c.y, c.x), __hiloint2double(c.w, c.z)};
         } else {
-            const int4 a = ld_stream16(&p->ox);
-            const int4 b = ld_stream16(&p->dx);
+            const int4 a = ld_rec16(&p->ox);
+            const int4 b = ld_rec16(&p->dx);
             o = {__int_as_float(a.x), __int_as_float(a.y), __int_as_float(a.z)};
             d = {__int_as_float(b.x), __int_as_float(b.y), __int_as_float(b.z)};
         }
@@ -394,8 +408,6 @@ struct RenderTraceIO {
         uint32_t i = 0;
         if (has) {
             i = path_of(k);
-            __stcs(&paths[i].t, t);
-            __stcs(&paths[i].ref, ref);
             if (ref == REF_MISS) {
                 q = Q_MISS;
             } else {
@@ -408,28 +420,40 @@ struct RenderTraceIO {
         }
         const uint32_t pos = warp_enqueue(ctl->queue_count, q);
         if (q >= 0) __stcs(&queues[(size_t)q * pool + pos], make_uint2(i, minfo));
+        if (q >= (int)Q_LAMBERTIAN && q < (int)Q_LAMBERTIAN + HIT_QUEUES) {  // the scatter shaders' (ref, t)
+            HitEntry<R>* hits = reinterpret_cast<HitEntry<R>*>(queues + (size_t)Q_COUNT * pool);
+            HitEntry<R> he;
+            he.t = t;
+            he.ref = ref;
+            if constexpr (sizeof(R) == 8) {
+                he.pad = 0;
+                __stcs(reinterpret_cast<int4*>(hits + (size_t)(q - (int)Q_LAMBERTIAN) * pool + pos), *reinterpret_cast<const int4*>(&he));
+            } else {
+                __stcs(reinterpret_cast<int2*>(hits + (size_t)(q - (int)Q_LAMBERTIAN) * pool + pos), *reinterpret_cast<const int2*>(&he));
+            }
+        }
     }
 };
 
 // remap == nullptr: the whole wavefront of side `side`; otherwise the retry list the order-free kernel left behind
 template <typename R, int REFILL, int MINB, bool ANIM>
-__global__ void __launch_bounds__(TRACE_BLOCK, MINB) k_trace(DevScene<R> sc, PathRec<R>* __restrict__ paths, Control* __restrict__ ctl,
+__global__ void __launch_bounds__(TRACE_BLOCK, MINB) k_trace(DevScene<R> sc, const PathRec<R>* __restrict__ paths, Control* __restrict__ ctl,
                                                         int side, uint2* __restrict__ queues, const FilterRec* __restrict__ filt, uint32_t pool,
                                                         const uint32_t* __restrict__ remap) {
     __shared__ LaneSlots<R, TRACE_BLOCK, ANIM> slots;
     RenderTraceIO<R> io{sc, paths, ctl, queues, filt, remap ? ctl->retry_count : ctl->n_in[side], pool, remap,
-                        remap ? &ctl->retry_next : &ctl->trace_next};
+                        remap ? &ctl->retry_next : &ctl->trace_next, sc.rec_bypass_l1 != 0};
     if (io.n == 0u) return;
     trace_persistent<R, REFILL, TRACE_BLOCK, ANIM>(sc, R(0.001), Num<R>::inf(), io, &slots);  // ray_casting.rs:119
 }
 
 // The order-free engine over the wavefront (fast_trace.cuh); undecidable rays go to retry_list for k_trace above.
 template <typename R, int MINB>
-__global__ void __launch_bounds__(TRACE_BLOCK, MINB) k_trace_fast(DevScene<R> sc, PathRec<R>* __restrict__ paths, Control* __restrict__ ctl,
+__global__ void __launch_bounds__(TRACE_BLOCK, MINB) k_trace_fast(DevScene<R> sc, const PathRec<R>* __restrict__ paths, Control* __restrict__ ctl,
                                                              int side, uint2* __restrict__ queues, const FilterRec* __restrict__ filt,
                                                              uint32_t pool, uint32_t* __restrict__ retry_list) {
     __shared__ FastSlots<R, TRACE_BLOCK> slots;
-    RenderTraceIO<R> io{sc, paths, ctl, queues, filt, ctl->n_in[side], pool, nullptr, &ctl->trace_next};
+    RenderTraceIO<R> io{sc, paths, ctl, queues, filt, ctl->n_in[side], pool, nullptr, &ctl->trace_next, sc.rec_bypass_l1 != 0};
     fast_trace_persistent<R, TRACE_BLOCK, false>(sc, R(0.001), Num<R>::inf(), io, &slots, retry_list, &ctl->retry_count);
 }
 
@@ -457,7 +481,7 @@ static __host__ __device__ FastSmemLayout fast_smem_layout(uint32_t n_fast_nodes
     return l;
 }
 template <typename R>
-__global__ void __launch_bounds__(FAST_BIG_BLOCK, 1) k_trace_fast_smem(DevScene<R> sc, PathRec<R>* __restrict__ paths, Control* __restrict__ ctl,
+__global__ void __launch_bounds__(FAST_BIG_BLOCK, 1) k_trace_fast_smem(DevScene<R> sc, const PathRec<R>* __restrict__ paths, Control* __restrict__ ctl,
                                                                        int side, uint2* __restrict__ queues, const FilterRec* __restrict__ filt,
                                                                        uint32_t pool, uint32_t* __restrict__ retry_list, uint32_t n_fast_nodes,
                                                                        uint32_t n_fast_prims, uint32_t n_sph, uint32_t n_tri, uint32_t n_quad,
@@ -496,7 +520,7 @@ __global__ void __launch_bounds__(FAST_BIG_BLOCK, 1) k_trace_fast_smem(DevScene<
     }
     __syncthreads();
     const uint32_t base = (uint32_t)__cvta_generic_to_shared(fast_smem);
-    RenderTraceIO<R> io{sc, paths, ctl, queues, filt, ctl->n_in[side], pool, nullptr, &ctl->trace_next};
+    RenderTraceIO<R> io{sc, paths, ctl, queues, filt, ctl->n_in[side], pool, nullptr, &ctl->trace_next, false};
     SmemTree tree;
     tree.node_stride = node_stride;
     tree.nodes = base + l.nodes; tree.prims = base + l.prims; tree.spheres32 = base + l.spheres32; tree.spheres = base + l.spheres;
@@ -537,19 +561,20 @@ __global__ void __launch_bounds__(SHADE_BLOCK, 8) k_shade_miss(DevScene<R> sc, c
         const PathRec<R>* rec = in + queue[k].x;
         V3<R> d, thr;
         uint32_t fbi;
-        if constexpr (sizeof(R) == 8) {  // sectors B and C only: direction + fb, throughput
-            const double2 a = *reinterpret_cast<const double2*>(&rec->dx);
-            const int4 b = *reinterpret_cast<const int4*>(&rec->dz);
-            const double2 c = *reinterpret_cast<const double2*>(&rec->tr);
-            d = {a.x, a.y, __hiloint2double(b.y, b.x)};
-            fbi = (uint32_t)b.z;
-            thr = {c.x, c.y, rec->tb};
+        if constexpr (sizeof(R) == 8) {  // the second 64 B half only: throughput, the direction's copy, fb
+            const double2 a = *reinterpret_cast<const double2*>(&rec->tr);
+            const double2 b = *reinterpret_cast<const double2*>(&rec->tb);
+            const double2 c = *reinterpret_cast<const double2*>(&rec->dy2);
+            const int4 e = *reinterpret_cast<const int4*>(&rec->pixel);
+            thr = {a.x, a.y, b.x};
+            d = {b.y, c.x, c.y};
+            fbi = (uint32_t)e.w;
         } else {
             const float4 a = *reinterpret_cast<const float4*>(&rec->dx);
             const float4 b = *reinterpret_cast<const float4*>(&rec->tr);
             d = {a.x, a.y, a.z};
             thr = {b.x, b.y, b.z};
-            fbi = rec->fb;
+            fbi = (uint32_t)__float_as_int(b.w);
         }
         const V3<R> sky = sky_color<R>(sc, d);
         const V3<R> c = col_mul(thr, sky, cl);
@@ -565,12 +590,12 @@ __global__ void __launch_bounds__(SHADE_BLOCK) k_shade_emissive(DevScene<R> sc, 
                                                                  unsigned long long* __restrict__ fb, double fb_scale) {
     const uint32_t n = ctl->queue_count[Q_EMISSIVE];
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-        PathRec<R> p;
         const uint2 e = queue[k];
-        load_path(in + e.x, p);
+        const PathRec<R>* rec = in + e.x;
+        const R tr = rec->tr, tg = rec->tg, tb = rec->tb;
+        const uint32_t fbi = rec->fb;
         const DevMaterial& mat = sc.mats[e.y & 0x00FFFFFFu];
-        fb_add(fb, p.fb, (double)(p.tr * (R)mat.emit[0]), (double)(p.tg * (R)mat.emit[1]), (double)(p.tb * (R)mat.emit[2]),
-               fb_scale);
+        fb_add(fb, fbi, (double)(tr * (R)mat.emit[0]), (double)(tg * (R)mat.emit[1]), (double)(tb * (R)mat.emit[2]), fb_scale);
     }
 }
 
@@ -579,11 +604,12 @@ __global__ void __launch_bounds__(SHADE_BLOCK) k_shade_emissive(DevScene<R> sc, 
 // (p.ref, p.t): rebuilds the HitRecord, draws from the (pixel, sample, bounce) stream, and on survival
 // turns p into the scattered ray.  Shared by the material-sorted shade kernels and the tail kernel.
 template <typename R, int MAT, bool ANIM>
-__device__ __forceinline__ bool scatter_path(const DevScene<R>& sc, PathRec<R>& p, uint32_t minfo, uint64_t seed, uint32_t max_depth) {
+__device__ __forceinline__ bool scatter_path(const DevScene<R>& sc, PathRec<R>& p, uint32_t hit_ref, R hit_t, uint32_t minfo, uint64_t seed,
+                                             uint32_t max_depth) {
     const bool cl = sc.clamp_colors != 0;
     const V3<R> o = {p.ox, p.oy, p.oz}, d = {p.dx, p.dy, p.dz};
     // u, v are needed only when a Lambertian's texture tree reaches an image
-    const HitInfo<R> h = finalize_geom<R, ANIM>(sc, p.ref, p.t, o, d, (minfo >> 31) != 0u, p.tm);
+    const HitInfo<R> h = finalize_geom<R, ANIM>(sc, hit_ref, hit_t, o, d, (minfo >> 31) != 0u, p.tm);
     const DevMaterial& mat = sc.mats[minfo & 0x00FFFFFFu];
     const uint32_t bounce = p.bounce + 1;  // this is the bounce-th hit of the path
     Rng<R> g(seed, p.pixel, p.sample, bounce);
@@ -623,10 +649,9 @@ __device__ __forceinline__ bool scatter_path(const DevScene<R>& sc, PathRec<R>& 
     if (alive) {
         const V3<R> thr = col_mul(V3<R>{p.tr, p.tg, p.tb}, att, cl);
         p.ox = h.p.x; p.oy = h.p.y; p.oz = h.p.z;
-        p.dx = nd.x; p.dy = nd.y; p.dz = nd.z;
+        set_dir(p, nd);
         p.tr = thr.x; p.tg = thr.y; p.tb = thr.z;
         p.bounce = bounce;
-        p.ref = REF_MISS;
     }
     return alive;
 }
@@ -635,8 +660,8 @@ __device__ __forceinline__ bool scatter_path(const DevScene<R>& sc, PathRec<R>& 
 template <typename R, int MAT, int MINB, bool ANIM>
 __global__ void __launch_bounds__(SHADE_BLOCK, MINB) k_shade_scatter(DevScene<R> sc, const PathRec<R>* __restrict__ in,
                                                                       PathRec<R>* __restrict__ out, Control* __restrict__ ctl, int nxt,
-                                                                      const uint2* __restrict__ queue, FilterRec* __restrict__ filt_out,
-                                                                      uint64_t seed, uint32_t max_depth) {
+                                                                      const uint2* __restrict__ queue, const HitEntry<R>* __restrict__ hits,
+                                                                      FilterRec* __restrict__ filt_out, uint64_t seed, uint32_t max_depth) {
     const uint32_t n = ctl->queue_count[Q_LAMBERTIAN + MAT];
     if (n == 0) return;
     __shared__ int4 s_tile[SHADE_BLOCK * (sizeof(PathRec<R>) / 16)];
@@ -647,8 +672,9 @@ __global__ void __launch_bounds__(SHADE_BLOCK, MINB) k_shade_scatter(DevScene<R>
         PathRec<R> p;
         if (k < n) {
             const uint2 e = queue[k];
+            const HitEntry<R> he = hits[k];
             load_path(in + e.x, p);
-            alive = scatter_path<R, MAT, ANIM>(sc, p, e.y, seed, max_depth);
+            alive = scatter_path<R, MAT, ANIM>(sc, p, he.ref, he.t, e.y, seed, max_depth);
         }
         const uint32_t amask = __ballot_sync(0xffffffffu, alive);
         if (amask != 0u) {  // warp-uniform
@@ -711,15 +737,13 @@ __global__ void __launch_bounds__(TRACE_BLOCK, 4) k_tail(DevScene<R> sc, const P
                 alive = false;
                 continue;
             }
-            p.ref = ref;
-            p.t = t;
-            const uint32_t kind = ref_kind(p.ref);
-            const PrimMeta pm = (kind == CR_PRIM_SPHERE ? sc.meta[0] : (kind == CR_PRIM_TRIANGLE ? sc.meta[1] : sc.meta[2]))[ref_index(p.ref)];
+            const uint32_t kind = ref_kind(ref);
+            const PrimMeta pm = (kind == CR_PRIM_SPHERE ? sc.meta[0] : (kind == CR_PRIM_TRIANGLE ? sc.meta[1] : sc.meta[2]))[ref_index(ref)];
             const uint32_t minfo = (uint32_t)pm.material | ((pm.mat_kind & MATKIND_NEEDS_UV) ? 0x80000000u : 0u);
             const int mk = pm.mat_kind & MATKIND_MASK;
-            if (mk == CR_MAT_LAMBERTIAN) alive = scatter_path<R, CR_MAT_LAMBERTIAN, ANIM>(sc, p, minfo, seed, max_depth);
-            else if (mk == CR_MAT_METAL) alive = scatter_path<R, CR_MAT_METAL, ANIM>(sc, p, minfo, seed, max_depth);
-            else if (mk == CR_MAT_DIELECTRIC) alive = scatter_path<R, CR_MAT_DIELECTRIC, ANIM>(sc, p, minfo, seed, max_depth);
+            if (mk == CR_MAT_LAMBERTIAN) alive = scatter_path<R, CR_MAT_LAMBERTIAN, ANIM>(sc, p, ref, t, minfo, seed, max_depth);
+            else if (mk == CR_MAT_METAL) alive = scatter_path<R, CR_MAT_METAL, ANIM>(sc, p, ref, t, minfo, seed, max_depth);
+            else if (mk == CR_MAT_DIELECTRIC) alive = scatter_path<R, CR_MAT_DIELECTRIC, ANIM>(sc, p, ref, t, minfo, seed, max_depth);
             else {  // EXTENSION emissive
                 const DevMaterial& mat = sc.mats[pm.material];
                 fb_add(fb, p.fb, (double)(p.tr * (R)mat.emit[0]), (double)(p.tg * (R)mat.emit[1]), (double)(p.tb * (R)mat.emit[2]), fb_scale);
@@ -851,6 +875,9 @@ static DevScene<R> make_dev_scene(const SceneDeviceData& s) {
     d.clamp_colors = s.clamp_colors;
     d.node_slice = s.node_slice;
     if (const char* e = getenv("CRB_NODE_SLICE")) d.node_slice = atoi(e) > 0 ? atoi(e) : 8;
+    // (a scene far beyond the caches gains nothing from a protected L1: 10 M triangles, +0.8 % with the bypass, A/B r02r)
+    d.rec_bypass_l1 = ((uint64_t)s.n_prims[0] + s.n_prims[1] + s.n_prims[2]) <= (1u << 18) ? 1 : 0;
+    if (const char* e = getenv("CRB_REC_BYPASS")) d.rec_bypass_l1 = atoi(e) != 0;
     d.min_node_lanes = 8;
     if (const char* e = getenv("CRB_MIN_LANES")) d.min_node_lanes = atoi(e);
     d.free_pass_nodes = 31;
@@ -1037,6 +1064,7 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
     uint32_t pool = opts.pool_paths ? opts.pool_paths : (64u << 20);
     if (pool < 1024) pool = 1024;
     if ((uint64_t)pool > total && total > 0) pool = (uint32_t)((total + 31) & ~31ull);
+    pool = (pool + 31u) & ~31u;  // whole warps; also keeps the hit arrays behind the queues 16 B aligned
     // u64 fixed point: 2^-44 resolution unless max_radiance * spp would overflow 62 bits
     uint32_t scale_bits = 44u;
     while (scale_bits > 8u && s.max_radiance * (double)cam_in.samples * (double)(1ull << scale_bits) >= 4.0e18) --scale_bits;
@@ -1053,7 +1081,7 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
     const size_t o_cam = carve(sizeof(DevCamera));
     const size_t o_paths0 = carve((size_t)pool * sizeof(PathRec<R>));
     const size_t o_paths1 = carve((size_t)pool * sizeof(PathRec<R>));
-    const size_t o_queues = carve((size_t)pool * Q_COUNT * sizeof(uint2));
+    const size_t o_queues = carve((size_t)pool * Q_COUNT * sizeof(uint2) + (size_t)pool * HIT_QUEUES * sizeof(HitEntry<R>));  // queues, then their hits
     const size_t o_filt0 = carve((size_t)pool * sizeof(FilterRec));
     const size_t o_filt1 = carve((size_t)pool * sizeof(FilterRec));
     const size_t o_retry = carve((size_t)pool * sizeof(uint32_t));
@@ -1065,6 +1093,7 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
     DevCamera* d_cam = reinterpret_cast<DevCamera*>(base + o_cam);
     PathRec<R>* paths[2] = {reinterpret_cast<PathRec<R>*>(base + o_paths0), reinterpret_cast<PathRec<R>*>(base + o_paths1)};
     uint2* queues = reinterpret_cast<uint2*>(base + o_queues);
+    const HitEntry<R>* qhits = reinterpret_cast<const HitEntry<R>*>(queues + (size_t)Q_COUNT * pool);  // written by the trace kernels' commit
     FilterRec* filt[2] = {reinterpret_cast<FilterRec*>(base + o_filt0), reinterpret_cast<FilterRec*>(base + o_filt1)};
     unsigned long long* fb = reinterpret_cast<unsigned long long*>(base + o_fb);
     uint32_t* retry_list = reinterpret_cast<uint32_t*>(base + o_retry);
@@ -1110,7 +1139,7 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
     // +4 %); where the f64 exact / leaf steps dominate (thin padded boxes of the Cornell quads) the spills of the
     // small budget lose 20 %.  Unless CRB_MINB pins one, the first large wavefront of a scene is traced with both
     // (same rays, same result) and the faster one is kept; the choice is cached per device by scene signature.
-    typedef void (*TraceFn)(DevScene<R>, PathRec<R>*, Control*, int, uint2*, const FilterRec*, uint32_t, const uint32_t*);
+    typedef void (*TraceFn)(DevScene<R>, const PathRec<R>*, Control*, int, uint2*, const FilterRec*, uint32_t, const uint32_t*);
     const bool animated = s.anim_keys != nullptr;  // object keyframes: the builds that evaluate timelines at the ray time
     // Static scenes with a search tree run the order-free engine (fast_trace.cuh); the rays it hands back are traced by
     // the reference-order kernel in a second, small launch.  CR_RENDER_REFERENCE_ORDER keeps reference order throughout.
@@ -1185,7 +1214,7 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
     int smb = 6;
     if (const char* e = getenv("CRB_SHADE_MINB")) smb = atoi(e);
     typedef void (*GenFn)(const Control*, const DevCamera*, const RaygenParams<R>, PathRec<R>*, FilterRec*);
-    typedef void (*ScatFn)(DevScene<R>, const PathRec<R>*, PathRec<R>*, Control*, int, const uint2*, FilterRec*, uint64_t, uint32_t);
+    typedef void (*ScatFn)(DevScene<R>, const PathRec<R>*, PathRec<R>*, Control*, int, const uint2*, const HitEntry<R>*, FilterRec*, uint64_t, uint32_t);
     GenFn gen_fn = smb <= 4 ? k_raygen<R, 4> : smb <= 6 ? k_raygen<R, 6> : k_raygen<R, 8>;
     ScatFn lam_fn = animated ? k_shade_scatter<R, CR_MAT_LAMBERTIAN, 6, true>
                               : (smb <= 4 ? k_shade_scatter<R, CR_MAT_LAMBERTIAN, 4, false> : smb <= 6 ? k_shade_scatter<R, CR_MAT_LAMBERTIAN, 6, false> : k_shade_scatter<R, CR_MAT_LAMBERTIAN, 8, false>);
@@ -1273,12 +1302,12 @@ int render_impl(const SceneDeviceData& s, Workspace& ws, const CrCamera& cam_in,
         }
         tm.begin(1, a);
         k_shade_miss<R><<<g_miss, SHADE_BLOCK, 0, stream>>>(sc, paths[cur], ctl, queues + (size_t)Q_MISS * pool, fb, fb_scale);
-        lam_fn<<<g_lam, SHADE_BLOCK, 0, stream>>>(sc, paths[cur], paths[nxt], ctl, nxt, queues + (size_t)Q_LAMBERTIAN * pool, filt[nxt],
+        lam_fn<<<g_lam, SHADE_BLOCK, 0, stream>>>(sc, paths[cur], paths[nxt], ctl, nxt, queues + (size_t)Q_LAMBERTIAN * pool, qhits, filt[nxt],
                                                   opts.seed, cam_in.max_depth);
-        met_fn<<<g_met, SHADE_BLOCK, 0, stream>>>(sc, paths[cur], paths[nxt], ctl, nxt, queues + (size_t)Q_METAL * pool, filt[nxt],
+        met_fn<<<g_met, SHADE_BLOCK, 0, stream>>>(sc, paths[cur], paths[nxt], ctl, nxt, queues + (size_t)Q_METAL * pool, qhits + (size_t)pool, filt[nxt],
                                                   opts.seed, cam_in.max_depth);
-        die_fn<<<g_die, SHADE_BLOCK, 0, stream>>>(sc, paths[cur], paths[nxt], ctl, nxt, queues + (size_t)Q_DIELECTRIC * pool, filt[nxt],
-                                                  opts.seed, cam_in.max_depth);
+        die_fn<<<g_die, SHADE_BLOCK, 0, stream>>>(sc, paths[cur], paths[nxt], ctl, nxt, queues + (size_t)Q_DIELECTRIC * pool, qhits + 2 * (size_t)pool,
+                                                  filt[nxt], opts.seed, cam_in.max_depth);
         launches += 5;
         if (!s.clamp_colors) {
             k_shade_emissive<R><<<g_emit, SHADE_BLOCK, 0, stream>>>(sc, paths[cur], ctl, queues + (size_t)Q_EMISSIVE * pool, fb,
