@@ -557,28 +557,49 @@ __global__ void __launch_bounds__(SHADE_BLOCK, 8) k_shade_miss(DevScene<R> sc, c
                                                              unsigned long long* __restrict__ fb, double fb_scale) {
     const uint32_t n = ctl->queue_count[Q_MISS];
     const bool cl = sc.clamp_colors != 0;
-    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-        const PathRec<R>* rec = in + queue[k].x;
-        V3<R> d, thr;
-        uint32_t fbi;
-        if constexpr (sizeof(R) == 8) {  // the second 64 B half only: throughput, the direction's copy, fb
-            const double2 a = *reinterpret_cast<const double2*>(&rec->tr);
-            const double2 b = *reinterpret_cast<const double2*>(&rec->tb);
-            const double2 c = *reinterpret_cast<const double2*>(&rec->dy2);
-            const int4 e = *reinterpret_cast<const int4*>(&rec->pixel);
-            thr = {a.x, a.y, b.x};
-            d = {b.y, c.x, c.y};
-            fbi = (uint32_t)e.w;
-        } else {
-            const float4 a = *reinterpret_cast<const float4*>(&rec->dx);
-            const float4 b = *reinterpret_cast<const float4*>(&rec->tr);
-            d = {a.x, a.y, a.z};
-            thr = {b.x, b.y, b.z};
-            fbi = (uint32_t)__float_as_int(b.w);
+    // Two paths per thread and trip, all loads of both issued before anything is used: the kernel is a chain of dependent
+    // long-latency accesses (queue entry -> record -> three framebuffer reductions, 58 % of which miss the L2) and ran at 16 %
+    // issue, 62 % DRAM, 47 % L2 — bound by none of them (ncu, profiles/shade_book1_r02g.md), i.e. by memory-level parallelism.
+    constexpr int U = 2;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t k0 = blockIdx.x * blockDim.x + threadIdx.x; k0 < n; k0 += U * stride) {
+        uint32_t idx[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t k = k0 + (uint32_t)u * stride;
+            idx[u] = k < n ? __ldcs(&queue[k].x) : 0xFFFFFFFFu;
         }
-        const V3<R> sky = sky_color<R>(sc, d);
-        const V3<R> c = col_mul(thr, sky, cl);
-        fb_add(fb, fbi, (double)c.x, (double)c.y, (double)c.z, fb_scale);
+        int4 w[U][sizeof(R) == 8 ? 4 : 2];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (idx[u] == 0xFFFFFFFFu) continue;
+            const PathRec<R>* rec = in + idx[u];
+            if constexpr (sizeof(R) == 8) {  // the second 64 B half only: throughput, the direction's copy, pixel / sample / bounce / fb
+                const int4* q = reinterpret_cast<const int4*>(&rec->tr);
+                w[u][0] = __ldcs(q); w[u][1] = __ldcs(q + 1); w[u][2] = __ldcs(q + 2); w[u][3] = __ldcs(q + 3);
+            } else {
+                w[u][0] = __ldcs(reinterpret_cast<const int4*>(&rec->dx));
+                w[u][1] = __ldcs(reinterpret_cast<const int4*>(&rec->tr));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (idx[u] == 0xFFFFFFFFu) continue;
+            V3<R> d, thr;
+            uint32_t fbi;
+            if constexpr (sizeof(R) == 8) {
+                thr = {__hiloint2double(w[u][0].y, w[u][0].x), __hiloint2double(w[u][0].w, w[u][0].z), __hiloint2double(w[u][1].y, w[u][1].x)};
+                d = {__hiloint2double(w[u][1].w, w[u][1].z), __hiloint2double(w[u][2].y, w[u][2].x), __hiloint2double(w[u][2].w, w[u][2].z)};
+                fbi = (uint32_t)w[u][3].w;
+            } else {
+                d = {__int_as_float(w[u][0].x), __int_as_float(w[u][0].y), __int_as_float(w[u][0].z)};
+                thr = {__int_as_float(w[u][1].x), __int_as_float(w[u][1].y), __int_as_float(w[u][1].z)};
+                fbi = (uint32_t)w[u][1].w;
+            }
+            const V3<R> sky = sky_color<R>(sc, d);
+            const V3<R> c = col_mul(thr, sky, cl);
+            fb_add(fb, fbi, (double)c.x, (double)c.y, (double)c.z, fb_scale);
+        }
     }
 }
 
