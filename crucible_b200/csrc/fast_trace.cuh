@@ -114,6 +114,11 @@ struct SmemTree {
     // kernel's shared-memory wavefronts).  At 80 the group is (5 cur + j) mod 8, a bijection of cur mod 8: distinct nodes
     // spread over all banks, with the same base + immediate addressing (no extra instruction), for 25 % more node memory.
     uint32_t node_stride;
+    // Quad records (128 B in f64) likewise: at a stride of 128 B every record starts in the same bank, so the eight LDS.128 of
+    // a quad test by lanes on DIFFERENT quads conflict completely (ncu, Cornell box, profiles/trace_cornell_r02u.md: 12.6
+    // wavefronts per LDS.128 where 3.2 were needed; those loads were 65 % of the kernel's 1.6 G shared-memory wavefronts, the
+    // L1 data pipe at 89 %).  Stride = record + 16 B: bank group (9 quad + j) mod 8.
+    uint32_t quad_stride;
     // the primitive records of the leaf tests (R precision) and, per leaf-table entry, the box of the primitive's
     // REFERENCE leaf node (the candidate confirmation): with these the kernel reads no scene data from global memory
     uint32_t spheres, tris, quads, leafbox;
@@ -306,7 +311,7 @@ struct FastTrav {
                     hit = tri_hit_t(lds_rec<TriRec<R>>(tree.tris + idx * (uint32_t)sizeof(TriRec<R>)), o, d, tmin, tmax, c);
                 } else {
                     R al, be;
-                    hit = quad_hit_t(lds_rec<QuadRec<R>>(tree.quads + idx * (uint32_t)sizeof(QuadRec<R>)), o, d, tmin, tmax, c, al, be);
+                    hit = quad_hit_t(lds_rec<QuadRec<R>>(tree.quads + idx * tree.quad_stride), o, d, tmin, tmax, c, al, be);
                 }
                 if (!hit) continue;
             } else {

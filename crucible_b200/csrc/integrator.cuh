@@ -476,7 +476,7 @@ static __host__ __device__ FastSmemLayout fast_smem_layout(uint32_t n_fast_nodes
     l.spheres = l.spheres32 + up(n_sph * 16u);
     l.tris = l.spheres + up(n_sph * (uint32_t)sizeof(SphereRec<R>));
     l.quads = l.tris + up(n_tri * (uint32_t)sizeof(TriRec<R>));
-    l.leafbox = l.quads + up(n_quad * (uint32_t)sizeof(QuadRec<R>));
+    l.leafbox = l.quads + up(n_quad * ((uint32_t)sizeof(QuadRec<R>) + 16u));  // quad records padded by 16 B (SmemTree::quad_stride)
     l.total = l.leafbox + up(n_fast_prims * (uint32_t)sizeof(LeafBox<R>));
     return l;
 }
@@ -516,13 +516,19 @@ __global__ void __launch_bounds__(FAST_BIG_BLOCK, 1) k_trace_fast_smem(DevScene<
         copy16(l.spheres32, sc.spheres32, n_sph);
         copy16(l.spheres, sc.spheres, n_sph * (uint32_t)(sizeof(SphereRec<R>) / 16));
         copy16(l.tris, sc.tris, n_tri * (uint32_t)(sizeof(TriRec<R>) / 16));
-        copy16(l.quads, sc.quads, n_quad * (uint32_t)(sizeof(QuadRec<R>) / 16));
+        {  // quad records at a stride of sizeof + 16 B (see SmemTree::quad_stride)
+            int4* d = reinterpret_cast<int4*>(fast_smem + l.quads);
+            const int4* s = reinterpret_cast<const int4*>(sc.quads);
+            constexpr uint32_t W = (uint32_t)(sizeof(QuadRec<R>) / 16);
+            for (uint32_t i = threadIdx.x; i < n_quad * W; i += blockDim.x) d[(i / W) * (W + 1u) + (i % W)] = __ldg(s + i);
+        }
     }
     __syncthreads();
     const uint32_t base = (uint32_t)__cvta_generic_to_shared(fast_smem);
     RenderTraceIO<R> io{sc, paths, ctl, queues, filt, ctl->n_in[side], pool, nullptr, &ctl->trace_next, false};
     SmemTree tree;
     tree.node_stride = node_stride;
+    tree.quad_stride = (uint32_t)sizeof(QuadRec<R>) + 16u;
     tree.nodes = base + l.nodes; tree.prims = base + l.prims; tree.spheres32 = base + l.spheres32; tree.spheres = base + l.spheres;
     tree.tris = base + l.tris; tree.quads = base + l.quads; tree.leafbox = base + l.leafbox;
     fast_trace_persistent<R, FAST_BIG_BLOCK, true, FAST_BIG_LEVELS>(sc, R(0.001), Num<R>::inf(), io, slots, retry_list, &ctl->retry_count, tree);
