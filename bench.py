@@ -224,7 +224,7 @@ def main():
 
     def add_stats(acc, st):
         for k, v in st.items():
-            acc[k] = acc.get(k, 0) + v
+            acc[k] = v if k == "trace_engine" else acc.get(k, 0) + v  # an id, not a quantity: the last frame's
         return acc
 
     def step(time_kernels):
