@@ -111,6 +111,7 @@ SIGNATURES = {
     "cr_scene_add_spheres": (C.c_int64, [_P, _P, _P, _P, C.c_size_t]),
     "cr_scene_add_triangles": (C.c_int64, [_P, _P, _P, _P, C.c_size_t]),
     "cr_scene_add_quads": (C.c_int64, [_P, _P, _P, _P, C.c_size_t]),
+    "cr_scene_add_batches": (C.c_int64, [_P, C.c_size_t, _P, _P, _P, _P, _P]),
     "cr_scene_begin_group": (C.c_int, [_P, C.c_int]),
     "cr_scene_end_group": (C.c_int, [_P]),
     "cr_scene_set_hidden": (C.c_int, [_P, C.c_size_t, C.c_int]),

@@ -54,6 +54,8 @@ struct Element {  // one entry of Scene.elements (scene/mod.rs:77), insertion or
     bool hide;
     Box box;
 };
+template <>
+struct pool_no_init<Element> : std::true_type {};  // kind / idx / hide are written by the add call, the box by ensure_boxes at commit
 typedef HostVec<Element> ElementVec;  // 64 B per primitive: 640 MB for the 10 M-triangle scene, cached between scenes (host_pool.h)
 
 static constexpr uint32_t FLAT_ALWAYS_PASS = 0x100u;  // FlatNode::axis flag: member of a nested HitList, no box test (api.cu GroupEmitter)

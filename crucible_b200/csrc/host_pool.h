@@ -15,6 +15,8 @@
 #include <map>
 #include <mutex>
 #include <new>
+#include <type_traits>
+#include <utility>
 #include <vector>
 
 namespace crb {
@@ -108,9 +110,24 @@ private:
     uint64_t hits_ = 0, misses_ = 0;
 };
 
+// Types whose default construction a HostVec may skip entirely (every field is written before it is read); everything else
+// is DEFAULT-initialised by resize() / the sizing constructor, i.e. trivial types (double, int32_t, uchar4, plain structs)
+// are left uninitialised instead of being zero-filled: the arrays are hundreds of megabytes and are filled right after,
+// often by several threads.  resize(n, value) and copies are unaffected.
+template <typename T>
+struct pool_no_init : std::false_type {};
+
 template <typename T>
 struct PoolAlloc {
     using value_type = T;
+    template <typename U>
+    void construct(U* p) noexcept(std::is_nothrow_default_constructible<U>::value) {
+        if constexpr (!pool_no_init<U>::value) ::new (static_cast<void*>(p)) U;
+    }
+    template <typename U, typename A0, typename... A>
+    void construct(U* p, A0&& a0, A&&... a) {
+        ::new (static_cast<void*>(p)) U(std::forward<A0>(a0), std::forward<A>(a)...);
+    }
     PoolAlloc() noexcept = default;
     template <typename U>
     PoolAlloc(const PoolAlloc<U>&) noexcept {}

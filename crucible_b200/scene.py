@@ -413,24 +413,55 @@ class SceneDesc:
             if rc < 0:
                 raise abi.CrucibleError(rc, f("last_error")().decode())
         cache = self.__dict__.setdefault("_c_args", {})
-        for kind, data, mat, oid in self.batches:
-            if kind in (abi.GROUP_BEGIN, abi.GROUP_END):
-                rc = f("scene_begin_group")(handle, int(mat[0])) if kind == abi.GROUP_BEGIN else f("scene_end_group")(handle)
-                if rc < 0:
-                    raise abi.CrucibleError(rc, f("last_error")().decode())
-                continue
+        live = {id(b[1]) for b in self.batches}
+        for k in [k for k in cache if k not in live]:  # batches that were replaced since the last call
+            del cache[k]
+
+        def c_args(data, mat, oid):
             # the converted arrays and their pointers are kept with the batch: a mesh world is ~1 600 batches, and a caller
             # that rebuilds the scene every frame (Scene::render_image) would pay numpy / ctypes bookkeeping for each again
-            key = id(data)
-            hit = cache.get(key)
+            hit = cache.get(id(data))
             if hit is None or hit[0] is not data:
                 cd, cm, co = np.ascontiguousarray(data, np.float64), np.ascontiguousarray(mat, np.int32), np.ascontiguousarray(oid, np.int32)
                 hit = (data, cd, cm, co, cd.ctypes.data_as(C.c_void_p), cm.ctypes.data_as(C.c_void_p), co.ctypes.data_as(C.c_void_p))
                 if cd is data and cm is mat and co is oid:  # only views of the batch's own memory are kept (no stale copies)
-                    cache[key] = hit
-            rc = f(add[kind])(handle, hit[4], hit[5], hit[6], len(data))
-            if rc < 0:
-                raise abi.CrucibleError(rc, f(("last_error"))().decode())
+                    cache[id(data)] = hit
+            return hit
+
+        def flush(run):
+            """The primitive batches collected since the last group marker: one cr_scene_add_batches call when the library
+            has it (validated and copied on all host threads), else one add call per batch (the oracle)."""
+            if not run:
+                return
+            if len(run) > 1 and hasattr(lib, prefix + "scene_add_batches"):
+                n = len(run)
+                hits = [c_args(d, m, o) for _, d, m, o in run]  # (keeps converted copies alive during the call)
+                kinds = (C.c_int32 * n)(*[k for k, _, _, _ in run])
+                counts = (C.c_size_t * n)(*[len(d) for _, d, _, _ in run])
+                pd = (C.c_void_p * n)(*[h[4].value for h in hits])
+                pm = (C.c_void_p * n)(*[h[5].value for h in hits])
+                po = (C.c_void_p * n)(*[h[6].value for h in hits])
+                rc = f("scene_add_batches")(handle, n, kinds, pd, pm, po, counts)
+                if rc < 0:
+                    raise abi.CrucibleError(rc, f("last_error")().decode())
+            else:
+                for kind, data, mat, oid in run:
+                    hit = c_args(data, mat, oid)
+                    rc = f(add[kind])(handle, hit[4], hit[5], hit[6], len(data))
+                    if rc < 0:
+                        raise abi.CrucibleError(rc, f(("last_error"))().decode())
+            run.clear()
+
+        run = []
+        for kind, data, mat, oid in self.batches:
+            if kind in (abi.GROUP_BEGIN, abi.GROUP_END):
+                flush(run)
+                rc = f("scene_begin_group")(handle, int(mat[0])) if kind == abi.GROUP_BEGIN else f("scene_end_group")(handle)
+                if rc < 0:
+                    raise abi.CrucibleError(rc, f("last_error")().decode())
+                continue
+            run.append((kind, data, mat, oid))
+        flush(run)
         for im in self.images:
             im = np.ascontiguousarray(im, np.uint8)
             rc = f("scene_add_image")(handle, im.ctypes.data_as(C.c_void_p), im.shape[1], im.shape[0])

@@ -223,6 +223,13 @@ int64_t cr_scene_add_triangles(CrScene*, const double* abc, const int32_t* mater
 /* EXTENSION: quads Q,u,v = [n][9]. */
 int64_t cr_scene_add_quads(CrScene*, const double* quv, const int32_t* material,
                            const int32_t* obj_id, size_t n);
+/* Many add calls in one: batch b appends counts[b] primitives of kind kinds[b] (CR_PRIM_SPHERE: data[b] = [n][4],
+ * CR_PRIM_TRIANGLE / CR_PRIM_QUAD: [n][9]) exactly as the matching cr_scene_add_* call would, in order; material / obj_id may be
+ * NULL, and so may their entries.  A flattener that walks Scene.elements (scene/mod.rs:75-82) has one batch per mesh
+ * (load_asset, scene/mod.rs:211-229); together they are validated and copied on all host threads.  Returns the index of the
+ * first appended primitive; on error nothing is appended. */
+int64_t cr_scene_add_batches(CrScene*, size_t n_batches, const int32_t* kinds, const double* const* data,
+                             const int32_t* const* material, const int32_t* const* obj_id, const size_t* counts);
 /* ---- nested elements: Scene::add_element also takes a whole Hittables::HitList or Hittables::BVHWrapper as ONE element
  *      (scene/mod.rs:160-166).  Primitives added between cr_scene_begin_group and the matching cr_scene_end_group are the
  *      members of that element, in call order; groups nest.  Members keep flat prim_index values in call order.

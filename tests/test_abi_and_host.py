@@ -296,3 +296,73 @@ def test_reserve_and_cached_staging_blocks_change_nothing(crlib):
     nodes, order = build(True)
     assert nodes == ref_nodes and np.array_equal(order, ref_order)
     assert lib.cr_scene_reserve(None, 1, 1, 1) == abi.CR_ERR_INVALID
+
+
+def test_add_batches_equals_the_separate_calls(crlib):
+    """cr_scene_add_batches (one call for a run of elements, validated and copied on all host threads) builds the scene the
+    separate cr_scene_add_* calls build: same prim indices, same tree, same DFS leaf order; a bad batch leaves the scene untouched."""
+    lib = crlib
+    rng = np.random.default_rng(9)
+    per = 3000
+    runs = []  # (kind, data, material, obj_id)
+    runs.append((abi.CR_PRIM_SPHERE, np.array([[0.0, -1000.0, 0.0, 1000.0], [2.0, 1.0, 0.0, 1.0]]), np.array([0, 1], np.int32), None))
+    for k in range(30):  # 90 000 triangles: enough for the threaded path (>= 64 K primitives)
+        tri = (rng.uniform(-40, 40, (per, 1, 3)) + rng.uniform(-1, 1, (per, 3, 3))).reshape(per, 9)
+        runs.append((abi.CR_PRIM_TRIANGLE, tri, np.full(per, k % 3, np.int32), np.full(per, 100 + k, np.int32) if k % 2 else None))
+    runs.append((abi.CR_PRIM_QUAD, np.array([[0.0, 0, 0, 1, 0, 0, 0, 1, 0]]), None, None))
+    runs.append((abi.CR_PRIM_SPHERE, np.array([[5.0, 1.0, 5.0, 0.5]]), np.array([2], np.int32), np.array([7], np.int32)))
+    m = (abi.CrMaterial * 3)(abi.CrMaterial(kind=abi.CR_MAT_LAMBERTIAN, scatter_prob=1.0), abi.CrMaterial(kind=abi.CR_MAT_METAL),
+                             abi.CrMaterial(kind=abi.CR_MAT_DIELECTRIC, ior=1.5))
+    t = abi.CrTexture(kind=abi.CR_TEX_SOLID)
+    ptr = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+    add = {abi.CR_PRIM_SPHERE: lib.cr_scene_add_spheres, abi.CR_PRIM_TRIANGLE: lib.cr_scene_add_triangles, abi.CR_PRIM_QUAD: lib.cr_scene_add_quads}
+
+    def finish(h):
+        assert lib.cr_scene_set_materials(h, C.cast(m, C.c_void_p), 3) == 0 and lib.cr_scene_set_textures(h, C.byref(t), 1) == 0
+        assert lib.cr_scene_set_bvh_builder(h, abi.CR_BVH_HOST) == 0 and lib.cr_scene_commit(h) == 0, lib.cr_last_error()
+        n = lib.cr_scene_bvh_nodes(h, None, 0)
+        nodes = np.zeros(n, dtype=abi.BVH_NODE_DTYPE)
+        assert lib.cr_scene_bvh_nodes(h, nodes.ctypes.data_as(C.c_void_p), n) == n
+        k = lib.cr_scene_bvh_leaf_order(h, None, 0)
+        order = np.empty(k, np.int32)
+        assert lib.cr_scene_bvh_leaf_order(h, order.ctypes.data_as(C.c_void_p), k) == k
+        path = None
+        import tempfile
+        with tempfile.NamedTemporaryFile(suffix=".crscene") as fh:  # the export file holds every staging array (materials, ids)
+            assert lib.cr_scene_save(h, fh.name.encode()) == 0
+            blob = open(fh.name, "rb").read()
+        lib.cr_scene_destroy(h)
+        return nodes.tobytes(), order, blob
+
+    h = lib.cr_scene_create(-1)
+    for kind, d, mm, oo in runs:
+        assert add[kind](h, ptr(d), ptr(mm), ptr(oo), len(d)) >= 0
+    ref = finish(h)
+
+    def batched(h, rs):
+        n = len(rs)
+        kinds = (C.c_int32 * n)(*[r[0] for r in rs])
+        counts = (C.c_size_t * n)(*[len(r[1]) for r in rs])
+        pd = (C.c_void_p * n)(*[r[1].ctypes.data for r in rs])
+        pm = (C.c_void_p * n)(*[None if r[2] is None else r[2].ctypes.data for r in rs])
+        po = (C.c_void_p * n)(*[None if r[3] is None else r[3].ctypes.data for r in rs])
+        return lib.cr_scene_add_batches(h, n, kinds, pd, pm, po, counts)
+
+    h = lib.cr_scene_create(-1)
+    assert batched(h, runs[:5]) == 0           # first index of the call
+    assert batched(h, runs[5:]) == 2 + 4 * per
+    got = finish(h)
+    assert got[0] == ref[0] and np.array_equal(got[1], ref[1]) and got[2] == ref[2]
+
+    h = lib.cr_scene_create(-1)
+    assert batched(h, runs[:3]) == 0
+    bad = [list(r) for r in runs[3:8]]
+    bad[2][1] = bad[2][1].copy()
+    bad[2][1][17, 4] = np.nan
+    assert batched(h, bad) == abi.CR_ERR_INVALID and b"non-finite" in lib.cr_last_error()
+    neg = [(abi.CR_PRIM_SPHERE, np.array([[0.0, 0.0, 0.0, -1.0]]), None, None)]
+    assert batched(h, runs[3:4] + neg) == abi.CR_ERR_INVALID and b"negative radius" in lib.cr_last_error()
+    assert batched(h, [(7, runs[1][1], None, None)]) == abi.CR_ERR_INVALID
+    assert batched(h, runs[3:]) == 2 + 2 * per  # the rejected calls appended nothing
+    got = finish(h)
+    assert got[0] == ref[0] and np.array_equal(got[1], ref[1]) and got[2] == ref[2]
